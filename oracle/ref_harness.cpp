@@ -1,0 +1,426 @@
+// TEST INFRASTRUCTURE ONLY — flat C entry points over the REAL reference code.
+//
+// Compiled (oracle/Makefile) together with the reference's own, unmodified
+// translation units from /root/reference/app/src/main/cpp/svo into
+// oracle/_ref/libsvo_ref.so.  No reference source is copied into this repo:
+// this file only *calls* the reference's public operator surface
+// (vk::halfSample, FastDetector::detect, SparseImgAlign::run,
+// feature_alignment::align2D/align1D, Matcher::find*MatchDirect,
+// DepthFilter::updateSeed/computeTau/addFrame) so that tests can pin the C
+// restatement (svo_oracle.c) and the CUDA path against it.
+//
+// Pose layout: double[7] = {tx,ty,tz,qx,qy,qz,qw}.
+#include <svo/global.h>
+#include <svo/config.h>
+#include <svo/vision.h>
+#include <svo/patch_score.h>
+#include <svo/pinhole_camera.h>
+#include <svo/frame.h>
+#include <svo/feature.h>
+#include <svo/point.h>
+#include <svo/feature_detection.h>
+#include <svo/feature_alignment.h>
+#include <svo/sparse_img_align.h>
+#include <svo/matcher.h>
+#include <svo/depth_filter.h>
+#include <map>
+#include <cstring>
+
+using namespace svo;
+namespace svo { bool depthFromTriangulation(const SE3& T_search_ref, const Vector3d& f_ref, const Vector3d& f_cur, double& depth); }
+
+namespace {
+
+SE3 to_se3(const double* T) { return SE3(T[0], T[1], T[2], T[3], T[4], T[5], T[6]); }
+void from_se3(const SE3& T, double* o)
+{
+  o[0] = T.get_translation().x; o[1] = T.get_translation().y; o[2] = T.get_translation().z;
+  o[3] = T.get_rotation().x; o[4] = T.get_rotation().y; o[5] = T.get_rotation().z; o[6] = T.get_rotation().w;
+}
+
+cv::Mat aligned_copy(const uint8_t* img, int w, int h)
+{
+  cv::Mat m(h, w, CV_8UC1);
+  memcpy(m.data, img, (size_t)w * h);
+  return m;
+}
+
+// exposes the protected solver state of SparseImgAlign
+struct AlignProbe : public SparseImgAlign {
+  AlignProbe(int maxl, int minl, int n_iter) : SparseImgAlign(maxl, minl, n_iter, GaussNewton, false, false) {}
+  std::vector<int> evals;
+  virtual double computeResiduals(const SE3& m, bool lin, bool w = false)
+  {
+    if ((int)evals.size() <= level_) evals.resize(level_ + 1, 0);
+    evals[level_]++;
+    return SparseImgAlign::computeResiduals(m, lin, w);
+  }
+  const Matrix<double, 6, 6>& H() const { return H_; }
+  const Matrix<double, 6, 1>& Jres() const { return Jres_; }
+  const Matrix<double, 6, 1>& x() const { return x_; }
+  double chi2() const { return chi2_; }
+  size_t nmeas() const { return n_meas_; }
+  bool stopped() const { return stop_; }
+};
+
+vk::PinholeCamera* make_cam(const int* wh, const double* k) { return new vk::PinholeCamera(wh[0], wh[1], k[0], k[1], k[2], k[3]); }
+
+}  // namespace
+
+extern "C" {
+
+void svo_ref_config(int n_pyr_levels, int klt_max_level, int klt_min_level)
+{
+  Config::nPyrLevels() = n_pyr_levels;
+  Config::kltMaxLevel() = klt_max_level;
+  Config::kltMinLevel() = klt_min_level;
+}
+
+int svo_ref_has_sse2()
+{
+#ifdef __SSE2__
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// vk::halfSample on 64-byte aligned Mats (dispatch rule of the host build applies)
+void svo_ref_half_sample(const uint8_t* in, int w, int h, uint8_t* out)
+{
+  cv::Mat mi = aligned_copy(in, w, h);
+  cv::Mat mo(h / 2, w / 2, CV_8U);
+  vk::halfSample(mi, mo);
+  memcpy(out, mo.data, (size_t)(w / 2) * (h / 2));
+}
+
+// frame_utils::createImgPyramid; out = levels 1..n-1 concatenated
+void svo_ref_pyramid(const uint8_t* img, int w, int h, int n_levels, uint8_t* out)
+{
+  cv::Mat m0 = aligned_copy(img, w, h);
+  ImgPyr pyr;
+  frame_utils::createImgPyramid(m0, n_levels, pyr);
+  for (int l = 1; l < n_levels; ++l) {
+    memcpy(out, pyr[l].data, (size_t)pyr[l].cols * pyr[l].rows);
+    out += (size_t)pyr[l].cols * pyr[l].rows;
+  }
+}
+
+float svo_ref_shi_tomasi(const uint8_t* img, int w, int h, int u, int v)
+{
+  cv::Mat m(h, w, CV_8UC1, (void*)img);
+  return vk::shiTomasiScore(m, u, v);
+}
+
+int svo_ref_zmssd(const uint8_t* ref_patch, const uint8_t* cur, int stride)
+{
+  uint8_t patch[64] __attribute__((aligned(16)));
+  memcpy(patch, ref_patch, 64);
+  vk::patch_score::ZMSSD<4> score(patch);
+  return score.computeScore((uint8_t*)cur, stride);
+}
+
+// FastDetector::detect on a Frame built from img (pyramid depth from Config).
+// occ_px: n_occ pixel positions marked via setGridOccpuancy before detect.
+int svo_ref_fast_detect(const uint8_t* img, const int* wh, const double* k, int n_detect_levels, int cell, double thr,
+                        int n_occ, const double* occ_px, int cap, double* out_px, int* out_level)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  int n = 0;
+  {
+    cv::Mat m0 = aligned_copy(img, wh[0], wh[1]);
+    Frame frame(cam, m0, 0.0);
+    feature_detection::FastDetector det(wh[0], wh[1], cell, n_detect_levels);
+    for (int i = 0; i < n_occ; ++i) det.setGridOccpuancy(Vector2d(occ_px[2 * i], occ_px[2 * i + 1]));
+    Features fts;
+    det.detect(&frame, frame.img_pyr_, thr, fts);
+    for (auto it = fts.begin(); it != fts.end(); ++it, ++n) {
+      if (n < cap) { out_px[2 * n] = (*it)->px[0]; out_px[2 * n + 1] = (*it)->px[1]; out_level[n] = (*it)->level; }
+      delete *it;
+    }
+  }
+  delete cam;
+  return n;
+}
+
+int svo_ref_align2d(const uint8_t* img, int w, int h, const uint8_t* pwb, const uint8_t* patch, int n_iter, double* px)
+{
+  cv::Mat m(h, w, CV_8UC1, (void*)img);
+  uint8_t a[100] __attribute__((aligned(16))), b[64] __attribute__((aligned(16)));
+  memcpy(a, pwb, 100); memcpy(b, patch, 64);
+  Vector2d p(px[0], px[1]);
+  bool ok = feature_alignment::align2D(m, a, b, n_iter, p);
+  px[0] = p[0]; px[1] = p[1];
+  return ok ? 1 : 0;
+}
+
+int svo_ref_align1d(const uint8_t* img, int w, int h, const float* dir, const uint8_t* pwb, const uint8_t* patch,
+                    int n_iter, double* px, double* h_inv)
+{
+  cv::Mat m(h, w, CV_8UC1, (void*)img);
+  uint8_t a[100] __attribute__((aligned(16))), b[64] __attribute__((aligned(16)));
+  memcpy(a, pwb, 100); memcpy(b, patch, 64);
+  Vector2d p(px[0], px[1]);
+  bool ok = feature_alignment::align1D(m, Vector2f(dir[0], dir[1]), a, b, n_iter, p, *h_inv);
+  px[0] = p[0]; px[1] = p[1];
+  return ok ? 1 : 0;
+}
+
+void svo_ref_se3_mul(const double* A, const double* B, double* o) { from_se3(to_se3(A) * to_se3(B), o); }
+void svo_ref_se3_inverse(const double* A, double* o) { from_se3(to_se3(A).inverse(), o); }
+void svo_ref_se3_exp(const double* x, double* o) { from_se3(SE3::exp(x), o); }
+void svo_ref_se3_transform(const double* T, const double* p, double* o)
+{
+  Vector3d r = to_se3(T) * Vector3d(p[0], p[1], p[2]);
+  o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+}
+void svo_ref_cam2world(const int* wh, const double* k, double u, double v, double* f)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  Vector3d r = cam->cam2world(Vector2d(u, v));
+  f[0] = r[0]; f[1] = r[1]; f[2] = r[2];
+  delete cam;
+}
+
+// Builds the reference-side inputs of sparse alignment from level-0 pixels and
+// world points exactly as the reference does (Feature ctor: f = cam2world(px);
+// sparse_img_align.cpp:132-134: depth = |pos - ref_pos|, xyz_ref = f*depth),
+// runs SparseImgAlign::run, and returns both the result and the derived
+// per-feature arrays so the other implementations can be fed identical values.
+// pt_world: 3N, NaN in x => feature without point.
+int svo_ref_sparse_align(const uint8_t* ref_img, const uint8_t* cur_img, const int* wh, const double* k,
+                         int max_level, int min_level, int n_iter,
+                         const double* T_ref_w, const double* T_cur_w_init,
+                         int N, const double* px, const int* level, const double* pt_world,
+                         double* T_cur_w_out, double* T_cur_ref_init_out, double* T_cur_ref_out,
+                         double* H_out, double* Jres_out, double* x_out, double* chi2_out, int* n_meas_out,
+                         int* iters_out /*8*/, int* stop_out,
+                         double* f_out /*3N*/, double* xyz_ref_out /*3N*/)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  size_t ret = 0;
+  {
+    FramePtr ref(new Frame(cam, aligned_copy(ref_img, wh[0], wh[1]), 0.0));
+    FramePtr cur(new Frame(cam, aligned_copy(cur_img, wh[0], wh[1]), 1.0));
+    ref->T_f_w_ = to_se3(T_ref_w);
+    cur->T_f_w_ = to_se3(T_cur_w_init);
+    std::vector<Point*> pts;
+    const Vector3d ref_pos = ref->pos();
+    for (int i = 0; i < N; ++i) {
+      Feature* ftr = new Feature(ref.get(), Vector2d(px[2 * i], px[2 * i + 1]), level ? level[i] : 0);
+      if (!std::isnan(pt_world[3 * i])) {
+        Point* pt = new Point(Vector3d(pt_world[3 * i], pt_world[3 * i + 1], pt_world[3 * i + 2]));
+        ftr->point = pt; pts.push_back(pt);
+        const double depth((ftr->point->pos_ - ref_pos).norm());
+        const Vector3d xyz_ref(ftr->f * depth);
+        for (int c = 0; c < 3; ++c) xyz_ref_out[3 * i + c] = xyz_ref[c];
+      } else {
+        for (int c = 0; c < 3; ++c) xyz_ref_out[3 * i + c] = 0.0;
+      }
+      for (int c = 0; c < 3; ++c) f_out[3 * i + c] = ftr->f[c];
+      ref->addFeature(ftr);
+    }
+    from_se3(SE3(cur->T_f_w_ * ref->T_f_w_.inverse()), T_cur_ref_init_out);
+    AlignProbe al(max_level, min_level, n_iter);
+    ret = al.run(ref, cur);
+    from_se3(cur->T_f_w_, T_cur_w_out);
+    from_se3(SE3(cur->T_f_w_ * ref->T_f_w_.inverse()), T_cur_ref_out);  // informational (recomposed)
+    for (int a = 0; a < 6; ++a) {
+      for (int b = 0; b < 6; ++b) H_out[a * 6 + b] = al.H()(a, b);
+      Jres_out[a] = al.Jres()[a]; x_out[a] = al.x()[a];
+    }
+    *chi2_out = al.chi2(); *n_meas_out = (int)al.nmeas(); *stop_out = al.stopped() ? 1 : 0;
+    for (int l = 0; l < 8; ++l) iters_out[l] = l < (int)al.evals.size() ? al.evals[l] : 0;
+    for (auto p : pts) delete p;
+  }
+  delete cam;
+  return (int)ret;
+}
+
+// warp::getWarpMatrixAffine + getBestSearchLevel + warpAffine(halfpatch 5)
+int svo_ref_warp(const uint8_t* ref_img_level, int w, int h, const int* wh, const double* k,
+                 const double* px_ref, const double* f_ref, double depth_ref, const double* T_cur_ref,
+                 int level_ref, int max_search_level, double* A_out /*row-major*/, int* search_level_out, uint8_t* patch100)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  Matrix2d A;
+  warp::getWarpMatrixAffine(*cam, *cam, Vector2d(px_ref[0], px_ref[1]), Vector3d(f_ref[0], f_ref[1], f_ref[2]), depth_ref,
+                            to_se3(T_cur_ref), level_ref, A);
+  A_out[0] = A(0, 0); A_out[1] = A(0, 1); A_out[2] = A(1, 0); A_out[3] = A(1, 1);
+  const int sl = warp::getBestSearchLevel(A, max_search_level);
+  *search_level_out = sl;
+  cv::Mat m(h, w, CV_8UC1, (void*)ref_img_level);
+  warp::warpAffine(A, m, Vector2d(px_ref[0], px_ref[1]), level_ref, sl, 5, patch100);
+  delete cam;
+  return 1;
+}
+
+// Matcher::findMatchDirect with a Point that has exactly the given observations.
+// obs k: frame image index (into imgs), pose, px, level. The reference picks the close-view obs itself.
+int svo_ref_find_match_direct(int n_frames, const uint8_t* const* imgs, const double* T_f_w /*7 per frame*/,
+                              const int* wh, const double* k,
+                              const double* pt_world, int n_obs, const int* obs_frame, const double* obs_px, const int* obs_level,
+                              const int* obs_type, const double* obs_grad,
+                              int cur_frame, double* px_cur /*inout*/,
+                              int* chosen_obs, int* search_level, double* A_out, double* h_inv, uint8_t* pwb_out, uint8_t* patch_out)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  bool ok = false;
+  {
+    std::vector<FramePtr> frames;
+    for (int i = 0; i < n_frames; ++i) {
+      FramePtr f(new Frame(cam, aligned_copy(imgs[i], wh[0], wh[1]), (double)i));
+      f->T_f_w_ = to_se3(T_f_w + 7 * i);
+      frames.push_back(f);
+    }
+    Point pt(Vector3d(pt_world[0], pt_world[1], pt_world[2]));
+    std::vector<Feature*> fs;
+    for (int i = 0; i < n_obs; ++i) {
+      Feature* ftr = new Feature(frames[obs_frame[i]].get(), Vector2d(obs_px[2 * i], obs_px[2 * i + 1]), obs_level[i]);
+      ftr->type = obs_type[i] ? Feature::EDGELET : Feature::CORNER;
+      ftr->grad = Vector2d(obs_grad[2 * i], obs_grad[2 * i + 1]);
+      ftr->point = &pt;
+      pt.addFrameRef(ftr);
+      fs.push_back(ftr);
+    }
+    Matcher matcher;
+    matcher.ref_ftr_ = NULL; matcher.search_level_ = -1; matcher.h_inv_ = 0; matcher.A_cur_ref_.setZero();
+    memset(matcher.patch_with_border_, 0, 100); memset(matcher.patch_, 0, 64);
+    Vector2d p(px_cur[0], px_cur[1]);
+    ok = matcher.findMatchDirect(pt, *frames[cur_frame], p);
+    px_cur[0] = p[0]; px_cur[1] = p[1];
+    *chosen_obs = -1;
+    for (int i = 0; i < n_obs; ++i) if (fs[i] == matcher.ref_ftr_) *chosen_obs = i;
+    *search_level = matcher.search_level_;
+    A_out[0] = matcher.A_cur_ref_(0, 0); A_out[1] = matcher.A_cur_ref_(0, 1); A_out[2] = matcher.A_cur_ref_(1, 0); A_out[3] = matcher.A_cur_ref_(1, 1);
+    *h_inv = matcher.h_inv_;
+    memcpy(pwb_out, matcher.patch_with_border_, 100); memcpy(patch_out, matcher.patch_, 64);
+    pt.obs_.clear();
+    for (auto f : fs) delete f;
+  }
+  delete cam;
+  return ok ? 1 : 0;
+}
+
+// Matcher::findEpipolarMatchDirect
+int svo_ref_find_epipolar_match(const uint8_t* ref_img, const uint8_t* cur_img, const int* wh, const double* k,
+                                const double* T_ref_w, const double* T_cur_w,
+                                const double* px_ref, int level_ref, int type, const double* grad,
+                                double d_estimate, double d_min, double d_max,
+                                int align_1d, int align_max_iter, int max_epi_search_steps, int subpix_refinement,
+                                double* depth, double* px_cur, double* epi_length, int* search_level, int* reject,
+                                double* A_out, double* f_ref_out, uint8_t* pwb_out, uint8_t* patch_out)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  bool ok = false;
+  {
+    Frame ref(cam, aligned_copy(ref_img, wh[0], wh[1]), 0.0);
+    Frame cur(cam, aligned_copy(cur_img, wh[0], wh[1]), 1.0);
+    ref.T_f_w_ = to_se3(T_ref_w); cur.T_f_w_ = to_se3(T_cur_w);
+    Feature ftr(&ref, Vector2d(px_ref[0], px_ref[1]), level_ref);
+    ftr.type = type ? Feature::EDGELET : Feature::CORNER;
+    ftr.grad = Vector2d(grad[0], grad[1]);
+    for (int c = 0; c < 3; ++c) f_ref_out[c] = ftr.f[c];
+    Matcher m;
+    m.options_.align_1d = align_1d; m.options_.align_max_iter = align_max_iter;
+    m.options_.max_epi_search_steps = max_epi_search_steps; m.options_.subpix_refinement = subpix_refinement;
+    m.px_cur_.setZero(); m.epi_length_ = 0; m.search_level_ = -1; m.reject_ = false; m.A_cur_ref_.setZero();
+    memset(m.patch_with_border_, 0, 100); memset(m.patch_, 0, 64);
+    *depth = 0;
+    ok = m.findEpipolarMatchDirect(ref, cur, ftr, d_estimate, d_min, d_max, *depth);
+    px_cur[0] = m.px_cur_[0]; px_cur[1] = m.px_cur_[1];
+    *epi_length = m.epi_length_; *search_level = m.search_level_; *reject = m.reject_ ? 1 : 0;
+    A_out[0] = m.A_cur_ref_(0, 0); A_out[1] = m.A_cur_ref_(0, 1); A_out[2] = m.A_cur_ref_(1, 0); A_out[3] = m.A_cur_ref_(1, 1);
+    memcpy(pwb_out, m.patch_with_border_, 100); memcpy(patch_out, m.patch_, 64);
+  }
+  delete cam;
+  return ok ? 1 : 0;
+}
+
+int svo_ref_depth_from_triangulation(const double* T, const double* f_ref, const double* f_cur, double* depth)
+{
+  return svo::depthFromTriangulation(to_se3(T), Vector3d(f_ref[0], f_ref[1], f_ref[2]), Vector3d(f_cur[0], f_cur[1], f_cur[2]), *depth) ? 1 : 0;
+}
+
+void svo_ref_seed_init(float depth_mean, float depth_min, float* s /*a,b,mu,z_range,sigma2*/)
+{
+  Seed seed(NULL, depth_mean, depth_min);
+  s[0] = seed.a; s[1] = seed.b; s[2] = seed.mu; s[3] = seed.z_range; s[4] = seed.sigma2;
+}
+
+void svo_ref_update_seed(float x, float tau2, float* s)
+{
+  Seed seed(NULL, 1.0f, 1.0f);
+  seed.a = s[0]; seed.b = s[1]; seed.mu = s[2]; seed.z_range = s[3]; seed.sigma2 = s[4];
+  DepthFilter::updateSeed(x, tau2, &seed);
+  s[0] = seed.a; s[1] = seed.b; s[2] = seed.mu; s[3] = seed.z_range; s[4] = seed.sigma2;
+}
+
+double svo_ref_compute_tau(const double* T_ref_cur, const double* f, double z, double px_error_angle)
+{
+  return DepthFilter::computeTau(to_se3(T_ref_cur), Vector3d(f[0], f[1], f[2]), z, px_error_angle);
+}
+
+// DepthFilter::updateSeeds (through addFrame, synchronous mode) over S seeds that live on
+// n_ref reference frames.  status: 0 = seed still in list, 1 = converged (callback fired), 2 = erased otherwise.
+// For converged seeds the callback's sigma2 is returned in state[4] and the other fields are
+// recomputed by a second run with an infinite convergence threshold.
+int svo_ref_update_seeds(int n_ref, const uint8_t* const* ref_imgs, const double* T_ref_w,
+                         const uint8_t* cur_img, const double* T_cur_w, const int* wh, const double* k,
+                         int S, const int* seed_ref, const double* px, const int* level,
+                         float* state /*5 per seed, inout*/, int* status, double conv_thresh)
+{
+  vk::PinholeCamera* cam = make_cam(wh, k);
+  {
+    std::vector<FramePtr> refs;
+    for (int i = 0; i < n_ref; ++i) {
+      FramePtr f(new Frame(cam, aligned_copy(ref_imgs[i], wh[0], wh[1]), (double)i));
+      f->T_f_w_ = to_se3(T_ref_w + 7 * i);
+      refs.push_back(f);
+    }
+    FramePtr cur(new Frame(cam, aligned_copy(cur_img, wh[0], wh[1]), 100.0));
+    cur->T_f_w_ = to_se3(T_cur_w);
+    std::vector<float> in(state, state + 5 * S), out_inf(5 * S);
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<Feature*> fs(S);
+      std::map<Feature*, int> index;
+      std::vector<Point*> new_points;
+      std::vector<int> st(S, 2);
+      std::vector<float> conv_sigma2(S, 0.f);
+      DepthFilter df(feature_detection::DetectorPtr(), [&](Point* p, double sigma2) {
+        const int i = index[p->obs_.front()];
+        st[i] = 1; conv_sigma2[i] = (float)sigma2; new_points.push_back(p);
+      });
+      df.options_.seed_convergence_sigma2_thresh = pass == 0 ? conv_thresh : 1e300;
+      Seed::batch_counter = 0;
+      for (int i = 0; i < S; ++i) {
+        fs[i] = new Feature(refs[seed_ref[i]].get(), Vector2d(px[2 * i], px[2 * i + 1]), level[i]);
+        index[fs[i]] = i;
+        Seed seed(fs[i], 1.0f, 1.0f);
+        seed.a = in[5 * i]; seed.b = in[5 * i + 1]; seed.mu = in[5 * i + 2]; seed.z_range = in[5 * i + 3]; seed.sigma2 = in[5 * i + 4];
+        df.getSeeds().push_back(seed);
+      }
+      df.addFrame(cur);
+      std::vector<float>& dst = out_inf;
+      for (auto& s : df.getSeeds()) {
+        const int i = index[s.ftr];
+        if (pass == 0) st[i] = 0;
+        if (pass == 1) { dst[5 * i] = s.a; dst[5 * i + 1] = s.b; dst[5 * i + 2] = s.mu; dst[5 * i + 3] = s.z_range; dst[5 * i + 4] = s.sigma2; }
+      }
+      if (pass == 0) for (int i = 0; i < S; ++i) status[i] = st[i];
+      if (pass == 1) {
+        // seeds erased in the infinite-threshold pass (NaN) keep their input state
+        std::vector<char> seen(S, 0);
+        for (auto& s : df.getSeeds()) seen[index[s.ftr]] = 1;
+        for (int i = 0; i < S; ++i) if (!seen[i]) for (int c = 0; c < 5; ++c) dst[5 * i + c] = in[5 * i + c];
+      }
+      for (auto p : new_points) { p->obs_.clear(); delete p; }
+      for (auto f : fs) delete f;
+    }
+    memcpy(state, out_inf.data(), sizeof(float) * 5 * S);
+  }
+  delete cam;
+  return 0;
+}
+
+}  // extern "C"
