@@ -1,0 +1,343 @@
+"""ctypes bindings of libsvob200.so (include/svob200.h) — the thin Python layer tests and bench.py
+drive the CUDA path through.  There is no fallback of any kind: if the shared library is missing
+or no CUDA device is usable, importing / creating a context raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsvob200.so")
+MAX_LEVELS = 8
+MEM_HOST, MEM_DEVICE = 0, 1
+ROUND_TRUNC, ROUND_SSE2 = 0, 1
+SEED_BEHIND, SEED_NOT_IN_FRAME, SEED_NO_MATCH, SEED_UPDATED, SEED_CONVERGED, SEED_NAN_ERASED = 1, 2, 3, 4, 5, 6
+
+c_u8p = C.POINTER(C.c_uint8)
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int)
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double)]
+
+    @staticmethod
+    def make(w, h, fx, fy, cx, cy):
+        return Camera(int(w), int(h), float(fx), float(fy), float(cx), float(cy))
+
+
+class AlignOpts(C.Structure):
+    _fields_ = [("max_level", C.c_int), ("min_level", C.c_int), ("n_iter", C.c_int), ("eps", C.c_double)]
+
+
+class MatcherOpts(C.Structure):
+    _fields_ = [("align_1d", C.c_int), ("align_max_iter", C.c_int), ("max_epi_search_steps", C.c_int),
+                ("subpix_refinement", C.c_int), ("epi_search_edgelet_filtering", C.c_int),
+                ("epi_search_edgelet_max_angle", C.c_double), ("max_search_level", C.c_int)]
+
+
+# numpy dtypes with C layout (align=True reproduces the struct padding)
+corner_dt = np.dtype([("x", "i4"), ("y", "i4"), ("level", "i4"), ("score", "f4")], align=True)
+align_result_dt = np.dtype([("T_cur_ref", "f8", 7), ("H", "f8", 36), ("Jres", "f8", 6), ("x", "f8", 6), ("chi2", "f8"),
+                            ("n_meas", "i4"), ("iters", "i4", MAX_LEVELS), ("stop", "i4"), ("n_exact_chi2", "i4")], align=True)
+feature_ref_dt = np.dtype([("ref_frame_id", "i8"), ("ref_image", "i4"), ("cur_image", "i4"), ("level", "i4"), ("type", "i4"),
+                           ("px", "f8", 2), ("f", "f8", 3), ("grad", "f8", 2), ("T_cur_ref", "f8", 7)], align=True)
+match_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("px_cur", "f8", 2), ("A_cur_ref", "f8", 4),
+                            ("h_inv", "f8"), ("patch_with_border", "u1", 100), ("patch", "u1", 64)], align=True)
+epi_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("reject", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"),
+                          ("n_steps", "i4"), ("depth", "f8"), ("px_cur", "f8", 2), ("epi_length", "f8"), ("A_cur_ref", "f8", 4),
+                          ("h_inv", "f8"), ("patch_with_border", "u1", 100), ("patch", "u1", 64)], align=True)
+seed_dt = np.dtype([("a", "f4"), ("b", "f4"), ("mu", "f4"), ("z_range", "f4"), ("sigma2", "f4")], align=True)
+seed_obs_dt = np.dtype([("status", "i4"), ("search_level", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"), ("z", "f8"),
+                        ("px_cur", "f8", 2), ("epi_length", "f8")], align=True)
+
+_lib = None
+
+
+def load_library():
+    """Load libsvob200.so; raise loudly if it is not there (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libsvob200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or android_svo_b200/build.sh — there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.svob200_last_error.restype = C.c_char_p
+    L.svob200_ctx_stream.restype = C.c_void_p
+    L.svob200_ctx_launch_count.restype = C.c_longlong
+    V = C.c_void_p
+    L.svob200_ctx_create.argtypes = [C.c_int, C.POINTER(V)]
+    for name in ("svob200_ctx_destroy", "svob200_ctx_sync", "svob200_ctx_timer_start"):
+        getattr(L, name).argtypes = [V]
+    L.svob200_last_error.argtypes = [V]
+    L.svob200_ctx_stream.argtypes = [V]
+    L.svob200_ctx_launch_count.argtypes = [V]
+    L.svob200_ctx_timer_stop_ms.argtypes = [V, c_fp]
+    L.svob200_frame_create.argtypes = [V, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.svob200_frame_upload.argtypes = [V, C.c_int64, V, C.c_int, c_ip, C.c_int]
+    L.svob200_frame_bind.argtypes = [V, C.c_int64, V, C.c_int, c_ip]
+    L.svob200_frame_slot.argtypes = [V, C.c_int64]
+    L.svob200_frame_download.argtypes = [V, C.c_int64, C.c_int, C.c_int, V, C.c_int]
+    L.svob200_frame_release.argtypes = [V, C.c_int64]
+    L.svob200_frame_info.argtypes = [V, C.c_int64, c_ip, c_ip, c_ip, c_ip]
+    L.svob200_half_sample.argtypes = [V, V, C.c_int, C.c_int, C.c_int, V, C.c_int, C.c_int]
+    L.svob200_fast_detect.argtypes = [V, C.c_int64, C.c_int, C.c_int, C.c_double, V, V, V, C.c_int]
+    L.svob200_fast_corners.argtypes = [V, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V, V, V]
+    L.svob200_sparse_align.argtypes = [V, C.c_int64, C.c_int64, C.POINTER(Camera), C.c_int, V, V, V, V, V, C.POINTER(AlignOpts), V, C.c_int]
+    L.svob200_align_patches.argtypes = [V, C.c_int64, C.c_int, C.c_int, V, V, V, V, C.c_int, V, V, V, C.c_int]
+    L.svob200_matcher_opts_default.argtypes = [C.POINTER(MatcherOpts), C.c_int]
+    L.svob200_match_direct.argtypes = [V, C.c_int64, C.POINTER(Camera), C.c_int, V, V, V, C.POINTER(MatcherOpts), V, C.c_int]
+    L.svob200_epipolar_match.argtypes = [V, C.c_int64, C.POINTER(Camera), C.c_int, V, V, C.POINTER(MatcherOpts), V, C.c_int]
+    L.svob200_seeds_update.argtypes = [V, C.c_int64, C.POINTER(Camera), C.c_int, V, V, V, C.POINTER(MatcherOpts), C.c_double, V, V, C.c_int]
+    L.svob200_update_seed.argtypes = [V, C.c_int, V, V, V]
+    L.svob200_compute_tau.argtypes = [V, C.c_int, V, V, V, C.c_double, V]
+    L.svob200_dev_alloc.argtypes = [V, C.c_size_t, C.POINTER(V)]
+    L.svob200_dev_free.argtypes = [V, V]
+    L.svob200_dev_upload.argtypes = [V, V, V, C.c_size_t]
+    L.svob200_dev_download.argtypes = [V, V, V, C.c_size_t]
+    L.svob200_host_alloc_pinned.argtypes = [V, C.c_size_t, C.POINTER(V)]
+    L.svob200_host_free_pinned.argtypes = [V, V]
+    L.svob200_synth_render.argtypes = [V, V, C.c_int, C.c_double, C.c_double, C.POINTER(Camera), C.c_int, V, V]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "svob200_ctx_create", "svob200_ctx_destroy", "svob200_last_error", "svob200_ctx_sync", "svob200_ctx_stream",
+    "svob200_ctx_launch_count", "svob200_abi_sizes", "svob200_ctx_timer_start", "svob200_ctx_timer_stop_ms", "svob200_round_mode_x86",
+    "svob200_frame_create", "svob200_frame_upload", "svob200_frame_bind", "svob200_frame_slot", "svob200_frame_download",
+    "svob200_frame_release", "svob200_frame_info", "svob200_half_sample", "svob200_fast_detect", "svob200_fast_corners",
+    "svob200_sparse_align", "svob200_align_patches", "svob200_matcher_opts_default", "svob200_match_direct",
+    "svob200_epipolar_match", "svob200_seeds_update", "svob200_update_seed", "svob200_compute_tau", "svob200_dev_alloc",
+    "svob200_dev_free", "svob200_dev_upload", "svob200_dev_download", "svob200_host_alloc_pinned", "svob200_host_free_pinned",
+    "svob200_synth_render",
+]
+
+
+def _ptr(a):
+    """host numpy array, int device address, or None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+class Svob200Error(RuntimeError):
+    pass
+
+
+class Context:
+    """One CUDA stream + device-resident frame store on one GPU."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.svob200_ctx_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise Svob200Error("svob200_ctx_create(device=%d) failed with %d: no usable CUDA device — "
+                               "this library has no CPU fallback" % (device, rc))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.svob200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise Svob200Error("svob200 error %d: %s" % (rc, self.L.svob200_last_error(self.h).decode()))
+        return rc
+
+    # ---- context
+    def sync(self):
+        self._ck(self.L.svob200_ctx_sync(self.h))
+
+    def launch_count(self):
+        return int(self.L.svob200_ctx_launch_count(self.h))
+
+    def timer_start(self):
+        self._ck(self.L.svob200_ctx_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float(0)
+        self._ck(self.L.svob200_ctx_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- frames
+    def frame_create(self, fid, batch, w, h, n_levels):
+        self._ck(self.L.svob200_frame_create(self.h, fid, batch, w, h, n_levels))
+
+    def frame_upload(self, fid, gray, stride=None, round_modes=None, mem=MEM_HOST):
+        if mem == MEM_HOST:
+            gray = np.ascontiguousarray(gray, dtype=np.uint8)
+            stride = gray.shape[-1] if stride is None else stride
+        modes = np.ascontiguousarray(round_modes, dtype=np.int32) if round_modes is not None else None
+        self._ck(self.L.svob200_frame_upload(self.h, fid, _ptr(gray), int(stride), modes.ctypes.data_as(c_ip) if modes is not None else None, mem))
+
+    def frame_bind(self, fid, dev_ptr, stride, round_modes=None):
+        modes = np.ascontiguousarray(round_modes, dtype=np.int32) if round_modes is not None else None
+        self._ck(self.L.svob200_frame_bind(self.h, fid, _ptr(dev_ptr), int(stride), modes.ctypes.data_as(c_ip) if modes is not None else None))
+
+    def frame_slot(self, fid):
+        return self._ck(self.L.svob200_frame_slot(self.h, fid))
+
+    def frame_info(self, fid):
+        b, w, h, n = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.svob200_frame_info(self.h, fid, C.byref(b), C.byref(w), C.byref(h), C.byref(n)))
+        return b.value, w.value, h.value, n.value
+
+    def frame_download(self, fid, image, level):
+        _, w, h, _ = self.frame_info(fid)
+        lw, lh = w >> level, h >> level
+        out = np.zeros((lh, lw), np.uint8)
+        self._ck(self.L.svob200_frame_download(self.h, fid, image, level, _ptr(out), lw))
+        return out
+
+    def frame_release(self, fid):
+        self._ck(self.L.svob200_frame_release(self.h, fid))
+
+    def half_sample(self, img, mode):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        out = np.zeros((h // 2, w // 2), np.uint8)
+        self._ck(self.L.svob200_half_sample(self.h, _ptr(img), w, h, w, _ptr(out), w // 2, int(mode)))
+        return out
+
+    # ---- FAST
+    def fast_detect(self, fid, n_detect_levels, cell, thr, occupancy=None):
+        batch, w, h, _ = self.frame_info(fid)
+        n_cells = -(-w // cell) * -(-h // cell)
+        cells = np.zeros((batch, n_cells), corner_dt)
+        counts = np.zeros(batch, np.int32)
+        occ = np.ascontiguousarray(occupancy, dtype=np.uint8) if occupancy is not None else None
+        self._ck(self.L.svob200_fast_detect(self.h, fid, n_detect_levels, cell, float(thr), _ptr(occ), _ptr(cells), _ptr(counts), MEM_HOST))
+        return cells, counts
+
+    def fast_corners(self, fid, image, level, thr=10, nonmax=True):
+        _, w, h, _ = self.frame_info(fid)
+        cap = (w >> level) * (h >> level)
+        xs, ys, sc = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n = self._ck(self.L.svob200_fast_corners(self.h, fid, image, level, int(thr), int(nonmax), cap, _ptr(xs), _ptr(ys), _ptr(sc)))
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+    # ---- sparse align
+    def sparse_align(self, ref_fid, cur_fid, cam, offsets, px, xyz_ref, has_point, T_cur_ref, max_level, min_level, n_iter=30, eps=1e-6):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        batch = len(offsets) - 1
+        px = np.ascontiguousarray(px, dtype=np.float64)
+        xyz_ref = np.ascontiguousarray(xyz_ref, dtype=np.float64)
+        has_point = np.ascontiguousarray(has_point, dtype=np.uint8)
+        T = np.ascontiguousarray(T_cur_ref, dtype=np.float64)
+        opts = AlignOpts(max_level, min_level, n_iter, eps)
+        res = np.zeros(batch, align_result_dt)
+        self._ck(self.L.svob200_sparse_align(self.h, ref_fid, cur_fid, C.byref(cam), batch, _ptr(offsets), _ptr(px), _ptr(xyz_ref),
+                                             _ptr(has_point), _ptr(T), C.byref(opts), _ptr(res), MEM_HOST))
+        return res
+
+    # ---- feature alignment
+    def align_patches(self, fid, level, image, pwb, patch, n_iter, px, dirv=None):
+        image = np.ascontiguousarray(image, dtype=np.int32)
+        n = len(image)
+        pwb = np.ascontiguousarray(pwb, dtype=np.uint8)
+        patch = np.ascontiguousarray(patch, dtype=np.uint8)
+        px = np.ascontiguousarray(px, dtype=np.float64).copy()
+        conv = np.zeros(n, np.int32)
+        h_inv = np.zeros(n, np.float64)
+        d = np.ascontiguousarray(dirv, dtype=np.float32) if dirv is not None else None
+        self._ck(self.L.svob200_align_patches(self.h, fid, level, n, _ptr(image), _ptr(pwb), _ptr(patch), _ptr(d), n_iter,
+                                              _ptr(px), _ptr(conv), _ptr(h_inv), MEM_HOST))
+        return conv, px.reshape(n, 2), h_inv
+
+    # ---- matcher
+    def matcher_opts(self, n_pyr_levels, **kw):
+        o = MatcherOpts()
+        self.L.svob200_matcher_opts_default(C.byref(o), int(n_pyr_levels))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def match_direct(self, cur_fid, cam, ftrs, depth_ref, px_cur_in, opts):
+        n = len(ftrs)
+        res = np.zeros(n, match_result_dt)
+        d = np.ascontiguousarray(depth_ref, dtype=np.float64)
+        p = np.ascontiguousarray(px_cur_in, dtype=np.float64)
+        self._ck(self.L.svob200_match_direct(self.h, cur_fid, C.byref(cam), n, _ptr(ftrs), _ptr(d), _ptr(p), C.byref(opts), _ptr(res), MEM_HOST))
+        return res
+
+    def epipolar_match(self, cur_fid, cam, ftrs, d, opts):
+        n = len(ftrs)
+        res = np.zeros(n, epi_result_dt)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        self._ck(self.L.svob200_epipolar_match(self.h, cur_fid, C.byref(cam), n, _ptr(ftrs), _ptr(d), C.byref(opts), _ptr(res), MEM_HOST))
+        return res
+
+    # ---- depth filter
+    def seeds_update(self, cur_fid, cam, ftrs, T_ref_w, T_cur_w, opts, conv_thresh, seeds):
+        n = len(ftrs)
+        obs = np.zeros(n, seed_obs_dt)
+        seeds = np.ascontiguousarray(seeds, dtype=seed_dt).copy()
+        Tr = np.ascontiguousarray(T_ref_w, dtype=np.float64)
+        Tc = np.ascontiguousarray(T_cur_w, dtype=np.float64)
+        self._ck(self.L.svob200_seeds_update(self.h, cur_fid, C.byref(cam), n, _ptr(ftrs), _ptr(Tr), _ptr(Tc), C.byref(opts),
+                                             float(conv_thresh), _ptr(seeds), _ptr(obs), MEM_HOST))
+        return seeds, obs
+
+    def update_seed(self, x, tau2, seeds):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        tau2 = np.ascontiguousarray(tau2, dtype=np.float32)
+        seeds = np.ascontiguousarray(seeds, dtype=seed_dt).copy()
+        self._ck(self.L.svob200_update_seed(self.h, len(x), _ptr(x), _ptr(tau2), _ptr(seeds)))
+        return seeds
+
+    def compute_tau(self, T_ref_cur, f, z, ang):
+        T = np.ascontiguousarray(T_ref_cur, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.zeros(len(z))
+        self._ck(self.L.svob200_compute_tau(self.h, len(z), _ptr(T), _ptr(f), _ptr(z), float(ang), _ptr(out)))
+        return out
+
+    # ---- raw device helpers
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.svob200_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, dptr):
+        self._ck(self.L.svob200_dev_free(self.h, C.c_void_p(dptr)))
+
+    def dev_upload(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._ck(self.L.svob200_dev_upload(self.h, C.c_void_p(dptr), _ptr(arr), arr.nbytes))
+
+    def dev_download(self, arr, dptr):
+        self._ck(self.L.svob200_dev_download(self.h, _ptr(arr), C.c_void_p(dptr), arr.nbytes))
+
+    def synth_render(self, dev_tex, tex_size, ppm, plane_z, cam, poses, dev_out):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 7)
+        self._ck(self.L.svob200_synth_render(self.h, C.c_void_p(dev_tex), tex_size, float(ppm), float(plane_z), C.byref(cam),
+                                             len(poses), _ptr(poses), C.c_void_p(dev_out)))
+
+
+def abi_sizes():
+    """(C sizeof, numpy/ctypes sizeof) pairs for every struct crossing the ABI."""
+    L = load_library()
+    buf = (C.c_int * 16)()
+    n = L.svob200_abi_sizes(buf, 16)
+    mine = [C.sizeof(Camera), corner_dt.itemsize, C.sizeof(AlignOpts), align_result_dt.itemsize, C.sizeof(MatcherOpts),
+            feature_ref_dt.itemsize, match_result_dt.itemsize, epi_result_dt.itemsize, seed_dt.itemsize, seed_obs_dt.itemsize]
+    return list(buf[:n]), mine
+
+
+def make_feature_refs(n):
+    return np.zeros(n, feature_ref_dt)

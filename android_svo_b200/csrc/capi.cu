@@ -1,0 +1,642 @@
+// capi.cu — the C ABI of libsvob200 (include/svob200.h): context, device-resident frame store,
+// host<->device staging and the entry points that launch the kernels.  No compute happens on the
+// host here; a missing / unusable GPU makes every call fail with SVOB200_ERR_CUDA.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <mutex>
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kMaxFrames = 4096;
+
+struct FrameRec {
+  DevFrame f;
+  uint8_t* base = nullptr;       // owned allocation (all levels)
+  uint8_t* own_l0 = nullptr;     // owned level-0 storage (f.lvl[0] may alias caller memory after bind)
+  int own_pitch0 = 0;
+  int slot = -1;
+};
+
+struct GrowBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max(n, (size_t)1 << 16);
+    want = (want + (want >> 2) + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct svob200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  std::unordered_map<int64_t, FrameRec> frames;
+  std::vector<int> free_slots;
+  DevFrame* d_table = nullptr;
+  // staging arenas (HOST mem mode)
+  uint8_t* h_stage = nullptr; size_t h_cap = 0;
+  GrowBuf d_stage, d_scratch, d_scratch2;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+};
+
+namespace {
+
+int fail(svob200_ctx* c, int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+DevCam to_cam(const svob200_camera* c) { DevCam d; d.width = c->width; d.height = c->height; d.fx = c->fx; d.fy = c->fy; d.cx = c->cx; d.cy = c->cy; return d; }
+
+FrameRec* find_frame(svob200_ctx* ctx, int64_t id)
+{
+  auto it = ctx->frames.find(id);
+  return it == ctx->frames.end() ? nullptr : &it->second;
+}
+
+int ensure_host_stage(svob200_ctx* ctx, size_t n)
+{
+  if (n <= ctx->h_cap) return 0;
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr; ctx->h_cap = 0;
+  size_t want = std::max(n, (size_t)1 << 16);
+  want = (want + (want >> 2) + 255) & ~(size_t)255;
+  CU(cudaMallocHost((void**)&ctx->h_stage, want));
+  ctx->h_cap = want;
+  return 0;
+}
+
+// Three-region staging plan: IN | INOUT | OUT.  Device copies cover [0, end(INOUT)) on the way in
+// and [begin(INOUT), end) on the way out — one cudaMemcpyAsync each way per call.
+struct Stage {
+  svob200_ctx* ctx; int mem;
+  struct Item { const void* src; void* dst; size_t bytes, off; int kind; };   // kind 0 in, 1 inout, 2 out
+  std::vector<Item> items;
+  size_t total = 0, in_end = 0, io_begin = 0;
+  Stage(svob200_ctx* c, int m) : ctx(c), mem(m) {}
+  // returns an index; resolve() gives the device pointer
+  int add(const void* src, void* dst, size_t bytes, int kind) { items.push_back({src, dst, bytes, 0, kind}); return (int)items.size() - 1; }
+  int layout()
+  {
+    if (mem == SVOB200_MEM_DEVICE) return 0;
+    size_t off = 0;
+    for (int kind = 0; kind < 3; ++kind) {
+      if (kind == 1) io_begin = off;
+      for (auto& it : items) if (it.kind == kind) { it.off = off; off += (it.bytes + 255) & ~(size_t)255; }
+      if (kind == 1) in_end = off;
+    }
+    total = off;
+    if (int r = ensure_host_stage(ctx, total)) return r;
+    if (ctx->d_stage.ensure(total) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "device staging alloc of %zu bytes failed", total);
+    return 0;
+  }
+  template <class T> T* dev(int idx)
+  {
+    Item& it = items[idx];
+    if (mem == SVOB200_MEM_DEVICE) return (T*)(it.kind == 2 ? it.dst : (it.kind == 1 ? it.dst : const_cast<void*>(it.src)));
+    return reinterpret_cast<T*>(static_cast<uint8_t*>(ctx->d_stage.p) + it.off);
+  }
+  template <class T> T* host(int idx) { return reinterpret_cast<T*>(ctx->h_stage + items[idx].off); }   // staged host copy (HOST mode)
+  int upload()
+  {
+    if (mem == SVOB200_MEM_DEVICE) return 0;
+    for (auto& it : items) if (it.kind <= 1 && it.src && it.bytes) memcpy(ctx->h_stage + it.off, it.src, it.bytes);
+    return 0;
+  }
+  int push()
+  {
+    if (mem == SVOB200_MEM_DEVICE || in_end == 0) return 0;
+    CU(cudaMemcpyAsync(ctx->d_stage.p, ctx->h_stage, in_end, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+  }
+  int download()
+  {
+    if (mem == SVOB200_MEM_DEVICE) return 0;
+    if (total > io_begin)
+      CU(cudaMemcpyAsync(ctx->h_stage + io_begin, static_cast<uint8_t*>(ctx->d_stage.p) + io_begin, total - io_begin, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& it : items) if (it.kind >= 1 && it.dst && it.bytes) memcpy(it.dst, ctx->h_stage + it.off, it.bytes);
+    return 0;
+  }
+};
+
+// rewrite ref_frame_id -> frame-table slot in the staged copy of the feature records
+int resolve_slots(svob200_ctx* ctx, svob200_feature_ref* staged, int n)
+{
+  int64_t last_id = 0; int last_slot = -1; bool have = false;
+  for (int i = 0; i < n; ++i) {
+    const int64_t id = staged[i].ref_frame_id;
+    if (!have || id != last_id) {
+      FrameRec* r = find_frame(ctx, id);
+      if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "reference frame %lld of item %d is not resident", (long long)id, i);
+      last_id = id; last_slot = r->slot; have = true;
+    }
+    staged[i].ref_frame_id = last_slot;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svob200_ctx_create(int device, svob200_ctx** out)
+{
+  if (!out) return SVOB200_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SVOB200_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SVOB200_ERR_CUDA;
+  svob200_ctx* ctx = new svob200_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SVOB200_ERR_CUDA; }
+  if (cudaMalloc((void**)&ctx->d_table, sizeof(DevFrame) * kMaxFrames) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return SVOB200_ERR_CUDA; }
+  for (int i = kMaxFrames - 1; i >= 0; --i) ctx->free_slots.push_back(i);
+  *out = ctx;
+  return SVOB200_OK;
+}
+
+void svob200_ctx_destroy(svob200_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->frames) if (kv.second.base) cudaFree(kv.second.base);
+  if (ctx->d_table) cudaFree(ctx->d_table);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->d_stage.release(); ctx->d_scratch.release(); ctx->d_scratch2.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* svob200_last_error(const svob200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device?)"; }
+int svob200_ctx_sync(svob200_ctx* ctx) { if (!ctx) return SVOB200_ERR_ARG; CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+void* svob200_ctx_stream(svob200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+long long svob200_ctx_launch_count(const svob200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int svob200_ctx_timer_start(svob200_ctx* ctx)
+{
+  if (!ctx) return SVOB200_ERR_ARG;
+  if (!ctx->ev0) { CU(cudaEventCreate(&ctx->ev0)); CU(cudaEventCreate(&ctx->ev1)); }
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+int svob200_ctx_timer_stop_ms(svob200_ctx* ctx, float* ms)
+{
+  if (!ctx || !ms || !ctx->ev0) return SVOB200_ERR_ARG;
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev1));
+  CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+// sizeof() of every struct that crosses the ABI, in header order, so bindings can verify their layout
+int svob200_abi_sizes(int* sizes, int cap)
+{
+  const int v[] = {(int)sizeof(svob200_camera), (int)sizeof(svob200_corner), (int)sizeof(svob200_align_opts),
+                   (int)sizeof(svob200_align_result), (int)sizeof(svob200_matcher_opts), (int)sizeof(svob200_feature_ref),
+                   (int)sizeof(svob200_match_result), (int)sizeof(svob200_epi_result), (int)sizeof(svob200_seed),
+                   (int)sizeof(svob200_seed_obs)};
+  const int n = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < cap; ++i) sizes[i] = v[i];
+  return n;
+}
+
+int svob200_round_mode_x86(int in_cols) { return (in_cols % 16) == 0 ? SVOB200_ROUND_SSE2 : SVOB200_ROUND_TRUNC; }
+
+// ------------------------------------------------------------------ frames
+int svob200_frame_create(svob200_ctx* ctx, int64_t frame_id, int batch, int w, int h, int n_levels)
+{
+  if (!ctx || batch <= 0 || w <= 0 || h <= 0 || n_levels < 1 || n_levels > SVOB200_MAX_LEVELS) return fail(ctx, SVOB200_ERR_ARG, "frame_create: bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (find_frame(ctx, frame_id)) return fail(ctx, SVOB200_ERR_ARG, "frame %lld already exists", (long long)frame_id);
+  if (ctx->free_slots.empty()) return fail(ctx, SVOB200_ERR_NOMEM, "frame table full (%d)", kMaxFrames);
+  FrameRec r;
+  memset(&r.f, 0, sizeof(r.f));
+  r.f.n_levels = n_levels; r.f.batch = batch;
+  size_t total = 0;
+  size_t off[SVOB200_MAX_LEVELS];
+  int lw = w, lh = h;
+  for (int l = 0; l < n_levels; ++l) {
+    if (lw <= 0 || lh <= 0) return fail(ctx, SVOB200_ERR_ARG, "frame_create: level %d is empty", l);
+    r.f.w[l] = lw; r.f.h[l] = lh; r.f.pitch[l] = align_up_i(lw, 64);
+    r.f.img_stride[l] = (unsigned long long)r.f.pitch[l] * lh;
+    off[l] = total;
+    total += (size_t)r.f.img_stride[l] * batch;
+    total = (total + 255) & ~(size_t)255;
+    lw /= 2; lh /= 2;
+  }
+  total += 256;   // slack so word-granular reads at the very end stay inside the allocation
+  if (cudaMalloc((void**)&r.base, total) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SVOB200_ERR_NOMEM, "frame_create: cudaMalloc(%zu) failed", total); }
+  CU(cudaMemsetAsync(r.base, 0, total, ctx->stream));
+  for (int l = 0; l < n_levels; ++l) r.f.lvl[l] = r.base + off[l];
+  r.own_l0 = r.f.lvl[0]; r.own_pitch0 = r.f.pitch[0];
+  r.slot = ctx->free_slots.back(); ctx->free_slots.pop_back();
+  CU(cudaMemcpyAsync(ctx->d_table + r.slot, &r.f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));      // r.f is a stack object
+  ctx->frames[frame_id] = r;
+  return SVOB200_OK;
+}
+
+static int build_levels(svob200_ctx* ctx, FrameRec* r, const int* round_modes)
+{
+  int modes[SVOB200_MAX_LEVELS];
+  for (int l = 0; l + 1 < r->f.n_levels; ++l) modes[l] = round_modes ? round_modes[l] : svob200_round_mode_x86(r->f.w[l]);
+  if (launch_pyramid(r->f, modes, ctx->stream, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "pyramid launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+int svob200_frame_upload(svob200_ctx* ctx, int64_t frame_id, const uint8_t* gray, int stride, const int* round_modes, int mem)
+{
+  if (!ctx || !gray) return fail(ctx, SVOB200_ERR_ARG, "frame_upload: null argument");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (stride < r->f.w[0]) return fail(ctx, SVOB200_ERR_ARG, "frame_upload: stride < width");
+  if (r->f.lvl[0] != r->own_l0) {                       // undo a previous bind
+    r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
+    CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemcpy2DAsync(r->f.lvl[0], r->f.pitch[0], gray, stride, r->f.w[0], (size_t)r->f.h[0] * r->f.batch,
+                       mem == SVOB200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  if (int e = build_levels(ctx, r, round_modes)) return e;
+  if (mem == SVOB200_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+// Level 0 aliases the caller's device buffer (the reference's level 0 aliases the caller's cv::Mat,
+// frame.cpp:189): no copy at all, the pyramid kernel reads the frame where it already is in HBM.
+int svob200_frame_bind(svob200_ctx* ctx, int64_t frame_id, const uint8_t* dev_gray, int stride, const int* round_modes)
+{
+  if (!ctx || !dev_gray) return fail(ctx, SVOB200_ERR_ARG, "frame_bind: null argument");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (stride < r->f.w[0] || (stride & 15) || (reinterpret_cast<uintptr_t>(dev_gray) & 15))
+    return fail(ctx, SVOB200_ERR_ARG, "frame_bind: buffer and stride must be 16-byte aligned and stride >= width");
+  r->f.lvl[0] = const_cast<uint8_t*>(dev_gray); r->f.pitch[0] = stride; r->f.img_stride[0] = (unsigned long long)stride * r->f.h[0];
+  CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
+  return build_levels(ctx, r, round_modes);
+}
+
+int svob200_frame_download(svob200_ctx* ctx, int64_t frame_id, int image, int level, uint8_t* out, int out_stride)
+{
+  if (!ctx || !out) return fail(ctx, SVOB200_ERR_ARG, "frame_download: null argument");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (level < 0 || level >= r->f.n_levels || image < 0 || image >= r->f.batch || out_stride < r->f.w[level]) return fail(ctx, SVOB200_ERR_ARG, "frame_download: bad level/image/stride");
+  CU(cudaMemcpy2DAsync(out, out_stride, r->f.lvl[level] + (size_t)image * r->f.img_stride[level], r->f.pitch[level], r->f.w[level], r->f.h[level],
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+int svob200_frame_release(svob200_ctx* ctx, int64_t frame_id)
+{
+  if (!ctx) return SVOB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->frames.find(frame_id);
+  if (it == ctx->frames.end()) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(it->second.base);
+  ctx->free_slots.push_back(it->second.slot);
+  ctx->frames.erase(it);
+  return SVOB200_OK;
+}
+
+int svob200_frame_info(svob200_ctx* ctx, int64_t frame_id, int* batch, int* w, int* h, int* n_levels)
+{
+  FrameRec* r = ctx ? find_frame(ctx, frame_id) : nullptr;
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (batch) *batch = r->f.batch;
+  if (w) *w = r->f.w[0];
+  if (h) *h = r->f.h[0];
+  if (n_levels) *n_levels = r->f.n_levels;
+  return SVOB200_OK;
+}
+
+int svob200_frame_slot(svob200_ctx* ctx, int64_t frame_id)
+{
+  FrameRec* r = ctx ? find_frame(ctx, frame_id) : nullptr;
+  return r ? r->slot : fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+}
+
+int svob200_half_sample(svob200_ctx* ctx, const uint8_t* in, int w, int h, int in_stride, uint8_t* out, int out_stride, int round_mode)
+{
+  if (!ctx || !in || !out || w < 2 || h < 2 || in_stride < w || out_stride < w / 2) return fail(ctx, SVOB200_ERR_ARG, "half_sample: bad arguments");
+  const int ip = align_up_i(w, 64), op = align_up_i(w / 2, 64);
+  const size_t in_b = (size_t)ip * h, out_b = (size_t)op * (h / 2);
+  if (ctx->d_scratch.ensure(in_b + out_b + 512) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "half_sample: scratch alloc failed");
+  uint8_t* d_in = static_cast<uint8_t*>(ctx->d_scratch.p);
+  uint8_t* d_out = d_in + ((in_b + 255) & ~(size_t)255);
+  CU(cudaMemcpy2DAsync(d_in, ip, in, in_stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  if (launch_half_sample_single(d_in, ip, w, h, d_out, op, round_mode, ctx->stream, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "half_sample launch failed");
+  CU(cudaMemcpy2DAsync(out, out_stride, d_out, op, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+// ------------------------------------------------------------------ FAST
+int svob200_fast_detect(svob200_ctx* ctx, int64_t frame_id, int n_detect_levels, int cell_size, double thr,
+                        const uint8_t* occupancy, svob200_corner* cells_out, int* n_features_out, int mem)
+{
+  if (!ctx || !cells_out || cell_size <= 0) return fail(ctx, SVOB200_ERR_ARG, "fast_detect: bad arguments");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (n_detect_levels < 1 || n_detect_levels > r->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "fast_detect: n_detect_levels out of range");
+  if (r->f.w[0] >= 16384 || r->f.h[0] >= 16384) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "fast_detect: image larger than 16383");
+  const int gc = (r->f.w[0] + cell_size - 1) / cell_size, gr = (r->f.h[0] + cell_size - 1) / cell_size;
+  const size_t n_cells = (size_t)gc * gr, total = n_cells * r->f.batch;
+  Stage st(ctx, mem);
+  const int i_occ = occupancy ? st.add(occupancy, nullptr, total, 0) : -1;
+  const int i_cells = st.add(nullptr, cells_out, total * sizeof(svob200_corner), 2);
+  const int i_cnt = st.add(nullptr, n_features_out, sizeof(int) * r->f.batch, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (ctx->d_scratch.ensure(total * 8 + sizeof(int) * r->f.batch + 256) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "fast_detect: scratch alloc failed");
+  unsigned long long* d_keys = static_cast<unsigned long long*>(ctx->d_scratch.p);
+  int* d_cnt = (mem == SVOB200_MEM_DEVICE && !n_features_out) ? reinterpret_cast<int*>(d_keys + total) : st.dev<int>(i_cnt);
+  if (launch_fast_detect(r->f, n_detect_levels, cell_size, gc, gr, thr, occupancy ? st.dev<uint8_t>(i_occ) : nullptr, d_keys,
+                         st.dev<svob200_corner>(i_cells), d_cnt, ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "fast_detect launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+int svob200_fast_corners(svob200_ctx* ctx, int64_t frame_id, int image, int level, int threshold, int nonmax, int cap,
+                         int* xs, int* ys, int* scores)
+{
+  if (!ctx) return SVOB200_ERR_ARG;
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (level < 0 || level >= r->f.n_levels || image < 0 || image >= r->f.batch) return fail(ctx, SVOB200_ERR_ARG, "fast_corners: bad level/image");
+  const int w = r->f.w[level], h = r->f.h[level];
+  const size_t n = (size_t)w * h;
+  if (ctx->d_scratch.ensure(n + 256) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "fast_corners: scratch alloc failed");
+  uint8_t* d_sc = static_cast<uint8_t*>(ctx->d_scratch.p);
+  threshold = std::min(std::max(threshold, 0), 255);
+  if (launch_fast_raw(r->f, image, level, threshold, nonmax, d_sc, ctx->stream, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "fast_corners launch failed");
+  std::vector<uint8_t> sc(n);
+  CU(cudaMemcpyAsync(sc.data(), d_sc, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int cnt = 0;   // row-major compaction of the device score map (output formatting only)
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const int s = sc[(size_t)y * w + x];
+      if (!s) continue;
+      if (cnt < cap) { if (xs) xs[cnt] = x; if (ys) ys[cnt] = y; if (scores) scores[cnt] = s; }
+      ++cnt;
+    }
+  return cnt;
+}
+
+// ------------------------------------------------------------------ sparse alignment
+int svob200_sparse_align(svob200_ctx* ctx, int64_t ref_frame_id, int64_t cur_frame_id, const svob200_camera* cam, int batch,
+                         const int* ftr_offsets, const double* px, const double* xyz_ref, const uint8_t* has_point,
+                         const double* T_cur_ref, const svob200_align_opts* opts, svob200_align_result* results, int mem)
+{
+  if (!ctx || !cam || !ftr_offsets || !opts || !results || batch <= 0) return fail(ctx, SVOB200_ERR_ARG, "sparse_align: bad arguments");
+  FrameRec* ref = find_frame(ctx, ref_frame_id);
+  FrameRec* cur = find_frame(ctx, cur_frame_id);
+  if (!ref || !cur) return fail(ctx, SVOB200_ERR_NOFRAME, "sparse_align: frame not resident");
+  if (batch > ref->f.batch || batch > cur->f.batch) return fail(ctx, SVOB200_ERR_ARG, "sparse_align: batch exceeds the frames' batch");
+  if (opts->max_level >= ref->f.n_levels || opts->max_level >= cur->f.n_levels || opts->min_level < 0 || opts->min_level > opts->max_level)
+    return fail(ctx, SVOB200_ERR_ARG, "sparse_align: level range [%d,%d] outside the pyramid", opts->min_level, opts->max_level);
+  int total = 0, max_per = 0;
+  if (mem == SVOB200_MEM_HOST) {
+    total = ftr_offsets[batch];
+    for (int b = 0; b < batch; ++b) max_per = std::max(max_per, ftr_offsets[b + 1] - ftr_offsets[b]);
+  } else {
+    // device-resident offsets: one small read-back of the final offset (the scratch size depends on it)
+    CU(cudaMemcpyAsync(&total, ftr_offsets + batch, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    max_per = total;
+  }
+  Stage st(ctx, mem);
+  const int i_off = st.add(ftr_offsets, nullptr, sizeof(int) * (batch + 1), 0);
+  const int i_px = st.add(px, nullptr, sizeof(double) * 2 * total, 0);
+  const int i_xyz = st.add(xyz_ref, nullptr, sizeof(double) * 3 * total, 0);
+  const int i_hp = st.add(has_point, nullptr, (size_t)total, 0);
+  const int i_T = st.add(T_cur_ref, nullptr, sizeof(double) * 7 * batch, 0);
+  const int i_res = st.add(nullptr, results, sizeof(svob200_align_result) * batch, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (ctx->d_scratch.ensure(sparse_align_scratch_bytes(total)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "sparse_align: scratch alloc failed");
+  if (launch_sparse_align(ref->f, cur->f, to_cam(cam), batch, total, max_per, st.dev<int>(i_off), st.dev<double>(i_px), st.dev<double>(i_xyz),
+                          st.dev<uint8_t>(i_hp), st.dev<double>(i_T), *opts, st.dev<svob200_align_result>(i_res), ctx->d_scratch.p,
+                          ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "sparse_align launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+// ------------------------------------------------------------------ feature alignment
+int svob200_align_patches(svob200_ctx* ctx, int64_t frame_id, int level, int n, const int* image, const uint8_t* pwb,
+                          const uint8_t* patch, const float* dir, int n_iter, double* px, int* converged, double* h_inv, int mem)
+{
+  if (!ctx || n < 0 || !image || !pwb || !patch || !px || !converged) return fail(ctx, SVOB200_ERR_ARG, "align_patches: bad arguments");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (level < 0 || level >= r->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "align_patches: bad level");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_img = st.add(image, nullptr, sizeof(int) * n, 0);
+  const int i_pwb = st.add(pwb, nullptr, (size_t)100 * n, 0);
+  const int i_pat = st.add(patch, nullptr, (size_t)64 * n, 0);
+  const int i_dir = dir ? st.add(dir, nullptr, sizeof(float) * 2 * n, 0) : -1;
+  const int i_px = st.add(px, px, sizeof(double) * 2 * n, 1);
+  const int i_cv = st.add(nullptr, converged, sizeof(int) * n, 2);
+  const int i_hi = h_inv ? st.add(nullptr, h_inv, sizeof(double) * n, 2) : -1;
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_align_patches(r->f, level, n, st.dev<int>(i_img), st.dev<uint8_t>(i_pwb), st.dev<uint8_t>(i_pat), dir ? st.dev<float>(i_dir) : nullptr,
+                           n_iter, st.dev<double>(i_px), st.dev<int>(i_cv), h_inv ? st.dev<double>(i_hi) : nullptr, ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "align_patches launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+// ------------------------------------------------------------------ matcher
+void svob200_matcher_opts_default(svob200_matcher_opts* o, int n_pyr_levels)
+{
+  o->align_1d = 0; o->align_max_iter = 10; o->max_epi_search_steps = 1000; o->subpix_refinement = 1;
+  o->epi_search_edgelet_filtering = 1; o->epi_search_edgelet_max_angle = 0.7; o->max_search_level = n_pyr_levels - 1;
+}
+
+int svob200_match_direct(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int n, const svob200_feature_ref* ftrs,
+                         const double* depth_ref, const double* px_cur_in, const svob200_matcher_opts* opts,
+                         svob200_match_result* results, int mem)
+{
+  if (!ctx || !cam || n < 0 || !ftrs || !depth_ref || !px_cur_in || !opts || !results) return fail(ctx, SVOB200_ERR_ARG, "match_direct: bad arguments");
+  FrameRec* cur = find_frame(ctx, cur_frame_id);
+  if (!cur) return fail(ctx, SVOB200_ERR_NOFRAME, "match_direct: current frame not resident");
+  if (opts->max_search_level >= cur->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "match_direct: max_search_level outside the pyramid");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_f = st.add(ftrs, nullptr, sizeof(svob200_feature_ref) * n, 0);
+  const int i_d = st.add(depth_ref, nullptr, sizeof(double) * n, 0);
+  const int i_p = st.add(px_cur_in, nullptr, sizeof(double) * 2 * n, 0);
+  const int i_r = st.add(nullptr, results, sizeof(svob200_match_result) * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
+  if (int e = st.push()) return e;
+  if (launch_match_direct(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_d),
+                          st.dev<double>(i_p), *opts, st.dev<svob200_match_result>(i_r), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "match_direct launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+int svob200_epipolar_match(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int n, const svob200_feature_ref* ftrs,
+                           const double* d, const svob200_matcher_opts* opts, svob200_epi_result* results, int mem)
+{
+  if (!ctx || !cam || n < 0 || !ftrs || !d || !opts || !results) return fail(ctx, SVOB200_ERR_ARG, "epipolar_match: bad arguments");
+  FrameRec* cur = find_frame(ctx, cur_frame_id);
+  if (!cur) return fail(ctx, SVOB200_ERR_NOFRAME, "epipolar_match: current frame not resident");
+  if (opts->max_search_level >= cur->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "epipolar_match: max_search_level outside the pyramid");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_f = st.add(ftrs, nullptr, sizeof(svob200_feature_ref) * n, 0);
+  const int i_d = st.add(d, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_r = st.add(nullptr, results, sizeof(svob200_epi_result) * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
+  if (int e = st.push()) return e;
+  if (launch_epipolar(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_d), *opts,
+                      st.dev<svob200_epi_result>(i_r), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "epipolar launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+// ------------------------------------------------------------------ depth filter
+int svob200_seeds_update(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int n, const svob200_feature_ref* ftrs,
+                         const double* T_ref_w, const double* T_cur_w, const svob200_matcher_opts* opts, double conv_thresh,
+                         svob200_seed* seeds, svob200_seed_obs* obs, int mem)
+{
+  if (!ctx || !cam || n < 0 || !ftrs || !T_ref_w || !T_cur_w || !opts || !seeds || !obs) return fail(ctx, SVOB200_ERR_ARG, "seeds_update: bad arguments");
+  FrameRec* cur = find_frame(ctx, cur_frame_id);
+  if (!cur) return fail(ctx, SVOB200_ERR_NOFRAME, "seeds_update: current frame not resident");
+  if (opts->max_search_level >= cur->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "seeds_update: max_search_level outside the pyramid");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_f = st.add(ftrs, nullptr, sizeof(svob200_feature_ref) * n, 0);
+  const int i_tr = st.add(T_ref_w, nullptr, sizeof(double) * 7 * n, 0);
+  const int i_tc = st.add(T_cur_w, nullptr, sizeof(double) * 7 * cur->f.batch, 0);
+  const int i_s = st.add(seeds, seeds, sizeof(svob200_seed) * n, 1);
+  const int i_o = st.add(nullptr, obs, sizeof(svob200_seed_obs) * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
+  if (int e = st.push()) return e;
+  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_tr),
+                          st.dev<double>(i_tc), *opts, conv_thresh, st.dev<svob200_seed>(i_s), st.dev<svob200_seed_obs>(i_o),
+                          ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "seeds_update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+int svob200_update_seed(svob200_ctx* ctx, int n, const float* x, const float* tau2, svob200_seed* seeds)
+{
+  if (!ctx || n < 0 || !x || !tau2 || !seeds) return fail(ctx, SVOB200_ERR_ARG, "update_seed: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, SVOB200_MEM_HOST);
+  const int i_x = st.add(x, nullptr, sizeof(float) * n, 0);
+  const int i_t = st.add(tau2, nullptr, sizeof(float) * n, 0);
+  const int i_s = st.add(seeds, seeds, sizeof(svob200_seed) * n, 1);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_update_seed(n, st.dev<float>(i_x), st.dev<float>(i_t), st.dev<svob200_seed>(i_s), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "update_seed launch failed");
+  return st.download();
+}
+
+int svob200_compute_tau(svob200_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z, double px_error_angle, double* tau_out)
+{
+  if (!ctx || n < 0 || !T_ref_cur || !f || !z || !tau_out) return fail(ctx, SVOB200_ERR_ARG, "compute_tau: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, SVOB200_MEM_HOST);
+  const int i_T = st.add(T_ref_cur, nullptr, sizeof(double) * 7 * n, 0);
+  const int i_f = st.add(f, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_z = st.add(z, nullptr, sizeof(double) * n, 0);
+  const int i_o = st.add(nullptr, tau_out, sizeof(double) * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_compute_tau(n, st.dev<double>(i_T), st.dev<double>(i_f), st.dev<double>(i_z), px_error_angle, st.dev<double>(i_o), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "compute_tau launch failed");
+  return st.download();
+}
+
+// ------------------------------------------------------------------ raw device helpers
+int svob200_dev_alloc(svob200_ctx* ctx, size_t bytes, void** dptr)
+{
+  if (!ctx || !dptr) return SVOB200_ERR_ARG;
+  if (cudaMalloc(dptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SVOB200_ERR_NOMEM, "dev_alloc(%zu) failed", bytes); }
+  return SVOB200_OK;
+}
+int svob200_dev_free(svob200_ctx* ctx, void* dptr) { if (!ctx) return SVOB200_ERR_ARG; CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(dptr)); return 0; }
+int svob200_dev_upload(svob200_ctx* ctx, void* dptr, const void* host, size_t bytes)
+{
+  if (!ctx) return SVOB200_ERR_ARG;
+  CU(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int svob200_dev_download(svob200_ctx* ctx, void* host, const void* dptr, size_t bytes)
+{
+  if (!ctx) return SVOB200_ERR_ARG;
+  CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int svob200_host_alloc_pinned(svob200_ctx* ctx, size_t bytes, void** hptr) { if (!ctx || !hptr) return SVOB200_ERR_ARG; CU(cudaMallocHost(hptr, bytes ? bytes : 1)); return 0; }
+int svob200_host_free_pinned(svob200_ctx* ctx, void* hptr) { if (!ctx) return SVOB200_ERR_ARG; CU(cudaFreeHost(hptr)); return 0; }
+
+int svob200_synth_render(svob200_ctx* ctx, const uint8_t* dev_texture, int tex_size, double ppm, double plane_z,
+                         const svob200_camera* cam, int batch, const double* T_f_w, uint8_t* dev_out)
+{
+  if (!ctx || !dev_texture || !cam || !T_f_w || !dev_out || batch <= 0) return fail(ctx, SVOB200_ERR_ARG, "synth_render: bad arguments");
+  // host: invert each pose into (R row-major, camera centre) — 12 doubles per image
+  std::vector<double> rc((size_t)12 * batch);
+  for (int b = 0; b < batch; ++b) {
+    const double* T = T_f_w + 7 * (size_t)b;
+    const double x = -T[3], y = -T[4], z = -T[5], w = T[6];     // inverse rotation
+    double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                   2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                   2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+    for (int k = 0; k < 9; ++k) rc[12 * b + k] = R[k];
+    for (int i = 0; i < 3; ++i) rc[12 * b + 9 + i] = -(R[3 * i] * T[0] + R[3 * i + 1] * T[1] + R[3 * i + 2] * T[2]);
+  }
+  if (ctx->d_scratch2.ensure(rc.size() * sizeof(double)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "synth_render: scratch alloc failed");
+  CU(cudaMemcpyAsync(ctx->d_scratch2.p, rc.data(), rc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (launch_synth_render(dev_texture, tex_size, ppm, plane_z, to_cam(cam), batch, static_cast<const double*>(ctx->d_scratch2.p), dev_out,
+                          ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "synth_render launch failed");
+  return SVOB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// kernels.h — host-side launchers of the CUDA kernels (internal to libsvob200).
+#pragma once
+#include "common.cuh"
+
+struct AlignProblemDev;   // sparse_align.cu
+
+// pyramid.cu
+int launch_pyramid(const DevFrame& f, const int* modes, cudaStream_t s, long long* launches);
+int launch_half_sample_single(const uint8_t* in, int in_pitch, int w, int h, uint8_t* out, int out_pitch, int mode,
+                              cudaStream_t s, long long* launches);
+
+// fast.cu
+// keys: batch*n_cells 64-bit cell records (device scratch); raw_scores: optional w*h score map of
+// (raw_image, raw_level) for svob200_fast_corners.
+int launch_fast_detect(const DevFrame& f, int n_detect_levels, int cell, int grid_cols, int grid_rows, double thr,
+                       const uint8_t* d_occupancy, unsigned long long* d_keys, svob200_corner* d_cells, int* d_counts,
+                       cudaStream_t s, long long* launches);
+int launch_fast_raw(const DevFrame& f, int image, int level, int threshold, int nonmax, uint8_t* d_scores,
+                    cudaStream_t s, long long* launches);
+
+// sparse_align.cu
+size_t sparse_align_scratch_bytes(int total_features);
+int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
+                        const int* d_offsets, const double* d_px, const double* d_xyz, const uint8_t* d_has_point,
+                        const double* d_T_init, svob200_align_opts opts, svob200_align_result* d_results,
+                        void* d_scratch, cudaStream_t s, long long* launches);
+
+// matcher.cu
+int launch_align_patches(const DevFrame& f, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
+                         const float* d_dir, int n_iter, double* d_px, int* d_converged, double* d_h_inv,
+                         cudaStream_t s, long long* launches);
+int launch_match_direct(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
+                        const svob200_feature_ref* d_ftrs, const double* d_depth_ref, const double* d_px_in,
+                        svob200_matcher_opts opts, svob200_match_result* d_results, cudaStream_t s, long long* launches);
+int launch_epipolar(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
+                    const svob200_feature_ref* d_ftrs, const double* d_d, svob200_matcher_opts opts,
+                    svob200_epi_result* d_results, cudaStream_t s, long long* launches);
+int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
+                        const svob200_feature_ref* d_ftrs, const double* d_T_ref_w, const double* d_T_cur_w,
+                        svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs,
+                        cudaStream_t s, long long* launches);
+int launch_update_seed(int n, const float* d_x, const float* d_tau2, svob200_seed* d_seeds, cudaStream_t s, long long* launches);
+int launch_compute_tau(int n, const double* d_T, const double* d_f, const double* d_z, double angle, double* d_out,
+                       cudaStream_t s, long long* launches);
+
+// synth.cu
+int launch_synth_render(const uint8_t* d_tex, int tex_size, double ppm, double plane_z, const DevCam& cam, int batch,
+                        const double* d_T_w_f_R_c /*12 doubles per image: R row-major + c*/, uint8_t* d_out,
+                        cudaStream_t s, long long* launches);

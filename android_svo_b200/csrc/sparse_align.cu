@@ -1,0 +1,370 @@
+// sparse_align.cu — inverse-compositional sparse image alignment over 4x4 patches.
+//
+// reference: SparseImgAlign::run / precomputeReferencePatches / computeResiduals / solve / update
+// (sparse_img_align.cpp:51-308) driven by vk::NLLSSolver<6,SE3>::optimizeGaussNewton
+// (nlls_solver_impl.hpp:25-100), SE3::exp (SE3.h:153-182), Frame::jacobian_xyz2uv (frame.h:110-132).
+//
+// B200 design: the whole run() — every pyramid level, every Gauss-Newton iteration, the 6x6
+// solve, the SE3 update and the solver's convergence / rollback logic — is ONE kernel launch with
+// one CTA per alignment problem (= per sequence of a batch).  A GN iteration is a dependency
+// chain, not a bandwidth problem, so the design minimises round trips: the model lives in shared
+// memory, one thread per (feature, pixel) keeps its residual and Jacobian row in registers, the
+// 21 + 6 + 2 normal-equation sums are reduced with a 31-shuffle transposing butterfly per warp and
+// one shared-memory pass, and thread 0 runs the pivoted LDL^T and the decision logic.
+//
+// Parity: per-residual arithmetic (bilinear weights with their double promotions, unfused float
+// sums, Jacobian rows) is bit-identical to the reference.  H/Jres are summed in double in a
+// different order (tolerance-matched).  The rollback test `new_chi2 > chi2_` hangs on a float sum
+// accumulated sequentially in the reference; it is decided here on the double sum unless the two
+// values are closer than the worst-case rounding error of the float chain, in which case thread 0
+// replays the exact sequential float chain (counted in n_exact_chi2).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+struct AlignArgs {
+  DevFrame ref, cur;
+  DevCam cam;
+  const int* offsets;
+  const double* px;
+  const double* xyz;
+  const uint8_t* has_point;
+  const double* T_init;
+  svob200_align_opts opts;
+  svob200_align_result* results;
+  // scratch, indexed by global feature / feature-pixel
+  float* ref_patch;   // 16 per feature, persists across levels (sparse_img_align.cpp:66)
+  float* gdx;         // 16 per feature
+  float* gdy;
+  float* r2[2];       // res*res of the last two evaluations (ping-pong), for the exact chi2 chain
+  uint8_t* visible;   // sticky across levels (:67)
+  uint8_t* contrib[2];
+};
+
+// Pivoted LDL^T solve of the 6x6 system, mirroring Eigen::LDLT (tolerance-matched).
+__device__ void ldlt6_solve(const double* Hin, const double* b, double* x)
+{
+  double A[36];
+  int perm[6];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) A[i] = Hin[i];
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double big = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i) { const double v = fabs(A[i * 6 + i]); if (v > big) { big = v; piv = i; } }
+    perm[k] = piv;
+    if (piv != k) {
+      const int s = 6 - piv - 1;
+      for (int j = 0; j < k; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
+      for (int j = 0; j < s; ++j) { const double t = A[(piv + 1 + j) * 6 + k]; A[(piv + 1 + j) * 6 + k] = A[(piv + 1 + j) * 6 + piv]; A[(piv + 1 + j) * 6 + piv] = t; }
+      { const double t = A[k * 6 + k]; A[k * 6 + k] = A[piv * 6 + piv]; A[piv * 6 + piv] = t; }
+      for (int i = k + 1; i < piv; ++i) { const double t = A[i * 6 + k]; A[i * 6 + k] = A[piv * 6 + i]; A[piv * 6 + i] = t; }
+    }
+    const int rs = 6 - k - 1;
+    if (k > 0) {
+      double temp[6];
+      for (int j = 0; j < k; ++j) temp[j] = A[j * 6 + j] * A[k * 6 + j];
+      double s = 0;
+      for (int j = 0; j < k; ++j) s += A[k * 6 + j] * temp[j];
+      A[k * 6 + k] -= s;
+      for (int i = 0; i < rs; ++i) {
+        double t = 0;
+        for (int j = 0; j < k; ++j) t += A[(k + 1 + i) * 6 + j] * temp[j];
+        A[(k + 1 + i) * 6 + k] -= t;
+      }
+    }
+    const double d = A[k * 6 + k];
+    if (rs > 0 && fabs(d) > 2.2250738585072014e-308)
+      for (int i = 0; i < rs; ++i) A[(k + 1 + i) * 6 + k] /= d;
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) y[i] = b[i];
+  for (int k = 0; k < 6; ++k) if (perm[k] != k) { const double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
+  for (int i = 0; i < 6; ++i) { const double d = A[i * 6 + i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
+  for (int i = 5; i >= 0; --i) for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
+  for (int k = 5; k >= 0; --k) if (perm[k] != k) { const double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+  for (int i = 0; i < 6; ++i) x[i] = y[i];
+}
+
+// the reference's `float chi2; chi2 += res*res*weight` in feature-list / row-major pixel order
+__device__ float exact_chi2_chain(const float* r2, const uint8_t* visible, const uint8_t* contrib, int N)
+{
+  float chi2 = 0.0f;
+  for (int i = 0; i < N; ++i) {
+    if (!visible[i] || !contrib[i]) continue;
+    const float4* p = reinterpret_cast<const float4*>(r2 + 16 * (size_t)i);
+    const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+    chi2 += a.x; chi2 += a.y; chi2 += a.z; chi2 += a.w;
+    chi2 += b.x; chi2 += b.y; chi2 += b.z; chi2 += b.w;
+    chi2 += c.x; chi2 += c.y; chi2 += c.z; chi2 += c.w;
+    chi2 += d.x; chi2 += d.y; chi2 += d.z; chi2 += d.w;
+  }
+  return chi2;
+}
+
+constexpr int NACC = 32;   // 21 (H upper) + 6 (J*res) + chi2 + n_meas + 3 pad
+
+// After this, lane L of the warp holds the warp-wide sum of v[L]  (31 shuffles instead of 160).
+__device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int lane)
+{
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const double send = up ? v[j] : v[j + half];
+      const double keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
+{
+  constexpr int NW = BLOCK / 32;
+  __shared__ double s_model[7];
+  __shared__ double s_old[7];
+  __shared__ double s_red[NW][NACC];
+  __shared__ double s_tot[NACC];
+  __shared__ int s_ctrl;          // 0 continue iterating, 1 leave this level
+  __shared__ int s_iter_total;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f0 = A.offsets[b], N = A.offsets[b + 1] - f0;
+  svob200_align_result* R = &A.results[b];
+
+  if (tid < 7) s_model[tid] = A.T_init[7 * b + tid];
+  if (tid == 0) {
+    for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = A.T_init[7 * b + k];
+    for (int k = 0; k < 36; ++k) R->H[k] = 0;
+    for (int k = 0; k < 6; ++k) { R->Jres[k] = 0; R->x[k] = 0; }
+    R->chi2 = 1e10; R->n_meas = 0; R->stop = 0; R->n_exact_chi2 = 0;
+    for (int k = 0; k < SVOB200_MAX_LEVELS; ++k) R->iters[k] = 0;
+  }
+  if (N <= 0) return;                                   // sparse_img_align.cpp:55-59
+  for (int i = tid; i < N; i += BLOCK) { A.visible[f0 + i] = 0; A.contrib[0][f0 + i] = 0; A.contrib[1][f0 + i] = 0; }
+  __syncthreads();
+
+  const double* px = A.px + 2 * (size_t)f0;
+  const double* xyz = A.xyz + 3 * (size_t)f0;
+  const uint8_t* has_point = A.has_point + f0;
+  uint8_t* visible = A.visible + f0;
+  float* ref_patch = A.ref_patch + 16 * (size_t)f0;
+  float* gdx = A.gdx + 16 * (size_t)f0;
+  float* gdy = A.gdy + 16 * (size_t)f0;
+  const double focal_length = fabs(A.cam.fx);          // errorMultiplier2()
+
+  // thread-0 solver state (NLLSSolver::reset nlls_solver_impl.hpp:299-309)
+  double chi2_ = 1e10;
+  bool chi2_exact = true;
+  bool stop_ = false;
+  int n_exact = 0;
+  int pp = 0;                                          // ping-pong index of the *current* evaluation
+
+  for (int level = A.opts.max_level; level >= A.opts.min_level; --level) {
+    const float scale = 1.0f / (1 << level);
+    // ---------------- precomputeReferencePatches (sparse_img_align.cpp:105-178)
+    {
+      const uint8_t* img = A.ref.lvl[level] + (size_t)b * A.ref.img_stride[level];
+      const int cols = A.ref.w[level], rows = A.ref.h[level], stride = A.ref.pitch[level];
+      for (int idx = tid; idx < N * 16; idx += BLOCK) {
+        const int i = idx >> 4, p = idx & 15;
+        const float u_ref = (float)(px[2 * i] * (double)scale);
+        const float v_ref = (float)(px[2 * i + 1] * (double)scale);
+        const int u_i = (int)floorf(u_ref), v_i = (int)floorf(v_ref);
+        const bool ok = has_point[i] && !(u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= cols || v_i + 3 >= rows);
+        if (!ok) { gdx[idx] = 0.f; gdy[idx] = 0.f; continue; }   // jacobian_cache_.setZero() (:76)
+        if (p == 0) visible[i] = 1;
+        const float su = u_ref - u_i, sv = v_ref - v_i;
+        const float w_tl = (float)((1.0 - su) * (1.0 - sv));
+        const float w_tr = (float)(su * (1.0 - sv));
+        const float w_bl = (float)((1.0 - su) * sv);
+        const float w_br = su * sv;
+        const int yy = p >> 2, xx = p & 3;
+        const uint8_t* q = img + (size_t)(v_i + yy - 2) * stride + (u_i + xx - 2);
+        ref_patch[idx] = w_tl * q[0] + w_tr * q[1] + w_bl * q[stride] + w_br * q[stride + 1];
+        gdx[idx] = 0.5f * ((w_tl * q[1] + w_tr * q[2] + w_bl * q[stride + 1] + w_br * q[stride + 2])
+                           - (w_tl * q[-1] + w_tr * q[0] + w_bl * q[stride - 1] + w_br * q[stride]));
+        gdy[idx] = 0.5f * ((w_tl * q[stride] + w_tr * q[1 + stride] + w_bl * q[stride * 2] + w_br * q[stride * 2 + 1])
+                           - (w_tl * q[-stride] + w_tr * q[1 - stride] + w_bl * q[0] + w_br * q[1]));
+      }
+    }
+    if (tid < 7) s_old[tid] = s_model[tid];
+    __syncthreads();
+
+    const uint8_t* cimg = A.cur.lvl[level] + (size_t)b * A.cur.img_stride[level];
+    const int ccols = A.cur.w[level], crows = A.cur.h[level], cstride = A.cur.pitch[level];
+    const double fl = focal_length / (1 << level);
+
+    for (int iter = 0; iter < A.opts.n_iter; ++iter) {
+      // ---------------- computeResiduals(model, linearize) (sparse_img_align.cpp:184-286)
+      double acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      double m[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) m[k] = s_model[k];
+      float* r2 = A.r2[pp] + 16 * (size_t)f0;
+      uint8_t* contrib = A.contrib[pp] + f0;
+      for (int idx = tid; idx < N * 16; idx += BLOCK) {
+        const int i = idx >> 4, p = idx & 15;
+        if (!visible[i]) continue;
+        const v3d pr = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        const v3d pc = se3_transform(m, pr);
+        double pxd, pyd;
+        world2cam(A.cam, pc, pxd, pyd);
+        const float u_cur = (float)pxd * scale, v_cur = (float)pyd * scale;
+        const int u_i = (int)floorf(u_cur), v_i = (int)floorf(v_cur);
+        const bool in = !(u_i < 0 || v_i < 0 || u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= ccols || v_i + 3 >= crows);
+        if (p == 0) contrib[i] = in ? 1 : 0;
+        if (!in) continue;
+        const float su = u_cur - u_i, sv = v_cur - v_i;
+        const float w_tl = (float)((1.0 - su) * (1.0 - sv));
+        const float w_tr = (float)(su * (1.0 - sv));
+        const float w_bl = (float)((1.0 - su) * sv);
+        const float w_br = su * sv;
+        const int yy = p >> 2, xx = p & 3;
+        const uint8_t* q = cimg + (size_t)(v_i + yy - 2) * cstride + (u_i + xx - 2);
+        const float intensity = w_tl * q[0] + w_tr * q[1] + w_bl * q[cstride] + w_br * q[cstride + 1];
+        const float res = intensity - ref_patch[idx];
+        const float rr = res * res * 1.0f;
+        r2[idx] = rr;
+        // Jacobian row: (dx*J0 + dy*J1) * (focal_length / 2^level), Frame::jacobian_xyz2uv
+        const double x = pr.x, y = pr.y;
+        const double z_inv = 1. / pr.z, z_inv_2 = z_inv * z_inv;
+        const double j02 = x * z_inv_2, j03 = y * j02, j12 = y * z_inv_2;
+        const double J0[6] = {-z_inv, 0.0, j02, j03, -(1.0 + x * j02), y * z_inv};
+        const double J1[6] = {0.0, -z_inv, j12, 1.0 + y * j12, -j03, -x * z_inv};
+        const double dx = (double)gdx[idx], dy = (double)gdy[idx];
+        double J[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[k] = (dx * J0[k] + dy * J1[k]) * fl;
+        const double rd = (double)res;
+        int h = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+          for (int c = a; c < 6; ++c) acc[h++] += J[a] * J[c];
+          acc[21 + a] += J[a] * rd;
+        }
+        acc[27] += (double)rr;
+        acc[28] += 1.0;
+      }
+      // ---------------- block reduction
+      const double mine = warp_transpose_reduce(acc, lane);
+      s_red[warp][lane] = mine;
+      __syncthreads();
+      if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += s_red[w][lane];
+        s_tot[lane] = t;
+      }
+      __syncthreads();
+
+      // ---------------- solve / decide / update (thread 0), nlls_solver_impl.hpp:36-99
+      if (tid == 0) {
+        double H[36], Jres[6], xs[6];
+        int h = 0;
+        for (int a = 0; a < 6; ++a) {
+          for (int c = a; c < 6; ++c) { H[a * 6 + c] = s_tot[h]; H[c * 6 + a] = s_tot[h]; ++h; }
+          Jres[a] = -s_tot[21 + a];
+        }
+        const int n_meas = (int)s_tot[28];
+        double new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
+        bool new_exact = false;
+        ldlt6_solve(H, Jres, xs);
+        if (isnan(xs[0])) stop_ = true;
+        for (int k = 0; k < 36; ++k) R->H[k] = H[k];
+        for (int k = 0; k < 6; ++k) { R->Jres[k] = Jres[k]; R->x[k] = xs[k]; }
+        R->n_meas = n_meas;
+        R->iters[level] += 1;
+        int ctrl = 0;
+        if (iter > 0 && !stop_) {
+          // worst-case first-order rounding error of two sequential float sums of n_meas terms
+          const double tol = 2.0 * (double)n_meas * 5.9604644775390625e-08;
+          const double big = fmax(fabs(new_chi2), fabs(chi2_));
+          if (fabs(new_chi2 - chi2_) <= tol * big) {
+            ++n_exact;
+            new_chi2 = (double)(exact_chi2_chain(r2, visible, contrib, N) / (float)n_meas);
+            new_exact = true;
+            if (!chi2_exact) {
+              // previous evaluation lives in the other ping-pong buffer
+              const float prev = exact_chi2_chain(A.r2[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N);
+              int pn = 0;
+              for (int i = 0; i < N; ++i) pn += (visible[i] && A.contrib[pp ^ 1][f0 + i]) ? 16 : 0;
+              chi2_ = (double)(prev / (float)pn);
+              chi2_exact = true;
+            }
+          }
+        }
+        if ((iter > 0 && new_chi2 > chi2_) || stop_) {
+          for (int k = 0; k < 7; ++k) s_model[k] = s_old[k];        // rollback
+          ctrl = 1;
+        } else {
+          double nx[6], E[7], nm[7];
+          for (int k = 0; k < 6; ++k) nx[k] = -xs[k];
+          se3_exp(nx, E);                                            // update(): T * exp(-x)
+          se3_mul(s_model, E, nm);
+          for (int k = 0; k < 7; ++k) { s_old[k] = s_model[k]; s_model[k] = nm[k]; }
+          chi2_ = new_chi2;
+          chi2_exact = new_exact;
+          double nmax = 0;
+          for (int k = 0; k < 6; ++k) nmax = fmax(nmax, fabs(xs[k]));   // vk::norm_max
+          if (nmax <= A.opts.eps) ctrl = 1;
+        }
+        s_ctrl = ctrl;
+      }
+      pp ^= 1;
+      __syncthreads();
+      if (s_ctrl) break;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = s_model[k];
+    R->chi2 = chi2_;
+    R->stop = stop_ ? 1 : 0;
+    R->n_exact_chi2 = n_exact;
+  }
+}
+
+}  // namespace
+
+size_t sparse_align_scratch_bytes(int total_features)
+{
+  const size_t n = (size_t)(total_features > 0 ? total_features : 1);
+  return n * 16 * sizeof(float) * 5 + n * 3 + 256 * 8;
+}
+
+int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
+                        const int* d_offsets, const double* d_px, const double* d_xyz, const uint8_t* d_has_point,
+                        const double* d_T_init, svob200_align_opts opts, svob200_align_result* d_results,
+                        void* d_scratch, cudaStream_t s, long long* launches)
+{
+  AlignArgs A{};
+  A.ref = ref; A.cur = cur; A.cam = cam; A.offsets = d_offsets; A.px = d_px; A.xyz = d_xyz; A.has_point = d_has_point;
+  A.T_init = d_T_init; A.opts = opts; A.results = d_results;
+  // carve the scratch in the order sparse_align_scratch_bytes() counts it
+  const size_t T = (size_t)(total_features > 0 ? total_features : 1);
+  char* p = static_cast<char*>(d_scratch);
+  const size_t fsz = T * 16 * sizeof(float);
+  A.ref_patch = reinterpret_cast<float*>(p); p += fsz;
+  A.gdx = reinterpret_cast<float*>(p); p += fsz;
+  A.gdy = reinterpret_cast<float*>(p); p += fsz;
+  A.r2[0] = reinterpret_cast<float*>(p); p += fsz;
+  A.r2[1] = reinterpret_cast<float*>(p); p += fsz;
+  A.visible = reinterpret_cast<uint8_t*>(p); p += T;
+  A.contrib[0] = reinterpret_cast<uint8_t*>(p); p += T;
+  A.contrib[1] = reinterpret_cast<uint8_t*>(p);
+  // one (feature, pixel) pair per thread and pass: 256 threads cover 16 features per pass
+  if (max_per_problem <= 512) sparse_align_kernel<256><<<batch, 256, 0, s>>>(A);
+  else sparse_align_kernel<512><<<batch, 512, 0, s>>>(A);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -1,0 +1,217 @@
+/*
+ * svob200.h — C ABI of the B200-native SVO tracking front end (libsvob200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, int status
+ * returns (0 = ok, <0 = error; svob200_last_error() gives the text).  Each entry point names
+ * the reference interface it replaces (paths relative to
+ * /root/reference/app/src/main/cpp/svo).  INTEGRATION.md shows the reference-side bindings.
+ *
+ * Conventions
+ *   pose      double[7] = {tx,ty,tz, qx,qy,qz,qw}   (SE3 ctor order, include/svo/SE3.h:17-19)
+ *   camera    distortion-free pinhole (pinhole_camera.cpp:48-53, :83-87)
+ *   frames    device-resident image pyramids keyed by a caller-chosen 64-bit id (Frame::id_);
+ *             a frame may hold a BATCH of independent images of equal size (one per sequence)
+ *   mem       every array argument of a compute call lives either in host memory
+ *             (SVOB200_MEM_HOST: the call stages, copies H2D/D2H and synchronises) or in device
+ *             memory (SVOB200_MEM_DEVICE: no copies, asynchronous on the context's stream)
+ *   batching  per-item arrays carry the image (= sequence) index inside the frame batch
+ *
+ * There is no CPU fallback: every compute entry point launches CUDA kernels and fails with
+ * SVOB200_ERR_CUDA if no device is usable.
+ */
+#ifndef SVOB200_H_
+#define SVOB200_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVOB200_MAX_LEVELS 8          /* array extent; the fused pyramid kernel supports <= 7 */
+
+enum { SVOB200_OK = 0, SVOB200_ERR_ARG = -1, SVOB200_ERR_CUDA = -2, SVOB200_ERR_NOFRAME = -3,
+       SVOB200_ERR_UNSUPPORTED = -4, SVOB200_ERR_NOMEM = -5 };
+enum { SVOB200_MEM_HOST = 0, SVOB200_MEM_DEVICE = 1 };
+/* vk::halfSample rounding (vision.cpp): TRUNC = scalar/NEON (a+b+c+d)/4; SSE2 = x86 double avg */
+enum { SVOB200_ROUND_TRUNC = 0, SVOB200_ROUND_SSE2 = 1 };
+
+typedef struct svob200_ctx svob200_ctx;
+typedef struct { int width, height; double fx, fy, cx, cy; } svob200_camera;
+
+/* ---------------------------------------------------------------- context */
+int         svob200_ctx_create(int device, svob200_ctx** out);
+void        svob200_ctx_destroy(svob200_ctx* ctx);
+const char* svob200_last_error(const svob200_ctx* ctx);
+int         svob200_ctx_sync(svob200_ctx* ctx);
+void*       svob200_ctx_stream(svob200_ctx* ctx);             /* cudaStream_t */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long   svob200_ctx_launch_count(const svob200_ctx* ctx);
+/* CUDA-event timing on the context's stream (events are created lazily) */
+int         svob200_ctx_timer_start(svob200_ctx* ctx);
+int         svob200_ctx_timer_stop_ms(svob200_ctx* ctx, float* ms);
+
+/* sizeof() of the ABI structs in declaration order (camera, corner, align_opts, align_result,
+ * matcher_opts, feature_ref, match_result, epi_result, seed, seed_obs); returns how many there are */
+int         svob200_abi_sizes(int* sizes, int cap);
+
+/* ---------------------------------------------------------------- frames / pyramid
+ * replaces: Frame::initFrame -> frame_utils::createImgPyramid -> vk::halfSample
+ *           (frame.cpp:51-64, :186-195; vision.cpp:71-110) */
+/* x86 host dispatch rule of vk::halfSample (vision.cpp:78): SSE2 iff in_cols % 16 == 0 */
+int svob200_round_mode_x86(int in_cols);
+/* allocate a device pyramid for `batch` images of w x h with n_levels levels */
+int svob200_frame_create(svob200_ctx* ctx, int64_t frame_id, int batch, int w, int h, int n_levels);
+/* copy level 0 (gray: batch images, row stride `stride` bytes, image stride stride*h) and build
+ * levels 1..n-1.  round_modes: n_levels-1 entries (mode used to produce level l+1 from l) or
+ * NULL for the x86 host rule.  mem says where `gray` lives. */
+int svob200_frame_upload(svob200_ctx* ctx, int64_t frame_id, const uint8_t* gray, int stride,
+                         const int* round_modes, int mem);
+/* level 0 ALIASES the caller's device buffer (like the reference, where level 0 aliases the caller's
+ * cv::Mat, frame.cpp:189): no copy, the pyramid kernel reads the frame where it already lies in HBM.
+ * dev_gray and stride must be 16-byte aligned; the buffer must outlive the frame's use. */
+int svob200_frame_bind(svob200_ctx* ctx, int64_t frame_id, const uint8_t* dev_gray, int stride,
+                       const int* round_modes);
+/* frame-table slot of a resident frame (>= 0).  In SVOB200_MEM_DEVICE mode the ref_frame_id field
+ * of svob200_feature_ref records must already hold this slot instead of the id. */
+int svob200_frame_slot(svob200_ctx* ctx, int64_t frame_id);
+/* download one level of one image into a dense (or strided) host buffer */
+int svob200_frame_download(svob200_ctx* ctx, int64_t frame_id, int image, int level,
+                           uint8_t* out, int out_stride);
+int svob200_frame_release(svob200_ctx* ctx, int64_t frame_id);
+int svob200_frame_info(svob200_ctx* ctx, int64_t frame_id, int* batch, int* w, int* h, int* n_levels);
+/* stand-alone vk::halfSample(in,out) on host buffers (vision.h:38): upload, one level, download */
+int svob200_half_sample(svob200_ctx* ctx, const uint8_t* in, int w, int h, int in_stride,
+                        uint8_t* out, int out_stride, int round_mode);
+
+/* ---------------------------------------------------------------- FAST + Shi-Tomasi + grid
+ * replaces: FastDetector::detect (feature_detection.cpp:77-122), cv::FAST(img,kps,10,true)
+ *           (OpenCV 4.5.4 features2d, FAST-9/16), vk::shiTomasiScore (vision.cpp:113-154) */
+typedef struct { int x, y, level; float score; } svob200_corner;
+/* cells_out: batch * n_cells entries (n_cells = ceil(W/cell)*ceil(H/cell)), each initialised to
+ * (0,0,0,thr) like the reference; a cell holds a feature iff score > thr.  occupancy: batch*n_cells
+ * bytes or NULL.  n_features_out: batch ints (may be NULL). */
+int svob200_fast_detect(svob200_ctx* ctx, int64_t frame_id, int n_detect_levels, int cell_size,
+                        double detection_threshold, const uint8_t* occupancy,
+                        svob200_corner* cells_out, int* n_features_out, int mem);
+/* raw cv::FAST keypoints of one level of one image (row-major order), for parity tests.
+ * Returns the keypoint count (<0 on error); writes at most cap entries. */
+int svob200_fast_corners(svob200_ctx* ctx, int64_t frame_id, int image, int level, int threshold,
+                         int nonmax, int cap, int* xs, int* ys, int* scores);
+
+/* ---------------------------------------------------------------- sparse image alignment
+ * replaces: SparseImgAlign::run (sparse_img_align.cpp:51-92) incl. precomputeReferencePatches,
+ *           computeResiduals, solve, update and vk::NLLSSolver::optimizeGaussNewton
+ *           (nlls_solver_impl.hpp:25-100) */
+typedef struct { int max_level, min_level, n_iter; double eps; } svob200_align_opts;
+typedef struct {
+  double T_cur_ref[7];
+  double H[36];          /* row-major; H_ of the last linearisation (getFisherInformation = H/(5e-4*255^2)) */
+  double Jres[6];
+  double x[6];
+  double chi2;
+  int    n_meas;         /* run() returns n_meas/16 */
+  int    iters[SVOB200_MAX_LEVELS];
+  int    stop;
+  int    n_exact_chi2;   /* iterations whose rollback decision needed the sequential float chi2 */
+} svob200_align_result;
+/* One alignment problem per image of the batch.  ftr_offsets: batch+1 prefix offsets into the
+ * per-feature arrays; px: 2 doubles (level-0 pixels); xyz_ref: 3 doubles (= f*depth,
+ * sparse_img_align.cpp:132-134); has_point: 1 byte; T_cur_ref: 7 doubles per image (in);
+ * results: one svob200_align_result per image (out). */
+int svob200_sparse_align(svob200_ctx* ctx, int64_t ref_frame_id, int64_t cur_frame_id,
+                         const svob200_camera* cam, int batch, const int* ftr_offsets,
+                         const double* px, const double* xyz_ref, const uint8_t* has_point,
+                         const double* T_cur_ref, const svob200_align_opts* opts,
+                         svob200_align_result* results, int mem);
+
+/* ---------------------------------------------------------------- feature alignment
+ * replaces: feature_alignment::align2D / align1D float paths (feature_alignment.cpp:35-282) */
+/* n independent problems on one level of a frame.  image: n ints; patch_with_border: n*100,
+ * patch: n*64 bytes; dir: n*2 floats (align1D only, NULL => align2D); px: n*2 doubles in/out at
+ * that level's scale; converged: n ints; h_inv: n doubles (align1D only, may be NULL) */
+int svob200_align_patches(svob200_ctx* ctx, int64_t frame_id, int level, int n, const int* image,
+                          const uint8_t* patch_with_border, const uint8_t* patch, const float* dir,
+                          int n_iter, double* px, int* converged, double* h_inv, int mem);
+
+/* ---------------------------------------------------------------- matcher
+ * replaces: Matcher::findMatchDirect (matcher.cpp:156-202) after Point::getCloseViewObs picked
+ *           the reference observation; warp::getWarpMatrixAffine / getBestSearchLevel / warpAffine
+ *           (matcher.cpp:36-116); Matcher::findEpipolarMatchDirect (matcher.cpp:207-355);
+ *           vk::patch_score::ZMSSD<4> (patch_score.h) */
+typedef struct {
+  int align_1d, align_max_iter, max_epi_search_steps, subpix_refinement, epi_search_edgelet_filtering;
+  double epi_search_edgelet_max_angle;
+  int max_search_level;            /* Config::nPyrLevels()-1 */
+} svob200_matcher_opts;
+void svob200_matcher_opts_default(svob200_matcher_opts* o, int n_pyr_levels);
+
+/* reference-side description of one feature (Feature{px,f,level,type,grad}, feature.h:24-76) */
+typedef struct {
+  int64_t ref_frame_id; int ref_image;     /* keyframe holding the reference patch */
+  int     cur_image;                       /* image inside the current frame batch */
+  int     level; int type;                 /* type: 0 CORNER, 1 EDGELET */
+  double  px[2]; double f[3]; double grad[2];
+  double  T_cur_ref[7];                    /* cur.T_f_w_ * ref.T_f_w_.inverse() */
+} svob200_feature_ref;
+
+typedef struct {
+  int success; int search_level; double px_cur[2]; double A_cur_ref[4]; double h_inv;
+  uint8_t patch_with_border[100]; uint8_t patch[64];
+} svob200_match_result;
+/* depth_ref: n doubles = |ref_frame.pos - point.pos|; px_cur_in: n*2 doubles (initial estimate) */
+int svob200_match_direct(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int n,
+                         const svob200_feature_ref* ftrs, const double* depth_ref,
+                         const double* px_cur_in, const svob200_matcher_opts* opts,
+                         svob200_match_result* results, int mem);
+
+typedef struct {
+  int success; int search_level; int reject; int zmssd_best; int n_evals; int n_steps;
+  double depth; double px_cur[2]; double epi_length; double A_cur_ref[4]; double h_inv;
+  uint8_t patch_with_border[100]; uint8_t patch[64];
+} svob200_epi_result;
+/* d: n*3 doubles (d_estimate, d_min, d_max) */
+int svob200_epipolar_match(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int n,
+                           const svob200_feature_ref* ftrs, const double* d,
+                           const svob200_matcher_opts* opts, svob200_epi_result* results, int mem);
+
+/* ---------------------------------------------------------------- depth filter
+ * replaces: DepthFilter::updateSeeds loop body (depth_filter.cpp:250-340), DepthFilter::updateSeed
+ *           (:368-391), DepthFilter::computeTau (:396-416), Seed ctor (:36-45) */
+typedef struct { float a, b, mu, z_range, sigma2; } svob200_seed;
+enum { SVOB200_SEED_BEHIND = 1, SVOB200_SEED_NOT_IN_FRAME = 2, SVOB200_SEED_NO_MATCH = 3,
+       SVOB200_SEED_UPDATED = 4, SVOB200_SEED_CONVERGED = 5, SVOB200_SEED_NAN_ERASED = 6 };
+typedef struct {
+  int status; int search_level; int zmssd_best; int n_evals;
+  double z; double px_cur[2]; double epi_length;
+} svob200_seed_obs;
+/* ftrs[i].T_cur_ref is ignored here: poses come as T_ref_w (7 doubles per seed) and T_cur_w
+ * (7 doubles per image of the current batch) because updateSeeds derives both T_ref_cur and
+ * T_cur_ref from them (depth_filter.cpp:263, matcher.cpp:216).  seeds: in/out.  obs: out. */
+int svob200_seeds_update(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int n,
+                         const svob200_feature_ref* ftrs, const double* T_ref_w, const double* T_cur_w,
+                         const svob200_matcher_opts* opts, double seed_convergence_sigma2_thresh,
+                         svob200_seed* seeds, svob200_seed_obs* obs, int mem);
+/* scalar helpers with the reference's static signatures (depth_filter.h:126-136); run on device */
+int svob200_update_seed(svob200_ctx* ctx, int n, const float* x, const float* tau2, svob200_seed* seeds);
+int svob200_compute_tau(svob200_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z,
+                        double px_error_angle, double* tau_out);
+
+/* ---------------------------------------------------------------- device-side helpers for the
+ * resident ("value") path and the synthetic bench: raw device allocations and a plane renderer.
+ * Not part of the reference surface. */
+int svob200_dev_alloc(svob200_ctx* ctx, size_t bytes, void** dptr);
+int svob200_dev_free(svob200_ctx* ctx, void* dptr);
+int svob200_dev_upload(svob200_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int svob200_dev_download(svob200_ctx* ctx, void* host, const void* dptr, size_t bytes);
+int svob200_host_alloc_pinned(svob200_ctx* ctx, size_t bytes, void** hptr);
+int svob200_host_free_pinned(svob200_ctx* ctx, void* hptr);
+/* render `batch` views of the textured plane z = plane_z into device memory (dense, w*h each) */
+int svob200_synth_render(svob200_ctx* ctx, const uint8_t* dev_texture, int tex_size, double ppm, double plane_z,
+                         const svob200_camera* cam, int batch, const double* T_f_w /*host, 7 per image*/,
+                         uint8_t* dev_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

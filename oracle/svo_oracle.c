@@ -909,6 +909,7 @@ int svo_oracle_find_epipolar_match(const svo_pyr* ref, const svo_pyr* cur, const
 {
   memset(r, 0, sizeof(*r));
   int zmssd_best = 2000 * 64;
+  r->zmssd_best = zmssd_best;
   double uv_best[2] = { 0, 0 };
   double p[3], t[3];
   for (int k = 0; k < 3; ++k) p[k] = f->f_ref[k] * d_min;
