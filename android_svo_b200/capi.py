@@ -50,6 +50,9 @@ epi_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("reject", 
                           ("n_steps", "i4"), ("depth", "f8"), ("px_cur", "f8", 2), ("epi_length", "f8"), ("A_cur_ref", "f8", 4),
                           ("h_inv", "f8"), ("patch_with_border", "u1", 100), ("patch", "u1", 64)], align=True)
 seed_dt = np.dtype([("a", "f4"), ("b", "f4"), ("mu", "f4"), ("z_range", "f4"), ("sigma2", "f4")], align=True)
+step_stats_dt = np.dtype([("T_cur_w", "f8", 7), ("chi2", "f8"), ("n_tracked", "i4"), ("n_matched", "i4"), ("n_seeds_updated", "i4"),
+                          ("n_seeds_converged", "i4"), ("n_seeds_failed", "i4"), ("n_seeds_skipped", "i4"), ("align_iters", "i4"),
+                          ("n_exact_chi2", "i4")], align=True)
 seed_obs_dt = np.dtype([("status", "i4"), ("search_level", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"), ("z", "f8"),
                         ("px_cur", "f8", 2), ("epi_length", "f8")], align=True)
 
@@ -94,6 +97,16 @@ def load_library():
     L.svob200_seeds_update.argtypes = [V, C.c_int64, C.POINTER(Camera), C.c_int, V, V, V, C.POINTER(MatcherOpts), C.c_double, V, V, C.c_int]
     L.svob200_update_seed.argtypes = [V, C.c_int, V, V, V]
     L.svob200_compute_tau.argtypes = [V, C.c_int, V, V, V, C.c_double, V]
+    L.svob200_features_prepare.argtypes = [V, C.POINTER(Camera), C.c_int, V, V, V, C.c_int, V, V, V, C.c_int]
+    L.svob200_compose_poses.argtypes = [V, C.c_int, V, V, V, C.c_int]
+    L.svob200_reproject_prepare.argtypes = [V, C.POINTER(Camera), C.c_int, V, V, V, C.c_int, V, V, V, C.c_int]
+    L.svob200_tracker_create.argtypes = [V, C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(AlignOpts), C.POINTER(MatcherOpts), C.c_double,
+                                         C.c_float, C.c_float, C.c_int, C.POINTER(V)]
+    L.svob200_tracker_destroy.argtypes = [V]
+    L.svob200_tracker_set_keyframe.argtypes = [V, V, C.c_int, V, V, V, V, V, V, V, V]
+    L.svob200_tracker_set_last.argtypes = [V, V, C.c_int, C.c_int]
+    L.svob200_tracker_step.argtypes = [V, V, C.c_int, V, V, V, V, V, C.c_int]
+    L.svob200_tracker_get_seeds.argtypes = [V, V]
     L.svob200_dev_alloc.argtypes = [V, C.c_size_t, C.POINTER(V)]
     L.svob200_dev_free.argtypes = [V, V]
     L.svob200_dev_upload.argtypes = [V, V, V, C.c_size_t]
@@ -113,7 +126,9 @@ EXPORTED_SYMBOLS = [
     "svob200_sparse_align", "svob200_align_patches", "svob200_matcher_opts_default", "svob200_match_direct",
     "svob200_epipolar_match", "svob200_seeds_update", "svob200_update_seed", "svob200_compute_tau", "svob200_dev_alloc",
     "svob200_dev_free", "svob200_dev_upload", "svob200_dev_download", "svob200_host_alloc_pinned", "svob200_host_free_pinned",
-    "svob200_synth_render",
+    "svob200_synth_render", "svob200_features_prepare", "svob200_compose_poses", "svob200_reproject_prepare",
+    "svob200_tracker_create", "svob200_tracker_destroy", "svob200_tracker_set_keyframe", "svob200_tracker_set_last",
+    "svob200_tracker_step", "svob200_tracker_get_seeds", "svob200_tracker_launches_per_step",
 ]
 
 
@@ -335,9 +350,70 @@ def abi_sizes():
     buf = (C.c_int * 16)()
     n = L.svob200_abi_sizes(buf, 16)
     mine = [C.sizeof(Camera), corner_dt.itemsize, C.sizeof(AlignOpts), align_result_dt.itemsize, C.sizeof(MatcherOpts),
-            feature_ref_dt.itemsize, match_result_dt.itemsize, epi_result_dt.itemsize, seed_dt.itemsize, seed_obs_dt.itemsize]
+            feature_ref_dt.itemsize, match_result_dt.itemsize, epi_result_dt.itemsize, seed_dt.itemsize, seed_obs_dt.itemsize,
+            step_stats_dt.itemsize]
     return list(buf[:n]), mine
 
 
 def make_feature_refs(n):
     return np.zeros(n, feature_ref_dt)
+
+
+class Tracker:
+    """svob200_tracker: one front-end step per call over a batch of independent sequences."""
+
+    def __init__(self, ctx, cam, batch, n_levels, max_level, min_level, n_pyr_levels_cfg, conv_thresh=100.0, depth_mean=2.4,
+                 depth_min=1.2, reseed=1, n_iter=30, eps=1e-6):
+        self.ctx, self.L, self.batch = ctx, ctx.L, batch
+        self.cam = cam
+        ao = AlignOpts(max_level, min_level, n_iter, eps)
+        mo = ctx.matcher_opts(n_pyr_levels_cfg)
+        h = C.c_void_p()
+        ctx._ck(self.L.svob200_tracker_create(ctx.h, C.byref(cam), batch, n_levels, C.byref(ao), C.byref(mo), float(conv_thresh),
+                                              depth_mean, depth_min, int(reseed), C.byref(h)))
+        self.h = h
+        self.N = self.S = 0
+
+    def set_keyframe(self, imgs, T_kf_w, ftr_offsets, kf_px, kf_level, pt_world, seed_offsets, seed_px, seed_level):
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        a = lambda x, t: np.ascontiguousarray(x, dtype=t)
+        fo, so = a(ftr_offsets, np.int32), a(seed_offsets, np.int32)
+        self.N, self.S = int(fo[-1]), int(so[-1])
+        args = [a(T_kf_w, np.float64), fo, a(kf_px, np.float64), a(kf_level, np.int32), a(pt_world, np.float64), so,
+                a(seed_px, np.float64), a(seed_level, np.int32)]
+        self.ctx._ck(self.L.svob200_tracker_set_keyframe(self.h, _ptr(imgs), imgs.shape[-1], *[_ptr(x) for x in args]))
+
+    def set_last(self, imgs, mem=MEM_HOST, stride=None):
+        if mem == MEM_HOST:
+            imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+            stride = imgs.shape[-1]
+        self.ctx._ck(self.L.svob200_tracker_set_last(self.h, _ptr(imgs), int(stride), mem))
+
+    def step(self, cur_imgs, T_last_w, last_px, want_px=False):
+        """Host-memory step: returns per-sequence stats (and refined pixels / success flags)."""
+        cur_imgs = np.ascontiguousarray(cur_imgs, dtype=np.uint8)
+        T = np.ascontiguousarray(T_last_w, dtype=np.float64)
+        lp = np.ascontiguousarray(last_px, dtype=np.float64)
+        stats = np.zeros(self.batch, step_stats_dt)
+        px = np.zeros((self.N, 2)) if want_px else None
+        ok = np.zeros(self.N, np.int32) if want_px else None
+        self.ctx._ck(self.L.svob200_tracker_step(self.h, _ptr(cur_imgs), cur_imgs.shape[-1], _ptr(T), _ptr(lp), _ptr(stats),
+                                                 _ptr(px), _ptr(ok), MEM_HOST))
+        return (stats, px, ok) if want_px else stats
+
+    def step_raw(self, cur_ptr, stride, T_ptr, px_ptr, stats_ptr, mem):
+        """Pointer-level step (pinned host or device addresses), no allocation on the Python side."""
+        rc = self.L.svob200_tracker_step(self.h, C.c_void_p(cur_ptr), int(stride), C.c_void_p(T_ptr), C.c_void_p(px_ptr),
+                                         C.c_void_p(stats_ptr) if stats_ptr else None, None, None, mem)
+        if rc < 0:
+            self.ctx._ck(rc)
+
+    def seeds(self):
+        out = np.zeros(max(self.S, 1), seed_dt)
+        self.ctx._ck(self.L.svob200_tracker_get_seeds(self.h, _ptr(out)))
+        return out[:self.S]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.svob200_tracker_destroy(self.h)
+            self.h = None

@@ -1,91 +1,9 @@
 // capi.cu — the C ABI of libsvob200 (include/svob200.h): context, device-resident frame store,
 // host<->device staging and the entry points that launch the kernels.  No compute happens on the
 // host here; a missing / unusable GPU makes every call fail with SVOB200_ERR_CUDA.
-#include <cstdio>
-#include <cstring>
-#include <cstdarg>
-#include <string>
-#include <vector>
-#include <unordered_map>
-#include <mutex>
-#include <algorithm>
-#include "common.cuh"
-#include "kernels.h"
+#include "ctx_internal.h"
 
 namespace {
-
-constexpr int kMaxFrames = 4096;
-
-struct FrameRec {
-  DevFrame f;
-  uint8_t* base = nullptr;       // owned allocation (all levels)
-  uint8_t* own_l0 = nullptr;     // owned level-0 storage (f.lvl[0] may alias caller memory after bind)
-  int own_pitch0 = 0;
-  int slot = -1;
-};
-
-struct GrowBuf {
-  void* p = nullptr; size_t cap = 0;
-  cudaError_t ensure(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    size_t want = std::max(n, (size_t)1 << 16);
-    want = (want + (want >> 2) + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-}  // namespace
-
-struct svob200_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  long long launches = 0;
-  std::unordered_map<int64_t, FrameRec> frames;
-  std::vector<int> free_slots;
-  DevFrame* d_table = nullptr;
-  // staging arenas (HOST mem mode)
-  uint8_t* h_stage = nullptr; size_t h_cap = 0;
-  GrowBuf d_stage, d_scratch, d_scratch2;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::mutex mu;
-};
-
-namespace {
-
-int fail(svob200_ctx* c, int code, const char* fmt, ...)
-{
-  char buf[512];
-  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-  if (c) c->err = buf;
-  return code;
-}
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
-
-DevCam to_cam(const svob200_camera* c) { DevCam d; d.width = c->width; d.height = c->height; d.fx = c->fx; d.fy = c->fy; d.cx = c->cx; d.cy = c->cy; return d; }
-
-FrameRec* find_frame(svob200_ctx* ctx, int64_t id)
-{
-  auto it = ctx->frames.find(id);
-  return it == ctx->frames.end() ? nullptr : &it->second;
-}
-
-int ensure_host_stage(svob200_ctx* ctx, size_t n)
-{
-  if (n <= ctx->h_cap) return 0;
-  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-  ctx->h_stage = nullptr; ctx->h_cap = 0;
-  size_t want = std::max(n, (size_t)1 << 16);
-  want = (want + (want >> 2) + 255) & ~(size_t)255;
-  CU(cudaMallocHost((void**)&ctx->h_stage, want));
-  ctx->h_cap = want;
-  return 0;
-}
 
 // Three-region staging plan: IN | INOUT | OUT.  Device copies cover [0, end(INOUT)) on the way in
 // and [begin(INOUT), end) on the way out — one cudaMemcpyAsync each way per call.
@@ -219,7 +137,7 @@ int svob200_abi_sizes(int* sizes, int cap)
   const int v[] = {(int)sizeof(svob200_camera), (int)sizeof(svob200_corner), (int)sizeof(svob200_align_opts),
                    (int)sizeof(svob200_align_result), (int)sizeof(svob200_matcher_opts), (int)sizeof(svob200_feature_ref),
                    (int)sizeof(svob200_match_result), (int)sizeof(svob200_epi_result), (int)sizeof(svob200_seed),
-                   (int)sizeof(svob200_seed_obs)};
+                   (int)sizeof(svob200_seed_obs), (int)sizeof(svob200_step_stats)};
   const int n = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < cap; ++i) sizes[i] = v[i];
   return n;
@@ -587,6 +505,65 @@ int svob200_compute_tau(svob200_ctx* ctx, int n, const double* T_ref_cur, const 
   if (int e = st.push()) return e;
   if (launch_compute_tau(n, st.dev<double>(i_T), st.dev<double>(i_f), st.dev<double>(i_z), px_error_angle, st.dev<double>(i_o), ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "compute_tau launch failed");
+  return st.download();
+}
+
+// ------------------------------------------------------------------ glue between operators
+int svob200_features_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n, const double* px, const double* pt_world,
+                             const int* image, int batch, const double* T_ref_w, double* f_out, double* xyz_ref_out, int mem)
+{
+  if (!ctx || !cam || n < 0 || !px || !pt_world || !image || !T_ref_w || !xyz_ref_out || batch <= 0) return fail(ctx, SVOB200_ERR_ARG, "features_prepare: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_px = st.add(px, nullptr, sizeof(double) * 2 * n, 0);
+  const int i_pt = st.add(pt_world, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_im = st.add(image, nullptr, sizeof(int) * n, 0);
+  const int i_T = st.add(T_ref_w, nullptr, sizeof(double) * 7 * batch, 0);
+  const int i_f = f_out ? st.add(nullptr, f_out, sizeof(double) * 3 * n, 2) : -1;
+  const int i_x = st.add(nullptr, xyz_ref_out, sizeof(double) * 3 * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_features_prepare(to_cam(cam), n, st.dev<double>(i_px), st.dev<double>(i_pt), st.dev<int>(i_im), st.dev<double>(i_T),
+                              f_out ? st.dev<double>(i_f) : nullptr, st.dev<double>(i_x), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "features_prepare launch failed");
+  return st.download();
+}
+
+int svob200_compose_poses(svob200_ctx* ctx, int batch, const svob200_align_result* results, const double* T_ref_w, double* T_cur_w, int mem)
+{
+  if (!ctx || batch <= 0 || !results || !T_ref_w || !T_cur_w) return fail(ctx, SVOB200_ERR_ARG, "compose_poses: bad arguments");
+  Stage st(ctx, mem);
+  const int i_r = st.add(results, nullptr, sizeof(svob200_align_result) * batch, 0);
+  const int i_T = st.add(T_ref_w, nullptr, sizeof(double) * 7 * batch, 0);
+  const int i_o = st.add(nullptr, T_cur_w, sizeof(double) * 7 * batch, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_compose_poses(batch, st.dev<svob200_align_result>(i_r), st.dev<double>(i_T), st.dev<double>(i_o), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "compose_poses launch failed");
+  return st.download();
+}
+
+int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n, svob200_feature_ref* ftrs, const double* pt_world,
+                              const double* T_kf_w, int batch, const double* T_cur_w, double* depth_ref_out, double* px_cur_out, int mem)
+{
+  if (!ctx || !cam || n < 0 || !ftrs || !pt_world || !T_kf_w || !T_cur_w || !depth_ref_out || !px_cur_out || batch <= 0)
+    return fail(ctx, SVOB200_ERR_ARG, "reproject_prepare: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_pt = st.add(pt_world, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_Tk = st.add(T_kf_w, nullptr, sizeof(double) * 7 * n, 0);
+  const int i_Tc = st.add(T_cur_w, nullptr, sizeof(double) * 7 * batch, 0);
+  const int i_f = st.add(ftrs, ftrs, sizeof(svob200_feature_ref) * n, 1);
+  const int i_d = st.add(nullptr, depth_ref_out, sizeof(double) * n, 2);
+  const int i_p = st.add(nullptr, px_cur_out, sizeof(double) * 2 * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_reproject_prepare(to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_pt), st.dev<double>(i_Tk), st.dev<double>(i_Tc),
+                               st.dev<double>(i_d), st.dev<double>(i_p), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "reproject_prepare launch failed");
   return st.download();
 }
 

@@ -47,3 +47,15 @@ int launch_compute_tau(int n, const double* d_T, const double* d_f, const double
 int launch_synth_render(const uint8_t* d_tex, int tex_size, double ppm, double plane_z, const DevCam& cam, int batch,
                         const double* d_T_w_f_R_c /*12 doubles per image: R row-major + c*/, uint8_t* d_out,
                         cudaStream_t s, long long* launches);
+
+// glue.cu
+int launch_features_prepare(const DevCam& cam, int n, const double* d_px, const double* d_pt, const int* d_image,
+                            const double* d_T_ref_w, double* d_f, double* d_xyz, cudaStream_t s, long long* launches);
+int launch_compose_poses(int batch, const svob200_align_result* d_res, const double* d_T_ref_w, double* d_T_cur_w,
+                         cudaStream_t s, long long* launches);
+int launch_reproject_prepare(const DevCam& cam, int n, svob200_feature_ref* d_ftrs, const double* d_pt, const double* d_T_kf_w,
+                             const double* d_T_cur_w, double* d_depth_ref, double* d_px_cur, cudaStream_t s, long long* launches);
+
+int launch_match_direct_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
+                                const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, double* d_px_out,
+                                int* d_ok_out, cudaStream_t s, long long* launches);

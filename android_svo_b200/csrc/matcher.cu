@@ -620,7 +620,8 @@ struct MatchSmem { __align__(16) uint8_t pwb[100]; __align__(16) uint8_t patch[6
 
 __global__ void __launch_bounds__(128) match_direct_kernel(const DevFrame* frames, const int* ref_slot, int cur_slot, DevCam cam, int n,
                                                            const svob200_feature_ref* ftrs, const double* depth_ref,
-                                                           const double* px_in, svob200_matcher_opts o, svob200_match_result* results)
+                                                           const double* px_in, svob200_matcher_opts o, svob200_match_result* results,
+                                                           double* px_out, int* ok_out)
 {
   __shared__ MatchSmem SM[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -628,13 +629,15 @@ __global__ void __launch_bounds__(128) match_direct_kernel(const DevFrame* frame
   if (i >= n) return;
   MatchSmem* S = &SM[warp];
   const svob200_feature_ref f = ftrs[i];
-  svob200_match_result* R = &results[i];
+  svob200_match_result* R = results ? &results[i] : nullptr;
   const DevFrame& ref = frames[(int)f.ref_frame_id];
   const DevFrame& cur = frames[cur_slot];
   double px_cur[2] = {px_in[2 * i], px_in[2 * i + 1]};
   // ref_ftr_->px.cast<int>()/(1<<level), boundary halfpatch_size_+2 (matcher.cpp:165-167)
   const int pxi = (int)f.px[0] / (1 << f.level), pyi = (int)f.px[1] / (1 << f.level);
   if (!in_frame_level(cam, pxi, pyi, 6, f.level)) {
+    if (lane == 0 && ok_out) { ok_out[i] = 0; px_out[2 * i] = px_cur[0]; px_out[2 * i + 1] = px_cur[1]; }
+    if (!R) return;
     if (lane == 0) {
       R->success = 0; R->search_level = 0; R->px_cur[0] = px_cur[0]; R->px_cur[1] = px_cur[1]; R->h_inv = 0;
       for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = 0;
@@ -664,6 +667,8 @@ __global__ void __launch_bounds__(128) match_direct_kernel(const DevFrame* frame
   } else {
     success = align2d_warp(cimg, cur.pitch[L], cur.w[L], cur.h[L], S->pwb, S->patch, o.align_max_iter, pxs, &S->al, lane);
   }
+  if (lane == 0 && ok_out) { ok_out[i] = success ? 1 : 0; px_out[2 * i] = pxs[0] * (1 << L); px_out[2 * i + 1] = pxs[1] * (1 << L); }
+  if (!R) return;
   if (lane == 0) {
     R->success = success ? 1 : 0; R->search_level = L; R->h_inv = h_inv;
     R->px_cur[0] = pxs[0] * (1 << L); R->px_cur[1] = pxs[1] * (1 << L);
@@ -728,7 +733,18 @@ int launch_match_direct(const DevFrame* d_frames, const int* d_ref_slot, int cur
                         svob200_matcher_opts opts, svob200_match_result* d_results, cudaStream_t s, long long* launches)
 {
   if (n <= 0) return 0;
-  match_direct_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, d_results);
+  match_direct_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, d_results, nullptr, nullptr);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// same kernel, compact outputs only (refined pixel + success flag): what the tracker keeps per map point
+int launch_match_direct_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
+                                const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, double* d_px_out,
+                                int* d_ok_out, cudaStream_t s, long long* launches)
+{
+  if (n <= 0) return 0;
+  match_direct_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, nullptr, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, nullptr, d_px_out, d_ok_out);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -1,0 +1,305 @@
+// tracker.cu — the per-frame front-end step as ONE C-ABI call over a batch of independent
+// sequences: pyramid -> sparse image alignment (last -> cur) -> reprojection refinement of the map
+// points against their keyframe patches -> depth-filter update of the keyframe's seeds.
+//
+// It chains the operators exactly the way FrameHandlerMono::processFrame + DepthFilter do
+// (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), minus the host-only stages that are
+// out of scope (pose_optimizer, map management): everything between the operators that the
+// reference does in host code is done by the glue kernels, so a step is 10 launches on one stream
+// with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
+// H2D of the small per-step inputs and one D2H of the per-sequence results.
+#include "ctx_internal.h"
+
+namespace {
+
+__global__ void init_pose_kernel(int batch, const double* T_last, double* T_init)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  // SparseImgAlign::run: SE3 T_cur_from_ref(cur->T_f_w_ * ref->T_f_w_.inverse()) with cur->T_f_w_ = last->T_f_w_
+  double inv[7], out[7];
+  se3_inverse(T_last + 7 * (size_t)b, inv);
+  se3_mul(T_last + 7 * (size_t)b, inv, out);
+  for (int k = 0; k < 7; ++k) T_init[7 * (size_t)b + k] = out[k];
+}
+
+// one CTA per sequence: per-sequence statistics + steady-state re-seeding of finished seeds
+__global__ void __launch_bounds__(128) step_stats_kernel(const int* ftr_off, const int* seed_off, const svob200_align_result* align,
+                                                         const double* T_cur_w, const int* match_ok, const svob200_seed_obs* obs,
+                                                         svob200_seed* seeds, svob200_seed init, int reseed, svob200_step_stats* stats)
+{
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int matched = 0, upd = 0, conv = 0, fail = 0, skipped = 0;
+  for (int i = ftr_off[b] + tid; i < ftr_off[b + 1]; i += 128) matched += match_ok[i] ? 1 : 0;
+  for (int i = seed_off[b] + tid; i < seed_off[b + 1]; i += 128) {
+    const int st = obs[i].status;
+    if (st == SVOB200_SEED_UPDATED) ++upd;
+    else if (st == SVOB200_SEED_CONVERGED) ++conv;
+    else if (st == SVOB200_SEED_NO_MATCH) ++fail;
+    else ++skipped;
+    if (reseed && (st == SVOB200_SEED_CONVERGED || st == SVOB200_SEED_NAN_ERASED)) seeds[i] = init;
+  }
+  __shared__ int s[5];
+  if (tid < 5) s[tid] = 0;
+  __syncthreads();
+  matched = warp_sum_i(matched); upd = warp_sum_i(upd); conv = warp_sum_i(conv); fail = warp_sum_i(fail); skipped = warp_sum_i(skipped);
+  if ((tid & 31) == 0) { atomicAdd(&s[0], matched); atomicAdd(&s[1], upd); atomicAdd(&s[2], conv); atomicAdd(&s[3], fail); atomicAdd(&s[4], skipped); }
+  __syncthreads();
+  if (tid == 0) {
+    svob200_step_stats* o = &stats[b];
+    for (int k = 0; k < 7; ++k) o->T_cur_w[k] = T_cur_w[7 * (size_t)b + k];
+    o->chi2 = align[b].chi2;
+    o->n_tracked = align[b].n_meas / 16;
+    o->n_matched = s[0]; o->n_seeds_updated = s[1]; o->n_seeds_converged = s[2]; o->n_seeds_failed = s[3]; o->n_seeds_skipped = s[4];
+    int it = 0;
+    for (int l = 0; l < SVOB200_MAX_LEVELS; ++l) it += align[b].iters[l];
+    o->align_iters = it;
+    o->n_exact_chi2 = align[b].n_exact_chi2;
+  }
+}
+
+template <class T> int dalloc(svob200_ctx* ctx, T** p, size_t n)
+{
+  *p = nullptr;
+  if (cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SVOB200_ERR_NOMEM, "tracker: device alloc of %zu bytes failed", sizeof(T) * n); }
+  return 0;
+}
+
+}  // namespace
+
+struct svob200_tracker {
+  svob200_ctx* ctx = nullptr;
+  svob200_camera cam{};
+  int batch = 0, n_levels = 0;
+  svob200_align_opts aopts{};
+  svob200_matcher_opts mopts{};
+  double conv_thresh = 100.0;
+  svob200_seed seed_init{};
+  int reseed = 1;
+  int64_t fid_kf = 0, fid_last = 0, fid_cur = 0;
+  int N = 0, S = 0, max_per = 0;
+  int *d_ftr_off = nullptr, *d_seed_off = nullptr, *d_ftr_image = nullptr, *d_match_ok = nullptr;
+  uint8_t* d_has_point = nullptr;
+  svob200_feature_ref *d_ftrs = nullptr, *d_seed_ftrs = nullptr;
+  double *d_pt_world = nullptr, *d_T_kf_ftr = nullptr, *d_T_kf_seed = nullptr;
+  svob200_seed* d_seeds = nullptr;
+  double *d_step_in = nullptr;      // [T_last_w 7B | last_px 2N]
+  double *d_xyz = nullptr, *d_T_init = nullptr, *d_T_cur = nullptr, *d_depth_ref = nullptr, *d_px_in = nullptr, *d_px_out = nullptr;
+  svob200_align_result* d_align = nullptr;
+  svob200_seed_obs* d_obs = nullptr;
+  svob200_step_stats* d_stats = nullptr;
+  void* d_align_scratch = nullptr;
+  uint8_t* h_pinned = nullptr; size_t h_cap = 0;
+  std::vector<void*> owned;
+};
+
+extern "C" {
+
+int svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batch, int n_levels, const svob200_align_opts* aopts,
+                           const svob200_matcher_opts* mopts, double conv_thresh, float depth_mean, float depth_min, int reseed,
+                           svob200_tracker** out)
+{
+  if (!ctx || !cam || !aopts || !mopts || !out || batch <= 0) return fail(ctx, SVOB200_ERR_ARG, "tracker_create: bad arguments");
+  static int64_t uid = 0;
+  svob200_tracker* t = new svob200_tracker();
+  t->ctx = ctx; t->cam = *cam; t->batch = batch; t->n_levels = n_levels; t->aopts = *aopts; t->mopts = *mopts;
+  t->conv_thresh = conv_thresh; t->reseed = reseed;
+  // Seed ctor depth_filter.cpp:36-45
+  t->seed_init.a = 10; t->seed_init.b = 10; t->seed_init.mu = (float)(1.0 / depth_mean); t->seed_init.z_range = (float)(1.0 / depth_min);
+  t->seed_init.sigma2 = t->seed_init.z_range * t->seed_init.z_range / 36;
+  ++uid;
+  t->fid_kf = -(uid * 4 + 1); t->fid_last = -(uid * 4 + 2); t->fid_cur = -(uid * 4 + 3);
+  for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur})
+    if (int e = svob200_frame_create(ctx, id, batch, cam->width, cam->height, n_levels)) { delete t; return e; }
+  *out = t;
+  return SVOB200_OK;
+}
+
+void svob200_tracker_destroy(svob200_tracker* t)
+{
+  if (!t) return;
+  svob200_ctx* ctx = t->ctx;
+  cudaStreamSynchronize(ctx->stream);
+  for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur}) svob200_frame_release(ctx, id);
+  for (void* p : t->owned) cudaFree(p);
+  if (t->h_pinned) cudaFreeHost(t->h_pinned);
+  delete t;
+}
+
+// Keyframe of every sequence: image, pose, map features (kf_px at level kf_level observing pt_world)
+// and depth-filter seeds (seed_px at seed_level), all in HOST memory.
+int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int stride, const double* T_kf_w, const int* ftr_offsets,
+                                 const double* kf_px, const int* kf_level, const double* pt_world, const int* seed_offsets,
+                                 const double* seed_px, const int* seed_level)
+{
+  if (!t || !imgs || !T_kf_w || !ftr_offsets || !seed_offsets) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (t->N || t->S) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_keyframe: keyframe already set (create a new tracker)");
+  const int B = t->batch;
+  if (int e = svob200_frame_upload(ctx, t->fid_kf, imgs, stride, nullptr, SVOB200_MEM_HOST)) return e;
+  const int N = ftr_offsets[B], S = seed_offsets[B];
+  t->N = N; t->S = S;
+  for (int b = 0; b < B; ++b) t->max_per = std::max(t->max_per, ftr_offsets[b + 1] - ftr_offsets[b]);
+  const int slot = svob200_frame_slot(ctx, t->fid_kf);
+  std::vector<svob200_feature_ref> ftrs(N), sftrs(S);
+  std::vector<int> image(N);
+  std::vector<double> Tf((size_t)7 * N), Ts((size_t)7 * S);
+  std::vector<svob200_seed> seeds(S, t->seed_init);
+  for (int b = 0; b < B; ++b) {
+    for (int i = ftr_offsets[b]; i < ftr_offsets[b + 1]; ++i) {
+      svob200_feature_ref& f = ftrs[i];
+      memset(&f, 0, sizeof(f));
+      f.ref_frame_id = slot; f.ref_image = b; f.cur_image = b; f.level = kf_level[i]; f.type = 0;
+      f.px[0] = kf_px[2 * i]; f.px[1] = kf_px[2 * i + 1]; f.grad[0] = 1.0; f.grad[1] = 0.0;
+      image[i] = b;
+      memcpy(&Tf[(size_t)7 * i], T_kf_w + 7 * b, 7 * sizeof(double));
+    }
+    for (int i = seed_offsets[b]; i < seed_offsets[b + 1]; ++i) {
+      svob200_feature_ref& f = sftrs[i];
+      memset(&f, 0, sizeof(f));
+      f.ref_frame_id = slot; f.ref_image = b; f.cur_image = b; f.level = seed_level[i]; f.type = 0;
+      f.px[0] = seed_px[2 * i]; f.px[1] = seed_px[2 * i + 1]; f.grad[0] = 1.0; f.grad[1] = 0.0;
+      memcpy(&Ts[(size_t)7 * i], T_kf_w + 7 * b, 7 * sizeof(double));
+    }
+  }
+#define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
+  DA(t->d_ftr_off, B + 1); DA(t->d_seed_off, B + 1); DA(t->d_ftr_image, N); DA(t->d_match_ok, N); DA(t->d_has_point, N);
+  DA(t->d_ftrs, N); DA(t->d_seed_ftrs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N); DA(t->d_T_kf_seed, 7 * (size_t)S);
+  DA(t->d_seeds, S); DA(t->d_step_in, 7 * (size_t)B + 2 * (size_t)N); DA(t->d_xyz, 3 * (size_t)N); DA(t->d_T_init, 7 * (size_t)B);
+  DA(t->d_T_cur, 7 * (size_t)B); DA(t->d_depth_ref, N); DA(t->d_px_in, 2 * (size_t)N); DA(t->d_px_out, 2 * (size_t)N);
+  DA(t->d_align, B); DA(t->d_obs, S); DA(t->d_stats, B);
+  {
+    uint8_t* p = nullptr;
+    if (int e = dalloc(ctx, &p, sparse_align_scratch_bytes(N))) return e;
+    t->owned.push_back(p); t->d_align_scratch = p;
+  }
+#undef DA
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(t->d_ftr_off, ftr_offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_seed_off, seed_offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_ftr_image, image.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(t->d_has_point, 1, N ? N : 1, s));
+  CU(cudaMemcpyAsync(t->d_ftrs, ftrs.data(), sizeof(svob200_feature_ref) * N, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_seed_ftrs, sftrs.data(), sizeof(svob200_feature_ref) * S, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_pt_world, pt_world, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_T_kf_ftr, Tf.data(), sizeof(double) * 7 * N, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_T_kf_seed, Ts.data(), sizeof(double) * 7 * S, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_seeds, seeds.data(), sizeof(svob200_seed) * S, cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  // Feature ctor: f = cam2world(px), for map features and seed features (device, bit-identical to the host formula)
+  {
+    std::vector<double> px(2 * (size_t)std::max(N, S)), f(3 * (size_t)std::max(N, S)), dummy_pt(3 * (size_t)std::max(N, S), 0.0), xyz(3 * (size_t)std::max(N, S));
+    std::vector<int> img0(std::max(N, S), 0);
+    const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+    for (int pass = 0; pass < 2; ++pass) {
+      const int n = pass == 0 ? N : S;
+      std::vector<svob200_feature_ref>& v = pass == 0 ? ftrs : sftrs;
+      if (!n) continue;
+      for (int i = 0; i < n; ++i) { px[2 * i] = v[i].px[0]; px[2 * i + 1] = v[i].px[1]; }
+      if (int e = svob200_features_prepare(ctx, &t->cam, n, px.data(), dummy_pt.data(), img0.data(), 1, ident, f.data(), xyz.data(), SVOB200_MEM_HOST)) return e;
+      for (int i = 0; i < n; ++i) { v[i].f[0] = f[3 * i]; v[i].f[1] = f[3 * i + 1]; v[i].f[2] = f[3 * i + 2]; }
+      CU(cudaMemcpyAsync(pass == 0 ? t->d_ftrs : t->d_seed_ftrs, v.data(), sizeof(svob200_feature_ref) * n, cudaMemcpyHostToDevice, s));
+      CU(cudaStreamSynchronize(s));
+    }
+  }
+  return SVOB200_OK;
+}
+
+int svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride, int mem)
+{
+  if (!t || !imgs) return SVOB200_ERR_ARG;
+  return svob200_frame_upload(t->ctx, t->fid_last, imgs, stride, nullptr, mem);
+}
+
+int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride, const double* T_last_w, const double* last_px,
+                         svob200_step_stats* stats, double* px_refined, int* match_ok, int mem)
+{
+  if (!t || !cur_imgs || !T_last_w || !last_px) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (!t->d_stats) return fail(ctx, SVOB200_ERR_ARG, "tracker_step: set_keyframe first");
+  const int B = t->batch, N = t->N, S = t->S;
+  cudaStream_t s = ctx->stream;
+  const DevCam cam = to_cam(&t->cam);
+  // 1. current frame: level 0 in place (device) or one H2D copy (host), then the fused pyramid kernel
+  if (mem == SVOB200_MEM_DEVICE) { if (int e = svob200_frame_bind(ctx, t->fid_cur, cur_imgs, stride, nullptr)) return e; }
+  else {
+    FrameRec* r = find_frame(ctx, t->fid_cur);
+    if (r->f.lvl[0] != r->own_l0) {   // drop an earlier device binding
+      r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
+      CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, s));
+    }
+    CU(cudaMemcpy2DAsync(r->f.lvl[0], r->f.pitch[0], cur_imgs, stride, r->f.w[0], (size_t)r->f.h[0] * B, cudaMemcpyHostToDevice, s));
+    int modes[SVOB200_MAX_LEVELS];
+    for (int l = 0; l + 1 < r->f.n_levels; ++l) modes[l] = svob200_round_mode_x86(r->f.w[l]);
+    if (launch_pyramid(r->f, modes, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: pyramid launch failed");
+  }
+  // 2. small per-step inputs
+  const size_t in_bytes = sizeof(double) * (7 * (size_t)B + 2 * (size_t)N);
+  const double* d_T_last; const double* d_last_px;
+  if (mem == SVOB200_MEM_DEVICE) { d_T_last = T_last_w; d_last_px = last_px; }
+  else {
+    const size_t out_bytes = sizeof(svob200_step_stats) * B + sizeof(double) * 2 * (size_t)N + sizeof(int) * (size_t)N;
+    if (t->h_cap < in_bytes + out_bytes + 512) {
+      if (t->h_pinned) cudaFreeHost(t->h_pinned);
+      t->h_pinned = nullptr; t->h_cap = 0;
+      CU(cudaMallocHost((void**)&t->h_pinned, in_bytes + out_bytes + 512));
+      t->h_cap = in_bytes + out_bytes + 512;
+    }
+    memcpy(t->h_pinned, T_last_w, sizeof(double) * 7 * B);
+    memcpy(t->h_pinned + sizeof(double) * 7 * B, last_px, sizeof(double) * 2 * (size_t)N);
+    CU(cudaMemcpyAsync(t->d_step_in, t->h_pinned, in_bytes, cudaMemcpyHostToDevice, s));
+    d_T_last = t->d_step_in; d_last_px = t->d_step_in + 7 * (size_t)B;
+  }
+  FrameRec* last = find_frame(ctx, t->fid_last);
+  FrameRec* cur = find_frame(ctx, t->fid_cur);
+  // 3. Feature/xyz_ref of the last frame's features, initial relative pose
+  if (launch_features_prepare(cam, N, d_last_px, t->d_pt_world, t->d_ftr_image, d_T_last, nullptr, t->d_xyz, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: features_prepare failed");
+  init_pose_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, d_T_last, t->d_T_init); ++ctx->launches;
+  // 4. SparseImgAlign::run(last, cur)
+  if (launch_sparse_align(last->f, cur->f, cam, B, N, t->max_per, t->d_ftr_off, d_last_px, t->d_xyz, t->d_has_point, t->d_T_init, t->aopts,
+                          t->d_align, t->d_align_scratch, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: sparse_align failed");
+  // 5. cur.T_f_w = T_cur_from_ref * last.T_f_w ; reprojection of the map points
+  if (launch_compose_poses(B, t->d_align, d_T_last, t->d_T_cur, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: compose failed");
+  if (launch_reproject_prepare(cam, N, t->d_ftrs, t->d_pt_world, t->d_T_kf_ftr, t->d_T_cur, t->d_depth_ref, t->d_px_in, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
+  // 6. Matcher::findMatchDirect per map point (keyframe patch -> current frame)
+  if (launch_match_direct_compact(ctx->d_table, cur->slot, cam, N, t->d_ftrs, t->d_depth_ref, t->d_px_in, t->mopts, t->d_px_out, t->d_match_ok, s, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
+  // 7. DepthFilter::updateSeeds(cur)
+  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, S, t->d_seed_ftrs, t->d_T_kf_seed, t->d_T_cur, t->mopts, t->conv_thresh, t->d_seeds, t->d_obs, s, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
+  // 8. per-sequence statistics (+ steady-state re-seeding)
+  step_stats_kernel<<<B, 128, 0, s>>>(t->d_ftr_off, t->d_seed_off, t->d_align, t->d_T_cur, t->d_match_ok, t->d_obs, t->d_seeds, t->seed_init, t->reseed, t->d_stats);
+  ++ctx->launches;
+  if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
+  // 9. results
+  if (mem == SVOB200_MEM_DEVICE) {
+    if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
+    if (px_refined) CU(cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s));
+    if (match_ok) CU(cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s));
+  } else {
+    uint8_t* ho = t->h_pinned + ((in_bytes + 255) & ~(size_t)255);
+    uint8_t* h_stats = ho; uint8_t* h_px = h_stats + sizeof(svob200_step_stats) * B; uint8_t* h_ok = h_px + sizeof(double) * 2 * (size_t)N;
+    if (stats) CU(cudaMemcpyAsync(h_stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToHost, s));
+    if (px_refined) CU(cudaMemcpyAsync(h_px, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (match_ok) CU(cudaMemcpyAsync(h_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) memcpy(stats, h_stats, sizeof(svob200_step_stats) * B);
+    if (px_refined) memcpy(px_refined, h_px, sizeof(double) * 2 * (size_t)N);
+    if (match_ok) memcpy(match_ok, h_ok, sizeof(int) * (size_t)N);
+  }
+  std::swap(t->fid_last, t->fid_cur);       // the current frame becomes the last frame
+  return SVOB200_OK;
+}
+
+int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
+{
+  if (!t || !out) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  CU(cudaMemcpyAsync(out, t->d_seeds, sizeof(svob200_seed) * (size_t)t->S, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+int svob200_tracker_launches_per_step(void) { return 10; }
+
+}  // extern "C"

@@ -12,12 +12,14 @@ import numpy as np
 
 CONFIGS = {
     # name: (width, height, fx, fy, cx, cy, n_levels, n_features, n_seeds, align_max_level, align_min_level)
-    "C2": dict(w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, n_levels=4, n_features=120, n_seeds=768,
-               max_level=3, min_level=2, detect_levels=3),
-    "C3": dict(w=752, h=480, fx=458.0, fy=458.0, cx=367.2, cy=248.4, n_levels=5, n_features=300, n_seeds=2000,
-               max_level=4, min_level=2, detect_levels=3),
-    "C4": dict(w=1920, h=1080, fx=1500.0, fy=1500.0, cx=959.5, cy=539.5, n_levels=5, n_features=1000, n_seeds=10000,
-               max_level=4, min_level=2, detect_levels=3),
+    # n_levels = pyramid depth = max(nPyrLevels, kltMaxLevel+1) (frame.cpp:63); n_pyr = Config::nPyrLevels()
+    # (detector levels and search-level cap); max/min_level = kltMaxLevel / kltMinLevel
+    "C2": dict(w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, n_levels=4, n_pyr=4, n_features=120, n_seeds=768,
+               max_level=3, min_level=2),
+    "C3": dict(w=752, h=480, fx=458.0, fy=458.0, cx=367.2, cy=248.4, n_levels=5, n_pyr=5, n_features=300, n_seeds=2000,
+               max_level=4, min_level=2),
+    "C4": dict(w=1920, h=1080, fx=1500.0, fy=1500.0, cx=959.5, cy=539.5, n_levels=5, n_pyr=5, n_features=1000, n_seeds=10000,
+               max_level=4, min_level=2),
 }
 CONFIGS["C1"] = CONFIGS["C2"]
 CONFIGS["C5"] = CONFIGS["C2"]

@@ -197,6 +197,61 @@ int svob200_update_seed(svob200_ctx* ctx, int n, const float* x, const float* ta
 int svob200_compute_tau(svob200_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z,
                         double px_error_angle, double* tau_out);
 
+/* ---------------------------------------------------------------- glue between the operators
+ * The few lines of host code that sit between the operators in the reference, as device kernels, so
+ * a whole front-end step can stay on one stream (bit-identical arithmetic):
+ *   features_prepare   f = cam2world(px) (feature.h:43-51); depth = |pos - ref_pos|; xyz_ref = f*depth
+ *                      (sparse_img_align.cpp:132-134).  image[i] selects the T_ref_w of feature i.
+ *   compose_poses      cur.T_f_w = T_cur_from_ref * ref.T_f_w (sparse_img_align.cpp:89)
+ *   reproject_prepare  px = cur.w2c(point.pos) (reprojector.cpp:131-145); depth_ref = |ref.pos()-pt.pos|
+ *                      and T_cur_ref = cur.T_f_w * ref.T_f_w^-1 (matcher.cpp:169-173); writes
+ *                      ftrs[i].T_cur_ref.  T_kf_w: 7 doubles per feature (pose of its keyframe). */
+int svob200_features_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n, const double* px,
+                             const double* pt_world, const int* image, int batch, const double* T_ref_w,
+                             double* f_out /*may be NULL*/, double* xyz_ref_out, int mem);
+int svob200_compose_poses(svob200_ctx* ctx, int batch, const svob200_align_result* results,
+                          const double* T_ref_w, double* T_cur_w, int mem);
+int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n, svob200_feature_ref* ftrs,
+                              const double* pt_world, const double* T_kf_w, int batch, const double* T_cur_w,
+                              double* depth_ref_out, double* px_cur_out, int mem);
+
+/* ---------------------------------------------------------------- tracker: one front-end step per call
+ * The chain FrameHandlerMono::processFrame + DepthFilter::updateSeeds run per frame
+ * (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), restricted to the hot-path operators:
+ *   pyramid(cur) -> SparseImgAlign::run(last, cur) -> Matcher::findMatchDirect for every map point of
+ *   the keyframe -> DepthFilter::updateSeeds(cur) for the keyframe's seeds,
+ * for a batch of independent sequences, 10 kernel launches on one stream, no host round trip.
+ * Finished seeds (converged / NaN) are re-initialised when `reseed` is set, which keeps the
+ * per-frame workload stationary for benchmarking (0 = leave them, the caller mutates its list). */
+typedef struct svob200_tracker svob200_tracker;
+typedef struct {
+  double T_cur_w[7];       /* pose after sparse alignment */
+  double chi2;
+  int n_tracked;           /* SparseImgAlign::run return value */
+  int n_matched;           /* successful findMatchDirect */
+  int n_seeds_updated, n_seeds_converged, n_seeds_failed, n_seeds_skipped;
+  int align_iters, n_exact_chi2;
+} svob200_step_stats;
+int  svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batch, int n_levels,
+                            const svob200_align_opts* aopts, const svob200_matcher_opts* mopts,
+                            double seed_convergence_sigma2_thresh, float depth_mean, float depth_min, int reseed,
+                            svob200_tracker** out);
+void svob200_tracker_destroy(svob200_tracker* t);
+/* all arguments in host memory; offsets are batch+1 prefix sums */
+int  svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int stride, const double* T_kf_w,
+                                  const int* ftr_offsets, const double* kf_px, const int* kf_level,
+                                  const double* pt_world, const int* seed_offsets, const double* seed_px,
+                                  const int* seed_level);
+int  svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride, int mem);
+/* cur_imgs: batch images; T_last_w: 7 doubles per sequence (pose of the last frame); last_px: 2 doubles
+ * per map feature (its pixel in the last frame).  stats (batch), px_refined (2 per feature), match_ok
+ * (1 per feature) may be NULL.  mem tells where ALL pointer arguments live; in device mode level 0 of
+ * the current frame aliases cur_imgs (which must stay valid through the next step) and nothing syncs. */
+int  svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride, const double* T_last_w,
+                          const double* last_px, svob200_step_stats* stats, double* px_refined, int* match_ok, int mem);
+int  svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out /*host*/);
+int  svob200_tracker_launches_per_step(void);
+
 /* ---------------------------------------------------------------- device-side helpers for the
  * resident ("value") path and the synthetic bench: raw device allocations and a plane renderer.
  * Not part of the reference surface. */

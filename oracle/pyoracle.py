@@ -527,3 +527,100 @@ class Ref:
                                       _p(cam.wh(), c_ip), _p(cam.k(), c_dp), S, _p(i32(seed_ref), c_ip), _p(f64(px), c_dp),
                                       _p(i32(level), c_ip), _p(st, c_fp), _p(status, c_ip), float(conv_thresh))
         return st.reshape(S, 5), status
+
+
+class StepStats(C.Structure):
+    _fields_ = [("T_cur_w", C.c_double * 7), ("chi2", C.c_double), ("n_tracked", C.c_int), ("n_matched", C.c_int),
+                ("n_seeds_updated", C.c_int), ("n_seeds_converged", C.c_int), ("n_seeds_failed", C.c_int),
+                ("n_seeds_skipped", C.c_int), ("align_iters", C.c_int), ("n_exact_chi2", C.c_int)]
+
+
+class _SeqBase:
+    """One sequence stepped frame by frame: pyramid -> sparse align -> reprojection refinement -> seed update."""
+
+    def step(self, cur_img, T_last_w, last_px, want_px=False):
+        cur_img = u8(cur_img)
+        last_px = f64(last_px)
+        st = StepStats()
+        n = self.N
+        px = np.zeros((n, 2)) if want_px else None
+        ok = np.zeros(n, np.int32) if want_px else None
+        self._step(self.h, _p(cur_img, c_u8p), _p(f64(T_last_w), c_dp), _p(last_px, c_dp), C.byref(st),
+                   _p(px, c_dp) if want_px else None, _p(ok, c_ip) if want_px else None)
+        return (st, px, ok) if want_px else st
+
+
+class OracleSeq(_SeqBase):
+    def __init__(self, oracle, cam, n_levels, max_level, min_level, n_pyr_levels_cfg, conv_thresh=100.0, depth_mean=2.4,
+                 depth_min=1.2, reseed=1, n_iter=30):
+        self.lib = L = oracle.lib
+        L.svo_oracle_seq_create.restype = C.c_void_p
+        L.svo_oracle_seq_create.argtypes = [C.POINTER(Cam), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, C.c_int]
+        L.svo_oracle_seq_destroy.argtypes = [C.c_void_p]
+        L.svo_oracle_seq_set_keyframe.argtypes = [C.c_void_p, c_u8p, c_dp, C.c_int, c_dp, c_ip, c_dp, C.c_int, c_dp, c_ip]
+        L.svo_oracle_seq_set_last.argtypes = [C.c_void_p, c_u8p]
+        L.svo_oracle_seq_step.argtypes = [C.c_void_p, c_u8p, c_dp, c_dp, C.POINTER(StepStats), c_dp, c_ip]
+        L.svo_oracle_seq_get_seeds.argtypes = [C.c_void_p, C.POINTER(Seed)]
+        self.h = L.svo_oracle_seq_create(C.byref(cam), n_levels, max_level, min_level, n_iter, n_pyr_levels_cfg, conv_thresh,
+                                         depth_mean, depth_min, reseed)
+        self._step = L.svo_oracle_seq_step
+        self.N = self.S = 0
+
+    def set_keyframe(self, img, T_kf_w, kf_px, kf_level, pt_world, seed_px, seed_level):
+        self.N, self.S = len(kf_level), len(seed_level)
+        self.lib.svo_oracle_seq_set_keyframe(self.h, _p(u8(img), c_u8p), _p(f64(T_kf_w), c_dp), self.N, _p(f64(kf_px), c_dp),
+                                             _p(i32(kf_level), c_ip), _p(f64(pt_world), c_dp), self.S, _p(f64(seed_px), c_dp),
+                                             _p(i32(seed_level), c_ip))
+
+    def set_last(self, img):
+        self.lib.svo_oracle_seq_set_last(self.h, _p(u8(img), c_u8p))
+
+    def seeds(self):
+        arr = (Seed * max(self.S, 1))()
+        self.lib.svo_oracle_seq_get_seeds(self.h, arr)
+        return np.array([(s.a, s.b, s.mu, s.z_range, s.sigma2) for s in arr[:self.S]], np.float32).reshape(self.S, 5)
+
+    def close(self):
+        if self.h:
+            self.lib.svo_oracle_seq_destroy(self.h)
+            self.h = None
+
+
+class RefSeq(_SeqBase):
+    """Same step through the real reference classes (oracle/_ref/libsvo_ref.so)."""
+
+    def __init__(self, ref, cam, n_levels, max_level, min_level, n_pyr_levels_cfg, conv_thresh=100.0, depth_mean=2.4,
+                 depth_min=1.2, reseed=1, n_iter=30):
+        self.lib = L = ref.lib
+        L.svo_ref_seq_create.restype = C.c_void_p
+        L.svo_ref_seq_create.argtypes = [c_ip, c_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, C.c_int]
+        L.svo_ref_seq_destroy.argtypes = [C.c_void_p]
+        L.svo_ref_seq_set_keyframe.argtypes = [C.c_void_p, c_u8p, c_dp, C.c_int, c_dp, c_ip, c_dp, C.c_int, c_dp, c_ip]
+        L.svo_ref_seq_set_last.argtypes = [C.c_void_p, c_u8p]
+        L.svo_ref_seq_step.argtypes = [C.c_void_p, c_u8p, c_dp, c_dp, C.POINTER(StepStats), c_dp, c_ip]
+        L.svo_ref_seq_get_seeds.argtypes = [C.c_void_p, c_fp]
+        # Config is a process-wide singleton in the reference: pyramid depth = max(nPyrLevels, kltMaxLevel+1)
+        ref.config(n_pyr_levels_cfg, n_levels - 1, min_level)
+        self.h = L.svo_ref_seq_create(_p(cam.wh(), c_ip), _p(cam.k(), c_dp), max_level, min_level, n_iter, conv_thresh,
+                                      depth_mean, depth_min, reseed)
+        self._step = L.svo_ref_seq_step
+        self.N = self.S = 0
+
+    def set_keyframe(self, img, T_kf_w, kf_px, kf_level, pt_world, seed_px, seed_level):
+        self.N, self.S = len(kf_level), len(seed_level)
+        self.lib.svo_ref_seq_set_keyframe(self.h, _p(u8(img), c_u8p), _p(f64(T_kf_w), c_dp), self.N, _p(f64(kf_px), c_dp),
+                                          _p(i32(kf_level), c_ip), _p(f64(pt_world), c_dp), self.S, _p(f64(seed_px), c_dp),
+                                          _p(i32(seed_level), c_ip))
+
+    def set_last(self, img):
+        self.lib.svo_ref_seq_set_last(self.h, _p(u8(img), c_u8p))
+
+    def seeds(self):
+        out = np.zeros((max(self.S, 1), 5), np.float32)
+        self.lib.svo_ref_seq_get_seeds(self.h, _p(out, c_fp))
+        return out[:self.S]
+
+    def close(self):
+        if self.h:
+            self.lib.svo_ref_seq_destroy(self.h)
+            self.h = None

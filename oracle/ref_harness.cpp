@@ -423,4 +423,139 @@ int svo_ref_update_seeds(int n_ref, const uint8_t* const* ref_imgs, const double
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One front-end step per frame with the reference's own operators, chained the way
+// FrameHandlerMono::processFrame + DepthFilter do (frame_handler_mono.cpp:171-262,
+// depth_filter.cpp:237-341) minus pose_optimizer / map management:
+//   new Frame (pyramid) -> SparseImgAlign::run(last, cur) -> Matcher::findMatchDirect per map point
+//   -> DepthFilter::addFrame(cur) (synchronous updateSeeds).
+struct svo_ref_step_stats {
+  double T_cur_w[7];
+  double chi2;
+  int n_tracked, n_matched, n_seeds_updated, n_seeds_converged, n_seeds_failed, n_seeds_skipped;
+  int align_iters, n_exact_chi2;
+};
+
+struct RefSeq {
+  vk::PinholeCamera* cam;
+  FramePtr kf, last;
+  std::vector<Point*> pts;
+  std::vector<Feature*> seed_ftrs;
+  std::map<Feature*, int> seed_index;
+  DepthFilter* df;
+  Matcher matcher;
+  int max_level, min_level, n_iter, reseed;
+  float depth_mean, depth_min;
+  std::vector<Point*> conv_points;
+};
+
+void* svo_ref_seq_create(const int* wh, const double* k, int max_level, int min_level, int n_iter, double conv_thresh,
+                         float depth_mean, float depth_min, int reseed)
+{
+  RefSeq* s = new RefSeq();
+  s->cam = make_cam(wh, k);
+  s->max_level = max_level; s->min_level = min_level; s->n_iter = n_iter; s->reseed = reseed;
+  s->depth_mean = depth_mean; s->depth_min = depth_min;
+  s->df = new DepthFilter(feature_detection::DetectorPtr(), [s](Point* p, double) { s->conv_points.push_back(p); });
+  s->df->options_.seed_convergence_sigma2_thresh = conv_thresh;
+  return s;
+}
+
+void svo_ref_seq_destroy(void* h)
+{
+  RefSeq* s = (RefSeq*)h;
+  s->df->getSeeds().clear();
+  delete s->df;
+  for (auto f : s->seed_ftrs) delete f;
+  s->kf.reset(); s->last.reset();          // ~Frame deletes its features
+  for (auto p : s->pts) { p->obs_.clear(); delete p; }
+  delete s->cam;
+  delete s;
+}
+
+void svo_ref_seq_set_keyframe(void* h, const uint8_t* img, const double* T_kf_w, int N, const double* kf_px, const int* kf_level,
+                              const double* pt_world, int S, const double* seed_px, const int* seed_level)
+{
+  RefSeq* s = (RefSeq*)h;
+  s->kf.reset(new Frame(s->cam, aligned_copy(img, s->cam->width(), s->cam->height()), 0.0));
+  s->kf->T_f_w_ = to_se3(T_kf_w);
+  for (int i = 0; i < N; ++i) {
+    Point* pt = new Point(Vector3d(pt_world[3 * i], pt_world[3 * i + 1], pt_world[3 * i + 2]));
+    Feature* f = new Feature(s->kf.get(), Vector2d(kf_px[2 * i], kf_px[2 * i + 1]), kf_level[i]);
+    f->point = pt;
+    pt->addFrameRef(f);
+    s->kf->addFeature(f);
+    s->pts.push_back(pt);
+  }
+  Seed::batch_counter = 0;
+  for (int i = 0; i < S; ++i) {
+    Feature* f = new Feature(s->kf.get(), Vector2d(seed_px[2 * i], seed_px[2 * i + 1]), seed_level[i]);
+    s->seed_ftrs.push_back(f);
+    s->seed_index[f] = i;
+    s->df->getSeeds().push_back(Seed(f, s->depth_mean, s->depth_min));
+  }
+}
+
+void svo_ref_seq_set_last(void* h, const uint8_t* img)
+{
+  RefSeq* s = (RefSeq*)h;
+  s->last.reset(new Frame(s->cam, aligned_copy(img, s->cam->width(), s->cam->height()), 0.0));
+}
+
+void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, const double* last_px,
+                      svo_ref_step_stats* st, double* px_refined, int* match_ok)
+{
+  RefSeq* s = (RefSeq*)h;
+  memset(st, 0, sizeof(*st));
+  FramePtr cur(new Frame(s->cam, aligned_copy(cur_img, s->cam->width(), s->cam->height()), 1.0));
+  FramePtr last = s->last;
+  last->T_f_w_ = to_se3(T_last_w);
+  for (auto f : last->fts_) delete f;
+  last->fts_.clear();
+  const int N = (int)s->pts.size();
+  for (int i = 0; i < N; ++i) {
+    Feature* f = new Feature(last.get(), Vector2d(last_px[2 * i], last_px[2 * i + 1]), 0);
+    f->point = s->pts[i];
+    last->fts_.push_back(f);
+  }
+  cur->T_f_w_ = last->T_f_w_;                                       // frame_handler_mono.cpp:175
+  AlignProbe al(s->max_level, s->min_level, s->n_iter);
+  st->n_tracked = (int)al.run(last, cur);
+  st->chi2 = al.chi2();
+  for (size_t l = 0; l < al.evals.size(); ++l) st->align_iters += al.evals[l];
+  from_se3(cur->T_f_w_, st->T_cur_w);
+  for (int i = 0; i < N; ++i) {
+    Vector2d px(cur->w2c(s->pts[i]->pos_));                         // reprojector.cpp:131-145
+    const bool ok = s->matcher.findMatchDirect(*s->pts[i], *cur, px);
+    st->n_matched += ok ? 1 : 0;
+    if (px_refined) { px_refined[2 * i] = px[0]; px_refined[2 * i + 1] = px[1]; }
+    if (match_ok) match_ok[i] = ok ? 1 : 0;
+  }
+  s->conv_points.clear();
+  s->df->addFrame(cur);                                             // synchronous updateSeeds
+  st->n_seeds_converged = (int)s->conv_points.size();
+  st->n_seeds_updated = st->n_seeds_failed = st->n_seeds_skipped = -1;   // not observable through the reference API
+  std::vector<Feature*> finished;
+  for (auto p : s->conv_points) { Feature* f = p->obs_.front(); f->point = NULL; p->obs_.clear(); delete p; finished.push_back(f); }
+  if ((int)s->df->getSeeds().size() + (int)finished.size() != (int)s->seed_ftrs.size()) {
+    std::map<Feature*, char> seen;                                   // seeds erased because z_inv_min was NaN
+    for (auto& sd : s->df->getSeeds()) seen[sd.ftr] = 1;
+    for (auto f : finished) seen[f] = 1;
+    for (auto f : s->seed_ftrs) if (!seen.count(f)) finished.push_back(f);
+  }
+  if (s->reseed) for (auto f : finished) s->df->getSeeds().push_back(Seed(f, s->depth_mean, s->depth_min));
+  s->last = cur;
+}
+
+// state of every seed by original index; seeds no longer in the list get a = -1
+void svo_ref_seq_get_seeds(void* h, float* out /*5 per seed*/)
+{
+  RefSeq* s = (RefSeq*)h;
+  for (size_t i = 0; i < s->seed_ftrs.size(); ++i) out[5 * i] = -1.f;
+  for (auto& sd : s->df->getSeeds()) {
+    const int i = s->seed_index[sd.ftr];
+    out[5 * i] = sd.a; out[5 * i + 1] = sd.b; out[5 * i + 2] = sd.mu; out[5 * i + 3] = sd.z_range; out[5 * i + 4] = sd.sigma2;
+  }
+}
+
 }  // extern "C"

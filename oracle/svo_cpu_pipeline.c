@@ -1,0 +1,191 @@
+/*
+ * svo_cpu_pipeline.c — CPU restatement of one front-end step per frame, built from the oracle's
+ * operator restatements (svo_oracle.c).  TEST INFRASTRUCTURE ONLY: the checker for
+ * svob200_tracker_step and the "port" CPU baseline of bench.py.
+ *
+ * A step chains the reference's hot-path operators the way FrameHandlerMono::processFrame and
+ * DepthFilter::updateSeeds do (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), without
+ * the host-only stages that are out of scope (pose_optimizer, map management):
+ *   Frame ctor (pyramid) -> SparseImgAlign::run(last, cur) -> cur.T_f_w = T_cur_from_ref * last.T_f_w
+ *   -> for every map point: px = cur.w2c(pos); Matcher::findMatchDirect(kf patch -> cur)
+ *   -> DepthFilter::updateSeeds(cur) over the keyframe's seeds.
+ * Finished seeds are re-initialised when `reseed` is set (stationary benchmark workload).
+ */
+#include "svo_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+typedef struct {
+  double T_cur_w[7];
+  double chi2;
+  int n_tracked, n_matched, n_seeds_updated, n_seeds_converged, n_seeds_failed, n_seeds_skipped;
+  int align_iters, n_exact_chi2;
+} svo_step_stats;
+
+typedef struct svo_seq {
+  svo_cam cam;
+  int n_levels, w, h;
+  svo_align_opts aopts;
+  svo_matcher_opts mopts;
+  double conv_thresh;
+  svo_seed seed_init;
+  int reseed;
+  /* frames: level 0 + upper levels, dense */
+  uint8_t *kf0, *kfu, *last0, *lastu, *cur0, *curu;
+  svo_pyr kf, last, cur;
+  double T_kf_w[7];
+  int N, S;
+  double *kf_px, *kf_f, *pt_world; int* kf_level;
+  double *seed_px, *seed_f; int* seed_level; svo_seed* seeds;
+  /* per-step scratch */
+  double *xyz; uint8_t* has_point;
+} svo_seq;
+
+static void build_frame(svo_seq* s, const uint8_t* img, uint8_t* l0, uint8_t* up, svo_pyr* p)
+{
+  memcpy(l0, img, (size_t)s->w * s->h);
+  svo_oracle_build_pyramid(l0, s->w, s->h, s->n_levels, NULL, up);
+  svo_oracle_make_pyr(p, l0, up, s->w, s->h, s->n_levels);
+}
+
+svo_seq* svo_oracle_seq_create(const svo_cam* cam, int n_levels, int align_max_level, int align_min_level, int n_iter,
+                               int n_pyr_levels_cfg, double conv_thresh, float depth_mean, float depth_min, int reseed)
+{
+  svo_seq* s = (svo_seq*)calloc(1, sizeof(svo_seq));
+  s->cam = *cam; s->n_levels = n_levels; s->w = cam->width; s->h = cam->height;
+  s->aopts.max_level = align_max_level; s->aopts.min_level = align_min_level; s->aopts.n_iter = n_iter; s->aopts.eps = 0.000001;
+  svo_oracle_matcher_opts_default(&s->mopts, n_pyr_levels_cfg);
+  s->conv_thresh = conv_thresh; s->reseed = reseed;
+  svo_oracle_seed_init(&s->seed_init, depth_mean, depth_min);
+  const size_t l0 = (size_t)s->w * s->h, up = svo_oracle_pyramid_bytes(s->w, s->h, n_levels) + 16;
+  s->kf0 = (uint8_t*)malloc(l0); s->kfu = (uint8_t*)malloc(up);
+  s->last0 = (uint8_t*)malloc(l0); s->lastu = (uint8_t*)malloc(up);
+  s->cur0 = (uint8_t*)malloc(l0); s->curu = (uint8_t*)malloc(up);
+  return s;
+}
+
+void svo_oracle_seq_destroy(svo_seq* s)
+{
+  if (!s) return;
+  free(s->kf0); free(s->kfu); free(s->last0); free(s->lastu); free(s->cur0); free(s->curu);
+  free(s->kf_px); free(s->kf_f); free(s->pt_world); free(s->kf_level);
+  free(s->seed_px); free(s->seed_f); free(s->seed_level); free(s->seeds); free(s->xyz); free(s->has_point);
+  free(s);
+}
+
+void svo_oracle_seq_set_keyframe(svo_seq* s, const uint8_t* img, const double* T_kf_w, int N, const double* kf_px,
+                                 const int* kf_level, const double* pt_world, int S, const double* seed_px, const int* seed_level)
+{
+  build_frame(s, img, s->kf0, s->kfu, &s->kf);
+  memcpy(s->T_kf_w, T_kf_w, sizeof(s->T_kf_w));
+  s->N = N; s->S = S;
+  s->kf_px = (double*)malloc(sizeof(double) * 2 * (N + 1)); s->kf_f = (double*)malloc(sizeof(double) * 3 * (N + 1));
+  s->pt_world = (double*)malloc(sizeof(double) * 3 * (N + 1)); s->kf_level = (int*)malloc(sizeof(int) * (N + 1));
+  s->seed_px = (double*)malloc(sizeof(double) * 2 * (S + 1)); s->seed_f = (double*)malloc(sizeof(double) * 3 * (S + 1));
+  s->seed_level = (int*)malloc(sizeof(int) * (S + 1)); s->seeds = (svo_seed*)malloc(sizeof(svo_seed) * (S + 1));
+  s->xyz = (double*)malloc(sizeof(double) * 3 * (N + 1)); s->has_point = (uint8_t*)malloc(N + 1);
+  memcpy(s->kf_px, kf_px, sizeof(double) * 2 * N); memcpy(s->pt_world, pt_world, sizeof(double) * 3 * N);
+  memcpy(s->kf_level, kf_level, sizeof(int) * N);
+  memcpy(s->seed_px, seed_px, sizeof(double) * 2 * S); memcpy(s->seed_level, seed_level, sizeof(int) * S);
+  for (int i = 0; i < N; ++i) { svo_oracle_cam2world(&s->cam, kf_px[2 * i], kf_px[2 * i + 1], s->kf_f + 3 * i); s->has_point[i] = 1; }
+  for (int i = 0; i < S; ++i) { svo_oracle_cam2world(&s->cam, seed_px[2 * i], seed_px[2 * i + 1], s->seed_f + 3 * i); s->seeds[i] = s->seed_init; }
+}
+
+void svo_oracle_seq_set_last(svo_seq* s, const uint8_t* img) { build_frame(s, img, s->last0, s->lastu, &s->last); }
+
+static double norm3d(double x, double y, double z) { return sqrt((x * x + y * y) + z * z); }
+
+void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_last_w, const double* last_px,
+                         svo_step_stats* st, double* px_refined, int* match_ok)
+{
+  memset(st, 0, sizeof(*st));
+  build_frame(s, cur_img, s->cur0, s->curu, &s->cur);
+  /* Feature ctor + sparse_img_align.cpp:132-134 */
+  double Tlw_inv[7];
+  svo_oracle_se3_inverse(T_last_w, Tlw_inv);
+  for (int i = 0; i < s->N; ++i) {
+    double f[3];
+    svo_oracle_cam2world(&s->cam, last_px[2 * i], last_px[2 * i + 1], f);
+    const double depth = norm3d(s->pt_world[3 * i] - Tlw_inv[0], s->pt_world[3 * i + 1] - Tlw_inv[1], s->pt_world[3 * i + 2] - Tlw_inv[2]);
+    s->xyz[3 * i] = f[0] * depth; s->xyz[3 * i + 1] = f[1] * depth; s->xyz[3 * i + 2] = f[2] * depth;
+  }
+  double T_init[7];
+  svo_oracle_se3_mul(T_last_w, Tlw_inv, T_init);          /* cur->T_f_w_ = last->T_f_w_ */
+  svo_align_result ar;
+  st->n_tracked = svo_oracle_sparse_align(&s->last, &s->cur, &s->cam, s->N, last_px, s->xyz, s->has_point, T_init, &s->aopts, &ar);
+  st->chi2 = ar.chi2;
+  for (int l = 0; l < SVO_MAX_LEVELS; ++l) st->align_iters += ar.iters[l];
+  svo_oracle_se3_mul(ar.T_cur_ref, T_last_w, st->T_cur_w);
+  /* reprojection refinement */
+  double Tkw_inv[7], T_cur_kf[7];
+  svo_oracle_se3_inverse(s->T_kf_w, Tkw_inv);
+  svo_oracle_se3_mul(st->T_cur_w, Tkw_inv, T_cur_kf);
+  for (int i = 0; i < s->N; ++i) {
+    svo_ref_feature f;
+    f.px_ref[0] = s->kf_px[2 * i]; f.px_ref[1] = s->kf_px[2 * i + 1];
+    memcpy(f.f_ref, s->kf_f + 3 * i, sizeof(f.f_ref));
+    f.level_ref = s->kf_level[i]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
+    const double depth_ref = norm3d(Tkw_inv[0] - s->pt_world[3 * i], Tkw_inv[1] - s->pt_world[3 * i + 1], Tkw_inv[2] - s->pt_world[3 * i + 2]);
+    double pc[3], px_in[2];
+    svo_oracle_se3_transform(st->T_cur_w, s->pt_world + 3 * i, pc);
+    svo_oracle_world2cam(&s->cam, pc, px_in);
+    svo_match_result mr;
+    const int ok = svo_oracle_find_match_direct(&s->kf, &s->cur, &s->cam, &f, depth_ref, T_cur_kf, &s->mopts, px_in, &mr);
+    st->n_matched += ok;
+    if (px_refined) { px_refined[2 * i] = mr.px_cur[0]; px_refined[2 * i + 1] = mr.px_cur[1]; }
+    if (match_ok) match_ok[i] = ok;
+  }
+  /* depth filter */
+  for (int i = 0; i < s->S; ++i) {
+    svo_ref_feature f;
+    f.px_ref[0] = s->seed_px[2 * i]; f.px_ref[1] = s->seed_px[2 * i + 1];
+    memcpy(f.f_ref, s->seed_f + 3 * i, sizeof(f.f_ref));
+    f.level_ref = s->seed_level[i]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
+    const int status = svo_oracle_update_seed_with_frame(&s->kf, &s->cur, &s->cam, &f, s->T_kf_w, st->T_cur_w, &s->mopts,
+                                                         s->conv_thresh, &s->seeds[i], NULL);
+    if (status == SVO_SEED_UPDATED) st->n_seeds_updated++;
+    else if (status == SVO_SEED_CONVERGED) st->n_seeds_converged++;
+    else if (status == SVO_SEED_NO_MATCH) st->n_seeds_failed++;
+    else st->n_seeds_skipped++;
+    if (s->reseed && (status == SVO_SEED_CONVERGED || status == SVO_SEED_NAN_ERASED)) s->seeds[i] = s->seed_init;
+  }
+  /* the current frame becomes the last frame */
+  { uint8_t* t0 = s->last0; uint8_t* tu = s->lastu; s->last0 = s->cur0; s->lastu = s->curu; s->cur0 = t0; s->curu = tu; }
+  svo_oracle_make_pyr(&s->last, s->last0, s->lastu, s->w, s->h, s->n_levels);
+}
+
+void svo_oracle_seq_get_seeds(const svo_seq* s, svo_seed* out) { memcpy(out, s->seeds, sizeof(svo_seed) * s->S); }
+
+/* ---- batch of independent sequences over a pthread pool (one work item = one sequence step) ---- */
+typedef struct {
+  svo_seq** seqs; int n; const uint8_t* const* imgs; const double* T_last_w; const double* const* last_px; svo_step_stats* stats;
+  int next; pthread_mutex_t mu;
+} batch_job;
+
+static void* batch_worker(void* arg)
+{
+  batch_job* j = (batch_job*)arg;
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    const int i = j->next++;
+    pthread_mutex_unlock(&j->mu);
+    if (i >= j->n) break;
+    svo_oracle_seq_step(j->seqs[i], j->imgs[i], j->T_last_w + 7 * i, j->last_px[i], &j->stats[i], NULL, NULL);
+  }
+  return NULL;
+}
+
+void svo_oracle_seq_step_batch(svo_seq** seqs, int n, const uint8_t* const* imgs, const double* T_last_w,
+                               const double* const* last_px, svo_step_stats* stats, int n_threads)
+{
+  batch_job j; j.seqs = seqs; j.n = n; j.imgs = imgs; j.T_last_w = T_last_w; j.last_px = last_px; j.stats = stats; j.next = 0;
+  pthread_mutex_init(&j.mu, NULL);
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  pthread_t th[256];
+  for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, batch_worker, &j);
+  for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+  pthread_mutex_destroy(&j.mu);
+}

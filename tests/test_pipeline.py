@@ -1,0 +1,107 @@
+"""Per-frame front-end step (pyramid -> sparse align -> reprojection refinement -> seed update):
+the C restatement against the real reference (CPU), and svob200_tracker_step against the C
+restatement (GPU)."""
+import numpy as np
+import pytest
+
+from android_svo_b200 import synth, frontend
+from oracle.pyoracle import Cam, OracleSeq, RefSeq
+import scenes
+
+
+def make_sequence(oracle, name, seed, n_frames, tex_size=1024, stride=3):
+    cfg = synth.CONFIGS[name]
+    poses = synth.trajectory(n_frames * stride, seed=seed)[::stride]
+    tex = scenes.texture(tex_size)
+    imgs = [synth.render(tex, cfg, T) for T in poses]
+    fc, ft, sc, st = frontend.DETECT[name]
+    pyr = oracle.pyramid(imgs[0], cfg["n_levels"])
+    _, fcells = oracle.fast_detect(pyr, cfg["n_pyr"], fc, ft)
+    _, scells = oracle.fast_detect(pyr, cfg["n_pyr"], sc, st)
+    kf = frontend.keyframe_setup(cfg, poses[0], fcells, scells, ft, st)
+    last_px = [frontend.project_many(cfg, poses[k], kf["pt_world"]) for k in range(n_frames)]
+    return cfg, poses, imgs, kf, last_px
+
+
+def test_oracle_step_matches_reference(oracle, ref):
+    cfg, poses, imgs, kf, last_px = make_sequence(oracle, "C2", 0x00C0FFEE, 11)
+    cam = scenes.cam_of(cfg, Cam)
+    args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
+    so, sr = OracleSeq(oracle, *args), RefSeq(ref, *args)
+    try:
+        for s in (so, sr):
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+            s.set_last(imgs[0])
+        total_conv = 0
+        for k in range(1, 11):
+            a, pxa, oka = so.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            b, pxb, okb = sr.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            assert a.n_tracked == b.n_tracked and a.align_iters == b.align_iters
+            rot, trans = synth.pose_error(np.array(a.T_cur_w[:]), np.array(b.T_cur_w[:]))
+            assert rot < 1e-12 and trans < 1e-12
+            assert a.n_matched == b.n_matched and np.array_equal(oka, okb)
+            assert np.abs(pxa - pxb).max() < 1e-9
+            assert a.n_seeds_converged == b.n_seeds_converged
+            sa, sb = so.seeds(), sr.seeds()
+            # float seed state: one ulp of difference in 1/z (pose differs by ~1e-16 through the LDL^T) is amplified
+            # by the cancellation in sigma2 = C1*(s2+m^2) + C2*(...) - mu_new^2, so: nearly all exact, all close
+            assert np.isclose(sa, sb, rtol=1e-6, atol=0).all(axis=1).mean() > 0.99, "seed states differ after frame %d" % k
+            assert np.allclose(sa, sb, rtol=1e-3, atol=0)
+            total_conv += a.n_seeds_converged
+            # sanity: alignment recovers the true pose to a few mm (stops at level 2)
+            grot, gtrans = synth.pose_error(np.array(a.T_cur_w[:]), poses[k])
+            assert grot < 1e-2 and gtrans < 3e-2
+            assert a.n_tracked > 90 and a.n_matched > 90
+        assert total_conv > 150
+    finally:
+        so.close(); sr.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,batch,n_frames", [("C2", 3, 10), ("C3", 2, 4)])
+def test_tracker_step_matches_oracle(ctx, oracle, name, batch, n_frames):
+    from android_svo_b200 import capi
+    seqs = [make_sequence(oracle, name, 0x00C0FFEE + i, n_frames + 1) for i in range(batch)]
+    cfg = seqs[0][0]
+    cam_o, cam_g = scenes.cam_of(cfg, Cam), scenes.cam_of(cfg, capi.Camera)
+    args = (cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
+    oseqs = [OracleSeq(oracle, cam_o, *args) for _ in range(batch)]
+    trk = capi.Tracker(ctx, cam_g, batch, *args)
+    try:
+        N, S = cfg["n_features"], cfg["n_seeds"]
+        for s, (_, poses, imgs, kf, _) in zip(oseqs, seqs):
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+            s.set_last(imgs[0])
+        cat = lambda key: np.concatenate([q[3][key] for q in seqs])
+        trk.set_keyframe(np.stack([q[2][0] for q in seqs]), np.stack([q[1][0] for q in seqs]), np.arange(batch + 1) * N,
+                         cat("kf_px"), cat("kf_level"), cat("pt_world"), np.arange(batch + 1) * S, cat("seed_px"), cat("seed_level"))
+        trk.set_last(np.stack([q[2][0] for q in seqs]))
+        n_flip = 0
+        for k in range(1, n_frames + 1):
+            stats, px, ok = trk.step(np.stack([q[2][k] for q in seqs]), np.stack([q[1][k - 1] for q in seqs]),
+                                     np.concatenate([q[4][k - 1] for q in seqs]), want_px=True)
+            seeds_g = trk.seeds()
+            for b, s in enumerate(oseqs):
+                e, pxe, oke = s.step(seqs[b][2][k], seqs[b][1][k - 1], seqs[b][4][k - 1], want_px=True)
+                g = stats[b]
+                assert g["n_tracked"] == e.n_tracked
+                assert g["align_iters"] == e.align_iters, "GN iteration count differs (decision flip)"
+                rot, trans = synth.pose_error(g["T_cur_w"], np.array(e.T_cur_w[:]))
+                assert rot <= 1e-4 and trans <= 2e-4
+                assert rot < 1e-9 and trans < 1e-9
+                assert g["n_matched"] == e.n_matched and np.array_equal(ok[b * N:(b + 1) * N], oke)
+                assert np.abs(px[b * N:(b + 1) * N] - pxe).max() <= 1e-3
+                for key in ("n_seeds_updated", "n_seeds_converged", "n_seeds_failed", "n_seeds_skipped"):
+                    if g[key] != getattr(e, key):
+                        n_flip += 1
+                se = s.seeds()
+                sg = seeds_g[b * S:(b + 1) * S]
+                sg = np.stack([sg[c] for c in ("a", "b", "mu", "z_range", "sigma2")], 1)
+                close = np.isclose(sg, se, rtol=1e-5, atol=0).all(axis=1)
+                assert close.mean() > 0.99, "seed states differ for %d of %d seeds" % ((~close).sum(), S)
+                assert np.allclose(sg, se, rtol=1e-3, atol=0)
+        assert n_flip == 0, "%d seed status count mismatches" % n_flip
+    finally:
+        trk.close()
+        for s in oseqs:
+            s.close()
