@@ -107,6 +107,9 @@ def load_library():
     L.svob200_tracker_set_last.argtypes = [V, V, C.c_int, C.c_int]
     L.svob200_tracker_step.argtypes = [V, V, C.c_int, V, V, V, V, V, C.c_int]
     L.svob200_tracker_get_seeds.argtypes = [V, V]
+    L.svob200_tracker_enable_profiling.argtypes = [V, C.c_int]
+    L.svob200_tracker_stage_ms.argtypes = [V, c_fp]
+    L.svob200_tracker_get_seed_obs.argtypes = [V, V]
     L.svob200_dev_alloc.argtypes = [V, C.c_size_t, C.POINTER(V)]
     L.svob200_dev_free.argtypes = [V, V]
     L.svob200_dev_upload.argtypes = [V, V, V, C.c_size_t]
@@ -129,6 +132,7 @@ EXPORTED_SYMBOLS = [
     "svob200_synth_render", "svob200_features_prepare", "svob200_compose_poses", "svob200_reproject_prepare",
     "svob200_tracker_create", "svob200_tracker_destroy", "svob200_tracker_set_keyframe", "svob200_tracker_set_last",
     "svob200_tracker_step", "svob200_tracker_get_seeds", "svob200_tracker_launches_per_step",
+    "svob200_tracker_enable_profiling", "svob200_tracker_stage_ms", "svob200_tracker_get_seed_obs",
 ]
 
 
@@ -412,6 +416,21 @@ class Tracker:
         out = np.zeros(max(self.S, 1), seed_dt)
         self.ctx._ck(self.L.svob200_tracker_get_seeds(self.h, _ptr(out)))
         return out[:self.S]
+
+    def seed_obs(self):
+        out = np.zeros(max(self.S, 1), seed_obs_dt)
+        self.ctx._ck(self.L.svob200_tracker_get_seed_obs(self.h, _ptr(out)))
+        return out[:self.S]
+
+    def enable_profiling(self, on=True):
+        self.ctx._ck(self.L.svob200_tracker_enable_profiling(self.h, int(on)))
+
+    STAGES = ("frame+pyramid", "features_prepare", "sparse_align", "reproject_prepare", "match_direct", "seeds_update", "stats")
+
+    def stage_ms(self):
+        ms = (C.c_float * 7)()
+        self.ctx._ck(self.L.svob200_tracker_stage_ms(self.h, ms))
+        return dict(zip(self.STAGES, [float(x) for x in ms]))
 
     def close(self):
         if getattr(self, "h", None):

@@ -91,7 +91,11 @@ struct svob200_tracker {
   void* d_align_scratch = nullptr;
   uint8_t* h_pinned = nullptr; size_t h_cap = 0;
   std::vector<void*> owned;
+  // optional per-stage CUDA-event timing (bench.py's stage breakdown / roofline)
+  bool profiling = false;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+#define STAGE_MARK(k) do { if (t->profiling) cudaEventRecord(t->ev[k], s); } while (0)
 
 extern "C" {
 
@@ -220,6 +224,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
   const int B = t->batch, N = t->N, S = t->S;
   cudaStream_t s = ctx->stream;
   const DevCam cam = to_cam(&t->cam);
+  STAGE_MARK(0);
   // 1. current frame: level 0 in place (device) or one H2D copy (host), then the fused pyramid kernel
   if (mem == SVOB200_MEM_DEVICE) { if (int e = svob200_frame_bind(ctx, t->fid_cur, cur_imgs, stride, nullptr)) return e; }
   else {
@@ -252,25 +257,32 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
   }
   FrameRec* last = find_frame(ctx, t->fid_last);
   FrameRec* cur = find_frame(ctx, t->fid_cur);
+  STAGE_MARK(1);
   // 3. Feature/xyz_ref of the last frame's features, initial relative pose
   if (launch_features_prepare(cam, N, d_last_px, t->d_pt_world, t->d_ftr_image, d_T_last, nullptr, t->d_xyz, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: features_prepare failed");
   init_pose_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, d_T_last, t->d_T_init); ++ctx->launches;
+  STAGE_MARK(2);
   // 4. SparseImgAlign::run(last, cur)
   if (launch_sparse_align(last->f, cur->f, cam, B, N, t->max_per, t->d_ftr_off, d_last_px, t->d_xyz, t->d_has_point, t->d_T_init, t->aopts,
                           t->d_align, t->d_align_scratch, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: sparse_align failed");
+  STAGE_MARK(3);
   // 5. cur.T_f_w = T_cur_from_ref * last.T_f_w ; reprojection of the map points
   if (launch_compose_poses(B, t->d_align, d_T_last, t->d_T_cur, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: compose failed");
   if (launch_reproject_prepare(cam, N, t->d_ftrs, t->d_pt_world, t->d_T_kf_ftr, t->d_T_cur, t->d_depth_ref, t->d_px_in, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
+  STAGE_MARK(4);
   // 6. Matcher::findMatchDirect per map point (keyframe patch -> current frame)
   if (launch_match_direct_compact(ctx->d_table, cur->slot, cam, N, t->d_ftrs, t->d_depth_ref, t->d_px_in, t->mopts, t->d_px_out, t->d_match_ok, s, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
+  STAGE_MARK(5);
   // 7. DepthFilter::updateSeeds(cur)
   if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, S, t->d_seed_ftrs, t->d_T_kf_seed, t->d_T_cur, t->mopts, t->conv_thresh, t->d_seeds, t->d_obs, s, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
+  STAGE_MARK(6);
   // 8. per-sequence statistics (+ steady-state re-seeding)
   step_stats_kernel<<<B, 128, 0, s>>>(t->d_ftr_off, t->d_seed_off, t->d_align, t->d_T_cur, t->d_match_ok, t->d_obs, t->d_seeds, t->seed_init, t->reseed, t->d_stats);
   ++ctx->launches;
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
+  STAGE_MARK(7);
   // 9. results
   if (mem == SVOB200_MEM_DEVICE) {
     if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
@@ -301,5 +313,35 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
 }
 
 int svob200_tracker_launches_per_step(void) { return 10; }
+
+// stage timing: 7 durations [frame copy/bind + pyramid + per-step input copy, features_prepare + init_pose,
+// sparse_align, compose + reproject_prepare, match_direct, seeds_update, stats]
+int svob200_tracker_enable_profiling(svob200_tracker* t, int on)
+{
+  if (!t) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (on && !t->ev[0]) for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&t->ev[k]));
+  t->profiling = on != 0;
+  return SVOB200_OK;
+}
+
+int svob200_tracker_stage_ms(svob200_tracker* t, float* ms /*7*/)
+{
+  if (!t || !ms || !t->ev[0]) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  CU(cudaEventSynchronize(t->ev[7]));
+  for (int k = 0; k < 7; ++k) CU(cudaEventElapsedTime(&ms[k], t->ev[k], t->ev[k + 1]));
+  return SVOB200_OK;
+}
+
+// per-seed observation records of the last step (status, n_evals, ...) for workload accounting
+int svob200_tracker_get_seed_obs(svob200_tracker* t, svob200_seed_obs* out)
+{
+  if (!t || !out) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  CU(cudaMemcpyAsync(out, t->d_obs, sizeof(svob200_seed_obs) * (size_t)t->S, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,528 @@
+#!/usr/bin/env python
+"""bench.py — front-end frames/s of the B200-native SVO tracking front end (and the CPU reference arm).
+
+Workload (BASELINE.json configs[4] built from configs[1]): a batch of independent synthetic
+640x480 sequences (C2 shape: 4-level pyramid, 120 map features, 768 depth-filter seeds), sharded
+over the GPUs of one node (strong scaling: the total number of sequences is fixed).  One step =
+one frame of every sequence through pyramid -> sparse image alignment -> reprojection refinement ->
+depth-filter seed update (svob200_tracker_step).  `value` times the steps with every input already
+resident in HBM; `e2e` times the same steps through the C ABI with HOST (pinned) buffers, the H2D
+copy of the frames + per-step inputs and the D2H read of the per-sequence results inside the timed
+region.  The single-stream C2 latency (one sequence, p50 per frame) is reported in `latency`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--seqs TOTAL]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from android_svo_b200 import synth, frontend  # noqa: E402
+
+METRIC = "front-end frames/s (pyramid + sparse align + refine + seed update), batched C2 sequences"
+CFG_NAME = "C2"
+TEX_SIZE = 2048
+PPM = 400.0
+PLANE_Z = 2.0
+KF_INDEX = 0
+POOL_INDICES = (36, 39, 42, 45)     # trajectory frames cycled (ping-pong) as the live stream
+DEPTH_MEAN, DEPTH_MIN = 2.4, 1.2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seqs", type=int, default=4096, help="total number of independent sequences (all GPUs)")
+    ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences in the CPU sample (0 = 4 per host thread)")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def ping_pong(n_pool, n_steps):
+    """frame-pool indices visited so that consecutive frames are adjacent in time: 0,1,2,3,2,1,0,1,..."""
+    order, i, d = [0], 0, 1
+    while len(order) < n_steps + 1:
+        if i + d < 0 or i + d >= n_pool:
+            d = -d
+        i += d
+        order.append(i)
+    return order
+
+
+# ------------------------------------------------------------------ batched numpy geometry (setup only)
+def poses_for(seq_ids, indices):
+    """T_f_w[seq, frame] for the given trajectory frame indices."""
+    n = max(indices) + 1
+    return np.stack([synth.trajectory(n, seed=0x00C0FFEE + int(s))[list(indices)] for s in seq_ids])
+
+
+def q_rot_many(q, p):
+    """rotate points p[...,3] by quaternions q[...,4] (x,y,z,w)"""
+    qv = q[..., :3]
+    uv = np.cross(qv, p)
+    uv = uv + uv
+    return p + q[..., 3:4] * uv + np.cross(qv, uv)
+
+
+def se3_inverse_many(T):
+    qi = np.concatenate([-T[..., 3:6], T[..., 6:7]], -1)
+    return np.concatenate([-q_rot_many(qi, T[..., :3]), qi], -1)
+
+
+def backproject_many(cfg, T_f_w, px):
+    """px[B,N,2] seen from T_f_w[B,7] -> world points on the plane z = PLANE_Z"""
+    Tw = se3_inverse_many(T_f_w)
+    d = np.stack([(px[..., 0] - cfg["cx"]) / cfg["fx"], (px[..., 1] - cfg["cy"]) / cfg["fy"], np.ones(px.shape[:-1])], -1)
+    d = q_rot_many(Tw[:, None, 3:], d)
+    s = (PLANE_Z - Tw[:, None, 2]) / d[..., 2]
+    return Tw[:, None, :3] + s[..., None] * d
+
+
+def project_many(cfg, T_f_w, pts):
+    pc = q_rot_many(T_f_w[:, None, 3:], pts) + T_f_w[:, None, :3]
+    return np.stack([cfg["fx"] * pc[..., 0] / pc[..., 2] + cfg["cx"], cfg["fy"] * pc[..., 1] / pc[..., 2] + cfg["cy"]], -1)
+
+
+def select_batch(cells, thr, n):
+    px = np.zeros((len(cells), n, 2))
+    lv = np.zeros((len(cells), n), np.int32)
+    for b in range(len(cells)):
+        good = cells[b][cells[b]["score"].astype(np.float64) > thr]
+        if len(good) < n:      # texture-poor view: recycle the available corners so every sequence has the same load
+            good = np.resize(good, n)
+        good = good[:n]
+        px[b] = np.stack([good["x"], good["y"]], 1)
+        lv[b] = good["level"]
+    return px, lv
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------ CPU arm (reference / oracle port)
+def cpu_arm(cfg, n_seqs, steps, warmup, threads):
+    """Times the front-end step of `n_seqs` independent sequences on the host cores.  Uses the real
+    reference (oracle/_ref/libsvo_ref.so) when it was built, else the C restatement."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.pyoracle import Oracle, Ref, Cam, OracleSeq, RefSeq
+    oracle, ref = Oracle(), Ref()
+    kind = "reference" if ref.available() else "port"
+    cam = Cam.make(cfg["w"], cfg["h"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
+    tex = synth.make_texture(TEX_SIZE)
+    idx = (KF_INDEX,) + POOL_INDICES
+    poses = poses_for(range(n_seqs), idx)
+    fc, ft, sc, st = frontend.DETECT[CFG_NAME]
+
+    def setup(i):
+        imgs = [oracle.synth_render(tex, PPM, PLANE_Z, cam, poses[i, k]) for k in range(len(idx))]
+        pyr = oracle.pyramid(imgs[0], cfg["n_levels"])
+        _, fcells = oracle.fast_detect(pyr, cfg["n_pyr"], fc, ft)
+        _, scells = oracle.fast_detect(pyr, cfg["n_pyr"], sc, st)
+        kf = frontend.keyframe_setup(cfg, poses[i, 0], fcells, scells, ft, st, PLANE_Z)
+        args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, DEPTH_MEAN, DEPTH_MIN, 1)
+        s = RefSeq(ref, *args) if kind == "reference" else OracleSeq(oracle, *args)
+        s.set_keyframe(imgs[0], poses[i, 0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+        s.set_last(imgs[1])
+        last_px = [frontend.project_many(cfg, poses[i, 1 + k], kf["pt_world"]) for k in range(len(POOL_INDICES))]
+        return s, imgs[1:], last_px
+
+    with ThreadPoolExecutor(threads) as ex:
+        seqs = list(ex.map(setup, range(n_seqs)))
+        order = ping_pong(len(POOL_INDICES), warmup + steps)
+
+        def step_all(k):
+            a, b = order[k], order[k + 1]
+            return list(ex.map(lambda i: seqs[i][0].step(seqs[i][1][b], poses[i, 1 + a], seqs[i][2][a]), range(n_seqs)))
+
+        for k in range(warmup):
+            step_all(k)
+        t0 = time.perf_counter()
+        for k in range(warmup, warmup + steps):
+            stats = step_all(k)
+        dt = time.perf_counter() - t0
+    tracked = float(np.mean([s.n_tracked for s in stats]))
+    for s, _, _ in seqs:
+        s.close()
+    return dict(kind=kind, fps=n_seqs * steps / dt, seconds=dt, n_seqs=n_seqs, tracked=tracked)
+
+
+# ------------------------------------------------------------------ GPU arm
+def pinned_array(ctx, shape, dtype):
+    import ctypes as C
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    ctx._ck(ctx.L.svob200_host_alloc_pinned(ctx.h, n, C.byref(p)))
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p.value
+
+
+class GpuWorkload:
+    """Everything the timed loops need, resident: tracker, frame pool on device + pinned host, per-step inputs."""
+
+    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None):
+        self.ctx, self.capi, self.cfg = ctx, capi, cfg
+        B = len(seq_ids)
+        self.B = B
+        w, h, N, S = cfg["w"], cfg["h"], cfg["n_features"], cfg["n_seeds"]
+        cam = capi.Camera.make(w, h, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
+        self.cam = cam
+        idx = (KF_INDEX,) + POOL_INDICES
+        poses = poses_for(seq_ids, idx)                         # [B, 1+F, 7]
+        self.poses = poses
+        own_tex = tex_dev is None
+        if own_tex:
+            tex = synth.make_texture(TEX_SIZE)
+            tex_dev = ctx.dev_alloc(tex.nbytes)
+            ctx.dev_upload(tex_dev, tex)
+        self.tex_dev, self.own_tex = tex_dev, own_tex
+        F = len(POOL_INDICES)
+        img_bytes = w * h
+        # frame pool on the device (dense, stride = w) and in pinned host memory
+        self.pool_dev = [ctx.dev_alloc(B * img_bytes) for _ in range(F)]
+        self.pool_host = []
+        for k in range(F):
+            ctx.synth_render(tex_dev, TEX_SIZE, PPM, PLANE_Z, cam, poses[:, 1 + k], self.pool_dev[k])
+            arr, ptr = pinned_array(ctx, (B, h, w), np.uint8)
+            ctx.dev_download(arr, self.pool_dev[k])
+            self.pool_host.append((arr, ptr))
+        # keyframes: render, detect (GPU FAST), select features / seeds
+        kf_dev = ctx.dev_alloc(B * img_bytes)
+        ctx.synth_render(tex_dev, TEX_SIZE, PPM, PLANE_Z, cam, poses[:, 0], kf_dev)
+        self.kf_host = np.zeros((B, h, w), np.uint8)
+        ctx.dev_download(self.kf_host, kf_dev)
+        ctx.dev_free(kf_dev)
+        fid = 7
+        ctx.frame_create(fid, B, w, h, cfg["n_levels"])
+        ctx.frame_upload(fid, self.kf_host)
+        fc, ft, sc, st = frontend.DETECT[CFG_NAME]
+        fcells, _ = ctx.fast_detect(fid, cfg["n_pyr"], fc, ft)
+        scells, _ = ctx.fast_detect(fid, cfg["n_pyr"], sc, st)
+        ctx.frame_release(fid)
+        kf_px, kf_level = select_batch(fcells, ft, N)
+        seed_px, seed_level = select_batch(scells, st, S)
+        pt_world = backproject_many(cfg, poses[:, 0], kf_px)
+        self.kf = dict(kf_px=kf_px, kf_level=kf_level, pt_world=pt_world, seed_px=seed_px, seed_level=seed_level)
+        self.trk = capi.Tracker(ctx, cam, B, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0,
+                                DEPTH_MEAN, DEPTH_MIN, 1)
+        self.trk.set_keyframe(self.kf_host, poses[:, 0], np.arange(B + 1) * N, kf_px.reshape(-1, 2), kf_level.reshape(-1),
+                              pt_world.reshape(-1, 3), np.arange(B + 1) * S, seed_px.reshape(-1, 2), seed_level.reshape(-1))
+        # per-step inputs for every pool frame used as "last": pose + pixel of every map point
+        self.in_host, self.in_dev = [], []
+        for k in range(F):
+            T = np.ascontiguousarray(poses[:, 1 + k])
+            lp = np.ascontiguousarray(project_many(cfg, T, pt_world).reshape(-1, 2))
+            hT, pT = pinned_array(ctx, T.shape, np.float64); hT[...] = T
+            hp, pp = pinned_array(ctx, lp.shape, np.float64); hp[...] = lp
+            dT, dp = ctx.dev_alloc(T.nbytes), ctx.dev_alloc(lp.nbytes)
+            ctx.dev_upload(dT, T); ctx.dev_upload(dp, lp)
+            self.in_host.append((pT, pp)); self.in_dev.append((dT, dp))
+        self.stats_host, self.stats_ptr = pinned_array(ctx, (B,), capi.step_stats_dt)
+        self.stats_dev = ctx.dev_alloc(self.stats_host.nbytes)
+        self.h2d_bytes = B * img_bytes + B * 56 + B * N * 16
+        self.d2h_bytes = self.stats_host.nbytes
+        self.reset()
+
+    def reset(self):
+        self.trk.set_last(self.pool_dev[0], mem=self.capi.MEM_DEVICE, stride=self.cfg["w"])
+        self.pos = 0
+
+    def step(self, order, k, mem):
+        a, b = order[k], order[k + 1]
+        w = self.cfg["w"]
+        if mem == self.capi.MEM_DEVICE:
+            self.trk.step_raw(self.pool_dev[b], w, self.in_dev[a][0], self.in_dev[a][1], self.stats_dev, mem)
+        else:
+            self.trk.step_raw(self.pool_host[b][1], w, self.in_host[a][0], self.in_host[a][1], self.stats_ptr, mem)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from android_svo_b200 import capi
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = capi.Context(local_rank)
+    cfg = synth.CONFIGS[CFG_NAME]
+    total = args.seqs - args.seqs % world
+    per = total // world
+    seq_ids = list(range(rank * per, (rank + 1) * per))          # contiguous block partition
+    t_setup = time.time()
+    wl = GpuWorkload(ctx, capi, cfg, seq_ids)
+    t_setup = time.time() - t_setup
+    K, W = args.steps, args.warmup
+    order = ping_pong(len(POOL_INDICES), 2 * (W + K) + 8)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: inputs resident in HBM, CUDA events on the launching stream
+    wl.reset()
+    for k in range(W):
+        wl.step(order, k, capi.MEM_DEVICE)
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.timer_start()
+    for k in range(W, W + K):
+        wl.step(order, k, capi.MEM_DEVICE)
+    ms = ctx.timer_stop_ms()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count() - launches0
+    ms = max_over_ranks(ms)
+    value = total * K / (ms * 1e-3)
+    stats_dev_copy = np.zeros(wl.B, capi.step_stats_dt)
+    ctx.dev_download(stats_dev_copy, wl.stats_dev)
+
+    # ---------------- stage breakdown (separate, untimed-for-the-headline pass)
+    wl.trk.enable_profiling(True)
+    stage_acc, n_prof = {}, 3
+    for k in range(W + K, W + K + n_prof):
+        wl.step(order, k, capi.MEM_DEVICE)
+        for name, v in wl.trk.stage_ms().items():
+            stage_acc[name] = stage_acc.get(name, 0.0) + v / n_prof
+    obs = wl.trk.seed_obs()
+    wl.trk.enable_profiling(False)
+    mean_evals = float(obs["n_evals"].mean())
+    N, S = cfg["n_features"], cfg["n_seeds"]
+    iters_mean = float(stats_dev_copy["align_iters"].mean())
+    # algorithmic bytes per launch (SURVEY.md §8d per-unit figures x units per launch)
+    alg = {
+        "frame+pyramid": wl.B * 408000.0,
+        "sparse_align": wl.B * N * (857.0 * iters_mean + 36.0 * (cfg["max_level"] - cfg["min_level"] + 1)),
+        "match_direct": wl.B * N * (400.0 + 2 * 81.0),
+        "seeds_update": wl.B * S * (400.0 + 64.0 * mean_evals + 2 * 81.0 + 40.0),
+    }
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    stages = {}
+    for name, v in stage_acc.items():
+        e = {"ms": round(v, 4)}
+        if name in alg and v > 0:
+            e["alg_GBps"] = round(alg[name] / (v * 1e-3) / 1e9, 2)
+            e["hbm_frac"] = round(e["alg_GBps"] / peak, 4)
+        stages[name] = e
+    dom = max(alg.keys(), key=lambda n: stage_acc.get(n, 0.0))
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch_per_seq")
+        if traffic is not None:
+            traffic = traffic * wl.B
+    except Exception:
+        pass
+    roofline = {"kernel": {"frame+pyramid": "pyramid_fused_kernel", "sparse_align": "sparse_align_kernel", "match_direct": "match_direct_kernel",
+                           "seeds_update": "seeds_update_kernel"}[dom],
+                "bound": "hbm", "achieved": round(alg[dom] / (stage_acc[dom] * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(alg[dom] / (stage_acc[dom] * 1e-3) / 1e9 / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "ms_per_launch": round(stage_acc[dom], 4), "share_of_step": round(stage_acc[dom] / max(sum(stage_acc.values()), 1e-9), 3),
+                "note": "latency/issue-bound kernel (one CTA per seed, data L2-resident); HBM fraction stated for completeness, "
+                        "the HBM-bound kernel is the pyramid (see stages)"}
+
+    # ---------------- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
+    wl.reset()
+    for k in range(W):
+        wl.step(order, k, capi.MEM_HOST)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        wl.step(order, k, capi.MEM_HOST)
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = total * K / e2e_s
+    stats_last = wl.stats_host.copy()
+
+    # ---------------- per-sequence statistics: NCCL gather over NVLink, 64 B per sequence
+    rec = np.zeros((wl.B, 8), np.float64)
+    rec[:, 0] = seq_ids
+    rec[:, 1] = stats_last["n_tracked"]; rec[:, 2] = stats_last["n_matched"]; rec[:, 3] = stats_last["n_seeds_updated"]
+    rec[:, 4] = stats_last["n_seeds_converged"]; rec[:, 5] = stats_last["align_iters"]
+    gt = wl.poses[:, 1 + order[W + K]]
+    for b in range(wl.B):
+        rec[b, 6], rec[b, 7] = synth.pose_error(stats_last["T_cur_w"][b], gt[b])
+    if world > 1:
+        mine = torch.from_numpy(rec).cuda()
+        allrec = torch.empty((world * wl.B, 8), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allrec, mine)
+        rec = allrec.cpu().numpy()
+    seq_stats = {"n_sequences": int(len(rec)), "tracked_mean": float(rec[:, 1].mean()), "matched_mean": float(rec[:, 2].mean()),
+                 "seeds_updated_mean": float(rec[:, 3].mean()), "seeds_converged_mean": float(rec[:, 4].mean()),
+                 "align_iters_mean": float(rec[:, 5].mean()), "pose_err_rot_max": float(rec[:, 6].max()),
+                 "pose_err_trans_max": float(rec[:, 7].max())}
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 pixels / f32 photometric / f64 geometry", "data": "synthetic",
+            "config": {"workload": "C5: %d independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each), "
+                                   "block-sharded over %d GPU(s); step = 1 frame of every sequence" % (total, N, S, world),
+                       "sequences_total": total, "sequences_per_gpu": per, "frame_pool": list(POOL_INDICES),
+                       "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (per * cfg["w"] * cfg["h"] / 1e6)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d_bytes * world),
+                    "d2h_bytes_per_step": int(wl.d2h_bytes * world), "ms_per_step": round(e2e_s / K * 1e3, 4)},
+            "gpu_launches": int(launches), "launches_per_step": int(launches // max(K, 1)),
+            "clocks": clocks, "roofline": roofline, "stages": stages, "sequence_stats": seq_stats,
+            "setup_s": round(t_setup, 1),
+        }
+    return out, ctx, wl
+
+
+def latency_c2(ctx, capi, n_frames=60):
+    """Single-stream C2: one sequence, per-frame latency through the C ABI with host buffers (p50) and resident."""
+    cfg = synth.CONFIGS[CFG_NAME]
+    wl = GpuWorkload(ctx, capi, cfg, [4096])
+    order = ping_pong(len(POOL_INDICES), n_frames + 30)
+    res = {}
+    for name, mem in (("host_buffers", capi.MEM_HOST), ("resident", capi.MEM_DEVICE)):
+        wl.reset()
+        for k in range(10):
+            wl.step(order, k, mem)
+        ctx.sync()
+        ts = []
+        for k in range(10, 10 + n_frames):
+            t0 = time.perf_counter()
+            wl.step(order, k, mem)
+            ctx.sync()
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts) * 1e3
+        res[name] = {"p50_ms": round(float(np.median(ts)), 4), "p95_ms": round(float(np.percentile(ts, 95)), 4),
+                     "frames_per_s": round(1e3 / float(np.median(ts)), 1)}
+    wl.trk.enable_profiling(True)
+    acc = {}
+    for k in range(5):
+        wl.step(order, 10 + n_frames + k, capi.MEM_DEVICE)
+        for n, v in wl.trk.stage_ms().items():
+            acc[n] = acc.get(n, 0.0) + v / 5
+    res["stages_ms_resident"] = {k: round(v, 4) for k, v in acc.items()}
+    res["config"] = "C2: one 640x480 sequence, 4-level pyramid, 120 features, 768 seeds"
+    wl.trk.close()
+    return res
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = synth.CONFIGS[CFG_NAME]
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path, all host threads, rank 0 only
+        if rank != 0:
+            return
+        n = args.cpu_seqs or max(8, 4 * threads)
+        r = cpu_arm(cfg, n, args.steps, args.warmup, threads)
+        line = {"impl": "reference", "metric": METRIC, "value": round(r["fps"], 2), "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["seconds"] / args.steps * 1e3, 3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 pixels / f32 photometric / f64 geometry",
+                "data": "synthetic",
+                "config": {"workload": "C5: independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each); "
+                                       "step = 1 frame of every sequence of the sample" % (cfg["n_features"], cfg["n_seeds"]),
+                           "sequences_total": args.seqs, "sample_sequences": n},
+                "cpu_baseline": {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
+                                 "sample": "%d sequences x %d steps (+%d warm-up), one frame per sequence per step, %d host threads"
+                                           % (n, args.steps, args.warmup, threads)},
+                "e2e": {"value": round(r["fps"], 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "tracked_mean": r["tracked"]}
+        print(json.dumps(line))
+        return
+
+    out, ctx, wl = run_b200(args, rank, world, local_rank)
+    if rank == 0:
+        from android_svo_b200 import capi
+        if not args.no_latency:
+            try:
+                out["latency"] = latency_c2(ctx, capi)
+            except Exception as e:   # pragma: no cover
+                out["latency"] = {"error": str(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            n = args.cpu_seqs or max(8, 4 * threads)
+            r = cpu_arm(cfg, n, 3, 1, threads)
+            out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
+                                   "sample": "%d sequences x 3 steps (+1 warm-up), %d host threads, %.1f s" % (n, threads, r["seconds"])}
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

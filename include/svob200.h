@@ -251,6 +251,12 @@ int  svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int strid
                           const double* last_px, svob200_step_stats* stats, double* px_refined, int* match_ok, int mem);
 int  svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out /*host*/);
 int  svob200_tracker_launches_per_step(void);
+/* optional CUDA-event timing of the stages of a step: ms[7] = {frame copy/bind + pyramid + per-step
+ * input copy, features_prepare + init pose, sparse_align, compose + reproject_prepare, match_direct,
+ * seeds_update, stats} for the most recent step */
+int  svob200_tracker_enable_profiling(svob200_tracker* t, int on);
+int  svob200_tracker_stage_ms(svob200_tracker* t, float* ms);
+int  svob200_tracker_get_seed_obs(svob200_tracker* t, svob200_seed_obs* out /*host*/);
 
 /* ---------------------------------------------------------------- device-side helpers for the
  * resident ("value") path and the synthetic bench: raw device allocations and a plane renderer.

@@ -183,6 +183,13 @@ class Oracle:
             off += w * h
         return Pyramid(levels)
 
+    def synth_render(self, tex, ppm, plane_z, cam, T_f_w):
+        tex = u8(tex)
+        out = np.zeros((cam.height, cam.width), np.uint8)
+        self.lib.svo_oracle_synth_render.argtypes = [c_u8p, C.c_int, C.c_double, C.c_double, C.POINTER(Cam), c_dp, c_u8p]
+        self.lib.svo_oracle_synth_render(_p(tex, c_u8p), tex.shape[0], float(ppm), float(plane_z), C.byref(cam), _p(f64(T_f_w), c_dp), _p(out, c_u8p))
+        return out
+
     # -- FAST
     def fast(self, img, thr=10, nonmax=True):
         img = u8(img)

@@ -189,3 +189,35 @@ void svo_oracle_seq_step_batch(svo_seq** seqs, int n, const uint8_t* const* imgs
   for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
   pthread_mutex_destroy(&j.mu);
 }
+
+/* ---- synthetic plane renderer (same float64 arithmetic / operation order as
+ *      android_svo_b200/synth.py:render and csrc/synth.cu) — input generation for the CPU arms ---- */
+void svo_oracle_synth_render(const uint8_t* tex, int size, double ppm, double plane_z, const svo_cam* cam,
+                             const double* T_f_w, uint8_t* out)
+{
+  double Tw[7];
+  svo_oracle_se3_inverse(T_f_w, Tw);
+  const double x = Tw[3], y = Tw[4], z = Tw[5], w = Tw[6];
+  const double R[9] = { 1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                        2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                        2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y) };
+  const double* c = Tw;
+  for (int v = 0; v < cam->height; ++v)
+    for (int u = 0; u < cam->width; ++u) {
+      const double X = ((double)u - cam->cx) / cam->fx, Y = ((double)v - cam->cy) / cam->fy;
+      const double dx = R[0] * X + R[1] * Y + R[2];
+      const double dy = R[3] * X + R[4] * Y + R[5];
+      const double dz = R[6] * X + R[7] * Y + R[8];
+      const double s = (plane_z - c[2]) / dz;
+      const double tu = (c[0] + s * dx) * ppm + (double)(size / 2);
+      const double tv = (c[1] + s * dy) * ppm + (double)(size / 2);
+      const double uf = floor(tu), vf = floor(tv);
+      const long long ui = (long long)uf, vi = (long long)vf;
+      const double fu = tu - uf, fv = tv - vf;
+      long long u0 = ui % size, v0 = vi % size, u1 = (ui + 1) % size, v1 = (vi + 1) % size;
+      if (u0 < 0) u0 += size; if (v0 < 0) v0 += size; if (u1 < 0) u1 += size; if (v1 < 0) v1 += size;
+      const double t00 = tex[v0 * size + u0], t01 = tex[v0 * size + u1], t10 = tex[v1 * size + u0], t11 = tex[v1 * size + u1];
+      const double val = (1 - fu) * (1 - fv) * t00 + fu * (1 - fv) * t01 + (1 - fu) * fv * t10 + fu * fv * t11;
+      out[(size_t)v * cam->width + u] = (uint8_t)floor(val + 0.5);
+    }
+}
