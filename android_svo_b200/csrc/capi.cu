@@ -468,9 +468,10 @@ int svob200_seeds_update(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_c
   st.upload();
   if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
   if (int e = st.push()) return e;
+  if (ctx->d_scratch.ensure(seeds_scratch_bytes(n)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "seeds_update: scratch alloc failed");
   if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_tr),
                           st.dev<double>(i_tc), *opts, conv_thresh, st.dev<svob200_seed>(i_s), st.dev<svob200_seed_obs>(i_o),
-                          ctx->stream, &ctx->launches))
+                          ctx->d_scratch.p, ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "seeds_update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return st.download();
 }

@@ -363,115 +363,169 @@ __device__ inline double compute_tau(const double* T_ref_cur, v3d f, double z, d
   return z_plus - z;
 }
 
-// ---------------------------------------------------------------- findEpipolarMatchDirect
-constexpr int EPI_BLOCK = 128;
-constexpr int EPI_MAX_STEPS = 1024;      // max_epi_search_steps is clamped to this
+// ---------------------------------------------------------------- findEpipolarMatchDirect in three phases
+// Phase 1 (per-thread double geometry), phase 2 (warp-cooperative patch warp / ZMSSD walk / LK),
+// phase 3 (per-thread triangulation).  The depth filter runs them as three kernels — thread per
+// seed, warp per seed, thread per seed — so the FP64 pipe (64 lanes/SM) never executes the same
+// geometry redundantly across a CTA; the stand-alone epipolar query kernel runs them back to back
+// in one warp.
+constexpr int EPI_CHUNK = 256;           // epipolar samples staged per round
+constexpr int EPI_MAX_STEPS = 1023;      // max_epi_search_steps is clamped to this
+enum { EPI_MODE_NONE = 0, EPI_MODE_DIRECT = 1, EPI_MODE_WALK = 2 };
 
-struct EpiSmem {
+struct EpiGeom {
+  double T_cur_ref[7];
+  double A[4];                          // A_cur_ref, row-major
+  double Bx0, By0, stepx, stepy;        // epipolar sample chain: uv_0 = B - step, uv_{i+1} = uv_i + step
+  double px_mid[2];                     // (px_A + px_B) / 2
+  double epi_length;
+  float a00, a01, a10, a11, pr0, pr1;   // A_ref_cur (float) and px_ref at the reference level
+  float dirx, diry;                     // (px_A - px_B).cast<float>().normalized()
+  int warp_ok, L, mode, n, n_steps_report, reject;
+};
+
+struct EpiSearch {
+  int found;                            // 0 none, 1 px_cur refined by LK, 2 uv_best only (no subpixel refinement)
+  int zmssd_best, n_evals;
+  double px_cur[2], uv_best[2], h_inv;
+};
+
+struct EpiWarpSmem {
   __align__(16) uint8_t pwb[100];
   __align__(16) uint8_t patch[64];
   AlignSmem al;
-  short2 pxi[EPI_MAX_STEPS + 2];
-  unsigned long long red[EPI_BLOCK / 32];
-  int flag;
-  double d0, d1;
+  short2 pxi[EPI_CHUNK + 1];
 };
 
-struct EpiOut {
-  int success, search_level, reject, zmssd_best, n_evals, n_steps;
-  double depth, px_cur[2], epi_length, A[4], h_inv;
-};
-
-// Block-cooperative: every thread of the CTA must call it with identical arguments.
-__device__ void epipolar_match_block(const DevFrame& ref, int ref_image, const DevFrame& cur, int cur_image, const DevCam& cam,
-                                     const svob200_feature_ref& f, const double* T_cur_ref, double d_estimate, double d_min,
-                                     double d_max, const svob200_matcher_opts& o, EpiSmem* S, EpiOut* out)
+// matcher.cpp:207-288 up to the start of the walk: pure per-thread math
+__device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref& f, const double* T_cur_ref, double d_estimate,
+                                    double d_min, double d_max, const svob200_matcher_opts& o, EpiGeom* g)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  out->success = 0; out->search_level = 0; out->reject = 0; out->zmssd_best = 2000 * 64; out->n_evals = 0; out->n_steps = 0;
-  out->depth = 0; out->px_cur[0] = 0; out->px_cur[1] = 0; out->epi_length = 0; out->h_inv = 0;
+  for (int k = 0; k < 7; ++k) g->T_cur_ref[k] = T_cur_ref[k];
+  g->reject = 0; g->mode = EPI_MODE_NONE; g->n = 0; g->n_steps_report = 0; g->L = 0; g->epi_length = 0; g->warp_ok = 0;
+  g->Bx0 = g->By0 = g->stepx = g->stepy = 0; g->px_mid[0] = g->px_mid[1] = 0;
+  g->a00 = g->a01 = g->a10 = g->a11 = g->pr0 = g->pr1 = g->dirx = g->diry = 0;
   const v3d f_ref = {f.f[0], f.f[1], f.f[2]};
-  // epipolar segment on the unit plane (matcher.cpp:222-225)
   const v3d tA = se3_transform(T_cur_ref, {f_ref.x * d_min, f_ref.y * d_min, f_ref.z * d_min});
   const double Ax = tA.x / tA.z, Ay = tA.y / tA.z;
   const v3d tB = se3_transform(T_cur_ref, {f_ref.x * d_max, f_ref.y * d_max, f_ref.z * d_max});
   const double Bx = tB.x / tB.z, By = tB.y / tB.z;
   const double ex = Ax - Bx, ey = Ay - By;
-  double A[4];
-  warp_matrix_affine(cam, f.px, f_ref, d_estimate, T_cur_ref, f.level, A);
-  for (int k = 0; k < 4; ++k) out->A[k] = A[k];
+  warp_matrix_affine(cam, f.px, f_ref, d_estimate, T_cur_ref, f.level, g->A);
+  const double* A = g->A;
   if (f.type == 1 && o.epi_search_edgelet_filtering) {
     double gx = A[0] * f.grad[0] + A[1] * f.grad[1], gy = A[2] * f.grad[0] + A[3] * f.grad[1];
     { const double z = gx * gx + gy * gy; if (z > 0) { const double n = sqrt(z); gx /= n; gy /= n; } }
     double nx = ex, ny = ey;
     { const double z = nx * nx + ny * ny; if (z > 0) { const double n = sqrt(z); nx /= n; ny /= n; } }
     const double cosangle = fabs(gx * nx + gy * ny);
-    if (cosangle < o.epi_search_edgelet_max_angle) { out->reject = 1; return; }
+    if (cosangle < o.epi_search_edgelet_max_angle) { g->reject = 1; return; }
   }
   const int L = best_search_level(A, o.max_search_level);
-  out->search_level = L;
+  g->L = L;
   double pAx, pAy, pBx, pBy;
   world2cam_uv(cam, Ax, Ay, pAx, pAy);
   world2cam_uv(cam, Bx, By, pBx, pBy);
-  double epi_length;
-  { const double dx = pAx - pBx, dy = pAy - pBy; epi_length = sqrt(dx * dx + dy * dy) / (1 << L); }
-  out->epi_length = epi_length;
+  { const double dx = pAx - pBx, dy = pAy - pBy; g->epi_length = sqrt(dx * dx + dy * dy) / (1 << L); }
+  // warpAffine prologue (matcher.cpp:92-102)
+  {
+    const double det = A[0] * A[3] - A[2] * A[1];
+    const double invdet = 1.0 / det;
+    g->a00 = (float)(A[3] * invdet); g->a01 = (float)(-A[1] * invdet);
+    g->a10 = (float)(-A[2] * invdet); g->a11 = (float)(A[0] * invdet);
+    g->warp_ok = isnan(g->a00) ? 0 : 1;
+    g->pr0 = (float)f.px[0] / (float)(1 << f.level); g->pr1 = (float)f.px[1] / (float)(1 << f.level);
+  }
+  {
+    float dx = (float)(pAx - pBx), dy = (float)(pAy - pBy);
+    const float z = dx * dx + dy * dy;
+    if (z > 0.0f) { const float n = sqrtf(z); dx /= n; dy /= n; }
+    g->dirx = dx; g->diry = dy;
+  }
+  g->px_mid[0] = (pAx + pBx) / 2.0; g->px_mid[1] = (pAy + pBy) / 2.0;
+  if (g->epi_length < 2.0) { g->mode = EPI_MODE_DIRECT; return; }
+  // x86 (size_t)(double): NaN / out of range -> 2^63 -> "skip epipolar search" (matcher.cpp:283-288)
+  const double q = g->epi_length / 0.7;
+  if (!(q == q) || q >= 9.2e18) { g->n_steps_report = 0x7fffffff; return; }
+  const unsigned long long n_steps = (unsigned long long)q;
+  g->n_steps_report = (int)(n_steps > 0x7fffffffULL ? 0x7fffffffULL : n_steps);
+  g->stepx = ex / (double)n_steps; g->stepy = ey / (double)n_steps;
+  int max_steps = o.max_epi_search_steps;
+  if (max_steps > EPI_MAX_STEPS) max_steps = EPI_MAX_STEPS;
+  if (n_steps > (unsigned long long)max_steps) return;
+  g->n = (int)n_steps + 1;
+  g->Bx0 = Bx - g->stepx; g->By0 = By - g->stepy;
+  g->mode = EPI_MODE_WALK;
+}
 
-  // warp the reference patch (matcher.cpp:251-253)
-  const uint8_t* rimg = ref.lvl[f.level] + (size_t)ref_image * ref.img_stride[f.level];
-  warp_affine_10x10(A, rimg, ref.pitch[f.level], ref.w[f.level], ref.h[f.level], f.px, f.level, L, S->pwb, tid, EPI_BLOCK);
-  __syncthreads();
-  if (tid < 64) S->patch[tid] = S->pwb[((tid >> 3) + 1) * 10 + 1 + (tid & 7)];
-  __syncthreads();
-
+// matcher.cpp:251-340: warp the patch, walk the epipolar segment, refine.  One full warp cooperates.
+__device__ void epi_search_warp(const DevFrame& ref, int ref_image, const DevFrame& cur, int cur_image, const DevCam& cam,
+                                const svob200_feature_ref& f, const EpiGeom& g, const svob200_matcher_opts& o, EpiWarpSmem* S,
+                                int lane, bool always_warp, EpiSearch* out)
+{
+  out->found = 0; out->zmssd_best = 2000 * 64; out->n_evals = 0; out->px_cur[0] = out->px_cur[1] = 0;
+  out->uv_best[0] = out->uv_best[1] = 0; out->h_inv = 0;
+  if (g.reject) return;
+  if (g.mode == EPI_MODE_NONE && !always_warp) return;
+  const int L = g.L;
+  if (g.warp_ok) {
+    const uint8_t* rimg = ref.lvl[f.level] + (size_t)ref_image * ref.img_stride[f.level];
+    const int rp = ref.pitch[f.level], rc = ref.w[f.level], rr = ref.h[f.level];
+    for (int i = lane; i < 100; i += 32) {
+      const int y = i / 10, x = i - y * 10;
+      float p0 = (float)(x - 5), p1 = (float)(y - 5);
+      p0 *= (float)(1 << L); p1 *= (float)(1 << L);
+      const float qx = (g.a00 * p0 + g.a01 * p1) + g.pr0;
+      const float qy = (g.a10 * p0 + g.a11 * p1) + g.pr1;
+      uint8_t v = 0;
+      if (!(qx < 0 || qy < 0 || qx >= rc - 1 || qy >= rr - 1)) v = (uint8_t)interpolate_8u(rimg, rp, qx, qy);
+      S->pwb[i] = v;
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < 64; k += 32) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
+  __syncwarp();
+  if (g.mode == EPI_MODE_NONE) return;
   const uint8_t* cimg = cur.lvl[L] + (size_t)cur_image * cur.img_stride[L];
   const int cpitch = cur.pitch[L], ccols = cur.w[L], crows = cur.h[L];
-  // (px_A-px_B).cast<float>().normalized()
-  float dirx = (float)(pAx - pBx), diry = (float)(pAy - pBy);
-  { const float z = dirx * dirx + diry * diry; if (z > 0.0f) { const float n = sqrtf(z); dirx /= n; diry /= n; } }
-
-  double px_cur0, px_cur1;
-  bool do_align = false;
-  if (epi_length < 2.0) {
-    px_cur0 = (pAx + pBx) / 2.0; px_cur1 = (pAy + pBy) / 2.0;
-    out->px_cur[0] = px_cur0; out->px_cur[1] = px_cur1;
-    do_align = true;
+  double px0, px1;
+  if (g.mode == EPI_MODE_DIRECT) {
+    px0 = g.px_mid[0]; px1 = g.px_mid[1];
+    out->px_cur[0] = px0; out->px_cur[1] = px1;
   } else {
-    // x86 (size_t)(double): NaN / out of range -> 2^63 -> "skip epipolar search" (matcher.cpp:283-288)
-    const double q = epi_length / 0.7;
-    if (!(q == q) || q >= 9.2e18) { out->n_steps = 0x7fffffff; return; }
-    unsigned long long n_steps = (unsigned long long)q;
-    out->n_steps = (int)(n_steps > 0x7fffffffULL ? 0x7fffffffULL : n_steps);
-    const double stepx = ex / (double)n_steps, stepy = ey / (double)n_steps;
-    int max_steps = o.max_epi_search_steps; if (max_steps > EPI_MAX_STEPS - 1) max_steps = EPI_MAX_STEPS - 1;
-    if (n_steps > (unsigned long long)max_steps) return;
-    const int n = (int)n_steps + 1;
-    // the reference's running sums uv += step: x chain on thread 0, y chain on thread 1
-    if (tid < 2) {
-      double uv = (tid == 0 ? Bx : By) - (tid == 0 ? stepx : stepy);
-      const double st = tid == 0 ? stepx : stepy, fxy = tid == 0 ? cam.fx : cam.fy, cxy = tid == 0 ? cam.cx : cam.cy;
-      short* dst = reinterpret_cast<short*>(S->pxi) + tid;
-      for (int i = 0; i < n; ++i, uv += st) {
-        const double p = fxy * uv + cxy;
-        const double v = p / (1 << L) + 0.5;
-        int iv = (v == v) ? (v >= 32767.0 ? 32767 : (v <= -32768.0 ? -32768 : (int)v)) : -32768;
-        dst[2 * (i + 1)] = (short)iv;
-      }
-      dst[0] = 0;                                          // last_checked_pxi(0,0)
-    }
-    __syncthreads();
-    RefPatchRegs rp;
-    load_ref_patch(S->patch, rp);
+    RefPatchRegs rpatch;
+    load_ref_patch(S->patch, rpatch);
     unsigned long long best = ((unsigned long long)(2000 * 64) << 32);   // PatchScore::threshold(), strict <
     int evals = 0;
-    for (int i = tid; i < n; i += EPI_BLOCK) {
-      const short2 c = S->pxi[i + 1], prev = S->pxi[i];
-      if (c.x == prev.x && c.y == prev.y) continue;
-      if (!in_frame_level(cam, c.x, c.y, 8, L)) continue;
-      const int z = zmssd_8x8(rp, cimg + (size_t)(c.y - 4) * cpitch + (c.x - 4), cpitch);
-      ++evals;
-      const unsigned long long key = ((unsigned long long)(unsigned)z << 32) | (unsigned)i;
-      if (key < best) best = key;
+    // the reference's running sums uv += step: x chain on lane 0, y chain on lane 1
+    double uv = lane == 0 ? g.Bx0 : g.By0;
+    const double st = lane == 0 ? g.stepx : g.stepy, fxy = lane == 0 ? cam.fx : cam.fy, cxy = lane == 0 ? cam.cx : cam.cy;
+    const double inv_scale = 1.0 / (double)(1 << L);                     // exact: dividing by 2^L == multiplying by 2^-L
+    short lastv = 0;                                                     // last_checked_pxi(0,0)
+    short* dst = reinterpret_cast<short*>(S->pxi) + lane;
+    for (int base = 0; base < g.n; base += EPI_CHUNK) {
+      const int m = min(EPI_CHUNK, g.n - base);
+      if (lane < 2) {
+        dst[0] = lastv;
+        for (int i = 0; i < m; ++i, uv += st) {
+          const double p = fxy * uv + cxy;
+          const double v = p * inv_scale + 0.5;
+          const int iv = (v == v) ? (v >= 32767.0 ? 32767 : (v <= -32768.0 ? -32768 : (int)v)) : -32768;
+          lastv = (short)iv;
+          dst[2 * (i + 1)] = lastv;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < m; i += 32) {
+        const short2 c = S->pxi[i + 1], prev = S->pxi[i];
+        if (c.x == prev.x && c.y == prev.y) continue;
+        if (!in_frame_level(cam, c.x, c.y, 8, L)) continue;
+        const int z = zmssd_8x8(rpatch, cimg + (size_t)(c.y - 4) * cpitch + (c.x - 4), cpitch);
+        ++evals;
+        const unsigned long long key = ((unsigned long long)(unsigned)z << 32) | (unsigned)(base + i);
+        if (key < best) best = key;
+      }
+      __syncwarp();
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -479,140 +533,179 @@ __device__ void epipolar_match_block(const DevFrame& ref, int ref_image, const D
       if (other < best) best = other;
       evals += __shfl_xor_sync(0xffffffffu, evals, off);
     }
-    if (lane == 0) { S->red[warp] = best; }
-    __syncthreads();
-    if (tid == 0) S->flag = 0;
-    __syncthreads();
-    if (lane == 0) atomicAdd(&S->flag, evals);
-    __syncthreads();
-    for (int w = 0; w < EPI_BLOCK / 32; ++w) if (S->red[w] < best) best = S->red[w];
-    out->n_evals = S->flag;
+    out->n_evals = evals;
     const int zbest = (int)(best >> 32);
     out->zmssd_best = zbest;
     if (!(zbest < 2000 * 64)) return;
     // uv_best: replay the chain up to the winning step
     const int ibest = (int)(best & 0xffffffffu);
-    if (tid < 2) {
-      double uv = (tid == 0 ? Bx : By) - (tid == 0 ? stepx : stepy);
-      const double st = tid == 0 ? stepx : stepy;
-      for (int i = 0; i < ibest; ++i) uv += st;
-      if (tid == 0) S->d0 = uv; else S->d1 = uv;
-    }
-    __syncthreads();
-    const double ubx = S->d0, uby = S->d1;
-    world2cam_uv(cam, ubx, uby, px_cur0, px_cur1);
-    out->px_cur[0] = px_cur0; out->px_cur[1] = px_cur1;
-    if (!o.subpix_refinement) {
-      const v3d fc = normalized3({ubx, uby, 1.0});
-      double depth;
-      if (depth_from_triangulation(T_cur_ref, f_ref, fc, &depth)) { out->depth = depth; out->success = 1; }
-      return;
-    }
-    do_align = true;
+    double ub = lane == 0 ? g.Bx0 : g.By0;
+    if (lane < 2) for (int i = 0; i < ibest; ++i) ub += st;
+    const double ubx = __shfl_sync(0xffffffffu, ub, 0), uby = __shfl_sync(0xffffffffu, ub, 1);
+    world2cam_uv(cam, ubx, uby, px0, px1);
+    out->px_cur[0] = px0; out->px_cur[1] = px1;
+    out->uv_best[0] = ubx; out->uv_best[1] = uby;
+    if (!o.subpix_refinement) { out->found = 2; return; }
   }
-  if (do_align) {
-    // Gauss-Newton patch refinement by warp 0, result broadcast through shared memory
-    if (warp == 0) {
-      double pxs[2] = {px_cur0 / (1 << L), px_cur1 / (1 << L)};
-      double h_inv = 0;
-      bool res;
-      if (o.align_1d) res = align1d_warp(cimg, cpitch, ccols, crows, dirx, diry, S->pwb, S->patch, o.align_max_iter, pxs, &h_inv, &S->al, lane);
-      else res = align2d_warp(cimg, cpitch, ccols, crows, S->pwb, S->patch, o.align_max_iter, pxs, &S->al, lane);
-      if (lane == 0) { S->flag = res ? 1 : 0; S->d0 = pxs[0]; S->d1 = pxs[1]; S->red[0] = (unsigned long long)__double_as_longlong(h_inv); }
-    }
-    __syncthreads();
-    out->h_inv = __longlong_as_double((long long)S->red[0]);
-    if (S->flag) {
-      px_cur0 = S->d0 * (1 << L); px_cur1 = S->d1 * (1 << L);
-      out->px_cur[0] = px_cur0; out->px_cur[1] = px_cur1;
-      double depth;
-      if (depth_from_triangulation(T_cur_ref, f_ref, cam2world(cam, px_cur0, px_cur1), &depth)) { out->depth = depth; out->success = 1; }
-    }
-  }
+  double pxs[2] = {px0 / (1 << L), px1 / (1 << L)};
+  double h_inv = 0;
+  bool res;
+  if (o.align_1d) res = align1d_warp(cimg, cpitch, ccols, crows, g.dirx, g.diry, S->pwb, S->patch, o.align_max_iter, pxs, &h_inv, &S->al, lane);
+  else res = align2d_warp(cimg, cpitch, ccols, crows, S->pwb, S->patch, o.align_max_iter, pxs, &S->al, lane);
+  out->h_inv = h_inv;
+  if (res) { out->px_cur[0] = pxs[0] * (1 << L); out->px_cur[1] = pxs[1] * (1 << L); out->found = 1; }
 }
 
-__global__ void __launch_bounds__(EPI_BLOCK) epipolar_kernel(const DevFrame* frames, const int* ref_slot, int cur_slot, DevCam cam,
-                                                             int n, const svob200_feature_ref* ftrs, const double* d,
-                                                             svob200_matcher_opts o, svob200_epi_result* results)
+// matcher.cpp:269-276 / :341-351: triangulate from the matched pixel (per thread)
+__device__ inline bool epi_finish(const DevCam& cam, const svob200_feature_ref& f, const double* T_cur_ref, const EpiSearch& s, double* depth)
 {
-  __shared__ EpiSmem S;
-  const int i = blockIdx.x;
+  v3d fc;
+  if (s.found == 1) fc = cam2world(cam, s.px_cur[0], s.px_cur[1]);
+  else if (s.found == 2) fc = normalized3({s.uv_best[0], s.uv_best[1], 1.0});
+  else return false;
+  return depth_from_triangulation(T_cur_ref, {f.f[0], f.f[1], f.f[2]}, fc, depth);
+}
+
+// stand-alone epipolar query: one warp per query, the three phases back to back
+struct EpiQuerySmem { EpiWarpSmem w; EpiGeom g; };
+
+__global__ void __launch_bounds__(128) epipolar_kernel(const DevFrame* frames, const int* ref_slot, int cur_slot, DevCam cam,
+                                                       int n, const svob200_feature_ref* ftrs, const double* d,
+                                                       svob200_matcher_opts o, svob200_epi_result* results)
+{
+  __shared__ EpiQuerySmem SM[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 4 + warp;
   if (i >= n) return;
+  EpiQuerySmem* S = &SM[warp];
   const svob200_feature_ref f = ftrs[i];
-  EpiOut out;
-  epipolar_match_block(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, f.T_cur_ref,
-                       d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &S, &out);
-  __syncthreads();
+  for (int k = lane; k < 100; k += 32) S->w.pwb[k] = 0;
+  if (lane == 0) epi_geometry(cam, f, f.T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &S->g);
+  __syncwarp();
+  const EpiGeom g = S->g;
+  EpiSearch sr;
+  epi_search_warp(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, g, o, &S->w, lane, true, &sr);
+  double depth = 0;
+  const bool ok = epi_finish(cam, f, g.T_cur_ref, sr, &depth);
+  __syncwarp();
   svob200_epi_result* R = &results[i];
-  if (threadIdx.x == 0) {
-    R->success = out.success; R->search_level = out.search_level; R->reject = out.reject; R->zmssd_best = out.zmssd_best;
-    R->n_evals = out.n_evals; R->n_steps = out.n_steps; R->depth = out.depth; R->px_cur[0] = out.px_cur[0]; R->px_cur[1] = out.px_cur[1];
-    R->epi_length = out.epi_length; R->h_inv = out.h_inv;
-    for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = out.A[k];
+  if (lane == 0) {
+    R->success = ok ? 1 : 0; R->search_level = g.L; R->reject = g.reject; R->zmssd_best = sr.zmssd_best;
+    R->n_evals = sr.n_evals; R->n_steps = g.n_steps_report; R->depth = ok ? depth : 0.0;
+    R->px_cur[0] = sr.px_cur[0]; R->px_cur[1] = sr.px_cur[1];
+    R->epi_length = g.epi_length; R->h_inv = sr.h_inv;
+    for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g.A[k];
   }
-  if (threadIdx.x < 100) R->patch_with_border[threadIdx.x] = out.reject ? 0 : S.pwb[threadIdx.x];
-  if (threadIdx.x < 64) R->patch[threadIdx.x] = out.reject ? 0 : S.patch[threadIdx.x];
+  for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = g.reject ? 0 : S->w.pwb[k];
+  for (int k = lane; k < 64; k += 32) R->patch[k] = g.reject ? 0 : S->w.patch[k];
 }
 
-// loop body of DepthFilter::updateSeeds (depth_filter.cpp:250-340), one CTA per seed
-__global__ void __launch_bounds__(EPI_BLOCK) seeds_update_kernel(const DevFrame* frames, const int* ref_slot, int cur_slot, DevCam cam,
-                                                                 int n, const svob200_feature_ref* ftrs, const double* T_ref_w_all,
-                                                                 const double* T_cur_w_all, svob200_matcher_opts o, double conv_thresh,
-                                                                 svob200_seed* seeds, svob200_seed_obs* obs)
+// ---------------------------------------------------------------- depth filter: DepthFilter::updateSeeds loop body
+// (depth_filter.cpp:250-340) as three kernels over all seeds
+struct SeedPre {
+  int status;                  // 0 = run the matcher; else the final status (BEHIND / NOT_IN_FRAME)
+  float z_inv_min;
+  double t_ref_cur[3];         // translation of T_ref_cur (computeTau)
+};
+
+// phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry
+__global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* T_ref_w_all,
+                                                         const double* T_cur_w_all, svob200_matcher_opts o, const svob200_seed* seeds,
+                                                         SeedPre* pre, EpiGeom* geom)
 {
-  __shared__ EpiSmem S;
-  const int i = blockIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const svob200_feature_ref f = ftrs[i];
-  svob200_seed s = seeds[i];
+  const svob200_seed s = seeds[i];
   const double* T_ref_w = T_ref_w_all + 7 * (size_t)i;
   const double* T_cur_w = T_cur_w_all + 7 * (size_t)f.cur_image;
-  int status;
-  EpiOut out;
-  out.search_level = 0; out.zmssd_best = 2000 * 64; out.n_evals = 0; out.depth = 0; out.px_cur[0] = out.px_cur[1] = 0; out.epi_length = 0;
   double Tcw_inv[7], T_ref_cur[7], T_cur_ref[7];
   se3_inverse(T_cur_w, Tcw_inv);
   se3_mul(T_ref_w, Tcw_inv, T_ref_cur);                              // depth_filter.cpp:263
   se3_inverse(T_ref_cur, T_cur_ref);
+  SeedPre p;
+  p.status = 0; p.z_inv_min = 0.f;
+  p.t_ref_cur[0] = T_ref_cur[0]; p.t_ref_cur[1] = T_ref_cur[1]; p.t_ref_cur[2] = T_ref_cur[2];
   const double inv_mu = 1.0 / s.mu;
   const v3d xyz_f = se3_transform(T_cur_ref, {inv_mu * f.f[0], inv_mu * f.f[1], inv_mu * f.f[2]});
-  bool done = false;
-  if (xyz_f.z < 0.0) { status = SVOB200_SEED_BEHIND; done = true; }
-  if (!done) {
+  if (xyz_f.z < 0.0) p.status = SVOB200_SEED_BEHIND;
+  else {
     double pxf, pyf;
     world2cam(cam, xyz_f, pxf, pyf);
-    if (!in_frame(cam, (int)pxf, (int)pyf, 0)) { status = SVOB200_SEED_NOT_IN_FRAME; done = true; }
+    if (!in_frame(cam, (int)pxf, (int)pyf, 0)) p.status = SVOB200_SEED_NOT_IN_FRAME;
   }
-  if (!done) {
+  if (p.status == 0) {
     const float z_inv_min = s.mu + sqrtf(s.sigma2);
     const float z_inv_max = fmaxf(s.mu - sqrtf(s.sigma2), 0.00000001f);
+    p.z_inv_min = z_inv_min;
     double Trw_inv[7], T_cur_ref_m[7];
     se3_inverse(T_ref_w, Trw_inv);
     se3_mul(T_cur_w, Trw_inv, T_cur_ref_m);                          // matcher.cpp:216
-    epipolar_match_block(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, T_cur_ref_m,
-                         1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &S, &out);
-    if (!out.success) {
+    epi_geometry(cam, f, T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &geom[i]);
+  }
+  pre[i] = p;
+}
+
+// phase 2: warp per seed — patch warp, ZMSSD walk, LK refinement
+__global__ void __launch_bounds__(128) seeds_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n,
+                                                           const svob200_feature_ref* ftrs, svob200_matcher_opts o,
+                                                           const SeedPre* pre, const EpiGeom* geom, EpiSearch* search)
+{
+  __shared__ EpiWarpSmem SM[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= n) return;
+  if (pre[i].status != 0) return;
+  const EpiGeom g = geom[i];
+  if (g.reject || g.mode == EPI_MODE_NONE) {
+    if (lane == 0) { EpiSearch z; z.found = 0; z.zmssd_best = 2000 * 64; z.n_evals = 0; z.px_cur[0] = z.px_cur[1] = 0; z.uv_best[0] = z.uv_best[1] = 0; z.h_inv = 0; search[i] = z; }
+    return;
+  }
+  const svob200_feature_ref f = ftrs[i];
+  EpiSearch sr;
+  epi_search_warp(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, g, o, &SM[warp], lane, false, &sr);
+  if (lane == 0) search[i] = sr;
+}
+
+// phase 3: thread per seed — triangulation, tau, Gaussian x Beta update, status
+__global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, double conv_thresh,
+                                                           const SeedPre* pre, const EpiGeom* geom, const EpiSearch* search,
+                                                           svob200_seed* seeds, svob200_seed_obs* obs)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SeedPre p = pre[i];
+  svob200_seed_obs ob;
+  ob.status = p.status; ob.search_level = 0; ob.zmssd_best = 2000 * 64; ob.n_evals = 0; ob.z = 0; ob.px_cur[0] = ob.px_cur[1] = 0; ob.epi_length = 0;
+  if (p.status == 0) {
+    const svob200_feature_ref f = ftrs[i];
+    const EpiSearch sr = search[i];
+    const EpiGeom* g = &geom[i];
+    svob200_seed s = seeds[i];
+    ob.search_level = g->L; ob.zmssd_best = sr.zmssd_best; ob.n_evals = sr.n_evals; ob.epi_length = g->epi_length;
+    ob.px_cur[0] = sr.px_cur[0]; ob.px_cur[1] = sr.px_cur[1];
+    double T_cur_ref[7];
+    for (int k = 0; k < 7; ++k) T_cur_ref[k] = g->T_cur_ref[k];
+    double z = 0;
+    if (!epi_finish(cam, f, T_cur_ref, sr, &z)) {
       s.b++;                                                         // depth_filter.cpp:286
-      status = SVOB200_SEED_NO_MATCH;
+      ob.status = SVOB200_SEED_NO_MATCH;
     } else {
-      const double z = out.depth;
+      ob.z = z;
       const double focal_length = fabs(cam.fx);
       const double px_error_angle = atan(1.0 / (2.0 * focal_length)) * 2.0;
+      const double T_ref_cur[7] = {p.t_ref_cur[0], p.t_ref_cur[1], p.t_ref_cur[2], 0, 0, 0, 1};
       const double tau = compute_tau(T_ref_cur, {f.f[0], f.f[1], f.f[2]}, z, px_error_angle);
       const double zmt = z - tau;
       const double tau_inverse = 0.5 * (1.0 / (0.0000001 > zmt ? 0.0000001 : zmt) - 1.0 / (z + tau));
       update_seed((float)(1. / z), (float)(tau_inverse * tau_inverse), &s);
-      if ((double)sqrtf(s.sigma2) < (double)s.z_range / conv_thresh) status = SVOB200_SEED_CONVERGED;
-      else if (isnan(z_inv_min)) status = SVOB200_SEED_NAN_ERASED;
-      else status = SVOB200_SEED_UPDATED;
+      if ((double)sqrtf(s.sigma2) < (double)s.z_range / conv_thresh) ob.status = SVOB200_SEED_CONVERGED;
+      else if (isnan(p.z_inv_min)) ob.status = SVOB200_SEED_NAN_ERASED;
+      else ob.status = SVOB200_SEED_UPDATED;
     }
-  }
-  if (threadIdx.x == 0) {
     seeds[i] = s;
-    svob200_seed_obs* ob = &obs[i];
-    ob->status = status; ob->search_level = out.search_level; ob->zmssd_best = out.zmssd_best; ob->n_evals = out.n_evals;
-    ob->z = out.depth; ob->px_cur[0] = out.px_cur[0]; ob->px_cur[1] = out.px_cur[1]; ob->epi_length = out.epi_length;
   }
+  obs[i] = ob;
 }
 
 // ---------------------------------------------------------------- findMatchDirect: one warp per candidate
@@ -754,19 +847,33 @@ int launch_epipolar(const DevFrame* d_frames, const int* d_ref_slot, int cur_slo
                     svob200_epi_result* d_results, cudaStream_t s, long long* launches)
 {
   if (n <= 0) return 0;
-  epipolar_kernel<<<n, EPI_BLOCK, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_d, opts, d_results);
+  epipolar_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_d, opts, d_results);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+size_t seeds_scratch_bytes(int n)
+{
+  const size_t m = (size_t)(n > 0 ? n : 1);
+  return m * (sizeof(SeedPre) + sizeof(EpiGeom) + sizeof(EpiSearch)) + 1024;
 }
 
 int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
                         const svob200_feature_ref* d_ftrs, const double* d_T_ref_w, const double* d_T_cur_w,
                         svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs,
-                        cudaStream_t s, long long* launches)
+                        void* d_scratch, cudaStream_t s, long long* launches)
 {
+  (void)d_ref_slot;
   if (n <= 0) return 0;
-  seeds_update_kernel<<<n, EPI_BLOCK, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, conv_thresh, d_seeds, d_obs);
-  ++*launches;
+  const size_t m = (size_t)n;
+  char* p = static_cast<char*>(d_scratch);
+  EpiGeom* geom = reinterpret_cast<EpiGeom*>(p); p += ((m * sizeof(EpiGeom) + 255) & ~(size_t)255);
+  EpiSearch* search = reinterpret_cast<EpiSearch*>(p); p += ((m * sizeof(EpiSearch) + 255) & ~(size_t)255);
+  SeedPre* pre = reinterpret_cast<SeedPre*>(p);
+  seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, geom);
+  seeds_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, pre, geom, search);
+  seeds_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, conv_thresh, pre, geom, search, d_seeds, d_obs);
+  *launches += 3;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -5,7 +5,7 @@
 // It chains the operators exactly the way FrameHandlerMono::processFrame + DepthFilter do
 // (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), minus the host-only stages that are
 // out of scope (pose_optimizer, map management): everything between the operators that the
-// reference does in host code is done by the glue kernels, so a step is 10 launches on one stream
+// reference does in host code is done by the glue kernels, so a step is 12 launches on one stream
 // with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
 // H2D of the small per-step inputs and one D2H of the per-sequence results.
 #include "ctx_internal.h"
@@ -89,6 +89,7 @@ struct svob200_tracker {
   svob200_seed_obs* d_obs = nullptr;
   svob200_step_stats* d_stats = nullptr;
   void* d_align_scratch = nullptr;
+  void* d_seed_scratch = nullptr;
   uint8_t* h_pinned = nullptr; size_t h_cap = 0;
   std::vector<void*> owned;
   // optional per-stage CUDA-event timing (bench.py's stage breakdown / roofline)
@@ -176,6 +177,9 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
     uint8_t* p = nullptr;
     if (int e = dalloc(ctx, &p, sparse_align_scratch_bytes(N))) return e;
     t->owned.push_back(p); t->d_align_scratch = p;
+    uint8_t* q = nullptr;
+    if (int e = dalloc(ctx, &q, seeds_scratch_bytes(S))) return e;
+    t->owned.push_back(q); t->d_seed_scratch = q;
   }
 #undef DA
   cudaStream_t s = ctx->stream;
@@ -275,7 +279,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
   STAGE_MARK(5);
   // 7. DepthFilter::updateSeeds(cur)
-  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, S, t->d_seed_ftrs, t->d_T_kf_seed, t->d_T_cur, t->mopts, t->conv_thresh, t->d_seeds, t->d_obs, s, &ctx->launches))
+  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, S, t->d_seed_ftrs, t->d_T_kf_seed, t->d_T_cur, t->mopts, t->conv_thresh, t->d_seeds, t->d_obs, t->d_seed_scratch, s, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
   STAGE_MARK(6);
   // 8. per-sequence statistics (+ steady-state re-seeding)
@@ -312,7 +316,7 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
   return SVOB200_OK;
 }
 
-int svob200_tracker_launches_per_step(void) { return 10; }
+int svob200_tracker_launches_per_step(void) { return 12; }
 
 // stage timing: 7 durations [frame copy/bind + pyramid + per-step input copy, features_prepare + init_pose,
 // sparse_align, compose + reproject_prepare, match_direct, seeds_update, stats]

@@ -220,7 +220,7 @@ int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n
  * (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), restricted to the hot-path operators:
  *   pyramid(cur) -> SparseImgAlign::run(last, cur) -> Matcher::findMatchDirect for every map point of
  *   the keyframe -> DepthFilter::updateSeeds(cur) for the keyframe's seeds,
- * for a batch of independent sequences, 10 kernel launches on one stream, no host round trip.
+ * for a batch of independent sequences, 12 kernel launches on one stream, no host round trip.
  * Finished seeds (converged / NaN) are re-initialised when `reseed` is set, which keeps the
  * per-frame workload stationary for benchmarking (0 = leave them, the caller mutates its list). */
 typedef struct svob200_tracker svob200_tracker;
