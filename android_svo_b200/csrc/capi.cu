@@ -218,6 +218,18 @@ int svob200_frame_bind(svob200_ctx* ctx, int64_t frame_id, const uint8_t* dev_gr
   return build_levels(ctx, r, round_modes);
 }
 
+// bind level 0 without building the pyramid (tracker: the pyramid launch is part of the step)
+int svob200_frame_bind_only(svob200_ctx* ctx, int64_t frame_id, const uint8_t* dev_gray, int stride)
+{
+  FrameRec* r = ctx ? find_frame(ctx, frame_id) : nullptr;
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (stride < r->f.w[0] || (stride & 15) || (reinterpret_cast<uintptr_t>(dev_gray) & 15))
+    return fail(ctx, SVOB200_ERR_ARG, "frame_bind: buffer and stride must be 16-byte aligned and stride >= width");
+  r->f.lvl[0] = const_cast<uint8_t*>(dev_gray); r->f.pitch[0] = stride; r->f.img_stride[0] = (unsigned long long)stride * r->f.h[0];
+  CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
+  return SVOB200_OK;
+}
+
 int svob200_frame_download(svob200_ctx* ctx, int64_t frame_id, int image, int level, uint8_t* out, int out_stride)
 {
   if (!ctx || !out) return fail(ctx, SVOB200_ERR_ARG, "frame_download: null argument");
@@ -471,7 +483,7 @@ int svob200_seeds_update(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_c
   if (ctx->d_scratch.ensure(seeds_scratch_bytes(n)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "seeds_update: scratch alloc failed");
   if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_tr),
                           st.dev<double>(i_tc), *opts, conv_thresh, st.dev<svob200_seed>(i_s), st.dev<svob200_seed_obs>(i_o),
-                          ctx->d_scratch.p, ctx->stream, &ctx->launches))
+                          ctx->d_scratch.p, n, 0, ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "seeds_update launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return st.download();
 }

@@ -80,3 +80,5 @@ inline int ensure_host_stage(svob200_ctx* ctx, size_t n)
   return 0;
 }
 
+
+extern "C" int svob200_frame_bind_only(svob200_ctx* ctx, int64_t frame_id, const uint8_t* dev_gray, int stride);

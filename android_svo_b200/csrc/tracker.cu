@@ -5,7 +5,7 @@
 // It chains the operators exactly the way FrameHandlerMono::processFrame + DepthFilter do
 // (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), minus the host-only stages that are
 // out of scope (pose_optimizer, map management): everything between the operators that the
-// reference does in host code is done by the glue kernels, so a step is 12 launches on one stream
+// reference does in host code is done by the glue kernels, so a step is 13 launches on one stream
 // with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
 // H2D of the small per-step inputs and one D2H of the per-sequence results.
 #include "ctx_internal.h"
@@ -92,11 +92,15 @@ struct svob200_tracker {
   void* d_seed_scratch = nullptr;
   uint8_t* h_pinned = nullptr; size_t h_cap = 0;
   std::vector<void*> owned;
+  std::vector<int> h_ftr_off, h_seed_off;
+  int chunk = 256;                     // sequences per H2D/compute pipeline chunk (host mode)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
   // optional per-stage CUDA-event timing (bench.py's stage breakdown / roofline)
   bool profiling = false;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
-#define STAGE_MARK(k) do { if (t->profiling) cudaEventRecord(t->ev[k], s); } while (0)
+
 
 extern "C" {
 
@@ -128,6 +132,9 @@ void svob200_tracker_destroy(svob200_tracker* t)
   for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur}) svob200_frame_release(ctx, id);
   for (void* p : t->owned) cudaFree(p);
   if (t->h_pinned) cudaFreeHost(t->h_pinned);
+  for (auto e : t->chunk_ev) cudaEventDestroy(e);
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  for (int k = 0; k < 8; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   delete t;
 }
 
@@ -144,6 +151,8 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   if (int e = svob200_frame_upload(ctx, t->fid_kf, imgs, stride, nullptr, SVOB200_MEM_HOST)) return e;
   const int N = ftr_offsets[B], S = seed_offsets[B];
   t->N = N; t->S = S;
+  t->h_ftr_off.assign(ftr_offsets, ftr_offsets + B + 1);
+  t->h_seed_off.assign(seed_offsets, seed_offsets + B + 1);
   for (int b = 0; b < B; ++b) t->max_per = std::max(t->max_per, ftr_offsets[b + 1] - ftr_offsets[b]);
   const int slot = svob200_frame_slot(ctx, t->fid_kf);
   std::vector<svob200_feature_ref> ftrs(N), sftrs(S);
@@ -219,34 +228,95 @@ int svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride
   return svob200_frame_upload(t->ctx, t->fid_last, imgs, stride, nullptr, mem);
 }
 
+// sub-batch view of a frame batch: images [c0, c0+cnt)
+static DevFrame frame_view(const DevFrame& f, int c0, int cnt)
+{
+  DevFrame v = f;
+  for (int l = 0; l < f.n_levels; ++l) v.lvl[l] = f.lvl[l] + (size_t)c0 * f.img_stride[l];
+  v.batch = cnt;
+  return v;
+}
+
+// all stages of one step for the sequences [c0, c1) on the compute stream (level 0 of cur is in place)
+static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last, const double* d_last_px, bool marks)
+{
+  svob200_ctx* ctx = t->ctx;
+  cudaStream_t s = ctx->stream;
+  const DevCam cam = to_cam(&t->cam);
+  FrameRec* last = find_frame(ctx, t->fid_last);
+  FrameRec* cur = find_frame(ctx, t->fid_cur);
+  const int cnt = c1 - c0;
+  const int f0 = t->h_ftr_off[c0], nf = t->h_ftr_off[c1] - f0;
+  const int s0 = t->h_seed_off[c0], ns = t->h_seed_off[c1] - s0;
+  const DevFrame vlast = frame_view(last->f, c0, cnt), vcur = frame_view(cur->f, c0, cnt);
+#define MARK(k) do { if (marks && t->profiling) cudaEventRecord(t->ev[k], s); } while (0)
+  // 1. fused pyramid of the current frames
+  {
+    int modes[SVOB200_MAX_LEVELS];
+    for (int l = 0; l + 1 < vcur.n_levels; ++l) modes[l] = svob200_round_mode_x86(vcur.w[l]);
+    if (launch_pyramid(vcur, modes, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: pyramid launch failed");
+  }
+  MARK(1);
+  // 2. Feature ctor / xyz_ref of the last frame's features, initial relative pose
+  if (launch_features_prepare(cam, nf, d_last_px + 2 * (size_t)f0, t->d_pt_world + 3 * (size_t)f0, t->d_ftr_image + f0, d_T_last, nullptr,
+                              t->d_xyz + 3 * (size_t)f0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: features_prepare failed");
+  init_pose_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, d_T_last + 7 * (size_t)c0, t->d_T_init + 7 * (size_t)c0); ++ctx->launches;
+  MARK(2);
+  // 3. SparseImgAlign::run(last, cur)
+  if (launch_sparse_align(vlast, vcur, cam, cnt, t->N, t->max_per, t->d_ftr_off + c0, d_last_px, t->d_xyz, t->d_has_point,
+                          t->d_T_init + 7 * (size_t)c0, t->aopts, t->d_align + c0, t->d_align_scratch, s, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: sparse_align failed");
+  MARK(3);
+  // 4. cur.T_f_w = T_cur_from_ref * last.T_f_w ; reprojection of the map points
+  if (launch_compose_poses(cnt, t->d_align + c0, d_T_last + 7 * (size_t)c0, t->d_T_cur + 7 * (size_t)c0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: compose failed");
+  if (launch_reproject_prepare(cam, nf, t->d_ftrs + f0, t->d_pt_world + 3 * (size_t)f0, t->d_T_kf_ftr + 7 * (size_t)f0, t->d_T_cur,
+                               t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
+  MARK(4);
+  // 5. Matcher::findMatchDirect per map point (keyframe patch -> current frame)
+  if (launch_match_direct_compact(ctx->d_table, cur->slot, cam, nf, t->d_ftrs + f0, t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->mopts,
+                                  t->d_px_out + 2 * (size_t)f0, t->d_match_ok + f0, s, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
+  MARK(5);
+  // 6. DepthFilter::updateSeeds(cur)
+  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
+                          t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
+  MARK(6);
+  // 7. per-sequence statistics (+ steady-state re-seeding)
+  step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
+                                        t->d_seeds, t->seed_init, t->reseed, t->d_stats + c0);
+  ++ctx->launches;
+  if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
+  MARK(7);
+#undef MARK
+  return 0;
+}
+
 int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride, const double* T_last_w, const double* last_px,
                          svob200_step_stats* stats, double* px_refined, int* match_ok, int mem)
 {
   if (!t || !cur_imgs || !T_last_w || !last_px) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
   if (!t->d_stats) return fail(ctx, SVOB200_ERR_ARG, "tracker_step: set_keyframe first");
-  const int B = t->batch, N = t->N, S = t->S;
+  const int B = t->batch, N = t->N;
   cudaStream_t s = ctx->stream;
-  const DevCam cam = to_cam(&t->cam);
-  STAGE_MARK(0);
-  // 1. current frame: level 0 in place (device) or one H2D copy (host), then the fused pyramid kernel
-  if (mem == SVOB200_MEM_DEVICE) { if (int e = svob200_frame_bind(ctx, t->fid_cur, cur_imgs, stride, nullptr)) return e; }
-  else {
+  const size_t in_bytes = sizeof(double) * (7 * (size_t)B + 2 * (size_t)N);
+  if (t->profiling) cudaEventRecord(t->ev[0], s);
+  if (mem == SVOB200_MEM_DEVICE) {
+    // level 0 of the current frames aliases the caller's device buffer: no copy at all
+    if (int e = svob200_frame_bind_only(ctx, t->fid_cur, cur_imgs, stride)) return e;
+    if (int e = run_range(t, 0, B, T_last_w, last_px, true)) return e;
+    if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
+    if (px_refined) CU(cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s));
+    if (match_ok) CU(cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s));
+  } else {
+    // host buffers: the frame copy is split into chunks on a copy stream so that chunk c+1 crosses
+    // PCIe while chunk c is being processed; one small H2D for the per-step inputs, one D2H for results
     FrameRec* r = find_frame(ctx, t->fid_cur);
     if (r->f.lvl[0] != r->own_l0) {   // drop an earlier device binding
       r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
       CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, s));
     }
-    CU(cudaMemcpy2DAsync(r->f.lvl[0], r->f.pitch[0], cur_imgs, stride, r->f.w[0], (size_t)r->f.h[0] * B, cudaMemcpyHostToDevice, s));
-    int modes[SVOB200_MAX_LEVELS];
-    for (int l = 0; l + 1 < r->f.n_levels; ++l) modes[l] = svob200_round_mode_x86(r->f.w[l]);
-    if (launch_pyramid(r->f, modes, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: pyramid launch failed");
-  }
-  // 2. small per-step inputs
-  const size_t in_bytes = sizeof(double) * (7 * (size_t)B + 2 * (size_t)N);
-  const double* d_T_last; const double* d_last_px;
-  if (mem == SVOB200_MEM_DEVICE) { d_T_last = T_last_w; d_last_px = last_px; }
-  else {
     const size_t out_bytes = sizeof(svob200_step_stats) * B + sizeof(double) * 2 * (size_t)N + sizeof(int) * (size_t)N;
     if (t->h_cap < in_bytes + out_bytes + 512) {
       if (t->h_pinned) cudaFreeHost(t->h_pinned);
@@ -257,42 +327,27 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     memcpy(t->h_pinned, T_last_w, sizeof(double) * 7 * B);
     memcpy(t->h_pinned + sizeof(double) * 7 * B, last_px, sizeof(double) * 2 * (size_t)N);
     CU(cudaMemcpyAsync(t->d_step_in, t->h_pinned, in_bytes, cudaMemcpyHostToDevice, s));
-    d_T_last = t->d_step_in; d_last_px = t->d_step_in + 7 * (size_t)B;
-  }
-  FrameRec* last = find_frame(ctx, t->fid_last);
-  FrameRec* cur = find_frame(ctx, t->fid_cur);
-  STAGE_MARK(1);
-  // 3. Feature/xyz_ref of the last frame's features, initial relative pose
-  if (launch_features_prepare(cam, N, d_last_px, t->d_pt_world, t->d_ftr_image, d_T_last, nullptr, t->d_xyz, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: features_prepare failed");
-  init_pose_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, d_T_last, t->d_T_init); ++ctx->launches;
-  STAGE_MARK(2);
-  // 4. SparseImgAlign::run(last, cur)
-  if (launch_sparse_align(last->f, cur->f, cam, B, N, t->max_per, t->d_ftr_off, d_last_px, t->d_xyz, t->d_has_point, t->d_T_init, t->aopts,
-                          t->d_align, t->d_align_scratch, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: sparse_align failed");
-  STAGE_MARK(3);
-  // 5. cur.T_f_w = T_cur_from_ref * last.T_f_w ; reprojection of the map points
-  if (launch_compose_poses(B, t->d_align, d_T_last, t->d_T_cur, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: compose failed");
-  if (launch_reproject_prepare(cam, N, t->d_ftrs, t->d_pt_world, t->d_T_kf_ftr, t->d_T_cur, t->d_depth_ref, t->d_px_in, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
-  STAGE_MARK(4);
-  // 6. Matcher::findMatchDirect per map point (keyframe patch -> current frame)
-  if (launch_match_direct_compact(ctx->d_table, cur->slot, cam, N, t->d_ftrs, t->d_depth_ref, t->d_px_in, t->mopts, t->d_px_out, t->d_match_ok, s, &ctx->launches))
-    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
-  STAGE_MARK(5);
-  // 7. DepthFilter::updateSeeds(cur)
-  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, S, t->d_seed_ftrs, t->d_T_kf_seed, t->d_T_cur, t->mopts, t->conv_thresh, t->d_seeds, t->d_obs, t->d_seed_scratch, s, &ctx->launches))
-    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
-  STAGE_MARK(6);
-  // 8. per-sequence statistics (+ steady-state re-seeding)
-  step_stats_kernel<<<B, 128, 0, s>>>(t->d_ftr_off, t->d_seed_off, t->d_align, t->d_T_cur, t->d_match_ok, t->d_obs, t->d_seeds, t->seed_init, t->reseed, t->d_stats);
-  ++ctx->launches;
-  if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
-  STAGE_MARK(7);
-  // 9. results
-  if (mem == SVOB200_MEM_DEVICE) {
-    if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
-    if (px_refined) CU(cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s));
-    if (match_ok) CU(cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s));
-  } else {
+    const double* d_T_last = t->d_step_in;
+    const double* d_last_px = t->d_step_in + 7 * (size_t)B;
+    const int chunk = (t->profiling || B <= t->chunk) ? B : t->chunk;
+    const int n_chunks = (B + chunk - 1) / chunk;
+    if (!t->copy_stream) CU(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    while ((int)t->chunk_ev.size() < n_chunks + 1) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); t->chunk_ev.push_back(e); }
+    // the copy stream must not overwrite level 0 before earlier work on the compute stream is done
+    CU(cudaEventRecord(t->chunk_ev[n_chunks], s));
+    CU(cudaStreamWaitEvent(t->copy_stream, t->chunk_ev[n_chunks], 0));
+    const int h = r->f.h[0];
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c * chunk, c1 = std::min(B, c0 + chunk);
+      CU(cudaMemcpy2DAsync(r->f.lvl[0] + (size_t)c0 * r->f.img_stride[0], r->f.pitch[0], cur_imgs + (size_t)c0 * h * stride, stride,
+                           r->f.w[0], (size_t)h * (c1 - c0), cudaMemcpyHostToDevice, t->copy_stream));
+      CU(cudaEventRecord(t->chunk_ev[c], t->copy_stream));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c * chunk, c1 = std::min(B, c0 + chunk);
+      CU(cudaStreamWaitEvent(s, t->chunk_ev[c], 0));
+      if (int e = run_range(t, c0, c1, d_T_last, d_last_px, n_chunks == 1)) return e;
+    }
     uint8_t* ho = t->h_pinned + ((in_bytes + 255) & ~(size_t)255);
     uint8_t* h_stats = ho; uint8_t* h_px = h_stats + sizeof(svob200_step_stats) * B; uint8_t* h_ok = h_px + sizeof(double) * 2 * (size_t)N;
     if (stats) CU(cudaMemcpyAsync(h_stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToHost, s));
@@ -316,7 +371,7 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
   return SVOB200_OK;
 }
 
-int svob200_tracker_launches_per_step(void) { return 12; }
+int svob200_tracker_launches_per_step(void) { return 13; }
 
 // stage timing: 7 durations [frame copy/bind + pyramid + per-step input copy, features_prepare + init_pose,
 // sparse_align, compose + reproject_prepare, match_direct, seeds_update, stats]

@@ -282,7 +282,7 @@ class Oracle:
         img = u8(img)
         rp = u8(ref_patch)
         off = (y - 4) * img.shape[1] + (x - 4)
-        ptr = C.cast(C.c_void_p(img.ctypes.data + off), c_u8p)
+        ptr = C.cast(C.c_void_p(int(img.ctypes.data) + int(off)), c_u8p)
         return self.lib.svo_oracle_zmssd(_p(rp, c_u8p), ptr, img.shape[1])
 
     def matcher_opts(self, n_pyr_levels, **kw):
@@ -394,7 +394,7 @@ class Ref:
     def zmssd(self, ref_patch, img, x, y):
         img = u8(img)
         off = (y - 4) * img.shape[1] + (x - 4)
-        ptr = C.cast(C.c_void_p(img.ctypes.data + off), c_u8p)
+        ptr = C.cast(C.c_void_p(int(img.ctypes.data) + int(off)), c_u8p)
         return self.lib.svo_ref_zmssd(_p(u8(ref_patch), c_u8p), ptr, img.shape[1])
 
     def fast_detect(self, img, cam, n_detect_levels, cell, thr, occ_px=None):
