@@ -56,7 +56,7 @@ __device__ __forceinline__ int best_search_level(const double* A, int max_level)
 // vision.h:19-36
 __device__ __forceinline__ float interpolate_8u(const uint8_t* img, int stride, float u, float v)
 {
-  const int x = (int)floor((double)u), y = (int)floor((double)v);
+  const int x = (int)floorf(u), y = (int)floorf(v);     // == floor((double)u) for a float argument
   const float sx = u - x, sy = v - y;
   const float w00 = (1.0f - sx) * (1.0f - sy);
   const float w01 = (1.0f - sx) * sy;
@@ -94,7 +94,7 @@ __device__ inline bool warp_affine_10x10(const double* A, const uint8_t* img, in
 // ---------------------------------------------------------------- feature alignment
 struct AlignSmem {
   float dx[64], dy[64];
-  float p0[64], p1[64], p2[64];
+  float term[5][64];       // per-pixel terms of the sequential float sums, one row per chain
 };
 
 // Eigen Matrix3f::inverse(), cofactor path (Eigen/src/LU/InverseImpl.h)
@@ -112,19 +112,21 @@ __device__ __forceinline__ void inv3f(const float* m, float* r)
 #undef M_
 }
 
-// sequential `acc += v[i]` / `acc -= v[i]` over 64 shared-memory floats
-__device__ __forceinline__ float chain_add64(const float* v)
+// The reference accumulates its float sums pixel by pixel (`acc += term`, `acc -= term`); float
+// addition is not associative, so a tree reduction would change the result.  Lanes 0..n_chains-1
+// each replay ONE chain over the 64 staged terms with identical (non-divergent) code; a 64-long
+// dependent FADD chain costs ~64 x 4 cycles.  sign = +1 adds, -1 subtracts.
+__device__ __forceinline__ float chain64(const AlignSmem* S, int lane, int n_chains, float sign_mask_sub)
 {
+  const float* v = S->term[lane < n_chains ? lane : 0];
   float a = 0.f;
+  if (sign_mask_sub != 0.f) {
 #pragma unroll 16
-  for (int i = 0; i < 64; ++i) a += v[i];
-  return a;
-}
-__device__ __forceinline__ float chain_sub64(const float* v)
-{
-  float a = 0.f;
+    for (int i = 0; i < 64; ++i) a -= v[i];
+  } else {
 #pragma unroll 16
-  for (int i = 0; i < 64; ++i) a -= v[i];
+    for (int i = 0; i < 64; ++i) a += v[i];
+  }
   return a;
 }
 
@@ -133,7 +135,7 @@ __device__ __forceinline__ float chain_sub64(const float* v)
 __device__ bool align2d_warp(const uint8_t* img, int pitch, int cols, int rows, const uint8_t* pwb, const uint8_t* ref_patch,
                              int n_iter, double* px, AlignSmem* S, int lane)
 {
-  // derivative of the template: 2 pixels per lane
+  // derivative of the template: 2 pixels per lane; H += J*J^T terms (H22 = 64 exactly)
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int idx = lane + 32 * k, y = idx >> 3, x = idx & 7;
@@ -141,16 +143,14 @@ __device__ bool align2d_warp(const uint8_t* img, int pitch, int cols, int rows, 
     const float j0 = (float)(0.5 * ((int)it[1] - (int)it[-1]));
     const float j1 = (float)(0.5 * ((int)it[10] - (int)it[-10]));
     S->dx[idx] = j0; S->dy[idx] = j1;
-    S->p0[idx] = j0 * j0; S->p1[idx] = j0 * j1; S->p2[idx] = j1 * j1;
+    S->term[0][idx] = j0 * j0;      // H00
+    S->term[1][idx] = j0 * j1;      // H01
+    S->term[2][idx] = j0;           // H02 (J[2] = 1)
+    S->term[3][idx] = j1 * j1;      // H11
+    S->term[4][idx] = j1;           // H12
   }
   __syncwarp();
-  // H += J*J^T sequentially: lanes 0..4 replay one chain each (H22 = 64 exactly)
-  float hv = 0.f;
-  if (lane == 0) hv = chain_add64(S->p0);       // H00
-  else if (lane == 1) hv = chain_add64(S->p1);  // H01
-  else if (lane == 2) hv = chain_add64(S->dx);  // H02 (J[2] = 1)
-  else if (lane == 3) hv = chain_add64(S->p2);  // H11
-  else if (lane == 4) hv = chain_add64(S->dy);  // H12
+  const float hv = chain64(S, lane, 5, 0.f);
   const float h00 = __shfl_sync(0xffffffffu, hv, 0), h01 = __shfl_sync(0xffffffffu, hv, 1), h02 = __shfl_sync(0xffffffffu, hv, 2);
   const float h11 = __shfl_sync(0xffffffffu, hv, 3), h12 = __shfl_sync(0xffffffffu, hv, 4);
   const float H[9] = {h00, h01, h02, h01, h11, h12, h02, h12, 64.0f};
@@ -161,7 +161,7 @@ __device__ bool align2d_warp(const uint8_t* img, int pitch, int cols, int rows, 
   const float min_update_squared = (float)(0.5 * 0.5);
   bool converged = false;
   for (int iter = 0; iter < n_iter; ++iter) {
-    const int u_r = (int)floor((double)u), v_r = (int)floor((double)v);
+    const int u_r = (int)floorf(u), v_r = (int)floorf(v);          // == floor((double)u) for a float argument
     if (u_r < 4 || v_r < 4 || u_r >= cols - 4 || v_r >= rows - 4) break;
     if (isnan(u) || isnan(v)) return false;
     const float sx = u - u_r, sy = v - v_r;
@@ -176,15 +176,12 @@ __device__ bool align2d_warp(const uint8_t* img, int pitch, int cols, int rows, 
       const uint8_t* it = img + (size_t)(v_r + y - 4) * pitch + (u_r - 4 + x);
       const float search_pixel = wTL * it[0] + wTR * it[1] + wBL * it[pitch] + wBR * it[pitch + 1];
       const float res = search_pixel - ref_patch[idx] + mean_diff;
-      S->p0[idx] = res * S->dx[idx];
-      S->p1[idx] = res * S->dy[idx];
-      S->p2[idx] = res;
+      S->term[0][idx] = res * S->dx[idx];
+      S->term[1][idx] = res * S->dy[idx];
+      S->term[2][idx] = res;
     }
     __syncwarp();
-    float jv = 0.f;
-    if (lane == 0) jv = chain_sub64(S->p0);
-    else if (lane == 1) jv = chain_sub64(S->p1);
-    else if (lane == 2) jv = chain_sub64(S->p2);
+    const float jv = chain64(S, lane, 3, 1.f);
     const float J0 = __shfl_sync(0xffffffffu, jv, 0), J1 = __shfl_sync(0xffffffffu, jv, 1), J2 = __shfl_sync(0xffffffffu, jv, 2);
     // update = Hinv * Jres (Eigen lazy product: x0 + (x1 + x2))
     const float up0 = Hinv[0] * J0 + (Hinv[1] * J1 + Hinv[2] * J2);
@@ -207,12 +204,11 @@ __device__ bool align1d_warp(const uint8_t* img, int pitch, int cols, int rows, 
     const uint8_t* it = pwb + (y + 1) * 10 + 1 + x;
     const float j0 = (float)(0.5 * (double)(dir0 * (float)((int)it[1] - (int)it[-1]) + dir1 * (float)((int)it[10] - (int)it[-10])));
     S->dx[idx] = j0;
-    S->p0[idx] = j0 * j0;
+    S->term[0][idx] = j0 * j0;      // H00
+    S->term[1][idx] = j0;           // H01 = H10
   }
   __syncwarp();
-  float hv = 0.f;
-  if (lane == 0) hv = chain_add64(S->p0);       // H00
-  else if (lane == 1) hv = chain_add64(S->dx);  // H01 = H10
+  const float hv = chain64(S, lane, 2, 0.f);
   const float h00 = __shfl_sync(0xffffffffu, hv, 0), h01 = __shfl_sync(0xffffffffu, hv, 1), h11 = 64.0f;
   *h_inv = 1.0 / h00 * 8 * 8;
   const float det = h00 * h11 - h01 * h01;
@@ -225,7 +221,7 @@ __device__ bool align1d_warp(const uint8_t* img, int pitch, int cols, int rows, 
   float up0 = 0, up1 = 0;
   bool converged = false;
   for (int iter = 0; iter < n_iter; ++iter) {
-    const int u_r = (int)floor((double)u), v_r = (int)floor((double)v);
+    const int u_r = (int)floorf(u), v_r = (int)floorf(v);
     if (u_r < 4 || v_r < 4 || u_r >= cols - 4 || v_r >= rows - 4) break;
     if (isnan(u) || isnan(v)) return false;
     const float sx = u - u_r, sy = v - v_r;
@@ -240,15 +236,12 @@ __device__ bool align1d_warp(const uint8_t* img, int pitch, int cols, int rows, 
       const uint8_t* it = img + (size_t)(v_r + y - 4) * pitch + (u_r - 4 + x);
       const float search_pixel = wTL * it[0] + wTR * it[1] + wBL * it[pitch] + wBR * it[pitch + 1];
       const float res = search_pixel - ref_patch[idx] + mean_diff;
-      S->p0[idx] = res * S->dx[idx];
-      S->p1[idx] = res;
-      S->p2[idx] = res * res;
+      S->term[0][idx] = res * S->dx[idx];
+      S->term[1][idx] = res;
+      S->term[2][idx] = -(res * res);   // chain subtracts: 0 - (-(r*r)) ... == 0 + r*r exactly
     }
     __syncwarp();
-    float jv = 0.f;
-    if (lane == 0) jv = chain_sub64(S->p0);
-    else if (lane == 1) jv = chain_sub64(S->p1);
-    else if (lane == 2) jv = chain_add64(S->p2);
+    const float jv = chain64(S, lane, 3, 1.f);
     const float J0 = __shfl_sync(0xffffffffu, jv, 0), J1 = __shfl_sync(0xffffffffu, jv, 1), new_chi2 = __shfl_sync(0xffffffffu, jv, 2);
     if (iter > 0 && new_chi2 > chi2) { u -= up0; v -= up1; break; }   // sic (:122-123)
     chi2 = new_chi2;

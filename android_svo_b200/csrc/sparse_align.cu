@@ -8,9 +8,11 @@
 // solve, the SE3 update and the solver's convergence / rollback logic — is ONE kernel launch with
 // one CTA per alignment problem (= per sequence of a batch).  A GN iteration is a dependency
 // chain, not a bandwidth problem, so the design minimises round trips: the model lives in shared
-// memory, one thread per (feature, pixel) keeps its residual and Jacobian row in registers, the
-// 21 + 6 + 2 normal-equation sums are reduced with a 31-shuffle transposing butterfly per warp and
-// one shared-memory pass, and thread 0 runs the pivoted LDL^T and the decision logic.
+// memory; each iteration is three data-parallel phases (thread per feature: projection; thread per
+// pixel: bilinear residual; thread per feature: normal equations from five patch sums, exploiting
+// that the 16 Jacobian rows of a patch are dx*a + dy*b with the same a, b), the 21 + 6 + 2 sums are
+// reduced with a 31-shuffle transposing butterfly per warp and one shared-memory pass, and thread 0
+// runs the register-resident pivoted LDL^T and the decision logic.
 //
 // Parity: per-residual arithmetic (bilinear weights with their double promotions, unfused float
 // sums, Jacobian rows) is bit-identical to the reference.  H/Jres are summed in double in a
@@ -35,71 +37,106 @@ struct AlignArgs {
   svob200_align_result* results;
   // scratch, indexed by global feature / feature-pixel
   float* ref_patch;   // 16 per feature, persists across levels (sparse_img_align.cpp:66)
-  float* gdx;         // 16 per feature
-  float* gdy;
-  float* r2[2];       // res*res of the last two evaluations (ping-pong), for the exact chi2 chain
+  float* gdx;         // 16 per feature: image gradient of the reference patch (zero when the feature is
+  float* gdy;         //                 outside the level's border => zero Jacobian, :76)
+  float* res[2];      // residuals of the last two evaluations (ping-pong), for the exact chi2 chain
+  double* jab;        // 12 per feature: a = J0*fl, b = J1*fl  (pixel Jacobian row = dx*a + dy*b)
+  float2* uv;         // projected position of the feature at the current level
   uint8_t* visible;   // sticky across levels (:67)
   uint8_t* contrib[2];
 };
 
-// Pivoted LDL^T solve of the 6x6 system, mirroring Eigen::LDLT (tolerance-matched).
+// Pivoted LDL^T solve of the 6x6 system, mirroring Eigen::LDLT's algorithm (largest-diagonal
+// symmetric pivoting, tolerance-matched).  Fully unrolled with compile-time indices so the matrix
+// lives in registers: the dynamic pivot is handled by predicated swaps over the candidates.
+__device__ __forceinline__ void swapd(double& a, double& b) { const double t = a; a = b; b = t; }
+
 __device__ void ldlt6_solve(const double* Hin, const double* b, double* x)
 {
-  double A[36];
+  double A[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) A[i][j] = Hin[i * 6 + j];
   int perm[6];
 #pragma unroll
-  for (int i = 0; i < 36; ++i) A[i] = Hin[i];
   for (int k = 0; k < 6; ++k) {
     int piv = k;
-    double big = fabs(A[k * 6 + k]);
-    for (int i = k + 1; i < 6; ++i) { const double v = fabs(A[i * 6 + i]); if (v > big) { big = v; piv = i; } }
+    double big = fabs(A[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) { const double v = fabs(A[i][i]); if (v > big) { big = v; piv = i; } }
     perm[k] = piv;
-    if (piv != k) {
-      const int s = 6 - piv - 1;
-      for (int j = 0; j < k; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
-      for (int j = 0; j < s; ++j) { const double t = A[(piv + 1 + j) * 6 + k]; A[(piv + 1 + j) * 6 + k] = A[(piv + 1 + j) * 6 + piv]; A[(piv + 1 + j) * 6 + piv] = t; }
-      { const double t = A[k * 6 + k]; A[k * 6 + k] = A[piv * 6 + piv]; A[piv * 6 + piv] = t; }
-      for (int i = k + 1; i < piv; ++i) { const double t = A[i * 6 + k]; A[i * 6 + k] = A[piv * 6 + i]; A[piv * 6 + i] = t; }
-    }
-    const int rs = 6 - k - 1;
-    if (k > 0) {
-      double temp[6];
-      for (int j = 0; j < k; ++j) temp[j] = A[j * 6 + j] * A[k * 6 + j];
-      double s = 0;
-      for (int j = 0; j < k; ++j) s += A[k * 6 + j] * temp[j];
-      A[k * 6 + k] -= s;
-      for (int i = 0; i < rs; ++i) {
-        double t = 0;
-        for (int j = 0; j < k; ++j) t += A[(k + 1 + i) * 6 + j] * temp[j];
-        A[(k + 1 + i) * 6 + k] -= t;
+#pragma unroll
+    for (int p = k + 1; p < 6; ++p) {
+      if (piv == p) {
+#pragma unroll
+        for (int j = 0; j < k; ++j) swapd(A[k][j], A[p][j]);
+#pragma unroll
+        for (int j = p + 1; j < 6; ++j) swapd(A[j][k], A[j][p]);
+        swapd(A[k][k], A[p][p]);
+#pragma unroll
+        for (int i = k + 1; i < p; ++i) swapd(A[i][k], A[p][i]);
       }
     }
-    const double d = A[k * 6 + k];
-    if (rs > 0 && fabs(d) > 2.2250738585072014e-308)
-      for (int i = 0; i < rs; ++i) A[(k + 1 + i) * 6 + k] /= d;
+    if (k > 0) {
+      double temp[6];
+      double sdiag = 0;
+#pragma unroll
+      for (int j = 0; j < k; ++j) { temp[j] = A[j][j] * A[k][j]; sdiag += A[k][j] * temp[j]; }
+      A[k][k] -= sdiag;
+#pragma unroll
+      for (int i = k + 1; i < 6; ++i) {
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < k; ++j) t += A[i][j] * temp[j];
+        A[i][k] -= t;
+      }
+    }
+    const double d = A[k][k];
+    if (fabs(d) > 2.2250738585072014e-308) {
+#pragma unroll
+      for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
+    }
   }
   double y[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) y[i] = b[i];
-  for (int k = 0; k < 6; ++k) if (perm[k] != k) { const double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
-  for (int i = 0; i < 6; ++i) { const double d = A[i * 6 + i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
-  for (int i = 5; i >= 0; --i) for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
-  for (int k = 5; k >= 0; --k) if (perm[k] != k) { const double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int p = k + 1; p < 6; ++p) if (perm[k] == p) swapd(y[k], y[p]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { const double d = A[i][i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
+#pragma unroll
+  for (int i = 5; i >= 0; --i)
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+#pragma unroll
+  for (int k = 5; k >= 0; --k) {
+#pragma unroll
+    for (int p = k + 1; p < 6; ++p) if (perm[k] == p) swapd(y[k], y[p]);
+  }
+#pragma unroll
   for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
 // the reference's `float chi2; chi2 += res*res*weight` in feature-list / row-major pixel order
-__device__ float exact_chi2_chain(const float* r2, const uint8_t* visible, const uint8_t* contrib, int N)
+__device__ float exact_chi2_chain(const float* res, const uint8_t* visible, const uint8_t* contrib, int N)
 {
   float chi2 = 0.0f;
   for (int i = 0; i < N; ++i) {
     if (!visible[i] || !contrib[i]) continue;
-    const float4* p = reinterpret_cast<const float4*>(r2 + 16 * (size_t)i);
+    const float4* p = reinterpret_cast<const float4*>(res + 16 * (size_t)i);
     const float4 a = p[0], b = p[1], c = p[2], d = p[3];
-    chi2 += a.x; chi2 += a.y; chi2 += a.z; chi2 += a.w;
-    chi2 += b.x; chi2 += b.y; chi2 += b.z; chi2 += b.w;
-    chi2 += c.x; chi2 += c.y; chi2 += c.z; chi2 += c.w;
-    chi2 += d.x; chi2 += d.y; chi2 += d.z; chi2 += d.w;
+    chi2 += a.x * a.x * 1.0f; chi2 += a.y * a.y * 1.0f; chi2 += a.z * a.z * 1.0f; chi2 += a.w * a.w * 1.0f;
+    chi2 += b.x * b.x * 1.0f; chi2 += b.y * b.y * 1.0f; chi2 += b.z * b.z * 1.0f; chi2 += b.w * b.w * 1.0f;
+    chi2 += c.x * c.x * 1.0f; chi2 += c.y * c.y * 1.0f; chi2 += c.z * c.z * 1.0f; chi2 += c.w * c.w * 1.0f;
+    chi2 += d.x * d.x * 1.0f; chi2 += d.y * d.y * 1.0f; chi2 += d.z * d.z * 1.0f; chi2 += d.w * d.w * 1.0f;
   }
   return chi2;
 }
@@ -122,8 +159,15 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int l
   return v[0];
 }
 
+// One CTA per alignment problem.  Every Gauss-Newton iteration is three data-parallel phases
+//   P1  thread per feature : project xyz_ref with the current model (double), bounds test
+//   P2  thread per pixel   : bilinear intensity, residual (float, bit-identical to the reference)
+//   P3  thread per feature : the 16 pixel Jacobian rows of a feature are dx*a + dy*b with the SAME two
+//                            6-vectors a, b, so  sum J J^T = Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T  and
+//                            sum J r = Sxr a + Syr b : five double sums over the patch, then 27 entries
+// followed by one block reduction and the serial solve / update / decision on thread 0.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignArgs A)
 {
   constexpr int NW = BLOCK / 32;
   __shared__ double s_model[7];
@@ -131,7 +175,6 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
   __shared__ double s_red[NW][NACC];
   __shared__ double s_tot[NACC];
   __shared__ int s_ctrl;          // 0 continue iterating, 1 leave this level
-  __shared__ int s_iter_total;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -157,6 +200,8 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
   float* ref_patch = A.ref_patch + 16 * (size_t)f0;
   float* gdx = A.gdx + 16 * (size_t)f0;
   float* gdy = A.gdy + 16 * (size_t)f0;
+  double* jab = A.jab + 12 * (size_t)f0;
+  float2* uv = A.uv + f0;
   const double focal_length = fabs(A.cam.fx);          // errorMultiplier2()
 
   // thread-0 solver state (NLLSSolver::reset nlls_solver_impl.hpp:299-309)
@@ -172,6 +217,7 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
     {
       const uint8_t* img = A.ref.lvl[level] + (size_t)b * A.ref.img_stride[level];
       const int cols = A.ref.w[level], rows = A.ref.h[level], stride = A.ref.pitch[level];
+      const double fl = focal_length / (1 << level);
       for (int idx = tid; idx < N * 16; idx += BLOCK) {
         const int i = idx >> 4, p = idx & 15;
         const float u_ref = (float)(px[2 * i] * (double)scale);
@@ -179,7 +225,16 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
         const int u_i = (int)floorf(u_ref), v_i = (int)floorf(v_ref);
         const bool ok = has_point[i] && !(u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= cols || v_i + 3 >= rows);
         if (!ok) { gdx[idx] = 0.f; gdy[idx] = 0.f; continue; }   // jacobian_cache_.setZero() (:76)
-        if (p == 0) visible[i] = 1;
+        if (p == 0) {
+          visible[i] = 1;
+          // Frame::jacobian_xyz2uv (frame.h:110-132), scaled by focal_length / 2^level
+          const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+          const double z_inv = 1. / z, z_inv_2 = z_inv * z_inv;
+          const double j02 = x * z_inv_2, j03 = y * j02, j12 = y * z_inv_2;
+          double* ja = jab + 12 * (size_t)i;
+          ja[0] = -z_inv * fl; ja[1] = 0.0; ja[2] = j02 * fl; ja[3] = j03 * fl; ja[4] = -(1.0 + x * j02) * fl; ja[5] = y * z_inv * fl;
+          ja[6] = 0.0; ja[7] = -z_inv * fl; ja[8] = j12 * fl; ja[9] = (1.0 + y * j12) * fl; ja[10] = -j03 * fl; ja[11] = -x * z_inv * fl;
+        }
         const float su = u_ref - u_i, sv = v_ref - v_i;
         const float w_tl = (float)((1.0 - su) * (1.0 - sv));
         const float w_tr = (float)(su * (1.0 - sv));
@@ -199,31 +254,35 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
 
     const uint8_t* cimg = A.cur.lvl[level] + (size_t)b * A.cur.img_stride[level];
     const int ccols = A.cur.w[level], crows = A.cur.h[level], cstride = A.cur.pitch[level];
-    const double fl = focal_length / (1 << level);
 
     for (int iter = 0; iter < A.opts.n_iter; ++iter) {
-      // ---------------- computeResiduals(model, linearize) (sparse_img_align.cpp:184-286)
-      double acc[NACC];
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      double m[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) m[k] = s_model[k];
-      float* r2 = A.r2[pp] + 16 * (size_t)f0;
+      float* res = A.res[pp] + 16 * (size_t)f0;
       uint8_t* contrib = A.contrib[pp] + f0;
+      // ---------------- P1: projection (sparse_img_align.cpp:219-231)
+      {
+        double m[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) m[k] = s_model[k];
+        for (int i = tid; i < N; i += BLOCK) {
+          if (!visible[i]) continue;
+          const v3d pc = se3_transform(m, {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+          double pxd, pyd;
+          world2cam(A.cam, pc, pxd, pyd);
+          const float u_cur = (float)pxd * scale, v_cur = (float)pyd * scale;
+          const int u_i = (int)floorf(u_cur), v_i = (int)floorf(v_cur);
+          const bool in = !(u_i < 0 || v_i < 0 || u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= ccols || v_i + 3 >= crows);
+          contrib[i] = in ? 1 : 0;
+          uv[i] = make_float2(u_cur, v_cur);
+        }
+      }
+      __syncthreads();
+      // ---------------- P2: residuals (sparse_img_align.cpp:233-266)
       for (int idx = tid; idx < N * 16; idx += BLOCK) {
         const int i = idx >> 4, p = idx & 15;
-        if (!visible[i]) continue;
-        const v3d pr = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
-        const v3d pc = se3_transform(m, pr);
-        double pxd, pyd;
-        world2cam(A.cam, pc, pxd, pyd);
-        const float u_cur = (float)pxd * scale, v_cur = (float)pyd * scale;
-        const int u_i = (int)floorf(u_cur), v_i = (int)floorf(v_cur);
-        const bool in = !(u_i < 0 || v_i < 0 || u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= ccols || v_i + 3 >= crows);
-        if (p == 0) contrib[i] = in ? 1 : 0;
-        if (!in) continue;
-        const float su = u_cur - u_i, sv = v_cur - v_i;
+        if (!visible[i] || !contrib[i]) continue;
+        const float2 c = uv[i];
+        const int u_i = (int)floorf(c.x), v_i = (int)floorf(c.y);
+        const float su = c.x - u_i, sv = c.y - v_i;
         const float w_tl = (float)((1.0 - su) * (1.0 - sv));
         const float w_tr = (float)(su * (1.0 - sv));
         const float w_bl = (float)((1.0 - su) * sv);
@@ -231,29 +290,43 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
         const int yy = p >> 2, xx = p & 3;
         const uint8_t* q = cimg + (size_t)(v_i + yy - 2) * cstride + (u_i + xx - 2);
         const float intensity = w_tl * q[0] + w_tr * q[1] + w_bl * q[cstride] + w_br * q[cstride + 1];
-        const float res = intensity - ref_patch[idx];
-        const float rr = res * res * 1.0f;
-        r2[idx] = rr;
-        // Jacobian row: (dx*J0 + dy*J1) * (focal_length / 2^level), Frame::jacobian_xyz2uv
-        const double x = pr.x, y = pr.y;
-        const double z_inv = 1. / pr.z, z_inv_2 = z_inv * z_inv;
-        const double j02 = x * z_inv_2, j03 = y * j02, j12 = y * z_inv_2;
-        const double J0[6] = {-z_inv, 0.0, j02, j03, -(1.0 + x * j02), y * z_inv};
-        const double J1[6] = {0.0, -z_inv, j12, 1.0 + y * j12, -j03, -x * z_inv};
-        const double dx = (double)gdx[idx], dy = (double)gdy[idx];
-        double J[6];
+        res[idx] = intensity - ref_patch[idx];
+      }
+      __syncthreads();
+      // ---------------- P3: normal equations, one feature per thread
+      double acc[NACC];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) J[k] = (dx * J0[k] + dy * J1[k]) * fl;
-        const double rd = (double)res;
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      for (int i = tid; i < N; i += BLOCK) {
+        if (!visible[i] || !contrib[i]) continue;
+        const float4* r4 = reinterpret_cast<const float4*>(res + 16 * (size_t)i);
+        const float4* x4 = reinterpret_cast<const float4*>(gdx + 16 * (size_t)i);
+        const float4* y4 = reinterpret_cast<const float4*>(gdy + 16 * (size_t)i);
+        double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0, Srr = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 r = r4[q], dx = x4[q], dy = y4[q];
+          const float rv[4] = {r.x, r.y, r.z, r.w}, xv[4] = {dx.x, dx.y, dx.z, dx.w}, yv[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double X = (double)xv[e], Y = (double)yv[e], Rr = (double)rv[e];
+            Sxx += X * X; Sxy += X * Y; Syy += Y * Y; Sxr += X * Rr; Syr += Y * Rr;
+            Srr += (double)(rv[e] * rv[e] * 1.0f);          // the reference's float term res*res*weight
+          }
+        }
+        const double* ja = jab + 12 * (size_t)i;
+        double a[6], bb[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { a[k] = ja[k]; bb[k] = ja[6 + k]; }
         int h = 0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
+        for (int r = 0; r < 6; ++r) {
 #pragma unroll
-          for (int c = a; c < 6; ++c) acc[h++] += J[a] * J[c];
-          acc[21 + a] += J[a] * rd;
+          for (int c = r; c < 6; ++c) acc[h++] += Sxx * (a[r] * a[c]) + Sxy * (a[r] * bb[c] + bb[r] * a[c]) + Syy * (bb[r] * bb[c]);
+          acc[21 + r] += Sxr * a[r] + Syr * bb[r];
         }
-        acc[27] += (double)rr;
-        acc[28] += 1.0;
+        acc[27] += Srr;
+        acc[28] += 16.0;
       }
       // ---------------- block reduction
       const double mine = warp_transpose_reduce(acc, lane);
@@ -271,16 +344,20 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
       if (tid == 0) {
         double H[36], Jres[6], xs[6];
         int h = 0;
-        for (int a = 0; a < 6; ++a) {
-          for (int c = a; c < 6; ++c) { H[a * 6 + c] = s_tot[h]; H[c * 6 + a] = s_tot[h]; ++h; }
-          Jres[a] = -s_tot[21 + a];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int c = r; c < 6; ++c) { H[r * 6 + c] = s_tot[h]; H[c * 6 + r] = s_tot[h]; ++h; }
+          Jres[r] = -s_tot[21 + r];
         }
         const int n_meas = (int)s_tot[28];
         double new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
         bool new_exact = false;
         ldlt6_solve(H, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
+#pragma unroll
         for (int k = 0; k < 36; ++k) R->H[k] = H[k];
+#pragma unroll
         for (int k = 0; k < 6; ++k) { R->Jres[k] = Jres[k]; R->x[k] = xs[k]; }
         R->n_meas = n_meas;
         R->iters[level] += 1;
@@ -291,11 +368,11 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
           const double big = fmax(fabs(new_chi2), fabs(chi2_));
           if (fabs(new_chi2 - chi2_) <= tol * big) {
             ++n_exact;
-            new_chi2 = (double)(exact_chi2_chain(r2, visible, contrib, N) / (float)n_meas);
+            new_chi2 = (double)(exact_chi2_chain(res, visible, contrib, N) / (float)n_meas);
             new_exact = true;
             if (!chi2_exact) {
               // previous evaluation lives in the other ping-pong buffer
-              const float prev = exact_chi2_chain(A.r2[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N);
+              const float prev = exact_chi2_chain(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N);
               int pn = 0;
               for (int i = 0; i < N; ++i) pn += (visible[i] && A.contrib[pp ^ 1][f0 + i]) ? 16 : 0;
               chi2_ = (double)(prev / (float)pn);
@@ -304,17 +381,23 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
           }
         }
         if ((iter > 0 && new_chi2 > chi2_) || stop_) {
+#pragma unroll
           for (int k = 0; k < 7; ++k) s_model[k] = s_old[k];        // rollback
           ctrl = 1;
         } else {
-          double nx[6], E[7], nm[7];
+          double nx[6], E[7], nm[7], cm[7];
+#pragma unroll
           for (int k = 0; k < 6; ++k) nx[k] = -xs[k];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) cm[k] = s_model[k];
           se3_exp(nx, E);                                            // update(): T * exp(-x)
-          se3_mul(s_model, E, nm);
-          for (int k = 0; k < 7; ++k) { s_old[k] = s_model[k]; s_model[k] = nm[k]; }
+          se3_mul(cm, E, nm);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) { s_old[k] = cm[k]; s_model[k] = nm[k]; }
           chi2_ = new_chi2;
           chi2_exact = new_exact;
           double nmax = 0;
+#pragma unroll
           for (int k = 0; k < 6; ++k) nmax = fmax(nmax, fabs(xs[k]));   // vk::norm_max
           if (nmax <= A.opts.eps) ctrl = 1;
         }
@@ -336,10 +419,11 @@ __global__ void __launch_bounds__(BLOCK) sparse_align_kernel(AlignArgs A)
 
 }  // namespace
 
+// per feature: 16 floats x (ref_patch, gdx, gdy, res0, res1) + 12 doubles (a, b) + float2 uv + 3 flag bytes
 size_t sparse_align_scratch_bytes(int total_features)
 {
   const size_t n = (size_t)(total_features > 0 ? total_features : 1);
-  return n * 16 * sizeof(float) * 5 + n * 3 + 256 * 8;
+  return n * (16 * sizeof(float) * 5 + 12 * sizeof(double) + sizeof(float2) + 3) + 4096;
 }
 
 int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
@@ -350,21 +434,25 @@ int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& 
   AlignArgs A{};
   A.ref = ref; A.cur = cur; A.cam = cam; A.offsets = d_offsets; A.px = d_px; A.xyz = d_xyz; A.has_point = d_has_point;
   A.T_init = d_T_init; A.opts = opts; A.results = d_results;
-  // carve the scratch in the order sparse_align_scratch_bytes() counts it
+  // carve the scratch in the order sparse_align_scratch_bytes() counts it (all sub-arrays stay 16-byte aligned)
   const size_t T = (size_t)(total_features > 0 ? total_features : 1);
   char* p = static_cast<char*>(d_scratch);
+  auto take = [&p](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
   const size_t fsz = T * 16 * sizeof(float);
-  A.ref_patch = reinterpret_cast<float*>(p); p += fsz;
-  A.gdx = reinterpret_cast<float*>(p); p += fsz;
-  A.gdy = reinterpret_cast<float*>(p); p += fsz;
-  A.r2[0] = reinterpret_cast<float*>(p); p += fsz;
-  A.r2[1] = reinterpret_cast<float*>(p); p += fsz;
-  A.visible = reinterpret_cast<uint8_t*>(p); p += T;
-  A.contrib[0] = reinterpret_cast<uint8_t*>(p); p += T;
-  A.contrib[1] = reinterpret_cast<uint8_t*>(p);
-  // one (feature, pixel) pair per thread and pass: 256 threads cover 16 features per pass
-  if (max_per_problem <= 512) sparse_align_kernel<256><<<batch, 256, 0, s>>>(A);
-  else sparse_align_kernel<512><<<batch, 512, 0, s>>>(A);
+  A.jab = reinterpret_cast<double*>(take(T * 12 * sizeof(double)));
+  A.ref_patch = reinterpret_cast<float*>(take(fsz));
+  A.gdx = reinterpret_cast<float*>(take(fsz));
+  A.gdy = reinterpret_cast<float*>(take(fsz));
+  A.res[0] = reinterpret_cast<float*>(take(fsz));
+  A.res[1] = reinterpret_cast<float*>(take(fsz));
+  A.uv = reinterpret_cast<float2*>(take(T * sizeof(float2)));
+  A.visible = reinterpret_cast<uint8_t*>(take(T));
+  A.contrib[0] = reinterpret_cast<uint8_t*>(take(T));
+  A.contrib[1] = reinterpret_cast<uint8_t*>(take(T));
+  // small problems / few problems: more threads per problem (latency); big batches: more CTAs per SM (throughput)
+  if (max_per_problem > 512) sparse_align_kernel<512><<<batch, 512, 0, s>>>(A);
+  else if (max_per_problem > 128 || batch < 296) sparse_align_kernel<256><<<batch, 256, 0, s>>>(A);
+  else sparse_align_kernel<128><<<batch, 128, 0, s>>>(A);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
