@@ -48,7 +48,8 @@ match_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("px_cur"
                             ("h_inv", "f8"), ("patch_with_border", "u1", 100), ("patch", "u1", 64)], align=True)
 epi_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("reject", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"),
                           ("n_steps", "i4"), ("depth", "f8"), ("px_cur", "f8", 2), ("epi_length", "f8"), ("A_cur_ref", "f8", 4),
-                          ("h_inv", "f8"), ("patch_with_border", "u1", 100), ("patch", "u1", 64)], align=True)
+                          ("h_inv", "f8"), ("epi_dir", "f8", 2), ("px_cur_valid", "i4"), ("patch_with_border", "u1", 100),
+                          ("patch", "u1", 64)], align=True)
 seed_dt = np.dtype([("a", "f4"), ("b", "f4"), ("mu", "f4"), ("z_range", "f4"), ("sigma2", "f4")], align=True)
 step_stats_dt = np.dtype([("T_cur_w", "f8", 7), ("chi2", "f8"), ("n_tracked", "i4"), ("n_matched", "i4"), ("n_seeds_updated", "i4"),
                           ("n_seeds_converged", "i4"), ("n_seeds_failed", "i4"), ("n_seeds_skipped", "i4"), ("align_iters", "i4"),
@@ -116,6 +117,11 @@ def load_library():
     L.svob200_dev_download.argtypes = [V, V, V, C.c_size_t]
     L.svob200_host_alloc_pinned.argtypes = [V, C.c_size_t, C.POINTER(V)]
     L.svob200_host_free_pinned.argtypes = [V, V]
+    L.svob200_frame_upload_level.argtypes = [V, C.c_int64, C.c_int, C.c_int, V, C.c_int]
+    L.svob200_shi_tomasi.argtypes = [V, V, C.c_int, C.c_int, C.c_int, C.c_int, V, V]
+    L.svob200_warp_matrix_affine.argtypes = [V, C.POINTER(Camera), C.c_int, V, V, V, V, V, V, C.c_int]
+    L.svob200_warp_affine.argtypes = [V, V, C.c_int, C.c_int, C.c_int, V, V, C.c_int, C.c_int, C.c_int, V]
+    L.svob200_depth_from_triangulation.argtypes = [V, C.c_int, V, V, V, V, V]
     L.svob200_synth_render.argtypes = [V, V, C.c_int, C.c_double, C.c_double, C.POINTER(Camera), C.c_int, V, V]
     _lib = L
     return L
@@ -133,6 +139,8 @@ EXPORTED_SYMBOLS = [
     "svob200_tracker_create", "svob200_tracker_destroy", "svob200_tracker_set_keyframe", "svob200_tracker_set_last",
     "svob200_tracker_step", "svob200_tracker_get_seeds", "svob200_tracker_launches_per_step",
     "svob200_tracker_enable_profiling", "svob200_tracker_stage_ms", "svob200_tracker_get_seed_obs",
+    "svob200_frame_upload_level", "svob200_shi_tomasi", "svob200_warp_matrix_affine", "svob200_warp_affine",
+    "svob200_depth_from_triangulation",
 ]
 
 

@@ -580,6 +580,107 @@ int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n
   return st.download();
 }
 
+// one level of one image of a resident frame, copied verbatim from host memory: lets a host-side
+// image pyramid (Frame::img_pyr_) be mirrored on the device exactly as the host holds it
+int svob200_frame_upload_level(svob200_ctx* ctx, int64_t frame_id, int image, int level, const uint8_t* data, int stride)
+{
+  if (!ctx || !data) return fail(ctx, SVOB200_ERR_ARG, "frame_upload_level: null argument");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (level < 0 || level >= r->f.n_levels || image < 0 || image >= r->f.batch || stride < r->f.w[level]) return fail(ctx, SVOB200_ERR_ARG, "frame_upload_level: bad level/image/stride");
+  if (level == 0 && r->f.lvl[0] != r->own_l0) {          // undo a previous bind
+    r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
+    CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemcpy2DAsync(r->f.lvl[level] + (size_t)image * r->f.img_stride[level], r->f.pitch[level], data, stride, r->f.w[level], r->f.h[level],
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+// vk::shiTomasiScore (vision.cpp:113-154) for n pixels of a host image
+int svob200_shi_tomasi(svob200_ctx* ctx, const uint8_t* img, int w, int h, int stride, int n, const int* uv, float* scores)
+{
+  if (!ctx || !img || w <= 0 || h <= 0 || stride < w || n < 0 || !uv || !scores) return fail(ctx, SVOB200_ERR_ARG, "shi_tomasi: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  const int pitch = align_up_i(w, 64);
+  const size_t img_b = ((size_t)pitch * h + 255) & ~(size_t)255, uv_b = ((size_t)n * 8 + 255) & ~(size_t)255;
+  if (ctx->d_scratch.ensure(img_b + uv_b + (size_t)n * 4 + 256) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "shi_tomasi: scratch alloc failed");
+  uint8_t* d_img = static_cast<uint8_t*>(ctx->d_scratch.p);
+  int* d_uv = reinterpret_cast<int*>(d_img + img_b);
+  float* d_out = reinterpret_cast<float*>(d_img + img_b + uv_b);
+  CU(cudaMemcpy2DAsync(d_img, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_uv, uv, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (launch_shi_tomasi_points(d_img, pitch, w, h, n, d_uv, d_out, ctx->stream, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "shi_tomasi launch failed");
+  CU(cudaMemcpyAsync(scores, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+// warp::getWarpMatrixAffine (matcher.cpp:36-60) for n items; A_out row-major 2x2 per item
+int svob200_warp_matrix_affine(svob200_ctx* ctx, const svob200_camera* cam, int n, const double* px_ref, const double* f_ref,
+                               const double* depth_ref, const double* T_cur_ref, const int* level_ref, double* A_out, int mem)
+{
+  if (!ctx || !cam || n < 0 || !px_ref || !f_ref || !depth_ref || !T_cur_ref || !level_ref || !A_out) return fail(ctx, SVOB200_ERR_ARG, "warp_matrix_affine: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, mem);
+  const int i_px = st.add(px_ref, nullptr, sizeof(double) * 2 * n, 0);
+  const int i_f = st.add(f_ref, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_d = st.add(depth_ref, nullptr, sizeof(double) * n, 0);
+  const int i_T = st.add(T_cur_ref, nullptr, sizeof(double) * 7 * n, 0);
+  const int i_l = st.add(level_ref, nullptr, sizeof(int) * n, 0);
+  const int i_A = st.add(nullptr, A_out, sizeof(double) * 4 * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_warp_matrix(to_cam(cam), n, st.dev<double>(i_px), st.dev<double>(i_f), st.dev<double>(i_d), st.dev<double>(i_T), st.dev<int>(i_l),
+                         st.dev<double>(i_A), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "warp_matrix_affine launch failed");
+  return st.download();
+}
+
+// warp::warpAffine (matcher.cpp:83-116) on a host image level; patch: (2*halfpatch)^2 bytes, in/out
+// (left untouched when the warp matrix inverts to NaN, like the reference)
+int svob200_warp_affine(svob200_ctx* ctx, const uint8_t* img, int w, int h, int stride, const double* A_cur_ref, const double* px_ref,
+                        int level_ref, int search_level, int halfpatch_size, uint8_t* patch)
+{
+  if (!ctx || !img || w <= 0 || h <= 0 || stride < w || !A_cur_ref || !px_ref || halfpatch_size <= 0 || halfpatch_size > 64 || !patch
+      || level_ref < 0 || level_ref > 30 || search_level < 0 || search_level > 30)
+    return fail(ctx, SVOB200_ERR_ARG, "warp_affine: bad arguments");
+  const int pitch = align_up_i(w, 64), np = 4 * halfpatch_size * halfpatch_size;
+  const size_t img_b = ((size_t)pitch * h + 255) & ~(size_t)255;
+  if (ctx->d_scratch.ensure(img_b + np + 256) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "warp_affine: scratch alloc failed");
+  uint8_t* d_img = static_cast<uint8_t*>(ctx->d_scratch.p);
+  uint8_t* d_patch = d_img + img_b;
+  CU(cudaMemcpy2DAsync(d_img, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_patch, patch, np, cudaMemcpyHostToDevice, ctx->stream));
+  if (launch_warp_affine(d_img, pitch, w, h, A_cur_ref, px_ref, level_ref, search_level, halfpatch_size, d_patch, ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "warp_affine launch failed");
+  CU(cudaMemcpyAsync(patch, d_patch, np, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+// depthFromTriangulation (matcher.cpp:123-136) for n items; depth is in/out (left untouched where ok = 0)
+int svob200_depth_from_triangulation(svob200_ctx* ctx, int n, const double* T_search_ref, const double* f_ref, const double* f_cur,
+                                     double* depth, int* ok)
+{
+  if (!ctx || n < 0 || !T_search_ref || !f_ref || !f_cur || !depth || !ok) return fail(ctx, SVOB200_ERR_ARG, "depth_from_triangulation: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  Stage st(ctx, SVOB200_MEM_HOST);
+  const int i_T = st.add(T_search_ref, nullptr, sizeof(double) * 7 * n, 0);
+  const int i_a = st.add(f_ref, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_b = st.add(f_cur, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_d = st.add(depth, depth, sizeof(double) * n, 1);
+  const int i_o = st.add(nullptr, ok, sizeof(int) * n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_triangulate(n, st.dev<double>(i_T), st.dev<double>(i_a), st.dev<double>(i_b), st.dev<double>(i_d), st.dev<int>(i_o), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "depth_from_triangulation launch failed");
+  return st.download();
+}
+
 // ------------------------------------------------------------------ raw device helpers
 int svob200_dev_alloc(svob200_ctx* ctx, size_t bytes, void** dptr)
 {

@@ -210,6 +210,31 @@ __global__ void fast_finalize_kernel(const unsigned long long* keys, int n_cells
   if (threadIdx.x == 0 && counts) counts[b] = s_cnt;
 }
 
+// stand-alone vk::shiTomasiScore(img, u, v) (vision.cpp:113-154) for n points of one image
+__global__ void shi_tomasi_points_kernel(const uint8_t* img, int pitch, int cols, int rows, int n, const int* uv, float* out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int u = uv[2 * i], v = uv[2 * i + 1];
+  const int halfbox = 4;
+  if (u - halfbox < 1 || u + halfbox >= cols - 1 || v - halfbox < 1 || v + halfbox >= rows - 1) { out[i] = 0.f; return; }   // :129
+  float dXX = 0.f, dYY = 0.f, dXY = 0.f;
+  for (int y = -4; y < 4; ++y) {
+    const uint8_t* r = img + (size_t)(v + y) * pitch + u;
+    for (int x = -4; x < 4; ++x) {
+      const float dx = (float)((int)r[x + 1] - (int)r[x - 1]);
+      const float dy = (float)((int)r[x + pitch] - (int)r[x - pitch]);
+      dXX += dx * dx; dYY += dy * dy; dXY += dx * dy;
+    }
+  }
+  dXX = (float)((double)dXX / 128.0);
+  dYY = (float)((double)dYY / 128.0);
+  dXY = (float)((double)dXY / 128.0);
+  const float tr = dXX + dYY;
+  const float disc = tr * tr - 4 * (dXX * dYY - dXY * dXY);
+  out[i] = (float)(0.5 * ((double)tr - sqrt((double)disc)));
+}
+
 }  // namespace
 
 int launch_fast_detect(const DevFrame& f, int n_detect_levels, int cell, int grid_cols, int grid_rows, double thr,
@@ -239,6 +264,15 @@ int launch_fast_raw(const DevFrame& f, int image, int level, int threshold, int 
   A.raw_threshold = threshold; A.raw_nonmax = nonmax;
   const int tiles = ((f.w[level] + TW - 1) / TW) * ((f.h[level] + TH - 1) / TH);
   fast_kernel<<<dim3(tiles, 1), 256, 0, s>>>(A);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_shi_tomasi_points(const uint8_t* d_img, int pitch, int cols, int rows, int n, const int* d_uv, float* d_out,
+                             cudaStream_t s, long long* launches)
+{
+  if (n <= 0) return 0;
+  shi_tomasi_points_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_img, pitch, cols, rows, n, d_uv, d_out);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

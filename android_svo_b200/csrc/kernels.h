@@ -60,3 +60,13 @@ int launch_reproject_prepare(const DevCam& cam, int n, svob200_feature_ref* d_ft
 int launch_match_direct_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                                 const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, double* d_px_out,
                                 int* d_ok_out, cudaStream_t s, long long* launches);
+
+// stand-alone helpers behind the C++ drop-in (vk::shiTomasiScore, warp::getWarpMatrixAffine, warp::warpAffine)
+int launch_shi_tomasi_points(const uint8_t* d_img, int pitch, int cols, int rows, int n, const int* d_uv, float* d_out,
+                             cudaStream_t s, long long* launches);
+int launch_warp_matrix(const DevCam& cam, int n, const double* d_px_ref, const double* d_f_ref, const double* d_depth_ref,
+                       const double* d_T_cur_ref, const int* d_level_ref, double* d_A_out, cudaStream_t s, long long* launches);
+int launch_warp_affine(const uint8_t* d_img, int pitch, int cols, int rows, const double* A, const double* px_ref, int level_ref,
+                       int search_level, int halfpatch, uint8_t* d_patch, cudaStream_t s, long long* launches);
+int launch_triangulate(int n, const double* d_T, const double* d_f_ref, const double* d_f_cur, double* d_depth, int* d_ok,
+                       cudaStream_t s, long long* launches);

@@ -371,6 +371,7 @@ struct EpiGeom {
   double A[4];                          // A_cur_ref, row-major
   double Bx0, By0, stepx, stepy;        // epipolar sample chain: uv_0 = B - step, uv_{i+1} = uv_i + step
   double px_mid[2];                     // (px_A + px_B) / 2
+  double ex, ey;                        // epi_dir_ = A - B on the unit plane (matcher.cpp:224)
   double epi_length;
   float a00, a01, a10, a11, pr0, pr1;   // A_ref_cur (float) and px_ref at the reference level
   float dirx, diry;                     // (px_A - px_B).cast<float>().normalized()
@@ -396,7 +397,7 @@ __device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref
 {
   for (int k = 0; k < 7; ++k) g->T_cur_ref[k] = T_cur_ref[k];
   g->reject = 0; g->mode = EPI_MODE_NONE; g->n = 0; g->n_steps_report = 0; g->L = 0; g->epi_length = 0; g->warp_ok = 0;
-  g->Bx0 = g->By0 = g->stepx = g->stepy = 0; g->px_mid[0] = g->px_mid[1] = 0;
+  g->Bx0 = g->By0 = g->stepx = g->stepy = 0; g->px_mid[0] = g->px_mid[1] = 0; g->ex = g->ey = 0;
   g->a00 = g->a01 = g->a10 = g->a11 = g->pr0 = g->pr1 = g->dirx = g->diry = 0;
   const v3d f_ref = {f.f[0], f.f[1], f.f[2]};
   const v3d tA = se3_transform(T_cur_ref, {f_ref.x * d_min, f_ref.y * d_min, f_ref.z * d_min});
@@ -404,6 +405,7 @@ __device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref
   const v3d tB = se3_transform(T_cur_ref, {f_ref.x * d_max, f_ref.y * d_max, f_ref.z * d_max});
   const double Bx = tB.x / tB.z, By = tB.y / tB.z;
   const double ex = Ax - Bx, ey = Ay - By;
+  g->ex = ex; g->ey = ey;
   warp_matrix_affine(cam, f.px, f_ref, d_estimate, T_cur_ref, f.level, g->A);
   const double* A = g->A;
   if (f.type == 1 && o.epi_search_edgelet_filtering) {
@@ -587,6 +589,8 @@ __global__ void __launch_bounds__(128) epipolar_kernel(const DevFrame* frames, c
     R->n_evals = sr.n_evals; R->n_steps = g.n_steps_report; R->depth = ok ? depth : 0.0;
     R->px_cur[0] = sr.px_cur[0]; R->px_cur[1] = sr.px_cur[1];
     R->epi_length = g.epi_length; R->h_inv = sr.h_inv;
+    R->epi_dir[0] = g.ex; R->epi_dir[1] = g.ey;
+    R->px_cur_valid = (!g.reject && (g.mode == EPI_MODE_DIRECT || (g.mode == EPI_MODE_WALK && sr.zmssd_best < 2000 * 64))) ? 1 : 0;
     for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g.A[k];
   }
   for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = g.reject ? 0 : S->w.pwb[k];
@@ -802,6 +806,53 @@ __global__ void compute_tau_kernel(int n, const double* T, const double* f, cons
   out[i] = compute_tau(T + 7 * (size_t)i, {f[3 * i], f[3 * i + 1], f[3 * i + 2]}, z[i], angle);
 }
 
+// stand-alone warp::getWarpMatrixAffine (matcher.cpp:36-60): thread per item
+__global__ void warp_matrix_kernel(DevCam cam, int n, const double* px_ref, const double* f_ref, const double* depth_ref,
+                                   const double* T_cur_ref, const int* level_ref, double* A_out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double A[4];
+  warp_matrix_affine(cam, px_ref + 2 * i, {f_ref[3 * i], f_ref[3 * i + 1], f_ref[3 * i + 2]}, depth_ref[i], T_cur_ref + 7 * (size_t)i, level_ref[i], A);
+  for (int k = 0; k < 4; ++k) A_out[4 * (size_t)i + k] = A[k];
+}
+
+// stand-alone warp::warpAffine (matcher.cpp:83-116) for any halfpatch size: thread per patch pixel.
+// Leaves the patch untouched when the warp is NaN, like the reference (:94-98).
+__global__ void warp_affine_kernel(const uint8_t* img, int pitch, int cols, int rows, double A0, double A1, double A2, double A3,
+                                   double px0, double px1, int level_ref, int search_level, int halfpatch, uint8_t* patch)
+{
+  const int ps = 2 * halfpatch;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ps * ps) return;
+  const double det = A0 * A3 - A2 * A1;
+  const double invdet = 1.0 / det;
+  const float a00 = (float)(A3 * invdet), a01 = (float)(-A1 * invdet);
+  const float a10 = (float)(-A2 * invdet), a11 = (float)(A0 * invdet);
+  if (isnan(a00)) return;
+  const float pr0 = (float)px0 / (float)(1 << level_ref), pr1 = (float)px1 / (float)(1 << level_ref);
+  const int y = i / ps, x = i - y * ps;
+  float p0 = (float)(x - halfpatch), p1 = (float)(y - halfpatch);
+  p0 *= (float)(1 << search_level); p1 *= (float)(1 << search_level);
+  const float qx = (a00 * p0 + a01 * p1) + pr0;
+  const float qy = (a10 * p0 + a11 * p1) + pr1;
+  uint8_t v = 0;
+  if (!(qx < 0 || qy < 0 || qx >= cols - 1 || qy >= rows - 1)) v = (uint8_t)interpolate_8u(img, pitch, qx, qy);
+  patch[i] = v;
+}
+
+// stand-alone depthFromTriangulation (matcher.cpp:123-136): thread per item
+__global__ void triangulate_kernel(int n, const double* T, const double* f_ref, const double* f_cur, double* depth, int* ok)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 0.0;
+  const bool r = depth_from_triangulation(T + 7 * (size_t)i, {f_ref[3 * i], f_ref[3 * i + 1], f_ref[3 * i + 2]},
+                                          {f_cur[3 * i], f_cur[3 * i + 1], f_cur[3 * i + 2]}, &d);
+  ok[i] = r ? 1 : 0;
+  if (r) depth[i] = d;
+}
+
 }  // namespace
 
 int launch_align_patches(const DevFrame& f, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
@@ -885,6 +936,35 @@ int launch_compute_tau(int n, const double* d_T, const double* d_f, const double
 {
   if (n <= 0) return 0;
   compute_tau_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, d_T, d_f, d_z, angle, d_out);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_warp_matrix(const DevCam& cam, int n, const double* d_px_ref, const double* d_f_ref, const double* d_depth_ref,
+                       const double* d_T_cur_ref, const int* d_level_ref, double* d_A_out, cudaStream_t s, long long* launches)
+{
+  if (n <= 0) return 0;
+  warp_matrix_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_px_ref, d_f_ref, d_depth_ref, d_T_cur_ref, d_level_ref, d_A_out);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_warp_affine(const uint8_t* d_img, int pitch, int cols, int rows, const double* A, const double* px_ref, int level_ref,
+                       int search_level, int halfpatch, uint8_t* d_patch, cudaStream_t s, long long* launches)
+{
+  const int n = 4 * halfpatch * halfpatch;
+  if (n <= 0) return 0;
+  warp_affine_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_img, pitch, cols, rows, A[0], A[1], A[2], A[3], px_ref[0], px_ref[1], level_ref,
+                                                     search_level, halfpatch, d_patch);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_triangulate(int n, const double* d_T, const double* d_f_ref, const double* d_f_cur, double* d_depth, int* d_ok,
+                       cudaStream_t s, long long* launches)
+{
+  if (n <= 0) return 0;
+  triangulate_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, d_T, d_f_ref, d_f_cur, d_depth, d_ok);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -1,0 +1,670 @@
+// svo_b200_dropin.cpp — the reference's hot-path C++ symbols, defined on top of libsvob200's C ABI.
+//
+// Compiled against the reference's UNCHANGED headers (-I /root/reference/app/src/main/cpp/svo/include
+// and its vendored Eigen) and linked instead of vision.cpp / feature_alignment.cpp / matcher.cpp /
+// sparse_img_align.cpp / feature_detection.cpp.  Everything arithmetic happens in CUDA kernels behind
+// include/svob200.h; this file only marshals the reference's pointer-rich host model (Frame, Feature,
+// Point, std::list<Seed>) into the flat arrays of the C ABI and writes the results back into the
+// members the reference's callers read.  There is no CPU fallback: if no CUDA device is usable the
+// first call throws std::runtime_error (the one exception type the reference itself uses, frame.cpp:55).
+//
+// Paths cited below are relative to /root/reference/app/src/main/cpp/svo.
+#include <svo/global.h>
+#include <svo/config.h>
+#include <svo/vision.h>
+#include <svo/aligned_mem.h>
+#include <svo/abstract_camera.h>
+#include <svo/pinhole_camera.h>
+#include <svo/frame.h>
+#include <svo/feature.h>
+#include <svo/point.h>
+#include <svo/feature_detection.h>
+#include <svo/feature_alignment.h>
+#include <svo/sparse_img_align.h>
+#include <svo/matcher.h>
+#include <svo/depth_filter.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "svob200.h"
+#include "svo_b200_dropin.h"
+
+namespace svo {
+namespace b200 {
+namespace {
+
+struct CacheEntry {
+  const uint8_t* data0;      // level-0 pixel pointer of the host pyramid the mirror was made from
+  int w, h, n_levels;
+  unsigned long long stamp;
+};
+
+struct Runtime {
+  std::recursive_mutex mu;   // one stream + one staging arena: calls from the tracking and depth-filter threads serialise here
+  svob200_ctx* ctx = nullptr;
+  std::unordered_map<int, CacheEntry> cache;          // Frame::id_ -> mirror
+  std::unordered_map<long long, int64_t> scratch;     // (w,h,levels) -> temp frame id for bare cv::Mat arguments
+  size_t capacity = 64;
+  unsigned long long clock = 0;
+  int64_t next_temp_id = (int64_t)1 << 40;
+};
+
+Runtime& rt()
+{
+  static Runtime r;
+  return r;
+}
+
+[[noreturn]] void die(const char* what)
+{
+  Runtime& r = rt();
+  std::string msg = std::string("svo_b200: ") + what + ": " + (r.ctx ? svob200_last_error(r.ctx) : "no usable CUDA device (there is no CPU fallback)");
+  throw std::runtime_error(msg);
+}
+
+inline void check(int rc, const char* what) { if (rc != SVOB200_OK) die(what); }
+
+svob200_ctx* ctx_locked()
+{
+  Runtime& r = rt();
+  if (!r.ctx) {
+    const char* dev = getenv("SVOB200_DEVICE");
+    if (svob200_ctx_create(dev ? atoi(dev) : 0, &r.ctx) != SVOB200_OK) { r.ctx = nullptr; die("svob200_ctx_create"); }
+  }
+  return r.ctx;
+}
+
+inline int step_of(const cv::Mat& m) { return (int)m.step.p[0]; }
+
+inline void pose7(const SE3& T, double* o)
+{
+  o[0] = T.get_translation().x; o[1] = T.get_translation().y; o[2] = T.get_translation().z;
+  o[3] = T.get_rotation().x; o[4] = T.get_rotation().y; o[5] = T.get_rotation().z; o[6] = T.get_rotation().w;
+}
+inline SE3 se3_of(const double* T) { return SE3(T[0], T[1], T[2], T[3], T[4], T[5], T[6]); }
+
+svob200_camera camera_of(const vk::AbstractCamera* cam)
+{
+  const vk::PinholeCamera* p = dynamic_cast<const vk::PinholeCamera*>(cam);
+  if (!p) throw std::runtime_error("svo_b200: only vk::PinholeCamera is supported on the device path");
+  if (p->d0() != 0.0 || p->d1() != 0.0 || p->d2() != 0.0 || p->d3() != 0.0 || p->d4() != 0.0)
+    throw std::runtime_error("svo_b200: the device path implements the distortion-free pinhole branches only (pinhole_camera.cpp:48-53, :83-87)");
+  svob200_camera c;
+  c.width = p->width(); c.height = p->height(); c.fx = p->fx(); c.fy = p->fy(); c.cx = p->cx(); c.cy = p->cy();
+  return c;
+}
+
+void matcher_opts_of(const Matcher::Options& o, svob200_matcher_opts* m)
+{
+  m->align_1d = o.align_1d ? 1 : 0;
+  m->align_max_iter = o.align_max_iter;
+  m->max_epi_search_steps = o.max_epi_search_steps > 0x7fffffffu ? 0x7fffffff : (int)o.max_epi_search_steps;
+  m->subpix_refinement = o.subpix_refinement ? 1 : 0;
+  m->epi_search_edgelet_filtering = o.epi_search_edgelet_filtering ? 1 : 0;
+  m->epi_search_edgelet_max_angle = o.epi_search_edgelet_max_angle;
+  m->max_search_level = (int)Config::nPyrLevels() - 1;            // matcher.cpp:174, :243
+}
+
+void evict_locked(Runtime& r)
+{
+  while (r.cache.size() > r.capacity) {
+    auto victim = r.cache.begin();
+    for (auto it = r.cache.begin(); it != r.cache.end(); ++it) if (it->second.stamp < victim->second.stamp) victim = it;
+    svob200_frame_release(r.ctx, victim->first);
+    r.cache.erase(victim);
+  }
+}
+
+// Mirror a host pyramid on the device under `id`, level by level, exactly as the host holds it.
+void upload_pyramid_locked(svob200_ctx* ctx, int64_t id, const ImgPyr& pyr, int n_levels)
+{
+  for (int l = 0; l < n_levels; ++l)
+    check(svob200_frame_upload_level(ctx, id, 0, l, pyr[l].data, step_of(pyr[l])), "svob200_frame_upload_level");
+}
+
+bool pyramid_is_halving(const ImgPyr& pyr, int n_levels)
+{
+  for (int l = 1; l < n_levels; ++l)
+    if (pyr[l].cols != pyr[l - 1].cols / 2 || pyr[l].rows != pyr[l - 1].rows / 2) return false;
+  return true;
+}
+
+// Device mirror of a Frame's pyramid, keyed by Frame::id_ (images are immutable after the ctor).
+int64_t ensure_frame_locked(const Frame& f)
+{
+  Runtime& r = rt();
+  svob200_ctx* ctx = ctx_locked();
+  const int n_levels = (int)f.img_pyr_.size();
+  if (n_levels < 1 || n_levels > SVOB200_MAX_LEVELS) throw std::runtime_error("svo_b200: frame pyramid depth outside [1, 8]");
+  if (!pyramid_is_halving(f.img_pyr_, n_levels)) throw std::runtime_error("svo_b200: frame pyramid is not an integer-halving pyramid (frame.cpp:192)");
+  const cv::Mat& l0 = f.img_pyr_[0];
+  auto it = r.cache.find(f.id_);
+  if (it != r.cache.end()) {
+    CacheEntry& e = it->second;
+    if (e.data0 == l0.data && e.w == l0.cols && e.h == l0.rows && e.n_levels == n_levels) { e.stamp = ++r.clock; return f.id_; }
+    svob200_frame_release(ctx, f.id_);
+    r.cache.erase(it);
+  }
+  check(svob200_frame_create(ctx, f.id_, 1, l0.cols, l0.rows, n_levels), "svob200_frame_create");
+  upload_pyramid_locked(ctx, f.id_, f.img_pyr_, n_levels);
+  r.cache[f.id_] = CacheEntry{l0.data, l0.cols, l0.rows, n_levels, ++r.clock};
+  evict_locked(r);
+  return f.id_;
+}
+
+// Temp device frame for operators that receive bare images (align1D/2D, FastDetector::detect's img_pyr).
+int64_t scratch_frame_locked(int w, int h, int n_levels)
+{
+  Runtime& r = rt();
+  svob200_ctx* ctx = ctx_locked();
+  const long long key = ((long long)w << 36) | ((long long)h << 8) | n_levels;
+  auto it = r.scratch.find(key);
+  if (it != r.scratch.end()) return it->second;
+  if (r.scratch.size() >= 16) {                       // bounded: drop all and start over
+    for (auto& kv : r.scratch) svob200_frame_release(ctx, kv.second);
+    r.scratch.clear();
+  }
+  const int64_t id = r.next_temp_id++;
+  check(svob200_frame_create(ctx, id, 1, w, h, n_levels), "svob200_frame_create");
+  r.scratch[key] = id;
+  return id;
+}
+
+thread_local int g_last_iters[SVOB200_MAX_LEVELS] = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local int g_last_exact = 0;
+
+typedef std::lock_guard<std::recursive_mutex> Lock;
+
+}  // namespace
+
+svob200_ctx* context() { Lock lk(rt().mu); return ctx_locked(); }
+
+void releaseFrame(const Frame& frame)
+{
+  Runtime& r = rt();
+  Lock lk(r.mu);
+  auto it = r.cache.find(frame.id_);
+  if (it == r.cache.end() || !r.ctx) return;
+  svob200_frame_release(r.ctx, frame.id_);
+  r.cache.erase(it);
+}
+
+void setFrameCacheCapacity(size_t capacity)
+{
+  Runtime& r = rt();
+  Lock lk(r.mu);
+  r.capacity = capacity < 4 ? 4 : capacity;
+  if (r.ctx) evict_locked(r);
+}
+
+void shutdown()
+{
+  Runtime& r = rt();
+  Lock lk(r.mu);
+  if (!r.ctx) return;
+  svob200_ctx_destroy(r.ctx);     // frees every resident frame
+  r.ctx = nullptr; r.cache.clear(); r.scratch.clear();
+}
+
+long long launchCount() { Runtime& r = rt(); Lock lk(r.mu); return r.ctx ? svob200_ctx_launch_count(r.ctx) : 0; }
+const int* lastAlignIterations() { return g_last_iters; }
+int lastAlignExactChi2() { return g_last_exact; }
+
+}  // namespace b200
+}  // namespace svo
+
+using svo::b200::rt;
+using svo::b200::Lock;
+using svo::b200::check;
+using svo::b200::ctx_locked;
+using svo::b200::step_of;
+
+// ============================================================================ vision.h
+namespace vk {
+
+// vision.cpp:71-110.  The rounding the reference computes depends on the ISA it was compiled for:
+// SSE2 builds take the double-rounding _mm_avg path iff both buffers are 16-byte aligned and
+// in.cols % 16 == 0 (:78); every other case (NEON, scalar) truncates (a+b+c+d)/4.
+void halfSample(const cv::Mat& in, cv::Mat& out)
+{
+  assert(in.rows / 2 == out.rows && in.cols / 2 == out.cols);
+  assert(in.type() == CV_8U && out.type() == CV_8U);
+  int mode = SVOB200_ROUND_TRUNC;
+#ifdef __SSE2__
+  if (aligned_mem::is_aligned16(in.data) && aligned_mem::is_aligned16(out.data) && ((in.cols % 16) == 0)) mode = SVOB200_ROUND_SSE2;
+#endif
+  Lock lk(rt().mu);
+  check(svob200_half_sample(ctx_locked(), in.data, in.cols, in.rows, step_of(in), out.data, step_of(out), mode), "svob200_half_sample");
+}
+
+// vision.cpp:113-154
+float shiTomasiScore(const cv::Mat& img, int u, int v)
+{
+  assert(img.type() == CV_8UC1);
+  const int uv[2] = {u, v};
+  float score = 0.f;
+  Lock lk(rt().mu);
+  check(svob200_shi_tomasi(ctx_locked(), img.data, img.cols, img.rows, step_of(img), 1, uv, &score), "svob200_shi_tomasi");
+  return score;
+}
+
+}  // namespace vk
+
+namespace svo {
+
+// ============================================================================ feature_alignment.h
+namespace feature_alignment {
+
+namespace {
+bool align_on_device(const cv::Mat& cur_img, const float* dir, uint8_t* ref_patch_with_border, uint8_t* ref_patch, int n_iter,
+                     Vector2d& cur_px_estimate, double* h_inv)
+{
+  Lock lk(rt().mu);
+  svob200_ctx* ctx = ctx_locked();
+  const int64_t id = b200::scratch_frame_locked(cur_img.cols, cur_img.rows, 1);
+  check(svob200_frame_upload_level(ctx, id, 0, 0, cur_img.data, step_of(cur_img)), "svob200_frame_upload_level");
+  const int image = 0;
+  double px[2] = {cur_px_estimate[0], cur_px_estimate[1]};
+  int converged = 0;
+  check(svob200_align_patches(ctx, id, 0, 1, &image, ref_patch_with_border, ref_patch, dir, n_iter, px, &converged, h_inv, SVOB200_MEM_HOST),
+        "svob200_align_patches");
+  cur_px_estimate << px[0], px[1];
+  return converged != 0;
+}
+}  // namespace
+
+// feature_alignment.cpp:35-152
+bool align1D(const cv::Mat& cur_img, const Vector2f& dir, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter,
+             Vector2d& cur_px_estimate, double& h_inv)
+{
+  const float d[2] = {dir[0], dir[1]};
+  return align_on_device(cur_img, d, ref_patch_with_border, ref_patch, n_iter, cur_px_estimate, &h_inv);
+}
+
+// feature_alignment.cpp:154-282 (float path; the SSE2/NEON integer variants are compiled out of the
+// reference's align2D by its `no_simd` default and are not on the path)
+bool align2D(const cv::Mat& cur_img, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate, bool)
+{
+  return align_on_device(cur_img, nullptr, ref_patch_with_border, ref_patch, n_iter, cur_px_estimate, nullptr);
+}
+
+}  // namespace feature_alignment
+
+// ============================================================================ matcher.h: warp
+namespace warp {
+
+// matcher.cpp:36-60
+void getWarpMatrixAffine(const vk::AbstractCamera& cam_ref, const vk::AbstractCamera& /*cam_cur: same camera*/, const Vector2d& px_ref,
+                         const Vector3d& f_ref, const double depth_ref, const SE3& T_cur_ref, const int level_ref, Matrix2d& A_cur_ref)
+{
+  const svob200_camera cam = b200::camera_of(&cam_ref);
+  const double px[2] = {px_ref[0], px_ref[1]}, f[3] = {f_ref[0], f_ref[1], f_ref[2]};
+  double T[7], A[4];
+  b200::pose7(T_cur_ref, T);
+  Lock lk(rt().mu);
+  check(svob200_warp_matrix_affine(ctx_locked(), &cam, 1, px, f, &depth_ref, T, &level_ref, A, SVOB200_MEM_HOST), "svob200_warp_matrix_affine");
+  A_cur_ref << A[0], A[1], A[2], A[3];
+}
+
+// matcher.cpp:65-78 — three lines of integer control on a determinant, kept on the host
+int getBestSearchLevel(const Matrix2d& A_cur_ref, const int max_level)
+{
+  int search_level = 0;
+  double D = A_cur_ref(0, 0) * A_cur_ref(1, 1) - A_cur_ref(1, 0) * A_cur_ref(0, 1);
+  while (D > 3.0 && search_level < max_level) { search_level += 1; D *= 0.25; }
+  return search_level;
+}
+
+// matcher.cpp:83-116
+void warpAffine(const Matrix2d& A_cur_ref, const cv::Mat& img_ref, const Vector2d& px_ref, const int level_ref, const int search_level,
+                const int halfpatch_size, uint8_t* patch)
+{
+  const double A[4] = {A_cur_ref(0, 0), A_cur_ref(0, 1), A_cur_ref(1, 0), A_cur_ref(1, 1)}, px[2] = {px_ref[0], px_ref[1]};
+  Lock lk(rt().mu);
+  check(svob200_warp_affine(ctx_locked(), img_ref.data, img_ref.cols, img_ref.rows, step_of(img_ref), A, px, level_ref, search_level,
+                            halfpatch_size, patch), "svob200_warp_affine");
+}
+
+}  // namespace warp
+
+// matcher.cpp:123-136 (not declared in matcher.h, but an external symbol of matcher.cpp)
+bool depthFromTriangulation(const SE3& T_search_ref, const Vector3d& f_ref, const Vector3d& f_cur, double& depth)
+{
+  double T[7];
+  b200::pose7(T_search_ref, T);
+  const double a[3] = {f_ref[0], f_ref[1], f_ref[2]}, b[3] = {f_cur[0], f_cur[1], f_cur[2]};
+  int ok = 0;
+  Lock lk(rt().mu);
+  check(svob200_depth_from_triangulation(ctx_locked(), 1, T, a, b, &depth, &ok), "svob200_depth_from_triangulation");
+  return ok != 0;
+}
+
+// ============================================================================ matcher.h: Matcher
+namespace {
+
+void fill_feature_ref(const Feature& ftr, int64_t ref_frame_id, const SE3& T_cur_ref, svob200_feature_ref* f)
+{
+  memset(f, 0, sizeof(*f));
+  f->ref_frame_id = ref_frame_id; f->ref_image = 0; f->cur_image = 0;
+  f->level = ftr.level; f->type = ftr.type == Feature::EDGELET ? 1 : 0;
+  f->px[0] = ftr.px[0]; f->px[1] = ftr.px[1];
+  f->f[0] = ftr.f[0]; f->f[1] = ftr.f[1]; f->f[2] = ftr.f[2];
+  f->grad[0] = ftr.grad[0]; f->grad[1] = ftr.grad[1];
+  b200::pose7(T_cur_ref, f->T_cur_ref);
+}
+
+}  // namespace
+
+// matcher.cpp:138-147
+void Matcher::createPatchFromPatchWithBorder()
+{
+  for (int y = 0; y < patch_size_; ++y)
+    memcpy(patch_ + y * patch_size_, patch_with_border_ + (y + 1) * (patch_size_ + 2) + 1, patch_size_);
+}
+
+// matcher.cpp:156-202
+bool Matcher::findMatchDirect(const Point& pt, const Frame& cur_frame, Vector2d& px_cur)
+{
+  if (!pt.getCloseViewObs(cur_frame.pos(), ref_ftr_)) return false;                       // host: picks the observation (point.cpp:101-125)
+  const Vector2i pxi(ref_ftr_->px.cast<int>() / (1 << ref_ftr_->level));
+  if (!ref_ftr_->frame->cam_->isInFrame(pxi, halfpatch_size_ + 2, ref_ftr_->level)) return false;
+
+  const svob200_camera cam = b200::camera_of(cur_frame.cam_);
+  svob200_matcher_opts mo;
+  b200::matcher_opts_of(options_, &mo);
+  const double depth_ref = (ref_ftr_->frame->pos() - pt.pos_).norm();
+  const double px_in[2] = {px_cur[0], px_cur[1]};
+  svob200_match_result res;
+  {
+    Lock lk(rt().mu);
+    svob200_ctx* ctx = ctx_locked();
+    const int64_t ref_id = b200::ensure_frame_locked(*ref_ftr_->frame);
+    const int64_t cur_id = b200::ensure_frame_locked(cur_frame);
+    svob200_feature_ref f;
+    fill_feature_ref(*ref_ftr_, ref_id, cur_frame.T_f_w_ * ref_ftr_->frame->T_f_w_.inverse(), &f);
+    check(svob200_match_direct(ctx, cur_id, &cam, 1, &f, &depth_ref, px_in, &mo, &res, SVOB200_MEM_HOST), "svob200_match_direct");
+  }
+  A_cur_ref_ << res.A_cur_ref[0], res.A_cur_ref[1], res.A_cur_ref[2], res.A_cur_ref[3];
+  search_level_ = res.search_level;
+  memcpy(patch_with_border_, res.patch_with_border, sizeof(patch_with_border_));
+  memcpy(patch_, res.patch, sizeof(patch_));
+  if (ref_ftr_->type == Feature::EDGELET) h_inv_ = res.h_inv;
+  px_cur << res.px_cur[0], res.px_cur[1];                                                 // written whether or not LK converged (:200)
+  return res.success != 0;
+}
+
+// matcher.cpp:207-355
+bool Matcher::findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const Feature& ref_ftr, const double d_estimate,
+                                      const double d_min, const double d_max, double& depth)
+{
+  const svob200_camera cam = b200::camera_of(cur_frame.cam_);
+  svob200_matcher_opts mo;
+  b200::matcher_opts_of(options_, &mo);
+  const SE3 T_cur_ref = cur_frame.T_f_w_ * ref_frame.T_f_w_.inverse();
+  const double d[3] = {d_estimate, d_min, d_max};
+  svob200_epi_result res;
+  {
+    Lock lk(rt().mu);
+    svob200_ctx* ctx = ctx_locked();
+    const int64_t ref_id = b200::ensure_frame_locked(ref_frame);
+    const int64_t cur_id = b200::ensure_frame_locked(cur_frame);
+    svob200_feature_ref f;
+    fill_feature_ref(ref_ftr, ref_id, T_cur_ref, &f);
+    check(svob200_epipolar_match(ctx, cur_id, &cam, 1, &f, d, &mo, &res, SVOB200_MEM_HOST), "svob200_epipolar_match");
+  }
+  epi_dir_ << res.epi_dir[0], res.epi_dir[1];
+  A_cur_ref_ << res.A_cur_ref[0], res.A_cur_ref[1], res.A_cur_ref[2], res.A_cur_ref[3];
+  reject_ = res.reject != 0;
+  if (reject_) return false;                                                              // :236-239: nothing else is touched
+  search_level_ = res.search_level;
+  epi_length_ = res.epi_length;
+  memcpy(patch_with_border_, res.patch_with_border, sizeof(patch_with_border_));
+  memcpy(patch_, res.patch, sizeof(patch_));
+  if (res.px_cur_valid) px_cur_ << res.px_cur[0], res.px_cur[1];
+  if (options_.align_1d && res.h_inv != 0.0) h_inv_ = res.h_inv;
+  if (!res.success) return false;
+  depth = res.depth;
+  return true;
+}
+
+// ============================================================================ sparse_img_align.h
+// sparse_img_align.cpp:29-41
+SparseImgAlign::SparseImgAlign(int max_level, int min_level, int n_iter, Method method, bool display, bool verbose)
+  : display_(display), max_level_(max_level), min_level_(min_level)
+{
+  n_iter_ = n_iter;
+  n_iter_init_ = n_iter_;
+  method_ = method;
+  verbose_ = verbose;
+  eps_ = 0.000001;
+}
+
+// sparse_img_align.cpp:51-92.  precomputeReferencePatches / computeResiduals / solve / update and the
+// whole vk::NLLSSolver::optimizeGaussNewton loop (nlls_solver_impl.hpp:25-100) run inside ONE kernel launch.
+size_t SparseImgAlign::run(FramePtr ref_frame, FramePtr cur_frame)
+{
+  reset();
+  if (ref_frame->fts_.empty()) {
+    fprintf(stderr, "[svo_b200] SparseImgAlign: no features to track!\n");
+    return 0;
+  }
+  if (method_ != GaussNewton) throw std::runtime_error("svo_b200: SparseImgAlign runs Gauss-Newton only (the one method the reference uses, frame_handler_mono.cpp:186-187)");
+  ref_frame_ = ref_frame;
+  cur_frame_ = cur_frame;
+  const int N = (int)ref_frame_->fts_.size();
+  visible_fts_.resize(N, false);
+  have_ref_patch_cache_ = false;
+
+  // flatten the feature list (sparse_img_align.cpp:114-134: depth = |pos - ref_pos|, xyz_ref = f * depth)
+  std::vector<double> px(2 * (size_t)N), xyz(3 * (size_t)N, 0.0);
+  std::vector<uint8_t> has_point(N, 0);
+  const Vector3d ref_pos = ref_frame_->pos();
+  {
+    int i = 0;
+    for (auto it = ref_frame_->fts_.begin(); it != ref_frame_->fts_.end(); ++it, ++i) {
+      const Feature* ftr = *it;
+      px[2 * i] = ftr->px[0]; px[2 * i + 1] = ftr->px[1];
+      if (ftr->point == NULL) continue;
+      has_point[i] = 1;
+      const double depth = (ftr->point->pos_ - ref_pos).norm();
+      const Vector3d xyz_ref(ftr->f * depth);
+      xyz[3 * i] = xyz_ref[0]; xyz[3 * i + 1] = xyz_ref[1]; xyz[3 * i + 2] = xyz_ref[2];
+    }
+  }
+  SE3 T_cur_from_ref(cur_frame_->T_f_w_ * ref_frame_->T_f_w_.inverse());
+  double T_init[7];
+  b200::pose7(T_cur_from_ref, T_init);
+  const svob200_camera cam = b200::camera_of(ref_frame_->cam_);
+  svob200_align_opts opts;
+  opts.max_level = max_level_; opts.min_level = min_level_; opts.n_iter = (int)n_iter_; opts.eps = eps_;
+  const int offsets[2] = {0, N};
+  svob200_align_result res;
+  {
+    Lock lk(rt().mu);
+    svob200_ctx* ctx = ctx_locked();
+    const int64_t ref_id = b200::ensure_frame_locked(*ref_frame_);
+    const int64_t cur_id = b200::ensure_frame_locked(*cur_frame_);
+    check(svob200_sparse_align(ctx, ref_id, cur_id, &cam, 1, offsets, px.data(), xyz.data(), has_point.data(), T_init, &opts, &res, SVOB200_MEM_HOST),
+          "svob200_sparse_align");
+  }
+  // solver state the reference leaves behind (read by getFisherInformation and by callers of NLLSSolver's public members)
+  for (int r = 0; r < 6; ++r) {
+    for (int c = 0; c < 6; ++c) H_(r, c) = res.H[r * 6 + c];
+    Jres_[r] = res.Jres[r];
+    x_[r] = res.x[r];
+  }
+  chi2_ = res.chi2;
+  n_meas_ = (size_t)res.n_meas;
+  stop_ = res.stop != 0;
+  level_ = min_level_ - 1;                                   // value of the loop variable after run() (:65)
+  iter_ = 0;
+  for (int l = 0; l < SVOB200_MAX_LEVELS; ++l) { b200::g_last_iters[l] = res.iters[l]; if (l == min_level_ && res.iters[l] > 0) iter_ = (size_t)res.iters[l] - 1; }
+  b200::g_last_exact = res.n_exact_chi2;
+
+  T_cur_from_ref = b200::se3_of(res.T_cur_ref);
+  cur_frame_->T_f_w_ = T_cur_from_ref * ref_frame_->T_f_w_;  // :89
+  return n_meas_ / patch_area_;
+}
+
+// sparse_img_align.cpp:94-99
+Matrix<double, 6, 6> SparseImgAlign::getFisherInformation()
+{
+  const double sigma_i_sq = 5e-4 * 255 * 255;
+  Matrix<double, 6, 6> I = H_ / sigma_i_sq;
+  return I;
+}
+
+// NLLSSolver's per-iteration hooks (nlls_solver.h:63-87).  The Gauss-Newton loop lives on the device, so
+// run() never calls them; they exist because the class declares them (vtable) and keep the solver's contract
+// for a caller that drives vk::NLLSSolver::optimize() by hand: that route is not accelerated and says so.
+void SparseImgAlign::precomputeReferencePatches() {}
+double SparseImgAlign::computeResiduals(const SE3&, bool, bool)
+{
+  throw std::runtime_error("svo_b200: SparseImgAlign::computeResiduals is fused into run() on the device; call run()");
+}
+int SparseImgAlign::solve()
+{
+  x_ = H_.ldlt().solve(Jres_);                               // sparse_img_align.cpp:291-297
+  if ((bool)std::isnan((double)x_[0])) return 0;
+  return 1;
+}
+void SparseImgAlign::update(const ModelType& T_curold_from_ref, ModelType& T_curnew_from_ref)
+{
+  const Matrix<double, 6, 1> neg = -x_;
+  T_curnew_from_ref = T_curold_from_ref * SE3::exp(neg.data());   // sparse_img_align.cpp:302-308
+}
+void SparseImgAlign::startIteration() {}
+void SparseImgAlign::finishIteration() {}
+
+// ============================================================================ feature_detection.h
+namespace feature_detection {
+
+// feature_detection.cpp:24-64 — grid bookkeeping (host state of the detector object)
+AbstractDetector::AbstractDetector(const int img_width, const int img_height, const int cell_size, const int n_pyr_levels)
+  : cell_size_(cell_size), n_pyr_levels_(n_pyr_levels),
+    grid_n_cols_(ceil(static_cast<double>(img_width) / cell_size_)),
+    grid_n_rows_(ceil(static_cast<double>(img_height) / cell_size_)),
+    grid_occupancy_(grid_n_cols_ * grid_n_rows_, false)
+{}
+
+void AbstractDetector::resetGrid() { std::fill(grid_occupancy_.begin(), grid_occupancy_.end(), false); }
+
+void AbstractDetector::setExistingFeatures(const Features& fts)
+{
+  for (auto it = fts.begin(); it != fts.end(); ++it) setGridOccpuancy((*it)->px);
+}
+
+void AbstractDetector::setGridOccpuancy(const Vector2d& px)
+{
+  grid_occupancy_.at(static_cast<int>(px[1] / cell_size_) * grid_n_cols_ + static_cast<int>(px[0] / cell_size_)) = true;
+}
+
+FastDetector::FastDetector(const int img_width, const int img_height, const int cell_size, const int n_pyr_levels)
+  : AbstractDetector(img_width, img_height, cell_size, n_pyr_levels)
+{}
+
+// feature_detection.cpp:77-122: cv::FAST + shiTomasiScore + per-cell strict-> argmax over all levels in one pass on the device
+void FastDetector::detect(Frame* frame, const ImgPyr& img_pyr, const double detection_threshold, Features& fts)
+{
+  if ((int)img_pyr.size() < n_pyr_levels_) throw std::runtime_error("svo_b200: FastDetector::detect: pyramid has fewer levels than n_pyr_levels");
+  if (!b200::pyramid_is_halving(img_pyr, n_pyr_levels_)) throw std::runtime_error("svo_b200: FastDetector::detect: not an integer-halving pyramid");
+  const int n_cells = grid_n_cols_ * grid_n_rows_;
+  const int w = img_pyr[0].cols, h = img_pyr[0].rows;
+  if ((w + cell_size_ - 1) / cell_size_ != grid_n_cols_ || (h + cell_size_ - 1) / cell_size_ != grid_n_rows_)
+    throw std::runtime_error("svo_b200: FastDetector::detect: image size does not match the detector grid");
+  std::vector<uint8_t> occ(n_cells);
+  for (int k = 0; k < n_cells; ++k) occ[k] = grid_occupancy_[k] ? 1 : 0;
+  std::vector<svob200_corner> cells(n_cells);
+  int n_features = 0;
+  {
+    Lock lk(rt().mu);
+    svob200_ctx* ctx = ctx_locked();
+    const int64_t id = b200::scratch_frame_locked(w, h, n_pyr_levels_);
+    b200::upload_pyramid_locked(ctx, id, img_pyr, n_pyr_levels_);
+    check(svob200_fast_detect(ctx, id, n_pyr_levels_, cell_size_, detection_threshold, occ.data(), cells.data(), &n_features, SVOB200_MEM_HOST),
+          "svob200_fast_detect");
+  }
+  for (int k = 0; k < n_cells; ++k) {                          // cell-index order, like the reference's for_each (:115-119)
+    const svob200_corner& c = cells[k];
+    if ((double)c.score > detection_threshold) fts.push_back(new Feature(frame, Vector2d(c.x, c.y), c.level));
+  }
+  resetGrid();
+}
+
+}  // namespace feature_detection
+
+// ============================================================================ depth_filter.h
+// depth_filter.cpp:237-341.  Every seed's update depends only on its own state, the two frames and the
+// two poses, so the sequential list walk is a batch: flatten -> three launches -> apply in list order.
+void B200DepthFilter::updateSeeds(FramePtr frame)
+{
+  lock_t lock(seeds_mut_);
+  last_n_seeds_ = seeds_.size(); last_n_updates_ = 0; last_n_failed_matches_ = 0;
+  if (seeds_updating_halt_) return;                                   // the reference polls the flag per seed (:253-254); a batch polls it once
+
+  // too-old seeds go first (:258-261); the reference erases them lazily while walking the list — same result
+  for (auto it = seeds_.begin(); it != seeds_.end();) {
+    if ((Seed::batch_counter - it->batch_id) > options_.max_n_kfs) it = seeds_.erase(it);
+    else ++it;
+  }
+  const int n = (int)seeds_.size();
+  if (n == 0) return;
+
+  const svob200_camera cam = b200::camera_of(frame->cam_);
+  svob200_matcher_opts mo;
+  b200::matcher_opts_of(matcher_.options_, &mo);
+  std::vector<svob200_feature_ref> ftrs(n);
+  std::vector<double> T_ref_w(7 * (size_t)n);
+  std::vector<svob200_seed> state(n);
+  std::vector<svob200_seed_obs> obs(n);
+  double T_cur_w[7];
+  b200::pose7(frame->T_f_w_, T_cur_w);
+  {
+    Lock lk(rt().mu);
+    svob200_ctx* ctx = ctx_locked();
+    const int64_t cur_id = b200::ensure_frame_locked(*frame);
+    int i = 0;
+    for (auto it = seeds_.begin(); it != seeds_.end(); ++it, ++i) {
+      const int64_t ref_id = b200::ensure_frame_locked(*it->ftr->frame);
+      fill_feature_ref(*it->ftr, ref_id, SE3(), &ftrs[i]);              // poses travel separately (T_ref_w / T_cur_w)
+      b200::pose7(it->ftr->frame->T_f_w_, &T_ref_w[7 * (size_t)i]);
+      state[i].a = it->a; state[i].b = it->b; state[i].mu = it->mu; state[i].z_range = it->z_range; state[i].sigma2 = it->sigma2;
+    }
+    b200::ensure_frame_locked(*frame);                                  // keep the current frame the most recently used entry
+    check(svob200_seeds_update(ctx, cur_id, &cam, n, ftrs.data(), T_ref_w.data(), T_cur_w, &mo, options_.seed_convergence_sigma2_thresh,
+                               state.data(), obs.data(), SVOB200_MEM_HOST), "svob200_seeds_update");
+  }
+
+  int i = 0;
+  for (auto it = seeds_.begin(); it != seeds_.end(); ++i) {
+    const svob200_seed_obs& o = obs[i];
+    if (o.status == SVOB200_SEED_BEHIND || o.status == SVOB200_SEED_NOT_IN_FRAME) { ++it; continue; }     // :266-273
+    it->a = state[i].a; it->b = state[i].b; it->mu = state[i].mu; it->sigma2 = state[i].sigma2;
+    if (o.status == SVOB200_SEED_NO_MATCH) { ++last_n_failed_matches_; ++it; continue; }                  // b++ happened on the device (:286)
+    ++last_n_updates_;
+    if (frame->isKeyframe() && feature_detector_)
+      feature_detector_->setGridOccpuancy(Vector2d(o.px_cur[0], o.px_cur[1]));                          // :306-310
+    if (o.status == SVOB200_SEED_CONVERGED) {                                                            // :314-337
+      assert(it->ftr->point == NULL);
+      Vector3d xyz_world(it->ftr->frame->T_f_w_.inverse() * (it->ftr->f * (1.0 / it->mu)));
+      Point* point = new Point(xyz_world, it->ftr);
+      it->ftr->point = point;
+      seed_converged_cb_(point, it->sigma2);
+      it = seeds_.erase(it);
+    } else if (o.status == SVOB200_SEED_NAN_ERASED) {                                                    // :338-342
+      fprintf(stderr, "[svo_b200] z_min is NaN\n");
+      it = seeds_.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+}  // namespace svo

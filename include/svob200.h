@@ -78,6 +78,9 @@ int svob200_frame_slot(svob200_ctx* ctx, int64_t frame_id);
 /* download one level of one image into a dense (or strided) host buffer */
 int svob200_frame_download(svob200_ctx* ctx, int64_t frame_id, int image, int level,
                            uint8_t* out, int out_stride);
+/* copy ONE level of one image verbatim from host memory: mirrors a host pyramid (Frame::img_pyr_,
+ * frame.h) on the device exactly as the host holds it; used by the C++ drop-in's frame cache */
+int svob200_frame_upload_level(svob200_ctx* ctx, int64_t frame_id, int image, int level, const uint8_t* data, int stride);
 int svob200_frame_release(svob200_ctx* ctx, int64_t frame_id);
 int svob200_frame_info(svob200_ctx* ctx, int64_t frame_id, int* batch, int* w, int* h, int* n_levels);
 /* stand-alone vk::halfSample(in,out) on host buffers (vision.h:38): upload, one level, download */
@@ -98,6 +101,9 @@ int svob200_fast_detect(svob200_ctx* ctx, int64_t frame_id, int n_detect_levels,
  * Returns the keypoint count (<0 on error); writes at most cap entries. */
 int svob200_fast_corners(svob200_ctx* ctx, int64_t frame_id, int image, int level, int threshold,
                          int nonmax, int cap, int* xs, int* ys, int* scores);
+
+/* vk::shiTomasiScore(img,u,v) (vision.cpp:113-154, vision.h:40) for n pixels (uv: 2 ints each) of a host image */
+int svob200_shi_tomasi(svob200_ctx* ctx, const uint8_t* img, int w, int h, int stride, int n, const int* uv, float* scores);
 
 /* ---------------------------------------------------------------- sparse image alignment
  * replaces: SparseImgAlign::run (sparse_img_align.cpp:51-92) incl. precomputeReferencePatches,
@@ -165,9 +171,25 @@ int svob200_match_direct(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_c
                          const double* px_cur_in, const svob200_matcher_opts* opts,
                          svob200_match_result* results, int mem);
 
+/* warp::getWarpMatrixAffine (matcher.cpp:36-60, matcher.h:40-48) for n items: px_ref 2, f_ref 3, depth_ref 1,
+ * T_cur_ref 7, level_ref 1 per item -> A_cur_ref row-major 2x2 per item */
+int svob200_warp_matrix_affine(svob200_ctx* ctx, const svob200_camera* cam, int n, const double* px_ref, const double* f_ref,
+                               const double* depth_ref, const double* T_cur_ref, const int* level_ref, double* A_out, int mem);
+/* warp::warpAffine (matcher.cpp:83-116, matcher.h:54-61) on a host image level; patch = (2*halfpatch_size)^2 bytes,
+ * in/out: left untouched when A_cur_ref inverts to NaN, like the reference */
+int svob200_warp_affine(svob200_ctx* ctx, const uint8_t* img, int w, int h, int stride, const double* A_cur_ref, const double* px_ref,
+                        int level_ref, int search_level, int halfpatch_size, uint8_t* patch);
+
+/* depthFromTriangulation (matcher.cpp:123-136) for n items: T_search_ref 7, f_ref 3, f_cur 3 per item;
+ * depth is in/out (untouched where ok[i] = 0, like the reference's reference parameter) */
+int svob200_depth_from_triangulation(svob200_ctx* ctx, int n, const double* T_search_ref, const double* f_ref, const double* f_cur,
+                                     double* depth, int* ok);
+
 typedef struct {
   int success; int search_level; int reject; int zmssd_best; int n_evals; int n_steps;
   double depth; double px_cur[2]; double epi_length; double A_cur_ref[4]; double h_inv;
+  double epi_dir[2];         /* Matcher::epi_dir_ = A - B on the unit plane (matcher.cpp:224) */
+  int px_cur_valid;          /* the reference wrote Matcher::px_cur_ on this call (matcher.cpp:259, :327, :345) */
   uint8_t patch_with_border[100]; uint8_t patch[64];
 } svob200_epi_result;
 /* d: n*3 doubles (d_estimate, d_min, d_max) */

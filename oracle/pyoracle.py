@@ -53,6 +53,9 @@ def build(force=False):
             for f in ("ref_harness.cpp", "shim/cv_fast.cpp", "shim/opencv2/opencv.hpp", "svo_oracle.c"))
         if force or stale:
             subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        # the same harness over the C++ drop-in (needs the product library to link against)
+        if os.path.exists(os.path.join(HERE, "..", "android_svo_b200", "lib", "libsvob200.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])
 
 
 class Cam(C.Structure):
@@ -340,8 +343,10 @@ class Ref:
     machines where it was never built (e.g. a checkout without /root/reference and without the
     prebuilt .so)."""
 
-    def __init__(self, nosse=False):
-        name = "libsvo_ref_nosse.so" if nosse else "libsvo_ref.so"
+    def __init__(self, nosse=False, dropin=False):
+        # dropin: the SAME C++ harness linked over android_svo_b200/host/svo_b200_dropin.cpp instead of the
+        # reference's hot-path TUs (oracle/_ref/libsvo_dropin.so) — every operator call lands in CUDA
+        name = "libsvo_dropin.so" if dropin else ("libsvo_ref_nosse.so" if nosse else "libsvo_ref.so")
         self.path = os.path.join(OUT, name)
         self.lib = None
         if os.path.exists(self.path):
@@ -363,6 +368,13 @@ class Ref:
 
     def available(self):
         return self.lib is not None
+
+    def is_dropin(self):
+        return bool(self.lib.svo_ref_is_dropin())
+
+    def dropin_launches(self):
+        self.lib.svo_ref_dropin_launches.restype = C.c_longlong
+        return int(self.lib.svo_ref_dropin_launches())
 
     def config(self, n_pyr_levels, klt_max_level, klt_min_level=2):
         self.lib.svo_ref_config(n_pyr_levels, klt_max_level, klt_min_level)

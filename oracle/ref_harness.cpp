@@ -25,6 +25,15 @@
 #include <svo/depth_filter.h>
 #include <map>
 #include <cstring>
+#ifdef SVOB200_DROPIN
+// Same harness, linked over android_svo_b200/host/svo_b200_dropin.cpp INSTEAD OF the reference's
+// vision / feature_alignment / matcher / sparse_img_align / feature_detection TUs
+// (oracle/_ref/libsvo_dropin.so): every call below then lands in CUDA through the C ABI.
+#include "svo_b200_dropin.h"
+typedef svo::B200DepthFilter DepthFilterT;
+#else
+typedef svo::DepthFilter DepthFilterT;
+#endif
 
 using namespace svo;
 namespace svo { bool depthFromTriangulation(const SE3& T_search_ref, const Vector3d& f_ref, const Vector3d& f_cur, double& depth); }
@@ -55,6 +64,11 @@ struct AlignProbe : public SparseImgAlign {
     evals[level_]++;
     return SparseImgAlign::computeResiduals(m, lin, w);
   }
+#ifdef SVOB200_DROPIN
+  void fetch_evals() { evals.assign(svo::b200::lastAlignIterations(), svo::b200::lastAlignIterations() + 8); }
+#else
+  void fetch_evals() {}
+#endif
   const Matrix<double, 6, 6>& H() const { return H_; }
   const Matrix<double, 6, 1>& Jres() const { return Jres_; }
   const Matrix<double, 6, 1>& x() const { return x_; }
@@ -74,6 +88,32 @@ void svo_ref_config(int n_pyr_levels, int klt_max_level, int klt_min_level)
   Config::nPyrLevels() = n_pyr_levels;
   Config::kltMaxLevel() = klt_max_level;
   Config::kltMinLevel() = klt_min_level;
+}
+
+// 1 when this library is the B200 drop-in build (the hot-path symbols resolve to the CUDA adapter)
+int svo_ref_is_dropin()
+{
+#ifdef SVOB200_DROPIN
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+long long svo_ref_dropin_launches()
+{
+#ifdef SVOB200_DROPIN
+  return svo::b200::launchCount();
+#else
+  return 0;
+#endif
+}
+
+void svo_ref_dropin_shutdown()
+{
+#ifdef SVOB200_DROPIN
+  svo::b200::shutdown();
+#endif
 }
 
 int svo_ref_has_sse2()
@@ -223,6 +263,7 @@ int svo_ref_sparse_align(const uint8_t* ref_img, const uint8_t* cur_img, const i
     from_se3(SE3(cur->T_f_w_ * ref->T_f_w_.inverse()), T_cur_ref_init_out);
     AlignProbe al(max_level, min_level, n_iter);
     ret = al.run(ref, cur);
+    al.fetch_evals();
     from_se3(cur->T_f_w_, T_cur_w_out);
     from_se3(SE3(cur->T_f_w_ * ref->T_f_w_.inverse()), T_cur_ref_out);  // informational (recomposed)
     for (int a = 0; a < 6; ++a) {
@@ -387,7 +428,7 @@ int svo_ref_update_seeds(int n_ref, const uint8_t* const* ref_imgs, const double
       std::vector<Point*> new_points;
       std::vector<int> st(S, 2);
       std::vector<float> conv_sigma2(S, 0.f);
-      DepthFilter df(feature_detection::DetectorPtr(), [&](Point* p, double sigma2) {
+      DepthFilterT df(feature_detection::DetectorPtr(), [&](Point* p, double sigma2) {
         const int i = index[p->obs_.front()];
         st[i] = 1; conv_sigma2[i] = (float)sigma2; new_points.push_back(p);
       });
@@ -456,7 +497,7 @@ void* svo_ref_seq_create(const int* wh, const double* k, int max_level, int min_
   s->cam = make_cam(wh, k);
   s->max_level = max_level; s->min_level = min_level; s->n_iter = n_iter; s->reseed = reseed;
   s->depth_mean = depth_mean; s->depth_min = depth_min;
-  s->df = new DepthFilter(feature_detection::DetectorPtr(), [s](Point* p, double) { s->conv_points.push_back(p); });
+  s->df = new DepthFilterT(feature_detection::DetectorPtr(), [s](Point* p, double) { s->conv_points.push_back(p); });
   s->df->options_.seed_convergence_sigma2_thresh = conv_thresh;
   return s;
 }
@@ -521,6 +562,7 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   cur->T_f_w_ = last->T_f_w_;                                       // frame_handler_mono.cpp:175
   AlignProbe al(s->max_level, s->min_level, s->n_iter);
   st->n_tracked = (int)al.run(last, cur);
+  al.fetch_evals();
   st->chi2 = al.chi2();
   for (size_t l = 0; l < al.evals.size(); ++l) st->align_iters += al.evals[l];
   from_se3(cur->T_f_w_, st->T_cur_w);
