@@ -109,7 +109,9 @@ def load_library():
     L.svob200_tracker_step.argtypes = [V, V, C.c_int, V, V, V, V, V, C.c_int]
     L.svob200_tracker_get_seeds.argtypes = [V, V]
     L.svob200_tracker_enable_profiling.argtypes = [V, C.c_int]
-    L.svob200_tracker_stage_ms.argtypes = [V, c_fp]
+    L.svob200_tracker_stage_ms.argtypes = [V, c_fp, C.c_int]
+    L.svob200_tracker_stage_name.restype = C.c_char_p
+    L.svob200_tracker_stage_name.argtypes = [C.c_int]
     L.svob200_tracker_get_seed_obs.argtypes = [V, V]
     L.svob200_dev_alloc.argtypes = [V, C.c_size_t, C.POINTER(V)]
     L.svob200_dev_free.argtypes = [V, V]
@@ -139,6 +141,7 @@ EXPORTED_SYMBOLS = [
     "svob200_tracker_create", "svob200_tracker_destroy", "svob200_tracker_set_keyframe", "svob200_tracker_set_last",
     "svob200_tracker_step", "svob200_tracker_get_seeds", "svob200_tracker_launches_per_step",
     "svob200_tracker_enable_profiling", "svob200_tracker_stage_ms", "svob200_tracker_get_seed_obs",
+    "svob200_tracker_num_stages", "svob200_tracker_stage_name",
     "svob200_frame_upload_level", "svob200_shi_tomasi", "svob200_warp_matrix_affine", "svob200_warp_affine",
     "svob200_depth_from_triangulation",
 ]
@@ -433,12 +436,12 @@ class Tracker:
     def enable_profiling(self, on=True):
         self.ctx._ck(self.L.svob200_tracker_enable_profiling(self.h, int(on)))
 
-    STAGES = ("frame+pyramid", "features_prepare", "sparse_align", "reproject_prepare", "match_direct", "seeds_update", "stats")
-
     def stage_ms(self):
-        ms = (C.c_float * 7)()
-        self.ctx._ck(self.L.svob200_tracker_stage_ms(self.h, ms))
-        return dict(zip(self.STAGES, [float(x) for x in ms]))
+        """CUDA-event duration of every stage (kernel) of the most recent step, by name."""
+        n = self.L.svob200_tracker_num_stages()
+        ms = (C.c_float * n)()
+        self.ctx._ck(self.L.svob200_tracker_stage_ms(self.h, ms, n))
+        return {self.L.svob200_tracker_stage_name(i).decode(): float(ms[i]) for i in range(n)}
 
     def close(self):
         if getattr(self, "h", None):

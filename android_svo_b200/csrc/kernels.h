@@ -38,7 +38,8 @@ int launch_epipolar(const DevFrame* d_frames, const int* d_ref_slot, int cur_slo
 int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
                         const svob200_feature_ref* d_ftrs, const double* d_T_ref_w, const double* d_T_cur_w,
                         svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs,
-                        void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches);
+                        void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches,
+                        cudaEvent_t* marks = nullptr /* 2 events: after the geometry kernel, after the search kernel */);
 size_t seeds_scratch_bytes(int n);
 int launch_update_seed(int n, const float* d_x, const float* d_tau2, svob200_seed* d_seeds, cudaStream_t s, long long* launches);
 int launch_compute_tau(int n, const double* d_T, const double* d_f, const double* d_z, double angle, double* d_out,

@@ -905,7 +905,7 @@ size_t seeds_scratch_bytes(int n)
 int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
                         const svob200_feature_ref* d_ftrs, const double* d_T_ref_w, const double* d_T_cur_w,
                         svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs,
-                        void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches)
+                        void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches, cudaEvent_t* marks)
 {
   // d_ftrs / d_T_ref_w / d_seeds / d_obs already point at seed `first`; the scratch was sized for
   // scratch_total seeds and is indexed by absolute seed number
@@ -917,7 +917,9 @@ int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur
   EpiSearch* search = reinterpret_cast<EpiSearch*>(p) + first; p += ((m * sizeof(EpiSearch) + 255) & ~(size_t)255);
   SeedPre* pre = reinterpret_cast<SeedPre*>(p) + first;
   seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, geom);
+  if (marks) cudaEventRecord(marks[0], s);
   seeds_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, pre, geom, search);
+  if (marks) cudaEventRecord(marks[1], s);
   seeds_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, conv_thresh, pre, geom, search, d_seeds, d_obs);
   *launches += 3;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

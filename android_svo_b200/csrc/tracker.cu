@@ -5,7 +5,7 @@
 // It chains the operators exactly the way FrameHandlerMono::processFrame + DepthFilter do
 // (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), minus the host-only stages that are
 // out of scope (pose_optimizer, map management): everything between the operators that the
-// reference does in host code is done by the glue kernels, so a step is 13 launches on one stream
+// reference does in host code is done by the glue kernels, so a step is 11 launches on one stream
 // with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
 // H2D of the small per-step inputs and one D2H of the per-sequence results.
 #include "ctx_internal.h"
@@ -67,6 +67,12 @@ template <class T> int dalloc(svob200_ctx* ctx, T** p, size_t n)
 
 }  // namespace
 
+// CUDA-event stage marks of one step (svob200_tracker_stage_ms / _stage_name): one entry per kernel of the
+// step, except that the first also covers the frame copy/bind and the small per-step input copy
+constexpr int kNumStages = 9;
+static const char* const kStageNames[kNumStages] = {"frame+pyramid", "features_prepare", "sparse_align", "reproject_prepare",
+                                                    "match_direct", "seeds_geom", "seeds_search", "seeds_finish", "stats"};
+
 struct svob200_tracker {
   svob200_ctx* ctx = nullptr;
   svob200_camera cam{};
@@ -98,7 +104,7 @@ struct svob200_tracker {
   std::vector<cudaEvent_t> chunk_ev;
   // optional per-stage CUDA-event timing (bench.py's stage breakdown / roofline)
   bool profiling = false;
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kNumStages + 1] = {};
 };
 
 
@@ -134,7 +140,7 @@ void svob200_tracker_destroy(svob200_tracker* t)
   if (t->h_pinned) cudaFreeHost(t->h_pinned);
   for (auto e : t->chunk_ev) cudaEventDestroy(e);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
-  for (int k = 0; k < 8; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
+  for (int k = 0; k <= kNumStages; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   delete t;
 }
 
@@ -279,15 +285,16 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   MARK(5);
   // 6. DepthFilter::updateSeeds(cur)
   if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
-                          t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s, &ctx->launches))
+                          t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s, &ctx->launches,
+                          (marks && t->profiling) ? &t->ev[6] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
-  MARK(6);
+  MARK(8);
   // 7. per-sequence statistics (+ steady-state re-seeding)
   step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
                                         t->d_seeds, t->seed_init, t->reseed, t->d_stats + c0);
   ++ctx->launches;
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
-  MARK(7);
+  MARK(9);
 #undef MARK
   return 0;
 }
@@ -371,25 +378,27 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
   return SVOB200_OK;
 }
 
-int svob200_tracker_launches_per_step(void) { return 13; }
+int svob200_tracker_launches_per_step(void) { return 11; }
 
-// stage timing: 7 durations [frame copy/bind + pyramid + per-step input copy, features_prepare + init_pose,
-// sparse_align, compose + reproject_prepare, match_direct, seeds_update, stats]
+// stage timing: CUDA events recorded on the launching stream between the kernels of a step
 int svob200_tracker_enable_profiling(svob200_tracker* t, int on)
 {
   if (!t) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
-  if (on && !t->ev[0]) for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&t->ev[k]));
+  if (on && !t->ev[0]) for (int k = 0; k <= kNumStages; ++k) CU(cudaEventCreate(&t->ev[k]));
   t->profiling = on != 0;
   return SVOB200_OK;
 }
 
-int svob200_tracker_stage_ms(svob200_tracker* t, float* ms /*7*/)
+int svob200_tracker_num_stages(void) { return kNumStages; }
+const char* svob200_tracker_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+
+int svob200_tracker_stage_ms(svob200_tracker* t, float* ms, int cap)
 {
-  if (!t || !ms || !t->ev[0]) return SVOB200_ERR_ARG;
+  if (!t || !ms || !t->ev[0] || cap < kNumStages) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
-  CU(cudaEventSynchronize(t->ev[7]));
-  for (int k = 0; k < 7; ++k) CU(cudaEventElapsedTime(&ms[k], t->ev[k], t->ev[k + 1]));
+  CU(cudaEventSynchronize(t->ev[kNumStages]));
+  for (int k = 0; k < kNumStages; ++k) CU(cudaEventElapsedTime(&ms[k], t->ev[k], t->ev[k + 1]));
   return SVOB200_OK;
 }
 

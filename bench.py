@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from android_svo_b200 import synth, frontend  # noqa: E402
+from android_svo_b200 import synth, frontend, sharding  # noqa: E402
 
 METRIC = "front-end frames/s (pyramid + sparse align + refine + seed update), batched C2 sequences"
 CFG_NAME = "C2"
@@ -155,9 +155,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm (reference / oracle port)
-def cpu_arm(cfg, n_seqs, steps, warmup, threads):
+CPU_FRAMES_PER_STEP = 16   # a CPU "step" = this many consecutive frames of every sampled sequence (bounded sample, ~10-30 core-s per run)
+
+
+def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP):
     """Times the front-end step of `n_seqs` independent sequences on the host cores.  Uses the real
-    reference (oracle/_ref/libsvo_ref.so) when it was built, else the C restatement."""
+    reference (oracle/_ref/libsvo_ref.so) when it was built, else the C restatement.  One timed step =
+    `inner` consecutive frames of every sequence, one worker task per sequence."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle.pyoracle import Oracle, Ref, Cam, OracleSeq, RefSeq
     oracle, ref = Oracle(), Ref()
@@ -183,11 +187,17 @@ def cpu_arm(cfg, n_seqs, steps, warmup, threads):
 
     with ThreadPoolExecutor(threads) as ex:
         seqs = list(ex.map(setup, range(n_seqs)))
-        order = ping_pong(len(POOL_INDICES), warmup + steps)
+        order = ping_pong(len(POOL_INDICES), (warmup + steps) * inner)
+
+        def run_seq(i, k):
+            st = None
+            for j in range(k * inner, (k + 1) * inner):
+                a, b = order[j], order[j + 1]
+                st = seqs[i][0].step(seqs[i][1][b], poses[i, 1 + a], seqs[i][2][a])
+            return st
 
         def step_all(k):
-            a, b = order[k], order[k + 1]
-            return list(ex.map(lambda i: seqs[i][0].step(seqs[i][1][b], poses[i, 1 + a], seqs[i][2][a]), range(n_seqs)))
+            return list(ex.map(lambda i: run_seq(i, k), range(n_seqs)))
 
         for k in range(warmup):
             step_all(k)
@@ -198,7 +208,7 @@ def cpu_arm(cfg, n_seqs, steps, warmup, threads):
     tracked = float(np.mean([s.n_tracked for s in stats]))
     for s, _, _ in seqs:
         s.close()
-    return dict(kind=kind, fps=n_seqs * steps / dt, seconds=dt, n_seqs=n_seqs, tracked=tracked)
+    return dict(kind=kind, fps=n_seqs * steps * inner / dt, seconds=dt, n_seqs=n_seqs, tracked=tracked, inner=inner)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -214,7 +224,7 @@ def pinned_array(ctx, shape, dtype):
 class GpuWorkload:
     """Everything the timed loops need, resident: tracker, frame pool on device + pinned host, per-step inputs."""
 
-    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None):
+    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME):
         self.ctx, self.capi, self.cfg = ctx, capi, cfg
         B = len(seq_ids)
         self.B = B
@@ -249,7 +259,7 @@ class GpuWorkload:
         fid = 7
         ctx.frame_create(fid, B, w, h, cfg["n_levels"])
         ctx.frame_upload(fid, self.kf_host)
-        fc, ft, sc, st = frontend.DETECT[CFG_NAME]
+        fc, ft, sc, st = frontend.DETECT[cfg_name]
         fcells, _ = ctx.fast_detect(fid, cfg["n_pyr"], fc, ft)
         scells, _ = ctx.fast_detect(fid, cfg["n_pyr"], sc, st)
         ctx.frame_release(fid)
@@ -281,6 +291,25 @@ class GpuWorkload:
         self.trk.set_last(self.pool_dev[0], mem=self.capi.MEM_DEVICE, stride=self.cfg["w"])
         self.pos = 0
 
+    def close(self):
+        """release the tracker and every device / pinned buffer of this workload"""
+        if self.trk is None:
+            return
+        self.ctx.sync()
+        self.trk.close()
+        self.trk = None
+        for d in self.pool_dev + [x for pair in self.in_dev for x in pair] + [self.stats_dev]:
+            self.ctx.dev_free(d)
+        if self.own_tex:
+            self.ctx.dev_free(self.tex_dev)
+        for _, ptr in self.pool_host:
+            self.ctx._ck(self.ctx.L.svob200_host_free_pinned(self.ctx.h, ptr))
+        for pair in self.in_host:
+            for ptr in pair:
+                self.ctx._ck(self.ctx.L.svob200_host_free_pinned(self.ctx.h, ptr))
+        self.ctx._ck(self.ctx.L.svob200_host_free_pinned(self.ctx.h, self.stats_ptr))
+        self.pool_dev, self.pool_host, self.in_dev, self.in_host = [], [], [], []
+
     def step(self, order, k, mem):
         a, b = order[k], order[k + 1]
         w = self.cfg["w"]
@@ -301,9 +330,8 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
     cfg = synth.CONFIGS[CFG_NAME]
-    total = args.seqs - args.seqs % world
-    per = total // world
-    seq_ids = list(range(rank * per, (rank + 1) * per))          # contiguous block partition
+    total, per, rng = sharding.shard(args.seqs, rank, world)     # contiguous block partition
+    seq_ids = list(rng)
     t_setup = time.time()
     wl = GpuWorkload(ctx, capi, cfg, seq_ids)
     t_setup = time.time() - t_setup
@@ -316,11 +344,7 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, world, "cuda")
 
     # ---------------- value: inputs resident in HBM, CUDA events on the launching stream
     wl.reset()
@@ -358,8 +382,10 @@ def run_b200(args, rank, world, local_rank):
         "frame+pyramid": wl.B * 408000.0,
         "sparse_align": wl.B * N * (857.0 * iters_mean + 36.0 * (cfg["max_level"] - cfg["min_level"] + 1)),
         "match_direct": wl.B * N * (400.0 + 2 * 81.0),
-        "seeds_update": wl.B * S * (400.0 + 64.0 * mean_evals + 2 * 81.0 + 40.0),
+        "seeds_search": wl.B * S * (400.0 + 64.0 * mean_evals + 2 * 81.0),
     }
+    kernel_of = {"frame+pyramid": "pyramid_fused_kernel", "sparse_align": "sparse_align_kernel", "match_direct": "match_direct_kernel",
+                 "seeds_search": "seeds_search_kernel"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -375,21 +401,38 @@ def run_b200(args, rank, world, local_rank):
             e["hbm_frac"] = round(e["alg_GBps"] / peak, 4)
         stages[name] = e
     dom = max(alg.keys(), key=lambda n: stage_acc.get(n, 0.0))
-    traffic = None
+    # dram bytes per launch from the committed `ncu --set full` capture (profiles/traffic.json: bytes per sequence)
+    tj = {}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(dom, {}).get("dram_bytes_per_launch_per_seq")
-        if traffic is not None:
-            traffic = traffic * wl.B
     except Exception:
         pass
-    roofline = {"kernel": {"frame+pyramid": "pyramid_fused_kernel", "sparse_align": "sparse_align_kernel", "match_direct": "match_direct_kernel",
-                           "seeds_update": "seeds_update_kernel"}[dom],
-                "bound": "hbm", "achieved": round(alg[dom] / (stage_acc[dom] * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(alg[dom] / (stage_acc[dom] * 1e-3) / 1e9 / peak, 5), "traffic": traffic, "peak_source": peak_src,
-                "ms_per_launch": round(stage_acc[dom], 4), "share_of_step": round(stage_acc[dom] / max(sum(stage_acc.values()), 1e-9), 3),
-                "note": "latency/issue-bound kernel (one CTA per seed, data L2-resident); HBM fraction stated for completeness, "
-                        "the HBM-bound kernel is the pyramid (see stages)"}
+
+    def traffic_of(name):
+        t = tj.get(kernel_of[name], {}).get("dram_bytes_per_sequence")
+        return None if t is None else round(t * wl.B)
+
+    def roof(name):
+        a = alg[name] / (stage_acc[name] * 1e-3) / 1e9
+        return {"kernel": kernel_of[name], "bound": "hbm", "achieved": round(a, 2), "peak": peak, "unit": "GB/s", "frac": round(a / peak, 5),
+                "traffic": traffic_of(name), "algorithmic_bytes": round(alg[name]), "peak_source": peak_src,
+                "ms_per_launch": round(stage_acc[name], 4), "share_of_step": round(stage_acc[name] / max(sum(stage_acc.values()), 1e-9), 3)}
+
+    roofline = roof(dom)
+    roofline["note"] = ("dominant kernel of the step; it is integer-issue/L2-bound (ZMSSD dot products and LK on L2-resident windows), "
+                        "so its HBM fraction is small by construction; the HBM-streaming kernel of the path is the pyramid: "
+                        "see roofline_pyramid") if dom != "frame+pyramid" else "HBM-streaming kernel"
+    roofline_pyr = roof("frame+pyramid")
+    for name in stages:
+        if name in alg:
+            stages[name]["traffic"] = traffic_of(name)
+
+    # ---------------- plain pinned H2D rate of this box (context for the PCIe-bound e2e number)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.dev_upload(wl.pool_dev[0], wl.pool_host[1][0])
+    pcie = 3 * wl.pool_host[1][0].nbytes / (time.perf_counter() - t0) / 1e9
+    ctx.dev_upload(wl.pool_dev[0], wl.pool_host[0][0])
 
     # ---------------- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
     wl.reset()
@@ -407,22 +450,11 @@ def run_b200(args, rank, world, local_rank):
     stats_last = wl.stats_host.copy()
 
     # ---------------- per-sequence statistics: NCCL gather over NVLink, 64 B per sequence
-    rec = np.zeros((wl.B, 8), np.float64)
-    rec[:, 0] = seq_ids
-    rec[:, 1] = stats_last["n_tracked"]; rec[:, 2] = stats_last["n_matched"]; rec[:, 3] = stats_last["n_seeds_updated"]
-    rec[:, 4] = stats_last["n_seeds_converged"]; rec[:, 5] = stats_last["align_iters"]
     gt = wl.poses[:, 1 + order[W + K]]
-    for b in range(wl.B):
-        rec[b, 6], rec[b, 7] = synth.pose_error(stats_last["T_cur_w"][b], gt[b])
-    if world > 1:
-        mine = torch.from_numpy(rec).cuda()
-        allrec = torch.empty((world * wl.B, 8), dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allrec, mine)
-        rec = allrec.cpu().numpy()
-    seq_stats = {"n_sequences": int(len(rec)), "tracked_mean": float(rec[:, 1].mean()), "matched_mean": float(rec[:, 2].mean()),
-                 "seeds_updated_mean": float(rec[:, 3].mean()), "seeds_converged_mean": float(rec[:, 4].mean()),
-                 "align_iters_mean": float(rec[:, 5].mean()), "pose_err_rot_max": float(rec[:, 6].max()),
-                 "pose_err_trans_max": float(rec[:, 7].max())}
+    perr = np.array([synth.pose_error(stats_last["T_cur_w"][b], gt[b]) for b in range(wl.B)])
+    rec = sharding.gather_records(sharding.make_records(seq_ids, stats_last, perr), world, "cuda")
+    seq_stats = sharding.summarize(rec)
+    seq_stats["record_bytes"] = sharding.RECORD_BYTES
 
     out = None
     if rank == 0:
@@ -435,21 +467,28 @@ def run_b200(args, rank, world, local_rank):
                        "sequences_total": total, "sequences_per_gpu": per, "frame_pool": list(POOL_INDICES),
                        "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (per * cfg["w"] * cfg["h"] / 1e6)},
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d_bytes * world),
-                    "d2h_bytes_per_step": int(wl.d2h_bytes * world), "ms_per_step": round(e2e_s / K * 1e3, 4)},
+                    "d2h_bytes_per_step": int(wl.d2h_bytes * world), "ms_per_step": round(e2e_s / K * 1e3, 4),
+                    "h2d_GBps_per_gpu": round(wl.h2d_bytes / (e2e_s / K) / 1e9, 2), "pcie_h2d_GBps_measured": round(pcie, 2),
+                    "note": "host-buffer path is PCIe-bound: the frame upload (307,200 B/frame) is chunked and overlapped with compute"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(K, 1)),
-            "clocks": clocks, "roofline": roofline, "stages": stages, "sequence_stats": seq_stats,
+            "clocks": clocks, "roofline": roofline, "roofline_pyramid": roofline_pyr, "stages": stages, "sequence_stats": seq_stats,
             "setup_s": round(t_setup, 1),
         }
     return out, ctx, wl
 
 
-def latency_c2(ctx, capi, n_frames=60):
-    """Single-stream C2: one sequence, per-frame latency through the C ABI with host buffers (p50) and resident."""
-    cfg = synth.CONFIGS[CFG_NAME]
-    wl = GpuWorkload(ctx, capi, cfg, [4096])
+LATENCY_DESC = {"C2": "C2: one 640x480 sequence, 4-level pyramid, 120 features, 768 seeds",
+                "C3": "C3: one 752x480 sequence (EuRoC-shaped), 5-level pyramid, 300 features, 2,000 seeds",
+                "C4": "C4: one 1920x1080 sequence (phone-shaped), 5-level pyramid, 1,000 features, 10,000 seeds"}
+
+
+def latency_single(ctx, capi, name, n_frames=60):
+    """Single-stream: one sequence, per-frame latency through the C ABI with host buffers (p50) and resident."""
+    cfg = synth.CONFIGS[name]
+    wl = GpuWorkload(ctx, capi, cfg, [4096], cfg_name=name)
     order = ping_pong(len(POOL_INDICES), n_frames + 30)
     res = {}
-    for name, mem in (("host_buffers", capi.MEM_HOST), ("resident", capi.MEM_DEVICE)):
+    for mode, mem in (("host_buffers", capi.MEM_HOST), ("resident", capi.MEM_DEVICE)):
         wl.reset()
         for k in range(10):
             wl.step(order, k, mem)
@@ -461,7 +500,7 @@ def latency_c2(ctx, capi, n_frames=60):
             ctx.sync()
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts) * 1e3
-        res[name] = {"p50_ms": round(float(np.median(ts)), 4), "p95_ms": round(float(np.percentile(ts, 95)), 4),
+        res[mode] = {"p50_ms": round(float(np.median(ts)), 4), "p95_ms": round(float(np.percentile(ts, 95)), 4),
                      "frames_per_s": round(1e3 / float(np.median(ts)), 1)}
     wl.trk.enable_profiling(True)
     acc = {}
@@ -470,8 +509,11 @@ def latency_c2(ctx, capi, n_frames=60):
         for n, v in wl.trk.stage_ms().items():
             acc[n] = acc.get(n, 0.0) + v / 5
     res["stages_ms_resident"] = {k: round(v, 4) for k, v in acc.items()}
-    res["config"] = "C2: one 640x480 sequence, 4-level pyramid, 120 features, 768 seeds"
-    wl.trk.close()
+    res["config"] = LATENCY_DESC[name]
+    st = np.zeros(1, capi.step_stats_dt)
+    ctx.dev_download(st, wl.stats_dev)
+    res["tracked"] = int(st["n_tracked"][0]); res["matched"] = int(st["n_matched"][0]); res["seeds_updated"] = int(st["n_seeds_updated"][0])
+    wl.close()
     return res
 
 
@@ -495,10 +537,10 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "C5: independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each); "
                                        "step = 1 frame of every sequence of the sample" % (cfg["n_features"], cfg["n_seeds"]),
-                           "sequences_total": args.seqs, "sample_sequences": n},
+                           "sequences_total": args.seqs, "sample_sequences": n, "frames_per_sequence_per_step": r["inner"]},
                 "cpu_baseline": {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
-                                 "sample": "%d sequences x %d steps (+%d warm-up), one frame per sequence per step, %d host threads"
-                                           % (n, args.steps, args.warmup, threads)},
+                                 "sample": "%d sequences x %d steps x %d frames (+%d warm-up steps), %d host threads, %.1f s wall"
+                                           % (n, args.steps, r["inner"], args.warmup, threads, r["seconds"])},
                 "e2e": {"value": round(r["fps"], 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "tracked_mean": r["tracked"]}
         print(json.dumps(line))
@@ -508,15 +550,19 @@ def main():
     if rank == 0:
         from android_svo_b200 import capi
         if not args.no_latency:
-            try:
-                out["latency"] = latency_c2(ctx, capi)
-            except Exception as e:   # pragma: no cover
-                out["latency"] = {"error": str(e)}
+            wl.close()
+            out["latency"] = {}
+            for name in ("C2", "C3", "C4"):
+                try:
+                    out["latency"][name] = latency_single(ctx, capi, name)
+                except Exception as e:   # pragma: no cover
+                    out["latency"][name] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_seqs or max(8, 4 * threads)
             r = cpu_arm(cfg, n, 3, 1, threads)
             out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
-                                   "sample": "%d sequences x 3 steps (+1 warm-up), %d host threads, %.1f s" % (n, threads, r["seconds"])}
+                                   "sample": "%d sequences x 3 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
+                                             % (n, r["inner"], threads, r["seconds"])}
         print(json.dumps(out))
     if world > 1:
         import torch.distributed as dist

@@ -242,7 +242,7 @@ int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n
  * (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), restricted to the hot-path operators:
  *   pyramid(cur) -> SparseImgAlign::run(last, cur) -> Matcher::findMatchDirect for every map point of
  *   the keyframe -> DepthFilter::updateSeeds(cur) for the keyframe's seeds,
- * for a batch of independent sequences, 12 kernel launches on one stream, no host round trip.
+ * for a batch of independent sequences, 11 kernel launches on one stream, no host round trip.
  * Finished seeds (converged / NaN) are re-initialised when `reseed` is set, which keeps the
  * per-frame workload stationary for benchmarking (0 = leave them, the caller mutates its list). */
 typedef struct svob200_tracker svob200_tracker;
@@ -273,11 +273,12 @@ int  svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int strid
                           const double* last_px, svob200_step_stats* stats, double* px_refined, int* match_ok, int mem);
 int  svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out /*host*/);
 int  svob200_tracker_launches_per_step(void);
-/* optional CUDA-event timing of the stages of a step: ms[7] = {frame copy/bind + pyramid + per-step
- * input copy, features_prepare + init pose, sparse_align, compose + reproject_prepare, match_direct,
- * seeds_update, stats} for the most recent step */
+/* optional CUDA-event timing of the most recent step, one duration per stage (events recorded on the
+ * launching stream between the kernels): stage names from svob200_tracker_stage_name(i), i < num_stages */
 int  svob200_tracker_enable_profiling(svob200_tracker* t, int on);
-int  svob200_tracker_stage_ms(svob200_tracker* t, float* ms);
+int  svob200_tracker_num_stages(void);
+const char* svob200_tracker_stage_name(int i);
+int  svob200_tracker_stage_ms(svob200_tracker* t, float* ms, int cap);
 int  svob200_tracker_get_seed_obs(svob200_tracker* t, svob200_seed_obs* out /*host*/);
 
 /* ---------------------------------------------------------------- device-side helpers for the
