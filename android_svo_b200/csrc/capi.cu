@@ -401,8 +401,9 @@ int svob200_align_patches(svob200_ctx* ctx, int64_t frame_id, int level, int n, 
   if (int e = st.layout()) return e;
   st.upload();
   if (int e = st.push()) return e;
-  if (launch_align_patches(r->f, level, n, st.dev<int>(i_img), st.dev<uint8_t>(i_pwb), st.dev<uint8_t>(i_pat), dir ? st.dev<float>(i_dir) : nullptr,
-                           n_iter, st.dev<double>(i_px), st.dev<int>(i_cv), h_inv ? st.dev<double>(i_hi) : nullptr, ctx->stream, &ctx->launches))
+  if (ctx->d_scratch.ensure(lk_jobs_bytes(n)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "align_patches: scratch alloc failed");
+  if (launch_align_patches(ctx->d_table, r->slot, level, n, st.dev<int>(i_img), st.dev<uint8_t>(i_pwb), st.dev<uint8_t>(i_pat), dir ? st.dev<float>(i_dir) : nullptr,
+                           n_iter, st.dev<double>(i_px), st.dev<int>(i_cv), h_inv ? st.dev<double>(i_hi) : nullptr, ctx->d_scratch.p, ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "align_patches launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return st.download();
 }
@@ -432,8 +433,9 @@ int svob200_match_direct(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_c
   st.upload();
   if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
   if (int e = st.push()) return e;
-  if (launch_match_direct(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_d),
-                          st.dev<double>(i_p), *opts, st.dev<svob200_match_result>(i_r), ctx->stream, &ctx->launches))
+  if (ctx->d_scratch.ensure(lk_jobs_bytes(n)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "match_direct: scratch alloc failed");
+  if (launch_match_direct(ctx->d_table, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_d),
+                          st.dev<double>(i_p), *opts, st.dev<svob200_match_result>(i_r), nullptr, nullptr, ctx->d_scratch.p, ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "match_direct launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return st.download();
 }
@@ -454,8 +456,9 @@ int svob200_epipolar_match(svob200_ctx* ctx, int64_t cur_frame_id, const svob200
   st.upload();
   if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
   if (int e = st.push()) return e;
-  if (launch_epipolar(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_d), *opts,
-                      st.dev<svob200_epi_result>(i_r), ctx->stream, &ctx->launches))
+  if (ctx->d_scratch.ensure(epipolar_scratch_bytes(n)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "epipolar_match: scratch alloc failed");
+  if (launch_epipolar(ctx->d_table, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_d), *opts,
+                      st.dev<svob200_epi_result>(i_r), ctx->d_scratch.p, ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "epipolar launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return st.download();
 }
@@ -481,7 +484,7 @@ int svob200_seeds_update(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_c
   if (mem == SVOB200_MEM_HOST) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_f), n)) return e;
   if (int e = st.push()) return e;
   if (ctx->d_scratch.ensure(seeds_scratch_bytes(n)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "seeds_update: scratch alloc failed");
-  if (launch_seeds_update(ctx->d_table, nullptr, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_tr),
+  if (launch_seeds_update(ctx->d_table, cur->slot, to_cam(cam), n, st.dev<svob200_feature_ref>(i_f), st.dev<double>(i_tr),
                           st.dev<double>(i_tc), *opts, conv_thresh, st.dev<svob200_seed>(i_s), st.dev<svob200_seed_obs>(i_o),
                           ctx->d_scratch.p, n, 0, ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "seeds_update launch failed: %s", cudaGetErrorString(cudaGetLastError()));

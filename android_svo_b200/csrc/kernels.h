@@ -26,21 +26,22 @@ int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& 
                         void* d_scratch, cudaStream_t s, long long* launches);
 
 // matcher.cu
-int launch_align_patches(const DevFrame& f, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
-                         const float* d_dir, int n_iter, double* d_px, int* d_converged, double* d_h_inv,
+size_t lk_jobs_bytes(int n);                 // scratch of launch_align_patches / launch_match_direct
+int launch_align_patches(const DevFrame* d_frames, int slot, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
+                         const float* d_dir, int n_iter, double* d_px, int* d_converged, double* d_h_inv, void* d_scratch,
                          cudaStream_t s, long long* launches);
-int launch_match_direct(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
-                        const svob200_feature_ref* d_ftrs, const double* d_depth_ref, const double* d_px_in,
-                        svob200_matcher_opts opts, svob200_match_result* d_results, cudaStream_t s, long long* launches);
-int launch_epipolar(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
-                    const svob200_feature_ref* d_ftrs, const double* d_d, svob200_matcher_opts opts,
-                    svob200_epi_result* d_results, cudaStream_t s, long long* launches);
-int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
-                        const svob200_feature_ref* d_ftrs, const double* d_T_ref_w, const double* d_T_cur_w,
-                        svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs,
-                        void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches,
-                        cudaEvent_t* marks = nullptr /* 2 events: after the geometry kernel, after the search kernel */);
+// results: full records (API) or nullptr; px_out / ok_out: compact outputs (tracker) or nullptr; mark: optional event between the two kernels
+int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
+                        const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, svob200_match_result* d_results,
+                        double* d_px_out, int* d_ok_out, void* d_scratch, cudaStream_t s, long long* launches, cudaEvent_t* mark = nullptr);
+size_t epipolar_scratch_bytes(int n);
+int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs, const double* d_d,
+                    svob200_matcher_opts opts, svob200_epi_result* d_results, void* d_scratch, cudaStream_t s, long long* launches);
 size_t seeds_scratch_bytes(int n);
+int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
+                        const double* d_T_ref_w, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
+                        svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first,
+                        cudaStream_t s, long long* launches, cudaEvent_t* marks = nullptr /* 3 events between the four kernels */);
 int launch_update_seed(int n, const float* d_x, const float* d_tau2, svob200_seed* d_seeds, cudaStream_t s, long long* launches);
 int launch_compute_tau(int n, const double* d_T, const double* d_f, const double* d_z, double angle, double* d_out,
                        cudaStream_t s, long long* launches);
@@ -58,9 +59,7 @@ int launch_compose_poses(int batch, const svob200_align_result* d_res, const dou
 int launch_reproject_prepare(const DevCam& cam, int n, svob200_feature_ref* d_ftrs, const double* d_pt, const double* d_T_kf_w,
                              const double* d_T_cur_w, double* d_depth_ref, double* d_px_cur, cudaStream_t s, long long* launches);
 
-int launch_match_direct_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
-                                const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, double* d_px_out,
-                                int* d_ok_out, cudaStream_t s, long long* launches);
+
 
 // stand-alone helpers behind the C++ drop-in (vk::shiTomasiScore, warp::getWarpMatrixAffine, warp::warpAffine)
 int launch_shi_tomasi_points(const uint8_t* d_img, int pitch, int cols, int rows, int n, const int* d_uv, float* d_out,

@@ -91,11 +91,28 @@ __device__ inline bool warp_affine_10x10(const double* A, const uint8_t* img, in
   return true;
 }
 
-// ---------------------------------------------------------------- feature alignment
-struct AlignSmem {
-  float dx[64], dy[64];
-  float term[5][64];       // per-pixel terms of the sequential float sums, one row per chain
+// ---------------------------------------------------------------- feature alignment: one THREAD per problem
+// feature_alignment::align2D / align1D float paths (feature_alignment.cpp:35-282).
+//
+// The reference accumulates H and J*res pixel by pixel in float (`acc += term`); float addition is not
+// associative, so the sums cannot be tree-reduced without changing results.  With millions of
+// independent problems per step the natural mapping is therefore the reference's own loop, one thread
+// per problem: the 10x10 template lives in 25 registers, the per-pixel template gradient (an integer in
+// [-255,255] per axis) is staged once as packed int16 pairs in shared memory ([64][LK_T] words, conflict
+// free), the 9x9 search window is streamed row by row with three aligned word loads per row, and every
+// float operation happens in the reference's order.  Results are bit-identical to the CPU code.
+constexpr int LK_T = 128;
+
+// One refinement problem, written by the warp-cooperative producers with ONE coalesced 128-byte store.
+struct __align__(16) LkJob {
+  uint8_t pwb[100];        // 10x10 (patch with border), row-major
+  float u, v;              // start position at the scale of the search image (the reference's first statement casts to float)
+  float dirx, diry;        // align1D direction
+  int item;                // index of the seed / candidate / problem the result belongs to
+  int image;               // image inside the frame batch
+  int level_mode;          // search level | mode << 8 (0 align2D, 1 align1D); < 0: nothing to do
 };
+static_assert(sizeof(LkJob) == 128, "LkJob must be one 128-byte line");
 
 // Eigen Matrix3f::inverse(), cofactor path (Eigen/src/LU/InverseImpl.h)
 __device__ __forceinline__ void inv3f(const float* m, float* r)
@@ -112,113 +129,45 @@ __device__ __forceinline__ void inv3f(const float* m, float* r)
 #undef M_
 }
 
-// The reference accumulates its float sums pixel by pixel (`acc += term`, `acc -= term`); float
-// addition is not associative, so a tree reduction would change the result.  Lanes 0..n_chains-1
-// each replay ONE chain over the 64 staged terms with identical (non-divergent) code; a 64-long
-// dependent FADD chain costs ~64 x 4 cycles.  sign = +1 adds, -1 subtracts.
-__device__ __forceinline__ float chain64(const AlignSmem* S, int lane, int n_chains, float sign_mask_sub)
+// byte k of a register-resident byte array (k is a compile-time constant after unrolling)
+template <int NW> __device__ __forceinline__ int reg_byte(const uint32_t (&w)[NW], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu); }
+
+// nine consecutive pixels starting at p (any alignment) as floats; reads the three aligned words that hold them
+__device__ __forceinline__ void load_row9(const uint8_t* p, float (&o)[9])
 {
-  const float* v = S->term[lane < n_chains ? lane : 0];
-  float a = 0.f;
-  if (sign_mask_sub != 0.f) {
-#pragma unroll 16
-    for (int i = 0; i < 64; ++i) a -= v[i];
-  } else {
-#pragma unroll 16
-    for (int i = 0; i < 64; ++i) a += v[i];
-  }
-  return a;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(a & 3) * 8;
+  const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+  const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh), b8 = w2 >> sh;
+  o[0] = (float)(lo & 0xffu); o[1] = (float)((lo >> 8) & 0xffu); o[2] = (float)((lo >> 16) & 0xffu); o[3] = (float)(lo >> 24);
+  o[4] = (float)(hi & 0xffu); o[5] = (float)((hi >> 8) & 0xffu); o[6] = (float)((hi >> 16) & 0xffu); o[7] = (float)(hi >> 24);
+  o[8] = (float)(b8 & 0xffu);
 }
 
-// feature_alignment::align2D float path (feature_alignment.cpp:154-282); one full warp cooperates.
-// px is at the scale of `img`.  Returns converged (uniform across the warp).
-__device__ bool align2d_warp(const uint8_t* img, int pitch, int cols, int rows, const uint8_t* pwb, const uint8_t* ref_patch,
-                             int n_iter, double* px, AlignSmem* S, int lane)
+// align2D (feature_alignment.cpp:154-282).  w: template with border, rp: 8x8 reference patch, sd: this thread's
+// column of the shared gradient array.  u, v in/out at the scale of `img`.  Returns converged.
+__device__ bool lk_align2d(const uint8_t* img, int pitch, int cols, int rows, const uint32_t (&w)[25], const uint32_t (&rp)[16],
+                           int n_iter, float& u_io, float& v_io, uint32_t* sd)
 {
-  // derivative of the template: 2 pixels per lane; H += J*J^T terms (H22 = 64 exactly)
+  float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int idx = lane + 32 * k, y = idx >> 3, x = idx & 7;
-    const uint8_t* it = pwb + (y + 1) * 10 + 1 + x;
-    const float j0 = (float)(0.5 * ((int)it[1] - (int)it[-1]));
-    const float j1 = (float)(0.5 * ((int)it[10] - (int)it[-10]));
-    S->dx[idx] = j0; S->dy[idx] = j1;
-    S->term[0][idx] = j0 * j0;      // H00
-    S->term[1][idx] = j0 * j1;      // H01
-    S->term[2][idx] = j0;           // H02 (J[2] = 1)
-    S->term[3][idx] = j1 * j1;      // H11
-    S->term[4][idx] = j1;           // H12
+  for (int y = 0; y < 8; ++y) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const int k = (y + 1) * 10 + 1 + x;
+      const int dxi = reg_byte(w, k + 1) - reg_byte(w, k - 1), dyi = reg_byte(w, k + 10) - reg_byte(w, k - 10);
+      const float j0 = 0.5f * (float)dxi, j1 = 0.5f * (float)dyi;      // exact: 0.5 * int (the reference goes through double)
+      h00 += j0 * j0; h01 += j0 * j1; h02 += j0; h11 += j1 * j1; h12 += j1;
+      sd[(y * 8 + x) * LK_T] = ((uint32_t)dxi & 0xffffu) | ((uint32_t)dyi << 16);
+    }
   }
-  __syncwarp();
-  const float hv = chain64(S, lane, 5, 0.f);
-  const float h00 = __shfl_sync(0xffffffffu, hv, 0), h01 = __shfl_sync(0xffffffffu, hv, 1), h02 = __shfl_sync(0xffffffffu, hv, 2);
-  const float h11 = __shfl_sync(0xffffffffu, hv, 3), h12 = __shfl_sync(0xffffffffu, hv, 4);
   const float H[9] = {h00, h01, h02, h01, h11, h12, h02, h12, 64.0f};
   float Hinv[9];
   inv3f(H, Hinv);
-  float mean_diff = 0;
-  float u = (float)px[0], v = (float)px[1];
+  float mean_diff = 0.f;
+  float u = u_io, v = v_io;
   const float min_update_squared = (float)(0.5 * 0.5);
-  bool converged = false;
-  for (int iter = 0; iter < n_iter; ++iter) {
-    const int u_r = (int)floorf(u), v_r = (int)floorf(v);          // == floor((double)u) for a float argument
-    if (u_r < 4 || v_r < 4 || u_r >= cols - 4 || v_r >= rows - 4) break;
-    if (isnan(u) || isnan(v)) return false;
-    const float sx = u - u_r, sy = v - v_r;
-    const float wTL = (float)((1.0 - sx) * (1.0 - sy));
-    const float wTR = (float)(sx * (1.0 - sy));
-    const float wBL = (float)((1.0 - sx) * sy);
-    const float wBR = sx * sy;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = lane + 32 * k, y = idx >> 3, x = idx & 7;
-      const uint8_t* it = img + (size_t)(v_r + y - 4) * pitch + (u_r - 4 + x);
-      const float search_pixel = wTL * it[0] + wTR * it[1] + wBL * it[pitch] + wBR * it[pitch + 1];
-      const float res = search_pixel - ref_patch[idx] + mean_diff;
-      S->term[0][idx] = res * S->dx[idx];
-      S->term[1][idx] = res * S->dy[idx];
-      S->term[2][idx] = res;
-    }
-    __syncwarp();
-    const float jv = chain64(S, lane, 3, 1.f);
-    const float J0 = __shfl_sync(0xffffffffu, jv, 0), J1 = __shfl_sync(0xffffffffu, jv, 1), J2 = __shfl_sync(0xffffffffu, jv, 2);
-    // update = Hinv * Jres (Eigen lazy product: x0 + (x1 + x2))
-    const float up0 = Hinv[0] * J0 + (Hinv[1] * J1 + Hinv[2] * J2);
-    const float up1 = Hinv[3] * J0 + (Hinv[4] * J1 + Hinv[5] * J2);
-    const float up2 = Hinv[6] * J0 + (Hinv[7] * J1 + Hinv[8] * J2);
-    u += up0; v += up1; mean_diff += up2;
-    if (up0 * up0 + up1 * up1 < min_update_squared) { converged = true; break; }
-  }
-  px[0] = u; px[1] = v;
-  return converged;
-}
-
-// feature_alignment::align1D (feature_alignment.cpp:35-152); one full warp cooperates.
-__device__ bool align1d_warp(const uint8_t* img, int pitch, int cols, int rows, float dir0, float dir1, const uint8_t* pwb,
-                             const uint8_t* ref_patch, int n_iter, double* px, double* h_inv, AlignSmem* S, int lane)
-{
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int idx = lane + 32 * k, y = idx >> 3, x = idx & 7;
-    const uint8_t* it = pwb + (y + 1) * 10 + 1 + x;
-    const float j0 = (float)(0.5 * (double)(dir0 * (float)((int)it[1] - (int)it[-1]) + dir1 * (float)((int)it[10] - (int)it[-10])));
-    S->dx[idx] = j0;
-    S->term[0][idx] = j0 * j0;      // H00
-    S->term[1][idx] = j0;           // H01 = H10
-  }
-  __syncwarp();
-  const float hv = chain64(S, lane, 2, 0.f);
-  const float h00 = __shfl_sync(0xffffffffu, hv, 0), h01 = __shfl_sync(0xffffffffu, hv, 1), h11 = 64.0f;
-  *h_inv = 1.0 / h00 * 8 * 8;
-  const float det = h00 * h11 - h01 * h01;
-  const float invdet = 1.0f / det;
-  const float Hinv[4] = {h11 * invdet, -h01 * invdet, -h01 * invdet, h00 * invdet};
-  float mean_diff = 0;
-  float u = (float)px[0], v = (float)px[1];
-  const float min_update_squared = (float)(0.03 * 0.03);
-  float chi2 = 0;
-  float up0 = 0, up1 = 0;
   bool converged = false;
   for (int iter = 0; iter < n_iter; ++iter) {
     const int u_r = (int)floorf(u), v_r = (int)floorf(v);
@@ -229,20 +178,88 @@ __device__ bool align1d_warp(const uint8_t* img, int pitch, int cols, int rows, 
     const float wTR = (float)(sx * (1.0 - sy));
     const float wBL = (float)((1.0 - sx) * sy);
     const float wBR = sx * sy;
-    __syncwarp();
+    const uint8_t* base = img + (size_t)(v_r - 4) * pitch + (u_r - 4);
+    float J0 = 0.f, J1 = 0.f, J2 = 0.f;
+    float top[9], bot[9];
+    load_row9(base, top);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = lane + 32 * k, y = idx >> 3, x = idx & 7;
-      const uint8_t* it = img + (size_t)(v_r + y - 4) * pitch + (u_r - 4 + x);
-      const float search_pixel = wTL * it[0] + wTR * it[1] + wBL * it[pitch] + wBR * it[pitch + 1];
-      const float res = search_pixel - ref_patch[idx] + mean_diff;
-      S->term[0][idx] = res * S->dx[idx];
-      S->term[1][idx] = res;
-      S->term[2][idx] = -(res * res);   // chain subtracts: 0 - (-(r*r)) ... == 0 + r*r exactly
+    for (int y = 0; y < 8; ++y) {
+      load_row9(base + (size_t)(y + 1) * pitch, bot);
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float search_pixel = wTL * top[x] + wTR * top[x + 1] + wBL * bot[x] + wBR * bot[x + 1];
+        const float res = search_pixel - (float)reg_byte(rp, y * 8 + x) + mean_diff;
+        const uint32_t d = sd[(y * 8 + x) * LK_T];
+        const float j0 = 0.5f * (float)(short)(d & 0xffffu), j1 = 0.5f * (float)((int)d >> 16);
+        J0 -= res * j0; J1 -= res * j1; J2 -= res;
+      }
+#pragma unroll
+      for (int x = 0; x < 9; ++x) top[x] = bot[x];
     }
-    __syncwarp();
-    const float jv = chain64(S, lane, 3, 1.f);
-    const float J0 = __shfl_sync(0xffffffffu, jv, 0), J1 = __shfl_sync(0xffffffffu, jv, 1), new_chi2 = __shfl_sync(0xffffffffu, jv, 2);
+    // update = Hinv * Jres (Eigen lazy product: x0 + (x1 + x2))
+    const float up0 = Hinv[0] * J0 + (Hinv[1] * J1 + Hinv[2] * J2);
+    const float up1 = Hinv[3] * J0 + (Hinv[4] * J1 + Hinv[5] * J2);
+    const float up2 = Hinv[6] * J0 + (Hinv[7] * J1 + Hinv[8] * J2);
+    u += up0; v += up1; mean_diff += up2;
+    if (up0 * up0 + up1 * up1 < min_update_squared) { converged = true; break; }
+  }
+  u_io = u; v_io = v;
+  return converged;
+}
+
+// align1D (feature_alignment.cpp:35-152): motion restricted to `dir`; the projected template gradient is a
+// general float, staged as float bits.
+__device__ bool lk_align1d(const uint8_t* img, int pitch, int cols, int rows, float dir0, float dir1, const uint32_t (&w)[25],
+                           const uint32_t (&rp)[16], int n_iter, float& u_io, float& v_io, double& h_inv, uint32_t* sd)
+{
+  float h00 = 0.f, h01 = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const int k = (y + 1) * 10 + 1 + x;
+      const int dxi = reg_byte(w, k + 1) - reg_byte(w, k - 1), dyi = reg_byte(w, k + 10) - reg_byte(w, k - 10);
+      const float j0 = (float)(0.5 * (double)(dir0 * (float)dxi + dir1 * (float)dyi));
+      h00 += j0 * j0; h01 += j0;
+      sd[(y * 8 + x) * LK_T] = __float_as_uint(j0);
+    }
+  }
+  const float h11 = 64.0f;
+  h_inv = 1.0 / h00 * 8 * 8;
+  const float det = h00 * h11 - h01 * h01;
+  const float invdet = 1.0f / det;
+  const float Hinv[4] = {h11 * invdet, -h01 * invdet, -h01 * invdet, h00 * invdet};
+  float mean_diff = 0.f;
+  float u = u_io, v = v_io;
+  const float min_update_squared = (float)(0.03 * 0.03);
+  float chi2 = 0.f, up0 = 0.f, up1 = 0.f;
+  bool converged = false;
+  for (int iter = 0; iter < n_iter; ++iter) {
+    const int u_r = (int)floorf(u), v_r = (int)floorf(v);
+    if (u_r < 4 || v_r < 4 || u_r >= cols - 4 || v_r >= rows - 4) break;
+    if (isnan(u) || isnan(v)) return false;
+    const float sx = u - u_r, sy = v - v_r;
+    const float wTL = (float)((1.0 - sx) * (1.0 - sy));
+    const float wTR = (float)(sx * (1.0 - sy));
+    const float wBL = (float)((1.0 - sx) * sy);
+    const float wBR = sx * sy;
+    const uint8_t* base = img + (size_t)(v_r - 4) * pitch + (u_r - 4);
+    float J0 = 0.f, J1 = 0.f, new_chi2 = 0.f;
+    float top[9], bot[9];
+    load_row9(base, top);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      load_row9(base + (size_t)(y + 1) * pitch, bot);
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float search_pixel = wTL * top[x] + wTR * top[x + 1] + wBL * bot[x] + wBR * bot[x + 1];
+        const float res = search_pixel - (float)reg_byte(rp, y * 8 + x) + mean_diff;
+        const float j0 = __uint_as_float(sd[(y * 8 + x) * LK_T]);
+        J0 -= res * j0; J1 -= res; new_chi2 += res * res;
+      }
+#pragma unroll
+      for (int x = 0; x < 9; ++x) top[x] = bot[x];
+    }
     if (iter > 0 && new_chi2 > chi2) { u -= up0; v -= up1; break; }   // sic (:122-123)
     chi2 = new_chi2;
     up0 = Hinv[0] * J0 + Hinv[1] * J1;
@@ -250,7 +267,7 @@ __device__ bool align1d_warp(const uint8_t* img, int pitch, int cols, int rows, 
     u += up0 * dir0; v += up0 * dir1; mean_diff += up1;
     if (up0 * up0 + up1 * up1 < min_update_squared) { converged = true; break; }
   }
-  px[0] = u; px[1] = v;
+  u_io = u; v_io = v;
   return converged;
 }
 
@@ -356,15 +373,15 @@ __device__ inline double compute_tau(const double* T_ref_cur, v3d f, double z, d
   return z_plus - z;
 }
 
-// ---------------------------------------------------------------- findEpipolarMatchDirect in three phases
-// Phase 1 (per-thread double geometry), phase 2 (warp-cooperative patch warp / ZMSSD walk / LK),
-// phase 3 (per-thread triangulation).  The depth filter runs them as three kernels — thread per
-// seed, warp per seed, thread per seed — so the FP64 pipe (64 lanes/SM) never executes the same
-// geometry redundantly across a CTA; the stand-alone epipolar query kernel runs them back to back
-// in one warp.
+// ---------------------------------------------------------------- findEpipolarMatchDirect in phases
+// Phase 1 (per-thread double geometry), phase 2 (warp-cooperative patch warp + ZMSSD walk), phase 3
+// (thread-per-problem LK refinement, shared with findMatchDirect), phase 4 (per-thread triangulation /
+// seed update).  Each phase is its own kernel so that every one of them runs with the mapping that suits
+// it and the FP64 pipe never executes the same geometry redundantly across a warp.
 constexpr int EPI_CHUNK = 256;           // epipolar samples staged per round
 constexpr int EPI_MAX_STEPS = 1023;      // max_epi_search_steps is clamped to this
 enum { EPI_MODE_NONE = 0, EPI_MODE_DIRECT = 1, EPI_MODE_WALK = 2 };
+enum { EPI_FOUND_NONE = 0, EPI_FOUND_REFINED = 1, EPI_FOUND_UV_ONLY = 2 };
 
 struct EpiGeom {
   double T_cur_ref[7];
@@ -379,15 +396,16 @@ struct EpiGeom {
 };
 
 struct EpiSearch {
-  int found;                            // 0 none, 1 px_cur refined by LK, 2 uv_best only (no subpixel refinement)
+  int found;                            // EPI_FOUND_*
   int zmssd_best, n_evals;
+  int px_cur_valid;                     // the reference wrote Matcher::px_cur_ (matcher.cpp:259, :327, :345)
   double px_cur[2], uv_best[2], h_inv;
 };
 
 struct EpiWarpSmem {
-  __align__(16) uint8_t pwb[100];
+  __align__(16) uint8_t pwb[112];       // 100 used
   __align__(16) uint8_t patch[64];
-  AlignSmem al;
+  double uv[2 * EPI_CHUNK];             // the reference's running sums uv += step (x, y interleaved)
   short2 pxi[EPI_CHUNK + 1];
 };
 
@@ -453,64 +471,92 @@ __device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref
   g->mode = EPI_MODE_WALK;
 }
 
-// matcher.cpp:251-340: warp the patch, walk the epipolar segment, refine.  One full warp cooperates.
+// one coalesced 128-byte store of a refinement job by a full warp (pwb words come from shared memory)
+__device__ __forceinline__ void emit_lk_job(LkJob* dst, const uint8_t* s_pwb, float u, float v, float dirx, float diry, int item,
+                                            int image, int level_mode, int lane)
+{
+  uint32_t word;
+  if (lane < 25) word = reinterpret_cast<const uint32_t*>(s_pwb)[lane];
+  else if (lane == 25) word = __float_as_uint(u);
+  else if (lane == 26) word = __float_as_uint(v);
+  else if (lane == 27) word = __float_as_uint(dirx);
+  else if (lane == 28) word = __float_as_uint(diry);
+  else if (lane == 29) word = (uint32_t)item;
+  else if (lane == 30) word = (uint32_t)image;
+  else word = (uint32_t)level_mode;
+  reinterpret_cast<uint32_t*>(dst)[lane] = word;
+}
+
+// affine warp of the 10x10 reference patch (matcher.cpp:83-116) into shared memory by a full warp
+__device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, int rc, int rr, float a00, float a01, float a10, float a11,
+                                                 float pr0, float pr1, int L, uint8_t* s_pwb, int lane)
+{
+  const float sc = (float)(1 << L);
+  for (int i = lane; i < 100; i += 32) {
+    const int y = i / 10, x = i - y * 10;
+    float p0 = (float)(x - 5), p1 = (float)(y - 5);
+    p0 *= sc; p1 *= sc;
+    const float qx = (a00 * p0 + a01 * p1) + pr0;
+    const float qy = (a10 * p0 + a11 * p1) + pr1;
+    uint8_t v = 0;
+    if (!(qx < 0 || qy < 0 || qx >= rc - 1 || qy >= rr - 1)) v = (uint8_t)interpolate_8u(rimg, rp, qx, qy);
+    s_pwb[i] = v;
+  }
+}
+
+// matcher.cpp:251-340 minus the LK refinement: warp the patch, walk the epipolar segment, and hand the
+// refinement to the thread-per-problem LK kernel as a job.  One full warp cooperates.
 __device__ void epi_search_warp(const DevFrame& ref, int ref_image, const DevFrame& cur, int cur_image, const DevCam& cam,
                                 const svob200_feature_ref& f, const EpiGeom& g, const svob200_matcher_opts& o, EpiWarpSmem* S,
-                                int lane, bool always_warp, EpiSearch* out)
+                                int lane, bool always_warp, int item, LkJob* jobs, int* job_count, EpiSearch* out)
 {
-  out->found = 0; out->zmssd_best = 2000 * 64; out->n_evals = 0; out->px_cur[0] = out->px_cur[1] = 0;
+  out->found = EPI_FOUND_NONE; out->zmssd_best = 2000 * 64; out->n_evals = 0; out->px_cur_valid = 0; out->px_cur[0] = out->px_cur[1] = 0;
   out->uv_best[0] = out->uv_best[1] = 0; out->h_inv = 0;
   if (g.reject) return;
   if (g.mode == EPI_MODE_NONE && !always_warp) return;
   const int L = g.L;
   if (g.warp_ok) {
     const uint8_t* rimg = ref.lvl[f.level] + (size_t)ref_image * ref.img_stride[f.level];
-    const int rp = ref.pitch[f.level], rc = ref.w[f.level], rr = ref.h[f.level];
-    for (int i = lane; i < 100; i += 32) {
-      const int y = i / 10, x = i - y * 10;
-      float p0 = (float)(x - 5), p1 = (float)(y - 5);
-      p0 *= (float)(1 << L); p1 *= (float)(1 << L);
-      const float qx = (g.a00 * p0 + g.a01 * p1) + g.pr0;
-      const float qy = (g.a10 * p0 + g.a11 * p1) + g.pr1;
-      uint8_t v = 0;
-      if (!(qx < 0 || qy < 0 || qx >= rc - 1 || qy >= rr - 1)) v = (uint8_t)interpolate_8u(rimg, rp, qx, qy);
-      S->pwb[i] = v;
-    }
+    warp_patch_10x10(rimg, ref.pitch[f.level], ref.w[f.level], ref.h[f.level], g.a00, g.a01, g.a10, g.a11, g.pr0, g.pr1, L, S->pwb, lane);
   }
   __syncwarp();
   for (int k = lane; k < 64; k += 32) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
   __syncwarp();
   if (g.mode == EPI_MODE_NONE) return;
   const uint8_t* cimg = cur.lvl[L] + (size_t)cur_image * cur.img_stride[L];
-  const int cpitch = cur.pitch[L], ccols = cur.w[L], crows = cur.h[L];
+  const int cpitch = cur.pitch[L];
   double px0, px1;
   if (g.mode == EPI_MODE_DIRECT) {
     px0 = g.px_mid[0]; px1 = g.px_mid[1];
-    out->px_cur[0] = px0; out->px_cur[1] = px1;
   } else {
     RefPatchRegs rpatch;
     load_ref_patch(S->patch, rpatch);
-    unsigned long long best = ((unsigned long long)(2000 * 64) << 32);   // PatchScore::threshold(), strict <
+    unsigned long long best = ((unsigned long long)(2000 * 64) << 32) | 0xffffffffu;   // PatchScore::threshold(), strict <
+    double best_u = 0.0, best_v = 0.0;
     int evals = 0;
-    // the reference's running sums uv += step: x chain on lane 0, y chain on lane 1
+    // the reference's running sums uv += step: x chain on lane 0, y chain on lane 1 (two independent DADD chains)
     double uv = lane == 0 ? g.Bx0 : g.By0;
-    const double st = lane == 0 ? g.stepx : g.stepy, fxy = lane == 0 ? cam.fx : cam.fy, cxy = lane == 0 ? cam.cx : cam.cy;
+    const double st = lane == 0 ? g.stepx : g.stepy;
     const double inv_scale = 1.0 / (double)(1 << L);                     // exact: dividing by 2^L == multiplying by 2^-L
-    short lastv = 0;                                                     // last_checked_pxi(0,0)
-    short* dst = reinterpret_cast<short*>(S->pxi) + lane;
+    short2 last = make_short2(0, 0);                                     // last_checked_pxi(0,0)
     for (int base = 0; base < g.n; base += EPI_CHUNK) {
       const int m = min(EPI_CHUNK, g.n - base);
       if (lane < 2) {
-        dst[0] = lastv;
-        for (int i = 0; i < m; ++i, uv += st) {
-          const double p = fxy * uv + cxy;
-          const double v = p * inv_scale + 0.5;
-          const int iv = (v == v) ? (v >= 32767.0 ? 32767 : (v <= -32768.0 ? -32768 : (int)v)) : -32768;
-          lastv = (short)iv;
-          dst[2 * (i + 1)] = lastv;
-        }
+        double* dst = S->uv + lane;
+        for (int i = 0; i < m; ++i, uv += st) dst[2 * i] = uv;
+      }
+      if (lane == 0) S->pxi[0] = last;
+      __syncwarp();
+      // pixel of every sample, in parallel: Vector2i(px/(1<<L) + 0.5) with the x86 truncating conversion
+      for (int i = lane; i < m; i += 32) {
+        const double ux = S->uv[2 * i], uy = S->uv[2 * i + 1];
+        const double vx = (cam.fx * ux + cam.cx) * inv_scale + 0.5, vy = (cam.fy * uy + cam.cy) * inv_scale + 0.5;
+        const int ix = (vx == vx) ? (vx >= 32767.0 ? 32767 : (vx <= -32768.0 ? -32768 : (int)vx)) : -32768;
+        const int iy = (vy == vy) ? (vy >= 32767.0 ? 32767 : (vy <= -32768.0 ? -32768 : (int)vy)) : -32768;
+        S->pxi[i + 1] = make_short2((short)ix, (short)iy);
       }
       __syncwarp();
+      last = S->pxi[m];
       for (int i = lane; i < m; i += 32) {
         const short2 c = S->pxi[i + 1], prev = S->pxi[i];
         if (c.x == prev.x && c.y == prev.y) continue;
@@ -518,87 +564,133 @@ __device__ void epi_search_warp(const DevFrame& ref, int ref_image, const DevFra
         const int z = zmssd_8x8(rpatch, cimg + (size_t)(c.y - 4) * cpitch + (c.x - 4), cpitch);
         ++evals;
         const unsigned long long key = ((unsigned long long)(unsigned)z << 32) | (unsigned)(base + i);
-        if (key < best) best = key;
+        if (key < best) { best = key; best_u = S->uv[2 * i]; best_v = S->uv[2 * i + 1]; }
       }
       __syncwarp();
     }
+    unsigned long long gbest = best;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
-      if (other < best) best = other;
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, gbest, off);
+      if (other < gbest) gbest = other;
       evals += __shfl_xor_sync(0xffffffffu, evals, off);
     }
     out->n_evals = evals;
-    const int zbest = (int)(best >> 32);
+    const int zbest = (int)(gbest >> 32);
     out->zmssd_best = zbest;
     if (!(zbest < 2000 * 64)) return;
-    // uv_best: replay the chain up to the winning step
-    const int ibest = (int)(best & 0xffffffffu);
-    double ub = lane == 0 ? g.Bx0 : g.By0;
-    if (lane < 2) for (int i = 0; i < ibest; ++i) ub += st;
-    const double ubx = __shfl_sync(0xffffffffu, ub, 0), uby = __shfl_sync(0xffffffffu, ub, 1);
+    // uv_best lives on the lane that evaluated the winning step (keys are unique: they contain the step index)
+    const unsigned owner = __ffs(__ballot_sync(0xffffffffu, best == gbest)) - 1;
+    const double ubx = __shfl_sync(0xffffffffu, best_u, owner), uby = __shfl_sync(0xffffffffu, best_v, owner);
     world2cam_uv(cam, ubx, uby, px0, px1);
-    out->px_cur[0] = px0; out->px_cur[1] = px1;
     out->uv_best[0] = ubx; out->uv_best[1] = uby;
-    if (!o.subpix_refinement) { out->found = 2; return; }
+    if (!o.subpix_refinement) { out->px_cur[0] = px0; out->px_cur[1] = px1; out->px_cur_valid = 1; out->found = EPI_FOUND_UV_ONLY; return; }
   }
-  double pxs[2] = {px0 / (1 << L), px1 / (1 << L)};
-  double h_inv = 0;
-  bool res;
-  if (o.align_1d) res = align1d_warp(cimg, cpitch, ccols, crows, g.dirx, g.diry, S->pwb, S->patch, o.align_max_iter, pxs, &h_inv, &S->al, lane);
-  else res = align2d_warp(cimg, cpitch, ccols, crows, S->pwb, S->patch, o.align_max_iter, pxs, &S->al, lane);
-  out->h_inv = h_inv;
-  if (res) { out->px_cur[0] = pxs[0] * (1 << L); out->px_cur[1] = pxs[1] * (1 << L); out->found = 1; }
+  out->px_cur[0] = px0; out->px_cur[1] = px1; out->px_cur_valid = 1;
+  // hand over to the LK kernel: px_scaled = px_cur / (1 << L) (double), cast to float at the start of align1D/2D
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(job_count, 1);
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), g.dirx, g.diry, item, cur_image,
+              L | ((o.align_1d ? 1 : 0) << 8), lane);
 }
 
 // matcher.cpp:269-276 / :341-351: triangulate from the matched pixel (per thread)
 __device__ inline bool epi_finish(const DevCam& cam, const svob200_feature_ref& f, const double* T_cur_ref, const EpiSearch& s, double* depth)
 {
   v3d fc;
-  if (s.found == 1) fc = cam2world(cam, s.px_cur[0], s.px_cur[1]);
-  else if (s.found == 2) fc = normalized3({s.uv_best[0], s.uv_best[1], 1.0});
+  if (s.found == EPI_FOUND_REFINED) fc = cam2world(cam, s.px_cur[0], s.px_cur[1]);
+  else if (s.found == EPI_FOUND_UV_ONLY) fc = normalized3({s.uv_best[0], s.uv_best[1], 1.0});
   else return false;
   return depth_from_triangulation(T_cur_ref, {f.f[0], f.f[1], f.f[2]}, fc, depth);
 }
 
-// stand-alone epipolar query: one warp per query, the three phases back to back
-struct EpiQuerySmem { EpiWarpSmem w; EpiGeom g; };
+// ---------------------------------------------------------------- the LK kernel: thread per job
+// Where the result of a job goes (the consumers read plain arrays; no extra "finish" pass for the LK itself).
+enum { LK_SINK_EPI = 0, LK_SINK_MATCH_COMPACT = 1, LK_SINK_MATCH_RESULT = 2, LK_SINK_ARRAYS = 3 };
+struct LkSink {
+  int kind;
+  EpiSearch* search;              // LK_SINK_EPI: found / px_cur / h_inv of seed `item`
+  double* px_out; int* ok_out;    // LK_SINK_MATCH_COMPACT (level-0 pixels) and LK_SINK_ARRAYS (pixels at the image's scale)
+  svob200_match_result* mres;     // LK_SINK_MATCH_RESULT
+  double* h_inv_out;              // LK_SINK_ARRAYS (may be null)
+  const uint8_t* patches;         // LK_SINK_ARRAYS: caller-provided 8x8 reference patches, 64 B per job (else the centre of pwb)
+};
 
-__global__ void __launch_bounds__(128) epipolar_kernel(const DevFrame* frames, const int* ref_slot, int cur_slot, DevCam cam,
-                                                       int n, const svob200_feature_ref* ftrs, const double* d,
-                                                       svob200_matcher_opts o, svob200_epi_result* results)
+__global__ void __launch_bounds__(LK_T) lk_refine_kernel(const DevFrame* frames, int cur_slot, const LkJob* jobs, const int* job_count,
+                                                         int n_max, int n_iter, LkSink sink)
 {
-  __shared__ EpiQuerySmem SM[4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
-  if (i >= n) return;
-  EpiQuerySmem* S = &SM[warp];
-  const svob200_feature_ref f = ftrs[i];
-  for (int k = lane; k < 100; k += 32) S->w.pwb[k] = 0;
-  if (lane == 0) epi_geometry(cam, f, f.T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &S->g);
-  __syncwarp();
-  const EpiGeom g = S->g;
-  EpiSearch sr;
-  epi_search_warp(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, g, o, &S->w, lane, true, &sr);
-  double depth = 0;
-  const bool ok = epi_finish(cam, f, g.T_cur_ref, sr, &depth);
-  __syncwarp();
-  svob200_epi_result* R = &results[i];
-  if (lane == 0) {
-    R->success = ok ? 1 : 0; R->search_level = g.L; R->reject = g.reject; R->zmssd_best = sr.zmssd_best;
-    R->n_evals = sr.n_evals; R->n_steps = g.n_steps_report; R->depth = ok ? depth : 0.0;
-    R->px_cur[0] = sr.px_cur[0]; R->px_cur[1] = sr.px_cur[1];
-    R->epi_length = g.epi_length; R->h_inv = sr.h_inv;
-    R->epi_dir[0] = g.ex; R->epi_dir[1] = g.ey;
-    R->px_cur_valid = (!g.reject && (g.mode == EPI_MODE_DIRECT || (g.mode == EPI_MODE_WALK && sr.zmssd_best < 2000 * 64))) ? 1 : 0;
-    for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g.A[k];
+  __shared__ uint32_t s_d[64 * LK_T];
+  const int j = blockIdx.x * LK_T + threadIdx.x;
+  int n = n_max;
+  if (job_count) { const int c = *job_count; n = c < n_max ? c : n_max; }
+  if (j >= n) return;
+  const uint4* q = reinterpret_cast<const uint4*>(&jobs[j]);
+  uint32_t w[25];
+  const uint4 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4], a5 = q[5], a6 = q[6], a7 = q[7];
+  w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+  w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
+  w[16] = a4.x; w[17] = a4.y; w[18] = a4.z; w[19] = a4.w; w[20] = a5.x; w[21] = a5.y; w[22] = a5.z; w[23] = a5.w;
+  w[24] = a6.x;
+  float u = __uint_as_float(a6.y), v = __uint_as_float(a6.z);
+  const float dirx = __uint_as_float(a6.w), diry = __uint_as_float(a7.x);
+  const int item = (int)a7.y, image = (int)a7.z, level_mode = (int)a7.w;
+  if (level_mode < 0) return;
+  const int L = level_mode & 0xff, mode1d = (level_mode >> 8) & 1;
+  uint32_t rp[16];
+  if (sink.kind == LK_SINK_ARRAYS && sink.patches) {
+    const uint4* pq = reinterpret_cast<const uint4*>(sink.patches + 64 * (size_t)j);
+    const uint4 b0 = pq[0], b1 = pq[1], b2 = pq[2], b3 = pq[3];
+    rp[0] = b0.x; rp[1] = b0.y; rp[2] = b0.z; rp[3] = b0.w; rp[4] = b1.x; rp[5] = b1.y; rp[6] = b1.z; rp[7] = b1.w;
+    rp[8] = b2.x; rp[9] = b2.y; rp[10] = b2.z; rp[11] = b2.w; rp[12] = b3.x; rp[13] = b3.y; rp[14] = b3.z; rp[15] = b3.w;
+  } else {
+    // Matcher::createPatchFromPatchWithBorder (matcher.cpp:138-147): the 8x8 centre of the 10x10 template
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = (y + 1) * 10 + 1 + 4 * h;
+        rp[2 * y + h] = (uint32_t)reg_byte(w, k) | ((uint32_t)reg_byte(w, k + 1) << 8) | ((uint32_t)reg_byte(w, k + 2) << 16) | ((uint32_t)reg_byte(w, k + 3) << 24);
+      }
+    }
   }
-  for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = g.reject ? 0 : S->w.pwb[k];
-  for (int k = lane; k < 64; k += 32) R->patch[k] = g.reject ? 0 : S->w.patch[k];
+  const DevFrame& cur = frames[cur_slot];
+  const uint8_t* img = cur.lvl[L] + (size_t)image * cur.img_stride[L];
+  const int pitch = cur.pitch[L], cols = cur.w[L], rows = cur.h[L];
+  uint32_t* sd = s_d + threadIdx.x;
+  double h_inv = 0.0;
+  bool ok;
+  if (mode1d) ok = lk_align1d(img, pitch, cols, rows, dirx, diry, w, rp, n_iter, u, v, h_inv, sd);
+  else ok = lk_align2d(img, pitch, cols, rows, w, rp, n_iter, u, v, sd);
+  const double s = (double)(1 << L);
+  if (sink.kind == LK_SINK_EPI) {
+    EpiSearch* e = &sink.search[item];
+    e->h_inv = h_inv;
+    if (ok) { e->px_cur[0] = (double)u * s; e->px_cur[1] = (double)v * s; e->found = EPI_FOUND_REFINED; }
+  } else if (sink.kind == LK_SINK_MATCH_COMPACT) {
+    sink.px_out[2 * item] = (double)u * s; sink.px_out[2 * item + 1] = (double)v * s;      // written whether or not LK converged (matcher.cpp:200)
+    sink.ok_out[item] = ok ? 1 : 0;
+  } else if (sink.kind == LK_SINK_MATCH_RESULT) {
+    svob200_match_result* R = &sink.mres[item];
+    R->px_cur[0] = (double)u * s; R->px_cur[1] = (double)v * s; R->success = ok ? 1 : 0; R->h_inv = h_inv;
+  } else {
+    sink.px_out[2 * item] = (double)u; sink.px_out[2 * item + 1] = (double)v;
+    sink.ok_out[item] = ok ? 1 : 0;
+    if (sink.h_inv_out) sink.h_inv_out[item] = h_inv;
+  }
+}
+
+int launch_lk_refine(const DevFrame* d_frames, int cur_slot, const LkJob* d_jobs, const int* d_count, int n_max, int n_iter, const LkSink& sink,
+                     cudaStream_t s, long long* launches)
+{
+  if (n_max <= 0) return 0;
+  lk_refine_kernel<<<(n_max + LK_T - 1) / LK_T, LK_T, 0, s>>>(d_frames, cur_slot, d_jobs, d_count, n_max, n_iter, sink);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ---------------------------------------------------------------- depth filter: DepthFilter::updateSeeds loop body
-// (depth_filter.cpp:250-340) as three kernels over all seeds
+// (depth_filter.cpp:250-340) as four kernels over all seeds: geometry (thread), search (warp), LK (thread), update (thread)
 struct SeedPre {
   int status;                  // 0 = run the matcher; else the final status (BEHIND / NOT_IN_FRAME)
   float z_inv_min;
@@ -608,9 +700,10 @@ struct SeedPre {
 // phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry
 __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* T_ref_w_all,
                                                          const double* T_cur_w_all, svob200_matcher_opts o, const svob200_seed* seeds,
-                                                         SeedPre* pre, EpiGeom* geom)
+                                                         SeedPre* pre, EpiGeom* geom, int* job_count)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *job_count = 0;                                        // consumed by the search kernel that follows on the stream
   if (i >= n) return;
   const svob200_feature_ref f = ftrs[i];
   const svob200_seed s = seeds[i];
@@ -643,28 +736,54 @@ __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, cons
   pre[i] = p;
 }
 
-// phase 2: warp per seed — patch warp, ZMSSD walk, LK refinement
-__global__ void __launch_bounds__(128) seeds_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n,
-                                                           const svob200_feature_ref* ftrs, svob200_matcher_opts o,
-                                                           const SeedPre* pre, const EpiGeom* geom, EpiSearch* search)
+// geometry of stand-alone epipolar queries (svob200_epipolar_match): T_cur_ref and the depth range come from the caller
+__global__ void __launch_bounds__(128) epi_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* d,
+                                                       svob200_matcher_opts o, EpiGeom* geom, int* job_count)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *job_count = 0;
+  if (i >= n) return;
+  const svob200_feature_ref f = ftrs[i];
+  epi_geometry(cam, f, f.T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &geom[i]);
+}
+
+// phase 2: warp per seed / query — patch warp, ZMSSD walk, LK job.  pre == nullptr: stand-alone queries, which
+// always warp the patch and return it in api_results.
+__global__ void __launch_bounds__(128) epi_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n,
+                                                         const svob200_feature_ref* ftrs, svob200_matcher_opts o,
+                                                         const SeedPre* pre, const EpiGeom* geom, EpiSearch* search,
+                                                         LkJob* jobs, int* job_count, svob200_epi_result* api_results)
 {
   __shared__ EpiWarpSmem SM[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 4 + warp;
   if (i >= n) return;
-  if (pre[i].status != 0) return;
+  if (pre && pre[i].status != 0) return;
   const EpiGeom g = geom[i];
-  if (g.reject || g.mode == EPI_MODE_NONE) {
-    if (lane == 0) { EpiSearch z; z.found = 0; z.zmssd_best = 2000 * 64; z.n_evals = 0; z.px_cur[0] = z.px_cur[1] = 0; z.uv_best[0] = z.uv_best[1] = 0; z.h_inv = 0; search[i] = z; }
+  EpiSearch sr;
+  if (!api_results && (g.reject || g.mode == EPI_MODE_NONE)) {
+    if (lane == 0) {
+      sr.found = EPI_FOUND_NONE; sr.zmssd_best = 2000 * 64; sr.n_evals = 0; sr.px_cur_valid = 0; sr.px_cur[0] = sr.px_cur[1] = 0;
+      sr.uv_best[0] = sr.uv_best[1] = 0; sr.h_inv = 0;
+      search[i] = sr;
+    }
     return;
   }
+  EpiWarpSmem* S = &SM[warp];
+  if (api_results) { for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0; __syncwarp(); }
   const svob200_feature_ref f = ftrs[i];
-  EpiSearch sr;
-  epi_search_warp(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, g, o, &SM[warp], lane, false, &sr);
+  epi_search_warp(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, g, o, S, lane, api_results != nullptr, i,
+                  jobs, job_count, &sr);
   if (lane == 0) search[i] = sr;
+  if (api_results) {
+    __syncwarp();
+    svob200_epi_result* R = &api_results[i];
+    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = g.reject ? 0 : S->pwb[k];
+    for (int k = lane; k < 64; k += 32) R->patch[k] = g.reject ? 0 : S->patch[k];
+  }
 }
 
-// phase 3: thread per seed — triangulation, tau, Gaussian x Beta update, status
+// phase 4: thread per seed — triangulation, tau, Gaussian x Beta update, status
 __global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, double conv_thresh,
                                                            const SeedPre* pre, const EpiGeom* geom, const EpiSearch* search,
                                                            svob200_seed* seeds, svob200_seed_obs* obs)
@@ -705,89 +824,116 @@ __global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, co
   obs[i] = ob;
 }
 
-// ---------------------------------------------------------------- findMatchDirect: one warp per candidate
-struct MatchSmem { __align__(16) uint8_t pwb[100]; __align__(16) uint8_t patch[64]; AlignSmem al; };
-
-__global__ void __launch_bounds__(128) match_direct_kernel(const DevFrame* frames, const int* ref_slot, int cur_slot, DevCam cam, int n,
-                                                           const svob200_feature_ref* ftrs, const double* depth_ref,
-                                                           const double* px_in, svob200_matcher_opts o, svob200_match_result* results,
-                                                           double* px_out, int* ok_out)
+// stand-alone queries: triangulate and fill the scalar fields of svob200_epi_result (patches were written by the search kernel)
+__global__ void __launch_bounds__(128) epi_result_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const EpiGeom* geom,
+                                                         const EpiSearch* search, svob200_epi_result* results)
 {
-  __shared__ MatchSmem SM[4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  MatchSmem* S = &SM[warp];
   const svob200_feature_ref f = ftrs[i];
-  svob200_match_result* R = results ? &results[i] : nullptr;
-  const DevFrame& ref = frames[(int)f.ref_frame_id];
-  const DevFrame& cur = frames[cur_slot];
-  double px_cur[2] = {px_in[2 * i], px_in[2 * i + 1]};
-  // ref_ftr_->px.cast<int>()/(1<<level), boundary halfpatch_size_+2 (matcher.cpp:165-167)
-  const int pxi = (int)f.px[0] / (1 << f.level), pyi = (int)f.px[1] / (1 << f.level);
-  if (!in_frame_level(cam, pxi, pyi, 6, f.level)) {
-    if (lane == 0 && ok_out) { ok_out[i] = 0; px_out[2 * i] = px_cur[0]; px_out[2 * i + 1] = px_cur[1]; }
-    if (!R) return;
-    if (lane == 0) {
-      R->success = 0; R->search_level = 0; R->px_cur[0] = px_cur[0]; R->px_cur[1] = px_cur[1]; R->h_inv = 0;
-      for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = 0;
-    }
-    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = 0;
-    for (int k = lane; k < 64; k += 32) R->patch[k] = 0;
-    return;
-  }
-  double A[4];
-  warp_matrix_affine(cam, f.px, {f.f[0], f.f[1], f.f[2]}, depth_ref[i], f.T_cur_ref, f.level, A);
-  const int L = best_search_level(A, o.max_search_level);
-  for (int k = lane; k < 100; k += 32) S->pwb[k] = 0;
-  __syncwarp();
-  const uint8_t* rimg = ref.lvl[f.level] + (size_t)f.ref_image * ref.img_stride[f.level];
-  warp_affine_10x10(A, rimg, ref.pitch[f.level], ref.w[f.level], ref.h[f.level], f.px, f.level, L, S->pwb, lane, 32);
-  __syncwarp();
-  for (int k = lane; k < 64; k += 32) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
-  __syncwarp();
-  double pxs[2] = {px_cur[0] / (1 << L), px_cur[1] / (1 << L)};
-  const uint8_t* cimg = cur.lvl[L] + (size_t)f.cur_image * cur.img_stride[L];
-  bool success;
-  double h_inv = 0;
-  if (f.type == 1) {
-    double dx = A[0] * f.grad[0] + A[1] * f.grad[1], dy = A[2] * f.grad[0] + A[3] * f.grad[1];
-    { const double z = dx * dx + dy * dy; if (z > 0) { const double nn = sqrt(z); dx /= nn; dy /= nn; } }
-    success = align1d_warp(cimg, cur.pitch[L], cur.w[L], cur.h[L], (float)dx, (float)dy, S->pwb, S->patch, o.align_max_iter, pxs, &h_inv, &S->al, lane);
-  } else {
-    success = align2d_warp(cimg, cur.pitch[L], cur.w[L], cur.h[L], S->pwb, S->patch, o.align_max_iter, pxs, &S->al, lane);
-  }
-  if (lane == 0 && ok_out) { ok_out[i] = success ? 1 : 0; px_out[2 * i] = pxs[0] * (1 << L); px_out[2 * i + 1] = pxs[1] * (1 << L); }
-  if (!R) return;
-  if (lane == 0) {
-    R->success = success ? 1 : 0; R->search_level = L; R->h_inv = h_inv;
-    R->px_cur[0] = pxs[0] * (1 << L); R->px_cur[1] = pxs[1] * (1 << L);
-    for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = A[k];
-  }
-  for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = S->pwb[k];
-  for (int k = lane; k < 64; k += 32) R->patch[k] = S->patch[k];
+  const EpiGeom* g = &geom[i];
+  const EpiSearch sr = search[i];
+  double T_cur_ref[7];
+  for (int k = 0; k < 7; ++k) T_cur_ref[k] = g->T_cur_ref[k];
+  double depth = 0;
+  const bool ok = epi_finish(cam, f, T_cur_ref, sr, &depth);
+  svob200_epi_result* R = &results[i];
+  R->success = ok ? 1 : 0; R->search_level = g->L; R->reject = g->reject; R->zmssd_best = sr.zmssd_best;
+  R->n_evals = sr.n_evals; R->n_steps = g->n_steps_report; R->depth = ok ? depth : 0.0;
+  R->px_cur[0] = sr.px_cur[0]; R->px_cur[1] = sr.px_cur[1];
+  R->epi_length = g->epi_length; R->h_inv = sr.h_inv;
+  R->epi_dir[0] = g->ex; R->epi_dir[1] = g->ey;
+  R->px_cur_valid = sr.px_cur_valid;
+  for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g->A[k];
 }
 
-// stand-alone align2D / align1D on caller-provided patches: one warp per problem
-__global__ void __launch_bounds__(128) align_patches_kernel(DevFrame f, int level, int n, const int* image, const uint8_t* pwb,
-                                                            const uint8_t* patch, const float* dir, int n_iter, double* px,
-                                                            int* converged, double* h_inv)
+// ---------------------------------------------------------------- findMatchDirect: warp per candidate + LK job
+struct MatchSmem { __align__(16) uint8_t pwb[112]; };
+
+// matcher.cpp:156-194 up to the alignment call: in-frame test, affine warp matrix (lane 0, FP64), search level,
+// 10x10 patch warp by the whole warp, then the LK job.  Candidates that fail the in-frame test get their final
+// outputs here and an empty job.
+__global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n,
+                                                            const svob200_feature_ref* ftrs, const double* depth_ref,
+                                                            const double* px_in, svob200_matcher_opts o, LkJob* jobs,
+                                                            svob200_match_result* results, double* px_out, int* ok_out)
 {
   __shared__ MatchSmem SM[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 4 + warp;
   if (i >= n) return;
   MatchSmem* S = &SM[warp];
-  for (int k = lane; k < 100; k += 32) S->pwb[k] = pwb[100 * (size_t)i + k];
-  for (int k = lane; k < 64; k += 32) S->patch[k] = patch[64 * (size_t)i + k];
+  const svob200_feature_ref* fp = &ftrs[i];
+  const int level = fp->level, type = fp->type, ref_image = fp->ref_image, cur_image = fp->cur_image;
+  const double fpx0 = fp->px[0], fpx1 = fp->px[1];
+  svob200_match_result* R = results ? &results[i] : nullptr;
+  const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
+  // ref_ftr_->px.cast<int>()/(1<<level), boundary halfpatch_size_+2 (matcher.cpp:165-167)
+  const int pxi = (int)fpx0 / (1 << level), pyi = (int)fpx1 / (1 << level);
+  if (!in_frame_level(cam, pxi, pyi, 6, level)) {
+    if (lane == 0) {
+      jobs[i].level_mode = -1;
+      if (ok_out) { ok_out[i] = 0; px_out[2 * i] = px0; px_out[2 * i + 1] = px1; }
+      if (R) { R->success = 0; R->search_level = 0; R->px_cur[0] = px0; R->px_cur[1] = px1; R->h_inv = 0; for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = 0; }
+    }
+    if (R) {
+      for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = 0;
+      for (int k = lane; k < 64; k += 32) R->patch[k] = 0;
+    }
+    return;
+  }
+  // lane 0: double-precision geometry; the float warp coefficients travel by shuffle
+  double A[4] = {0, 0, 0, 0};
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, dir0 = 0.f, dir1 = 0.f;
+  int L = 0, warp_ok = 0;
+  if (lane == 0) {
+    const svob200_feature_ref f = *fp;
+    warp_matrix_affine(cam, f.px, {f.f[0], f.f[1], f.f[2]}, depth_ref[i], f.T_cur_ref, f.level, A);
+    L = best_search_level(A, o.max_search_level);
+    const double det = A[0] * A[3] - A[2] * A[1];
+    const double invdet = 1.0 / det;
+    a00 = (float)(A[3] * invdet); a01 = (float)(-A[1] * invdet); a10 = (float)(-A[2] * invdet); a11 = (float)(A[0] * invdet);
+    warp_ok = isnan(a00) ? 0 : 1;
+    if (type == 1) {
+      double dx = A[0] * f.grad[0] + A[1] * f.grad[1], dy = A[2] * f.grad[0] + A[3] * f.grad[1];
+      { const double z = dx * dx + dy * dy; if (z > 0) { const double nn = sqrt(z); dx /= nn; dy /= nn; } }
+      dir0 = (float)dx; dir1 = (float)dy;
+    }
+    if (R) { R->search_level = L; R->h_inv = 0; for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = A[k]; }
+  }
+  L = __shfl_sync(0xffffffffu, L, 0); warp_ok = __shfl_sync(0xffffffffu, warp_ok, 0);
+  a00 = __shfl_sync(0xffffffffu, a00, 0); a01 = __shfl_sync(0xffffffffu, a01, 0);
+  a10 = __shfl_sync(0xffffffffu, a10, 0); a11 = __shfl_sync(0xffffffffu, a11, 0);
+  dir0 = __shfl_sync(0xffffffffu, dir0, 0); dir1 = __shfl_sync(0xffffffffu, dir1, 0);
+  for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0;
   __syncwarp();
-  const uint8_t* img = f.lvl[level] + (size_t)image[i] * f.img_stride[level];
-  double pxs[2] = {px[2 * i], px[2 * i + 1]};
-  bool ok;
-  double hi = 0;
-  if (dir) ok = align1d_warp(img, f.pitch[level], f.w[level], f.h[level], dir[2 * i], dir[2 * i + 1], S->pwb, S->patch, n_iter, pxs, &hi, &S->al, lane);
-  else ok = align2d_warp(img, f.pitch[level], f.w[level], f.h[level], S->pwb, S->patch, n_iter, pxs, &S->al, lane);
-  if (lane == 0) { px[2 * i] = pxs[0]; px[2 * i + 1] = pxs[1]; converged[i] = ok ? 1 : 0; if (h_inv) h_inv[i] = hi; }
+  if (warp_ok) {
+    const DevFrame& ref = frames[(int)fp->ref_frame_id];
+    const uint8_t* rimg = ref.lvl[level] + (size_t)ref_image * ref.img_stride[level];
+    const float pr0 = (float)fpx0 / (float)(1 << level), pr1 = (float)fpx1 / (float)(1 << level);
+    warp_patch_10x10(rimg, ref.pitch[level], ref.w[level], ref.h[level], a00, a01, a10, a11, pr0, pr1, L, S->pwb, lane);
+  }
+  __syncwarp();
+  if (R) {
+    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = S->pwb[k];
+    for (int k = lane; k < 64; k += 32) R->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
+  }
+  emit_lk_job(&jobs[i], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), dir0, dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), lane);
+}
+
+// stand-alone align2D / align1D on caller-provided patches: thread per problem builds the job
+__global__ void __launch_bounds__(128) align_jobs_kernel(int level, int n, const int* image, const uint8_t* pwb, const float* dir,
+                                                         const double* px, LkJob* jobs)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LkJob* J = &jobs[i];
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(pwb + 100 * (size_t)i);     // 100 * i is a multiple of 4
+  uint32_t* dst = reinterpret_cast<uint32_t*>(J->pwb);
+  for (int k = 0; k < 25; ++k) dst[k] = src[k];
+  J->u = (float)px[2 * i]; J->v = (float)px[2 * i + 1];
+  J->dirx = dir ? dir[2 * i] : 0.f; J->diry = dir ? dir[2 * i + 1] : 0.f;
+  J->item = i; J->image = image[i]; J->level_mode = level | ((dir ? 1 : 0) << 8);
 }
 
 __global__ void update_seed_kernel(int n, const float* x, const float* tau2, svob200_seed* seeds)
@@ -855,43 +1001,66 @@ __global__ void triangulate_kernel(int n, const double* T, const double* f_ref, 
 
 }  // namespace
 
-int launch_align_patches(const DevFrame& f, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
-                         const float* d_dir, int n_iter, double* d_px, int* d_converged, double* d_h_inv,
+// ---------------------------------------------------------------- launchers
+static inline size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+size_t lk_jobs_bytes(int n) { return up256((size_t)(n > 0 ? n : 1) * sizeof(LkJob)) + 256; }
+
+int launch_align_patches(const DevFrame* d_frames, int slot, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
+                         const float* d_dir, int n_iter, double* d_px, int* d_converged, double* d_h_inv, void* d_scratch,
                          cudaStream_t s, long long* launches)
 {
   if (n <= 0) return 0;
-  align_patches_kernel<<<(n + 3) / 4, 128, 0, s>>>(f, level, n, d_image, d_pwb, d_patch, d_dir, n_iter, d_px, d_converged, d_h_inv);
+  LkJob* jobs = static_cast<LkJob*>(d_scratch);
+  align_jobs_kernel<<<(n + 127) / 128, 128, 0, s>>>(level, n, d_image, d_pwb, d_dir, d_px, jobs);
   ++*launches;
+  LkSink sink{};
+  sink.kind = LK_SINK_ARRAYS; sink.px_out = d_px; sink.ok_out = d_converged; sink.h_inv_out = d_h_inv; sink.patches = d_patch;
+  if (launch_lk_refine(d_frames, slot, jobs, nullptr, n, n_iter, sink, s, launches)) return -1;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int launch_match_direct(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
-                        const svob200_feature_ref* d_ftrs, const double* d_depth_ref, const double* d_px_in,
-                        svob200_matcher_opts opts, svob200_match_result* d_results, cudaStream_t s, long long* launches)
+// Matcher::findMatchDirect for n candidates: prepare (warp per candidate) + LK (thread per candidate).
+// results: full records (API) or nullptr; px_out / ok_out: compact outputs (tracker) or nullptr.
+int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
+                        const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, svob200_match_result* d_results,
+                        double* d_px_out, int* d_ok_out, void* d_scratch, cudaStream_t s, long long* launches, cudaEvent_t* mark)
 {
   if (n <= 0) return 0;
-  match_direct_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, d_results, nullptr, nullptr);
+  LkJob* jobs = static_cast<LkJob*>(d_scratch);
+  match_prepare_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, jobs, d_results, d_px_out, d_ok_out);
   ++*launches;
+  if (mark) cudaEventRecord(*mark, s);
+  LkSink sink{};
+  if (d_results) { sink.kind = LK_SINK_MATCH_RESULT; sink.mres = d_results; }
+  else { sink.kind = LK_SINK_MATCH_COMPACT; sink.px_out = d_px_out; sink.ok_out = d_ok_out; }
+  if (launch_lk_refine(d_frames, cur_slot, jobs, nullptr, n, opts.align_max_iter, sink, s, launches)) return -1;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// same kernel, compact outputs only (refined pixel + success flag): what the tracker keeps per map point
-int launch_match_direct_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
-                                const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, double* d_px_out,
-                                int* d_ok_out, cudaStream_t s, long long* launches)
+size_t epipolar_scratch_bytes(int n)
 {
-  if (n <= 0) return 0;
-  match_direct_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, nullptr, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, nullptr, d_px_out, d_ok_out);
-  ++*launches;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  const size_t m = (size_t)(n > 0 ? n : 1);
+  return up256(m * sizeof(EpiGeom)) + up256(m * sizeof(EpiSearch)) + up256(m * sizeof(LkJob)) + 512;
 }
 
-int launch_epipolar(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
-                    const svob200_feature_ref* d_ftrs, const double* d_d, svob200_matcher_opts opts,
-                    svob200_epi_result* d_results, cudaStream_t s, long long* launches)
+int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs, const double* d_d,
+                    svob200_matcher_opts opts, svob200_epi_result* d_results, void* d_scratch, cudaStream_t s, long long* launches)
 {
   if (n <= 0) return 0;
-  epipolar_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, d_ref_slot, cur_slot, cam, n, d_ftrs, d_d, opts, d_results);
+  const size_t m = (size_t)n;
+  char* p = static_cast<char*>(d_scratch);
+  EpiGeom* geom = reinterpret_cast<EpiGeom*>(p); p += up256(m * sizeof(EpiGeom));
+  EpiSearch* search = reinterpret_cast<EpiSearch*>(p); p += up256(m * sizeof(EpiSearch));
+  LkJob* jobs = reinterpret_cast<LkJob*>(p); p += up256(m * sizeof(LkJob));
+  int* count = reinterpret_cast<int*>(p);
+  epi_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_d, opts, geom, count);
+  epi_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, nullptr, geom, search, jobs, count, d_results);
+  *launches += 2;
+  LkSink sink{};
+  sink.kind = LK_SINK_EPI; sink.search = search;
+  if (launch_lk_refine(d_frames, cur_slot, jobs, count, n, opts.align_max_iter, sink, s, launches)) return -1;
+  epi_result_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, geom, search, d_results);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -899,29 +1068,37 @@ int launch_epipolar(const DevFrame* d_frames, const int* d_ref_slot, int cur_slo
 size_t seeds_scratch_bytes(int n)
 {
   const size_t m = (size_t)(n > 0 ? n : 1);
-  return m * (sizeof(SeedPre) + sizeof(EpiGeom) + sizeof(EpiSearch)) + 2048;
+  return up256(m * sizeof(EpiGeom)) + up256(m * sizeof(EpiSearch)) + up256(m * sizeof(SeedPre)) + up256(m * sizeof(LkJob)) + 512;
 }
 
-int launch_seeds_update(const DevFrame* d_frames, const int* d_ref_slot, int cur_slot, const DevCam& cam, int n,
-                        const svob200_feature_ref* d_ftrs, const double* d_T_ref_w, const double* d_T_cur_w,
-                        svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs,
-                        void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches, cudaEvent_t* marks)
+// DepthFilter::updateSeeds for n seeds: geometry (thread) -> search (warp) -> LK (thread per job) -> update (thread).
+// marks: optional 3 events recorded between the four kernels.
+int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
+                        const double* d_T_ref_w, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
+                        svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first,
+                        cudaStream_t s, long long* launches, cudaEvent_t* marks)
 {
   // d_ftrs / d_T_ref_w / d_seeds / d_obs already point at seed `first`; the scratch was sized for
   // scratch_total seeds and is indexed by absolute seed number
-  (void)d_ref_slot;
   if (n <= 0) return 0;
   const size_t m = (size_t)(scratch_total > 0 ? scratch_total : 1);
   char* p = static_cast<char*>(d_scratch);
-  EpiGeom* geom = reinterpret_cast<EpiGeom*>(p) + first; p += ((m * sizeof(EpiGeom) + 255) & ~(size_t)255);
-  EpiSearch* search = reinterpret_cast<EpiSearch*>(p) + first; p += ((m * sizeof(EpiSearch) + 255) & ~(size_t)255);
-  SeedPre* pre = reinterpret_cast<SeedPre*>(p) + first;
-  seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, geom);
+  EpiGeom* geom = reinterpret_cast<EpiGeom*>(p) + first; p += up256(m * sizeof(EpiGeom));
+  EpiSearch* search = reinterpret_cast<EpiSearch*>(p) + first; p += up256(m * sizeof(EpiSearch));
+  SeedPre* pre = reinterpret_cast<SeedPre*>(p) + first; p += up256(m * sizeof(SeedPre));
+  LkJob* jobs = reinterpret_cast<LkJob*>(p) + first; p += up256(m * sizeof(LkJob));
+  int* count = reinterpret_cast<int*>(p);
+  seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, geom, count);
   if (marks) cudaEventRecord(marks[0], s);
-  seeds_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, pre, geom, search);
+  epi_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, pre, geom, search, jobs, count, nullptr);
   if (marks) cudaEventRecord(marks[1], s);
+  *launches += 2;
+  LkSink sink{};
+  sink.kind = LK_SINK_EPI; sink.search = search;
+  if (launch_lk_refine(d_frames, cur_slot, jobs, count, n, opts.align_max_iter, sink, s, launches)) return -1;
+  if (marks) cudaEventRecord(marks[2], s);
   seeds_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, conv_thresh, pre, geom, search, d_seeds, d_obs);
-  *launches += 3;
+  ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
