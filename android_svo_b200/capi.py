@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsvob200.so")
+# SVOB200_LIB: alternative build of the same library (A/B experiments); default is the in-tree build
+LIB_PATH = os.environ.get("SVOB200_LIB") or os.path.join(HERE, "lib", "libsvob200.so")
 MAX_LEVELS = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 ROUND_TRUNC, ROUND_SSE2 = 0, 1

@@ -30,10 +30,13 @@ size_t lk_jobs_bytes(int n);                 // scratch of launch_align_patches 
 int launch_align_patches(const DevFrame* d_frames, int slot, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,
                          const float* d_dir, int n_iter, double* d_px, int* d_converged, double* d_h_inv, void* d_scratch,
                          cudaStream_t s, long long* launches);
-// results: full records (API) or nullptr; px_out / ok_out: compact outputs (tracker) or nullptr; mark: optional event between the two kernels
+// results: full records (API) or nullptr; px_out / ok_out: compact outputs (tracker) or nullptr; the scratch
+// (match_scratch_bytes(scratch_total)) is indexed from `first`; marks: optional 2 events between the three kernels
+size_t match_scratch_bytes(int n);
 int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                         const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, svob200_match_result* d_results,
-                        double* d_px_out, int* d_ok_out, void* d_scratch, cudaStream_t s, long long* launches, cudaEvent_t* mark = nullptr);
+                        double* d_px_out, int* d_ok_out, void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches,
+                        cudaEvent_t* marks = nullptr);
 size_t epipolar_scratch_bytes(int n);
 int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs, const double* d_d,
                     svob200_matcher_opts opts, svob200_epi_result* d_results, void* d_scratch, cudaStream_t s, long long* launches);

@@ -296,7 +296,7 @@ __device__ __forceinline__ int zmssd_8x8(const RefPatchRegs& r, const uint8_t* c
 #pragma unroll
   for (int y = 0; y < 8; ++y) {
     const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 & ~(uintptr_t)3) + (size_t)y * pitch);   // pitch % 4 == 0
-    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
     const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
     sb = __dp4a(lo, 0x01010101u, sb); sb = __dp4a(hi, 0x01010101u, sb);
     sbb = __dp4a(lo, lo, sbb); sbb = __dp4a(hi, hi, sbb);
@@ -383,6 +383,7 @@ constexpr int EPI_MAX_STEPS = 1023;      // max_epi_search_steps is clamped to t
 enum { EPI_MODE_NONE = 0, EPI_MODE_DIRECT = 1, EPI_MODE_WALK = 2 };
 enum { EPI_FOUND_NONE = 0, EPI_FOUND_REFINED = 1, EPI_FOUND_UV_ONLY = 2 };
 
+// everything epi_geometry() derives (thread-local); split into a cold record (finish kernels) and a packed task (search kernel)
 struct EpiGeom {
   double T_cur_ref[7];
   double A[4];                          // A_cur_ref, row-major
@@ -395,12 +396,62 @@ struct EpiGeom {
   int warp_ok, L, mode, n, n_steps_report, reject;
 };
 
-struct EpiSearch {
+// what the per-item finish kernels need, 128 B
+struct __align__(16) EpiCold {
+  double T_cur_ref[7];
+  double A[4];
+  double ex, ey;
+  double epi_length;
+  int L, mode, reject, n_steps_report;
+};
+static_assert(sizeof(EpiCold) == 128, "EpiCold layout");
+
+// what the search kernel needs, packed into ONE 128-byte line: a warp fetches it with a single coalesced load (lane k
+// holds word k) one item ahead of the item it is working on, and pulls fields out by shuffle
+struct __align__(16) SearchTask { uint32_t w[32]; };
+enum { ST_FLAGS = 0, ST_LEVELS = 1, ST_N = 2, ST_REF_SLOT = 3, ST_REF_IMAGE = 4, ST_CUR_IMAGE = 5, ST_A00 = 6, ST_A01 = 7, ST_A10 = 8, ST_A11 = 9,
+       ST_PR0 = 10, ST_PR1 = 11, ST_DIRX = 12, ST_DIRY = 13, ST_BX0 = 14, ST_BY0 = 16, ST_STEPX = 18, ST_STEPY = 20, ST_MIDX = 22, ST_MIDY = 24 };
+enum { ST_ACTIVE = 1, ST_WARP_OK = 2, ST_MODE_SHIFT = 2 };
+
+__device__ inline void store_geometry(const EpiGeom& g, const svob200_feature_ref& f, bool active, EpiCold* cold, SearchTask* task)
+{
+  EpiCold c;
+  for (int k = 0; k < 7; ++k) c.T_cur_ref[k] = g.T_cur_ref[k];
+  for (int k = 0; k < 4; ++k) c.A[k] = g.A[k];
+  c.ex = g.ex; c.ey = g.ey; c.epi_length = g.epi_length; c.L = g.L; c.mode = g.mode; c.reject = g.reject; c.n_steps_report = g.n_steps_report;
+  *cold = c;
+  SearchTask t;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) t.w[k] = 0;
+  t.w[ST_FLAGS] = (active ? ST_ACTIVE : 0) | (g.warp_ok ? ST_WARP_OK : 0) | ((uint32_t)g.mode << ST_MODE_SHIFT);
+  t.w[ST_LEVELS] = (uint32_t)g.L | ((uint32_t)f.level << 8);
+  t.w[ST_N] = (uint32_t)g.n; t.w[ST_REF_SLOT] = (uint32_t)f.ref_frame_id; t.w[ST_REF_IMAGE] = (uint32_t)f.ref_image; t.w[ST_CUR_IMAGE] = (uint32_t)f.cur_image;
+  t.w[ST_A00] = __float_as_uint(g.a00); t.w[ST_A01] = __float_as_uint(g.a01); t.w[ST_A10] = __float_as_uint(g.a10); t.w[ST_A11] = __float_as_uint(g.a11);
+  t.w[ST_PR0] = __float_as_uint(g.pr0); t.w[ST_PR1] = __float_as_uint(g.pr1); t.w[ST_DIRX] = __float_as_uint(g.dirx); t.w[ST_DIRY] = __float_as_uint(g.diry);
+  const double d[6] = {g.Bx0, g.By0, g.stepx, g.stepy, g.px_mid[0], g.px_mid[1]};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { t.w[ST_BX0 + 2 * k] = (uint32_t)__double2loint(d[k]); t.w[ST_BX0 + 2 * k + 1] = (uint32_t)__double2hiint(d[k]); }
+  uint4* dst = reinterpret_cast<uint4*>(task);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dst[k] = make_uint4(t.w[4 * k], t.w[4 * k + 1], t.w[4 * k + 2], t.w[4 * k + 3]);
+}
+
+struct __align__(16) EpiSearch {
   int found;                            // EPI_FOUND_*
   int zmssd_best, n_evals;
   int px_cur_valid;                     // the reference wrote Matcher::px_cur_ (matcher.cpp:259, :327, :345)
   double px_cur[2], uv_best[2], h_inv;
+  double pad_;
 };
+static_assert(sizeof(EpiSearch) == 64, "EpiSearch layout");
+
+__device__ __forceinline__ EpiSearch epi_search_none()
+{
+  EpiSearch s;
+  s.found = EPI_FOUND_NONE; s.zmssd_best = 2000 * 64; s.n_evals = 0; s.px_cur_valid = 0; s.px_cur[0] = s.px_cur[1] = 0;
+  s.uv_best[0] = s.uv_best[1] = 0; s.h_inv = 0; s.pad_ = 0;
+  return s;
+}
 
 struct EpiWarpSmem {
   __align__(16) uint8_t pwb[112];       // 100 used
@@ -491,56 +542,103 @@ __device__ __forceinline__ void emit_lk_job(LkJob* dst, const uint8_t* s_pwb, fl
 __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, int rc, int rr, float a00, float a01, float a10, float a11,
                                                  float pr0, float pr1, int L, uint8_t* s_pwb, int lane)
 {
+  // lane handles taps lane, lane+32, lane+64, lane+96 (< 100); the loop is unrolled so that the 16 pixel loads of a
+  // lane are in flight together (one memory latency per patch instead of four)
   const float sc = (float)(1 << L);
-  for (int i = lane; i < 100; i += 32) {
+  const float xmax = (float)(rc - 1), ymax = (float)(rr - 1);
+  bool inb[4];
+  float w00[4], w01[4], w10[4], w11[4];
+  uint8_t p00[4], p01[4], p10[4], p11[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = lane + 32 * r;
     const int y = i / 10, x = i - y * 10;
     float p0 = (float)(x - 5), p1 = (float)(y - 5);
     p0 *= sc; p1 *= sc;
     const float qx = (a00 * p0 + a01 * p1) + pr0;
     const float qy = (a10 * p0 + a11 * p1) + pr1;
-    uint8_t v = 0;
-    if (!(qx < 0 || qy < 0 || qx >= rc - 1 || qy >= rr - 1)) v = (uint8_t)interpolate_8u(rimg, rp, qx, qy);
-    s_pwb[i] = v;
+    inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    // vk::interpolateMat_8u (vision.h:19-36)
+    const int ix = (int)floorf(qx), iy = (int)floorf(qy);
+    const float sx = qx - ix, sy = qy - iy;
+    w00[r] = (1.0f - sx) * (1.0f - sy);
+    w01[r] = (1.0f - sx) * sy;
+    w10[r] = sx * (1.0f - sy);
+    w11[r] = 1.0f - w00[r] - w01[r] - w10[r];
+    p00[r] = p01[r] = p10[r] = p11[r] = 0;
+    if (inb[r]) {
+      const uint8_t* p = rimg + (size_t)iy * rp + ix;
+      p00[r] = p[0]; p01[r] = p[rp]; p10[r] = p[1]; p11[r] = p[rp + 1];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = lane + 32 * r;
+    if (i < 100) s_pwb[i] = inb[r] ? (uint8_t)(w00[r] * p00[r] + w01[r] * p01[r] + w10[r] * p10[r] + w11[r] * p11[r]) : (uint8_t)0;
   }
 }
 
-// matcher.cpp:251-340 minus the LK refinement: warp the patch, walk the epipolar segment, and hand the
-// refinement to the thread-per-problem LK kernel as a job.  One full warp cooperates.
-__device__ void epi_search_warp(const DevFrame& ref, int ref_image, const DevFrame& cur, int cur_image, const DevCam& cam,
-                                const svob200_feature_ref& f, const EpiGeom& g, const svob200_matcher_opts& o, EpiWarpSmem* S,
-                                int lane, bool always_warp, int item, LkJob* jobs, int* job_count, EpiSearch* out)
+__device__ __forceinline__ double shfl_double(uint32_t word, int src)
 {
-  out->found = EPI_FOUND_NONE; out->zmssd_best = 2000 * 64; out->n_evals = 0; out->px_cur_valid = 0; out->px_cur[0] = out->px_cur[1] = 0;
-  out->uv_best[0] = out->uv_best[1] = 0; out->h_inv = 0;
-  if (g.reject) return;
-  if (g.mode == EPI_MODE_NONE && !always_warp) return;
-  const int L = g.L;
-  if (g.warp_ok) {
-    const uint8_t* rimg = ref.lvl[f.level] + (size_t)ref_image * ref.img_stride[f.level];
-    warp_patch_10x10(rimg, ref.pitch[f.level], ref.w[f.level], ref.h[f.level], g.a00, g.a01, g.a10, g.a11, g.pr0, g.pr1, L, S->pwb, lane);
+  const int lo = (int)__shfl_sync(0xffffffffu, word, src), hi = (int)__shfl_sync(0xffffffffu, word, src + 1);
+  return __hiloint2double(hi, lo);
+}
+
+constexpr int JOB_BATCH = 8;             // LK job slots a warp reserves per atomicAdd
+
+// matcher.cpp:251-340 minus the LK refinement, for ONE item whose packed task sits in `tw` (lane k = word k): warp the
+// patch, walk the epipolar segment, and hand the refinement to the thread-per-problem LK kernel as a job.
+__device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_slot, const DevCam& cam, const svob200_matcher_opts& o,
+                                                uint32_t tw, int item, EpiWarpSmem* S, int lane, LkJob* jobs, int* job_count,
+                                                int& slot_base, int& slots_left, EpiSearch* search, svob200_epi_result* api_results)
+{
+  const uint32_t FULL = 0xffffffffu;
+  const int flags = (int)__shfl_sync(FULL, tw, ST_FLAGS);
+  const int mode = (flags >> ST_MODE_SHIFT) & 3;
+  const int levels = (int)__shfl_sync(FULL, tw, ST_LEVELS);
+  const int L = levels & 0xff, ref_level = (levels >> 8) & 0xff;
+  const int cur_image = (int)__shfl_sync(FULL, tw, ST_CUR_IMAGE);
+  EpiSearch out = epi_search_none();
+  if (api_results) { for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0; __syncwarp(); }
+  if (flags & ST_WARP_OK) {
+    const DevFrame& ref = frames[(int)__shfl_sync(FULL, tw, ST_REF_SLOT)];
+    const int ref_image = (int)__shfl_sync(FULL, tw, ST_REF_IMAGE);
+    const uint8_t* rimg = ref.lvl[ref_level] + (size_t)ref_image * ref.img_stride[ref_level];
+    warp_patch_10x10(rimg, ref.pitch[ref_level], ref.w[ref_level], ref.h[ref_level],
+                     __uint_as_float(__shfl_sync(FULL, tw, ST_A00)), __uint_as_float(__shfl_sync(FULL, tw, ST_A01)),
+                     __uint_as_float(__shfl_sync(FULL, tw, ST_A10)), __uint_as_float(__shfl_sync(FULL, tw, ST_A11)),
+                     __uint_as_float(__shfl_sync(FULL, tw, ST_PR0)), __uint_as_float(__shfl_sync(FULL, tw, ST_PR1)), L, S->pwb, lane);
   }
   __syncwarp();
   for (int k = lane; k < 64; k += 32) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
   __syncwarp();
-  if (g.mode == EPI_MODE_NONE) return;
-  const uint8_t* cimg = cur.lvl[L] + (size_t)cur_image * cur.img_stride[L];
-  const int cpitch = cur.pitch[L];
-  double px0, px1;
-  if (g.mode == EPI_MODE_DIRECT) {
-    px0 = g.px_mid[0]; px1 = g.px_mid[1];
-  } else {
+  if (api_results) {
+    svob200_epi_result* R = &api_results[item];
+    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = S->pwb[k];
+    for (int k = lane; k < 64; k += 32) R->patch[k] = S->patch[k];
+  }
+  bool want_job = false;
+  double px0 = 0.0, px1 = 0.0;
+  if (mode == EPI_MODE_DIRECT) {
+    px0 = shfl_double(tw, ST_MIDX); px1 = shfl_double(tw, ST_MIDY);
+    want_job = true;
+  } else if (mode == EPI_MODE_WALK) {
+    const DevFrame& cur = frames[cur_slot];
+    const uint8_t* cimg = cur.lvl[L] + (size_t)cur_image * cur.img_stride[L];
+    const int cpitch = cur.pitch[L];
+    const int n = (int)__shfl_sync(FULL, tw, ST_N);
     RefPatchRegs rpatch;
     load_ref_patch(S->patch, rpatch);
-    unsigned long long best = ((unsigned long long)(2000 * 64) << 32) | 0xffffffffu;   // PatchScore::threshold(), strict <
+    unsigned long long best = ((unsigned long long)(2000 * 64) << 32);   // PatchScore::threshold(), strict <
     double best_u = 0.0, best_v = 0.0;
     int evals = 0;
     // the reference's running sums uv += step: x chain on lane 0, y chain on lane 1 (two independent DADD chains)
-    double uv = lane == 0 ? g.Bx0 : g.By0;
-    const double st = lane == 0 ? g.stepx : g.stepy;
+    double uv = shfl_double(tw, ST_BX0 + 2 * (lane & 1));
+    const double st = shfl_double(tw, ST_STEPX + 2 * (lane & 1));
     const double inv_scale = 1.0 / (double)(1 << L);                     // exact: dividing by 2^L == multiplying by 2^-L
     short2 last = make_short2(0, 0);                                     // last_checked_pxi(0,0)
-    for (int base = 0; base < g.n; base += EPI_CHUNK) {
-      const int m = min(EPI_CHUNK, g.n - base);
+    for (int base = 0; base < n; base += EPI_CHUNK) {
+      const int m = min(EPI_CHUNK, n - base);
       if (lane < 2) {
         double* dst = S->uv + lane;
         for (int i = 0; i < m; ++i, uv += st) dst[2 * i] = uv;
@@ -571,28 +669,36 @@ __device__ void epi_search_warp(const DevFrame& ref, int ref_image, const DevFra
     unsigned long long gbest = best;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, gbest, off);
+      const unsigned long long other = __shfl_xor_sync(FULL, gbest, off);
       if (other < gbest) gbest = other;
-      evals += __shfl_xor_sync(0xffffffffu, evals, off);
+      evals += __shfl_xor_sync(FULL, evals, off);
     }
-    out->n_evals = evals;
+    out.n_evals = evals;
     const int zbest = (int)(gbest >> 32);
-    out->zmssd_best = zbest;
-    if (!(zbest < 2000 * 64)) return;
-    // uv_best lives on the lane that evaluated the winning step (keys are unique: they contain the step index)
-    const unsigned owner = __ffs(__ballot_sync(0xffffffffu, best == gbest)) - 1;
-    const double ubx = __shfl_sync(0xffffffffu, best_u, owner), uby = __shfl_sync(0xffffffffu, best_v, owner);
-    world2cam_uv(cam, ubx, uby, px0, px1);
-    out->uv_best[0] = ubx; out->uv_best[1] = uby;
-    if (!o.subpix_refinement) { out->px_cur[0] = px0; out->px_cur[1] = px1; out->px_cur_valid = 1; out->found = EPI_FOUND_UV_ONLY; return; }
+    out.zmssd_best = zbest;
+    if (zbest < 2000 * 64) {
+      // uv_best lives on the lane that evaluated the winning step (keys are unique: they contain the step index)
+      const unsigned owner = __ffs(__ballot_sync(FULL, best == gbest)) - 1;
+      const double ubx = __shfl_sync(FULL, best_u, owner), uby = __shfl_sync(FULL, best_v, owner);
+      world2cam_uv(cam, ubx, uby, px0, px1);
+      out.uv_best[0] = ubx; out.uv_best[1] = uby;
+      if (!o.subpix_refinement) { out.px_cur[0] = px0; out.px_cur[1] = px1; out.px_cur_valid = 1; out.found = EPI_FOUND_UV_ONLY; }
+      else want_job = true;
+    }
   }
-  out->px_cur[0] = px0; out->px_cur[1] = px1; out->px_cur_valid = 1;
+  if (want_job) { out.px_cur[0] = px0; out.px_cur[1] = px1; out.px_cur_valid = 1; }
+  if (lane == 0) search[item] = out;
+  if (!want_job) return;
   // hand over to the LK kernel: px_scaled = px_cur / (1 << L) (double), cast to float at the start of align1D/2D
-  int slot = 0;
-  if (lane == 0) slot = atomicAdd(job_count, 1);
-  slot = __shfl_sync(0xffffffffu, slot, 0);
-  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), g.dirx, g.diry, item, cur_image,
-              L | ((o.align_1d ? 1 : 0) << 8), lane);
+  if (slots_left == 0) {
+    if (lane == 0) slot_base = atomicAdd(job_count, JOB_BATCH);
+    slot_base = __shfl_sync(FULL, slot_base, 0);
+    slots_left = JOB_BATCH;
+  }
+  const int slot = slot_base + (JOB_BATCH - slots_left);
+  --slots_left;
+  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), __uint_as_float(__shfl_sync(FULL, tw, ST_DIRX)),
+              __uint_as_float(__shfl_sync(FULL, tw, ST_DIRY)), item, cur_image, L | ((o.align_1d ? 1 : 0) << 8), lane);
 }
 
 // matcher.cpp:269-276 / :341-351: triangulate from the matched pixel (per thread)
@@ -700,7 +806,7 @@ struct SeedPre {
 // phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry
 __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* T_ref_w_all,
                                                          const double* T_cur_w_all, svob200_matcher_opts o, const svob200_seed* seeds,
-                                                         SeedPre* pre, EpiGeom* geom, int* job_count)
+                                                         SeedPre* pre, EpiCold* cold, SearchTask* tasks, int* job_count)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *job_count = 0;                                        // consumed by the search kernel that follows on the stream
@@ -731,61 +837,57 @@ __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, cons
     double Trw_inv[7], T_cur_ref_m[7];
     se3_inverse(T_ref_w, Trw_inv);
     se3_mul(T_cur_w, Trw_inv, T_cur_ref_m);                          // matcher.cpp:216
-    epi_geometry(cam, f, T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &geom[i]);
+    EpiGeom g;
+    epi_geometry(cam, f, T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &g);
+    store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, &cold[i], &tasks[i]);
+  } else {
+    reinterpret_cast<uint4*>(&tasks[i])[0] = make_uint4(0, 0, 0, 0);        // flags = 0: nothing to search
   }
   pre[i] = p;
 }
 
 // geometry of stand-alone epipolar queries (svob200_epipolar_match): T_cur_ref and the depth range come from the caller
 __global__ void __launch_bounds__(128) epi_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* d,
-                                                       svob200_matcher_opts o, EpiGeom* geom, int* job_count)
+                                                       svob200_matcher_opts o, EpiCold* cold, SearchTask* tasks, int* job_count)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *job_count = 0;
   if (i >= n) return;
   const svob200_feature_ref f = ftrs[i];
-  epi_geometry(cam, f, f.T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &geom[i]);
+  EpiGeom g;
+  epi_geometry(cam, f, f.T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &g);
+  store_geometry(g, f, !g.reject, &cold[i], &tasks[i]);               // stand-alone queries always warp the patch (unless rejected)
 }
 
-// phase 2: warp per seed / query — patch warp, ZMSSD walk, LK job.  pre == nullptr: stand-alone queries, which
-// always warp the patch and return it in api_results.
-__global__ void __launch_bounds__(128) epi_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n,
-                                                         const svob200_feature_ref* ftrs, svob200_matcher_opts o,
-                                                         const SeedPre* pre, const EpiGeom* geom, EpiSearch* search,
-                                                         LkJob* jobs, int* job_count, svob200_epi_result* api_results)
+// phase 2: warp per item, PERSISTENT — the grid is sized to the machine (8 CTAs per SM) and every warp strides over the
+// items; the packed task of the next item is fetched (one coalesced 128-byte load) while the current one is processed,
+// and LK job slots are reserved JOB_BATCH at a time, so neither a DRAM round trip nor an atomic sits on the critical
+// path of an item.  api_results != nullptr: stand-alone queries, which also return the warped patch.
+__global__ void __launch_bounds__(128, 8) epi_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n, svob200_matcher_opts o,
+                                                            const SearchTask* tasks, EpiSearch* search, LkJob* jobs, int* job_count,
+                                                            svob200_epi_result* api_results)
 {
   __shared__ EpiWarpSmem SM[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
-  if (i >= n) return;
-  if (pre && pre[i].status != 0) return;
-  const EpiGeom g = geom[i];
-  EpiSearch sr;
-  if (!api_results && (g.reject || g.mode == EPI_MODE_NONE)) {
-    if (lane == 0) {
-      sr.found = EPI_FOUND_NONE; sr.zmssd_best = 2000 * 64; sr.n_evals = 0; sr.px_cur_valid = 0; sr.px_cur[0] = sr.px_cur[1] = 0;
-      sr.uv_best[0] = sr.uv_best[1] = 0; sr.h_inv = 0;
-      search[i] = sr;
-    }
-    return;
-  }
   EpiWarpSmem* S = &SM[warp];
-  if (api_results) { for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0; __syncwarp(); }
-  const svob200_feature_ref f = ftrs[i];
-  epi_search_warp(frames[(int)f.ref_frame_id], f.ref_image, frames[cur_slot], f.cur_image, cam, f, g, o, S, lane, api_results != nullptr, i,
-                  jobs, job_count, &sr);
-  if (lane == 0) search[i] = sr;
-  if (api_results) {
+  const int nw = gridDim.x * 4;
+  int slot_base = 0, slots_left = 0;
+  int i = blockIdx.x * 4 + warp;
+  uint32_t next = (i < n) ? __ldg(&tasks[i].w[lane]) : 0u;
+  for (; i < n; i += nw) {
+    const uint32_t tw = next;
+    if (i + nw < n) next = __ldg(&tasks[i + nw].w[lane]);
+    if (!(__shfl_sync(0xffffffffu, tw, ST_FLAGS) & ST_ACTIVE)) continue;
+    epi_search_item(frames, cur_slot, cam, o, tw, i, S, lane, jobs, job_count, slot_base, slots_left, search, api_results);
     __syncwarp();
-    svob200_epi_result* R = &api_results[i];
-    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = g.reject ? 0 : S->pwb[k];
-    for (int k = lane; k < 64; k += 32) R->patch[k] = g.reject ? 0 : S->patch[k];
   }
+  // reserved but unused job slots become empty jobs
+  for (int k = lane; k < slots_left; k += 32) jobs[slot_base + (JOB_BATCH - slots_left) + k].level_mode = -1;
 }
 
 // phase 4: thread per seed — triangulation, tau, Gaussian x Beta update, status
 __global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, double conv_thresh,
-                                                           const SeedPre* pre, const EpiGeom* geom, const EpiSearch* search,
+                                                           const SeedPre* pre, const EpiCold* cold, const EpiSearch* search,
                                                            svob200_seed* seeds, svob200_seed_obs* obs)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,8 +897,8 @@ __global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, co
   ob.status = p.status; ob.search_level = 0; ob.zmssd_best = 2000 * 64; ob.n_evals = 0; ob.z = 0; ob.px_cur[0] = ob.px_cur[1] = 0; ob.epi_length = 0;
   if (p.status == 0) {
     const svob200_feature_ref f = ftrs[i];
-    const EpiSearch sr = search[i];
-    const EpiGeom* g = &geom[i];
+    const EpiCold* g = &cold[i];
+    const EpiSearch sr = (!g->reject && g->mode != EPI_MODE_NONE) ? search[i] : epi_search_none();
     svob200_seed s = seeds[i];
     ob.search_level = g->L; ob.zmssd_best = sr.zmssd_best; ob.n_evals = sr.n_evals; ob.epi_length = g->epi_length;
     ob.px_cur[0] = sr.px_cur[0]; ob.px_cur[1] = sr.px_cur[1];
@@ -825,14 +927,19 @@ __global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, co
 }
 
 // stand-alone queries: triangulate and fill the scalar fields of svob200_epi_result (patches were written by the search kernel)
-__global__ void __launch_bounds__(128) epi_result_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const EpiGeom* geom,
+__global__ void __launch_bounds__(128) epi_result_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const EpiCold* cold,
                                                          const EpiSearch* search, svob200_epi_result* results)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const svob200_feature_ref f = ftrs[i];
-  const EpiGeom* g = &geom[i];
-  const EpiSearch sr = search[i];
+  const EpiCold* g = &cold[i];
+  const EpiSearch sr = g->reject ? epi_search_none() : search[i];
+  if (g->reject) {
+    svob200_epi_result* R0 = &results[i];
+    for (int k = 0; k < 100; ++k) R0->patch_with_border[k] = 0;
+    for (int k = 0; k < 64; ++k) R0->patch[k] = 0;
+  }
   double T_cur_ref[7];
   for (int k = 0; k < 7; ++k) T_cur_ref[k] = g->T_cur_ref[k];
   double depth = 0;
@@ -847,78 +954,91 @@ __global__ void __launch_bounds__(128) epi_result_kernel(DevCam cam, int n, cons
   for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g->A[k];
 }
 
-// ---------------------------------------------------------------- findMatchDirect: warp per candidate + LK job
+// ---------------------------------------------------------------- findMatchDirect: geometry (thread) + patch warp (warp) + LK job
+struct MatchGeom {
+  double A[4];                          // A_cur_ref (row-major)
+  float a00, a01, a10, a11, pr0, pr1;   // A_ref_cur as float, px_ref at the reference level
+  float dir0, dir1;                     // align1D direction for edgelets
+  int L, flags;                         // search level; bit 0: in frame, bit 1: warp is finite
+};
+
+// matcher.cpp:156-183 up to warpAffine: in-frame test, affine warp matrix (FP64), search level.  Thread per candidate,
+// so the double-precision geometry runs lane-parallel.  Candidates that fail the in-frame test get their final
+// outputs here and an empty job.
+__global__ void __launch_bounds__(128) match_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* depth_ref,
+                                                         const double* px_in, svob200_matcher_opts o, MatchGeom* geom, LkJob* jobs,
+                                                         svob200_match_result* results, double* px_out, int* ok_out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const svob200_feature_ref f = ftrs[i];
+  MatchGeom g;
+  g.A[0] = g.A[1] = g.A[2] = g.A[3] = 0; g.a00 = g.a01 = g.a10 = g.a11 = g.pr0 = g.pr1 = g.dir0 = g.dir1 = 0.f; g.L = 0; g.flags = 0;
+  svob200_match_result* R = results ? &results[i] : nullptr;
+  // ref_ftr_->px.cast<int>()/(1<<level), boundary halfpatch_size_+2 (matcher.cpp:165-167)
+  const int pxi = (int)f.px[0] / (1 << f.level), pyi = (int)f.px[1] / (1 << f.level);
+  if (!in_frame_level(cam, pxi, pyi, 6, f.level)) {
+    const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
+    jobs[i].level_mode = -1;
+    if (ok_out) { ok_out[i] = 0; px_out[2 * i] = px0; px_out[2 * i + 1] = px1; }
+    if (R) {
+      R->success = 0; R->search_level = 0; R->px_cur[0] = px0; R->px_cur[1] = px1; R->h_inv = 0;
+      for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = 0;
+      for (int k = 0; k < 100; ++k) R->patch_with_border[k] = 0;
+      for (int k = 0; k < 64; ++k) R->patch[k] = 0;
+    }
+    geom[i] = g;
+    return;
+  }
+  g.flags = 1;
+  warp_matrix_affine(cam, f.px, {f.f[0], f.f[1], f.f[2]}, depth_ref[i], f.T_cur_ref, f.level, g.A);
+  g.L = best_search_level(g.A, o.max_search_level);
+  const double det = g.A[0] * g.A[3] - g.A[2] * g.A[1];
+  const double invdet = 1.0 / det;
+  g.a00 = (float)(g.A[3] * invdet); g.a01 = (float)(-g.A[1] * invdet); g.a10 = (float)(-g.A[2] * invdet); g.a11 = (float)(g.A[0] * invdet);
+  if (!isnan(g.a00)) g.flags |= 2;
+  g.pr0 = (float)f.px[0] / (float)(1 << f.level); g.pr1 = (float)f.px[1] / (float)(1 << f.level);
+  if (f.type == 1) {
+    double dx = g.A[0] * f.grad[0] + g.A[1] * f.grad[1], dy = g.A[2] * f.grad[0] + g.A[3] * f.grad[1];
+    { const double z = dx * dx + dy * dy; if (z > 0) { const double nn = sqrt(z); dx /= nn; dy /= nn; } }
+    g.dir0 = (float)dx; g.dir1 = (float)dy;
+  }
+  if (R) { R->search_level = g.L; R->h_inv = 0; for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g.A[k]; }
+  geom[i] = g;
+}
+
 struct MatchSmem { __align__(16) uint8_t pwb[112]; };
 
-// matcher.cpp:156-194 up to the alignment call: in-frame test, affine warp matrix (lane 0, FP64), search level,
-// 10x10 patch warp by the whole warp, then the LK job.  Candidates that fail the in-frame test get their final
-// outputs here and an empty job.
-__global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n,
-                                                            const svob200_feature_ref* ftrs, const double* depth_ref,
-                                                            const double* px_in, svob200_matcher_opts o, LkJob* jobs,
-                                                            svob200_match_result* results, double* px_out, int* ok_out)
+// matcher.cpp:176-178: warpAffine of the 10x10 patch by a full warp, then the LK job (one coalesced 128-byte store)
+__global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* frames, int n, const svob200_feature_ref* ftrs,
+                                                            const double* px_in, const MatchGeom* geom, LkJob* jobs,
+                                                            svob200_match_result* results)
 {
   __shared__ MatchSmem SM[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 4 + warp;
   if (i >= n) return;
+  const MatchGeom* gp = &geom[i];
+  const int flags = gp->flags;
+  if (!(flags & 1)) return;
   MatchSmem* S = &SM[warp];
   const svob200_feature_ref* fp = &ftrs[i];
-  const int level = fp->level, type = fp->type, ref_image = fp->ref_image, cur_image = fp->cur_image;
-  const double fpx0 = fp->px[0], fpx1 = fp->px[1];
-  svob200_match_result* R = results ? &results[i] : nullptr;
-  const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
-  // ref_ftr_->px.cast<int>()/(1<<level), boundary halfpatch_size_+2 (matcher.cpp:165-167)
-  const int pxi = (int)fpx0 / (1 << level), pyi = (int)fpx1 / (1 << level);
-  if (!in_frame_level(cam, pxi, pyi, 6, level)) {
-    if (lane == 0) {
-      jobs[i].level_mode = -1;
-      if (ok_out) { ok_out[i] = 0; px_out[2 * i] = px0; px_out[2 * i + 1] = px1; }
-      if (R) { R->success = 0; R->search_level = 0; R->px_cur[0] = px0; R->px_cur[1] = px1; R->h_inv = 0; for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = 0; }
-    }
-    if (R) {
-      for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = 0;
-      for (int k = lane; k < 64; k += 32) R->patch[k] = 0;
-    }
-    return;
-  }
-  // lane 0: double-precision geometry; the float warp coefficients travel by shuffle
-  double A[4] = {0, 0, 0, 0};
-  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, dir0 = 0.f, dir1 = 0.f;
-  int L = 0, warp_ok = 0;
-  if (lane == 0) {
-    const svob200_feature_ref f = *fp;
-    warp_matrix_affine(cam, f.px, {f.f[0], f.f[1], f.f[2]}, depth_ref[i], f.T_cur_ref, f.level, A);
-    L = best_search_level(A, o.max_search_level);
-    const double det = A[0] * A[3] - A[2] * A[1];
-    const double invdet = 1.0 / det;
-    a00 = (float)(A[3] * invdet); a01 = (float)(-A[1] * invdet); a10 = (float)(-A[2] * invdet); a11 = (float)(A[0] * invdet);
-    warp_ok = isnan(a00) ? 0 : 1;
-    if (type == 1) {
-      double dx = A[0] * f.grad[0] + A[1] * f.grad[1], dy = A[2] * f.grad[0] + A[3] * f.grad[1];
-      { const double z = dx * dx + dy * dy; if (z > 0) { const double nn = sqrt(z); dx /= nn; dy /= nn; } }
-      dir0 = (float)dx; dir1 = (float)dy;
-    }
-    if (R) { R->search_level = L; R->h_inv = 0; for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = A[k]; }
-  }
-  L = __shfl_sync(0xffffffffu, L, 0); warp_ok = __shfl_sync(0xffffffffu, warp_ok, 0);
-  a00 = __shfl_sync(0xffffffffu, a00, 0); a01 = __shfl_sync(0xffffffffu, a01, 0);
-  a10 = __shfl_sync(0xffffffffu, a10, 0); a11 = __shfl_sync(0xffffffffu, a11, 0);
-  dir0 = __shfl_sync(0xffffffffu, dir0, 0); dir1 = __shfl_sync(0xffffffffu, dir1, 0);
+  const int level = fp->level, type = fp->type, ref_image = fp->ref_image, cur_image = fp->cur_image, L = gp->L;
   for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0;
   __syncwarp();
-  if (warp_ok) {
+  if (flags & 2) {
     const DevFrame& ref = frames[(int)fp->ref_frame_id];
     const uint8_t* rimg = ref.lvl[level] + (size_t)ref_image * ref.img_stride[level];
-    const float pr0 = (float)fpx0 / (float)(1 << level), pr1 = (float)fpx1 / (float)(1 << level);
-    warp_patch_10x10(rimg, ref.pitch[level], ref.w[level], ref.h[level], a00, a01, a10, a11, pr0, pr1, L, S->pwb, lane);
+    warp_patch_10x10(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, lane);
   }
   __syncwarp();
-  if (R) {
+  if (results) {
+    svob200_match_result* R = &results[i];
     for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = S->pwb[k];
     for (int k = lane; k < 64; k += 32) R->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
   }
-  emit_lk_job(&jobs[i], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), dir0, dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), lane);
+  const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
+  emit_lk_job(&jobs[i], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), gp->dir0, gp->dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), lane);
 }
 
 // stand-alone align2D / align1D on caller-provided patches: thread per problem builds the job
@@ -1020,17 +1140,31 @@ int launch_align_patches(const DevFrame* d_frames, int slot, int level, int n, c
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// Matcher::findMatchDirect for n candidates: prepare (warp per candidate) + LK (thread per candidate).
+size_t match_scratch_bytes(int n)
+{
+  const size_t m = (size_t)(n > 0 ? n : 1);
+  return up256(m * sizeof(LkJob)) + up256(m * sizeof(MatchGeom)) + 256;
+}
+
+// Matcher::findMatchDirect for n candidates: geometry (thread) -> patch warp (warp) -> LK (thread).
 // results: full records (API) or nullptr; px_out / ok_out: compact outputs (tracker) or nullptr.
+// The scratch was sized for scratch_total candidates; this call covers [first, first + n) of it (all other
+// pointers already point at candidate `first`).  marks: optional 2 events recorded between the three kernels.
 int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                         const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, svob200_match_result* d_results,
-                        double* d_px_out, int* d_ok_out, void* d_scratch, cudaStream_t s, long long* launches, cudaEvent_t* mark)
+                        double* d_px_out, int* d_ok_out, void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches,
+                        cudaEvent_t* marks)
 {
   if (n <= 0) return 0;
-  LkJob* jobs = static_cast<LkJob*>(d_scratch);
-  match_prepare_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, d_depth_ref, d_px_in, opts, jobs, d_results, d_px_out, d_ok_out);
-  ++*launches;
-  if (mark) cudaEventRecord(*mark, s);
+  const size_t m = (size_t)(scratch_total > 0 ? scratch_total : 1);
+  char* p = static_cast<char*>(d_scratch);
+  LkJob* jobs = reinterpret_cast<LkJob*>(p) + first; p += up256(m * sizeof(LkJob));
+  MatchGeom* geom = reinterpret_cast<MatchGeom*>(p) + first;
+  match_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_depth_ref, d_px_in, opts, geom, jobs, d_results, d_px_out, d_ok_out);
+  if (marks) cudaEventRecord(marks[0], s);
+  match_prepare_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, n, d_ftrs, d_px_in, geom, jobs, d_results);
+  *launches += 2;
+  if (marks) cudaEventRecord(marks[1], s);
   LkSink sink{};
   if (d_results) { sink.kind = LK_SINK_MATCH_RESULT; sink.mres = d_results; }
   else { sink.kind = LK_SINK_MATCH_COMPACT; sink.px_out = d_px_out; sink.ok_out = d_ok_out; }
@@ -1038,10 +1172,21 @@ int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& ca
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// persistent grid of the search kernel: 8 CTAs of 4 warps per SM
+static int search_grid(int n)
+{
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int want = (n + 3) / 4, cap = sms * 8;
+  return want < cap ? want : cap;
+}
+// LK jobs are compacted; a warp reserves JOB_BATCH slots at a time, so the list can exceed n by the unused tail of every warp
+static size_t job_capacity(size_t m) { return m + (size_t)JOB_BATCH * 4 * 8 * 512; }
+
 size_t epipolar_scratch_bytes(int n)
 {
   const size_t m = (size_t)(n > 0 ? n : 1);
-  return up256(m * sizeof(EpiGeom)) + up256(m * sizeof(EpiSearch)) + up256(m * sizeof(LkJob)) + 512;
+  return up256(m * sizeof(EpiCold)) + up256(m * sizeof(SearchTask)) + up256(m * sizeof(EpiSearch)) + up256(job_capacity(m) * sizeof(LkJob)) + 512;
 }
 
 int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs, const double* d_d,
@@ -1050,17 +1195,18 @@ int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, i
   if (n <= 0) return 0;
   const size_t m = (size_t)n;
   char* p = static_cast<char*>(d_scratch);
-  EpiGeom* geom = reinterpret_cast<EpiGeom*>(p); p += up256(m * sizeof(EpiGeom));
+  EpiCold* cold = reinterpret_cast<EpiCold*>(p); p += up256(m * sizeof(EpiCold));
+  SearchTask* tasks = reinterpret_cast<SearchTask*>(p); p += up256(m * sizeof(SearchTask));
   EpiSearch* search = reinterpret_cast<EpiSearch*>(p); p += up256(m * sizeof(EpiSearch));
-  LkJob* jobs = reinterpret_cast<LkJob*>(p); p += up256(m * sizeof(LkJob));
+  LkJob* jobs = reinterpret_cast<LkJob*>(p); p += up256(job_capacity(m) * sizeof(LkJob));
   int* count = reinterpret_cast<int*>(p);
-  epi_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_d, opts, geom, count);
-  epi_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, nullptr, geom, search, jobs, count, d_results);
+  epi_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_d, opts, cold, tasks, count);
+  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, search, jobs, count, d_results);
   *launches += 2;
   LkSink sink{};
   sink.kind = LK_SINK_EPI; sink.search = search;
-  if (launch_lk_refine(d_frames, cur_slot, jobs, count, n, opts.align_max_iter, sink, s, launches)) return -1;
-  epi_result_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, geom, search, d_results);
+  if (launch_lk_refine(d_frames, cur_slot, jobs, count, (int)job_capacity(m), opts.align_max_iter, sink, s, launches)) return -1;
+  epi_result_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, cold, search, d_results);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1068,10 +1214,11 @@ int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, i
 size_t seeds_scratch_bytes(int n)
 {
   const size_t m = (size_t)(n > 0 ? n : 1);
-  return up256(m * sizeof(EpiGeom)) + up256(m * sizeof(EpiSearch)) + up256(m * sizeof(SeedPre)) + up256(m * sizeof(LkJob)) + 512;
+  return up256(m * sizeof(EpiCold)) + up256(m * sizeof(SearchTask)) + up256(m * sizeof(EpiSearch)) + up256(m * sizeof(SeedPre))
+         + up256(job_capacity(m) * sizeof(LkJob)) + 512;
 }
 
-// DepthFilter::updateSeeds for n seeds: geometry (thread) -> search (warp) -> LK (thread per job) -> update (thread).
+// DepthFilter::updateSeeds for n seeds: geometry (thread) -> search (warp, persistent) -> LK (thread per job) -> update (thread).
 // marks: optional 3 events recorded between the four kernels.
 int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                         const double* d_T_ref_w, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
@@ -1083,21 +1230,22 @@ int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& ca
   if (n <= 0) return 0;
   const size_t m = (size_t)(scratch_total > 0 ? scratch_total : 1);
   char* p = static_cast<char*>(d_scratch);
-  EpiGeom* geom = reinterpret_cast<EpiGeom*>(p) + first; p += up256(m * sizeof(EpiGeom));
+  EpiCold* cold = reinterpret_cast<EpiCold*>(p) + first; p += up256(m * sizeof(EpiCold));
+  SearchTask* tasks = reinterpret_cast<SearchTask*>(p) + first; p += up256(m * sizeof(SearchTask));
   EpiSearch* search = reinterpret_cast<EpiSearch*>(p) + first; p += up256(m * sizeof(EpiSearch));
   SeedPre* pre = reinterpret_cast<SeedPre*>(p) + first; p += up256(m * sizeof(SeedPre));
-  LkJob* jobs = reinterpret_cast<LkJob*>(p) + first; p += up256(m * sizeof(LkJob));
+  LkJob* jobs = reinterpret_cast<LkJob*>(p) + first; p += up256(job_capacity(m) * sizeof(LkJob));
   int* count = reinterpret_cast<int*>(p);
-  seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, geom, count);
+  seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, cold, tasks, count);
   if (marks) cudaEventRecord(marks[0], s);
-  epi_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, cur_slot, cam, n, d_ftrs, opts, pre, geom, search, jobs, count, nullptr);
+  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, search, jobs, count, nullptr);
   if (marks) cudaEventRecord(marks[1], s);
   *launches += 2;
   LkSink sink{};
   sink.kind = LK_SINK_EPI; sink.search = search;
-  if (launch_lk_refine(d_frames, cur_slot, jobs, count, n, opts.align_max_iter, sink, s, launches)) return -1;
+  if (launch_lk_refine(d_frames, cur_slot, jobs, count, (int)job_capacity((size_t)n), opts.align_max_iter, sink, s, launches)) return -1;
   if (marks) cudaEventRecord(marks[2], s);
-  seeds_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, conv_thresh, pre, geom, search, d_seeds, d_obs);
+  seeds_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, conv_thresh, pre, cold, search, d_seeds, d_obs);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -69,10 +69,10 @@ template <class T> int dalloc(svob200_ctx* ctx, T** p, size_t n)
 
 // CUDA-event stage marks of one step (svob200_tracker_stage_ms / _stage_name): one entry per kernel of the
 // step, except that the first also covers the frame copy/bind and the small per-step input copy
-constexpr int kNumStages = 11;
+constexpr int kNumStages = 12;
 static const char* const kStageNames[kNumStages] = {"frame+pyramid", "features_prepare", "sparse_align", "reproject_prepare",
-                                                    "match_prepare", "match_refine", "seeds_geom", "seeds_search", "seeds_refine",
-                                                    "seeds_finish", "stats"};
+                                                    "match_geom", "match_prepare", "match_refine", "seeds_geom", "seeds_search",
+                                                    "seeds_refine", "seeds_finish", "stats"};
 
 struct svob200_tracker {
   svob200_ctx* ctx = nullptr;
@@ -198,7 +198,7 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
     if (int e = dalloc(ctx, &q, seeds_scratch_bytes(S))) return e;
     t->owned.push_back(q); t->d_seed_scratch = q;
     uint8_t* m = nullptr;
-    if (int e = dalloc(ctx, &m, lk_jobs_bytes(N))) return e;
+    if (int e = dalloc(ctx, &m, match_scratch_bytes(N))) return e;
     t->owned.push_back(m); t->d_match_scratch = m;
   }
 #undef DA
@@ -286,22 +286,22 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   // 5. Matcher::findMatchDirect per map point (keyframe patch -> current frame)
   // (item indices inside the call are relative to f0, so the output arrays are passed at f0 as well)
   if (launch_match_direct(ctx->d_table, cur->slot, cam, nf, t->d_ftrs + f0, t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->mopts, nullptr,
-                          t->d_px_out + 2 * (size_t)f0, t->d_match_ok + f0, static_cast<char*>(t->d_match_scratch) + 128 * (size_t)f0, s, &ctx->launches,
+                          t->d_px_out + 2 * (size_t)f0, t->d_match_ok + f0, t->d_match_scratch, t->N, f0, s, &ctx->launches,
                           (marks && t->profiling) ? &t->ev[5] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
-  MARK(6);
+  MARK(7);
   // 6. DepthFilter::updateSeeds(cur)
   if (launch_seeds_update(ctx->d_table, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
                           t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s, &ctx->launches,
-                          (marks && t->profiling) ? &t->ev[7] : nullptr))
+                          (marks && t->profiling) ? &t->ev[8] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
-  MARK(10);
+  MARK(11);
   // 7. per-sequence statistics (+ steady-state re-seeding)
   step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
                                         t->d_seeds, t->seed_init, t->reseed, t->d_stats + c0);
   ++ctx->launches;
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
-  MARK(11);
+  MARK(12);
 #undef MARK
   return 0;
 }
@@ -385,7 +385,7 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
   return SVOB200_OK;
 }
 
-int svob200_tracker_launches_per_step(void) { return 13; }
+int svob200_tracker_launches_per_step(void) { return 14; }
 
 // stage timing: CUDA events recorded on the launching stream between the kernels of a step
 int svob200_tracker_enable_profiling(svob200_tracker* t, int on)

@@ -381,11 +381,13 @@ def run_b200(args, rank, world, local_rank):
     alg = {
         "frame+pyramid": wl.B * 408000.0,
         "sparse_align": wl.B * N * (857.0 * iters_mean + 36.0 * (cfg["max_level"] - cfg["min_level"] + 1)),
-        "match_direct": wl.B * N * (400.0 + 2 * 81.0),
-        "seeds_search": wl.B * S * (400.0 + 64.0 * mean_evals + 2 * 81.0),
+        "match_prepare": wl.B * N * 400.0,                       # 100 bilinear taps of the reference patch
+        "match_refine": wl.B * N * (128.0 + 2 * 81.0),          # job record + ~2 LK iterations over a 9x9 window
+        "seeds_search": wl.B * S * (400.0 + 64.0 * mean_evals),  # patch warp + ZMSSD windows along the epipolar segment
+        "seeds_refine": wl.B * S * (128.0 + 2 * 81.0),
     }
-    kernel_of = {"frame+pyramid": "pyramid_fused_kernel", "sparse_align": "sparse_align_kernel", "match_direct": "match_direct_kernel",
-                 "seeds_search": "seeds_search_kernel"}
+    kernel_of = {"frame+pyramid": "pyramid_fused_kernel", "sparse_align": "sparse_align_kernel", "match_prepare": "match_prepare_kernel",
+                 "match_refine": "lk_refine_kernel", "seeds_search": "epi_search_kernel", "seeds_refine": "lk_refine_kernel"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

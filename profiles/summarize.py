@@ -16,8 +16,8 @@ seqs = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "..", "gpurun_out")
 STEP_KERNELS = ["pyramid_fused_kernel", "features_prepare_kernel", "init_pose_kernel", "sparse_align_kernel", "compose_poses_kernel",
-                "reproject_prepare_kernel", "match_direct_kernel", "seeds_geom_kernel", "seeds_search_kernel", "seeds_refine_kernel",
-                "seeds_finish_kernel", "step_stats_kernel"]
+                "reproject_prepare_kernel", "match_geom_kernel", "match_prepare_kernel", "match_direct_kernel", "seeds_geom_kernel",
+                "seeds_search_kernel", "epi_search_kernel", "lk_refine_kernel", "seeds_finish_kernel", "step_stats_kernel"]
 
 
 def short(name):
