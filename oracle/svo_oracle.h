@@ -141,6 +141,39 @@ int svo_oracle_update_seed_with_frame(const svo_pyr* ref, const svo_pyr* cur, co
                                       const svo_matcher_opts* o, double seed_convergence_sigma2_thresh,
                                       svo_seed* s, svo_epi_result* epi_out /* may be NULL */);
 
+/* ==================================================================== SURVEY §8f "next" rows (svo_oracle_map.c) */
+
+/* ---- f1: Reprojector::reprojectMap (reprojector.cpp:72-259) ---- */
+enum { SVO_POINT_DELETED = 0, SVO_POINT_CANDIDATE = 1, SVO_POINT_UNKNOWN = 2, SVO_POINT_GOOD = 3 };   /* point.h PointType */
+enum { SVO_REPROJ_NOT_IN_FRAME = 0, SVO_REPROJ_UNTRIED = 1, SVO_REPROJ_DELETED = 2, SVO_REPROJ_FAILED = 3, SVO_REPROJ_MATCHED = 4 };
+typedef struct { double pos[3]; int type; int obs_begin, obs_end; } svo_map_point;
+typedef struct { int keyframe; svo_ref_feature ftr; } svo_point_obs;          /* Feature of Point::obs_, in its keyframe */
+typedef struct { int status, cell, obs, search_level; double px[2]; double A_cur_ref[4]; } svo_reproj_result;
+void svo_oracle_frame_pos(const double T_f_w[7], double pos[3]);               /* Frame::pos() frame.h:105 */
+int  svo_oracle_reproject_map(const svo_pyr* const* ref_pyrs, const svo_pyr* cur, const svo_cam* cam, const double T_cur_w[7],
+                              int n_points, const svo_map_point* points, const svo_point_obs* obs, const double* T_kf_w,
+                              int cell_size, int max_fts, const svo_matcher_opts* mopts, svo_reproj_result* results,
+                              int* cell_winner, int* n_matches_out, int* n_trials_out);
+
+/* ---- f2: pose_optimizer::optimizeGaussNewton (pose_optimizer.cpp:31-181), Point::optimize (point.cpp:130-192) ---- */
+typedef struct { double A[36]; double chi2, estimated_scale, error_init, error_final; int iters, num_obs, rolled_back; } svo_pose_opt_result;
+void svo_oracle_pose_optimize(const svo_cam* cam, int n, const double* f, const int* level, const double* pos, double reproj_thresh,
+                              int n_iter, double eps, float tukey_b, double T_f_w[7], svo_pose_opt_result* res, uint8_t* outlier);
+int  svo_oracle_point_optimize(int n_obs, const double* T_f_w, const double* f, int n_iter, double eps, double pos[3]);
+
+/* ---- f3: camera input stage (../image_process.cpp:97-186, ../svo_system.cpp:49-51) ---- */
+void svo_oracle_yuv420_to_rgba(const uint8_t* y, int y_stride, const uint8_t* u, const uint8_t* v, int uv_stride, int uv_pixel_stride,
+                               int w, int h, uint8_t* rgba);
+void svo_oracle_rgba_to_gray(const uint8_t* rgba, int w, int h, uint8_t* gray);
+void svo_oracle_yuv420_to_gray(const uint8_t* y, int y_stride, const uint8_t* u, const uint8_t* v, int uv_stride, int uv_pixel_stride,
+                               int w, int h, uint8_t* gray);
+
+/* ---- f4: DepthFilter::initializeSeeds (depth_filter.cpp:129-151) ---- */
+void svo_oracle_grid_occupancy(const svo_cam* cam, int cell_size, int n, const double* px, uint8_t* occupancy);
+int  svo_oracle_initialize_seeds(const svo_pyr* pyr, const svo_cam* cam, int n_detect_levels, int cell_size, double thr,
+                                 int n_existing, const double* existing_px, float depth_mean, float depth_min,
+                                 svo_corner* corners_out, svo_seed* seeds_out);
+
 #ifdef __cplusplus
 }
 #endif
