@@ -41,7 +41,7 @@ def build(force=False):
     src_newer = False
     if not need:
         so_t = os.path.getmtime(os.path.join(OUT, "libsvo_oracle.so"))
-        for f in ("svo_oracle.c", "svo_oracle.h", "svo_cpu_pipeline.c"):
+        for f in ("svo_oracle.c", "svo_oracle.h", "svo_cpu_pipeline.c", "svo_oracle_map.c"):
             if os.path.getmtime(os.path.join(HERE, f)) > so_t:
                 src_newer = True
     if need or src_newer:
@@ -50,7 +50,7 @@ def build(force=False):
         ref_so = os.path.join(OUT, "libsvo_ref.so")
         stale = not os.path.exists(ref_so) or any(
             os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(ref_so)
-            for f in ("ref_harness.cpp", "shim/cv_fast.cpp", "shim/opencv2/opencv.hpp", "svo_oracle.c"))
+            for f in ("ref_harness.cpp", "ref_harness_map.cpp", "shim/cv_fast.cpp", "shim/opencv2/opencv.hpp", "svo_oracle.c"))
         if force or stale:
             subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
         # the same harness over the C++ drop-in (needs the product library to link against)

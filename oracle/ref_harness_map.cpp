@@ -48,7 +48,7 @@ typedef svo::DepthFilter DepthFilterBase;
 #endif
 struct SeedProbe : public DepthFilterBase {
   SeedProbe(feature_detection::DetectorPtr d, callback_t cb) : DepthFilterBase(d, cb) {}
-  std::list<Seed, aligned_allocator<Seed> >& seeds() { return seeds_; }
+  std::list<Seed>& seeds() { return seeds_; }
   void init(FramePtr f, double mean, double min) { new_keyframe_mean_depth_ = mean; new_keyframe_min_depth_ = min; initializeSeeds(f); }
 };
 
@@ -80,7 +80,7 @@ int svo_ref_reproject_map(int n_kf, const uint8_t* const* kf_imgs, const double*
   vk::PinholeCamera* cam = new vk::PinholeCamera(wh[0], wh[1], k[0], k[1], k[2], k[3]);
   int n_new = 0;
   {
-    Map map;
+    svo::Map map;
     std::vector<FramePtr> kfs;
     for (int i = 0; i < n_kf; ++i) {
       FramePtr f(new Frame(cam, mat_copy(kf_imgs[i], wh[0], wh[1]), (double)i));
@@ -94,7 +94,7 @@ int svo_ref_reproject_map(int n_kf, const uint8_t* const* kf_imgs, const double*
     for (int i = 0; i < n_points; ++i) {
       Point* p = new Point(Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
       pts[i] = p;
-      for (int o = obs_begin[i]; o < obs_end[i]; ++o) {
+      for (int o = obs_end[i] - 1; o >= obs_begin[i]; --o) {   // Point::addFrameRef pushes to the FRONT of obs_ (point.cpp:61-65)
         Feature* ftr = new Feature(kfs[obs_kf[o]].get(), Vector2d(obs_px[2 * o], obs_px[2 * o + 1]), obs_level[o]);
         ftr->type = obs_type[o] ? Feature::EDGELET : Feature::CORNER;
         ftr->grad = Vector2d(obs_grad[2 * o], obs_grad[2 * o + 1]);
@@ -179,7 +179,7 @@ void svo_ref_point_optimize(const int* wh, const double* k, const uint8_t* img, 
     std::vector<FramePtr> frames;
     Point pt(Vector3d(pos[0], pos[1], pos[2]));
     std::vector<Feature*> fs;
-    for (int i = 0; i < n_obs; ++i) {
+    for (int i = n_obs - 1; i >= 0; --i) {      // addFrameRef pushes to the front: obs_ ends up in array order
       FramePtr fr(new Frame(cam, mat_copy(img, wh[0], wh[1]), (double)i));
       fr->T_f_w_ = to_se3(T_f_w + 7 * i);
       frames.push_back(fr);
