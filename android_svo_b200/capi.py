@@ -58,6 +58,20 @@ step_stats_dt = np.dtype([("T_cur_w", "f8", 7), ("chi2", "f8"), ("n_tracked", "i
 seed_obs_dt = np.dtype([("status", "i4"), ("search_level", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"), ("z", "f8"),
                         ("px_cur", "f8", 2), ("epi_length", "f8")], align=True)
 
+map_point_dt = np.dtype([("pos", "f8", 3), ("type", "i4"), ("obs_begin", "i4"), ("obs_end", "i4"), ("reserved", "i4")], align=True)
+reproj_result_dt = np.dtype([("status", "i4"), ("cell", "i4"), ("obs", "i4"), ("search_level", "i4"), ("px", "f8", 2),
+                             ("A_cur_ref", "f8", 4)], align=True)
+reproj_stats_dt = np.dtype([("n_matches", "i4"), ("n_trials", "i4"), ("n_in_frame", "i4"), ("n_cells", "i4")], align=True)
+pose_opt_result_dt = np.dtype([("A", "f8", 36), ("chi2", "f8"), ("estimated_scale", "f8"), ("error_init", "f8"), ("error_final", "f8"),
+                               ("iters", "i4"), ("num_obs", "i4"), ("rolled_back", "i4"), ("reserved", "i4")], align=True)
+POINT_DELETED, POINT_CANDIDATE, POINT_UNKNOWN, POINT_GOOD = 0, 1, 2, 3
+REPROJ_NOT_IN_FRAME, REPROJ_UNTRIED, REPROJ_DELETED, REPROJ_FAILED, REPROJ_MATCHED = 0, 1, 2, 3, 4
+
+
+class PoseOptOpts(C.Structure):
+    _fields_ = [("reproj_thresh", C.c_double), ("n_iter", C.c_int), ("eps", C.c_double), ("tukey_b", C.c_float)]
+
+
 _lib = None
 
 
@@ -126,6 +140,13 @@ def load_library():
     L.svob200_warp_affine.argtypes = [V, V, C.c_int, C.c_int, C.c_int, V, V, C.c_int, C.c_int, C.c_int, V]
     L.svob200_depth_from_triangulation.argtypes = [V, C.c_int, V, V, V, V, V]
     L.svob200_synth_render.argtypes = [V, V, C.c_int, C.c_double, C.c_double, C.POINTER(Camera), C.c_int, V, V]
+    L.svob200_frame_upload_yuv420.argtypes = [V, C.c_int64, V, C.c_int, V, V, C.c_int, C.c_int, C.c_size_t, C.c_size_t, c_ip, C.c_int]
+    L.svob200_reproject_map.argtypes = [V, C.c_int64, C.POINTER(Camera), C.c_int, V, V, C.c_int, V, C.c_int, V, V, C.c_int, C.c_int,
+                                        C.POINTER(MatcherOpts), V, V, V, C.c_int]
+    L.svob200_pose_opt_opts_default.argtypes = [C.POINTER(PoseOptOpts)]
+    L.svob200_pose_optimize.argtypes = [V, C.POINTER(Camera), C.c_int, V, V, V, V, C.POINTER(PoseOptOpts), V, V, V, C.c_int]
+    L.svob200_points_optimize.argtypes = [V, C.c_int, V, V, V, C.c_int, C.c_double, V, V, C.c_int]
+    L.svob200_seeds_initialize.argtypes = [V, C.c_int64, C.c_int, C.c_int, C.c_double, V, V, V, V, V, V, V, C.c_int]
     _lib = L
     return L
 
@@ -145,6 +166,8 @@ EXPORTED_SYMBOLS = [
     "svob200_tracker_num_stages", "svob200_tracker_stage_name",
     "svob200_frame_upload_level", "svob200_shi_tomasi", "svob200_warp_matrix_affine", "svob200_warp_affine",
     "svob200_depth_from_triangulation",
+    "svob200_frame_upload_yuv420", "svob200_reproject_map", "svob200_pose_opt_opts_default", "svob200_pose_optimize",
+    "svob200_points_optimize", "svob200_seeds_initialize",
 ]
 
 
@@ -289,6 +312,73 @@ class Context:
                                               _ptr(px), _ptr(conv), _ptr(h_inv), MEM_HOST))
         return conv, px.reshape(n, 2), h_inv
 
+    # ---- callers either side of the hot path
+    def frame_upload_yuv420(self, fid, y, u, v, y_stride, uv_stride, uv_pixel_stride, y_image_stride=0, uv_image_stride=0,
+                            round_modes=None, mem=MEM_HOST):
+        """y/u/v: host uint8 arrays (u, v may be overlapping views of one interleaved buffer) or device addresses"""
+        modes = np.ascontiguousarray(round_modes, dtype=np.int32) if round_modes is not None else None
+        self._ck(self.L.svob200_frame_upload_yuv420(self.h, fid, _ptr(y), int(y_stride), _ptr(u), _ptr(v), int(uv_stride), int(uv_pixel_stride),
+                                                    int(y_image_stride), int(uv_image_stride),
+                                                    modes.ctypes.data_as(c_ip) if modes is not None else None, mem))
+
+    def reproject_map(self, cur_fid, cam, T_cur_w, point_offsets, points, obs, T_obs_w, cell, max_fts, opts):
+        T_cur_w = np.ascontiguousarray(T_cur_w, dtype=np.float64).reshape(-1, 7)
+        batch = len(T_cur_w)
+        off = np.ascontiguousarray(point_offsets, dtype=np.int32)
+        points = np.ascontiguousarray(points, dtype=map_point_dt)
+        obs = np.ascontiguousarray(obs, dtype=feature_ref_dt)
+        T_obs_w = np.ascontiguousarray(T_obs_w, dtype=np.float64)
+        n_cells = -(-cam.width // cell) * -(-cam.height // cell)
+        res = np.zeros(len(points), reproj_result_dt)
+        winner = np.zeros((batch, n_cells), np.int32)
+        stats = np.zeros(batch, reproj_stats_dt)
+        self._ck(self.L.svob200_reproject_map(self.h, cur_fid, C.byref(cam), batch, _ptr(T_cur_w), _ptr(off), len(points), _ptr(points),
+                                              len(obs), _ptr(obs), _ptr(T_obs_w), int(cell), int(max_fts), C.byref(opts), _ptr(res),
+                                              _ptr(winner), _ptr(stats), MEM_HOST))
+        return res, winner, stats
+
+    def pose_opt_opts(self, **kw):
+        o = PoseOptOpts()
+        self.L.svob200_pose_opt_opts_default(C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def pose_optimize(self, cam, ftr_offsets, f, level, pos, T_f_w, opts=None):
+        off = np.ascontiguousarray(ftr_offsets, dtype=np.int32)
+        batch = len(off) - 1
+        f = np.ascontiguousarray(f, dtype=np.float64); pos = np.ascontiguousarray(pos, dtype=np.float64)
+        level = np.ascontiguousarray(level, dtype=np.int32)
+        T = np.ascontiguousarray(T_f_w, dtype=np.float64).reshape(batch, 7).copy()
+        res = np.zeros(batch, pose_opt_result_dt)
+        outl = np.zeros(max(len(level), 1), np.uint8)
+        opts = opts or self.pose_opt_opts()
+        self._ck(self.L.svob200_pose_optimize(self.h, C.byref(cam), batch, _ptr(off), _ptr(f), _ptr(level), _ptr(pos), C.byref(opts), _ptr(T),
+                                              _ptr(res), _ptr(outl), MEM_HOST))
+        return T, res, outl[:len(level)]
+
+    def points_optimize(self, obs_offsets, T_f_w, f, pos, n_iter=20, eps=1e-10):
+        off = np.ascontiguousarray(obs_offsets, dtype=np.int32)
+        n = len(off) - 1
+        T = np.ascontiguousarray(T_f_w, dtype=np.float64); f = np.ascontiguousarray(f, dtype=np.float64)
+        p = np.ascontiguousarray(pos, dtype=np.float64).reshape(n, 3).copy()
+        it = np.zeros(n, np.int32)
+        self._ck(self.L.svob200_points_optimize(self.h, n, _ptr(off), _ptr(T), _ptr(f), int(n_iter), float(eps), _ptr(p), _ptr(it), MEM_HOST))
+        return p, it
+
+    def seeds_initialize(self, fid, n_detect_levels, cell, thr, existing_offsets, existing_px, depth_mean, depth_min):
+        batch, w, h, _ = self.frame_info(fid)
+        n_cells = -(-w // cell) * -(-h // cell)
+        off = np.ascontiguousarray(existing_offsets, dtype=np.int32)
+        epx = np.ascontiguousarray(existing_px, dtype=np.float64)
+        dm = np.ascontiguousarray(depth_mean, dtype=np.float32); dn = np.ascontiguousarray(depth_min, dtype=np.float32)
+        corners = np.zeros((batch, n_cells), corner_dt)
+        seeds = np.zeros((batch, n_cells), seed_dt)
+        counts = np.zeros(batch, np.int32)
+        self._ck(self.L.svob200_seeds_initialize(self.h, fid, int(n_detect_levels), int(cell), float(thr), _ptr(off), _ptr(epx), _ptr(dm), _ptr(dn),
+                                                 _ptr(corners), _ptr(seeds), _ptr(counts), MEM_HOST))
+        return corners, seeds, counts
+
     # ---- matcher
     def matcher_opts(self, n_pyr_levels, **kw):
         o = MatcherOpts()
@@ -363,11 +453,12 @@ class Context:
 def abi_sizes():
     """(C sizeof, numpy/ctypes sizeof) pairs for every struct crossing the ABI."""
     L = load_library()
-    buf = (C.c_int * 16)()
-    n = L.svob200_abi_sizes(buf, 16)
+    buf = (C.c_int * 32)()
+    n = L.svob200_abi_sizes(buf, 32)
     mine = [C.sizeof(Camera), corner_dt.itemsize, C.sizeof(AlignOpts), align_result_dt.itemsize, C.sizeof(MatcherOpts),
             feature_ref_dt.itemsize, match_result_dt.itemsize, epi_result_dt.itemsize, seed_dt.itemsize, seed_obs_dt.itemsize,
-            step_stats_dt.itemsize]
+            step_stats_dt.itemsize, map_point_dt.itemsize, reproj_result_dt.itemsize, reproj_stats_dt.itemsize,
+            pose_opt_result_dt.itemsize, C.sizeof(PoseOptOpts)]
     return list(buf[:n]), mine
 
 

@@ -137,7 +137,9 @@ int svob200_abi_sizes(int* sizes, int cap)
   const int v[] = {(int)sizeof(svob200_camera), (int)sizeof(svob200_corner), (int)sizeof(svob200_align_opts),
                    (int)sizeof(svob200_align_result), (int)sizeof(svob200_matcher_opts), (int)sizeof(svob200_feature_ref),
                    (int)sizeof(svob200_match_result), (int)sizeof(svob200_epi_result), (int)sizeof(svob200_seed),
-                   (int)sizeof(svob200_seed_obs), (int)sizeof(svob200_step_stats)};
+                   (int)sizeof(svob200_seed_obs), (int)sizeof(svob200_step_stats), (int)sizeof(svob200_map_point),
+                   (int)sizeof(svob200_reproj_result), (int)sizeof(svob200_reproj_stats), (int)sizeof(svob200_pose_opt_result),
+                   (int)sizeof(svob200_pose_opt_opts)};
   const int n = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < cap; ++i) sizes[i] = v[i];
   return n;
@@ -681,6 +683,207 @@ int svob200_depth_from_triangulation(svob200_ctx* ctx, int n, const double* T_se
   if (int e = st.push()) return e;
   if (launch_triangulate(n, st.dev<double>(i_T), st.dev<double>(i_a), st.dev<double>(i_b), st.dev<double>(i_d), st.dev<int>(i_o), ctx->stream, &ctx->launches))
     return fail(ctx, SVOB200_ERR_CUDA, "depth_from_triangulation launch failed");
+  return st.download();
+}
+
+// ------------------------------------------------------------------ camera input stage
+int svob200_frame_upload_yuv420(svob200_ctx* ctx, int64_t frame_id, const uint8_t* y, int y_stride, const uint8_t* u, const uint8_t* v,
+                                int uv_stride, int uv_pixel_stride, size_t y_image_stride, size_t uv_image_stride, const int* round_modes, int mem)
+{
+  if (!ctx || !y || !u || !v) return fail(ctx, SVOB200_ERR_ARG, "frame_upload_yuv420: null argument");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  const int w = r->f.w[0], h = r->f.h[0], B = r->f.batch;
+  if (y_stride < w || uv_pixel_stride < 1 || uv_pixel_stride > 2) return fail(ctx, SVOB200_ERR_ARG, "frame_upload_yuv420: bad strides");
+  const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+  const int uv_row_bytes = (cw - 1) * uv_pixel_stride + 1;
+  if (uv_stride < uv_row_bytes) return fail(ctx, SVOB200_ERR_ARG, "frame_upload_yuv420: uv_stride too small");
+  if (r->f.lvl[0] != r->own_l0) {                       // level 0 is produced here: undo a previous bind
+    r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
+    CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  YuvPlanes P;
+  if (mem == SVOB200_MEM_DEVICE) {
+    P.y = y; P.u = u; P.v = v; P.y_stride = y_stride; P.uv_stride = uv_stride; P.uv_pixel_stride = uv_pixel_stride;
+    P.y_img_stride = y_image_stride; P.uv_img_stride = uv_image_stride;
+  } else {
+    // stage the planes: Y with a 16-byte pitch; chroma either as ONE interleaved window (u, v are views of the same
+    // buffer, pixel stride 2) or as two planes
+    const bool inter = uv_pixel_stride == 2 && (u == v + 1 || v == u + 1);
+    const size_t ypitch = (size_t)align_up_i(w, 16), cpitch = (size_t)align_up_i(inter ? 2 * cw : uv_row_bytes, 16);
+    const size_t ybytes = ypitch * h * B, cbytes = cpitch * ch * B;
+    const size_t total = ybytes + (inter ? cbytes : 2 * cbytes) + 64;
+    if (ctx->d_stage.ensure(total) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "frame_upload_yuv420: staging alloc failed");
+    uint8_t* dy = static_cast<uint8_t*>(ctx->d_stage.p);
+    uint8_t* dc0 = dy + ybytes;
+    uint8_t* dc1 = dc0 + cbytes;
+    for (int b = 0; b < B; ++b) {
+      CU(cudaMemcpy2DAsync(dy + (size_t)b * ypitch * h, ypitch, y + (size_t)b * y_image_stride, y_stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+      if (inter) {
+        const uint8_t* base = (u < v ? u : v) + (size_t)b * uv_image_stride;
+        // the second plane's last sample sits one byte past 2*cw - 1 only when it is the +1 view: 2*cw bytes cover both
+        CU(cudaMemcpy2DAsync(dc0 + (size_t)b * cpitch * ch, cpitch, base, uv_stride, std::min((size_t)2 * cw, (size_t)uv_stride), ch, cudaMemcpyHostToDevice, ctx->stream));
+      } else {
+        CU(cudaMemcpy2DAsync(dc0 + (size_t)b * cpitch * ch, cpitch, u + (size_t)b * uv_image_stride, uv_stride, uv_row_bytes, ch, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpy2DAsync(dc1 + (size_t)b * cpitch * ch, cpitch, v + (size_t)b * uv_image_stride, uv_stride, uv_row_bytes, ch, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    }
+    P.y = dy; P.y_stride = (int)ypitch; P.y_img_stride = ypitch * h;
+    P.uv_stride = (int)cpitch; P.uv_pixel_stride = uv_pixel_stride; P.uv_img_stride = cpitch * ch;
+    if (inter) { P.u = dc0 + (u > v ? 1 : 0); P.v = dc0 + (v > u ? 1 : 0); }
+    else { P.u = dc0; P.v = dc1; }
+  }
+  int modes[SVOB200_MAX_LEVELS];
+  for (int l = 0; l + 1 < r->f.n_levels; ++l) modes[l] = round_modes ? round_modes[l] : svob200_round_mode_x86(r->f.w[l]);
+  if (launch_pyramid_yuv(r->f, P, modes, ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "yuv pyramid launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (mem == SVOB200_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
+// ------------------------------------------------------------------ reprojector
+int svob200_reproject_map(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int batch, const double* T_cur_w,
+                          const int* point_offsets, int n_points, const svob200_map_point* points, int n_obs, const svob200_feature_ref* obs,
+                          const double* T_obs_w, int cell_size, int max_fts, const svob200_matcher_opts* opts, svob200_reproj_result* results,
+                          int* cell_winner, svob200_reproj_stats* stats, int mem)
+{
+  if (!ctx || !cam || batch <= 0 || !T_cur_w || !point_offsets || n_points < 0 || n_obs < 0 || !opts || !results || !cell_winner || !stats || cell_size <= 0)
+    return fail(ctx, SVOB200_ERR_ARG, "reproject_map: bad arguments");
+  if (n_points > 0 && (!points || !obs || !T_obs_w)) return fail(ctx, SVOB200_ERR_ARG, "reproject_map: null point / observation arrays");
+  FrameRec* cur = find_frame(ctx, cur_frame_id);
+  if (!cur) return fail(ctx, SVOB200_ERR_NOFRAME, "reproject_map: current frame not resident");
+  if (batch != cur->f.batch) return fail(ctx, SVOB200_ERR_ARG, "reproject_map: batch differs from the frame's");
+  if (opts->max_search_level >= cur->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "reproject_map: max_search_level outside the pyramid");
+  const int gc = (cam->width + cell_size - 1) / cell_size, gr = (cam->height + cell_size - 1) / cell_size;
+  const size_t n_cells = (size_t)gc * gr;
+  Stage st(ctx, mem);
+  const int i_T = st.add(T_cur_w, nullptr, sizeof(double) * 7 * batch, 0);
+  const int i_off = st.add(point_offsets, nullptr, sizeof(int) * (batch + 1), 0);
+  const int i_p = st.add(points, nullptr, sizeof(svob200_map_point) * n_points, 0);
+  const int i_o = st.add(obs, nullptr, sizeof(svob200_feature_ref) * n_obs, 0);
+  const int i_To = st.add(T_obs_w, nullptr, sizeof(double) * 7 * n_obs, 0);
+  const int i_r = st.add(nullptr, results, sizeof(svob200_reproj_result) * n_points, 2);
+  const int i_w = st.add(nullptr, cell_winner, sizeof(int) * n_cells * batch, 2);
+  const int i_s = st.add(nullptr, stats, sizeof(svob200_reproj_stats) * batch, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (mem == SVOB200_MEM_HOST && n_obs > 0) if (int e = resolve_slots(ctx, st.host<svob200_feature_ref>(i_o), n_obs)) return e;
+  if (int e = st.push()) return e;
+  if (ctx->d_scratch.ensure(match_scratch_bytes(n_points)) != cudaSuccess || ctx->d_scratch2.ensure(reproject_scratch_bytes(n_points)) != cudaSuccess)
+    return fail(ctx, SVOB200_ERR_NOMEM, "reproject_map: scratch alloc failed");
+  const int rc = launch_reproject_map(ctx->d_table, cur->slot, to_cam(cam), batch, st.dev<double>(i_T), st.dev<int>(i_off), n_points,
+                                      st.dev<svob200_map_point>(i_p), st.dev<svob200_feature_ref>(i_o), st.dev<double>(i_To), cell_size, max_fts,
+                                      *opts, st.dev<svob200_reproj_result>(i_r), st.dev<int>(i_w), st.dev<svob200_reproj_stats>(i_s),
+                                      ctx->d_scratch2.p, ctx->d_scratch.p, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->stream, &ctx->launches);
+  if (rc == -2) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "reproject_map: grid of %zu cells exceeds the kernel's table (8192)", n_cells);
+  if (rc) return fail(ctx, SVOB200_ERR_CUDA, "reproject_map launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+// ------------------------------------------------------------------ pose / structure optimisation
+void svob200_pose_opt_opts_default(svob200_pose_opt_opts* o)
+{
+  o->reproj_thresh = 2.0;      // Config::poseOptimThresh (config.cpp)
+  o->n_iter = 10;              // Config::poseOptimNumIter
+  o->eps = 0.0000000001;       // svo::EPS global.h:91
+  o->tukey_b = 8.6851f;        // TukeyWeightFunction::DEFAULT_B robust_cost.cpp:87
+}
+
+int svob200_pose_optimize(svob200_ctx* ctx, const svob200_camera* cam, int batch, const int* ftr_offsets, const double* f, const int* level,
+                          const double* pos, const svob200_pose_opt_opts* opts, double* T_f_w, svob200_pose_opt_result* results,
+                          uint8_t* outlier, int mem)
+{
+  if (!ctx || !cam || batch <= 0 || !ftr_offsets || !opts || !T_f_w || !results) return fail(ctx, SVOB200_ERR_ARG, "pose_optimize: bad arguments");
+  int n = 0;
+  if (mem == SVOB200_MEM_HOST) n = ftr_offsets[batch];
+  else { CU(cudaMemcpyAsync(&n, ftr_offsets + batch, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
+  if (n < 0 || (n > 0 && (!f || !level || !pos || !outlier))) return fail(ctx, SVOB200_ERR_ARG, "pose_optimize: null feature arrays");
+  Stage st(ctx, mem);
+  const int i_off = st.add(ftr_offsets, nullptr, sizeof(int) * (batch + 1), 0);
+  const int i_f = st.add(f, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_l = st.add(level, nullptr, sizeof(int) * n, 0);
+  const int i_p = st.add(pos, nullptr, sizeof(double) * 3 * n, 0);
+  const int i_T = st.add(T_f_w, T_f_w, sizeof(double) * 7 * batch, 1);
+  const int i_r = st.add(nullptr, results, sizeof(svob200_pose_opt_result) * batch, 2);
+  const int i_o = st.add(nullptr, outlier, (size_t)n, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (ctx->d_scratch.ensure(sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "pose_optimize: scratch alloc failed");
+  const int* d_off = st.dev<int>(i_off);
+  if (launch_pose_optimize(to_cam(cam), batch, d_off, d_off + 1, st.dev<double>(i_f), st.dev<int>(i_l), st.dev<double>(i_p), opts->reproj_thresh,
+                           opts->n_iter, opts->eps, opts->tukey_b, st.dev<double>(i_T), st.dev<svob200_pose_opt_result>(i_r), st.dev<uint8_t>(i_o),
+                           static_cast<double*>(ctx->d_scratch.p), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "pose_optimize launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+int svob200_points_optimize(svob200_ctx* ctx, int n, const int* obs_offsets, const double* T_f_w, const double* f, int n_iter, double eps,
+                            double* pos, int* iters_out, int mem)
+{
+  if (!ctx || n < 0 || !obs_offsets || !pos) return fail(ctx, SVOB200_ERR_ARG, "points_optimize: bad arguments");
+  if (n == 0) return SVOB200_OK;
+  int m = 0;
+  if (mem == SVOB200_MEM_HOST) m = obs_offsets[n];
+  else { CU(cudaMemcpyAsync(&m, obs_offsets + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
+  if (m < 0 || (m > 0 && (!T_f_w || !f))) return fail(ctx, SVOB200_ERR_ARG, "points_optimize: null observation arrays");
+  Stage st(ctx, mem);
+  const int i_off = st.add(obs_offsets, nullptr, sizeof(int) * (n + 1), 0);
+  const int i_T = st.add(T_f_w, nullptr, sizeof(double) * 7 * m, 0);
+  const int i_f = st.add(f, nullptr, sizeof(double) * 3 * m, 0);
+  const int i_p = st.add(pos, pos, sizeof(double) * 3 * n, 1);
+  const int i_it = iters_out ? st.add(nullptr, iters_out, sizeof(int) * n, 2) : -1;
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_points_optimize(n, st.dev<int>(i_off), st.dev<double>(i_T), st.dev<double>(i_f), n_iter, eps, st.dev<double>(i_p),
+                             iters_out ? st.dev<int>(i_it) : nullptr, ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "points_optimize launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return st.download();
+}
+
+// ------------------------------------------------------------------ seed initialisation
+int svob200_seeds_initialize(svob200_ctx* ctx, int64_t frame_id, int n_detect_levels, int cell_size, double thr, const int* existing_offsets,
+                             const double* existing_px, const float* depth_mean, const float* depth_min, svob200_corner* corners_out,
+                             svob200_seed* seeds_out, int* counts, int mem)
+{
+  if (!ctx || cell_size <= 0 || !existing_offsets || !depth_mean || !depth_min || !corners_out || !seeds_out || !counts)
+    return fail(ctx, SVOB200_ERR_ARG, "seeds_initialize: bad arguments");
+  FrameRec* r = find_frame(ctx, frame_id);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (n_detect_levels < 1 || n_detect_levels > r->f.n_levels) return fail(ctx, SVOB200_ERR_ARG, "seeds_initialize: n_detect_levels out of range");
+  if (r->f.w[0] >= 16384 || r->f.h[0] >= 16384) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "seeds_initialize: image larger than 16383");
+  const int B = r->f.batch;
+  const int gc = (r->f.w[0] + cell_size - 1) / cell_size, gr = (r->f.h[0] + cell_size - 1) / cell_size;
+  const size_t n_cells = (size_t)gc * gr, total = n_cells * B;
+  int n = 0, max_per = 0;
+  if (mem == SVOB200_MEM_HOST) { n = existing_offsets[B]; for (int b = 0; b < B; ++b) max_per = std::max(max_per, existing_offsets[b + 1] - existing_offsets[b]); }
+  else { CU(cudaMemcpyAsync(&n, existing_offsets + B, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); max_per = n; }
+  if (n < 0 || (n > 0 && !existing_px)) return fail(ctx, SVOB200_ERR_ARG, "seeds_initialize: null existing_px");
+  Stage st(ctx, mem);
+  const int i_off = st.add(existing_offsets, nullptr, sizeof(int) * (B + 1), 0);
+  const int i_px = st.add(existing_px, nullptr, sizeof(double) * 2 * n, 0);
+  const int i_dm = st.add(depth_mean, nullptr, sizeof(float) * B, 0);
+  const int i_dn = st.add(depth_min, nullptr, sizeof(float) * B, 0);
+  const int i_c = st.add(nullptr, corners_out, sizeof(svob200_corner) * total, 2);
+  const int i_s = st.add(nullptr, seeds_out, sizeof(svob200_seed) * total, 2);
+  const int i_n = st.add(nullptr, counts, sizeof(int) * B, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  // scratch: cell keys (8 B) | cell records | occupancy | detector counts
+  const size_t need = total * 8 + total * sizeof(svob200_corner) + ((total + 255) & ~(size_t)255) + sizeof(int) * B + 1024;
+  if (ctx->d_scratch.ensure(need) != cudaSuccess) return fail(ctx, SVOB200_ERR_NOMEM, "seeds_initialize: scratch alloc failed");
+  unsigned long long* d_keys = static_cast<unsigned long long*>(ctx->d_scratch.p);
+  svob200_corner* d_cells = reinterpret_cast<svob200_corner*>(d_keys + total);
+  uint8_t* d_occ = reinterpret_cast<uint8_t*>(d_cells + total);
+  int* d_cnt = reinterpret_cast<int*>(d_occ + ((total + 255) & ~(size_t)255));
+  CU(cudaMemsetAsync(d_occ, 0, total, ctx->stream));
+  if (launch_occupancy(B, max_per, st.dev<int>(i_off), st.dev<double>(i_px), cell_size, gc, (int)n_cells, d_occ, ctx->stream, &ctx->launches) ||
+      launch_fast_detect(r->f, n_detect_levels, cell_size, gc, gr, thr, d_occ, d_keys, d_cells, d_cnt, ctx->stream, &ctx->launches) ||
+      launch_seeds_compact(B, d_cells, (int)n_cells, thr, st.dev<float>(i_dm), st.dev<float>(i_dn), st.dev<svob200_corner>(i_c),
+                           st.dev<svob200_seed>(i_s), st.dev<int>(i_n), ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "seeds_initialize launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return st.download();
 }
 

@@ -6,6 +6,13 @@ struct AlignProblemDev;   // sparse_align.cu
 
 // pyramid.cu
 int launch_pyramid(const DevFrame& f, const int* modes, cudaStream_t s, long long* launches);
+// camera planes as AImage hands them out (../image_process.cpp:151-186): strides in bytes, image strides for batches
+struct YuvPlanes {
+  const uint8_t *y = nullptr, *u = nullptr, *v = nullptr;
+  int y_stride = 0, uv_stride = 0, uv_pixel_stride = 1;
+  unsigned long long y_img_stride = 0, uv_img_stride = 0;
+};
+int launch_pyramid_yuv(const DevFrame& f, const YuvPlanes& yuv, const int* modes, cudaStream_t s, long long* launches);
 int launch_half_sample_single(const uint8_t* in, int in_pitch, int w, int h, uint8_t* out, int out_pitch, int mode,
                               cudaStream_t s, long long* launches);
 
@@ -36,7 +43,8 @@ size_t match_scratch_bytes(int n);
 int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                         const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, svob200_match_result* d_results,
                         double* d_px_out, int* d_ok_out, void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches,
-                        cudaEvent_t* marks = nullptr);
+                        cudaEvent_t* marks = nullptr, const uint8_t* d_active = nullptr /* per-candidate mask */,
+                        int* d_level_out = nullptr, double* d_A_out = nullptr /* search level and A_cur_ref (4) per candidate */);
 size_t epipolar_scratch_bytes(int n);
 int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs, const double* d_d,
                     svob200_matcher_opts opts, svob200_epi_result* d_results, void* d_scratch, cudaStream_t s, long long* launches);
@@ -48,6 +56,25 @@ int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& ca
 int launch_update_seed(int n, const float* d_x, const float* d_tau2, svob200_seed* d_seeds, cudaStream_t s, long long* launches);
 int launch_compute_tau(int n, const double* d_T, const double* d_f, const double* d_z, double angle, double* d_out,
                        cudaStream_t s, long long* launches);
+
+// map_ops.cu — reprojector, pose optimizer, point optimizer
+size_t reproject_scratch_bytes(int n_points);
+// returns -2 when the grid has more cells than the kernel's shared-memory table
+int launch_reproject_map(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int batch, const double* d_T_cur_w, const int* d_pt_off,
+                         int n_points, const svob200_map_point* d_points, const svob200_feature_ref* d_obs, const double* d_T_obs_w,
+                         int cell_size, int max_fts, svob200_matcher_opts opts, svob200_reproj_result* d_results, int* d_cell_winner,
+                         svob200_reproj_stats* d_stats, void* d_scratch, void* d_match_scratch,
+                         double* d_m_f, int* d_m_level, double* d_m_pos, int* d_m_point, int* d_m_count,   // optional compacted matches
+                         cudaStream_t s, long long* launches);
+int launch_pose_optimize(const DevCam& cam, int batch, const int* d_seg_begin, const int* d_seg_end, const double* d_f, const int* d_level,
+                         const double* d_pos, double reproj_thresh, int n_iter, double eps, float tukey_b, double* d_T_io,
+                         svob200_pose_opt_result* d_results, uint8_t* d_outlier, double* d_work, cudaStream_t s, long long* launches);
+int launch_points_optimize(int n, const int* d_obs_off, const double* d_T_f_w, const double* d_f, int n_iter, double eps, double* d_pos_io,
+                           int* d_iters, cudaStream_t s, long long* launches);
+int launch_occupancy(int batch, int max_per_image, const int* d_off, const double* d_px, int cell_size, int grid_cols, int n_cells, uint8_t* d_occ,
+                     cudaStream_t s, long long* launches);
+int launch_seeds_compact(int batch, const svob200_corner* d_cells, int n_cells, double thr, const float* d_depth_mean, const float* d_depth_min,
+                         svob200_corner* d_corners_out, svob200_seed* d_seeds_out, int* d_counts, cudaStream_t s, long long* launches);
 
 // synth.cu
 int launch_synth_render(const uint8_t* d_tex, int tex_size, double ppm, double plane_z, const DevCam& cam, int batch,

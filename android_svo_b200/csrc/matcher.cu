@@ -967,19 +967,25 @@ struct MatchGeom {
 // outputs here and an empty job.
 __global__ void __launch_bounds__(128) match_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* depth_ref,
                                                          const double* px_in, svob200_matcher_opts o, MatchGeom* geom, LkJob* jobs,
-                                                         svob200_match_result* results, double* px_out, int* ok_out)
+                                                         svob200_match_result* results, double* px_out, int* ok_out,
+                                                         const uint8_t* active, int* level_out, double* A_out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const svob200_feature_ref f = ftrs[i];
   MatchGeom g;
   g.A[0] = g.A[1] = g.A[2] = g.A[3] = 0; g.a00 = g.a01 = g.a10 = g.a11 = g.pr0 = g.pr1 = g.dir0 = g.dir1 = 0.f; g.L = 0; g.flags = 0;
   svob200_match_result* R = results ? &results[i] : nullptr;
+  // candidates the caller masked out (reprojector: not in frame / no close view, matcher.cpp:161-162) fail without work;
+  // their feature record is not read
+  const bool is_active = !active || active[i];
+  svob200_feature_ref f;
+  if (is_active) f = ftrs[i]; else { f.level = 0; f.px[0] = f.px[1] = -1.0; }
   // ref_ftr_->px.cast<int>()/(1<<level), boundary halfpatch_size_+2 (matcher.cpp:165-167)
   const int pxi = (int)f.px[0] / (1 << f.level), pyi = (int)f.px[1] / (1 << f.level);
-  if (!in_frame_level(cam, pxi, pyi, 6, f.level)) {
+  if (!is_active || !in_frame_level(cam, pxi, pyi, 6, f.level)) {
     const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
     jobs[i].level_mode = -1;
+    if (level_out) { level_out[i] = 0; for (int k = 0; k < 4; ++k) A_out[4 * (size_t)i + k] = 0.0; }
     if (ok_out) { ok_out[i] = 0; px_out[2 * i] = px0; px_out[2 * i + 1] = px1; }
     if (R) {
       R->success = 0; R->search_level = 0; R->px_cur[0] = px0; R->px_cur[1] = px1; R->h_inv = 0;
@@ -1004,6 +1010,7 @@ __global__ void __launch_bounds__(128) match_geom_kernel(DevCam cam, int n, cons
     g.dir0 = (float)dx; g.dir1 = (float)dy;
   }
   if (R) { R->search_level = g.L; R->h_inv = 0; for (int k = 0; k < 4; ++k) R->A_cur_ref[k] = g.A[k]; }
+  if (level_out) { level_out[i] = g.L; for (int k = 0; k < 4; ++k) A_out[4 * (size_t)i + k] = g.A[k]; }
   geom[i] = g;
 }
 
@@ -1153,14 +1160,15 @@ size_t match_scratch_bytes(int n)
 int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                         const double* d_depth_ref, const double* d_px_in, svob200_matcher_opts opts, svob200_match_result* d_results,
                         double* d_px_out, int* d_ok_out, void* d_scratch, int scratch_total, int first, cudaStream_t s, long long* launches,
-                        cudaEvent_t* marks)
+                        cudaEvent_t* marks, const uint8_t* d_active, int* d_level_out, double* d_A_out)
 {
   if (n <= 0) return 0;
   const size_t m = (size_t)(scratch_total > 0 ? scratch_total : 1);
   char* p = static_cast<char*>(d_scratch);
   LkJob* jobs = reinterpret_cast<LkJob*>(p) + first; p += up256(m * sizeof(LkJob));
   MatchGeom* geom = reinterpret_cast<MatchGeom*>(p) + first;
-  match_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_depth_ref, d_px_in, opts, geom, jobs, d_results, d_px_out, d_ok_out);
+  match_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_depth_ref, d_px_in, opts, geom, jobs, d_results, d_px_out, d_ok_out,
+                                                    d_active, d_level_out, d_A_out);
   if (marks) cudaEventRecord(marks[0], s);
   match_prepare_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, n, d_ftrs, d_px_in, geom, jobs, d_results);
   *launches += 2;

@@ -47,9 +47,84 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p)
   return r;
 }
 
+// ---------------------------------------------------------------- camera input stage
+// YUV_420_888 -> RGBA (ImageProcess::GetCVImage / YUV2RGB, ../image_process.cpp:97-186) -> gray
+// (cv::cvtColor(COLOR_RGBA2GRAY), ../svo_system.cpp:49-51; OpenCV 4.x RGB2Gray<uchar>: 15-bit fixed point on the
+// channels in MEMORY order, i.e. c0 = the app's B, c1 = G, c2 = R).  Integer, bit-exact.  The chroma terms are
+// shared by the 2x2 pixels of a chroma sample.
+struct ChromaTerms { int rv, guv, bu; };
+__device__ __forceinline__ ChromaTerms chroma_terms(int u, int v)
+{
+  const int nU = u - 128, nV = v - 128;
+  return {1634 * nV, -833 * nV - 400 * nU, 2066 * nU};
+}
+__device__ __forceinline__ uint32_t yuv_gray1(int y, const ChromaTerms& c)
+{
+  const int yy = 1192 * max(y - 16, 0);
+  const int r = min(max(yy + c.rv, 0), 262143) >> 10;
+  const int g = min(max(yy + c.guv, 0), 262143) >> 10;
+  const int b = min(max(yy + c.bu, 0), 262143) >> 10;
+  return (uint32_t)((b * 9798 + g * 19235 + r * 3735 + (1 << 14)) >> 15);
+}
+// 16 bytes starting at p (any alignment); bytes at index >= valid are not read (returned as 0)
+__device__ __forceinline__ uint4 load16_any(const uint8_t* p, int valid)
+{
+  if (valid >= 16 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return ldg_stream(reinterpret_cast<const uint4*>(p));
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 16 && k < valid; ++k) w[k >> 2] |= (uint32_t)__ldg(p + k) << (8 * (k & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ int byte_of(const uint4& q, int k)
+{
+  const uint32_t w = k < 4 ? q.x : (k < 8 ? q.y : (k < 12 ? q.z : q.w));
+  return (int)((w >> (8 * (k & 3))) & 0xffu);
+}
+// gray of 16 pixels of the row pair (y0, y0+1) starting at even x0; the planes as AImage hands them out
+__device__ __forceinline__ void yuv_rows16(const YuvPlanes& s, int b, int x0, int y0, int w, int h, uint4& g0, uint4& g1)
+{
+  const int valid = min(16, w - x0);
+  const uint8_t* py = s.y + (size_t)b * s.y_img_stride + (size_t)y0 * s.y_stride + x0;
+  const uint4 ya = load16_any(py, valid);
+  const uint4 yb = (y0 + 1 < h) ? load16_any(py + s.y_stride, valid) : make_uint4(0, 0, 0, 0);
+  const size_t uvo = (size_t)b * s.uv_img_stride + (size_t)(y0 >> 1) * s.uv_stride + (size_t)(x0 >> 1) * s.uv_pixel_stride;
+  const int nc = (valid + 1) >> 1;                 // chroma samples needed
+  int cu[8], cv[8];
+  if (s.uv_pixel_stride == 2 && (s.u == s.v + 1 || s.v == s.u + 1)) {
+    // interleaved chroma (NV21 / NV12 views): one 16-byte window holds both planes
+    const bool v_first = s.u == s.v + 1;
+    const uint8_t* base = (v_first ? s.v : s.u) + uvo;
+    const uint4 q = load16_any(base, 2 * nc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int a = byte_of(q, 2 * k), c = byte_of(q, 2 * k + 1); cu[k] = v_first ? c : a; cv[k] = v_first ? a : c; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool in = k < nc;
+      cu[k] = in ? (int)__ldg(s.u + uvo + (size_t)k * s.uv_pixel_stride) : 128;
+      cv[k] = in ? (int)__ldg(s.v + uvo + (size_t)k * s.uv_pixel_stride) : 128;
+    }
+  }
+  uint32_t o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const ChromaTerms c = chroma_terms(cu[k], cv[k]);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * k + e;
+      o0[i >> 2] |= yuv_gray1(byte_of(ya, i), c) << (8 * (i & 3));
+      o1[i >> 2] |= yuv_gray1(byte_of(yb, i), c) << (8 * (i & 3));
+    }
+  }
+  g0 = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+  g1 = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+}
+
 // One CTA = one 64x64 level-0 tile of one image; 128 threads.
 // Thread t: 16-pixel segment (t&3) of row pair (t>>2).
-__global__ void __launch_bounds__(128) pyramid_fused_kernel(DevFrame f, int modes_mask)
+// YUV = true: level 0 is PRODUCED here from the camera's YUV planes (and written once) instead of being read,
+// so the input stage costs no extra pass over the frame.
+template <bool YUV>
+__global__ void __launch_bounds__(128) pyramid_fused_kernel(DevFrame f, int modes_mask, YuvPlanes yuv)
 {
   __shared__ __align__(16) uint8_t s_a[32 * 32];
   __shared__ __align__(16) uint8_t s_b[16 * 16];
@@ -65,10 +140,26 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(DevFrame f, int mode
     const int x1 = x0 >> 1, y1 = y0 >> 1;
     uint32_t o0 = 0, o1 = 0;
     const bool act = (y1 < h1) && (x0 < f.pitch[0]) && (x1 < w1);
+    if (YUV && !act && y0 < f.h[0] && x0 < f.w[0]) {
+      // odd last row / column that the half-sampling drops: level 0 still has to be produced
+      uint4 g0, g1;
+      yuv_rows16(yuv, b, x0, y0, f.w[0], f.h[0], g0, g1);
+      uint8_t* l0 = f.lvl[0] + (size_t)b * f.img_stride[0] + (size_t)y0 * f.pitch[0] + x0;
+      *reinterpret_cast<uint4*>(l0) = g0;
+      if (y0 + 1 < f.h[0]) *reinterpret_cast<uint4*>(l0 + f.pitch[0]) = g1;
+    }
     if (act) {
-      const uint8_t* base = f.lvl[0] + (size_t)b * f.img_stride[0] + (size_t)y0 * f.pitch[0] + x0;
-      const uint4 r0 = ldg_stream(reinterpret_cast<const uint4*>(base));
-      const uint4 r1 = ldg_stream(reinterpret_cast<const uint4*>(base + f.pitch[0]));
+      uint4 r0, r1;
+      if (YUV) {
+        yuv_rows16(yuv, b, x0, y0, f.w[0], f.h[0], r0, r1);
+        uint8_t* l0 = f.lvl[0] + (size_t)b * f.img_stride[0] + (size_t)y0 * f.pitch[0] + x0;
+        *reinterpret_cast<uint4*>(l0) = r0;                  // pitch is a multiple of 16: the tail lands in the padding
+        *reinterpret_cast<uint4*>(l0 + f.pitch[0]) = r1;
+      } else {
+        const uint8_t* base = f.lvl[0] + (size_t)b * f.img_stride[0] + (size_t)y0 * f.pitch[0] + x0;
+        r0 = ldg_stream(reinterpret_cast<const uint4*>(base));
+        r1 = ldg_stream(reinterpret_cast<const uint4*>(base + f.pitch[0]));
+      }
       if (modes_mask & 1) {
         o0 = half4_sse2(r0.x, r0.y, r1.x, r1.y);
         o1 = half4_sse2(r0.z, r0.w, r1.z, r1.w);
@@ -144,18 +235,54 @@ __global__ void half_sample_generic_kernel(const uint8_t* in, int in_pitch, unsi
   out[(size_t)blockIdx.z * out_img_stride + (size_t)y * out_pitch + x] = (uint8_t)half1(a, b, c, d, mode);
 }
 
+// stand-alone input stage (frames the fused kernel does not take: odd level widths, > 7 levels, 1 level)
+__global__ void __launch_bounds__(128) yuv_gray_kernel(DevFrame f, YuvPlanes yuv)
+{
+  const int b = blockIdx.z;
+  const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 16, y0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * 2;
+  if (x0 >= f.w[0] || y0 >= f.h[0]) return;
+  uint4 g0, g1;
+  yuv_rows16(yuv, b, x0, y0, f.w[0], f.h[0], g0, g1);
+  uint8_t* l0 = f.lvl[0] + (size_t)b * f.img_stride[0] + (size_t)y0 * f.pitch[0] + x0;
+  *reinterpret_cast<uint4*>(l0) = g0;
+  if (y0 + 1 < f.h[0]) *reinterpret_cast<uint4*>(l0 + f.pitch[0]) = g1;
+}
+
 }  // namespace
+
+static bool fused_ok(const DevFrame& f)
+{
+  bool odd = false;
+  for (int l = 0; l + 1 < f.n_levels; ++l) odd |= (f.w[l] & 1) != 0;
+  return !odd && f.n_levels >= 2 && f.n_levels <= 7;
+}
+
+// level 0 from YUV planes (+ all coarser levels); level 0 must be owned storage with a 16-byte pitch
+int launch_pyramid_yuv(const DevFrame& f, const YuvPlanes& yuv, const int* modes, cudaStream_t s, long long* launches)
+{
+  if (fused_ok(f)) {
+    int mask = 0;
+    for (int l = 0; l + 1 < f.n_levels; ++l) if (modes[l] == SVOB200_ROUND_SSE2) mask |= 1 << l;
+    dim3 grid((f.w[0] + 63) / 64, (f.h[0] + 63) / 64, f.batch);
+    pyramid_fused_kernel<true><<<grid, 128, 0, s>>>(f, mask, yuv);
+    ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+  dim3 grid((f.w[0] + 511) / 512, (f.h[0] + 7) / 8, f.batch);
+  yuv_gray_kernel<<<grid, 128, 0, s>>>(f, yuv);
+  ++*launches;
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  return launch_pyramid(f, modes, s, launches);
+}
 
 int launch_pyramid(const DevFrame& f, const int* modes, cudaStream_t s, long long* launches)
 {
   if (f.n_levels <= 1) return 0;
-  bool odd = false;
-  for (int l = 0; l + 1 < f.n_levels; ++l) odd |= (f.w[l] & 1) != 0;
-  if (!odd && f.n_levels <= 7) {
+  if (fused_ok(f)) {
     int mask = 0;
     for (int l = 0; l + 1 < f.n_levels; ++l) if (modes[l] == SVOB200_ROUND_SSE2) mask |= 1 << l;
     dim3 grid((f.w[0] + 63) / 64, (f.h[0] + 63) / 64, f.batch);
-    pyramid_fused_kernel<<<grid, 128, 0, s>>>(f, mask);
+    pyramid_fused_kernel<false><<<grid, 128, 0, s>>>(f, mask, YuvPlanes{});
     ++*launches;
   } else {
     for (int l = 0; l + 1 < f.n_levels; ++l) {

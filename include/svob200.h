@@ -52,7 +52,8 @@ int         svob200_ctx_timer_start(svob200_ctx* ctx);
 int         svob200_ctx_timer_stop_ms(svob200_ctx* ctx, float* ms);
 
 /* sizeof() of the ABI structs in declaration order (camera, corner, align_opts, align_result,
- * matcher_opts, feature_ref, match_result, epi_result, seed, seed_obs); returns how many there are */
+ * matcher_opts, feature_ref, match_result, epi_result, seed, seed_obs, step_stats, map_point, reproj_result,
+ * reproj_stats, pose_opt_result, pose_opt_opts); returns how many there are */
 int         svob200_abi_sizes(int* sizes, int cap);
 
 /* ---------------------------------------------------------------- frames / pyramid
@@ -280,6 +281,77 @@ int  svob200_tracker_num_stages(void);
 const char* svob200_tracker_stage_name(int i);
 int  svob200_tracker_stage_ms(svob200_tracker* t, float* ms, int cap);
 int  svob200_tracker_get_seed_obs(svob200_tracker* t, svob200_seed_obs* out /*host*/);
+
+/* ================================================================ callers either side of the hot path
+ * (SURVEY.md §8f "next" rows; same conventions: POD, mem = HOST | DEVICE, int status) */
+
+/* ---------------------------------------------------------------- camera input stage
+ * replaces: ImageProcess::GetCVImage + YUV2RGB (../image_process.cpp:97-186: YUV_420_888 -> RGBA, integer) followed by
+ *           cv::cvtColor(img, COLOR_RGBA2GRAY) (../svo_system.cpp:49-51; OpenCV 4.5.4 imgproc, 15-bit fixed point) and
+ *           Frame::initFrame -> createImgPyramid (frame.cpp:51-64, :186-195).
+ * One fused kernel reads the planes once, writes level 0 (gray) once and every coarser level once.
+ * y/u/v, strides and pixel stride are what AImage_getPlaneData / getPlaneRowStride / getPlanePixelStride return
+ * (u, v may be views into one interleaved buffer, pixel stride 2).  Image b of a batch starts y_image_stride /
+ * uv_image_stride bytes after image b-1 (ignored for batch 1).  Crop rect = whole image. */
+int svob200_frame_upload_yuv420(svob200_ctx* ctx, int64_t frame_id, const uint8_t* y, int y_stride, const uint8_t* u,
+                                const uint8_t* v, int uv_stride, int uv_pixel_stride, size_t y_image_stride,
+                                size_t uv_image_stride, const int* round_modes, int mem);
+
+/* ---------------------------------------------------------------- reprojector
+ * replaces: Reprojector::reprojectMap / reprojectCell / reprojectPoint (reprojector.cpp:72-259) incl. Point::getCloseViewObs
+ *           (point.cpp:101-125) and Matcher::findMatchDirect per candidate.
+ * The caller flattens its map the way reprojectMap walks it (features of the close keyframes in closeness order, each
+ * point once, then the point candidates): points of image b are points[point_offsets[b] .. point_offsets[b+1]) in that
+ * insertion order; observation k of a point is obs[k] (ref_frame_id / ref_image / level / type / px / f / grad are read;
+ * cur_image and T_cur_ref are ignored) seen from the keyframe pose T_obs_w[7k..], in Point::obs_ list order.
+ * The per-point status tells the caller which side effects the reference would have applied:
+ *   FAILED  -> ++n_failed_reproj_ (and the deletion rules, :204-208)    MATCHED -> ++n_succeeded_reproj_, new Feature
+ *   DELETED -> the candidate was met and erased (:190-194)              UNTRIED -> in a cell, never reached
+ * cell_winner: batch * n_cells point indices (-1 = none), n_cells = ceil(W/cell)*ceil(H/cell); the new features of the
+ * frame are the winners in cell order.  stats: one record per image (n_matches_ / n_trials_). */
+enum { SVOB200_POINT_DELETED = 0, SVOB200_POINT_CANDIDATE = 1, SVOB200_POINT_UNKNOWN = 2, SVOB200_POINT_GOOD = 3 };   /* point.h */
+enum { SVOB200_REPROJ_NOT_IN_FRAME = 0, SVOB200_REPROJ_UNTRIED = 1, SVOB200_REPROJ_DELETED = 2, SVOB200_REPROJ_FAILED = 3,
+       SVOB200_REPROJ_MATCHED = 4 };
+typedef struct { double pos[3]; int type; int obs_begin, obs_end; int reserved; } svob200_map_point;
+typedef struct { int status, cell, obs, search_level; double px[2]; double A_cur_ref[4]; } svob200_reproj_result;
+typedef struct { int n_matches, n_trials, n_in_frame, n_cells; } svob200_reproj_stats;
+int svob200_reproject_map(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_camera* cam, int batch, const double* T_cur_w,
+                          const int* point_offsets, int n_points, const svob200_map_point* points, int n_obs,
+                          const svob200_feature_ref* obs, const double* T_obs_w, int cell_size, int max_fts,
+                          const svob200_matcher_opts* opts, svob200_reproj_result* results, int* cell_winner,
+                          svob200_reproj_stats* stats, int mem);
+
+/* ---------------------------------------------------------------- pose / structure optimisation
+ * replaces: pose_optimizer::optimizeGaussNewton (pose_optimizer.cpp:31-181) with vk::robust_cost::MADScaleEstimator and
+ *           TukeyWeightFunction (robust_cost.cpp), one problem per image of the batch: features of image b are
+ *           [ftr_offsets[b], ftr_offsets[b+1]) with bearing f (3), pyramid level and world point pos (3).
+ *           T_f_w: 7 doubles per image, in/out.  outlier[i] = 1 where the reference resets ftr->point (:149-153).
+ *           Frame::Cov_ = (A * errorMultiplier2^2)^-1 is left to the caller (A is returned). */
+typedef struct {
+  double A[36];            /* normal matrix of the last linearisation, row-major */
+  double chi2, estimated_scale, error_init, error_final;
+  int iters, num_obs, rolled_back, reserved;
+} svob200_pose_opt_result;
+typedef struct { double reproj_thresh; int n_iter; double eps; float tukey_b; } svob200_pose_opt_opts;
+void svob200_pose_opt_opts_default(svob200_pose_opt_opts* o);   /* Config::poseOptimThresh 2.0, poseOptimNumIter 10, EPS, DEFAULT_B */
+int svob200_pose_optimize(svob200_ctx* ctx, const svob200_camera* cam, int batch, const int* ftr_offsets, const double* f,
+                          const int* level, const double* pos, const svob200_pose_opt_opts* opts, double* T_f_w,
+                          svob200_pose_opt_result* results, uint8_t* outlier, int mem);
+/* replaces: Point::optimize (point.cpp:130-192) for n points (FrameHandlerBase::optimizeStructure picks them,
+ *           frame_handler_base.cpp:190-210): observations of point i are [obs_offsets[i], obs_offsets[i+1]) with the
+ *           observing frame's pose T_f_w (7) and bearing f (3), in Point::obs_ list order.  pos: 3 per point, in/out. */
+int svob200_points_optimize(svob200_ctx* ctx, int n, const int* obs_offsets, const double* T_f_w, const double* f,
+                            int n_iter, double eps, double* pos, int* iters_out /* may be NULL */, int mem);
+
+/* ---------------------------------------------------------------- seed initialisation
+ * replaces: DepthFilter::initializeSeeds (depth_filter.cpp:129-151): AbstractDetector::setExistingFeatures
+ *           (feature_detection.cpp:40-58), FastDetector::detect, one Seed (depth_filter.cpp:36-45) per new corner.
+ * existing_px: level-0 pixels of the frame's features, image b owns [existing_offsets[b], existing_offsets[b+1]).
+ * depth_mean / depth_min: one per image.  Outputs are compacted in cell order: image b writes counts[b] entries at
+ * [b * n_cells, ...). */
+int svob200_seeds_initialize(svob200_ctx* ctx, int64_t frame_id, int n_detect_levels, int cell_size, double detection_threshold,
+                             const int* existing_offsets, const double* existing_px, const float* depth_mean,
+                             const float* depth_min, svob200_corner* corners_out, svob200_seed* seeds_out, int* counts, int mem);
 
 /* ---------------------------------------------------------------- device-side helpers for the
  * resident ("value") path and the synthetic bench: raw device allocations and a plane renderer.

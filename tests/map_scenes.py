@@ -156,13 +156,14 @@ def yuv_frame(w, h, seed, uv_pixel_stride=2, pad=0):
     y = rng.randint(0, 256, (h, ys)).astype(np.uint8)
     # smooth-ish luma so the gray image is not pure noise, but keep full range incl. < 16 and > 235
     y[:, :w] = np.clip((np.add.outer(np.arange(h) * 255 // max(h - 1, 1), np.arange(w) * 64 // max(w - 1, 1)) // 1 + rng.randint(-40, 40, (h, w))), 0, 255)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
     if uv_pixel_stride == 2:
-        uvs = w + pad
-        buf = rng.randint(0, 256, (h // 2) * uvs + 1).astype(np.uint8)
+        uvs = 2 * cw + pad
+        buf = rng.randint(0, 256, ch * uvs + 1).astype(np.uint8)
         v = buf[:-1]          # V first (NV21): v[o], u = v + 1
         u = buf[1:]
     else:
-        uvs = w // 2 + pad
-        u = rng.randint(0, 256, (h // 2) * uvs).astype(np.uint8)
-        v = rng.randint(0, 256, (h // 2) * uvs).astype(np.uint8)
+        uvs = cw + pad
+        u = rng.randint(0, 256, ch * uvs).astype(np.uint8)
+        v = rng.randint(0, 256, ch * uvs).astype(np.uint8)
     return dict(y=y, y_stride=ys, u=u, v=v, uv_stride=uvs, uv_pixel_stride=uv_pixel_stride, w=w, h=h)
