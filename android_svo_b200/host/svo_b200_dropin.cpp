@@ -23,8 +23,14 @@
 #include <svo/sparse_img_align.h>
 #include <svo/matcher.h>
 #include <svo/depth_filter.h>
+#include <svo/map.h>
+#include <svo/reprojector.h>
+#include <svo/pose_optimizer.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <deque>
+#include <list>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -666,5 +672,245 @@ void B200DepthFilter::updateSeeds(FramePtr frame)
     }
   }
 }
+
+
+// ============================================================================ reprojector.h: Reprojector
+// Linked INSTEAD OF reprojector.cpp.  The walk over the map that decides WHICH points are candidates (close keyframes by
+// distance, one projection per point, the candidate list under its mutex: reprojector.cpp:76-146) is host control plane
+// and stays here; the geometry, the grid, every findMatchDirect and the per-cell / maxFts rules run on the device in one
+// svob200_reproject_map call; the side effects on Point / Map / Frame are applied afterwards in the reference's order.
+Reprojector::Reprojector(vk::AbstractCamera* cam, Map& map) : map_(map) { initializeGrid(cam); }
+
+Reprojector::~Reprojector() { std::for_each(grid_.cells.begin(), grid_.cells.end(), [&](Cell* c) { delete c; }); }
+
+void Reprojector::initializeGrid(vk::AbstractCamera* cam)      // reprojector.cpp:43-54 (the cell lists stay empty: the grid lives on the device)
+{
+  grid_.cell_size = Config::gridSize();
+  grid_.grid_n_cols = ceil(static_cast<double>(cam->width()) / grid_.cell_size);
+  grid_.grid_n_rows = ceil(static_cast<double>(cam->height()) / grid_.cell_size);
+  grid_.cells.resize(grid_.grid_n_cols * grid_.grid_n_rows);
+  std::for_each(grid_.cells.begin(), grid_.cells.end(), [&](Cell*& c) { c = new Cell; });
+  grid_.cell_order.resize(grid_.cells.size());
+  for (size_t i = 0; i < grid_.cells.size(); ++i) grid_.cell_order[i] = i;
+}
+
+void Reprojector::resetGrid()
+{
+  n_matches_ = 0;
+  n_trials_ = 0;
+  std::for_each(grid_.cells.begin(), grid_.cells.end(), [&](Cell* c) { c->clear(); });
+}
+
+bool Reprojector::pointQualityComparator(Candidate& lhs, Candidate& rhs) { return lhs.pt->type_ > rhs.pt->type_; }
+bool Reprojector::reprojectCell(Cell&, FramePtr) { return false; }       // the cell loop runs on the device
+bool Reprojector::reprojectPoint(FramePtr, Point*) { return false; }     // the projection runs on the device
+
+void Reprojector::reprojectMap(FramePtr frame, std::vector<std::pair<FramePtr, std::size_t> >& overlap_kfs)
+{
+  resetGrid();
+  // ---- which points (host, reprojector.cpp:78-119 and :125-131)
+  std::list<std::pair<FramePtr, double> > close_kfs;
+  map_.getCloseKeyframes(frame, close_kfs);
+  close_kfs.sort([](const std::pair<FramePtr, double>& l, const std::pair<FramePtr, double>& r) { return l.second < r.second; });
+  std::vector<Point*> pts;
+  std::vector<int> owner;                       // index into overlap_kfs, -1 for point candidates
+  size_t n = 0;
+  overlap_kfs.reserve(options_.max_n_kfs);
+  for (auto it_frame = close_kfs.begin(), ite_frame = close_kfs.end(); it_frame != ite_frame && n < options_.max_n_kfs; ++it_frame, ++n) {
+    FramePtr ref_frame = it_frame->first;
+    overlap_kfs.push_back(std::pair<FramePtr, size_t>(ref_frame, 0));
+    for (auto it_ftr = ref_frame->fts_.begin(), ite_ftr = ref_frame->fts_.end(); it_ftr != ite_ftr; ++it_ftr) {
+      if ((*it_ftr)->point == NULL) continue;
+      if ((*it_ftr)->point->last_projected_kf_id_ == frame->id_) continue;
+      (*it_ftr)->point->last_projected_kf_id_ = frame->id_;
+      pts.push_back((*it_ftr)->point);
+      owner.push_back((int)overlap_kfs.size() - 1);
+    }
+  }
+  std::unique_lock<std::mutex> cand_lock(map_.point_candidates_.mut_);
+  const size_t n_map = pts.size();
+  for (auto it = map_.point_candidates_.candidates_.begin(); it != map_.point_candidates_.candidates_.end(); ++it) { pts.push_back(it->first); owner.push_back(-1); }
+  const int n_points = (int)pts.size();
+  const int n_cells = grid_.grid_n_cols * grid_.grid_n_rows;
+  std::vector<svob200_reproj_result> res(n_points);
+  std::vector<int> winner(n_cells, -1);
+  svob200_reproj_stats stats = {0, 0, 0, 0};
+  std::vector<Feature*> obs_ftr;
+  if (n_points > 0) {
+    // ---- flat records: points in insertion order, observations in Point::obs_ list order
+    std::vector<svob200_map_point> mp(n_points);
+    std::vector<svob200_feature_ref> obs;
+    std::vector<double> T_obs;
+    Lock lk(rt().mu);
+    svob200_ctx* ctx = ctx_locked();
+    const int64_t cur_id = b200::ensure_frame_locked(*frame);
+    const SE3 ident;
+    for (int i = 0; i < n_points; ++i) {
+      Point* p = pts[i];
+      mp[i].pos[0] = p->pos_[0]; mp[i].pos[1] = p->pos_[1]; mp[i].pos[2] = p->pos_[2];
+      mp[i].type = (int)p->type_; mp[i].obs_begin = (int)obs.size(); mp[i].reserved = 0;
+      for (auto o = p->obs_.begin(); o != p->obs_.end(); ++o) {
+        svob200_feature_ref f;
+        fill_feature_ref(**o, b200::ensure_frame_locked(*(*o)->frame), ident, &f);
+        obs.push_back(f);
+        double T[7];
+        b200::pose7((*o)->frame->T_f_w_, T);
+        T_obs.insert(T_obs.end(), T, T + 7);
+        obs_ftr.push_back(*o);
+      }
+      mp[i].obs_end = (int)obs.size();
+    }
+    const svob200_camera cam = b200::camera_of(frame->cam_);
+    svob200_matcher_opts mo;
+    b200::matcher_opts_of(matcher_.options_, &mo);
+    double T_cur[7];
+    b200::pose7(frame->T_f_w_, T_cur);
+    const int off[2] = {0, n_points};
+    check(svob200_reproject_map(ctx, cur_id, &cam, 1, T_cur, off, n_points, mp.data(), (int)obs.size(), obs.data(), T_obs.data(),
+                                grid_.cell_size, (int)Config::maxFts(), &mo, res.data(), winner.data(), &stats, SVOB200_MEM_HOST),
+          "svob200_reproject_map");
+  }
+  // ---- side effects, in the reference's order
+  for (size_t i = 0; i < n_map; ++i)
+    if (res[i].status != SVOB200_REPROJ_NOT_IN_FRAME) overlap_kfs[owner[i]].second++;                   // :116-117
+  {
+    size_t i = n_map;
+    auto it = map_.point_candidates_.candidates_.begin();
+    while (it != map_.point_candidates_.candidates_.end()) {                                            // :129-144
+      const bool in_frame = res[i++].status != SVOB200_REPROJ_NOT_IN_FRAME;
+      if (!in_frame) {
+        it->first->n_failed_reproj_ += 3;
+        if (it->first->n_failed_reproj_ > 30) {
+          map_.point_candidates_.deleteCandidate(*it);
+          it = map_.point_candidates_.candidates_.erase(it);
+          continue;
+        }
+      }
+      ++it;
+    }
+  }
+  cand_lock.unlock();
+  // tried candidates of every visited cell, in trial order (type descending, then insertion order: :184)
+  std::vector<std::vector<int> > tried(n_cells);
+  for (int i = 0; i < n_points; ++i)
+    if (res[i].status == SVOB200_REPROJ_DELETED || res[i].status == SVOB200_REPROJ_FAILED || res[i].status == SVOB200_REPROJ_MATCHED)
+      tried[res[i].cell].push_back(i);
+  std::vector<int> type0(n_points);
+  for (int i = 0; i < n_points; ++i) type0[i] = (int)pts[i]->type_;
+  for (int c = 0; c < n_cells; ++c) {
+    std::vector<int>& t = tried[c];
+    std::stable_sort(t.begin(), t.end(), [&](int a, int b) { return type0[a] > type0[b]; });
+    for (int i : t) {
+      Point* pt = pts[i];
+      ++n_trials_;
+      if (res[i].status == SVOB200_REPROJ_DELETED) continue;                                            // :190-194
+      if (res[i].status == SVOB200_REPROJ_FAILED) {                                                     // :202-211
+        pt->n_failed_reproj_++;
+        if (pt->type_ == Point::TYPE_UNKNOWN && pt->n_failed_reproj_ > 15) map_.safeDeletePoint(pt);
+        if (pt->type_ == Point::TYPE_CANDIDATE && pt->n_failed_reproj_ > 30) map_.point_candidates_.deleteCandidatePoint(pt);
+        continue;
+      }
+      pt->n_succeeded_reproj_++;                                                                        // :214-231
+      if (pt->type_ == Point::TYPE_UNKNOWN && pt->n_succeeded_reproj_ > 10) pt->type_ = Point::TYPE_GOOD;
+      Vector2d px(res[i].px[0], res[i].px[1]);
+      Feature* new_feature = new Feature(frame.get(), px, res[i].search_level);
+      frame->addFeature(new_feature);
+      new_feature->point = pt;
+      Feature* ref_ftr = obs_ftr[res[i].obs];
+      if (ref_ftr->type == Feature::EDGELET) {
+        Matrix2d A;
+        A << res[i].A_cur_ref[0], res[i].A_cur_ref[1], res[i].A_cur_ref[2], res[i].A_cur_ref[3];
+        new_feature->type = Feature::EDGELET;
+        new_feature->grad = A * ref_ftr->grad;
+        new_feature->grad.normalize();
+      }
+      ++n_matches_;
+    }
+  }
+}
+
+// ============================================================================ pose_optimizer.h
+// Linked INSTEAD OF pose_optimizer.cpp (pose_optimizer.cpp:31-181): the whole Gauss-Newton loop, the MAD scale, the
+// Tukey weights, the outlier pass and the two medians run in ONE launch (svob200_pose_optimize).
+namespace pose_optimizer {
+
+void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter, const bool verbose, FramePtr& frame, double& estimated_scale,
+                         double& error_init, double& error_final, size_t& num_obs)
+{
+  std::vector<Feature*> fs;
+  for (auto it = frame->fts_.begin(); it != frame->fts_.end(); ++it) if ((*it)->point != NULL) fs.push_back(*it);
+  if (fs.empty()) return;                                                                               // :56-57
+  const int n = (int)fs.size();
+  std::vector<double> f(3 * n), pos(3 * n);
+  std::vector<int> level(n);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) { f[3 * i + k] = fs[i]->f[k]; pos[3 * i + k] = fs[i]->point->pos_[k]; }
+    level[i] = fs[i]->level;
+  }
+  const svob200_camera cam = b200::camera_of(frame->cam_);
+  svob200_pose_opt_opts o;
+  svob200_pose_opt_opts_default(&o);
+  o.reproj_thresh = reproj_thresh; o.n_iter = (int)n_iter; o.eps = EPS;
+  double T[7];
+  b200::pose7(frame->T_f_w_, T);
+  svob200_pose_opt_result r;
+  std::vector<uint8_t> outlier(n);
+  const int off[2] = {0, n};
+  {
+    Lock lk(rt().mu);
+    check(svob200_pose_optimize(ctx_locked(), &cam, 1, off, f.data(), level.data(), pos.data(), &o, T, &r, outlier.data(), SVOB200_MEM_HOST),
+          "svob200_pose_optimize");
+  }
+  frame->T_f_w_ = b200::se3_of(T);
+  Matrix<double, 6, 6> A;
+  for (int rr = 0; rr < 6; ++rr) for (int c = 0; c < 6; ++c) A(rr, c) = r.A[rr * 6 + c];
+  const double pixel_variance = 1.0;
+  frame->Cov_ = pixel_variance * (A * std::pow(frame->cam_->errorMultiplier2(), 2)).inverse();          // :139-140
+  for (int i = 0; i < n; ++i) if (outlier[i]) fs[i]->point = NULL;                                      // :149-153
+  estimated_scale = r.estimated_scale; error_init = r.error_init; error_final = r.error_final;
+  num_obs = (size_t)r.num_obs;
+  if (verbose) fprintf(stderr, "[svo_b200] pose optimizer: %d its, n obs = %d, scale = %f, error init = %f, error end = %f\n",
+                       r.iters, r.num_obs, estimated_scale, error_init, error_final);
+}
+
+}  // namespace pose_optimizer
+
+// ============================================================================ FrameHandlerBase::optimizeStructure
+namespace b200 {
+
+// frame_handler_base.cpp:190-210 with every Point::optimize (point.cpp:130-192) in one launch
+void optimizeStructure(FramePtr frame, size_t max_n_pts, int max_iter)
+{
+  std::deque<Point*> pts;
+  for (Features::iterator it = frame->fts_.begin(); it != frame->fts_.end(); ++it) if ((*it)->point != NULL) pts.push_back((*it)->point);
+  max_n_pts = std::min(max_n_pts, pts.size());
+  std::nth_element(pts.begin(), pts.begin() + max_n_pts, pts.end(),
+                   [](Point* lhs, Point* rhs) { return lhs->last_structure_optim_ < rhs->last_structure_optim_; });
+  const int n = (int)max_n_pts;
+  if (n == 0) return;
+  std::vector<int> off(n + 1, 0);
+  std::vector<double> T, f, pos(3 * n);
+  for (int i = 0; i < n; ++i) {
+    for (auto o = pts[i]->obs_.begin(); o != pts[i]->obs_.end(); ++o) {
+      double t[7];
+      pose7((*o)->frame->T_f_w_, t);
+      T.insert(T.end(), t, t + 7);
+      for (int k = 0; k < 3; ++k) f.push_back((*o)->f[k]);
+    }
+    off[i + 1] = (int)(T.size() / 7);
+    for (int k = 0; k < 3; ++k) pos[3 * i + k] = pts[i]->pos_[k];
+  }
+  {
+    Lock lk(rt().mu);
+    check(svob200_points_optimize(ctx_locked(), n, off.data(), T.data(), f.data(), max_iter, EPS, pos.data(), nullptr, SVOB200_MEM_HOST),
+          "svob200_points_optimize");
+  }
+  for (int i = 0; i < n; ++i) {
+    pts[i]->pos_ = Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    pts[i]->last_structure_optim_ = frame->id_;
+  }
+}
+
+}  // namespace b200
 
 }  // namespace svo

@@ -11,8 +11,11 @@
 //   svo::SparseImgAlign::SparseImgAlign / run / getFisherInformation (sparse_img_align.h:43-57)
 //   svo::feature_detection::AbstractDetector / FastDetector          (feature_detection.h:41-101)
 //
-// so it is linked INSTEAD OF vision.cpp, feature_alignment.cpp, matcher.cpp, sparse_img_align.cpp and
-// feature_detection.cpp.  The depth filter keeps the reference's depth_filter.cpp (threading, queues,
+//   svo::Reprojector (ctor, dtor, reprojectMap)                     (reprojector.h:48-60)
+//   svo::pose_optimizer::optimizeGaussNewton                         (pose_optimizer.h)
+//
+// so it is linked INSTEAD OF vision.cpp, feature_alignment.cpp, matcher.cpp, sparse_img_align.cpp,
+// feature_detection.cpp, reprojector.cpp and pose_optimizer.cpp.  The depth filter keeps the reference's depth_filter.cpp (threading, queues,
 // seed initialisation are control plane) and swaps only the hot loop through the protected virtual
 // DepthFilter::updateSeeds (depth_filter.h:159): construct svo::B200DepthFilter where the reference
 // constructs svo::DepthFilter (frame_handler_mono.cpp:43-48).  See INTEGRATION.md.
@@ -57,6 +60,11 @@ svob200_ctx* context();
 void releaseFrame(const Frame& frame);
 void setFrameCacheCapacity(size_t capacity);
 void shutdown();
+
+/// FrameHandlerBase::optimizeStructure (frame_handler_base.cpp:190-210) with every Point::optimize (point.cpp:130-192)
+/// of the call in one launch.  Point::optimize itself lives in point.cpp next to code the drop-in keeps, so the member
+/// symbol is not replaced: call this where the frame handler calls optimizeStructure (frame_handler_mono.cpp:233).
+void optimizeStructure(FramePtr frame, size_t max_n_pts, int max_iter);
 
 /// kernels launched so far by the drop-in's context (svob200_ctx_launch_count)
 long long launchCount();

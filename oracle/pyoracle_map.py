@@ -130,6 +130,7 @@ class RefMap:
             L.svo_ref_point_optimize.argtypes = [c_ip, c_dp, c_u8p, C.c_int, c_dp, c_dp, C.c_int, c_dp]
             L.svo_ref_initialize_seeds.argtypes = [c_ip, c_dp, c_u8p, C.c_int, C.c_int, C.c_double, C.c_int, c_dp, C.c_double, C.c_double,
                                                    C.c_int, c_ip, c_ip, c_ip, c_fp]
+            L.svo_ref_optimize_structure.argtypes = [c_ip, c_dp, c_u8p, C.c_int, c_ip, c_ip, c_dp, c_dp, c_ip, C.c_int, C.c_int, c_dp, c_ip]
 
     def available(self):
         return self.lib is not None and hasattr(self.lib, "svo_ref_reproject_map")
@@ -181,6 +182,18 @@ class RefMap:
         self.lib.svo_ref_point_optimize(_p(cam.wh(), c_ip), _p(cam.k(), c_dp), _p(img, c_u8p), len(T_f_w), _p(T_f_w, c_dp), _p(f, c_dp),
                                         int(n_iter), _p(p, c_dp))
         return p
+
+    def optimize_structure(self, cam, img, obs_offsets, T_f_w, f, pos, last_optim, max_n_pts, n_iter):
+        off = i32(obs_offsets)
+        n = len(off) - 1
+        ob, oe = i32(off[:-1]), i32(off[1:])
+        p = f64(pos).reshape(n, 3).copy()
+        done = np.zeros(n, np.int32)
+        img = u8(img)
+        self.lib.svo_ref_optimize_structure(_p(cam.wh(), c_ip), _p(cam.k(), c_dp), _p(img, c_u8p), n, _p(ob, c_ip), _p(oe, c_ip),
+                                            _p(f64(T_f_w), c_dp), _p(f64(f), c_dp), _p(i32(last_optim), c_ip), int(max_n_pts), int(n_iter),
+                                            _p(p, c_dp), _p(done, c_ip))
+        return p, done
 
     def initialize_seeds(self, cam, img, n_detect_levels, cell, thr, existing_px, depth_mean, depth_min):
         epx = f64(existing_px).reshape(-1, 2)

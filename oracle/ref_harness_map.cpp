@@ -17,7 +17,9 @@
 #include <svo/pose_optimizer.h>
 #include <svo/feature_detection.h>
 #include <svo/depth_filter.h>
+#include <algorithm>
 #include <cstring>
+#include <deque>
 #include <vector>
 #ifdef SVOB200_DROPIN
 #include "svo_b200_dropin.h"
@@ -222,6 +224,64 @@ int svo_ref_initialize_seeds(const int* wh, const double* k, const uint8_t* img,
   }
   delete cam;
   return n;
+}
+
+
+// FrameHandlerBase::optimizeStructure (frame_handler_base.cpp:190-210) on a frame whose n features reference n points;
+// point i is observed from obs[obs_begin[i]..obs_end[i]) = (pose, bearing).  The reference build runs the member's body
+// (the selection by last_structure_optim_ + Point::optimize; FrameHandlerBase itself is control plane and not linked);
+// the drop-in build calls svo::b200::optimizeStructure.
+void svo_ref_optimize_structure(const int* wh, const double* k, const uint8_t* img, int n_points, const int* obs_begin, const int* obs_end,
+                                const double* T_f_w, const double* f, const int* last_optim_in, int max_n_pts, int n_iter,
+                                double* pos /*inout*/, int* last_optim_out)
+{
+  vk::PinholeCamera* cam = new vk::PinholeCamera(wh[0], wh[1], k[0], k[1], k[2], k[3]);
+  {
+    const int n_obs = n_points ? obs_end[n_points - 1] : 0;
+    std::vector<FramePtr> frames;
+    for (int o = 0; o < n_obs; ++o) {
+      FramePtr fr(new Frame(cam, mat_copy(img, wh[0], wh[1]), (double)o));
+      fr->T_f_w_ = to_se3(T_f_w + 7 * o);
+      frames.push_back(fr);
+    }
+    FramePtr frame(new Frame(cam, mat_copy(img, wh[0], wh[1]), 1e6));
+    std::vector<Point*> pts(n_points);
+    std::vector<Feature*> obs_ftrs;
+    for (int i = 0; i < n_points; ++i) {
+      pts[i] = new Point(Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+      pts[i]->last_structure_optim_ = last_optim_in[i];
+      for (int o = obs_end[i] - 1; o >= obs_begin[i]; --o) {          // addFrameRef pushes to the front
+        Feature* ftr = new Feature(frames[o].get(), Vector2d(0, 0), 0);
+        ftr->f = Vector3d(f[3 * o], f[3 * o + 1], f[3 * o + 2]);
+        ftr->point = pts[i];
+        pts[i]->addFrameRef(ftr);
+        obs_ftrs.push_back(ftr);
+      }
+      Feature* cf = new Feature(frame.get(), Vector2d(10 + i, 10), 0);
+      cf->point = pts[i];
+      frame->addFeature(cf);
+    }
+#ifdef SVOB200_DROPIN
+    svo::b200::optimizeStructure(frame, (size_t)max_n_pts, n_iter);
+#else
+    {
+      std::deque<Point*> q;
+      for (Features::iterator it = frame->fts_.begin(); it != frame->fts_.end(); ++it) if ((*it)->point != NULL) q.push_back((*it)->point);
+      size_t m = std::min((size_t)max_n_pts, q.size());
+      std::nth_element(q.begin(), q.begin() + m, q.end(), [](Point* l, Point* r) { return l->last_structure_optim_ < r->last_structure_optim_; });
+      for (std::deque<Point*>::iterator it = q.begin(); it != q.begin() + m; ++it) { (*it)->optimize(n_iter); (*it)->last_structure_optim_ = frame->id_; }
+    }
+#endif
+    for (int i = 0; i < n_points; ++i) {
+      pos[3 * i] = pts[i]->pos_[0]; pos[3 * i + 1] = pts[i]->pos_[1]; pos[3 * i + 2] = pts[i]->pos_[2];
+      last_optim_out[i] = pts[i]->last_structure_optim_ == frame->id_ ? 1 : 0;
+    }
+    for (auto x : obs_ftrs) delete x;
+    for (int i = 0; i < n_points; ++i) { pts[i]->obs_.clear(); }
+    frame.reset();
+    for (int i = 0; i < n_points; ++i) delete pts[i];
+  }
+  delete cam;
 }
 
 }  // extern "C"

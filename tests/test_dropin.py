@@ -33,6 +33,8 @@ HOT_SYMBOLS = [
     "_ZN3svo7Matcher15findMatchDirectERKNS_5PointERKNS_5FrameERN5Eigen6MatrixIdLi2ELi1ELi0ELi2ELi1EEE",
     "_ZN3svo7Matcher23findEpipolarMatchDirectERKNS_5FrameES3_RKNS_7FeatureEdddRd",
     "_ZN3svo17feature_detection12FastDetector6detectEPNS_5FrameERKSt6vectorIN2cv3MatESaIS6_EEdRNSt7__cxx114listIPNS_7FeatureESaISE_EEE",
+    "_ZN3svo11Reprojector12reprojectMapESt10shared_ptrINS_5FrameEERSt6vectorISt4pairIS3_mESaIS6_EE",
+    "_ZN3svo14pose_optimizer19optimizeGaussNewtonEdmbRSt10shared_ptrINS_5FrameEERdS5_S5_Rm",
     "_ZN3svo15B200DepthFilter11updateSeedsESt10shared_ptrINS_5FrameEE",
 ]
 
@@ -236,3 +238,71 @@ def test_frontend_sequence(both, oracle):
         assert conv > 50
     finally:
         sr.close(); sd.close()
+
+
+# ---------------------------------------------------------------- callers either side of the hot path
+@pytest.fixture(scope="module")
+def both_map(both):
+    from oracle import pyoracle_map as pm
+    ref, d = both
+    return pm.RefMap(ref), pm.RefMap(d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,max_fts", [(5, 120), (7, 12)])
+def test_reprojector_dropin(both_map, oracle, seed, max_fts):
+    """svo::Reprojector::reprojectMap of the drop-in (device grid + batched matching) against the reference's, on the same
+    Map built by the same harness: counters, per-point side effects, the new features of the frame (bit-exact pixels)"""
+    import map_scenes as ms
+    rm, dm = both_map
+    sc = ms.build_map_scene(oracle, seed=seed)
+    cfg = sc["cfg"]
+    cam = Cam.make(cfg["w"], cfg["h"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
+    out = []
+    for m in (rm, dm):
+        m.config(cfg["n_pyr"], sc["cell"], max_fts)
+        out.append(m.reproject_map(sc["kf_imgs"], sc["T_kf"], sc["cur_img"], sc["T_cur"], cam, sc["points"], sc["obs"], sc["n_candidates"]))
+    a, b = out
+    assert (a["n_matches"], a["n_trials"]) == (b["n_matches"], b["n_trials"]) and a["n_matches"] > 10
+    for k in ("n_failed", "n_succeeded", "type_after", "new_point", "new_level", "new_type", "overlap_kf", "overlap_cnt"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["new_px"], b["new_px"])
+    assert np.allclose(a["new_grad"], b["new_grad"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_pose_optimizer_dropin(both_map):
+    import map_scenes as ms
+    rm, dm = both_map
+    for seed in (3, 9):
+        s = ms.pose_opt_scene(seed=seed)
+        cfg = s["cfg"]
+        cam = Cam.make(cfg["w"], cfg["h"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
+        img = np.zeros((cfg["h"], cfg["w"]), np.uint8)
+        a = rm.pose_optimize(cam, img, s["px"], s["level"], s["pos"], s["T_init"])
+        b = dm.pose_optimize(cam, img, s["px"], s["level"], s["pos"], s["T_init"])
+        rot, trans = synth.pose_error(a["T"], b["T"])
+        assert rot <= 1e-9 and trans <= 1e-9                    # spec: 1e-4 rad / 1e-4 of scene scale
+        assert np.array_equal(a["outlier"], b["outlier"]) and a["num_obs"] == b["num_obs"]
+        assert a["estimated_scale"] == b["estimated_scale"] and a["error_init"] == b["error_init"]
+        assert np.isclose(a["error_final"], b["error_final"], rtol=1e-9)
+        assert np.allclose(a["A"], b["A"], rtol=1e-6, atol=1e-6 * np.abs(a["A"]).max())
+
+
+@pytest.mark.gpu
+def test_optimize_structure_dropin(both_map):
+    """FrameHandlerBase::optimizeStructure: the selection by last_structure_optim_ and every Point::optimize, bit-exact"""
+    import map_scenes as ms
+    rm, dm = both_map
+    cfg = ms.SMALL
+    cam = Cam.make(cfg["w"], cfg["h"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
+    img = np.zeros((cfg["h"], cfg["w"]), np.uint8)
+    pts = ms.point_opt_scene()
+    off = np.concatenate([[0], np.cumsum([len(p["T"]) for p in pts])])
+    T = np.concatenate([p["T"] for p in pts]); f = np.concatenate([p["f"] for p in pts])
+    pos0 = np.stack([p["pos0"] for p in pts])
+    last = np.arange(len(pts))[::-1]
+    a_pos, a_done = rm.optimize_structure(cam, img, off, T, f, pos0, last, 20, 5)
+    b_pos, b_done = dm.optimize_structure(cam, img, off, T, f, pos0, last, 20, 5)
+    assert a_done.sum() == 20 and np.array_equal(a_done, b_done)
+    assert np.array_equal(a_pos, b_pos)
