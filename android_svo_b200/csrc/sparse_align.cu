@@ -20,8 +20,12 @@
 // accumulated sequentially in the reference; it is decided here on the double sum unless the two
 // values are closer than the worst-case rounding error of the float chain, in which case thread 0
 // replays the exact sequential float chain (counted in n_exact_chi2).
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -166,31 +170,42 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int l
 //                            6-vectors a, b, so  sum J J^T = Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T  and
 //                            sum J r = Sxr a + Syr b : five double sums over the patch, then 27 entries
 // followed by one block reduction and the serial solve / update / decision on thread 0.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignArgs A)
+//
+// CLUSTER > 1 (single-stream latency): one thread-block CLUSTER per problem.  Each CTA of the cluster owns a contiguous
+// slice of the features and runs P1-P3 on it on its own SM; the 29 partial sums travel to rank 0 through distributed
+// shared memory, rank 0 adds them in rank order (deterministic), solves, decides, and pushes the new model and the
+// control word into every CTA's shared memory; two hardware cluster barriers per iteration.
+template <int BLOCK, int CLUSTER>
+__global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : 512 / BLOCK) sparse_align_kernel(AlignArgs A)
 {
   constexpr int NW = BLOCK / 32;
   __shared__ double s_model[7];
   __shared__ double s_old[7];
   __shared__ double s_red[NW][NACC];
   __shared__ double s_tot[NACC];
+  __shared__ double s_clu[CLUSTER > 1 ? CLUSTER : 1][NACC];   // rank 0 only: the partial sums of every CTA of the cluster
   __shared__ int s_ctrl;          // 0 continue iterating, 1 leave this level
 
-  const int b = blockIdx.x;
+  const int b = CLUSTER > 1 ? blockIdx.x / CLUSTER : blockIdx.x;
+  const int rank = CLUSTER > 1 ? (int)(blockIdx.x % CLUSTER) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f0 = A.offsets[b], N = A.offsets[b + 1] - f0;
+  // this CTA's slice of the features
+  const int lo = CLUSTER > 1 ? (int)(((long long)N * rank) / CLUSTER) : 0;
+  const int hi = CLUSTER > 1 ? (int)(((long long)N * (rank + 1)) / CLUSTER) : N;
   svob200_align_result* R = &A.results[b];
+  const bool lead = rank == 0 && tid == 0;
 
   if (tid < 7) s_model[tid] = A.T_init[7 * b + tid];
-  if (tid == 0) {
+  if (lead) {
     for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = A.T_init[7 * b + k];
     for (int k = 0; k < 36; ++k) R->H[k] = 0;
     for (int k = 0; k < 6; ++k) { R->Jres[k] = 0; R->x[k] = 0; }
     R->chi2 = 1e10; R->n_meas = 0; R->stop = 0; R->n_exact_chi2 = 0;
     for (int k = 0; k < SVOB200_MAX_LEVELS; ++k) R->iters[k] = 0;
   }
-  if (N <= 0) return;                                   // sparse_img_align.cpp:55-59
-  for (int i = tid; i < N; i += BLOCK) { A.visible[f0 + i] = 0; A.contrib[0][f0 + i] = 0; A.contrib[1][f0 + i] = 0; }
+  if (N <= 0) return;                                   // sparse_img_align.cpp:55-59 (uniform over the cluster)
+  for (int i = lo + tid; i < hi; i += BLOCK) { A.visible[f0 + i] = 0; A.contrib[0][f0 + i] = 0; A.contrib[1][f0 + i] = 0; }
   __syncthreads();
 
   const double* px = A.px + 2 * (size_t)f0;
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
       const uint8_t* img = A.ref.lvl[level] + (size_t)b * A.ref.img_stride[level];
       const int cols = A.ref.w[level], rows = A.ref.h[level], stride = A.ref.pitch[level];
       const double fl = focal_length / (1 << level);
-      for (int idx = tid; idx < N * 16; idx += BLOCK) {
+      for (int idx = lo * 16 + tid; idx < hi * 16; idx += BLOCK) {
         const int i = idx >> 4, p = idx & 15;
         const float u_ref = (float)(px[2 * i] * (double)scale);
         const float v_ref = (float)(px[2 * i + 1] * (double)scale);
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
         double m[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) m[k] = s_model[k];
-        for (int i = tid; i < N; i += BLOCK) {
+        for (int i = lo + tid; i < hi; i += BLOCK) {
           if (!visible[i]) continue;
           const v3d pc = se3_transform(m, {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
           double pxd, pyd;
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
       }
       __syncthreads();
       // ---------------- P2: residuals (sparse_img_align.cpp:233-266)
-      for (int idx = tid; idx < N * 16; idx += BLOCK) {
+      for (int idx = lo * 16 + tid; idx < hi * 16; idx += BLOCK) {
         const int i = idx >> 4, p = idx & 15;
         if (!visible[i] || !contrib[i]) continue;
         const float2 c = uv[i];
@@ -297,7 +312,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
       double acc[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      for (int i = tid; i < N; i += BLOCK) {
+      for (int i = lo + tid; i < hi; i += BLOCK) {
         if (!visible[i] || !contrib[i]) continue;
         const float4* r4 = reinterpret_cast<const float4*>(res + 16 * (size_t)i);
         const float4* x4 = reinterpret_cast<const float4*>(gdx + 16 * (size_t)i);
@@ -337,11 +352,22 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
 #pragma unroll
         for (int w = 0; w < NW; ++w) t += s_red[w][lane];
         s_tot[lane] = t;
+        if (CLUSTER > 1) cg::this_cluster().map_shared_rank(&s_clu[0][0], 0)[rank * NACC + lane] = t;
+      }
+      if (CLUSTER > 1) {
+        __threadfence();                               // residuals / flags of this slice: visible to rank 0's exact chi2 replay
+        cg::this_cluster().sync();
+        if (rank == 0 && warp == 0) {
+          double t = s_clu[0][lane];
+#pragma unroll
+          for (int r = 1; r < CLUSTER; ++r) t += s_clu[r][lane];
+          s_tot[lane] = t;
+        }
       }
       __syncthreads();
 
-      // ---------------- solve / decide / update (thread 0), nlls_solver_impl.hpp:36-99
-      if (tid == 0) {
+      // ---------------- solve / decide / update (thread 0 of rank 0), nlls_solver_impl.hpp:36-99
+      if (lead) {
         double H[36], Jres[6], xs[6];
         int h = 0;
 #pragma unroll
@@ -402,14 +428,25 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
           if (nmax <= A.opts.eps) ctrl = 1;
         }
         s_ctrl = ctrl;
+        if (CLUSTER > 1) {
+          // push the new model, the rollback model and the control word into every CTA of the cluster
+          cg::cluster_group cl = cg::this_cluster();
+          for (int r = 1; r < CLUSTER; ++r) {
+            double* rm = cl.map_shared_rank(&s_model[0], r);
+            double* ro = cl.map_shared_rank(&s_old[0], r);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { rm[k] = s_model[k]; ro[k] = s_old[k]; }
+            *cl.map_shared_rank(&s_ctrl, r) = ctrl;
+          }
+        }
       }
       pp ^= 1;
-      __syncthreads();
+      if (CLUSTER > 1) cg::this_cluster().sync(); else __syncthreads();
       if (s_ctrl) break;
     }
-    __syncthreads();
+    if (CLUSTER > 1) cg::this_cluster().sync(); else __syncthreads();
   }
-  if (tid == 0) {
+  if (lead) {
     for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = s_model[k];
     R->chi2 = chi2_;
     R->stop = stop_ ? 1 : 0;
@@ -418,6 +455,14 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) sparse_align_kernel(AlignA
 }
 
 }  // namespace
+
+// SVOB200_ALIGN_CLUSTER=1|2|4|8 forces the cluster size (tests / A-B runs); unset or 0 = automatic
+static int sparse_align_cluster_override()
+{
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVOB200_ALIGN_CLUSTER"); v = e ? atoi(e) : 0; if (v != 1 && v != 2 && v != 4 && v != 8) v = 0; }
+  return v;
+}
 
 // per feature: 16 floats x (ref_patch, gdx, gdy, res0, res1) + 12 doubles (a, b) + float2 uv + 3 flag bytes
 size_t sparse_align_scratch_bytes(int total_features)
@@ -449,10 +494,32 @@ int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& 
   A.visible = reinterpret_cast<uint8_t*>(take(T));
   A.contrib[0] = reinterpret_cast<uint8_t*>(take(T));
   A.contrib[1] = reinterpret_cast<uint8_t*>(take(T));
+  // few problems (single-stream latency): spread each problem over a thread-block cluster, one SM per CTA, so the
+  // per-iteration work of a 1,000-feature frame is shared by 8 SMs instead of serialising on one;
   // small problems / few problems: more threads per problem (latency); big batches: more CTAs per SM (throughput)
-  if (max_per_problem > 512) sparse_align_kernel<512><<<batch, 512, 0, s>>>(A);
-  else if (max_per_problem > 128 || batch < 296) sparse_align_kernel<256><<<batch, 256, 0, s>>>(A);
-  else sparse_align_kernel<128><<<batch, 128, 0, s>>>(A);
+  const int force = sparse_align_cluster_override();
+  int cluster = 1;
+  if (batch <= 16 && max_per_problem >= 64) cluster = 8;
+  else if (batch <= 32 && max_per_problem >= 64) cluster = 4;
+  else if (batch <= 64 && max_per_problem >= 128) cluster = 2;
+  if (force > 0) cluster = force;
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)batch * cluster, 1, 1); cfg.blockDim = dim3(256, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (cluster == 8) e = cudaLaunchKernelEx(&cfg, sparse_align_kernel<256, 8>, A);
+    else if (cluster == 4) e = cudaLaunchKernelEx(&cfg, sparse_align_kernel<256, 4>, A);
+    else e = cudaLaunchKernelEx(&cfg, sparse_align_kernel<256, 2>, A);
+    ++*launches;
+    return e == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+  if (max_per_problem > 512) sparse_align_kernel<512, 1><<<batch, 512, 0, s>>>(A);
+  else if (max_per_problem > 128 || batch < 296) sparse_align_kernel<256, 1><<<batch, 256, 0, s>>>(A);
+  else sparse_align_kernel<128, 1><<<batch, 128, 0, s>>>(A);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -130,6 +130,43 @@ def _align_problem(cfg, poses, k0, rng, N):
     return px, has
 
 
+@pytest.mark.parametrize("batch", [1, 20, 40, 70])
+def test_sparse_align_cluster_paths(ctx, oracle, batch):
+    """The launcher spreads a problem over a thread-block cluster of 8 / 4 / 2 / 1 CTAs depending on the batch size
+    (single-stream latency vs throughput); every path must agree with the oracle (same tolerances, same GN iteration
+    counts).  The same problem is replicated `batch` times, plus one different problem at the end."""
+    cfg, poses, imgs = scenes.scene("C2", n_frames=8, stride=2, amp=1.0)
+    nl = 5
+    cam_o, cam_g = scenes.cam_of(cfg, Cam), scenes.cam_of(cfg, capi.Camera)
+    rng = np.random.RandomState(7)
+    probs = []
+    for (a, b, N) in ((0, 1, 300), (2, 3, 130)):
+        px, has = _align_problem(cfg, poses, a, rng, N)
+        ref_pos = oracle.se3_inverse(poses[a])[:3]
+        xyz = np.zeros((N, 3))
+        for i in range(N):
+            _, p = scenes.gt_depth(cfg, poses[a], px[i])
+            xyz[i] = oracle.cam2world(cam_o, px[i][0], px[i][1]) * np.sqrt(((p - ref_pos) ** 2).sum())
+        T_init = oracle.se3_mul(poses[a], oracle.se3_inverse(poses[a]))
+        n, res = oracle.sparse_align(oracle.pyramid(imgs[a], nl), oracle.pyramid(imgs[b], nl), cam_o, px.reshape(-1), xyz.reshape(-1), has, T_init, 4, 2)
+        probs.append(dict(a=a, b=b, N=N, px=px, has=has, xyz=xyz, T=T_init, n=n, res=res))
+    which = [0] * (batch - 1) + [1] if batch > 1 else [0]
+    rid = upload(ctx, [imgs[probs[k]["a"]] for k in which], nl)
+    cid = upload(ctx, [imgs[probs[k]["b"]] for k in which], nl)
+    try:
+        offs = np.concatenate([[0], np.cumsum([probs[k]["N"] for k in which])])
+        got = ctx.sparse_align(rid, cid, cam_g, offs, np.concatenate([probs[k]["px"] for k in which]), np.concatenate([probs[k]["xyz"] for k in which]),
+                               np.concatenate([probs[k]["has"] for k in which]), np.array([probs[k]["T"] for k in which]), 4, 2)
+        for i, k in enumerate(which):
+            g, res = got[i], probs[k]["res"]
+            assert g["n_meas"] == res.n_meas and list(g["iters"]) == list(res.iters) and g["stop"] == res.stop
+            rot, trans = synth.pose_error(g["T_cur_ref"], np.array(res.T_cur_ref[:]))
+            assert rot < 1e-9 and trans < 1e-9, (rot, trans)
+            assert np.allclose(g["H"], np.array(res.H[:]), rtol=1e-9, atol=1e-9 * np.abs(np.array(res.H[:])).max())
+    finally:
+        ctx.frame_release(rid); ctx.frame_release(cid)
+
+
 @pytest.mark.parametrize("name,max_level,min_level", [("C2", 3, 2), ("C2", 4, 2), ("C3", 4, 2), ("C2", 2, 0)])
 def test_sparse_align_matches_oracle(ctx, oracle, name, max_level, min_level):
     cfg, poses, imgs = scenes.scene(name, n_frames=8, stride=2, amp=1.0)
