@@ -378,7 +378,7 @@ __device__ inline double compute_tau(const double* T_ref_cur, v3d f, double z, d
 // (thread-per-problem LK refinement, shared with findMatchDirect), phase 4 (per-thread triangulation /
 // seed update).  Each phase is its own kernel so that every one of them runs with the mapping that suits
 // it and the FP64 pipe never executes the same geometry redundantly across a warp.
-constexpr int EPI_CHUNK = 256;           // epipolar samples staged per round
+
 constexpr int EPI_MAX_STEPS = 1023;      // max_epi_search_steps is clamped to this
 enum { EPI_MODE_NONE = 0, EPI_MODE_DIRECT = 1, EPI_MODE_WALK = 2 };
 enum { EPI_FOUND_NONE = 0, EPI_FOUND_REFINED = 1, EPI_FOUND_UV_ONLY = 2 };
@@ -453,12 +453,37 @@ __device__ __forceinline__ EpiSearch epi_search_none()
   return s;
 }
 
-struct EpiWarpSmem {
+// The search and patch-warp kernels work in GROUPS of 8 lanes: one item (seed / reprojection candidate) per group, four
+// items per warp in lockstep.  Per item the code path is ~1,300 SASS instructions of mostly straight-line work (task decode,
+// 100 bilinear taps, patch extraction, a short epipolar walk, reductions, job emission); run by a full warp it executed
+// once per item at ~22 of 32 lanes busy (ncu: 936 warp instructions per seed).  Four items per warp share every one of those
+// instructions, and the 8 taps a group issues per load still fall into 1-2 cache lines, so L1 wavefronts per item do not grow
+// (a thread-per-item mapping would need 32 lines per load instruction and is LSU-bound).
+constexpr int GL = 8;                    // lanes per group
+constexpr int GPW = 32 / GL;             // groups (items) per warp
+constexpr int EPI_GCHUNK = 32;           // epipolar samples a group stages per round (steady-state walks are <= 47 steps)
+constexpr int SEARCH_CTAS = 6;           // resident CTAs per SM of the persistent search kernel (85 registers per thread: no spills)
+
+struct EpiGroupSmem {
   __align__(16) uint8_t pwb[112];       // 100 used
   __align__(16) uint8_t patch[64];
-  double uv[2 * EPI_CHUNK];             // the reference's running sums uv += step (x, y interleaved)
-  short2 pxi[EPI_CHUNK + 1];
+  double uv[2 * EPI_GCHUNK];            // the reference's running sums uv += step (x, y interleaved)
+  short2 pxi[EPI_GCHUNK + 1];
+  int pad_[3];
 };
+static_assert(sizeof(EpiGroupSmem) % 16 == 0, "EpiGroupSmem must keep 16-byte alignment in an array");
+
+// word k of the 128-byte task a group holds as one uint4 per lane (lane s of the group has words 4s .. 4s+3)
+__device__ __forceinline__ uint32_t task_word(const uint4& tq, int k, int gbase, unsigned gmask)
+{
+  const uint32_t c = (k & 3) == 0 ? tq.x : ((k & 3) == 1 ? tq.y : ((k & 3) == 2 ? tq.z : tq.w));
+  return __shfl_sync(gmask, c, gbase + (k >> 2));
+}
+__device__ __forceinline__ double task_double(const uint4& tq, int k, int gbase, unsigned gmask)
+{
+  const int lo = (int)task_word(tq, k, gbase, gmask), hi = (int)task_word(tq, k + 1, gbase, gmask);
+  return __hiloint2double(hi, lo);
+}
 
 // matcher.cpp:207-288 up to the start of the walk: pure per-thread math
 __device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref& f, const double* T_cur_ref, double d_estimate,
@@ -522,140 +547,136 @@ __device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref
   g->mode = EPI_MODE_WALK;
 }
 
-// one coalesced 128-byte store of a refinement job by a full warp (pwb words come from shared memory)
+// one 128-byte store of a refinement job by a group: lane s writes words 4s .. 4s+3 (pwb words come from shared memory)
 __device__ __forceinline__ void emit_lk_job(LkJob* dst, const uint8_t* s_pwb, float u, float v, float dirx, float diry, int item,
-                                            int image, int level_mode, int lane)
+                                            int image, int level_mode, int sub)
 {
-  uint32_t word;
-  if (lane < 25) word = reinterpret_cast<const uint32_t*>(s_pwb)[lane];
-  else if (lane == 25) word = __float_as_uint(u);
-  else if (lane == 26) word = __float_as_uint(v);
-  else if (lane == 27) word = __float_as_uint(dirx);
-  else if (lane == 28) word = __float_as_uint(diry);
-  else if (lane == 29) word = (uint32_t)item;
-  else if (lane == 30) word = (uint32_t)image;
-  else word = (uint32_t)level_mode;
-  reinterpret_cast<uint32_t*>(dst)[lane] = word;
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_pwb);
+  uint4 q;
+  if (sub < 6) q = make_uint4(pw[4 * sub], pw[4 * sub + 1], pw[4 * sub + 2], pw[4 * sub + 3]);
+  else if (sub == 6) q = make_uint4(pw[24], __float_as_uint(u), __float_as_uint(v), __float_as_uint(dirx));
+  else q = make_uint4(__float_as_uint(diry), (uint32_t)item, (uint32_t)image, (uint32_t)level_mode);
+  reinterpret_cast<uint4*>(dst)[sub] = q;
 }
 
-// affine warp of the 10x10 reference patch (matcher.cpp:83-116) into shared memory by a full warp
+// affine warp of the 10x10 reference patch (matcher.cpp:83-116) into shared memory by a group of 8 lanes
 __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, int rc, int rr, float a00, float a01, float a10, float a11,
-                                                 float pr0, float pr1, int L, uint8_t* s_pwb, int lane)
+                                                 float pr0, float pr1, int L, uint8_t* s_pwb, int sub)
 {
-  // lane handles taps lane, lane+32, lane+64, lane+96 (< 100); the loop is unrolled so that the 16 pixel loads of a
-  // lane are in flight together (one memory latency per patch instead of four)
+  // lane handles taps sub, sub+8, ... (< 100), four at a time so that the 16 pixel loads of a lane are in flight together
   const float sc = (float)(1 << L);
   const float xmax = (float)(rc - 1), ymax = (float)(rr - 1);
-  bool inb[4];
-  float w00[4], w01[4], w10[4], w11[4];
-  uint8_t p00[4], p01[4], p10[4], p11[4];
+#pragma unroll 1
+  for (int r0 = 0; r0 < 13; r0 += 4) {
+    bool inb[4];
+    float w00[4], w01[4], w10[4], w11[4];
+    uint8_t p00[4], p01[4], p10[4], p11[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = lane + 32 * r;
-    const int y = i / 10, x = i - y * 10;
-    float p0 = (float)(x - 5), p1 = (float)(y - 5);
-    p0 *= sc; p1 *= sc;
-    const float qx = (a00 * p0 + a01 * p1) + pr0;
-    const float qy = (a10 * p0 + a11 * p1) + pr1;
-    inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
-    // vk::interpolateMat_8u (vision.h:19-36)
-    const int ix = (int)floorf(qx), iy = (int)floorf(qy);
-    const float sx = qx - ix, sy = qy - iy;
-    w00[r] = (1.0f - sx) * (1.0f - sy);
-    w01[r] = (1.0f - sx) * sy;
-    w10[r] = sx * (1.0f - sy);
-    w11[r] = 1.0f - w00[r] - w01[r] - w10[r];
-    p00[r] = p01[r] = p10[r] = p11[r] = 0;
-    if (inb[r]) {
-      const uint8_t* p = rimg + (size_t)iy * rp + ix;
-      p00[r] = p[0]; p01[r] = p[rp]; p10[r] = p[1]; p11[r] = p[rp + 1];
+    for (int r = 0; r < 4; ++r) {
+      const int i = sub + GL * (r0 + r);
+      const int y = i / 10, x = i - y * 10;
+      float p0 = (float)(x - 5), p1 = (float)(y - 5);
+      p0 *= sc; p1 *= sc;
+      const float qx = (a00 * p0 + a01 * p1) + pr0;
+      const float qy = (a10 * p0 + a11 * p1) + pr1;
+      inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+      // vk::interpolateMat_8u (vision.h:19-36)
+      const int ix = (int)floorf(qx), iy = (int)floorf(qy);
+      const float sx = qx - ix, sy = qy - iy;
+      w00[r] = (1.0f - sx) * (1.0f - sy);
+      w01[r] = (1.0f - sx) * sy;
+      w10[r] = sx * (1.0f - sy);
+      w11[r] = 1.0f - w00[r] - w01[r] - w10[r];
+      p00[r] = p01[r] = p10[r] = p11[r] = 0;
+      if (inb[r]) {
+        const uint8_t* p = rimg + (size_t)iy * rp + ix;
+        p00[r] = p[0]; p01[r] = p[rp]; p10[r] = p[1]; p11[r] = p[rp + 1];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = sub + GL * (r0 + r);
+      if (i < 100) s_pwb[i] = inb[r] ? (uint8_t)(w00[r] * p00[r] + w01[r] * p01[r] + w10[r] * p10[r] + w11[r] * p11[r]) : (uint8_t)0;
     }
   }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = lane + 32 * r;
-    if (i < 100) s_pwb[i] = inb[r] ? (uint8_t)(w00[r] * p00[r] + w01[r] * p01[r] + w10[r] * p10[r] + w11[r] * p11[r]) : (uint8_t)0;
-  }
 }
 
-__device__ __forceinline__ double shfl_double(uint32_t word, int src)
-{
-  const int lo = (int)__shfl_sync(0xffffffffu, word, src), hi = (int)__shfl_sync(0xffffffffu, word, src + 1);
-  return __hiloint2double(hi, lo);
-}
+constexpr int JOB_BATCH = 8;             // LK job slots a group reserves per atomicAdd
 
-constexpr int JOB_BATCH = 8;             // LK job slots a warp reserves per atomicAdd
-
-// matcher.cpp:251-340 minus the LK refinement, for ONE item whose packed task sits in `tw` (lane k = word k): warp the
-// patch, walk the epipolar segment, and hand the refinement to the thread-per-problem LK kernel as a job.
+// matcher.cpp:251-340 minus the LK refinement, for ONE item whose packed task the group holds in `tq`: warp the patch, walk
+// the epipolar segment, and hand the refinement to the thread-per-problem LK kernel as a job.  Executed by the 8 lanes of
+// a group (gmask); the other groups of the warp run their own items in lockstep.
 __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_slot, const DevCam& cam, const svob200_matcher_opts& o,
-                                                uint32_t tw, int item, EpiWarpSmem* S, int lane, LkJob* jobs, int* job_count,
-                                                int& slot_base, int& slots_left, EpiSearch* search, svob200_epi_result* api_results)
+                                                const uint4& tq, int item, EpiGroupSmem* S, int sub, int gbase, unsigned gmask,
+                                                LkJob* jobs, int* job_count, int& slot_base, int& slots_left, EpiSearch* search,
+                                                svob200_epi_result* api_results)
 {
-  const uint32_t FULL = 0xffffffffu;
-  const int flags = (int)__shfl_sync(FULL, tw, ST_FLAGS);
+  const int flags = (int)task_word(tq, ST_FLAGS, gbase, gmask);
   const int mode = (flags >> ST_MODE_SHIFT) & 3;
-  const int levels = (int)__shfl_sync(FULL, tw, ST_LEVELS);
+  const int levels = (int)task_word(tq, ST_LEVELS, gbase, gmask);
   const int L = levels & 0xff, ref_level = (levels >> 8) & 0xff;
-  const int cur_image = (int)__shfl_sync(FULL, tw, ST_CUR_IMAGE);
+  const int cur_image = (int)task_word(tq, ST_CUR_IMAGE, gbase, gmask);
   EpiSearch out = epi_search_none();
-  if (api_results) { for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0; __syncwarp(); }
+  if (api_results) { for (int k = sub; k < 28; k += GL) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0; __syncwarp(gmask); }
   if (flags & ST_WARP_OK) {
-    const DevFrame& ref = frames[(int)__shfl_sync(FULL, tw, ST_REF_SLOT)];
-    const int ref_image = (int)__shfl_sync(FULL, tw, ST_REF_IMAGE);
+    const DevFrame& ref = frames[(int)task_word(tq, ST_REF_SLOT, gbase, gmask)];
+    const int ref_image = (int)task_word(tq, ST_REF_IMAGE, gbase, gmask);
     const uint8_t* rimg = ref.lvl[ref_level] + (size_t)ref_image * ref.img_stride[ref_level];
     warp_patch_10x10(rimg, ref.pitch[ref_level], ref.w[ref_level], ref.h[ref_level],
-                     __uint_as_float(__shfl_sync(FULL, tw, ST_A00)), __uint_as_float(__shfl_sync(FULL, tw, ST_A01)),
-                     __uint_as_float(__shfl_sync(FULL, tw, ST_A10)), __uint_as_float(__shfl_sync(FULL, tw, ST_A11)),
-                     __uint_as_float(__shfl_sync(FULL, tw, ST_PR0)), __uint_as_float(__shfl_sync(FULL, tw, ST_PR1)), L, S->pwb, lane);
+                     __uint_as_float(task_word(tq, ST_A00, gbase, gmask)), __uint_as_float(task_word(tq, ST_A01, gbase, gmask)),
+                     __uint_as_float(task_word(tq, ST_A10, gbase, gmask)), __uint_as_float(task_word(tq, ST_A11, gbase, gmask)),
+                     __uint_as_float(task_word(tq, ST_PR0, gbase, gmask)), __uint_as_float(task_word(tq, ST_PR1, gbase, gmask)), L, S->pwb, sub);
   }
-  __syncwarp();
-  for (int k = lane; k < 64; k += 32) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
-  __syncwarp();
+  __syncwarp(gmask);
+  for (int k = sub; k < 64; k += GL) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
+  __syncwarp(gmask);
   if (api_results) {
     svob200_epi_result* R = &api_results[item];
-    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = S->pwb[k];
-    for (int k = lane; k < 64; k += 32) R->patch[k] = S->patch[k];
+    for (int k = sub; k < 100; k += GL) R->patch_with_border[k] = S->pwb[k];
+    for (int k = sub; k < 64; k += GL) R->patch[k] = S->patch[k];
   }
   bool want_job = false;
   double px0 = 0.0, px1 = 0.0;
   if (mode == EPI_MODE_DIRECT) {
-    px0 = shfl_double(tw, ST_MIDX); px1 = shfl_double(tw, ST_MIDY);
+    px0 = task_double(tq, ST_MIDX, gbase, gmask); px1 = task_double(tq, ST_MIDY, gbase, gmask);
     want_job = true;
   } else if (mode == EPI_MODE_WALK) {
     const DevFrame& cur = frames[cur_slot];
     const uint8_t* cimg = cur.lvl[L] + (size_t)cur_image * cur.img_stride[L];
     const int cpitch = cur.pitch[L];
-    const int n = (int)__shfl_sync(FULL, tw, ST_N);
+    const int n = (int)task_word(tq, ST_N, gbase, gmask);
     RefPatchRegs rpatch;
     load_ref_patch(S->patch, rpatch);
     unsigned long long best = ((unsigned long long)(2000 * 64) << 32);   // PatchScore::threshold(), strict <
     double best_u = 0.0, best_v = 0.0;
     int evals = 0;
-    // the reference's running sums uv += step: x chain on lane 0, y chain on lane 1 (two independent DADD chains)
-    double uv = shfl_double(tw, ST_BX0 + 2 * (lane & 1));
-    const double st = shfl_double(tw, ST_STEPX + 2 * (lane & 1));
+    // the reference's running sums uv += step: x chain on lane 0 of the group, y chain on lane 1 (two independent DADD chains)
+    // (task_word's k must be uniform over the group: the SOURCE lane picks the component with its own k)
+    const double bx0 = task_double(tq, ST_BX0, gbase, gmask), by0 = task_double(tq, ST_BY0, gbase, gmask);
+    const double stx = task_double(tq, ST_STEPX, gbase, gmask), sty = task_double(tq, ST_STEPY, gbase, gmask);
+    double uv = (sub & 1) ? by0 : bx0;
+    const double st = (sub & 1) ? sty : stx;
     const double inv_scale = 1.0 / (double)(1 << L);                     // exact: dividing by 2^L == multiplying by 2^-L
     short2 last = make_short2(0, 0);                                     // last_checked_pxi(0,0)
-    for (int base = 0; base < n; base += EPI_CHUNK) {
-      const int m = min(EPI_CHUNK, n - base);
-      if (lane < 2) {
-        double* dst = S->uv + lane;
+    for (int base = 0; base < n; base += EPI_GCHUNK) {
+      const int m = min(EPI_GCHUNK, n - base);
+      if (sub < 2) {
+        double* dst = S->uv + sub;
         for (int i = 0; i < m; ++i, uv += st) dst[2 * i] = uv;
       }
-      if (lane == 0) S->pxi[0] = last;
-      __syncwarp();
+      if (sub == 0) S->pxi[0] = last;
+      __syncwarp(gmask);
       // pixel of every sample, in parallel: Vector2i(px/(1<<L) + 0.5) with the x86 truncating conversion
-      for (int i = lane; i < m; i += 32) {
+      for (int i = sub; i < m; i += GL) {
         const double ux = S->uv[2 * i], uy = S->uv[2 * i + 1];
         const double vx = (cam.fx * ux + cam.cx) * inv_scale + 0.5, vy = (cam.fy * uy + cam.cy) * inv_scale + 0.5;
         const int ix = (vx == vx) ? (vx >= 32767.0 ? 32767 : (vx <= -32768.0 ? -32768 : (int)vx)) : -32768;
         const int iy = (vy == vy) ? (vy >= 32767.0 ? 32767 : (vy <= -32768.0 ? -32768 : (int)vy)) : -32768;
         S->pxi[i + 1] = make_short2((short)ix, (short)iy);
       }
-      __syncwarp();
+      __syncwarp(gmask);
       last = S->pxi[m];
-      for (int i = lane; i < m; i += 32) {
+      for (int i = sub; i < m; i += GL) {
         const short2 c = S->pxi[i + 1], prev = S->pxi[i];
         if (c.x == prev.x && c.y == prev.y) continue;
         if (!in_frame_level(cam, c.x, c.y, 8, L)) continue;
@@ -664,22 +685,22 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
         const unsigned long long key = ((unsigned long long)(unsigned)z << 32) | (unsigned)(base + i);
         if (key < best) { best = key; best_u = S->uv[2 * i]; best_v = S->uv[2 * i + 1]; }
       }
-      __syncwarp();
+      __syncwarp(gmask);
     }
     unsigned long long gbest = best;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(FULL, gbest, off);
+    for (int off = GL / 2; off > 0; off >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(gmask, gbest, off);
       if (other < gbest) gbest = other;
-      evals += __shfl_xor_sync(FULL, evals, off);
+      evals += __shfl_xor_sync(gmask, evals, off);
     }
     out.n_evals = evals;
     const int zbest = (int)(gbest >> 32);
     out.zmssd_best = zbest;
     if (zbest < 2000 * 64) {
       // uv_best lives on the lane that evaluated the winning step (keys are unique: they contain the step index)
-      const unsigned owner = __ffs(__ballot_sync(FULL, best == gbest)) - 1;
-      const double ubx = __shfl_sync(FULL, best_u, owner), uby = __shfl_sync(FULL, best_v, owner);
+      const unsigned owner = __ffs(__ballot_sync(gmask, best == gbest) & gmask) - 1;
+      const double ubx = __shfl_sync(gmask, best_u, owner), uby = __shfl_sync(gmask, best_v, owner);
       world2cam_uv(cam, ubx, uby, px0, px1);
       out.uv_best[0] = ubx; out.uv_best[1] = uby;
       if (!o.subpix_refinement) { out.px_cur[0] = px0; out.px_cur[1] = px1; out.px_cur_valid = 1; out.found = EPI_FOUND_UV_ONLY; }
@@ -687,18 +708,18 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
     }
   }
   if (want_job) { out.px_cur[0] = px0; out.px_cur[1] = px1; out.px_cur_valid = 1; }
-  if (lane == 0) search[item] = out;
+  if (sub == 0) search[item] = out;
   if (!want_job) return;
   // hand over to the LK kernel: px_scaled = px_cur / (1 << L) (double), cast to float at the start of align1D/2D
   if (slots_left == 0) {
-    if (lane == 0) slot_base = atomicAdd(job_count, JOB_BATCH);
-    slot_base = __shfl_sync(FULL, slot_base, 0);
+    if (sub == 0) slot_base = atomicAdd(job_count, JOB_BATCH);
+    slot_base = __shfl_sync(gmask, slot_base, gbase);
     slots_left = JOB_BATCH;
   }
   const int slot = slot_base + (JOB_BATCH - slots_left);
   --slots_left;
-  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), __uint_as_float(__shfl_sync(FULL, tw, ST_DIRX)),
-              __uint_as_float(__shfl_sync(FULL, tw, ST_DIRY)), item, cur_image, L | ((o.align_1d ? 1 : 0) << 8), lane);
+  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), __uint_as_float(task_word(tq, ST_DIRX, gbase, gmask)),
+              __uint_as_float(task_word(tq, ST_DIRY, gbase, gmask)), item, cur_image, L | ((o.align_1d ? 1 : 0) << 8), sub);
 }
 
 // matcher.cpp:269-276 / :341-351: triangulate from the matched pixel (per thread)
@@ -863,26 +884,28 @@ __global__ void __launch_bounds__(128) epi_geom_kernel(DevCam cam, int n, const 
 // items; the packed task of the next item is fetched (one coalesced 128-byte load) while the current one is processed,
 // and LK job slots are reserved JOB_BATCH at a time, so neither a DRAM round trip nor an atomic sits on the critical
 // path of an item.  api_results != nullptr: stand-alone queries, which also return the warped patch.
-__global__ void __launch_bounds__(128, 8) epi_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n, svob200_matcher_opts o,
+__global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n, svob200_matcher_opts o,
                                                             const SearchTask* tasks, EpiSearch* search, LkJob* jobs, int* job_count,
                                                             svob200_epi_result* api_results)
 {
-  __shared__ EpiWarpSmem SM[4];
+  __shared__ EpiGroupSmem SM[4 * GPW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  EpiWarpSmem* S = &SM[warp];
-  const int nw = gridDim.x * 4;
+  const int sub = lane & (GL - 1), grp = lane / GL, gbase = grp * GL;
+  const unsigned gmask = ((1u << GL) - 1u) << gbase;
+  EpiGroupSmem* S = &SM[warp * GPW + grp];
+  const int stride = gridDim.x * 4 * GPW;              // items per sweep of the persistent grid
   int slot_base = 0, slots_left = 0;
-  int i = blockIdx.x * 4 + warp;
-  uint32_t next = (i < n) ? __ldg(&tasks[i].w[lane]) : 0u;
-  for (; i < n; i += nw) {
-    const uint32_t tw = next;
-    if (i + nw < n) next = __ldg(&tasks[i + nw].w[lane]);
-    if (!(__shfl_sync(0xffffffffu, tw, ST_FLAGS) & ST_ACTIVE)) continue;
-    epi_search_item(frames, cur_slot, cam, o, tw, i, S, lane, jobs, job_count, slot_base, slots_left, search, api_results);
-    __syncwarp();
+  int i = (blockIdx.x * 4 + warp) * GPW + grp;
+  uint4 next = (i < n) ? __ldg(reinterpret_cast<const uint4*>(&tasks[i]) + sub) : make_uint4(0, 0, 0, 0);
+  for (; i < n; i += stride) {
+    const uint4 tq = next;
+    if (i + stride < n) next = __ldg(reinterpret_cast<const uint4*>(&tasks[i + stride]) + sub);
+    if (!(task_word(tq, ST_FLAGS, gbase, gmask) & ST_ACTIVE)) continue;
+    epi_search_item(frames, cur_slot, cam, o, tq, i, S, sub, gbase, gmask, jobs, job_count, slot_base, slots_left, search, api_results);
+    __syncwarp(gmask);
   }
   // reserved but unused job slots become empty jobs
-  for (int k = lane; k < slots_left; k += 32) jobs[slot_base + (JOB_BATCH - slots_left) + k].level_mode = -1;
+  for (int k = sub; k < slots_left; k += GL) jobs[slot_base + (JOB_BATCH - slots_left) + k].level_mode = -1;
 }
 
 // phase 4: thread per seed — triangulation, tau, Gaussian x Beta update, status
@@ -1016,36 +1039,38 @@ __global__ void __launch_bounds__(128) match_geom_kernel(DevCam cam, int n, cons
 
 struct MatchSmem { __align__(16) uint8_t pwb[112]; };
 
-// matcher.cpp:176-178: warpAffine of the 10x10 patch by a full warp, then the LK job (one coalesced 128-byte store)
+// matcher.cpp:176-178: warpAffine of the 10x10 patch by a group of 8 lanes (four candidates per warp), then the LK job
 __global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* frames, int n, const svob200_feature_ref* ftrs,
                                                             const double* px_in, const MatchGeom* geom, LkJob* jobs,
                                                             svob200_match_result* results)
 {
-  __shared__ MatchSmem SM[4];
+  __shared__ MatchSmem SM[4 * GPW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 4 + warp;
+  const int sub = lane & (GL - 1), grp = lane / GL;
+  const unsigned gmask = ((1u << GL) - 1u) << (grp * GL);
+  const int i = (blockIdx.x * 4 + warp) * GPW + grp;
   if (i >= n) return;
   const MatchGeom* gp = &geom[i];
   const int flags = gp->flags;
   if (!(flags & 1)) return;
-  MatchSmem* S = &SM[warp];
+  MatchSmem* S = &SM[warp * GPW + grp];
   const svob200_feature_ref* fp = &ftrs[i];
   const int level = fp->level, type = fp->type, ref_image = fp->ref_image, cur_image = fp->cur_image, L = gp->L;
-  for (int k = lane; k < 28; k += 32) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0;
-  __syncwarp();
+  for (int k = sub; k < 28; k += GL) reinterpret_cast<uint32_t*>(S->pwb)[k] = 0;
+  __syncwarp(gmask);
   if (flags & 2) {
     const DevFrame& ref = frames[(int)fp->ref_frame_id];
     const uint8_t* rimg = ref.lvl[level] + (size_t)ref_image * ref.img_stride[level];
-    warp_patch_10x10(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, lane);
+    warp_patch_10x10(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, sub);
   }
-  __syncwarp();
+  __syncwarp(gmask);
   if (results) {
     svob200_match_result* R = &results[i];
-    for (int k = lane; k < 100; k += 32) R->patch_with_border[k] = S->pwb[k];
-    for (int k = lane; k < 64; k += 32) R->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
+    for (int k = sub; k < 100; k += GL) R->patch_with_border[k] = S->pwb[k];
+    for (int k = sub; k < 64; k += GL) R->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
   }
   const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
-  emit_lk_job(&jobs[i], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), gp->dir0, gp->dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), lane);
+  emit_lk_job(&jobs[i], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), gp->dir0, gp->dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), sub);
 }
 
 // stand-alone align2D / align1D on caller-provided patches: thread per problem builds the job
@@ -1170,7 +1195,7 @@ int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& ca
   match_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_depth_ref, d_px_in, opts, geom, jobs, d_results, d_px_out, d_ok_out,
                                                     d_active, d_level_out, d_A_out);
   if (marks) cudaEventRecord(marks[0], s);
-  match_prepare_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_frames, n, d_ftrs, d_px_in, geom, jobs, d_results);
+  match_prepare_kernel<<<(n + 4 * GPW - 1) / (4 * GPW), 128, 0, s>>>(d_frames, n, d_ftrs, d_px_in, geom, jobs, d_results);
   *launches += 2;
   if (marks) cudaEventRecord(marks[1], s);
   LkSink sink{};
@@ -1180,16 +1205,20 @@ int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& ca
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// persistent grid of the search kernel: 8 CTAs of 4 warps per SM
-static int search_grid(int n)
+// persistent grid of the search kernel: SEARCH_CTAS CTAs of 4 warps (16 groups) per SM
+static int search_sms()
 {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int want = (n + 3) / 4, cap = sms * 8;
+  return sms;
+}
+static int search_grid(int n)
+{
+  const int want = (n + 4 * GPW - 1) / (4 * GPW), cap = search_sms() * SEARCH_CTAS;
   return want < cap ? want : cap;
 }
-// LK jobs are compacted; a warp reserves JOB_BATCH slots at a time, so the list can exceed n by the unused tail of every warp
-static size_t job_capacity(size_t m) { return m + (size_t)JOB_BATCH * 4 * 8 * 512; }
+// LK jobs are compacted; a group reserves JOB_BATCH slots at a time, so the list can exceed n by the unused tail of every group
+static size_t job_capacity(size_t m) { return m + (size_t)JOB_BATCH * 4 * GPW * ((size_t)search_sms() * 8 + 8); }
 
 size_t epipolar_scratch_bytes(int n)
 {
