@@ -146,6 +146,9 @@ __device__ float exact_chi2_chain(const float* res, const uint8_t* visible, cons
 }
 
 constexpr int NACC = 32;   // 21 (H upper) + 6 (J*res) + chi2 + n_meas + 3 pad
+#ifndef ALIGN_CTAS_128
+#define ALIGN_CTAS_128 4
+#endif
 
 // After this, lane L of the warp holds the warp-wide sum of v[L]  (31 shuffles instead of 160).
 __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int lane)
@@ -163,12 +166,11 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int l
   return v[0];
 }
 
-// One CTA per alignment problem.  Every Gauss-Newton iteration is three data-parallel phases
-//   P1  thread per feature : project xyz_ref with the current model (double), bounds test
-//   P2  thread per pixel   : bilinear intensity, residual (float, bit-identical to the reference)
-//   P3  thread per feature : the 16 pixel Jacobian rows of a feature are dx*a + dy*b with the SAME two
-//                            6-vectors a, b, so  sum J J^T = Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T  and
-//                            sum J r = Sxr a + Syr b : five double sums over the patch, then 27 entries
+// One CTA per alignment problem.  Every Gauss-Newton iteration is ONE data-parallel pass with a thread per feature:
+//   project xyz_ref with the current model (double), bounds test; fetch the 5x5 window of the current image under the
+//   4x4 patch once (10 aligned word loads instead of 64 byte loads); 16 bilinear residuals (float, bit-identical to the
+//   reference); the 16 pixel Jacobian rows of a feature are dx*a + dy*b with the SAME two 6-vectors a, b, so
+//   sum J J^T = Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T and sum J r = Sxr a + Syr b : five double sums, then 27 entries
 // followed by one block reduction and the serial solve / update / decision on thread 0.
 //
 // CLUSTER > 1 (single-stream latency): one thread-block CLUSTER per problem.  Each CTA of the cluster owns a contiguous
@@ -176,7 +178,7 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int l
 // shared memory, rank 0 adds them in rank order (deterministic), solves, decides, and pushes the new model and the
 // control word into every CTA's shared memory; two hardware cluster barriers per iteration.
 template <int BLOCK, int CLUSTER>
-__global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : 512 / BLOCK) sparse_align_kernel(AlignArgs A)
+__global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN_CTAS_128 : 512 / BLOCK)) sparse_align_kernel(AlignArgs A)
 {
   constexpr int NW = BLOCK / 32;
   __shared__ double s_model[7];
@@ -273,7 +275,14 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : 512 / BLOCK) sparse_a
     for (int iter = 0; iter < A.opts.n_iter; ++iter) {
       float* res = A.res[pp] + 16 * (size_t)f0;
       uint8_t* contrib = A.contrib[pp] + f0;
-      // ---------------- P1: projection (sparse_img_align.cpp:219-231)
+      // ---------------- one pass, thread per feature (sparse_img_align.cpp:219-266 + the normal equations):
+      //   project with the current model (double) -> bounds test -> the 5x5 window of the current image that the 4x4
+      //   patch's bilinear taps touch (two aligned words per row) -> 16 residuals (float, the reference's expression and
+      //   order per pixel) -> five patch sums -> 27 normal-equation entries.  Nothing but `res` / `contrib` (needed by the
+      //   exact chi2 replay) goes back to memory, and there is no barrier between projection, residuals and sums.
+      double acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
       {
         double m[7];
 #pragma unroll
@@ -287,61 +296,61 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : 512 / BLOCK) sparse_a
           const int u_i = (int)floorf(u_cur), v_i = (int)floorf(v_cur);
           const bool in = !(u_i < 0 || v_i < 0 || u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= ccols || v_i + 3 >= crows);
           contrib[i] = in ? 1 : 0;
-          uv[i] = make_float2(u_cur, v_cur);
-        }
-      }
-      __syncthreads();
-      // ---------------- P2: residuals (sparse_img_align.cpp:233-266)
-      for (int idx = lo * 16 + tid; idx < hi * 16; idx += BLOCK) {
-        const int i = idx >> 4, p = idx & 15;
-        if (!visible[i] || !contrib[i]) continue;
-        const float2 c = uv[i];
-        const int u_i = (int)floorf(c.x), v_i = (int)floorf(c.y);
-        const float su = c.x - u_i, sv = c.y - v_i;
-        const float w_tl = (float)((1.0 - su) * (1.0 - sv));
-        const float w_tr = (float)(su * (1.0 - sv));
-        const float w_bl = (float)((1.0 - su) * sv);
-        const float w_br = su * sv;
-        const int yy = p >> 2, xx = p & 3;
-        const uint8_t* q = cimg + (size_t)(v_i + yy - 2) * cstride + (u_i + xx - 2);
-        const float intensity = w_tl * q[0] + w_tr * q[1] + w_bl * q[cstride] + w_br * q[cstride + 1];
-        res[idx] = intensity - ref_patch[idx];
-      }
-      __syncthreads();
-      // ---------------- P3: normal equations, one feature per thread
-      double acc[NACC];
+          if (!in) continue;
+          const float su = u_cur - u_i, sv = v_cur - v_i;
+          const float w_tl = (float)((1.0 - su) * (1.0 - sv));
+          const float w_tr = (float)(su * (1.0 - sv));
+          const float w_bl = (float)((1.0 - su) * sv);
+          const float w_br = su * sv;
+          // window rows v_i-2 .. v_i+2, columns u_i-2 .. u_i+2
+          float W[5][5];
+          {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(cimg + (size_t)(v_i - 2) * cstride + (u_i - 2));
+            const unsigned sh = (unsigned)(a0 & 3) * 8;
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(a0 & ~(uintptr_t)3);
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-      for (int i = lo + tid; i < hi; i += BLOCK) {
-        if (!visible[i] || !contrib[i]) continue;
-        const float4* r4 = reinterpret_cast<const float4*>(res + 16 * (size_t)i);
-        const float4* x4 = reinterpret_cast<const float4*>(gdx + 16 * (size_t)i);
-        const float4* y4 = reinterpret_cast<const float4*>(gdy + 16 * (size_t)i);
-        double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0, Srr = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 r = r4[q], dx = x4[q], dy = y4[q];
-          const float rv[4] = {r.x, r.y, r.z, r.w}, xv[4] = {dx.x, dx.y, dx.z, dx.w}, yv[4] = {dy.x, dy.y, dy.z, dy.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const double X = (double)xv[e], Y = (double)yv[e], Rr = (double)rv[e];
-            Sxx += X * X; Sxy += X * Y; Syy += Y * Y; Sxr += X * Rr; Syr += Y * Rr;
-            Srr += (double)(rv[e] * rv[e] * 1.0f);          // the reference's float term res*res*weight
+            for (int r = 0; r < 5; ++r) {
+              const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (size_t)r * cstride);      // cstride % 4 == 0
+              const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+              const uint32_t lo4 = __funnelshift_r(w0, w1, sh), b4 = (w1 >> sh) & 0xffu;
+              W[r][0] = (float)(lo4 & 0xffu); W[r][1] = (float)((lo4 >> 8) & 0xffu); W[r][2] = (float)((lo4 >> 16) & 0xffu);
+              W[r][3] = (float)(lo4 >> 24); W[r][4] = (float)b4;
+            }
           }
+          const float4* p4 = reinterpret_cast<const float4*>(ref_patch + 16 * (size_t)i);
+          const float4* x4 = reinterpret_cast<const float4*>(gdx + 16 * (size_t)i);
+          const float4* y4 = reinterpret_cast<const float4*>(gdy + 16 * (size_t)i);
+          float4* r4 = reinterpret_cast<float4*>(res + 16 * (size_t)i);
+          double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0, Srr = 0;
+#pragma unroll
+          for (int yy = 0; yy < 4; ++yy) {
+            const float4 rp = p4[yy], dx = x4[yy], dy = y4[yy];
+            const float pv[4] = {rp.x, rp.y, rp.z, rp.w}, xv[4] = {dx.x, dx.y, dx.z, dx.w}, yv[4] = {dy.x, dy.y, dy.z, dy.w};
+            float rv[4];
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx) {
+              const float intensity = w_tl * W[yy][xx] + w_tr * W[yy][xx + 1] + w_bl * W[yy + 1][xx] + w_br * W[yy + 1][xx + 1];
+              rv[xx] = intensity - pv[xx];
+              const double X = (double)xv[xx], Y = (double)yv[xx], Rr = (double)rv[xx];
+              Sxx += X * X; Sxy += X * Y; Syy += Y * Y; Sxr += X * Rr; Syr += Y * Rr;
+              Srr += (double)(rv[xx] * rv[xx] * 1.0f);          // the reference's float term res*res*weight
+            }
+            r4[yy] = make_float4(rv[0], rv[1], rv[2], rv[3]);
+          }
+          const double* ja = jab + 12 * (size_t)i;
+          double a[6], bb[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { a[k] = ja[k]; bb[k] = ja[6 + k]; }
+          int h = 0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+#pragma unroll
+            for (int c = r; c < 6; ++c) acc[h++] += Sxx * (a[r] * a[c]) + Sxy * (a[r] * bb[c] + bb[r] * a[c]) + Syy * (bb[r] * bb[c]);
+            acc[21 + r] += Sxr * a[r] + Syr * bb[r];
+          }
+          acc[27] += Srr;
+          acc[28] += 16.0;
         }
-        const double* ja = jab + 12 * (size_t)i;
-        double a[6], bb[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { a[k] = ja[k]; bb[k] = ja[6 + k]; }
-        int h = 0;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-#pragma unroll
-          for (int c = r; c < 6; ++c) acc[h++] += Sxx * (a[r] * a[c]) + Sxy * (a[r] * bb[c] + bb[r] * a[c]) + Syy * (bb[r] * bb[c]);
-          acc[21 + r] += Sxr * a[r] + Syr * bb[r];
-        }
-        acc[27] += Srr;
-        acc[28] += 16.0;
       }
       // ---------------- block reduction
       const double mine = warp_transpose_reduce(acc, lane);

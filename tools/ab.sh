@@ -1,6 +1,6 @@
 #!/bin/bash
-# A/B bench of alternative builds of libsvob200 (android_svo_b200/lib/libsvob200_<tag>.so) on the GPU box:
-#   bash tools/ab.sh A B ...
+# A/B runs of alternative builds of libsvob200.so (android_svo_b200/lib/libsvob200_<tag>.so) on the GPU box:
+#   bash tools/ab.sh A B5 B6
 for v in "$@"; do
   SVOB200_LIB=$PWD/android_svo_b200/lib/libsvob200_$v.so python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python -c "
