@@ -129,20 +129,42 @@ __device__ void ldlt6_solve(const double* Hin, const double* b, double* x)
   for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
-// the reference's `float chi2; chi2 += res*res*weight` in feature-list / row-major pixel order
-__device__ float exact_chi2_chain(const float* res, const uint8_t* visible, const uint8_t* contrib, int N)
+// The reference's `float chi2; chi2 += res*res*weight` in feature-list / row-major pixel order.  The chain of float
+// additions is inherently sequential (4 cycles per FADD); everything around it is not: the whole CTA fetches the
+// residuals of a chunk of features (coalesced, L2: the other CTAs of a cluster wrote some of them), squares them
+// (res*res*1.0f, the reference's float term) into shared memory, and thread 0 only adds.  Bit-identical to the
+// single-thread loop it replaces, at ~64 cycles per contributing feature instead of ~150-200.
+constexpr int CHAIN_F = 128;            // features per staged chunk (8 KB of squares)
+
+__device__ void exact_chi2_chain_block(const float* res, const uint8_t* visible, const uint8_t* contrib, int N, float* s_sq, uint8_t* s_fl,
+                                       float* out_sum, int* out_cnt, int tid, int nthreads)
 {
   float chi2 = 0.0f;
-  for (int i = 0; i < N; ++i) {
-    if (!visible[i] || !contrib[i]) continue;
-    const float4* p = reinterpret_cast<const float4*>(res + 16 * (size_t)i);
-    const float4 a = p[0], b = p[1], c = p[2], d = p[3];
-    chi2 += a.x * a.x * 1.0f; chi2 += a.y * a.y * 1.0f; chi2 += a.z * a.z * 1.0f; chi2 += a.w * a.w * 1.0f;
-    chi2 += b.x * b.x * 1.0f; chi2 += b.y * b.y * 1.0f; chi2 += b.z * b.z * 1.0f; chi2 += b.w * b.w * 1.0f;
-    chi2 += c.x * c.x * 1.0f; chi2 += c.y * c.y * 1.0f; chi2 += c.z * c.z * 1.0f; chi2 += c.w * c.w * 1.0f;
-    chi2 += d.x * d.x * 1.0f; chi2 += d.y * d.y * 1.0f; chi2 += d.z * d.z * 1.0f; chi2 += d.w * d.w * 1.0f;
+  int cnt = 0;
+  for (int c0 = 0; c0 < N; c0 += CHAIN_F) {
+    const int m = min(CHAIN_F, N - c0);
+    for (int k = tid; k < m; k += nthreads) s_fl[k] = (__ldcg(visible + c0 + k) && __ldcg(contrib + c0 + k)) ? 1 : 0;
+    const float4* src = reinterpret_cast<const float4*>(res + 16 * (size_t)c0);
+    for (int k = tid; k < m * 4; k += nthreads) {
+      const float4 a = __ldcg(src + k);
+      reinterpret_cast<float4*>(s_sq)[k] = make_float4(a.x * a.x * 1.0f, a.y * a.y * 1.0f, a.z * a.z * 1.0f, a.w * a.w * 1.0f);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int f = 0; f < m; ++f) {
+        if (!s_fl[f]) continue;
+        const float4* p = reinterpret_cast<const float4*>(s_sq + 16 * f);
+        const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+        chi2 += a.x; chi2 += a.y; chi2 += a.z; chi2 += a.w;
+        chi2 += b.x; chi2 += b.y; chi2 += b.z; chi2 += b.w;
+        chi2 += c.x; chi2 += c.y; chi2 += c.z; chi2 += c.w;
+        chi2 += d.x; chi2 += d.y; chi2 += d.z; chi2 += d.w;
+        cnt += 16;
+      }
+    }
+    __syncthreads();
   }
-  return chi2;
+  if (tid == 0) { *out_sum = chi2; *out_cnt = cnt; }
 }
 
 constexpr int NACC = 32;   // 21 (H upper) + 6 (J*res) + chi2 + n_meas + 3 pad
@@ -187,6 +209,11 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   __shared__ double s_tot[NACC];
   __shared__ double s_clu[CLUSTER > 1 ? CLUSTER : 1][NACC];   // rank 0 only: the partial sums of every CTA of the cluster
   __shared__ int s_ctrl;          // 0 continue iterating, 1 leave this level
+  __shared__ int s_need;          // exact chi2 replay wanted: bit 0 this evaluation, bit 1 the previous one as well
+  __shared__ float s_chain[2];
+  __shared__ int s_chain_n[2];
+  __shared__ __align__(16) float s_sq[CHAIN_F * 16];
+  __shared__ uint8_t s_fl[CHAIN_F];
 
   const int b = CLUSTER > 1 ? blockIdx.x / CLUSTER : blockIdx.x;
   const int rank = CLUSTER > 1 ? (int)(blockIdx.x % CLUSTER) : 0;
@@ -375,9 +402,13 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       }
       __syncthreads();
 
-      // ---------------- solve / decide / update (thread 0 of rank 0), nlls_solver_impl.hpp:36-99
+      // ---------------- solve (thread 0 of rank 0), nlls_solver_impl.hpp:36-99
+      double xs[6];
+      int n_meas = 0;
+      double new_chi2 = 0.0;
+      bool new_exact = false;
       if (lead) {
-        double H[36], Jres[6], xs[6];
+        double H[36], Jres[6];
         int h = 0;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
@@ -385,9 +416,8 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
           for (int c = r; c < 6; ++c) { H[r * 6 + c] = s_tot[h]; H[c * 6 + r] = s_tot[h]; ++h; }
           Jres[r] = -s_tot[21 + r];
         }
-        const int n_meas = (int)s_tot[28];
-        double new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
-        bool new_exact = false;
+        n_meas = (int)s_tot[28];
+        new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
         ldlt6_solve(H, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
 #pragma unroll
@@ -396,24 +426,33 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         for (int k = 0; k < 6; ++k) { R->Jres[k] = Jres[k]; R->x[k] = xs[k]; }
         R->n_meas = n_meas;
         R->iters[level] += 1;
-        int ctrl = 0;
+        int need = 0;
         if (iter > 0 && !stop_) {
           // worst-case first-order rounding error of two sequential float sums of n_meas terms
           const double tol = 2.0 * (double)n_meas * 5.9604644775390625e-08;
           const double big = fmax(fabs(new_chi2), fabs(chi2_));
-          if (fabs(new_chi2 - chi2_) <= tol * big) {
-            ++n_exact;
-            new_chi2 = (double)(exact_chi2_chain(res, visible, contrib, N) / (float)n_meas);
-            new_exact = true;
-            if (!chi2_exact) {
-              // previous evaluation lives in the other ping-pong buffer
-              const float prev = exact_chi2_chain(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N);
-              int pn = 0;
-              for (int i = 0; i < N; ++i) pn += (visible[i] && A.contrib[pp ^ 1][f0 + i]) ? 16 : 0;
-              chi2_ = (double)(prev / (float)pn);
-              chi2_exact = true;
-            }
-          }
+          if (fabs(new_chi2 - chi2_) <= tol * big) need = chi2_exact ? 1 : 3;
+        }
+        s_need = need;
+      }
+      // ---------------- exact replay of the reference's float chi2 chain(s), when the decision hangs on it (rank 0's CTA)
+      if (rank == 0) {
+        __syncthreads();
+        const int need = s_need;
+        if (need & 1) exact_chi2_chain_block(res, visible, contrib, N, s_sq, s_fl, &s_chain[0], &s_chain_n[0], tid, BLOCK);
+        // the previous evaluation lives in the other ping-pong buffer
+        if (need & 2) exact_chi2_chain_block(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_sq, s_fl, &s_chain[1], &s_chain_n[1], tid, BLOCK);
+        if (need) __syncthreads();
+      }
+      // ---------------- decide / update (thread 0 of rank 0)
+      if (lead) {
+        int ctrl = 0;
+        const int need = s_need;
+        if (need & 1) {
+          ++n_exact;
+          new_chi2 = (double)(s_chain[0] / (float)n_meas);
+          new_exact = true;
+          if (need & 2) { chi2_ = (double)(s_chain[1] / (float)s_chain_n[1]); chi2_exact = true; }
         }
         if ((iter > 0 && new_chi2 > chi2_) || stop_) {
 #pragma unroll
