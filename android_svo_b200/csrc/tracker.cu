@@ -8,6 +8,7 @@
 // reference does in host code is done by the glue kernels, so a step is 11 launches on one stream
 // with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
 // H2D of the small per-step inputs and one D2H of the per-sequence results.
+#include <cstdlib>
 #include "ctx_internal.h"
 
 namespace {
@@ -104,6 +105,12 @@ struct svob200_tracker {
   int chunk = 256;                     // sequences per H2D/compute pipeline chunk (host mode)
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
+  // single-stream latency: in device mode with small batches the 14 launches of a step are replayed as ONE CUDA graph
+  // (captured once per distinct set of buffer addresses: a camera ring buffer has only a few), which removes the
+  // per-launch driver cost and most of the inter-kernel gaps
+  struct StepGraph { std::vector<uintptr_t> key; cudaGraphExec_t exec; long long launches; };
+  std::vector<StepGraph> graphs;
+  int graph_max_batch = 64;
   // optional per-stage CUDA-event timing (bench.py's stage breakdown / roofline)
   bool profiling = false;
   cudaEvent_t ev[kNumStages + 1] = {};
@@ -124,6 +131,7 @@ int svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batc
   // Seed ctor depth_filter.cpp:36-45
   t->seed_init.a = 10; t->seed_init.b = 10; t->seed_init.mu = (float)(1.0 / depth_mean); t->seed_init.z_range = (float)(1.0 / depth_min);
   t->seed_init.sigma2 = t->seed_init.z_range * t->seed_init.z_range / 36;
+  if (const char* e = getenv("SVOB200_TRACKER_GRAPH")) t->graph_max_batch = atoi(e) > 0 ? atoi(e) : 0;   // 0 disables graph replay; N = largest batch replayed as a graph
   ++uid;
   t->fid_kf = -(uid * 4 + 1); t->fid_last = -(uid * 4 + 2); t->fid_cur = -(uid * 4 + 3);
   for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur})
@@ -141,6 +149,7 @@ void svob200_tracker_destroy(svob200_tracker* t)
   for (void* p : t->owned) cudaFree(p);
   if (t->h_pinned) cudaFreeHost(t->h_pinned);
   for (auto e : t->chunk_ev) cudaEventDestroy(e);
+  for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   for (int k = 0; k <= kNumStages; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   delete t;
@@ -319,10 +328,46 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
   if (mem == SVOB200_MEM_DEVICE) {
     // level 0 of the current frames aliases the caller's device buffer: no copy at all
     if (int e = svob200_frame_bind_only(ctx, t->fid_cur, cur_imgs, stride)) return e;
-    if (int e = run_range(t, 0, B, T_last_w, last_px, true)) return e;
-    if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
-    if (px_refined) CU(cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s));
-    if (match_ok) CU(cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s));
+    const bool use_graph = !t->profiling && B <= t->graph_max_batch && t->graph_max_batch > 0;
+    svob200_tracker::StepGraph* hit = nullptr;
+    std::vector<uintptr_t> key;
+    if (use_graph) {
+      // everything the kernels of a step receive BY VALUE: the buffers of this call and the two frame views
+      FrameRec* last = find_frame(ctx, t->fid_last);
+      key = {(uintptr_t)cur_imgs, (uintptr_t)stride, (uintptr_t)T_last_w, (uintptr_t)last_px, (uintptr_t)stats, (uintptr_t)px_refined,
+             (uintptr_t)match_ok, (uintptr_t)t->fid_cur, (uintptr_t)t->fid_last, (uintptr_t)last->f.lvl[0], (uintptr_t)last->f.pitch[0]};
+      for (auto& g : t->graphs) if (g.key == key) { hit = &g; break; }
+    }
+    if (hit) {
+      CU(cudaGraphLaunch(hit->exec, s));
+      ctx->launches += hit->launches;
+    } else {
+      const long long launches0 = ctx->launches;
+      if (use_graph) CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = run_range(t, 0, B, T_last_w, last_px, true);
+      cudaError_t ce = cudaSuccess;
+      if (!rc) {
+        if (stats) ce = cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s);
+        if (ce == cudaSuccess && px_refined) ce = cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s);
+        if (ce == cudaSuccess && match_ok) ce = cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s);
+      }
+      if (use_graph) {
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || ee != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: graph capture failed: %s", cudaGetErrorString(ee != cudaSuccess ? ee : ce)); }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: graph instantiate failed: %s", cudaGetErrorString(ie));
+        if (t->graphs.size() >= 64) { for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec); t->graphs.clear(); }
+        t->graphs.push_back({key, exec, ctx->launches - launches0});
+        CU(cudaGraphLaunch(exec, s));
+      } else {
+        if (rc) return rc;
+        if (ce != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: result copy failed: %s", cudaGetErrorString(ce));
+      }
+    }
   } else {
     // host buffers: the frame copy is split into chunks on a copy stream so that chunk c+1 crosses
     // PCIe while chunk c is being processed; one small H2D for the per-step inputs, one D2H for results
