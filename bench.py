@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences in the CPU sample (0 = 4 per host thread)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (ncu captures: only full-batch launches remain)")
+    ap.add_argument("--no-widen", action="store_true", help="skip the timing of the SURVEY 8f operators (reprojector, optimizers, YUV, seed init)")
     return ap.parse_args()
 
 
@@ -438,21 +440,29 @@ def run_b200(args, rank, world, local_rank):
 
     # ---------------- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
     wl.reset()
-    for k in range(W):
-        wl.step(order, k, capi.MEM_HOST)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(W, W + K):
-        wl.step(order, k, capi.MEM_HOST)
-    ctx.sync()
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    e2e_s = max_over_ranks(e2e_s)
+    if args.no_e2e:
+        for k in range(2):
+            wl.step(order, k, capi.MEM_DEVICE)
+        ctx.sync()
+        ctx.dev_download(wl.stats_host, wl.stats_dev)
+        e2e_s, order_last = float("nan"), order[2]
+    else:
+        for k in range(W):
+            wl.step(order, k, capi.MEM_HOST)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(W, W + K):
+            wl.step(order, k, capi.MEM_HOST)
+        ctx.sync()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        e2e_s = max_over_ranks(e2e_s)
+        order_last = order[W + K]
     e2e_value = total * K / e2e_s
     stats_last = wl.stats_host.copy()
 
     # ---------------- per-sequence statistics: NCCL gather over NVLink, 64 B per sequence
-    gt = wl.poses[:, 1 + order[W + K]]
+    gt = wl.poses[:, 1 + order_last]
     perr = np.array([synth.pose_error(stats_last["T_cur_w"][b], gt[b]) for b in range(wl.B)])
     rec = sharding.gather_records(sharding.make_records(seq_ids, stats_last, perr), world, "cuda")
     seq_stats = sharding.summarize(rec)
@@ -468,7 +478,7 @@ def run_b200(args, rank, world, local_rank):
                                    "block-sharded over %d GPU(s); step = 1 frame of every sequence" % (total, N, S, world),
                        "sequences_total": total, "sequences_per_gpu": per, "frame_pool": list(POOL_INDICES),
                        "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (per * cfg["w"] * cfg["h"] / 1e6)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d_bytes * world),
+            "e2e": {"skipped": "--no-e2e"} if args.no_e2e else {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d_bytes * world),
                     "d2h_bytes_per_step": int(wl.d2h_bytes * world), "ms_per_step": round(e2e_s / K * 1e3, 4),
                     "h2d_GBps_per_gpu": round(wl.h2d_bytes / (e2e_s / K) / 1e9, 2), "pcie_h2d_GBps_measured": round(pcie, 2),
                     "note": "host-buffer path is PCIe-bound: the frame upload (307,200 B/frame) is chunked and overlapped with compute"},
@@ -477,6 +487,188 @@ def run_b200(args, rank, world, local_rank):
             "setup_s": round(t_setup, 1),
         }
     return out, ctx, wl
+
+
+def widen_rows(ctx, capi, wl, cfg, peak, steps=5, warm=2):
+    """The callers either side of the hot path, timed on the device over the same batch of sequences
+    (CUDA events on the context's stream, inputs resident) next to the reference's own CPU code on one host core:
+      yuv_pyramid      svob200_frame_upload_yuv420    YUV_420_888 -> gray -> pyramid, one fused kernel (HBM-bound)
+      reproject_map    svob200_reproject_map          grid + batched findMatchDirect + per-cell / maxFts rules
+      pose_optimize    svob200_pose_optimize          motion-only Gauss-Newton per frame
+      points_optimize  svob200_points_optimize        Point::optimize for every map point (3 observations each)
+      seeds_initialize svob200_seeds_initialize       occupancy + FAST + Shi-Tomasi + grid + Seed ctor"""
+    import ctypes as C
+    B, N, w, h = wl.B, cfg["n_features"], cfg["w"], cfg["h"]
+    out = {}
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        return ctx.timer_stop_ms() / steps
+
+    def dev(a):
+        a = np.ascontiguousarray(a)
+        d = ctx.dev_alloc(max(a.nbytes, 1))
+        ctx.dev_upload(d, a)
+        return d
+
+    L, P, V = ctx.L, capi._ptr, C.c_void_p
+    frees = []
+    try:
+        # ---- frames: keyframe batch (id 901) and a current batch (id 902) with the pose of pool frame 1
+        ctx.frame_create(901, B, w, h, cfg["n_levels"]); ctx.frame_upload(901, wl.kf_host)
+        ctx.frame_create(902, B, w, h, cfg["n_levels"])
+        ctx._ck(L.svob200_frame_upload(ctx.h, 902, V(wl.pool_dev[1]), w, None, capi.MEM_DEVICE))
+        T_cur = np.ascontiguousarray(wl.poses[:, 2]); T_kf = np.ascontiguousarray(wl.poses[:, 0])
+        # ---- YUV input stage: Y = the live frame, neutral chroma (NV21 layout: one interleaved VU plane)
+        d_y = wl.pool_dev[2]
+        d_vu = ctx.dev_alloc(B * (h // 2) * w + 16); frees.append(d_vu)
+        chroma = np.full(B * (h // 2) * w + 16, 128, np.uint8)
+        ctx.dev_upload(d_vu, chroma)
+        ctx.frame_create(903, B, w, h, cfg["n_levels"])
+        ms = timed(lambda: ctx.frame_upload_yuv420(903, d_y, d_vu + 1, d_vu, w, w, 2, w * h, (h // 2) * w, mem=capi.MEM_DEVICE))
+        lv = sum((w >> l) * (h >> l) for l in range(1, cfg["n_levels"]))
+        alg = B * (w * h * 1.5 + w * h + lv)            # read Y + VU once, write gray once, write every coarser level once
+        out["yuv_pyramid"] = {"ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1), "algorithmic_bytes": int(alg),
+                              "alg_GBps": round(alg / ms / 1e6, 1), "hbm_frac": round(alg / ms / 1e6 / peak, 4), "bound": "hbm"}
+        ctx.frame_release(903)
+        # ---- reprojector: every map point of the keyframe, one observation each
+        pts = np.zeros(B * N, capi.map_point_dt)
+        pts["pos"] = wl.kf["pt_world"].reshape(-1, 3); pts["type"] = capi.POINT_UNKNOWN
+        pts["obs_begin"] = np.arange(B * N); pts["obs_end"] = np.arange(B * N) + 1
+        obs = np.zeros(B * N, capi.feature_ref_dt)
+        obs["ref_frame_id"] = ctx.frame_slot(901); obs["ref_image"] = np.repeat(np.arange(B), N); obs["level"] = wl.kf["kf_level"].reshape(-1)
+        px = wl.kf["kf_px"].reshape(-1, 2)
+        obs["px"] = px
+        fv = np.stack([(px[:, 0] - cfg["cx"]) / cfg["fx"], (px[:, 1] - cfg["cy"]) / cfg["fy"], np.ones(len(px))], 1)
+        obs["f"] = fv / np.linalg.norm(fv, axis=1, keepdims=True); obs["grad"] = (1.0, 0.0)
+        cell, max_fts = 30, 120
+        n_cells = -(-w // cell) * -(-h // cell)
+        d_T, d_off, d_pts, d_obs = dev(T_cur), dev(np.arange(B + 1, dtype=np.int32) * N), dev(pts), dev(obs)
+        d_To = dev(np.repeat(T_kf, N, axis=0))
+        d_res = ctx.dev_alloc(B * N * capi.reproj_result_dt.itemsize); d_win = ctx.dev_alloc(B * n_cells * 4); d_st = ctx.dev_alloc(B * 16)
+        frees += [d_T, d_off, d_pts, d_obs, d_To, d_res, d_win, d_st]
+        mo = ctx.matcher_opts(cfg["n_pyr"])
+        ms = timed(lambda: ctx._ck(L.svob200_reproject_map(ctx.h, 902, C.byref(wl.cam), B, V(d_T), V(d_off), B * N, V(d_pts), B * N, V(d_obs), V(d_To),
+                                                           cell, max_fts, C.byref(mo), V(d_res), V(d_win), V(d_st), capi.MEM_DEVICE)))
+        st = np.zeros(B, capi.reproj_stats_dt); ctx.dev_download(st, d_st)
+        res = np.zeros(B * N, capi.reproj_result_dt); ctx.dev_download(res, d_res)
+        out["reproject_map"] = {"ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1), "points_per_frame": N,
+                                "matches_mean": float(st["n_matches"].mean()), "trials_mean": float(st["n_trials"].mean())}
+        # ---- pose optimizer on the matched features of every frame (alignment pose perturbed by the tracker's own error)
+        ok = res["status"] == capi.REPROJ_MATCHED
+        cnt = ok.reshape(B, N).sum(1)
+        foff = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        pxm = res["px"][ok]
+        fm = np.stack([(pxm[:, 0] - cfg["cx"]) / cfg["fx"], (pxm[:, 1] - cfg["cy"]) / cfg["fy"], np.ones(len(pxm))], 1)
+        fm /= np.linalg.norm(fm, axis=1, keepdims=True)
+        d_foff, d_f, d_lv, d_pos = dev(foff), dev(fm), dev(res["search_level"][ok].astype(np.int32)), dev(pts["pos"][ok])
+        d_Tp = ctx.dev_alloc(T_cur.nbytes); d_pr = ctx.dev_alloc(B * capi.pose_opt_result_dt.itemsize); d_out = ctx.dev_alloc(max(int(ok.sum()), 1))
+        frees += [d_foff, d_f, d_lv, d_pos, d_Tp, d_pr, d_out]
+        po = ctx.pose_opt_opts()
+
+        def pose_run():
+            ctx.dev_upload(d_Tp, T_cur)
+            ctx._ck(L.svob200_pose_optimize(ctx.h, C.byref(wl.cam), B, V(d_foff), V(d_f), V(d_lv), V(d_pos), C.byref(po), V(d_Tp), V(d_pr), V(d_out), capi.MEM_DEVICE))
+        ms = timed(pose_run)
+        pr = np.zeros(B, capi.pose_opt_result_dt); ctx.dev_download(pr, d_pr)
+        out["pose_optimize"] = {"ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1), "features_mean": float(cnt.mean()),
+                                "iters_mean": float(pr["iters"].mean()), "error_final_px_median": float(np.median(pr["error_final"])),
+                                "note": "includes the 229 KB pose re-upload per run"}
+        # ---- structure optimisation: every map point seen from the keyframe and two live frames
+        Tobs = np.stack([wl.poses[:, 0], wl.poses[:, 1], wl.poses[:, 3]], 1)              # [B, 3, 7]
+        pw = wl.kf["pt_world"].reshape(B, N, 3)
+        fb = np.zeros((B, N, 3, 3))
+        for k in range(3):
+            pc = q_rot_many(Tobs[:, None, k, 3:], pw) + Tobs[:, None, k, :3]
+            fb[:, :, k] = pc / np.linalg.norm(pc, axis=-1, keepdims=True)
+        d_ooff, d_To3, d_fb = dev(np.arange(B * N + 1, dtype=np.int32) * 3), dev(np.repeat(Tobs[:, None], N, axis=1).reshape(-1, 7)), dev(fb.reshape(-1, 3))
+        pos0 = pw.reshape(-1, 3) + np.random.RandomState(1).normal(0, 0.01, (B * N, 3))
+        d_p0 = ctx.dev_alloc(pos0.nbytes)
+        frees += [d_ooff, d_To3, d_fb, d_p0]
+
+        def pts_run():
+            ctx.dev_upload(d_p0, pos0)
+            ctx._ck(L.svob200_points_optimize(ctx.h, B * N, V(d_ooff), V(d_To3), V(d_fb), 20, 1e-10, V(d_p0), None, capi.MEM_DEVICE))
+        ms = timed(pts_run)
+        got = np.zeros_like(pos0); ctx.dev_download(got, d_p0)
+        out["points_optimize"] = {"ms": round(ms, 4), "points_per_s": round(B * N / ms * 1e3, 1), "obs_per_point": 3,
+                                  "median_error_m": float(np.median(np.linalg.norm(got - pw.reshape(-1, 3), axis=1))),
+                                  "note": "includes the 11.8 MB start-position re-upload per run"}
+        # ---- seed initialisation on the keyframe batch
+        d_eoff, d_epx = dev(np.arange(B + 1, dtype=np.int32) * N), dev(wl.kf["kf_px"].reshape(-1, 2))
+        d_dm, d_dn = dev(np.full(B, DEPTH_MEAN, np.float32)), dev(np.full(B, DEPTH_MIN, np.float32))
+        fc = frontend.DETECT[CFG_NAME][2]
+        nc = -(-w // fc) * -(-h // fc)
+        d_co, d_so, d_cn = ctx.dev_alloc(B * nc * 16), ctx.dev_alloc(B * nc * 20), ctx.dev_alloc(B * 4)
+        frees += [d_eoff, d_epx, d_dm, d_dn, d_co, d_so, d_cn]
+        ms = timed(lambda: ctx._ck(L.svob200_seeds_initialize(ctx.h, 901, cfg["n_pyr"], fc, frontend.DETECT[CFG_NAME][3], V(d_eoff), V(d_epx), V(d_dm), V(d_dn),
+                                                              V(d_co), V(d_so), V(d_cn), capi.MEM_DEVICE)))
+        cn = np.zeros(B, np.int32); ctx.dev_download(cn, d_cn)
+        alg = B * (408000.0 + nc * 36)
+        out["seeds_initialize"] = {"ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1), "new_seeds_mean": float(cn.mean()),
+                                   "alg_GBps": round(alg / ms / 1e6, 1), "hbm_frac": round(alg / ms / 1e6 / peak, 4)}
+    finally:
+        for fid in (901, 902):
+            try:
+                ctx.frame_release(fid)
+            except Exception:
+                pass
+        for d in frees:
+            ctx.dev_free(d)
+    return out
+
+
+def widen_cpu(cfg):
+    """The same operators in the reference's own code (oracle/_ref/libsvo_ref.so) on ONE host core, per frame / per
+    point, on a bounded sample; the YUV stage is the oracle's port of the app's loop + cv2-equivalent gray (kind: port)."""
+    from oracle.pyoracle import Oracle, Cam
+    from oracle import pyoracle_map as pm
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import map_scenes as ms
+    oracle = Oracle()
+    om, rm = pm.OracleMap(oracle), pm.RefMap()
+    out = {"cores": 1}
+    w, h = cfg["w"], cfg["h"]
+    fr = ms.yuv_frame(w, h, 1, 2, 0)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        g = om.yuv420_to_gray(fr["y"], fr["u"], fr["v"], fr["uv_stride"], 2, w, h, fr["y_stride"]); oracle.pyramid(g, cfg["n_levels"])
+    out["yuv_pyramid_ms_per_frame"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
+    if not rm.available():
+        out["kind"] = "port (reference .so not built)"
+        return out
+    out["kind"] = "reference"
+    full = dict(w=w, h=h, fx=cfg["fx"], fy=cfg["fy"], cx=cfg["cx"], cy=cfg["cy"], n_levels=cfg["n_levels"], n_pyr=cfg["n_pyr"])
+    sc = ms.build_map_scene(oracle, cfg=full, seed=5, n_kf=1, cell=40, tex_size=1024, n_candidates=0, with_edgelets=False, bad_frac=0.0)
+    cam = Cam.make(w, h, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
+    rm.config(cfg["n_pyr"], 30, 120)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        r = rm.reproject_map(sc["kf_imgs"], sc["T_kf"], sc["cur_img"], sc["T_cur"], cam, sc["points"], sc["obs"], 0)
+    out["reproject_map_ms_per_frame"] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
+    out["reproject_map_points"] = int(len(sc["points"])); out["reproject_map_note"] = "includes building the Map and three Frame pyramids in the harness"
+    s = ms.pose_opt_scene(cfg=full, seed=3, n=100)
+    img = np.zeros((h, w), np.uint8)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        rm.pose_optimize(cam, img, s["px"], s["level"], s["pos"], s["T_init"])
+    out["pose_optimize_ms_per_frame"] = round((time.perf_counter() - t0) / 20 * 1e3, 3)
+    pts = ms.point_opt_scene(cfg=full, n_points=50, max_obs=3)
+    t0 = time.perf_counter()
+    for p in pts:
+        rm.point_optimize(cam, img, p["T"], p["f"], p["pos0"])
+    out["points_optimize_us_per_point"] = round((time.perf_counter() - t0) / len(pts) * 1e6, 1)
+    out["points_optimize_note"] = "harness builds one Frame (pyramid) per observation: upper bound on the reference's cost"
+    t0 = time.perf_counter()
+    for _ in range(3):
+        rm.initialize_seeds(cam, sc["kf_imgs"][0], cfg["n_pyr"], 20, 10.0, sc["obs"]["ftr"]["px_ref"], DEPTH_MEAN, DEPTH_MIN)
+    out["seeds_initialize_ms_per_frame"] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
+    return out
 
 
 LATENCY_DESC = {"C2": "C2: one 640x480 sequence, 4-level pyramid, 120 features, 768 seeds",
@@ -551,6 +743,13 @@ def main():
     out, ctx, wl = run_b200(args, rank, world, local_rank)
     if rank == 0:
         from android_svo_b200 import capi
+        if world == 1 and not args.no_widen:
+            try:
+                out["next_rows"] = widen_rows(ctx, capi, wl, cfg, out["roofline"]["peak"])
+                if not args.no_cpu_baseline:
+                    out["next_rows"]["cpu"] = widen_cpu(cfg)
+            except Exception as e:   # pragma: no cover
+                out["next_rows"] = {"error": repr(e)}
         if not args.no_latency:
             wl.close()
             out["latency"] = {}

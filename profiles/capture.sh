@@ -7,7 +7,7 @@
 set -e
 TAG=${1:-r1}
 SEQS=${2:-4096}
-CMD="python bench.py --seqs $SEQS --steps 2 --warmup 1 --no-latency --no-cpu-baseline"
+CMD="python bench.py --seqs $SEQS --steps 2 --warmup 1 --no-latency --no-cpu-baseline --no-e2e --no-widen"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
