@@ -5,9 +5,10 @@
 // OpenCV 4.5.4 features2d (fast.cpp / fast_score.cpp — third party, restated from the published
 // algorithm and pinned against python cv2 in tests/golden); vk::shiTomasiScore vision.cpp:113-154.
 //
-// B200 design: one pass over each detected level.  A CTA stages a (64+10)x(16+10) pixel tile in
-// shared memory, computes FAST scores for the tile plus a 1-px ring, suppresses non-maxima, and
-// for each surviving keypoint evaluates the 8x8 Shi-Tomasi window straight from the staged tile.
+// B200 design: one pass over each detected level.  A CTA stages an 80x26 pixel tile in shared memory with aligned
+// 8-byte loads, runs the 4-point quick rejection for every pixel of the tile plus a 1-px ring, compacts the survivors
+// into a dense list (warp ballots), computes the 16-pixel ring test and the corner score for those only, suppresses
+// non-maxima, and for each surviving keypoint evaluates the 8x8 Shi-Tomasi window straight from the staged tile.
 // The reference's sequential "first strictly-greater wins" rule over (level, y, x) order becomes
 // a single 64-bit atomicMax per keypoint on key = (ordered(score) << 32) | ~(level,y,x), which is
 // order-independent and therefore bit-identical to the sequential loop.
@@ -17,12 +18,13 @@
 namespace {
 
 constexpr int TW = 64, TH = 16, HALO = 5;
-constexpr int PW = TW + 2 * HALO, PH = TH + 2 * HALO;   // 74 x 26 pixel tile
-constexpr int PP = 80;                                   // padded smem row
+constexpr int XOFF = 8;                                  // the staged tile starts 8 columns left of the output tile: rows are 8-byte aligned
+constexpr int PH = TH + 2 * HALO;                        // 26 staged rows
+constexpr int PP = TW + 2 * XOFF;                        // 80 staged columns (needs TW + 2 * HALO = 74 of them)
 constexpr int SW = TW + 2, SH = TH + 2;                  // score tile with 1-px ring
 
-__constant__ int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__constant__ int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+__device__ constexpr int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__device__ constexpr int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 
 __device__ __forceinline__ uint32_t ordered_bits(float f)
 {
@@ -117,10 +119,26 @@ struct FastArgs {
   uint8_t* raw_scores; int raw_image, raw_level, raw_threshold, raw_nonmax;
 };
 
+// Necessary condition for a FAST-9 corner: an arc of 9 contiguous ring pixels contains two ADJACENT compass points
+// (ring positions 0, 4, 8, 12), so both must be darker, or both brighter, than the centre by more than the threshold.
+// Four loads and eight compares reject most pixels; only the survivors pay for the 16-pixel ring and the score.
+__device__ __forceinline__ bool fast_quick_pass(const uint8_t* p, int threshold)
+{
+  const int v = p[0];
+  const int r0 = p[3 * PP], r4 = p[3], r8 = p[-3 * PP], r12 = p[-3];
+  const int lo = v - threshold, hi = v + threshold;
+  const uint32_t d = (r0 < lo ? 1u : 0u) | (r4 < lo ? 2u : 0u) | (r8 < lo ? 4u : 0u) | (r12 < lo ? 8u : 0u);
+  const uint32_t b = (r0 > hi ? 1u : 0u) | (r4 > hi ? 2u : 0u) | (r8 > hi ? 4u : 0u) | (r12 > hi ? 8u : 0u);
+  const uint32_t dr = ((d << 1) | (d >> 3)) & 15u, br = ((b << 1) | (b >> 3)) & 15u;
+  return ((d & dr) | (b & br)) != 0;
+}
+
 __global__ void __launch_bounds__(256) fast_kernel(FastArgs A)
 {
-  __shared__ uint8_t s_px[PH * PP];
+  __shared__ __align__(16) uint8_t s_px[PH * PP];
   __shared__ uint8_t s_sc[SH * SW];
+  __shared__ unsigned short s_list[SH * SW];
+  __shared__ int s_n;
   const bool raw = A.raw_scores != nullptr;
   const int level = raw ? A.raw_level : (int)(blockIdx.y % A.n_levels);
   const int b = raw ? A.raw_image : (int)(blockIdx.y / A.n_levels);
@@ -132,43 +150,87 @@ __global__ void __launch_bounds__(256) fast_kernel(FastArgs A)
   const uint8_t* img = A.f.lvl[level] + (size_t)b * A.f.img_stride[level];
   const int threshold = raw ? A.raw_threshold : 10;
 
-  for (int i = threadIdx.x; i < PH * PP; i += 256) {
-    const int r = i / PP, c = i - r * PP;
-    const int gx = ox - HALO + c, gy = oy - HALO + r;
-    uint8_t v = 0;
-    if (c < PW && gx >= 0 && gy >= 0 && gx < w && gy < h) v = img[(size_t)gy * pitch + gx];
-    s_px[i] = v;
+  // stage the tile: 8-byte chunks (ox is a multiple of 64, the pitch a multiple of 16 => chunks are aligned); a chunk that
+  // starts left of the image, or a row outside it, is zero.  Bytes at gx >= w come from the row padding / the next row:
+  // no corner, score or Shi-Tomasi window that is evaluated ever reads them (gx + 5 < w for every evaluated pixel).
+  if (threadIdx.x == 0) s_n = 0;
+  for (int i = threadIdx.x; i < PH * (PP / 8); i += 256) {
+    const int r = i / (PP / 8), c8 = i - r * (PP / 8);
+    const int gx = ox - XOFF + 8 * c8, gy = oy - HALO + r;
+    uint2 v = make_uint2(0u, 0u);
+    if (gx >= 0 && gy >= 0 && gx < pitch && gy < h) v = __ldg(reinterpret_cast<const uint2*>(img + (size_t)gy * pitch + gx));
+    *reinterpret_cast<uint2*>(&s_px[r * PP + 8 * c8]) = v;
   }
+  for (int i = threadIdx.x; i < SH * SW; i += 256) s_sc[i] = 0;
   __syncthreads();
 
-  for (int i = threadIdx.x; i < SH * SW; i += 256) {
+  // pass 1: the quick test for every pixel of the score tile; survivors go to a dense list
+  for (int i0 = 0; i0 < SH * SW; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    bool pass = false;
+    if (i < SH * SW) {
+      const int r = i / SW, c = i - r * SW;
+      const int gx = ox - 1 + c, gy = oy - 1 + r;
+      if (gx >= 3 && gy >= 3 && gx < w - 3 && gy < h - 3)
+        pass = fast_quick_pass(&s_px[(r + HALO - 1) * PP + (c + XOFF - 1)], threshold);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  // pass 2: full ring + cornerScore for the survivors only
+  for (int j = threadIdx.x; j < s_n; j += 256) {
+    const int i = s_list[j];
     const int r = i / SW, c = i - r * SW;
-    const int gx = ox - 1 + c, gy = oy - 1 + r;
-    int sc = 0;
-    if (gx >= 3 && gy >= 3 && gx < w - 3 && gy < h - 3)
-      sc = fast_score_at(&s_px[(r + HALO - 1) * PP + (c + HALO - 1)], threshold);
-    s_sc[i] = (uint8_t)sc;
+    s_sc[i] = (uint8_t)fast_score_at(&s_px[(r + HALO - 1) * PP + (c + XOFF - 1)], threshold);
   }
   __syncthreads();
 
-  for (int i = threadIdx.x; i < TH * TW; i += 256) {
+  // pass 3: 3x3 non-max suppression; the keypoints that survive go to a dense list (the Shi-Tomasi window is ~1,000
+  // instructions per keypoint: evaluated in place it would run with one or two live lanes per warp)
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < TH * TW; i0 += 256) {
+    const int i = i0 + threadIdx.x;
     const int r = i / TW, c = i - r * TW;
     const int gx = ox + c, gy = oy + r;
-    if (gx >= w || gy >= h) continue;
-    const uint8_t* q = &s_sc[(r + 1) * SW + (c + 1)];
-    const int s = q[0];
-    bool keep = s > 0;
-    if (keep && (!raw || A.raw_nonmax))
-      keep = s > q[-1] && s > q[1] && s > q[-SW - 1] && s > q[-SW] && s > q[-SW + 1] && s > q[SW - 1] && s > q[SW] && s > q[SW + 1];
-    if (raw) { A.raw_scores[(size_t)gy * w + gx] = keep ? (uint8_t)s : 0; continue; }
-    if (!keep) continue;
+    bool keep = false;
+    if (gx < w && gy < h) {
+      const uint8_t* q = &s_sc[(r + 1) * SW + (c + 1)];
+      const int sc = q[0];
+      keep = sc > 0;
+      if (keep && (!raw || A.raw_nonmax))
+        keep = sc > q[-1] && sc > q[1] && sc > q[-SW - 1] && sc > q[-SW] && sc > q[-SW + 1] && sc > q[SW - 1] && sc > q[SW] && sc > q[SW + 1];
+      if (raw) { A.raw_scores[(size_t)gy * w + gx] = keep ? (uint8_t)sc : 0; keep = false; }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  // pass 4: grid cell, occupancy, Shi-Tomasi score and the cell's 64-bit atomicMax, one thread per keypoint
+  for (int j = threadIdx.x; j < s_n; j += 256) {
+    const int i = s_list[j];
+    const int r = i / TW, c = i - r * TW;
+    const int gx = ox + c, gy = oy + r;
     // cell index: xy is a cv::Point2f, scale an int, cell_size_ an int (feature_detection.cpp:99-100)
     const float scale = (float)(1 << level);
     const int k = (int)(((float)gy * scale) / (float)A.cell) * A.grid_cols + (int)(((float)gx * scale) / (float)A.cell);
     if (A.occupancy && A.occupancy[(size_t)b * A.n_cells + k]) continue;
     float score = 0.0f;
     if (!(gx - 4 < 1 || gx + 4 >= w - 1 || gy - 4 < 1 || gy + 4 >= h - 1))
-      score = shi_tomasi_smem(&s_px[(r + HALO) * PP + (c + HALO)]);
+      score = shi_tomasi_smem(&s_px[(r + HALO) * PP + (c + XOFF)]);
     const uint32_t order = ((uint32_t)level << 28) | ((uint32_t)gy << 14) | (uint32_t)gx;
     const unsigned long long key = ((unsigned long long)ordered_bits(score) << 32) | (unsigned long long)(~order);
     atomicMax(&A.keys[(size_t)b * A.n_cells + k], key);

@@ -599,6 +599,17 @@ def widen_rows(ctx, capi, wl, cfg, peak, steps=5, warm=2):
         out["points_optimize"] = {"ms": round(ms, 4), "points_per_s": round(B * N / ms * 1e3, 1), "obs_per_point": 3,
                                   "median_error_m": float(np.median(np.linalg.norm(got - pw.reshape(-1, 3), axis=1))),
                                   "note": "includes the 11.8 MB start-position re-upload per run"}
+        # ---- FAST + Shi-Tomasi + grid (keyframes only, so it is reported here and not in the step)
+        fcell, fthr = frontend.DETECT[CFG_NAME][0], frontend.DETECT[CFG_NAME][1]
+        fnc = -(-w // fcell) * -(-h // fcell)
+        d_fc, d_fn = ctx.dev_alloc(B * fnc * 16), ctx.dev_alloc(B * 4)
+        frees += [d_fc, d_fn]
+        ms = timed(lambda: ctx._ck(L.svob200_fast_detect(ctx.h, 901, cfg["n_pyr"], fcell, fthr, None, V(d_fc), V(d_fn), capi.MEM_DEVICE)))
+        alg = B * (408000.0 + fnc * 20)
+        out["fast_detect"] = {"ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1), "Mpx_per_s": round(B * 408000 / ms / 1e3, 1),
+                              "algorithmic_bytes": int(alg), "alg_GBps": round(alg / ms / 1e6, 1), "hbm_frac": round(alg / ms / 1e6 / peak, 4),
+                              "bound": "integer issue (ncu: 75% issue-slot utilisation, 6.6 M warp instructions per VGA frame on this texture, "
+                                       "where more than half of the pixels pass the 4-point quick test)"}
         # ---- seed initialisation on the keyframe batch
         d_eoff, d_epx = dev(np.arange(B + 1, dtype=np.int32) * N), dev(wl.kf["kf_px"].reshape(-1, 2))
         d_dm, d_dn = dev(np.full(B, DEPTH_MEAN, np.float32)), dev(np.full(B, DEPTH_MIN, np.float32))
