@@ -8,7 +8,9 @@ one frame of every sequence through pyramid -> sparse image alignment -> reproje
 depth-filter seed update (svob200_tracker_step).  `value` times the steps with every input already
 resident in HBM; `e2e` times the same steps through the C ABI with HOST (pinned) buffers, the H2D
 copy of the frames + per-step inputs and the D2H read of the per-sequence results inside the timed
-region.  The single-stream C2 latency (one sequence, p50 per frame) is reported in `latency`.
+region.  The single-stream latency (one sequence, p50 / p95 per frame, C2 / C3 / C4 shapes) is reported in `latency`;
+`next_rows` times the callers either side of the path (YUV input stage, FAST, reprojector, pose and structure
+optimisers, seed initialisation) on the device next to the reference's code on one host core.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--seqs TOTAL]
 """
@@ -771,9 +773,9 @@ def main():
                     out["latency"][name] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_seqs or max(8, 4 * threads)
-            r = cpu_arm(cfg, n, 3, 1, threads)
+            r = cpu_arm(cfg, n, 10, 1, threads)
             out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
-                                   "sample": "%d sequences x 3 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
+                                   "sample": "%d sequences x 10 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
                                              % (n, r["inner"], threads, r["seconds"])}
         print(json.dumps(out))
     if world > 1:

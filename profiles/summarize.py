@@ -49,7 +49,7 @@ mean = {k: (sum(v[1:]) / len(v[1:]) if len(v) > 2 else sum(v) / len(v)) for k, v
 step_total = sum(mean[k] for k in STEP_KERNELS if k in mean)
 with open(os.path.join(HERE, tag + "_launches_summary.txt"), "w") as f:
     f.write("# %s ncu launch list (gpu__time_duration.sum, --clock-control none), command:\n" % tag)
-    f.write("#   python bench.py --seqs %d --steps 2 --warmup 1 --no-latency --no-cpu-baseline\n" % seqs)
+    f.write("#   python bench.py --seqs %d --steps 2 --warmup 1 --no-latency --no-cpu-baseline --no-e2e --no-widen\n" % seqs)
     f.write("# cold-cache, serialised launches: compare SHARES, not absolutes.  One tracker step = one launch of each kernel below.\n")
     f.write("%-30s %6s %12s %s\n" % ("kernel", "n", "mean_us", "share_of_step"))
     for k in STEP_KERNELS:
