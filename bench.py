@@ -724,8 +724,26 @@ def latency_single(ctx, capi, name, n_frames=60):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1: park the real stdout, point fd 1 at stderr, and emit the one
+    JSON line through the parked descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -750,7 +768,7 @@ def main():
                                            % (n, args.steps, r["inner"], args.warmup, threads, r["seconds"])},
                 "e2e": {"value": round(r["fps"], 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "tracked_mean": r["tracked"]}
-        print(json.dumps(line))
+        emit(json.dumps(line))
         return
 
     out, ctx, wl = run_b200(args, rank, world, local_rank)
@@ -777,7 +795,7 @@ def main():
             out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                    "sample": "%d sequences x 10 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
                                              % (n, r["inner"], threads, r["seconds"])}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
