@@ -128,6 +128,7 @@ def load_library():
     L.svob200_tracker_stage_name.restype = C.c_char_p
     L.svob200_tracker_stage_name.argtypes = [C.c_int]
     L.svob200_tracker_get_seed_obs.argtypes = [V, V]
+    L.svob200_tracker_debug_align.argtypes = [V, V]
     L.svob200_dev_alloc.argtypes = [V, C.c_size_t, C.POINTER(V)]
     L.svob200_dev_free.argtypes = [V, V]
     L.svob200_dev_upload.argtypes = [V, V, V, C.c_size_t]
@@ -167,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "svob200_frame_upload_level", "svob200_shi_tomasi", "svob200_warp_matrix_affine", "svob200_warp_affine",
     "svob200_depth_from_triangulation",
     "svob200_frame_upload_yuv420", "svob200_reproject_map", "svob200_pose_opt_opts_default", "svob200_pose_optimize",
-    "svob200_points_optimize", "svob200_seeds_initialize",
+    "svob200_points_optimize", "svob200_seeds_initialize", "svob200_tracker_debug_align",
 ]
 
 

@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   __shared__ double s_tot[NACC];
   __shared__ double s_clu[CLUSTER > 1 ? CLUSTER : 1][NACC];   // rank 0 only: the partial sums of every CTA of the cluster
   __shared__ int s_ctrl;          // 0 continue iterating, 1 leave this level
+  __shared__ double s_H[36], s_Jx[12];   // H_, Jres_, x_ of the last linearisation (copied to the result record once, at the end)
+  __shared__ int s_iters[SVOB200_MAX_LEVELS], s_nmeas;
   __shared__ int s_need;          // exact chi2 replay wanted: bit 0 this evaluation, bit 1 the previous one as well
   __shared__ float s_chain[2];
   __shared__ int s_chain_n[2];
@@ -228,10 +230,10 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   if (tid < 7) s_model[tid] = A.T_init[7 * b + tid];
   if (lead) {
     for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = A.T_init[7 * b + k];
-    for (int k = 0; k < 36; ++k) R->H[k] = 0;
-    for (int k = 0; k < 6; ++k) { R->Jres[k] = 0; R->x[k] = 0; }
-    R->chi2 = 1e10; R->n_meas = 0; R->stop = 0; R->n_exact_chi2 = 0;
-    for (int k = 0; k < SVOB200_MAX_LEVELS; ++k) R->iters[k] = 0;
+    for (int k = 0; k < 36; ++k) { R->H[k] = 0; s_H[k] = 0; }
+    for (int k = 0; k < 6; ++k) { R->Jres[k] = 0; R->x[k] = 0; s_Jx[k] = 0; s_Jx[6 + k] = 0; }
+    R->chi2 = 1e10; R->n_meas = 0; R->stop = 0; R->n_exact_chi2 = 0; s_nmeas = 0;
+    for (int k = 0; k < SVOB200_MAX_LEVELS; ++k) { R->iters[k] = 0; s_iters[k] = 0; }
   }
   if (N <= 0) return;                                   // sparse_img_align.cpp:55-59 (uniform over the cluster)
   for (int i = lo + tid; i < hi; i += BLOCK) { A.visible[f0 + i] = 0; A.contrib[0][f0 + i] = 0; A.contrib[1][f0 + i] = 0; }
@@ -254,6 +256,12 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   bool stop_ = false;
   int n_exact = 0;
   int pp = 0;                                          // ping-pong index of the *current* evaluation
+#ifdef ALIGN_TIMING
+  long long tA = 0, tB = 0, tC = 0, tD = 0, tP = 0, c0 = clock64(), cstart = c0;
+#define TICK(acc) do { const long long c1_ = clock64(); acc += c1_ - c0; c0 = c1_; } while (0)
+#else
+#define TICK(acc) do { } while (0)
+#endif
 
   for (int level = A.opts.max_level; level >= A.opts.min_level; --level) {
     const float scale = 1.0f / (1 << level);
@@ -262,15 +270,22 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       const uint8_t* img = A.ref.lvl[level] + (size_t)b * A.ref.img_stride[level];
       const int cols = A.ref.w[level], rows = A.ref.h[level], stride = A.ref.pitch[level];
       const double fl = focal_length / (1 << level);
-      for (int idx = lo * 16 + tid; idx < hi * 16; idx += BLOCK) {
-        const int i = idx >> 4, p = idx & 15;
+      // thread per feature: the 7x7 window under the 4x4 patch and its central-difference gradients is fetched once
+      // (three aligned words per row, all 21 loads in flight together) and every tap reads it from registers
+      for (int i = lo + tid; i < hi; i += BLOCK) {
         const float u_ref = (float)(px[2 * i] * (double)scale);
         const float v_ref = (float)(px[2 * i + 1] * (double)scale);
         const int u_i = (int)floorf(u_ref), v_i = (int)floorf(v_ref);
         const bool ok = has_point[i] && !(u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= cols || v_i + 3 >= rows);
-        if (!ok) { gdx[idx] = 0.f; gdy[idx] = 0.f; continue; }   // jacobian_cache_.setZero() (:76)
-        if (p == 0) {
-          visible[i] = 1;
+        float4* gx4 = reinterpret_cast<float4*>(gdx + 16 * (size_t)i);
+        float4* gy4 = reinterpret_cast<float4*>(gdy + 16 * (size_t)i);
+        if (!ok) {                                                    // jacobian_cache_.setZero() (:76)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { gx4[q] = make_float4(0.f, 0.f, 0.f, 0.f); gy4[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          continue;
+        }
+        visible[i] = 1;
+        {
           // Frame::jacobian_xyz2uv (frame.h:110-132), scaled by focal_length / 2^level
           const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
           const double z_inv = 1. / z, z_inv_2 = z_inv * z_inv;
@@ -284,17 +299,46 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         const float w_tr = (float)(su * (1.0 - sv));
         const float w_bl = (float)((1.0 - su) * sv);
         const float w_br = su * sv;
-        const int yy = p >> 2, xx = p & 3;
-        const uint8_t* q = img + (size_t)(v_i + yy - 2) * stride + (u_i + xx - 2);
-        ref_patch[idx] = w_tl * q[0] + w_tr * q[1] + w_bl * q[stride] + w_br * q[stride + 1];
-        gdx[idx] = 0.5f * ((w_tl * q[1] + w_tr * q[2] + w_bl * q[stride + 1] + w_br * q[stride + 2])
-                           - (w_tl * q[-1] + w_tr * q[0] + w_bl * q[stride - 1] + w_br * q[stride]));
-        gdy[idx] = 0.5f * ((w_tl * q[stride] + w_tr * q[1 + stride] + w_bl * q[stride * 2] + w_br * q[stride * 2 + 1])
-                           - (w_tl * q[-stride] + w_tr * q[1 - stride] + w_bl * q[0] + w_br * q[1]));
+        // window rows v_i-3 .. v_i+3, columns u_i-3 .. u_i+3 (7 bytes = at most three aligned words per row)
+        uint32_t wlo[7], whi[7];
+        {
+          const uintptr_t a0 = reinterpret_cast<uintptr_t>(img + (size_t)(v_i - 3) * stride + (u_i - 3));
+          const unsigned sh = (unsigned)(a0 & 3) * 8;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(a0 & ~(uintptr_t)3);
+#pragma unroll
+          for (int r = 0; r < 7; ++r) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (size_t)r * stride);          // stride % 4 == 0
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+            const uint32_t w2 = sh >= 16 ? __ldg(q + 2) : 0u;        // the third word holds a needed byte only then (never crosses the pitch)
+            wlo[r] = __funnelshift_r(w0, w1, sh); whi[r] = __funnelshift_r(w1, w2, sh);
+          }
+        }
+        // pixel (row r, column c) of the window, r and c compile-time after unrolling; window (3,3) is (v_i, u_i)
+#define WPX(r, c) ((float)((((c) < 4 ? wlo[r] : whi[r]) >> (8 * ((c) & 3))) & 0xffu))
+        float4* rp4 = reinterpret_cast<float4*>(ref_patch + 16 * (size_t)i);
+#pragma unroll
+        for (int yy = 0; yy < 4; ++yy) {
+          float pv[4], xv[4], yv[4];
+#pragma unroll
+          for (int xx = 0; xx < 4; ++xx) {
+            // q = window(yy + 1, xx + 1): q[a + b*stride] = WPX(yy + 1 + b, xx + 1 + a)
+            const int r = yy + 1, c = xx + 1;
+            pv[xx] = w_tl * WPX(r, c) + w_tr * WPX(r, c + 1) + w_bl * WPX(r + 1, c) + w_br * WPX(r + 1, c + 1);
+            xv[xx] = 0.5f * ((w_tl * WPX(r, c + 1) + w_tr * WPX(r, c + 2) + w_bl * WPX(r + 1, c + 1) + w_br * WPX(r + 1, c + 2))
+                             - (w_tl * WPX(r, c - 1) + w_tr * WPX(r, c) + w_bl * WPX(r + 1, c - 1) + w_br * WPX(r + 1, c)));
+            yv[xx] = 0.5f * ((w_tl * WPX(r + 1, c) + w_tr * WPX(r + 1, c + 1) + w_bl * WPX(r + 2, c) + w_br * WPX(r + 2, c + 1))
+                             - (w_tl * WPX(r - 1, c) + w_tr * WPX(r - 1, c + 1) + w_bl * WPX(r, c) + w_br * WPX(r, c + 1)));
+          }
+          rp4[yy] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+          gx4[yy] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+          gy4[yy] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        }
+#undef WPX
       }
     }
     if (tid < 7) s_old[tid] = s_model[tid];
     __syncthreads();
+    TICK(tP);
 
     const uint8_t* cimg = A.cur.lvl[level] + (size_t)b * A.cur.img_stride[level];
     const int ccols = A.cur.w[level], crows = A.cur.h[level], cstride = A.cur.pitch[level];
@@ -402,6 +446,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       }
       __syncthreads();
 
+      TICK(tA);
       // ---------------- solve (thread 0 of rank 0), nlls_solver_impl.hpp:36-99
       double xs[6];
       int n_meas = 0;
@@ -421,11 +466,11 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         ldlt6_solve(H, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
 #pragma unroll
-        for (int k = 0; k < 36; ++k) R->H[k] = H[k];
+        for (int k = 0; k < 36; ++k) s_H[k] = H[k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { R->Jres[k] = Jres[k]; R->x[k] = xs[k]; }
-        R->n_meas = n_meas;
-        R->iters[level] += 1;
+        for (int k = 0; k < 6; ++k) { s_Jx[k] = Jres[k]; s_Jx[6 + k] = xs[k]; }
+        s_nmeas = n_meas;
+        s_iters[level] += 1;
         int need = 0;
         if (iter > 0 && !stop_) {
           // worst-case first-order rounding error of two sequential float sums of n_meas terms
@@ -435,6 +480,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         }
         s_need = need;
       }
+      TICK(tB);
       // ---------------- exact replay of the reference's float chi2 chain(s), when the decision hangs on it (rank 0's CTA)
       if (rank == 0) {
         __syncthreads();
@@ -444,6 +490,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         if (need & 2) exact_chi2_chain_block(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_sq, s_fl, &s_chain[1], &s_chain_n[1], tid, BLOCK);
         if (need) __syncthreads();
       }
+      TICK(tC);
       // ---------------- decide / update (thread 0 of rank 0)
       if (lead) {
         int ctrl = 0;
@@ -490,15 +537,23 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       }
       pp ^= 1;
       if (CLUSTER > 1) cg::this_cluster().sync(); else __syncthreads();
+      TICK(tD);
       if (s_ctrl) break;
     }
     if (CLUSTER > 1) cg::this_cluster().sync(); else __syncthreads();
   }
   if (lead) {
+    for (int k = 0; k < 36; ++k) R->H[k] = s_H[k];
+    for (int k = 0; k < 6; ++k) { R->Jres[k] = s_Jx[k]; R->x[k] = s_Jx[6 + k]; }
+    R->n_meas = s_nmeas;
+    for (int k = 0; k < SVOB200_MAX_LEVELS; ++k) R->iters[k] = s_iters[k];
     for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = s_model[k];
     R->chi2 = chi2_;
     R->stop = stop_ ? 1 : 0;
     R->n_exact_chi2 = n_exact;
+#ifdef ALIGN_TIMING
+    R->H[0] = (double)tP; R->H[1] = (double)tA; R->H[2] = (double)tB; R->H[3] = (double)tC; R->H[4] = (double)tD; R->H[5] = (double)(clock64() - cstart);
+#endif
   }
 }
 

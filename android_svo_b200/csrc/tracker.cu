@@ -432,6 +432,16 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
 
 int svob200_tracker_launches_per_step(void) { return 14; }
 
+// raw svob200_align_result records of the most recent step (diagnostics: tools/align_timing.py)
+int svob200_tracker_debug_align(svob200_tracker* t, svob200_align_result* out)
+{
+  if (!t || !out || !t->d_align) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  CU(cudaMemcpyAsync(out, t->d_align, sizeof(svob200_align_result) * (size_t)t->batch, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SVOB200_OK;
+}
+
 // stage timing: CUDA events recorded on the launching stream between the kernels of a step
 int svob200_tracker_enable_profiling(svob200_tracker* t, int on)
 {

@@ -274,6 +274,8 @@ int  svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int strid
                           const double* last_px, svob200_step_stats* stats, double* px_refined, int* match_ok, int mem);
 int  svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out /*host*/);
 int  svob200_tracker_launches_per_step(void);
+/* diagnostics: the raw svob200_align_result records (one per sequence) of the most recent step, to host memory */
+int  svob200_tracker_debug_align(svob200_tracker* t, svob200_align_result* out);
 /* optional CUDA-event timing of the most recent step, one duration per stage (events recorded on the
  * launching stream between the kernels): stage names from svob200_tracker_stage_name(i), i < num_stages */
 int  svob200_tracker_enable_profiling(svob200_tracker* t, int on);
