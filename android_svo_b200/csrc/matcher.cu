@@ -66,30 +66,6 @@ __device__ __forceinline__ float interpolate_8u(const uint8_t* img, int stride, 
   return w00 * p[0] + w01 * p[stride] + w10 * p[1] + w11 * p[stride + 1];
 }
 
-// warpAffine with halfpatch 5 -> 10x10 patch; threads [t0, t0+nthreads) of the caller cooperate.
-// Returns false (patch untouched) when the warp is NaN (matcher.cpp:94-98).
-__device__ inline bool warp_affine_10x10(const double* A, const uint8_t* img, int pitch, int cols, int rows,
-                                         const double* px_ref, int level_ref, int search_level,
-                                         uint8_t* patch, int t, int nthreads)
-{
-  const double det = A[0] * A[3] - A[2] * A[1];
-  const double invdet = 1.0 / det;
-  const float a00 = (float)(A[3] * invdet), a01 = (float)(-A[1] * invdet);
-  const float a10 = (float)(-A[2] * invdet), a11 = (float)(A[0] * invdet);
-  if (isnan(a00)) return false;
-  const float pr0 = (float)px_ref[0] / (float)(1 << level_ref), pr1 = (float)px_ref[1] / (float)(1 << level_ref);
-  for (int i = t; i < 100; i += nthreads) {
-    const int y = i / 10, x = i - y * 10;
-    float p0 = (float)(x - 5), p1 = (float)(y - 5);
-    p0 *= (float)(1 << search_level); p1 *= (float)(1 << search_level);
-    const float qx = (a00 * p0 + a01 * p1) + pr0;
-    const float qy = (a10 * p0 + a11 * p1) + pr1;
-    uint8_t v = 0;
-    if (!(qx < 0 || qy < 0 || qx >= cols - 1 || qy >= rows - 1)) v = (uint8_t)interpolate_8u(img, pitch, qx, qy);
-    patch[i] = v;
-  }
-  return true;
-}
 
 // ---------------------------------------------------------------- feature alignment: one THREAD per problem
 // feature_alignment::align2D / align1D float paths (feature_alignment.cpp:35-282).
@@ -462,7 +438,10 @@ __device__ __forceinline__ EpiSearch epi_search_none()
 constexpr int GL = 8;                    // lanes per group
 constexpr int GPW = 32 / GL;             // groups (items) per warp
 constexpr int EPI_GCHUNK = 32;           // epipolar samples a group stages per round (steady-state walks are <= 47 steps)
-constexpr int SEARCH_CTAS = 6;           // resident CTAs per SM of the persistent search kernel (85 registers per thread: no spills)
+#ifndef SEARCH_CTAS_PER_SM
+#define SEARCH_CTAS_PER_SM 6
+#endif
+constexpr int SEARCH_CTAS = SEARCH_CTAS_PER_SM;   // resident CTAs per SM of the persistent search kernel (6: 85 registers per thread, no spills)
 
 struct EpiGroupSmem {
   __align__(16) uint8_t pwb[112];       // 100 used
@@ -566,6 +545,8 @@ __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, in
   // lane handles taps sub, sub+8, ... (< 100), four at a time so that the 16 pixel loads of a lane are in flight together
   const float sc = (float)(1 << L);
   const float xmax = (float)(rc - 1), ymax = (float)(rr - 1);
+  // tap i = sub + 8 r walks the 10x10 patch row-major: (x, y) advance by 8 columns per round with a carry into the row
+  int x = sub, y = 0;
 #pragma unroll 1
   for (int r0 = 0; r0 < 13; r0 += 4) {
     bool inb[4];
@@ -574,14 +555,15 @@ __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, in
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = sub + GL * (r0 + r);
-      const int y = i / 10, x = i - y * 10;
       float p0 = (float)(x - 5), p1 = (float)(y - 5);
+      x += GL; if (x >= 10) { x -= 10; ++y; }
       p0 *= sc; p1 *= sc;
       const float qx = (a00 * p0 + a01 * p1) + pr0;
       const float qy = (a10 * p0 + a11 * p1) + pr1;
       inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
-      // vk::interpolateMat_8u (vision.h:19-36)
-      const int ix = (int)floorf(qx), iy = (int)floorf(qy);
+      // vk::interpolateMat_8u (vision.h:19-36); floorf == truncation for the non-negative coordinates of an in-bounds tap
+      // (out-of-bounds taps produce 0 whatever ix, iy are)
+      const int ix = (int)qx, iy = (int)qy;
       const float sx = qx - ix, sy = qy - iy;
       w00[r] = (1.0f - sx) * (1.0f - sy);
       w01[r] = (1.0f - sx) * sy;
@@ -896,6 +878,8 @@ __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevF
   const int stride = gridDim.x * 4 * GPW;              // items per sweep of the persistent grid
   int slot_base = 0, slots_left = 0;
   int i = (blockIdx.x * 4 + warp) * GPW + grp;
+  // (an L2 prefetch of the NEXT item's reference window, issued one item ahead, was measured: 2.19 -> 2.41 ms; the kernel is
+  //  bound by issue slots and dependent arithmetic at 6 resident CTAs per SM, not by the DRAM latency of the taps)
   uint4 next = (i < n) ? __ldg(reinterpret_cast<const uint4*>(&tasks[i]) + sub) : make_uint4(0, 0, 0, 0);
   for (; i < n; i += stride) {
     const uint4 tq = next;
