@@ -78,6 +78,9 @@ __device__ __forceinline__ float interpolate_8u(const uint8_t* img, int stride, 
 // free), the 9x9 search window is streamed row by row with three aligned word loads per row, and every
 // float operation happens in the reference's order.  Results are bit-identical to the CPU code.
 constexpr int LK_T = 128;
+#ifndef LK_CTAS
+#define LK_CTAS 3
+#endif
 
 // One refinement problem, written by the warp-cooperative producers with ONE coalesced 128-byte store.
 struct __align__(16) LkJob {
@@ -726,7 +729,7 @@ struct LkSink {
   const uint8_t* patches;         // LK_SINK_ARRAYS: caller-provided 8x8 reference patches, 64 B per job (else the centre of pwb)
 };
 
-__global__ void __launch_bounds__(LK_T) lk_refine_kernel(const DevFrame* frames, int cur_slot, const LkJob* jobs, const int* job_count,
+__global__ void __launch_bounds__(LK_T, LK_CTAS) lk_refine_kernel(const DevFrame* frames, int cur_slot, const LkJob* jobs, const int* job_count,
                                                          int n_max, int n_iter, LkSink sink)
 {
   __shared__ uint32_t s_d[64 * LK_T];

@@ -45,7 +45,6 @@ struct AlignArgs {
   float* gdy;         //                 outside the level's border => zero Jacobian, :76)
   float* res[2];      // residuals of the last two evaluations (ping-pong), for the exact chi2 chain
   double* jab;        // 12 per feature: a = J0*fl, b = J1*fl  (pixel Jacobian row = dx*a + dy*b)
-  float2* uv;         // projected position of the feature at the current level
   uint8_t* visible;   // sticky across levels (:67)
   uint8_t* contrib[2];
 };
@@ -247,7 +246,6 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   float* gdx = A.gdx + 16 * (size_t)f0;
   float* gdy = A.gdy + 16 * (size_t)f0;
   double* jab = A.jab + 12 * (size_t)f0;
-  float2* uv = A.uv + f0;
   const double focal_length = fabs(A.cam.fx);          // errorMultiplier2()
 
   // thread-0 solver state (NLLSSolver::reset nlls_solver_impl.hpp:299-309)
@@ -567,11 +565,11 @@ static int sparse_align_cluster_override()
   return v;
 }
 
-// per feature: 16 floats x (ref_patch, gdx, gdy, res0, res1) + 12 doubles (a, b) + float2 uv + 3 flag bytes
+// per feature: 16 floats x (ref_patch, gdx, gdy, res0, res1) + 12 doubles (a, b) + 3 flag bytes
 size_t sparse_align_scratch_bytes(int total_features)
 {
   const size_t n = (size_t)(total_features > 0 ? total_features : 1);
-  return n * (16 * sizeof(float) * 5 + 12 * sizeof(double) + sizeof(float2) + 3) + 4096;
+  return n * (16 * sizeof(float) * 5 + 12 * sizeof(double) + 3) + 4096;
 }
 
 int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
@@ -593,7 +591,6 @@ int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& 
   A.gdy = reinterpret_cast<float*>(take(fsz));
   A.res[0] = reinterpret_cast<float*>(take(fsz));
   A.res[1] = reinterpret_cast<float*>(take(fsz));
-  A.uv = reinterpret_cast<float2*>(take(T * sizeof(float2)));
   A.visible = reinterpret_cast<uint8_t*>(take(T));
   A.contrib[0] = reinterpret_cast<uint8_t*>(take(T));
   A.contrib[1] = reinterpret_cast<uint8_t*>(take(T));

@@ -420,9 +420,14 @@ def run_b200(args, rank, world, local_rank):
 
     def roof(name):
         a = alg[name] / (stage_acc[name] * 1e-3) / 1e9
-        return {"kernel": kernel_of[name], "bound": "hbm", "achieved": round(a, 2), "peak": peak, "unit": "GB/s", "frac": round(a / peak, 5),
-                "traffic": traffic_of(name), "algorithmic_bytes": round(alg[name]), "peak_source": peak_src,
-                "ms_per_launch": round(stage_acc[name], 4), "share_of_step": round(stage_acc[name] / max(sum(stage_acc.values()), 1e-9), 3)}
+        r = {"kernel": kernel_of[name], "bound": "hbm", "achieved": round(a, 2), "peak": peak, "unit": "GB/s", "frac": round(a / peak, 5),
+             "traffic": traffic_of(name), "algorithmic_bytes": round(alg[name]), "peak_source": peak_src,
+             "ms_per_launch": round(stage_acc[name], 4), "share_of_step": round(stage_acc[name] / max(sum(stage_acc.values()), 1e-9), 3)}
+        ncu = tj.get(kernel_of[name], {}).get("ncu")
+        if ncu:   # what actually bounds the kernel, from the committed `ncu --set full` capture (profiles/)
+            r["ncu"] = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in ncu.items()}
+            r["ncu"]["source"] = tj[kernel_of[name]].get("source")
+        return r
 
     roofline = roof(dom)
     roofline["note"] = ("dominant kernel of the step; it is integer-issue/L2-bound (ZMSSD dot products and LK on L2-resident windows), "
@@ -789,6 +794,11 @@ def main():
                     out["latency"][name] = latency_single(ctx, capi, name)
                 except Exception as e:   # pragma: no cover
                     out["latency"][name] = {"error": str(e)}
+        if world == 1 and not args.no_cpu_baseline and not args.no_latency:
+            # the reference's per-frame latency on ONE host core, same C2 sequence shape (the reference's native single-stream mode)
+            r1 = cpu_arm(cfg, 1, 3, 1, 1)
+            out["latency"]["C2"]["cpu_reference_1_thread"] = {"p50_ms": round(1e3 / r1["fps"], 4), "kind": r1["kind"],
+                                                              "sample": "1 sequence x 3 steps x %d frames, 1 thread" % r1["inner"]}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_seqs or max(8, 4 * threads)
             r = cpu_arm(cfg, n, 10, 1, threads)

@@ -102,6 +102,14 @@ if os.path.exists(raw):
                 wr = to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
                 traffic[k] = {"dram_bytes_per_launch": rd + wr, "dram_bytes_per_sequence": (rd + wr) / seqs, "sequences_in_capture": seqs,
                               "source": "profiles/%s_full_summary.txt" % tag}
+                def num(name):
+                    return float(r[ix[name]].replace(",", "")) if name in ix else None
+                traffic[k]["ncu"] = {"issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                     "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                                     "warp_instructions_per_sequence": (num("smsp__inst_executed.sum") or 0) / seqs,
+                                     "registers_per_thread": num("launch__registers_per_thread"),
+                                     "stall_long_scoreboard": num("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+                                     "stall_barrier": num("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio")}
                 f.write("  %-82s %.0f byte\n" % ("=> dram read+write per launch", rd + wr))
     json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 print("summaries written for", tag)
