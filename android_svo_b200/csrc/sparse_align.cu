@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
+#include "ldlt.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -49,85 +50,11 @@ struct AlignArgs {
   uint8_t* contrib[2];
 };
 
-// Pivoted LDL^T solve of the 6x6 system, mirroring Eigen::LDLT's algorithm (largest-diagonal
-// symmetric pivoting, tolerance-matched).  Fully unrolled with compile-time indices so the matrix
-// lives in registers: the dynamic pivot is handled by predicated swaps over the candidates.
-__device__ __forceinline__ void swapd(double& a, double& b) { const double t = a; a = b; b = t; }
-
-__device__ void ldlt6_solve(const double* Hin, const double* b, double* x)
-{
-  double A[6][6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) A[i][j] = Hin[i * 6 + j];
-  int perm[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    int piv = k;
-    double big = fabs(A[k][k]);
-#pragma unroll
-    for (int i = k + 1; i < 6; ++i) { const double v = fabs(A[i][i]); if (v > big) { big = v; piv = i; } }
-    perm[k] = piv;
-#pragma unroll
-    for (int p = k + 1; p < 6; ++p) {
-      if (piv == p) {
-#pragma unroll
-        for (int j = 0; j < k; ++j) swapd(A[k][j], A[p][j]);
-#pragma unroll
-        for (int j = p + 1; j < 6; ++j) swapd(A[j][k], A[j][p]);
-        swapd(A[k][k], A[p][p]);
-#pragma unroll
-        for (int i = k + 1; i < p; ++i) swapd(A[i][k], A[p][i]);
-      }
-    }
-    if (k > 0) {
-      double temp[6];
-      double sdiag = 0;
-#pragma unroll
-      for (int j = 0; j < k; ++j) { temp[j] = A[j][j] * A[k][j]; sdiag += A[k][j] * temp[j]; }
-      A[k][k] -= sdiag;
-#pragma unroll
-      for (int i = k + 1; i < 6; ++i) {
-        double t = 0;
-#pragma unroll
-        for (int j = 0; j < k; ++j) t += A[i][j] * temp[j];
-        A[i][k] -= t;
-      }
-    }
-    const double d = A[k][k];
-    if (fabs(d) > 2.2250738585072014e-308) {
-#pragma unroll
-      for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
-    }
-  }
-  double y[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) y[i] = b[i];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-#pragma unroll
-    for (int p = k + 1; p < 6; ++p) if (perm[k] == p) swapd(y[k], y[p]);
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { const double d = A[i][i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
-#pragma unroll
-  for (int i = 5; i >= 0; --i)
-#pragma unroll
-    for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-#pragma unroll
-  for (int k = 5; k >= 0; --k) {
-#pragma unroll
-    for (int p = k + 1; p < 6; ++p) if (perm[k] == p) swapd(y[k], y[p]);
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) x[i] = y[i];
-}
-
+// The 6x6 solve is ldlt_solve_fixed<6> (ldlt.cuh): Eigen's pivoted LDL^T with the exact associations of its fixed-size
+// triangular solves, fully unrolled so the matrix lives in thread 0's registers.  (A warp-cooperative version with the
+// matrix in shared memory — five swap lanes, parallel column updates, the four libm calls of SE3::exp on four lanes — was
+// measured with tools/align_timing.py: 9.3 k cycles per solve against 6.2 k for this one; the shared-memory round trips and
+// warp barriers of a 6x6 problem cost more than the serial FP64 chain they replace.)
 // The reference's `float chi2; chi2 += res*res*weight` in feature-list / row-major pixel order.  The chain of float
 // additions is inherently sequential (4 cycles per FADD); everything around it is not: the whole CTA fetches the
 // residuals of a chunk of features (coalesced, L2: the other CTAs of a cluster wrote some of them), squares them
@@ -461,7 +388,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         }
         n_meas = (int)s_tot[28];
         new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
-        ldlt6_solve(H, Jres, xs);
+        ldlt_solve_fixed<6>(H, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
 #pragma unroll
         for (int k = 0; k < 36; ++k) s_H[k] = H[k];

@@ -371,8 +371,25 @@ static inline int in_frame_level(const svo_cam* cam, int x, int y, int boundary,
 /* a5-a8  sparse image alignment                                       */
 /* ------------------------------------------------------------------ */
 
+static double ldlt_halving_sum(const double* t, int m)
+{
+  if (m == 1) return t[0];
+  const int h = m / 2;
+  return ldlt_halving_sum(t, h) + ldlt_halving_sum(t + h, m - h);
+}
+static double ldlt_packet2_sum(const double* t, int m)
+{
+  const int np = m / 2;
+  if (np == 0) return ldlt_halving_sum(t, m);
+  double p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
+  for (int i = 0; i < np; ++i) { p0[i] = t[2 * i]; p1[i] = t[2 * i + 1]; }
+  double r = ldlt_halving_sum(p0, np) + ldlt_halving_sum(p1, np);
+  if (m & 1) r = r + t[m - 1];
+  return r;
+}
+
 /* Eigen LDLT (pivoted, lower) for a 6x6 SPD-ish matrix + solve; mirrors
- * Eigen/src/Cholesky/LDLT.h unblocked algorithm.  Tolerance-matched only. */
+ * Eigen/src/Cholesky/LDLT.h unblocked algorithm and the fixed-size solve's associations. */
 static void ldlt6_solve(const double Hin[36], const double b[6], double x[6])
 {
   double A[36]; memcpy(A, Hin, sizeof(A));
@@ -409,9 +426,12 @@ static void ldlt6_solve(const double Hin[36], const double b[6], double x[6])
   /* solve: x = P^T L^-T D^-1 L^-1 P b */
   double y[6]; memcpy(y, b, sizeof(y));
   for (int k = 0; k < n; ++k) if (perm[k] != k) { const double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
-  for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
+  /* Eigen's unrolled triangular solves on a fixed-size rhs subtract ONE reduced sum per row: halving association for the
+   * lower solve (strided rows, scalar redux), Packet2d association for the upper solve (rows of the adjoint view are
+   * contiguous).  Bit-identical to A.ldlt().solve(b) of the x86-64 SSE2 build (see svo_oracle_map.c). */
+  for (int i = 1; i < n; ++i) { double t[6]; for (int j = 0; j < i; ++j) t[j] = A[i * 6 + j] * y[j]; y[i] -= ldlt_halving_sum(t, i); }
   for (int i = 0; i < n; ++i) { const double d = A[i * 6 + i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
-  for (int i = n - 1; i >= 0; --i) for (int j = i + 1; j < n; ++j) y[i] -= A[j * 6 + i] * y[j];
+  for (int i = n - 2; i >= 0; --i) { double t[6]; const int m = n - 1 - i; for (int j = 0; j < m; ++j) t[j] = A[(i + 1 + j) * 6 + i] * y[i + 1 + j]; y[i] -= ldlt_packet2_sum(t, m); }
   for (int k = n - 1; k >= 0; --k) if (perm[k] != k) { const double t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
   memcpy(x, y, sizeof(y));
 }
