@@ -89,14 +89,17 @@ __device__ inline void se3_exp(const double* l, double* out)
     imag_factor = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
     real_factor = 1.0 - 0.5 * theta_sq + (1.0 / 384.0) * theta_po4;
   } else {
-    const double s = sin(half_theta);
+    double s, c;
+    sincos(half_theta, &s, &c);                     // one argument reduction for both (same values as sin() and cos())
     imag_factor = s / theta;
-    real_factor = cos(half_theta);
+    real_factor = c;
   }
   const v3d rxp = v3_cross(r, p);
   const v3d rxrxp = v3_cross(r, rxp);
-  const double c1 = (1 - cos(theta)) / theta_sq;
-  const double c2 = (theta - sin(theta)) / (theta_sq * theta);
+  double sin_t, cos_t;
+  sincos(theta, &sin_t, &cos_t);
+  const double c1 = (1 - cos_t) / theta_sq;
+  const double c2 = (theta - sin_t) / (theta_sq * theta);
   const v3d t = v3_add(v3_add(p, v3_scale(c1, rxp)), v3_scale(c2, rxrxp));
   out[0] = t.x; out[1] = t.y; out[2] = t.z;
   out[3] = imag_factor * r.x; out[4] = imag_factor * r.y; out[5] = imag_factor * r.z; out[6] = real_factor;

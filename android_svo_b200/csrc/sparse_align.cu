@@ -448,20 +448,22 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
           if (nmax <= A.opts.eps) ctrl = 1;
         }
         s_ctrl = ctrl;
-        if (CLUSTER > 1) {
-          // push the new model, the rollback model and the control word into every CTA of the cluster
-          cg::cluster_group cl = cg::this_cluster();
-          for (int r = 1; r < CLUSTER; ++r) {
-            double* rm = cl.map_shared_rank(&s_model[0], r);
-            double* ro = cl.map_shared_rank(&s_old[0], r);
-#pragma unroll
-            for (int k = 0; k < 7; ++k) { rm[k] = s_model[k]; ro[k] = s_old[k]; }
-            *cl.map_shared_rank(&s_ctrl, r) = ctrl;
-          }
-        }
       }
       pp ^= 1;
-      if (CLUSTER > 1) cg::this_cluster().sync(); else __syncthreads();
+      if (CLUSTER > 1) {
+        // every other CTA of the cluster PULLS the new model, the rollback model and the control word from rank 0 through
+        // distributed shared memory, 15 threads in parallel (rank 0 next writes them after the next iteration's barrier)
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();
+        if (rank != 0) {
+          if (tid < 7) s_model[tid] = cl.map_shared_rank(&s_model[0], 0)[tid];
+          else if (tid < 14) s_old[tid - 7] = cl.map_shared_rank(&s_old[0], 0)[tid - 7];
+          else if (tid == 14) s_ctrl = *cl.map_shared_rank(&s_ctrl, 0);
+        }
+        __syncthreads();
+      } else {
+        __syncthreads();
+      }
       TICK(tD);
       if (s_ctrl) break;
     }
