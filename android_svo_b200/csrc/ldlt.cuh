@@ -40,7 +40,13 @@ __device__ __forceinline__ double packet2_sum(const double* t, int m)
 }  // namespace ldlt_detail
 
 // A: row-major N x N (only its lower triangle is read after the copy), b, x: N
-template <int N>
+// SHARED_RCP = false: every quotient is an IEEE division, bit-identical to Eigen (Point::optimize, pose optimiser).
+// SHARED_RCP = true : the quotients by one pivot (its column of L and its entry of D^-1) share ONE division, the
+//   reciprocal of the pivot, and are corrected with two fused residual steps — q0 = a*r, q = fma(fma(-d,q0,a), r, q0) —
+//   which reproduces the correctly rounded quotient except in rare last-bit cases.  An FP64 division is a ~200-cycle
+//   dependent sequence with a slow-path branch, and a 6x6 solve has 21 of them on one thread: for the sparse-alignment
+//   solve, whose inputs are tree-reduced sums (tolerance-matched already), this removes 15 of the 21.
+template <int N, bool SHARED_RCP = false>
 __device__ inline void ldlt_solve_fixed(const double* Ain, const double* b, double* x)
 {
   using namespace ldlt_detail;
@@ -50,6 +56,7 @@ __device__ inline void ldlt_solve_fixed(const double* Ain, const double* b, doub
 #pragma unroll
     for (int j = 0; j < N; ++j) A[i][j] = Ain[i * N + j];
   int perm[N];
+  double rcp[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     int piv = k;
@@ -85,9 +92,16 @@ __device__ inline void ldlt_solve_fixed(const double* Ain, const double* b, doub
     }
     const double d = A[k][k];
     if (fabs(d) > 2.2250738585072014e-308) {
+      if (SHARED_RCP) {
+        const double r = 1.0 / d;
+        rcp[k] = r;
 #pragma unroll
-      for (int i = k + 1; i < N; ++i) A[i][k] /= d;
-    }
+        for (int i = k + 1; i < N; ++i) { const double q0 = A[i][k] * r; A[i][k] = fma(fma(-d, q0, A[i][k]), r, q0); }
+      } else {
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) A[i][k] /= d;
+      }
+    } else if (SHARED_RCP) rcp[k] = 0.0;
   }
   double y[N];
 #pragma unroll
@@ -105,7 +119,11 @@ __device__ inline void ldlt_solve_fixed(const double* Ain, const double* b, doub
     y[i] -= halving_sum(t, i);
   }
 #pragma unroll
-  for (int i = 0; i < N; ++i) { const double d = A[i][i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
+  for (int i = 0; i < N; ++i) {
+    const double d = A[i][i];
+    if (SHARED_RCP) { const double q0 = y[i] * rcp[i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? fma(fma(-d, q0, y[i]), rcp[i], q0) : 0.0; }
+    else y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0;
+  }
 #pragma unroll
   for (int i = N - 2; i >= 0; --i) {
     double t[N];

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(REPROJ_T) reproj_cells_kernel(DevCam cam, cons
 }
 
 // ---------------------------------------------------------------- pose optimizer
-constexpr int POSE_T = 256;
+constexpr int POSE_T = 128;         // a frame has ~100-1,000 matched features; 3 CTAs per SM (launch bounds) for batches
 constexpr int POSE_ACC = 28;        // 21 (upper triangle of A) + 6 (b) + 1 (chi2)
 
 // element n/2 of the sorted data (vk::getMedian, math_utils.h:125-131), by rank counting; all threads get the value
@@ -212,7 +212,7 @@ __device__ __forceinline__ void pose_residual(const double* T, const double* f, 
   e0 *= sic; e1 *= sic;
 }
 
-__global__ void __launch_bounds__(POSE_T) pose_optimize_kernel(DevCam cam, const int* seg_begin, const int* seg_end, const double* f_all,
+__global__ void __launch_bounds__(POSE_T, 3) pose_optimize_kernel(DevCam cam, const int* seg_begin, const int* seg_end, const double* f_all,
                                                                const int* level_all, const double* pos_all, double reproj_thresh, int n_iter,
                                                                double eps, float tukey_b, double* T_io, svob200_pose_opt_result* results,
                                                                uint8_t* outlier_all, double* work_all)
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(POSE_T) pose_optimize_kernel(DevCam cam, const
       double bv[6], dT[6];
       for (int r = 0; r < 6; ++r) bv[r] = sum[21 + r];
       const double new_chi2 = sum[27];
-      ldlt_solve_fixed<6>(A, bv, dT);
+      ldlt_solve_fixed<6, true>(A, bv, dT);     // sums are tree-reduced (tolerance-matched): shared-reciprocal quotients
       ++iters;
       int flag = 0;
       if ((iter > 0 && new_chi2 > chi2 * 1.2) || isnan(dT[0])) {

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         }
         n_meas = (int)s_tot[28];
         new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
-        ldlt_solve_fixed<6>(H, Jres, xs);
+        ldlt_solve_fixed<6, true>(H, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
 #pragma unroll
         for (int k = 0; k < 36; ++k) s_H[k] = H[k];
