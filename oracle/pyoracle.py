@@ -551,7 +551,8 @@ class Ref:
 class StepStats(C.Structure):
     _fields_ = [("T_cur_w", C.c_double * 7), ("chi2", C.c_double), ("n_tracked", C.c_int), ("n_matched", C.c_int),
                 ("n_seeds_updated", C.c_int), ("n_seeds_converged", C.c_int), ("n_seeds_failed", C.c_int),
-                ("n_seeds_skipped", C.c_int), ("align_iters", C.c_int), ("n_exact_chi2", C.c_int)]
+                ("n_seeds_skipped", C.c_int), ("align_iters", C.c_int), ("n_exact_chi2", C.c_int),
+                ("n_reproj_trials", C.c_int), ("n_pose_obs", C.c_int)]
 
 
 class _SeqBase:
@@ -594,6 +595,11 @@ class OracleSeq(_SeqBase):
     def set_last(self, img):
         self.lib.svo_oracle_seq_set_last(self.h, _p(u8(img), c_u8p))
 
+    def set_chain(self, cell_size=30, max_fts=120, pose_opt=1):
+        """Reprojector::reprojectMap + pose optimiser between alignment and the depth filter (frame_handler_mono.cpp:191-222)"""
+        self.lib.svo_oracle_seq_set_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.lib.svo_oracle_seq_set_chain(self.h, int(cell_size), int(max_fts), int(pose_opt))
+
     def seeds(self):
         arr = (Seed * max(self.S, 1))()
         self.lib.svo_oracle_seq_get_seeds(self.h, arr)
@@ -633,6 +639,11 @@ class RefSeq(_SeqBase):
 
     def set_last(self, img):
         self.lib.svo_ref_seq_set_last(self.h, _p(u8(img), c_u8p))
+
+    def set_chain(self, cell_size=30, max_fts=120, pose_opt=1):
+        """the reference's own Reprojector + pose_optimizer between alignment and the depth filter"""
+        self.lib.svo_ref_seq_set_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.lib.svo_ref_seq_set_chain(self.h, int(cell_size), int(max_fts), int(pose_opt))
 
     def seeds(self):
         out = np.zeros((max(self.S, 1), 5), np.float32)

@@ -23,6 +23,9 @@
 #include <svo/sparse_img_align.h>
 #include <svo/matcher.h>
 #include <svo/depth_filter.h>
+#include <svo/map.h>
+#include <svo/reprojector.h>
+#include <svo/pose_optimizer.h>
 #include <map>
 #include <cstring>
 #ifdef SVOB200_DROPIN
@@ -475,6 +478,7 @@ struct svo_ref_step_stats {
   double chi2;
   int n_tracked, n_matched, n_seeds_updated, n_seeds_converged, n_seeds_failed, n_seeds_skipped;
   int align_iters, n_exact_chi2;
+  int n_reproj_trials, n_pose_obs;
 };
 
 struct RefSeq {
@@ -488,6 +492,10 @@ struct RefSeq {
   int max_level, min_level, n_iter, reseed;
   float depth_mean, depth_min;
   std::vector<Point*> conv_points;
+  // chain mode: the reference's own Reprojector + pose optimiser between alignment and the depth filter
+  svo::Map* map = NULL;
+  Reprojector* reproj = NULL;
+  int chain_pose_opt = 0;
 };
 
 void* svo_ref_seq_create(const int* wh, const double* k, int max_level, int min_level, int n_iter, double conv_thresh,
@@ -502,9 +510,25 @@ void* svo_ref_seq_create(const int* wh, const double* k, int max_level, int min_
   return s;
 }
 
+// FrameHandlerMono::processFrame's Step 2 + Step 3 (frame_handler_mono.cpp:191-222) instead of refining every map point;
+// call after svo_ref_seq_set_keyframe.  Config::gridSize / maxFts are process-wide, like in the reference.
+void svo_ref_seq_set_chain(void* h, int cell_size, int max_fts, int pose_opt)
+{
+  RefSeq* s = (RefSeq*)h;
+  Config::gridSize() = cell_size;
+  Config::maxFts() = max_fts;
+  s->map = new svo::Map();
+  s->kf->setKeyframe();
+  s->map->addKeyframe(s->kf);
+  s->reproj = new Reprojector(s->cam, *s->map);
+  s->chain_pose_opt = pose_opt;
+}
+
 void svo_ref_seq_destroy(void* h)
 {
   RefSeq* s = (RefSeq*)h;
+  if (s->reproj) delete s->reproj;
+  if (s->map) { s->map->keyframes_.clear(); delete s->map; }
   s->df->getSeeds().clear();
   delete s->df;
   for (auto f : s->seed_ftrs) delete f;
@@ -566,12 +590,36 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   st->chi2 = al.chi2();
   for (size_t l = 0; l < al.evals.size(); ++l) st->align_iters += al.evals[l];
   from_se3(cur->T_f_w_, st->T_cur_w);
+  if (s->reproj) {
+    std::vector<std::pair<FramePtr, size_t> > overlap;
+    s->reproj->reprojectMap(cur, overlap);
+    st->n_matched = (int)s->reproj->n_matches_; st->n_reproj_trials = (int)s->reproj->n_trials_;
+    std::map<Point*, int> index;
+    for (int i = 0; i < N; ++i) index[s->pts[i]] = i;
+    if (match_ok) for (int i = 0; i < N; ++i) match_ok[i] = 0;
+    if (px_refined) for (int i = 0; i < N; ++i) { Vector2d p(cur->w2c(s->pts[i]->pos_)); px_refined[2 * i] = p[0]; px_refined[2 * i + 1] = p[1]; }
+    for (auto f : cur->fts_) {
+      const int i = index[f->point];
+      if (match_ok) match_ok[i] = 1;
+      if (px_refined) { px_refined[2 * i] = f->px[0]; px_refined[2 * i + 1] = f->px[1]; }
+    }
+    st->n_pose_obs = st->n_matched;
+    if (s->chain_pose_opt) {
+      double scale = 0, e0 = 0, e1 = 0; size_t nobs = 0;
+      pose_optimizer::optimizeGaussNewton(Config::poseOptimThresh(), Config::poseOptimNumIter(), false, cur, scale, e0, e1, nobs);
+      st->n_pose_obs = (int)nobs;
+      from_se3(cur->T_f_w_, st->T_cur_w);
+    }
+    // stationary benchmark workload: the per-point bookkeeping of the reprojector starts afresh every frame
+    for (auto p : s->pts) { p->n_failed_reproj_ = 0; p->n_succeeded_reproj_ = 0; p->type_ = Point::TYPE_UNKNOWN; }
+  } else {
   for (int i = 0; i < N; ++i) {
     Vector2d px(cur->w2c(s->pts[i]->pos_));                         // reprojector.cpp:131-145
     const bool ok = s->matcher.findMatchDirect(*s->pts[i], *cur, px);
     st->n_matched += ok ? 1 : 0;
     if (px_refined) { px_refined[2 * i] = px[0]; px_refined[2 * i + 1] = px[1]; }
     if (match_ok) match_ok[i] = ok ? 1 : 0;
+  }
   }
   s->conv_points.clear();
   s->df->addFrame(cur);                                             // synchronous updateSeeds

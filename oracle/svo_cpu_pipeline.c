@@ -22,6 +22,7 @@ typedef struct {
   double chi2;
   int n_tracked, n_matched, n_seeds_updated, n_seeds_converged, n_seeds_failed, n_seeds_skipped;
   int align_iters, n_exact_chi2;
+  int n_reproj_trials, n_pose_obs;     /* chain mode: Reprojector::n_trials_, features left after the pose optimiser */
 } svo_step_stats;
 
 typedef struct svo_seq {
@@ -41,6 +42,9 @@ typedef struct svo_seq {
   double *seed_px, *seed_f; int* seed_level; svo_seed* seeds;
   /* per-step scratch */
   double *xyz; uint8_t* has_point;
+  /* chain mode (svo_oracle_seq_set_chain): Reprojector::reprojectMap + pose_optimizer::optimizeGaussNewton replace the
+   * refine-every-map-point loop, as in FrameHandlerMono::processFrame (frame_handler_mono.cpp:191-222) */
+  int chain_cell, chain_max_fts, chain_pose_opt;
 } svo_seq;
 
 static void build_frame(svo_seq* s, const uint8_t* img, uint8_t* l0, uint8_t* up, svo_pyr* p)
@@ -93,6 +97,11 @@ void svo_oracle_seq_set_keyframe(svo_seq* s, const uint8_t* img, const double* T
   for (int i = 0; i < S; ++i) { svo_oracle_cam2world(&s->cam, seed_px[2 * i], seed_px[2 * i + 1], s->seed_f + 3 * i); s->seeds[i] = s->seed_init; }
 }
 
+void svo_oracle_seq_set_chain(svo_seq* s, int cell_size, int max_fts, int pose_opt)
+{
+  s->chain_cell = cell_size; s->chain_max_fts = max_fts; s->chain_pose_opt = pose_opt;
+}
+
 void svo_oracle_seq_set_last(svo_seq* s, const uint8_t* img) { build_frame(s, img, s->last0, s->lastu, &s->last); }
 
 static double norm3d(double x, double y, double z) { return sqrt((x * x + y * y) + z * z); }
@@ -118,6 +127,52 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
   st->chi2 = ar.chi2;
   for (int l = 0; l < SVO_MAX_LEVELS; ++l) st->align_iters += ar.iters[l];
   svo_oracle_se3_mul(ar.T_cur_ref, T_last_w, st->T_cur_w);
+  if (s->chain_cell > 0) {
+    /* Reprojector::reprojectMap over the keyframe's map points (one observation each, insertion order = fts_ order), every
+     * point TYPE_UNKNOWN: the benchmark resets the per-point counters every frame to keep the workload stationary */
+    const int N = s->N;
+    svo_map_point* pts = (svo_map_point*)malloc(sizeof(svo_map_point) * (size_t)(N + 1));
+    svo_point_obs* obs = (svo_point_obs*)malloc(sizeof(svo_point_obs) * (size_t)(N + 1));
+    svo_reproj_result* res = (svo_reproj_result*)malloc(sizeof(svo_reproj_result) * (size_t)(N + 1));
+    const int cols = (s->cam.width + s->chain_cell - 1) / s->chain_cell, rows = (s->cam.height + s->chain_cell - 1) / s->chain_cell;
+    int* winner = (int*)malloc(sizeof(int) * (size_t)cols * rows);
+    for (int i = 0; i < N; ++i) {
+      memcpy(pts[i].pos, s->pt_world + 3 * i, sizeof(pts[i].pos));
+      pts[i].type = SVO_POINT_UNKNOWN; pts[i].obs_begin = i; pts[i].obs_end = i + 1;
+      obs[i].keyframe = 0;
+      obs[i].ftr.px_ref[0] = s->kf_px[2 * i]; obs[i].ftr.px_ref[1] = s->kf_px[2 * i + 1];
+      memcpy(obs[i].ftr.f_ref, s->kf_f + 3 * i, sizeof(obs[i].ftr.f_ref));
+      obs[i].ftr.level_ref = s->kf_level[i]; obs[i].ftr.type = 0; obs[i].ftr.grad[0] = 1.0; obs[i].ftr.grad[1] = 0.0;
+    }
+    const svo_pyr* kfp = &s->kf;
+    int nm = 0, nt = 0;
+    svo_oracle_reproject_map(&kfp, &s->cur, &s->cam, st->T_cur_w, N, pts, obs, s->T_kf_w, s->chain_cell, s->chain_max_fts, &s->mopts,
+                             res, winner, &nm, &nt);
+    st->n_matched = nm; st->n_reproj_trials = nt;
+    for (int i = 0; i < N; ++i) {
+      const int ok = res[i].status == SVO_REPROJ_MATCHED;
+      if (px_refined) { px_refined[2 * i] = res[i].px[0]; px_refined[2 * i + 1] = res[i].px[1]; }
+      if (match_ok) match_ok[i] = ok;
+    }
+    st->n_pose_obs = nm;
+    if (s->chain_pose_opt && nm > 0) {
+      /* the new features of the frame, in cell order: f = cam2world(px) (Feature ctor), level = search level */
+      double* f = (double*)malloc(sizeof(double) * 3 * (size_t)nm); double* pos = (double*)malloc(sizeof(double) * 3 * (size_t)nm);
+      int* lv = (int*)malloc(sizeof(int) * (size_t)nm); uint8_t* outl = (uint8_t*)malloc((size_t)nm);
+      int m = 0;
+      for (int c = 0; c < cols * rows; ++c) {
+        const int i = winner[c];
+        if (i < 0) continue;
+        svo_oracle_cam2world(&s->cam, res[i].px[0], res[i].px[1], f + 3 * m);
+        memcpy(pos + 3 * m, pts[i].pos, sizeof(double) * 3); lv[m] = res[i].search_level; ++m;
+      }
+      svo_pose_opt_result pr;
+      svo_oracle_pose_optimize(&s->cam, m, f, lv, pos, 2.0, 10, 0.0000000001, 8.6851f, st->T_cur_w, &pr, outl);
+      st->n_pose_obs = pr.num_obs;
+      free(f); free(pos); free(lv); free(outl);
+    }
+    free(pts); free(obs); free(res); free(winner);
+  } else {
   /* reprojection refinement */
   double Tkw_inv[7], T_cur_kf[7];
   svo_oracle_se3_inverse(s->T_kf_w, Tkw_inv);
@@ -136,6 +191,7 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
     st->n_matched += ok;
     if (px_refined) { px_refined[2 * i] = mr.px_cur[0]; px_refined[2 * i + 1] = mr.px_cur[1]; }
     if (match_ok) match_ok[i] = ok;
+  }
   }
   /* depth filter */
   for (int i = 0; i < s->S; ++i) {

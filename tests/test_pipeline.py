@@ -199,3 +199,32 @@ def test_tracker_c5_size_replicas(ctx, oracle):
             so.close()
     finally:
         trk.close()
+
+
+def test_oracle_chain_matches_reference(oracle, ref):
+    """Chain mode: Reprojector::reprojectMap + pose_optimizer::optimizeGaussNewton between alignment and the depth filter,
+    as FrameHandlerMono::processFrame runs them (frame_handler_mono.cpp:191-222) — the oracle's restatement against the
+    reference's own classes over a sequence (per-point reprojection counters reset every frame on both sides)."""
+    cfg, poses, imgs, kf, last_px = make_sequence(oracle, "C2", 0x00C0FFEE + 3, 8)
+    cam = scenes.cam_of(cfg, Cam)
+    args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
+    so, sr = OracleSeq(oracle, *args), RefSeq(ref, *args)
+    try:
+        for s in (so, sr):
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+            s.set_chain(30, 120, 1)
+            s.set_last(imgs[0])
+        for k in range(1, 8):
+            a, pxa, oka = so.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            b, pxb, okb = sr.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            assert a.n_tracked == b.n_tracked and a.align_iters == b.align_iters
+            assert (a.n_matched, a.n_reproj_trials, a.n_pose_obs) == (b.n_matched, b.n_reproj_trials, b.n_pose_obs)
+            assert np.array_equal(oka, okb) and np.array_equal(pxa[oka == 1], pxb[okb == 1])     # the frame's new features: bit-exact
+            assert np.array_equal(np.array(a.T_cur_w[:]), np.array(b.T_cur_w[:]))                # pose after the optimiser: bit-exact
+            assert a.n_seeds_converged == b.n_seeds_converged
+            assert np.isclose(so.seeds(), sr.seeds(), rtol=1e-6, atol=0).all(axis=1).mean() > 0.99
+            # the pose optimiser tightens the alignment pose (which stops at level 2) against the ground truth
+            grot, gtrans = synth.pose_error(np.array(a.T_cur_w[:]), poses[k])
+            assert grot < 2e-3 and gtrans < 6e-3 and 40 < a.n_matched <= 121
+    finally:
+        so.close(); sr.close()
