@@ -54,7 +54,7 @@ epi_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("reject", 
 seed_dt = np.dtype([("a", "f4"), ("b", "f4"), ("mu", "f4"), ("z_range", "f4"), ("sigma2", "f4")], align=True)
 step_stats_dt = np.dtype([("T_cur_w", "f8", 7), ("chi2", "f8"), ("n_tracked", "i4"), ("n_matched", "i4"), ("n_seeds_updated", "i4"),
                           ("n_seeds_converged", "i4"), ("n_seeds_failed", "i4"), ("n_seeds_skipped", "i4"), ("align_iters", "i4"),
-                          ("n_exact_chi2", "i4")], align=True)
+                          ("n_exact_chi2", "i4"), ("n_reproj_trials", "i4"), ("n_pose_obs", "i4")], align=True)
 seed_obs_dt = np.dtype([("status", "i4"), ("search_level", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"), ("z", "f8"),
                         ("px_cur", "f8", 2), ("epi_length", "f8")], align=True)
 
@@ -129,6 +129,7 @@ def load_library():
     L.svob200_tracker_stage_name.argtypes = [C.c_int]
     L.svob200_tracker_get_seed_obs.argtypes = [V, V]
     L.svob200_tracker_debug_align.argtypes = [V, V]
+    L.svob200_tracker_set_chain.argtypes = [V, C.c_int, C.c_int, C.c_int]
     L.svob200_dev_alloc.argtypes = [V, C.c_size_t, C.POINTER(V)]
     L.svob200_dev_free.argtypes = [V, V]
     L.svob200_dev_upload.argtypes = [V, V, V, C.c_size_t]
@@ -168,7 +169,7 @@ EXPORTED_SYMBOLS = [
     "svob200_frame_upload_level", "svob200_shi_tomasi", "svob200_warp_matrix_affine", "svob200_warp_affine",
     "svob200_depth_from_triangulation",
     "svob200_frame_upload_yuv420", "svob200_reproject_map", "svob200_pose_opt_opts_default", "svob200_pose_optimize",
-    "svob200_points_optimize", "svob200_seeds_initialize", "svob200_tracker_debug_align",
+    "svob200_points_optimize", "svob200_seeds_initialize", "svob200_tracker_debug_align", "svob200_tracker_set_chain",
 ]
 
 
@@ -496,6 +497,10 @@ class Tracker:
             imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
             stride = imgs.shape[-1]
         self.ctx._ck(self.L.svob200_tracker_set_last(self.h, _ptr(imgs), int(stride), mem))
+
+    def set_chain(self, cell_size=30, max_fts=120, pose_opt=1):
+        """reprojector grid rules + pose optimiser between alignment and the depth filter (svob200_tracker_set_chain)"""
+        self.ctx._ck(self.L.svob200_tracker_set_chain(self.h, int(cell_size), int(max_fts), int(pose_opt)))
 
     def step(self, cur_imgs, T_last_w, last_px, want_px=False):
         """Host-memory step: returns per-sequence stats (and refined pixels / success flags)."""

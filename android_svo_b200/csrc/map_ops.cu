@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128) reproj_select_kernel(DevCam cam, const do
                                                             svob200_feature_ref* ftr_out, double* depth_ref, double* px_in, uint8_t* active,
                                                             svob200_reproj_result* results)
 {
-  const int b = blockIdx.x;
+  const int b = blockIdx.x;     // image inside the current frame batch
   const double* T = T_cur_w + 7 * (size_t)b;
   const v3d cur_pos = frame_pos(T);
   for (int i = pt_off[b] + threadIdx.x; i < pt_off[b + 1]; i += blockDim.x) {

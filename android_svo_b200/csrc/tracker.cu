@@ -56,7 +56,35 @@ __global__ void __launch_bounds__(128) step_stats_kernel(const int* ftr_off, con
     for (int l = 0; l < SVOB200_MAX_LEVELS; ++l) it += align[b].iters[l];
     o->align_iters = it;
     o->n_exact_chi2 = align[b].n_exact_chi2;
+    o->n_reproj_trials = 0; o->n_pose_obs = 0;
   }
+}
+
+// chain mode: segment of image b in the compacted match arrays = [b * n_cells, b * n_cells + count[b])
+__global__ void chain_segments_kernel(int batch, int n_cells, const int* count, int* seg_begin, int* seg_end)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  seg_begin[b] = b * n_cells;
+  seg_end[b] = b * n_cells + count[b];
+}
+
+// chain mode: per-point outputs of the step in the tracker's plain arrays
+__global__ void chain_export_kernel(int n, const svob200_reproj_result* res, double* px_out, int* match_ok)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const svob200_reproj_result r = res[i];
+  match_ok[i] = r.status == SVOB200_REPROJ_MATCHED ? 1 : 0;
+  px_out[2 * (size_t)i] = r.px[0]; px_out[2 * (size_t)i + 1] = r.px[1];
+}
+
+__global__ void chain_stats_kernel(int batch, const svob200_reproj_stats* rs, const svob200_pose_opt_result* pr, int pose_opt, svob200_step_stats* stats)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  stats[b].n_reproj_trials = rs[b].n_trials;
+  stats[b].n_pose_obs = pose_opt ? pr[b].num_obs : rs[b].n_matches;
 }
 
 template <class T> int dalloc(svob200_ctx* ctx, T** p, size_t n)
@@ -105,6 +133,17 @@ struct svob200_tracker {
   int chunk = 256;                     // sequences per H2D/compute pipeline chunk (host mode)
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
+  // chain mode (svob200_tracker_set_chain): reprojector grid rules + pose optimiser instead of refining every map point
+  int chain_cell = 0, chain_max_fts = 0, chain_pose_opt = 0, chain_cells = 0;
+  std::vector<double> h_pt_world;
+  svob200_map_point* d_points = nullptr;
+  svob200_reproj_result* d_reproj = nullptr;
+  svob200_reproj_stats* d_rstats = nullptr;
+  svob200_pose_opt_result* d_pose = nullptr;
+  int *d_winner = nullptr, *d_m_level = nullptr, *d_m_point = nullptr, *d_m_count = nullptr, *d_seg_begin = nullptr, *d_seg_end = nullptr;
+  double *d_m_f = nullptr, *d_m_pos = nullptr, *d_pose_work = nullptr;
+  uint8_t* d_outlier = nullptr;
+  void* d_reproj_scratch = nullptr;
   // single-stream latency: in device mode with small batches the 14 launches of a step are replayed as ONE CUDA graph
   // (captured once per distinct set of buffer addresses: a camera ring buffer has only a few), which removes the
   // per-launch driver cost and most of the inter-kernel gaps
@@ -200,6 +239,7 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   const int N = ftr_offsets[B], S = seed_offsets[B];
   t->N = N; t->S = S;
   t->h_ftr_off.assign(ftr_offsets, ftr_offsets + B + 1);
+  t->h_pt_world.assign(pt_world, pt_world + 3 * (size_t)N);
   t->h_seed_off.assign(seed_offsets, seed_offsets + B + 1);
   for (int b = 0; b < B; ++b) t->max_per = std::max(t->max_per, ftr_offsets[b + 1] - ftr_offsets[b]);
   const int slot = svob200_frame_slot(ctx, t->fid_kf);
@@ -273,6 +313,40 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   return SVOB200_OK;
 }
 
+int svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, int pose_opt)
+{
+  if (!t) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (!t->d_stats) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_chain: set_keyframe first");
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);          // captured steps belong to the other mode
+  t->graphs.clear();
+  if (cell_size <= 0) { t->chain_cell = 0; return SVOB200_OK; }
+  const int B = t->batch, N = t->N;
+  const int n_cells = ((t->cam.width + cell_size - 1) / cell_size) * ((t->cam.height + cell_size - 1) / cell_size);
+  if (n_cells > 8192) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_chain: grid of %d cells exceeds the kernel's table (8192)", n_cells);
+  if (!t->d_points || n_cells != t->chain_cells) {
+#define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
+    const size_t M = (size_t)B * n_cells;
+    if (!t->d_points) { DA(t->d_points, N); DA(t->d_reproj, N); DA(t->d_rstats, B); DA(t->d_pose, B); DA(t->d_m_count, B); DA(t->d_seg_begin, B); DA(t->d_seg_end, B);
+      uint8_t* q = nullptr; if (int e = dalloc(ctx, &q, reproject_scratch_bytes(N))) return e; t->owned.push_back(q); t->d_reproj_scratch = q; }
+    DA(t->d_winner, M); DA(t->d_m_level, M); DA(t->d_m_point, M); DA(t->d_m_f, 3 * M); DA(t->d_m_pos, 3 * M); DA(t->d_pose_work, M); DA(t->d_outlier, M);
+#undef DA
+  }
+  // the keyframe's map points as reprojector candidates: insertion order = the keyframe's fts_ order, one observation each
+  // (the keyframe feature), every point TYPE_UNKNOWN
+  std::vector<svob200_map_point> pts((size_t)N);
+  for (int i = 0; i < N; ++i) {
+    for (int k = 0; k < 3; ++k) pts[i].pos[k] = t->h_pt_world[3 * (size_t)i + k];
+    pts[i].type = SVOB200_POINT_UNKNOWN; pts[i].obs_begin = i; pts[i].obs_end = i + 1; pts[i].reserved = 0;
+  }
+  CU(cudaMemcpyAsync(t->d_points, pts.data(), sizeof(svob200_map_point) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(t->d_pose, 0, sizeof(svob200_pose_opt_result) * (size_t)B, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  t->chain_cell = cell_size; t->chain_max_fts = max_fts; t->chain_pose_opt = pose_opt ? 1 : 0; t->chain_cells = n_cells;
+  return SVOB200_OK;
+}
+
 int svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride, int mem)
 {
   if (!t || !imgs) return SVOB200_ERR_ARG;
@@ -323,6 +397,25 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   if (launch_reproject_prepare(cam, nf, t->d_ftrs + f0, t->d_pt_world + 3 * (size_t)f0, t->d_T_kf_ftr + 7 * (size_t)f0, t->d_T_cur,
                                t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
   MARK(4);
+  if (t->chain_cell > 0) {
+    // 4b-5. chain mode: Reprojector::reprojectMap (grid, every in-frame candidate matched in parallel, per-cell first success,
+    // maxFts) over the keyframe's map points, then pose_optimizer::optimizeGaussNewton on the frame's new features (in place
+    // on T_cur, so the depth filter sees the optimised pose).  Ranges always cover the whole batch in this mode.
+    MARK(4);
+    const int rc = launch_reproject_map(ctx->d_table, cur->slot, cam, cnt, t->d_T_cur, t->d_ftr_off, t->N, t->d_points, t->d_ftrs, t->d_T_kf_ftr,
+                                        t->chain_cell, t->chain_max_fts, t->mopts, t->d_reproj, t->d_winner, t->d_rstats, t->d_reproj_scratch,
+                                        t->d_match_scratch, t->d_m_f, t->d_m_level, t->d_m_pos, t->d_m_point, t->d_m_count, s, &ctx->launches);
+    if (rc) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_map failed (%d)", rc);
+    MARK(5); MARK(6);
+    chain_export_kernel<<<(t->N + 127) / 128, 128, 0, s>>>(t->N, t->d_reproj, t->d_px_out, t->d_match_ok); ++ctx->launches;
+    if (t->chain_pose_opt) {
+      chain_segments_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->chain_cells, t->d_m_count, t->d_seg_begin, t->d_seg_end); ++ctx->launches;
+      if (launch_pose_optimize(cam, cnt, t->d_seg_begin, t->d_seg_end, t->d_m_f, t->d_m_level, t->d_m_pos, 2.0, 10, 0.0000000001, 8.6851f, t->d_T_cur,
+                               t->d_pose, t->d_outlier, t->d_pose_work, s, &ctx->launches))
+        return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: pose_optimize failed");
+    }
+    MARK(7);
+  } else {
   // 5. Matcher::findMatchDirect per map point (keyframe patch -> current frame)
   // (item indices inside the call are relative to f0, so the output arrays are passed at f0 as well)
   if (launch_match_direct(ctx->d_table, cur->slot, cam, nf, t->d_ftrs + f0, t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->mopts, nullptr,
@@ -330,6 +423,7 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
                           (marks && t->profiling) ? &t->ev[5] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
   MARK(7);
+  }
   // 6. DepthFilter::updateSeeds(cur)
   if (launch_seeds_update(ctx->d_table, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
                           t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s, &ctx->launches,
@@ -340,6 +434,9 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
                                         t->d_seeds, t->seed_init, t->reseed, t->d_stats + c0);
   ++ctx->launches;
+  if (t->chain_cell > 0) {
+    chain_stats_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->d_rstats, t->d_pose, t->chain_pose_opt, t->d_stats + c0); ++ctx->launches;
+  }
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
   MARK(12);
 #undef MARK
@@ -393,7 +490,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     CU(cudaMemcpyAsync(t->d_step_in, t->h_pinned, in_bytes, cudaMemcpyHostToDevice, s));
     const double* d_T_last = t->d_step_in;
     const double* d_last_px = t->d_step_in + 7 * (size_t)B;
-    const int chunk = (t->profiling || B <= t->chunk) ? B : t->chunk;
+    const int chunk = (t->profiling || B <= t->chunk || t->chain_cell > 0) ? B : t->chunk;
     const int n_chunks = (B + chunk - 1) / chunk;
     if (!t->copy_stream) CU(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
     while ((int)t->chunk_ev.size() < n_chunks + 1) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); t->chunk_ev.push_back(e); }

@@ -254,6 +254,8 @@ typedef struct {
   int n_matched;           /* successful findMatchDirect */
   int n_seeds_updated, n_seeds_converged, n_seeds_failed, n_seeds_skipped;
   int align_iters, n_exact_chi2;
+  int n_reproj_trials;     /* chain mode: Reprojector::n_trials_ */
+  int n_pose_obs;          /* chain mode: features left after the pose optimiser (sfba_n_edges_final) */
 } svob200_step_stats;
 int  svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batch, int n_levels,
                             const svob200_align_opts* aopts, const svob200_matcher_opts* mopts,
@@ -266,6 +268,13 @@ int  svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int s
                                   const double* pt_world, const int* seed_offsets, const double* seed_px,
                                   const int* seed_level);
 int  svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride, int mem);
+/* Chain mode (call after set_keyframe): between sparse alignment and the depth filter the step runs
+ * Reprojector::reprojectMap over the keyframe's map points (grid of cell_size, first success per cell, max_fts) and, with
+ * pose_opt != 0, pose_optimizer::optimizeGaussNewton on the matched features — FrameHandlerMono::processFrame's Step 2 and
+ * Step 3 (frame_handler_mono.cpp:191-222) — instead of refining every map point; the depth filter then sees the optimised
+ * pose.  Every point enters as TYPE_UNKNOWN each frame (the per-point reprojection counters are host-side map management).
+ * cell_size <= 0 switches back. */
+int  svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, int pose_opt);
 /* cur_imgs: batch images; T_last_w: 7 doubles per sequence (pose of the last frame); last_px: 2 doubles
  * per map feature (its pixel in the last frame).  stats (batch), px_refined (2 per feature), match_ok
  * (1 per feature) may be NULL.  mem tells where ALL pointer arguments live; in device mode level 0 of

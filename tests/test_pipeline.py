@@ -228,3 +228,52 @@ def test_oracle_chain_matches_reference(oracle, ref):
             assert grot < 2e-3 and gtrans < 6e-3 and 40 < a.n_matched <= 121
     finally:
         so.close(); sr.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pose_opt", [1, 0])
+def test_tracker_chain_matches_oracle(ctx, oracle, pose_opt):
+    """svob200_tracker_step in chain mode (reprojector grid rules + pose optimiser inside the step) against the oracle's
+    chain, which is bit-exact to the reference's (test_oracle_chain_matches_reference)."""
+    from android_svo_b200 import capi
+    batch, n_frames = 3, 5
+    seqs = [make_sequence(oracle, "C2", 0x00C0FFEE + 20 + i, n_frames + 1) for i in range(batch)]
+    cfg = seqs[0][0]
+    cam_o, cam_g = scenes.cam_of(cfg, Cam), scenes.cam_of(cfg, capi.Camera)
+    args = (cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
+    oseqs = [OracleSeq(oracle, cam_o, *args) for _ in range(batch)]
+    trk = capi.Tracker(ctx, cam_g, batch, *args)
+    try:
+        N, S = cfg["n_features"], cfg["n_seeds"]
+        for s, (_, poses, imgs, kf, _) in zip(oseqs, seqs):
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+            s.set_chain(30, 40, pose_opt)                       # max_fts = 40: the break fires
+            s.set_last(imgs[0])
+        cat = lambda key: np.concatenate([q[3][key] for q in seqs])
+        trk.set_keyframe(np.stack([q[2][0] for q in seqs]), np.stack([q[1][0] for q in seqs]), np.arange(batch + 1) * N,
+                         cat("kf_px"), cat("kf_level"), cat("pt_world"), np.arange(batch + 1) * S, cat("seed_px"), cat("seed_level"))
+        trk.set_chain(30, 40, pose_opt)
+        trk.set_last(np.stack([q[2][0] for q in seqs]))
+        for k in range(1, n_frames + 1):
+            stats, px, ok = trk.step(np.stack([q[2][k] for q in seqs]), np.stack([q[1][k - 1] for q in seqs]),
+                                     np.concatenate([q[4][k - 1] for q in seqs]), want_px=True)
+            seeds_g = trk.seeds()
+            for b, s in enumerate(oseqs):
+                e, pxe, oke = s.step(seqs[b][2][k], seqs[b][1][k - 1], seqs[b][4][k - 1], want_px=True)
+                g = stats[b]
+                assert g["n_tracked"] == e.n_tracked and g["align_iters"] == e.align_iters
+                assert (g["n_matched"], g["n_reproj_trials"], g["n_pose_obs"]) == (e.n_matched, e.n_reproj_trials, e.n_pose_obs)
+                assert g["n_matched"] == 41
+                okb = ok[b * N:(b + 1) * N]
+                assert np.array_equal(okb, oke) and np.abs(px[b * N:(b + 1) * N][okb == 1] - pxe[oke == 1]).max() <= 1e-3
+                rot, trans = synth.pose_error(g["T_cur_w"], np.array(e.T_cur_w[:]))
+                assert rot < 1e-9 and trans < 1e-9
+                for key in ("n_seeds_updated", "n_seeds_converged", "n_seeds_failed", "n_seeds_skipped"):
+                    assert g[key] == getattr(e, key), key
+                sg = seeds_g[b * S:(b + 1) * S]
+                sg = np.stack([sg[c] for c in ("a", "b", "mu", "z_range", "sigma2")], 1)
+                assert np.isclose(sg, s.seeds(), rtol=1e-5, atol=0).all(axis=1).mean() > 0.99
+    finally:
+        trk.close()
+        for s in oseqs:
+            s.close()
