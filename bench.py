@@ -38,6 +38,7 @@ PLANE_Z = 2.0
 KF_INDEX = 0
 POOL_INDICES = (36, 39, 42, 45)     # trajectory frames cycled (ping-pong) as the live stream
 DEPTH_MEAN, DEPTH_MIN = 2.4, 1.2
+CHAIN_CELL, CHAIN_MAX_FTS = 30, 120   # Config::gridSize / maxFts defaults (config.cpp)
 
 
 def parse_args():
@@ -51,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (ncu captures: only full-batch launches remain)")
+    ap.add_argument("--chain", action="store_true", help="run the step in chain mode in BOTH arms: reprojector grid rules (cell 30, maxFts 120) + "
+                    "pose optimiser between alignment and the depth filter (FrameHandlerMono::processFrame Steps 2-3)")
     ap.add_argument("--no-widen", action="store_true", help="skip the timing of the SURVEY 8f operators (reprojector, optimizers, YUV, seed init)")
     return ap.parse_args()
 
@@ -162,7 +165,7 @@ class ClockSampler:
 CPU_FRAMES_PER_STEP = 16   # a CPU "step" = this many consecutive frames of every sampled sequence (bounded sample, ~10-30 core-s per run)
 
 
-def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP):
+def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False):
     """Times the front-end step of `n_seqs` independent sequences on the host cores.  Uses the real
     reference (oracle/_ref/libsvo_ref.so) when it was built, else the C restatement.  One timed step =
     `inner` consecutive frames of every sequence, one worker task per sequence."""
@@ -185,6 +188,8 @@ def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP):
         args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, DEPTH_MEAN, DEPTH_MIN, 1)
         s = RefSeq(ref, *args) if kind == "reference" else OracleSeq(oracle, *args)
         s.set_keyframe(imgs[0], poses[i, 0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+        if chain:
+            s.set_chain(CHAIN_CELL, CHAIN_MAX_FTS, 1)
         s.set_last(imgs[1])
         last_px = [frontend.project_many(cfg, poses[i, 1 + k], kf["pt_world"]) for k in range(len(POOL_INDICES))]
         return s, imgs[1:], last_px
@@ -228,7 +233,7 @@ def pinned_array(ctx, shape, dtype):
 class GpuWorkload:
     """Everything the timed loops need, resident: tracker, frame pool on device + pinned host, per-step inputs."""
 
-    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME):
+    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME, chain=False):
         self.ctx, self.capi, self.cfg = ctx, capi, cfg
         B = len(seq_ids)
         self.B = B
@@ -275,6 +280,8 @@ class GpuWorkload:
                                 DEPTH_MEAN, DEPTH_MIN, 1)
         self.trk.set_keyframe(self.kf_host, poses[:, 0], np.arange(B + 1) * N, kf_px.reshape(-1, 2), kf_level.reshape(-1),
                               pt_world.reshape(-1, 3), np.arange(B + 1) * S, seed_px.reshape(-1, 2), seed_level.reshape(-1))
+        if chain:
+            self.trk.set_chain(CHAIN_CELL, CHAIN_MAX_FTS, 1)
         # per-step inputs for every pool frame used as "last": pose + pixel of every map point
         self.in_host, self.in_dev = [], []
         for k in range(F):
@@ -337,7 +344,7 @@ def run_b200(args, rank, world, local_rank):
     total, per, rng = sharding.shard(args.seqs, rank, world)     # contiguous block partition
     seq_ids = list(rng)
     t_setup = time.time()
-    wl = GpuWorkload(ctx, capi, cfg, seq_ids)
+    wl = GpuWorkload(ctx, capi, cfg, seq_ids, chain=args.chain)
     t_setup = time.time() - t_setup
     K, W = args.steps, args.warmup
     order = ping_pong(len(POOL_INDICES), 2 * (W + K) + 8)
@@ -484,6 +491,8 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": "C5: %d independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each), "
                                    "block-sharded over %d GPU(s); step = 1 frame of every sequence" % (total, N, S, world),
                        "sequences_total": total, "sequences_per_gpu": per, "frame_pool": list(POOL_INDICES),
+                       "step": ("chain: reprojector grid rules (cell %d, maxFts %d) + pose optimiser between alignment and the depth filter"
+                                % (CHAIN_CELL, CHAIN_MAX_FTS)) if args.chain else "refine every map point of the keyframe (batched superset of the reprojector)",
                        "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (per * cfg["w"] * cfg["h"] / 1e6)},
             "e2e": {"skipped": "--no-e2e"} if args.no_e2e else {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d_bytes * world),
                     "d2h_bytes_per_step": int(wl.d2h_bytes * world), "ms_per_step": round(e2e_s / K * 1e3, 4),
@@ -694,10 +703,10 @@ LATENCY_DESC = {"C2": "C2: one 640x480 sequence, 4-level pyramid, 120 features, 
                 "C4": "C4: one 1920x1080 sequence (phone-shaped), 5-level pyramid, 1,000 features, 10,000 seeds"}
 
 
-def latency_single(ctx, capi, name, n_frames=60):
+def latency_single(ctx, capi, name, n_frames=60, chain=False):
     """Single-stream: one sequence, per-frame latency through the C ABI with host buffers (p50) and resident."""
     cfg = synth.CONFIGS[name]
-    wl = GpuWorkload(ctx, capi, cfg, [4096], cfg_name=name)
+    wl = GpuWorkload(ctx, capi, cfg, [4096], cfg_name=name, chain=chain)
     order = ping_pong(len(POOL_INDICES), n_frames + 30)
     res = {}
     for mode, mem in (("host_buffers", capi.MEM_HOST), ("resident", capi.MEM_DEVICE)):
@@ -755,19 +764,23 @@ def main():
     cfg = synth.CONFIGS[CFG_NAME]
     threads = os.cpu_count() or 1
 
+    global METRIC
+    if args.chain:
+        METRIC = "front-end frames/s (pyramid + sparse align + reprojector + pose optimiser + seed update), batched C2 sequences"
     if args.impl == "reference":
         # the reference's own CPU implementation of the path, all host threads, rank 0 only
         if rank != 0:
             return
         n = args.cpu_seqs or max(8, 4 * threads)
-        r = cpu_arm(cfg, n, args.steps, args.warmup, threads)
+        r = cpu_arm(cfg, n, args.steps, args.warmup, threads, chain=args.chain)
         line = {"impl": "reference", "metric": METRIC, "value": round(r["fps"], 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["seconds"] / args.steps * 1e3, 3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 pixels / f32 photometric / f64 geometry",
                 "data": "synthetic",
                 "config": {"workload": "C5: independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each); "
                                        "step = 1 frame of every sequence of the sample" % (cfg["n_features"], cfg["n_seeds"]),
-                           "sequences_total": args.seqs, "sample_sequences": n, "frames_per_sequence_per_step": r["inner"]},
+                           "sequences_total": args.seqs, "sample_sequences": n, "frames_per_sequence_per_step": r["inner"],
+                           "step": "chain (reprojector + pose optimiser)" if args.chain else "refine every map point of the keyframe"},
                 "cpu_baseline": {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                  "sample": "%d sequences x %d steps x %d frames (+%d warm-up steps), %d host threads, %.1f s wall"
                                            % (n, args.steps, r["inner"], args.warmup, threads, r["seconds"])},
@@ -791,17 +804,17 @@ def main():
             out["latency"] = {}
             for name in ("C2", "C3", "C4"):
                 try:
-                    out["latency"][name] = latency_single(ctx, capi, name)
+                    out["latency"][name] = latency_single(ctx, capi, name, chain=args.chain)
                 except Exception as e:   # pragma: no cover
                     out["latency"][name] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline and not args.no_latency:
             # the reference's per-frame latency on ONE host core, same C2 sequence shape (the reference's native single-stream mode)
-            r1 = cpu_arm(cfg, 1, 3, 1, 1)
+            r1 = cpu_arm(cfg, 1, 3, 1, 1, chain=args.chain)
             out["latency"]["C2"]["cpu_reference_1_thread"] = {"p50_ms": round(1e3 / r1["fps"], 4), "kind": r1["kind"],
                                                               "sample": "1 sequence x 3 steps x %d frames, 1 thread" % r1["inner"]}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_seqs or max(8, 4 * threads)
-            r = cpu_arm(cfg, n, 10, 1, threads)
+            r = cpu_arm(cfg, n, 10, 1, threads, chain=args.chain)
             out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                    "sample": "%d sequences x 10 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
                                              % (n, r["inner"], threads, r["seconds"])}
