@@ -65,7 +65,8 @@ int launch_reproject_map(const DevFrame* d_frames, int cur_slot, const DevCam& c
                          int cell_size, int max_fts, svob200_matcher_opts opts, svob200_reproj_result* d_results, int* d_cell_winner,
                          svob200_reproj_stats* d_stats, void* d_scratch, void* d_match_scratch,
                          double* d_m_f, int* d_m_level, double* d_m_pos, int* d_m_point, int* d_m_count,   // optional compacted matches
-                         cudaStream_t s, long long* launches);
+                         cudaStream_t s, long long* launches,
+                         int image_base = 0, int point_base = 0, int n_range = -1 /* sub-range of a larger batch (tracker chunks) */);
 int launch_pose_optimize(const DevCam& cam, int batch, const int* d_seg_begin, const int* d_seg_end, const double* d_f, const int* d_level,
                          const double* d_pos, double reproj_thresh, int n_iter, double eps, float tukey_b, double* d_T_io,
                          svob200_pose_opt_result* d_results, uint8_t* d_outlier, double* d_work, cudaStream_t s, long long* launches);

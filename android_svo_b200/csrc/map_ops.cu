@@ -32,7 +32,7 @@ __device__ __forceinline__ v3d frame_pos(const double* T)           // Frame::po
 // reprojectPoint (:246-259) + the head of findMatchDirect (getCloseViewObs, matcher.cpp:161-173)
 __global__ void __launch_bounds__(128) reproj_select_kernel(DevCam cam, const double* T_cur_w, const int* pt_off, const svob200_map_point* pts,
                                                             const svob200_feature_ref* obs, const double* T_obs_w, int cell_size, int grid_cols,
-                                                            svob200_feature_ref* ftr_out, double* depth_ref, double* px_in, uint8_t* active,
+                                                            int image_base, svob200_feature_ref* ftr_out, double* depth_ref, double* px_in, uint8_t* active,
                                                             svob200_reproj_result* results)
 {
   const int b = blockIdx.x;     // image inside the current frame batch
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) reproj_select_kernel(DevCam cam, const do
         if (!(min_cos < 0.5)) {
           act = 1;
           svob200_feature_ref f = obs[best];
-          f.cur_image = b;
+          f.cur_image = image_base + b;
           double inv[7];
           se3_inverse(T_obs_w + 7 * (size_t)best, inv);
           se3_mul(T, inv, f.T_cur_ref);
@@ -493,8 +493,11 @@ int launch_reproject_map(const DevFrame* d_frames, int cur_slot, const DevCam& c
                          int cell_size, int max_fts, svob200_matcher_opts opts, svob200_reproj_result* d_results, int* d_cell_winner,
                          svob200_reproj_stats* d_stats, void* d_scratch, void* d_match_scratch,
                          double* d_m_f, int* d_m_level, double* d_m_pos, int* d_m_point, int* d_m_count,
-                         cudaStream_t s, long long* launches)
+                         cudaStream_t s, long long* launches, int image_base, int point_base, int n_range)
 {
+  // d_T_cur_w, d_pt_off, d_cell_winner, d_stats, d_m_* already point at image `image_base` (offsets in d_pt_off stay
+  // ABSOLUTE indices into d_points / d_results); this call covers the points [point_base, point_base + n_range)
+  if (n_range < 0) n_range = n_points - point_base;
   if (batch <= 0) return 0;
   const int cols = (cam.width + cell_size - 1) / cell_size, rows = (cam.height + cell_size - 1) / cell_size;
   const int n_cells = cols * rows;
@@ -509,12 +512,14 @@ int launch_reproject_map(const DevFrame* d_frames, int cur_slot, const DevCam& c
   int* ok = reinterpret_cast<int*>(p); p += up256(m * sizeof(int));
   int* level = reinterpret_cast<int*>(p); p += up256(m * sizeof(int));
   double* A = reinterpret_cast<double*>(p);
-  reproj_select_kernel<<<batch, 128, 0, s>>>(cam, d_T_cur_w, d_pt_off, d_points, d_obs, d_T_obs_w, cell_size, cols, ftr, depth, px_in, active, d_results);
+  reproj_select_kernel<<<batch, 128, 0, s>>>(cam, d_T_cur_w, d_pt_off, d_points, d_obs, d_T_obs_w, cell_size, cols, image_base, ftr, depth, px_in, active, d_results);
   ++*launches;
-  if (n_points > 0)
-    if (launch_match_direct(d_frames, cur_slot, cam, n_points, ftr, depth, px_in, opts, nullptr, px_out, ok, d_match_scratch, n_points, 0, s, launches,
-                            nullptr, active, level, A))
+  if (n_range > 0) {
+    const size_t o = (size_t)point_base;
+    if (launch_match_direct(d_frames, cur_slot, cam, n_range, ftr + o, depth + o, px_in + 2 * o, opts, nullptr, px_out + 2 * o, ok + o, d_match_scratch,
+                            n_points, point_base, s, launches, nullptr, active + o, level + o, A + 4 * o))
       return -1;
+  }
   reproj_cells_kernel<<<batch, REPROJ_T, 0, s>>>(cam, d_pt_off, d_points, active, ok, px_out, level, A, n_cells, max_fts, d_results, d_cell_winner, d_stats,
                                                  d_m_f, d_m_level, d_m_pos, d_m_point, d_m_count);
   ++*launches;

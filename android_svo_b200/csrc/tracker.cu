@@ -400,18 +400,21 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   if (t->chain_cell > 0) {
     // 4b-5. chain mode: Reprojector::reprojectMap (grid, every in-frame candidate matched in parallel, per-cell first success,
     // maxFts) over the keyframe's map points, then pose_optimizer::optimizeGaussNewton on the frame's new features (in place
-    // on T_cur, so the depth filter sees the optimised pose).  Ranges always cover the whole batch in this mode.
+    // on T_cur, so the depth filter sees the optimised pose).
     MARK(4);
-    const int rc = launch_reproject_map(ctx->d_table, cur->slot, cam, cnt, t->d_T_cur, t->d_ftr_off, t->N, t->d_points, t->d_ftrs, t->d_T_kf_ftr,
-                                        t->chain_cell, t->chain_max_fts, t->mopts, t->d_reproj, t->d_winner, t->d_rstats, t->d_reproj_scratch,
-                                        t->d_match_scratch, t->d_m_f, t->d_m_level, t->d_m_pos, t->d_m_point, t->d_m_count, s, &ctx->launches);
+    const size_t cb = (size_t)c0 * t->chain_cells;
+    const int rc = launch_reproject_map(ctx->d_table, cur->slot, cam, cnt, t->d_T_cur + 7 * (size_t)c0, t->d_ftr_off + c0, t->N, t->d_points, t->d_ftrs,
+                                        t->d_T_kf_ftr, t->chain_cell, t->chain_max_fts, t->mopts, t->d_reproj, t->d_winner + cb, t->d_rstats + c0,
+                                        t->d_reproj_scratch, t->d_match_scratch, t->d_m_f + 3 * cb, t->d_m_level + cb, t->d_m_pos + 3 * cb,
+                                        t->d_m_point + cb, t->d_m_count + c0, s, &ctx->launches, c0, f0, nf);
     if (rc) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_map failed (%d)", rc);
     MARK(5); MARK(6);
-    chain_export_kernel<<<(t->N + 127) / 128, 128, 0, s>>>(t->N, t->d_reproj, t->d_px_out, t->d_match_ok); ++ctx->launches;
+    chain_export_kernel<<<(nf + 127) / 128, 128, 0, s>>>(nf, t->d_reproj + f0, t->d_px_out + 2 * (size_t)f0, t->d_match_ok + f0); ++ctx->launches;
     if (t->chain_pose_opt) {
-      chain_segments_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->chain_cells, t->d_m_count, t->d_seg_begin, t->d_seg_end); ++ctx->launches;
-      if (launch_pose_optimize(cam, cnt, t->d_seg_begin, t->d_seg_end, t->d_m_f, t->d_m_level, t->d_m_pos, 2.0, 10, 0.0000000001, 8.6851f, t->d_T_cur,
-                               t->d_pose, t->d_outlier, t->d_pose_work, s, &ctx->launches))
+      chain_segments_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->chain_cells, t->d_m_count + c0, t->d_seg_begin + c0, t->d_seg_end + c0); ++ctx->launches;
+      // segments are relative to this range's slice of the compacted arrays
+      if (launch_pose_optimize(cam, cnt, t->d_seg_begin + c0, t->d_seg_end + c0, t->d_m_f + 3 * cb, t->d_m_level + cb, t->d_m_pos + 3 * cb, 2.0, 10,
+                               0.0000000001, 8.6851f, t->d_T_cur + 7 * (size_t)c0, t->d_pose + c0, t->d_outlier + cb, t->d_pose_work + cb, s, &ctx->launches))
         return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: pose_optimize failed");
     }
     MARK(7);
@@ -435,7 +438,7 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
                                         t->d_seeds, t->seed_init, t->reseed, t->d_stats + c0);
   ++ctx->launches;
   if (t->chain_cell > 0) {
-    chain_stats_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->d_rstats, t->d_pose, t->chain_pose_opt, t->d_stats + c0); ++ctx->launches;
+    chain_stats_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->d_rstats + c0, t->d_pose + c0, t->chain_pose_opt, t->d_stats + c0); ++ctx->launches;
   }
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
   MARK(12);
@@ -490,7 +493,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     CU(cudaMemcpyAsync(t->d_step_in, t->h_pinned, in_bytes, cudaMemcpyHostToDevice, s));
     const double* d_T_last = t->d_step_in;
     const double* d_last_px = t->d_step_in + 7 * (size_t)B;
-    const int chunk = (t->profiling || B <= t->chunk || t->chain_cell > 0) ? B : t->chunk;
+    const int chunk = (t->profiling || B <= t->chunk) ? B : t->chunk;
     const int n_chunks = (B + chunk - 1) / chunk;
     if (!t->copy_stream) CU(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
     while ((int)t->chunk_ev.size() < n_chunks + 1) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); t->chunk_ev.push_back(e); }
