@@ -113,6 +113,7 @@ def load_library():
     L.svob200_seeds_update.argtypes = [V, C.c_int64, C.POINTER(Camera), C.c_int, V, V, V, C.POINTER(MatcherOpts), C.c_double, V, V, C.c_int]
     L.svob200_update_seed.argtypes = [V, C.c_int, V, V, V]
     L.svob200_compute_tau.argtypes = [V, C.c_int, V, V, V, C.c_double, V]
+    L.svob200_debug_chi2_chain.argtypes = [V, C.c_int, C.c_int, V, V, V, V, V]
     L.svob200_features_prepare.argtypes = [V, C.POINTER(Camera), C.c_int, V, V, V, C.c_int, V, V, V, C.c_int]
     L.svob200_compose_poses.argtypes = [V, C.c_int, V, V, V, C.c_int]
     L.svob200_reproject_prepare.argtypes = [V, C.POINTER(Camera), C.c_int, V, V, V, C.c_int, V, V, V, C.c_int]
@@ -167,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "svob200_tracker_enable_profiling", "svob200_tracker_stage_ms", "svob200_tracker_get_seed_obs",
     "svob200_tracker_num_stages", "svob200_tracker_stage_name",
     "svob200_frame_upload_level", "svob200_shi_tomasi", "svob200_warp_matrix_affine", "svob200_warp_affine",
-    "svob200_depth_from_triangulation",
+    "svob200_depth_from_triangulation", "svob200_debug_chi2_chain",
     "svob200_frame_upload_yuv420", "svob200_reproject_map", "svob200_pose_opt_opts_default", "svob200_pose_optimize",
     "svob200_points_optimize", "svob200_seeds_initialize", "svob200_tracker_debug_align", "svob200_tracker_set_chain",
 ]
@@ -421,6 +422,16 @@ class Context:
         seeds = np.ascontiguousarray(seeds, dtype=seed_dt).copy()
         self._ck(self.L.svob200_update_seed(self.h, len(x), _ptr(x), _ptr(tau2), _ptr(seeds)))
         return seeds
+
+    def debug_chi2_chain(self, res, visible, contrib, block=256):
+        """Both device replays of the reference's sequential float chi2 chain: ((serial, count), (parallel, count))."""
+        res = np.ascontiguousarray(res, dtype=np.float32).reshape(-1, 16)
+        vis = np.ascontiguousarray(visible, dtype=np.uint8)
+        con = np.ascontiguousarray(contrib, dtype=np.uint8)
+        sums = np.zeros(2, np.float32)
+        cnts = np.zeros(2, np.int32)
+        self._ck(self.L.svob200_debug_chi2_chain(self.h, int(block), len(res), _ptr(res), _ptr(vis), _ptr(con), _ptr(sums), _ptr(cnts)))
+        return (sums[0], int(cnts[0])), (sums[1], int(cnts[1]))
 
     def compute_tau(self, T_ref_cur, f, z, ang):
         T = np.ascontiguousarray(T_ref_cur, dtype=np.float64)

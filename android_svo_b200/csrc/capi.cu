@@ -509,6 +509,26 @@ int svob200_update_seed(svob200_ctx* ctx, int n, const float* x, const float* ta
   return st.download();
 }
 
+int svob200_debug_chi2_chain(svob200_ctx* ctx, int block, int n_features, const float* res, const uint8_t* visible, const uint8_t* contrib,
+                             float* sums, int* counts)
+{
+  if (!ctx || n_features <= 0 || !res || !visible || !contrib || !sums || !counts) return fail(ctx, SVOB200_ERR_ARG, "debug_chi2_chain: bad arguments");
+  if (block != 128 && block != 256 && block != 512) return fail(ctx, SVOB200_ERR_ARG, "debug_chi2_chain: block must be 128, 256 or 512");
+  Stage st(ctx, SVOB200_MEM_HOST);
+  const int i_r = st.add(res, nullptr, sizeof(float) * 16 * (size_t)n_features, 0);
+  const int i_v = st.add(visible, nullptr, (size_t)n_features, 0);
+  const int i_c = st.add(contrib, nullptr, (size_t)n_features, 0);
+  const int i_s = st.add(nullptr, sums, sizeof(float) * 2, 2);
+  const int i_n = st.add(nullptr, counts, sizeof(int) * 2, 2);
+  if (int e = st.layout()) return e;
+  st.upload();
+  if (int e = st.push()) return e;
+  if (launch_chi2_chain_test(block, st.dev<float>(i_r), st.dev<uint8_t>(i_v), st.dev<uint8_t>(i_c), n_features, st.dev<float>(i_s), st.dev<int>(i_n),
+                             ctx->stream, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "debug_chi2_chain launch failed");
+  return st.download();
+}
+
 int svob200_compute_tau(svob200_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z, double px_error_angle, double* tau_out)
 {
   if (!ctx || n < 0 || !T_ref_cur || !f || !z || !tau_out) return fail(ctx, SVOB200_ERR_ARG, "compute_tau: bad arguments");

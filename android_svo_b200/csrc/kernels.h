@@ -32,6 +32,9 @@ int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& 
                         const double* d_T_init, svob200_align_opts opts, svob200_align_result* d_results,
                         void* d_scratch, cudaStream_t s, long long* launches);
 
+int launch_chi2_chain_test(int block, const float* d_res, const uint8_t* d_visible, const uint8_t* d_contrib, int n, float* d_sums, int* d_cnts,
+                           cudaStream_t s, long long* launches);
+
 // matcher.cu
 size_t lk_jobs_bytes(int n);                 // scratch of launch_align_patches / launch_match_direct
 int launch_align_patches(const DevFrame* d_frames, int slot, int level, int n, const int* d_image, const uint8_t* d_pwb, const uint8_t* d_patch,

