@@ -424,14 +424,14 @@ class Context:
         return seeds
 
     def debug_chi2_chain(self, res, visible, contrib, block=256):
-        """Both device replays of the reference's sequential float chi2 chain: ((serial, count), (parallel, count))."""
+        """The device replays of the reference's sequential float chi2 chain: [(sum, count)] for serial, parallel (latency mode), parallel (batch mode)."""
         res = np.ascontiguousarray(res, dtype=np.float32).reshape(-1, 16)
         vis = np.ascontiguousarray(visible, dtype=np.uint8)
         con = np.ascontiguousarray(contrib, dtype=np.uint8)
-        sums = np.zeros(2, np.float32)
-        cnts = np.zeros(2, np.int32)
+        sums = np.zeros(3, np.float32)
+        cnts = np.zeros(3, np.int32)
         self._ck(self.L.svob200_debug_chi2_chain(self.h, int(block), len(res), _ptr(res), _ptr(vis), _ptr(con), _ptr(sums), _ptr(cnts)))
-        return (sums[0], int(cnts[0])), (sums[1], int(cnts[1]))
+        return [(sums[i], int(cnts[i])) for i in range(3)]
 
     def compute_tau(self, T_ref_cur, f, z, ang):
         T = np.ascontiguousarray(T_ref_cur, dtype=np.float64)

@@ -96,112 +96,149 @@ __device__ void exact_chi2_chain_block(const float* res, const uint8_t* visible,
 // The same chain, EXACT and parallel.  Inside one binade [2^e, 2^(e+1)) the running sum is M*q with q = 2^(e-23) and M an
 // integer in [2^23, 2^24), and a round-to-nearest addition of t >= 0 is M += round_half_even(t/q) as long as the result
 // stays below 2^24: every term then contributes an integer that does not depend on M — except exact ties (fraction 1/2,
-// ~2^-14 of the terms), which look at the parity of M, and the term that crosses into the next binade, which rounds with the
-// doubled quantum.  So: stage a chunk of 2,048 squared residuals, convert each to its integer contribution in parallel, take
-// a block-wide prefix sum, find the first "special" term (tie or crossing) with a block-wide minimum, jump the sum to just
-// before it (exactly: an integer below 2^24 times q), apply that one term with a real float addition, and repeat from the
-// term after it with the new binade.  The first chunk, where the sum climbs through many binades, is added sequentially.
-// Bit-identical to the sequential chain (tests/test_gpu_parity.py::test_exact_chi2_chain_parallel_property drives it with
-// adversarial data: ties, binade crossings, zeros, huge terms); ~10 us instead of ~37 us for a 1,000-feature frame.
-template <int NT>
-__device__ void exact_chi2_chain_parallel(const float* res, const uint8_t* visible, const uint8_t* contrib, int N, float* s_sq, uint8_t* s_fl,
-                                          double* s_wsum /*NT/32*/, float* s_val /*1*/, int* s_min /*1*/, float* out_sum, int* out_cnt, int tid)
+// probability 2^-d for a term d binades below the sum), which look at the parity of M, and the term that crosses into the
+// next binade, which rounds with the doubled quantum.  So: stage a chunk of 2,048 squared residuals (the next chunk's loads
+// are already in flight), convert each to its integer contribution in parallel (t/q is an exact float: floorf and the
+// fraction are exact too; all of this is FP32 / INT32), take a block-wide prefix sum, find the first "special" term (tie or
+// crossing) together with the integer sum just before it in ONE 64-bit shared-memory minimum, jump the sum there (an integer
+// below 2^24 times q: exact), apply that one term with a real float addition, and repeat from the term after it in the new
+// binade.  Two block barriers per round, one per chunk.  The first HEAD terms, where the sum is a few terms large and
+// every other addition is a tie or a crossing, are added by one thread: 256 in the latency-mode (cluster) kernels; the whole
+// first chunk in the batch kernels, where a round costs the SM ~1,000 warp instructions that its other resident CTAs could
+// use and one thread adding costs 1 per term (measured: 4,096 C2 problems 0.80 ms with the sequential head, 0.85 ms with the
+// short one).  NBUF = 2 double-buffers the staged squares (one barrier less per chunk).  Bit-identical to the sequential chain
+// (tests/test_gpu_parity.py::test_exact_chi2_chain_parallel_property drives it with adversarial data: ties, binade
+// crossings, zeros, huge and non-finite terms, sums that stay tiny).
+constexpr int CHAIN_TERMS = CHAIN_F * 16;
+constexpr int CHAIN_HEAD_LATENCY = 256;   // terms added sequentially at the start of the chain (latency mode)
+constexpr int CHAIN_MAX_ROUNDS = 40;      // per chunk; a chunk that needs more (adversarial data) is finished sequentially
+template <int NBUF>
+struct ChainSmem {
+  __align__(16) float sq[NBUF][CHAIN_TERMS]; // squares of the staged chunk
+  uint8_t fl[CHAIN_F];                    // (the sequential replay's feature flags)
+  int wsum[2][16];                        // per-warp totals (double-buffered across rounds)
+  unsigned long long key[2];              // min over (first special term << 32 | integer sum before it)
+  float val;
+  int cnt;
+};
+
+template <int NT, int HEAD, int NBUF>
+__device__ void exact_chi2_chain_parallel(const float* res, const uint8_t* visible, const uint8_t* contrib, int N, ChainSmem<NBUF>* S,
+                                          float* out_sum, int* out_cnt, int tid)
 {
-  constexpr int TERMS = CHAIN_F * 16;
-  constexpr int TPT = TERMS / NT;                  // consecutive terms per thread
+  constexpr int TPT = CHAIN_TERMS / NT;            // consecutive terms per thread
+  constexpr int F4 = CHAIN_F * 4 / NT;             // float4 loads per thread and chunk
+  constexpr int SAT = 1 << 25;                     // prefix sums saturate here (anything >= 2^24 only says "crossed")
   const int lane = tid & 31, warp = tid >> 5;
   float s = 0.0f;                                  // uniform over the block
   int cnt = 0;
-  for (int c0 = 0; c0 < N; c0 += CHAIN_F) {
+  int par = 0;                                     // round parity (wsum / key buffers)
+  float4 pre[F4];
+  bool pre_on[F4];
+  auto fetch = [&](int c0) {
     const int m = min(CHAIN_F, N - c0);
-    for (int k = tid; k < CHAIN_F; k += NT) {
-      const int fl = (k < m && __ldcg(visible + c0 + k) && __ldcg(contrib + c0 + k)) ? 1 : 0;
-      s_fl[k] = (uint8_t)fl;
-      cnt += 16 * fl;
-    }
-    __syncthreads();
     const float4* src = reinterpret_cast<const float4*>(res + 16 * (size_t)c0);
-    for (int k = tid; k < CHAIN_F * 4; k += NT) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // a feature that does not contribute adds +0: the sum is unchanged
-      if (s_fl[k >> 2]) { const float4 a = __ldcg(src + k); v = make_float4(a.x * a.x * 1.0f, a.y * a.y * 1.0f, a.z * a.z * 1.0f, a.w * a.w * 1.0f); }
-      reinterpret_cast<float4*>(s_sq)[k] = v;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      const int k = tid + j * NT, f = k >> 2;
+      pre_on[j] = f < m && __ldcg(visible + c0 + f) && __ldcg(contrib + c0 + f);
+      pre[j] = f < m ? __ldcg(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  int buf = 0;
+  for (int c0 = 0; c0 < N; c0 += CHAIN_F, buf ^= NBUF - 1) {
+    float* sq = S->sq[buf];
+    if (NBUF == 1 && c0 > 0) __syncthreads();     // the previous chunk's last reads
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      // a feature that does not contribute adds +0: the sum is unchanged
+      const float4 a = pre[j];
+      reinterpret_cast<float4*>(sq)[tid + j * NT] = pre_on[j] ? make_float4(a.x * a.x * 1.0f, a.y * a.y * 1.0f, a.z * a.z * 1.0f, a.w * a.w * 1.0f)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      cnt += pre_on[j] ? 4 : 0;
     }
     __syncthreads();
-    int pos = 0;
-    int rounds = 0;
-    while (pos < TERMS) {
+    if (c0 + CHAIN_F < N) fetch(c0 + CHAIN_F);     // in flight during this chunk's rounds
+    const int mterms = 16 * min(CHAIN_F, N - c0);  // terms past this are zero
+    int pos = 0, rounds = 0;
+    bool seq = c0 == 0;                            // the head of the chain
+    int seq_end = min(HEAD, mterms);
+    while (pos < mterms) {
       const int E = (__float_as_int(s) >> 23) & 255;
-      if (c0 == 0 || E < 32 || E > 250 || ++rounds > 12) {
-        // sequential: the first chunk, a (still) tiny / non-finite sum, or a pathological chunk
-        if (tid == 0) { float a = s; for (int k = pos; k < TERMS; ++k) a += s_sq[k]; *s_val = a; }
+      if (!seq && (E < 32 || E > 250 || ++rounds > CHAIN_MAX_ROUNDS)) { seq = true; seq_end = mterms; }   // tiny / non-finite sum, pathological chunk
+      if (seq) {
+        if (tid == 0) { float a = s; for (int k = pos; k < seq_end; ++k) a += sq[k]; S->val = a; }
         __syncthreads();
-        s = *s_val;
+        s = S->val;
         __syncthreads();
-        break;
+        pos = seq_end; seq = false;
+        continue;
       }
-      const double inv_q = __hiloint2double((1173 - E) << 20, 0);      // 2^(150 - E)
-      const double q = __hiloint2double((873 + E) << 20, 0);           // 2^(E - 150) = ulp(s)
-      const double M0 = (double)s * inv_q;                              // integer in [2^23, 2^24)
-      double c[TPT];
+      const float inv_q = __int_as_float((277 - E) << 23);             // 2^(150 - E)
+      const float q = __int_as_float((E - 23) << 23);                   // 2^(E - 150) = ulp(s)
+      const int M0 = (int)(s * inv_q);                                  // integer in [2^23, 2^24)
+      int c[TPT];
       unsigned tie_mask = 0;
-      double mine = 0.0;
+      int mine = 0;
 #pragma unroll
-      for (int j = 0; j < TPT; ++j) {
-        const int k = tid * TPT + j;
-        double cj = 0.0;
-        if (k >= pos) {
-          const double r = (double)s_sq[k] * inv_q;
-          const double a = floor(r), f = r - a;
-          cj = a + (f > 0.5 ? 1.0 : 0.0);
-          if (f == 0.5) tie_mask |= 1u << j;
+      for (int j4 = 0; j4 < TPT / 4; ++j4) {
+        const float4 t4 = reinterpret_cast<const float4*>(sq)[tid * (TPT / 4) + j4];
+        const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * j4 + i, k = tid * TPT + j;
+          const float r = t[i] * inv_q;                                  // exact (power of two), or inf / NaN / below 2^-126
+          const float a = floorf(r), f = r - a;                          // exact
+          int cj = (int)a + (f > 0.5f ? 1 : 0);
+          if (!(r < 16777216.0f)) cj = 1 << 24;                          // crosses for sure (also inf / NaN)
+          if (k < pos) cj = 0;
+          else if (f == 0.5f) tie_mask |= 1u << j;
+          c[j] = cj;
+          mine += cj;
         }
-        c[j] = cj;
-        mine += cj;
       }
-      // block-wide exclusive prefix of the per-thread sums (exact: integers far below 2^53)
-      double incl = mine;
+      mine = min(mine, SAT);
+      // block-wide exclusive prefix of the per-thread sums (exact below 2^24, saturating above)
+      int incl = mine;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (lane == 31) s_wsum[warp] = incl;
-      if (tid == 0) *s_min = TERMS;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = min(incl + v, SAT); }
+      if (lane == 31) S->wsum[par][warp] = incl;
+      if (tid == 0) S->key[par] = ~0ull;
       __syncthreads();
-      double base = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive (not incl - mine: a huge or infinite term would poison it)
-      if (lane == 0) base = 0.0;
-      for (int w = 0; w < warp; ++w) base += s_wsum[w];
-      // first special term of this thread: a tie, or the first term whose inclusive prefix reaches 2^24
-      int kspec = TERMS;
-      double run = base;
+      int base = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) base = 0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) base += w < warp ? S->wsum[par][w] : 0;
+      base = min(base, SAT);
+      // first special term of this thread (a tie, or the first term whose inclusive prefix reaches 2^24) and the sum before it
+      int kspec = CHAIN_TERMS, before = 0;
+      int run = base;
 #pragma unroll
       for (int j = 0; j < TPT; ++j) {
+        const int prev = run;
         run += c[j];
-        const int k = tid * TPT + j;
-        if (kspec == TERMS && k >= pos && (((tie_mask >> j) & 1u) || M0 + run >= 16777216.0)) kspec = k;
+        if (kspec == CHAIN_TERMS && (((tie_mask >> j) & 1u) || M0 + run >= (1 << 24))) { kspec = tid * TPT + j; before = prev; }
       }
-      if (kspec < TERMS) atomicMin(s_min, kspec);
+      if (kspec < CHAIN_TERMS) atomicMin(&S->key[par], ((unsigned long long)kspec << 32) | (unsigned)(M0 + before));
+      else if (tid == NT - 1) atomicMin(&S->key[par], ((unsigned long long)CHAIN_TERMS << 32) | (unsigned)(M0 + run));   // no special at all: the total
       __syncthreads();
-      const int ks = *s_min;                        // first special term of the block (TERMS: none)
-      // the sum just before it: prefix up to term ks - 1 (the thread that owns that term writes it)
-      const int klast = ks - 1;
-      if (klast >= pos && klast / TPT == tid) {
-        double upto = base;
-#pragma unroll
-        for (int j = 0; j < TPT; ++j) if (tid * TPT + j <= klast) upto += c[j];
-        *s_val = (float)((M0 + upto) * q);
-      }
-      __syncthreads();
-      if (klast >= pos) s = *s_val;
-      if (ks < TERMS) s = s + s_sq[ks];             // the special term: one real float addition (every thread, same value)
+      const unsigned long long key = S->key[par];
+      const int ks = (int)(key >> 32);             // first special term of the block (CHAIN_TERMS: none)
+      s = (float)(int)(unsigned)key * q;            // the sum just before it: an integer below 2^24 times q, exact
+      if (ks < CHAIN_TERMS) s = s + sq[ks];         // the special term: one real float addition (every thread, same value)
       pos = ks + 1;
-      __syncthreads();
+      par ^= 1;
     }
   }
   // the count of contributing pixels
   cnt = warp_sum_i(cnt);
-  if (tid == 0) *s_min = 0;
   __syncthreads();
-  if (lane == 0 && cnt) atomicAdd(s_min, cnt);
+  if (tid == 0) S->cnt = 0;
   __syncthreads();
-  if (tid == 0) { *out_sum = s; *out_cnt = *s_min; }
+  if (lane == 0 && cnt) atomicAdd(&S->cnt, cnt);
+  __syncthreads();
+  if (tid == 0) { *out_sum = s; *out_cnt = S->cnt; }
   __syncthreads();
 }
 
@@ -252,11 +289,9 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   __shared__ int s_need;          // exact chi2 replay wanted: bit 0 this evaluation, bit 1 the previous one as well
   __shared__ float s_chain[2];
   __shared__ int s_chain_n[2];
-  __shared__ __align__(16) float s_sq[CHAIN_F * 16];
-  __shared__ uint8_t s_fl[CHAIN_F];
-  __shared__ double s_wsum[BLOCK / 32];
-  __shared__ float s_cval;
-  __shared__ int s_cmin;
+  constexpr int CHAIN_HEAD = CLUSTER > 1 ? CHAIN_HEAD_LATENCY : CHAIN_TERMS;
+  constexpr int CHAIN_NBUF = (CLUSTER == 1 && BLOCK == 128) ? 1 : 2;       // <= 128 features per problem there: one chunk
+  __shared__ ChainSmem<CHAIN_NBUF> s_chainmem;
 
   const int b = CLUSTER > 1 ? blockIdx.x / CLUSTER : blockIdx.x;
   const int rank = CLUSTER > 1 ? (int)(blockIdx.x % CLUSTER) : 0;
@@ -526,12 +561,12 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         __syncthreads();
         const int need = s_need;
 #ifdef ALIGN_CHAIN_SERIAL   // A/B builds: one thread adds the staged squares in order
-        if (need & 1) exact_chi2_chain_block(res, visible, contrib, N, s_sq, s_fl, &s_chain[0], &s_chain_n[0], tid, BLOCK);
-        if (need & 2) exact_chi2_chain_block(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_sq, s_fl, &s_chain[1], &s_chain_n[1], tid, BLOCK);
+        if (need & 1) exact_chi2_chain_block(res, visible, contrib, N, s_chainmem.sq[0], s_chainmem.fl, &s_chain[0], &s_chain_n[0], tid, BLOCK);
+        if (need & 2) exact_chi2_chain_block(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_chainmem.sq[0], s_chainmem.fl, &s_chain[1], &s_chain_n[1], tid, BLOCK);
 #else
-        if (need & 1) exact_chi2_chain_parallel<BLOCK>(res, visible, contrib, N, s_sq, s_fl, s_wsum, &s_cval, &s_cmin, &s_chain[0], &s_chain_n[0], tid);
+        if (need & 1) exact_chi2_chain_parallel<BLOCK, CHAIN_HEAD, CHAIN_NBUF>(res, visible, contrib, N, &s_chainmem, &s_chain[0], &s_chain_n[0], tid);
         // the previous evaluation lives in the other ping-pong buffer
-        if (need & 2) exact_chi2_chain_parallel<BLOCK>(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, s_sq, s_fl, s_wsum, &s_cval, &s_cmin, &s_chain[1], &s_chain_n[1], tid);
+        if (need & 2) exact_chi2_chain_parallel<BLOCK, CHAIN_HEAD, CHAIN_NBUF>(A.res[pp ^ 1] + 16 * (size_t)f0, visible, A.contrib[pp ^ 1] + f0, N, &s_chainmem, &s_chain[1], &s_chain_n[1], tid);
 #endif
         if (need) __syncthreads();
       }
@@ -604,19 +639,18 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   }
 }
 
-// diagnostics (svob200_debug_chi2_chain): both replays of the float chi2 chain over caller-supplied residuals, one CTA
+// diagnostics (svob200_debug_chi2_chain): the replays of the float chi2 chain over caller-supplied residuals, one CTA:
+// [0] one thread adding, [1] the parallel replay as the latency-mode kernels run it, [2] as the batch kernels run it
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) chi2_chain_test_kernel(const float* res, const uint8_t* visible, const uint8_t* contrib, int N, float* sums, int* cnts)
 {
-  __shared__ __align__(16) float s_sq[CHAIN_F * 16];
-  __shared__ uint8_t s_fl[CHAIN_F];
-  __shared__ double s_wsum[BLOCK / 32];
-  __shared__ float s_cval;
-  __shared__ int s_cmin;
+  __shared__ ChainSmem<2> s_chainmem;
   const int tid = threadIdx.x;
-  exact_chi2_chain_block(res, visible, contrib, N, s_sq, s_fl, sums + 0, cnts + 0, tid, BLOCK);
+  exact_chi2_chain_block(res, visible, contrib, N, s_chainmem.sq[0], s_chainmem.fl, sums + 0, cnts + 0, tid, BLOCK);
   __syncthreads();
-  exact_chi2_chain_parallel<BLOCK>(res, visible, contrib, N, s_sq, s_fl, s_wsum, &s_cval, &s_cmin, sums + 1, cnts + 1, tid);
+  exact_chi2_chain_parallel<BLOCK, CHAIN_HEAD_LATENCY, 2>(res, visible, contrib, N, &s_chainmem, sums + 1, cnts + 1, tid);
+  __syncthreads();
+  exact_chi2_chain_parallel<BLOCK, CHAIN_TERMS, 1>(res, visible, contrib, N, reinterpret_cast<ChainSmem<1>*>(&s_chainmem), sums + 2, cnts + 2, tid);
 }
 
 }  // namespace

@@ -219,9 +219,10 @@ int svob200_seeds_update(svob200_ctx* ctx, int64_t cur_frame_id, const svob200_c
 int svob200_update_seed(svob200_ctx* ctx, int n, const float* x, const float* tau2, svob200_seed* seeds);
 /* diagnostics: sparse alignment decides NLLSSolver's rollback test `new_chi2 > chi2_` (nlls_solver_impl.hpp:56) on the reference's
  * sequentially accumulated `float chi2` (sparse_img_align.cpp:259-263) when the double sums are too close to call.  This entry
- * runs both device replays of that chain over caller-supplied residuals (16 per feature, host memory) with a CTA of `block`
- * threads (128, 256 or 512): sums[0]/counts[0] = one thread adding in order, sums[1]/counts[1] = the parallel exact replay the
- * alignment kernel uses.  The two must be bit-identical for any input. */
+ * runs the device replays of that chain over caller-supplied residuals (16 per feature, host memory) with a CTA of `block`
+ * threads (128, 256 or 512): sums[0]/counts[0] = one thread adding in order, [1] = the parallel exact replay as the
+ * latency-mode (cluster) alignment kernels run it, [2] = as the batch kernels run it.  sums and counts hold 3 entries; all
+ * three must be bit-identical for any input. */
 int svob200_debug_chi2_chain(svob200_ctx* ctx, int block, int n_features, const float* res, const uint8_t* visible,
                              const uint8_t* contrib, float* sums, int* counts);
 int svob200_compute_tau(svob200_ctx* ctx, int n, const double* T_ref_cur, const double* f, const double* z,

@@ -554,8 +554,7 @@ def _chain_reference(res, visible, contrib):
 def test_exact_chi2_chain_parallel_property(ctx, block):
     for name, res, vis, con in _chain_cases():
         want, want_n = _chain_reference(res, vis, con)
-        (ser, ser_n), (par, par_n) = ctx.debug_chi2_chain(res, vis, con, block=block)
-        assert ser_n == want_n and par_n == want_n, (name, ser_n, par_n, want_n)
         bits = lambda v: int(np.float32(v).view(np.uint32))
-        assert bits(ser) == bits(want), "%s: serial device chain %r != reference %r" % (name, ser, want)
-        assert bits(par) == bits(want), "%s: parallel chain %r (%08x) != sequential %r (%08x)" % (name, par, bits(par), want, bits(want))
+        for which, (got, got_n) in zip(("serial", "parallel/latency", "parallel/batch"), ctx.debug_chi2_chain(res, vis, con, block=block)):
+            assert got_n == want_n, (name, which, got_n, want_n)
+            assert bits(got) == bits(want), "%s: %s device chain %r (%08x) != reference %r (%08x)" % (name, which, got, bits(got), want, bits(want))
