@@ -150,6 +150,12 @@ struct svob200_tracker {
   struct StepGraph { std::vector<uintptr_t> key; cudaGraphExec_t exec; long long launches; };
   std::vector<StepGraph> graphs;
   int graph_max_batch = 64;
+  // inside a captured step the independent stages fork onto a second stream (see run_range): the graph then has parallel
+  // branches and its critical path is 8 kernels instead of 14
+  cudaStream_t fork_stream = nullptr;
+  cudaEvent_t fork_ev[4] = {};
+  bool forking = false;
+  int graph_fork = 1;
   // optional per-stage CUDA-event timing (bench.py's stage breakdown / roofline)
   bool profiling = false;
   cudaEvent_t ev[kNumStages + 1] = {};
@@ -201,6 +207,7 @@ int svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batc
   // Seed ctor depth_filter.cpp:36-45
   t->seed_init.a = 10; t->seed_init.b = 10; t->seed_init.mu = (float)(1.0 / depth_mean); t->seed_init.z_range = (float)(1.0 / depth_min);
   t->seed_init.sigma2 = t->seed_init.z_range * t->seed_init.z_range / 36;
+  if (const char* e = getenv("SVOB200_TRACKER_FORK")) t->graph_fork = atoi(e) != 0;   // 0: captured steps stay one chain of kernels (A/B runs)
   if (const char* e = getenv("SVOB200_TRACKER_GRAPH")) t->graph_max_batch = atoi(e) > 0 ? atoi(e) : 0;   // 0 disables graph replay; N = largest batch replayed as a graph
   ++uid;
   t->fid_kf = -(uid * 4 + 1); t->fid_last = -(uid * 4 + 2); t->fid_cur = -(uid * 4 + 3);
@@ -221,6 +228,8 @@ void svob200_tracker_destroy(svob200_tracker* t)
   for (auto e : t->chunk_ev) cudaEventDestroy(e);
   for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  if (t->fork_stream) cudaStreamDestroy(t->fork_stream);
+  for (auto e : t->fork_ev) if (e) cudaEventDestroy(e);
   for (int k = 0; k <= kNumStages; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   delete t;
 }
@@ -375,6 +384,12 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   const int s0 = t->h_seed_off[c0], ns = t->h_seed_off[c1] - s0;
   const DevFrame vlast = frame_view(last->f, c0, cnt), vcur = frame_view(cur->f, c0, cnt);
 #define MARK(k) do { if (marks && t->profiling) cudaEventRecord(t->ev[k], s); } while (0)
+  // Captured steps (single-stream latency) fork: the per-feature preparation does not read the new pyramid, and the depth
+  // filter and the map-point matching both depend on the aligned pose only (default mode), so each pair runs as parallel
+  // branches of the graph; s2 == s everywhere else.
+  const bool fork = t->forking;
+  cudaStream_t s2 = fork ? t->fork_stream : s;
+  if (fork) { CU(cudaEventRecord(t->fork_ev[0], s)); CU(cudaStreamWaitEvent(s2, t->fork_ev[0], 0)); }
   // 1. fused pyramid of the current frames
   {
     int modes[SVOB200_MAX_LEVELS];
@@ -384,8 +399,9 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   MARK(1);
   // 2. Feature ctor / xyz_ref of the last frame's features, initial relative pose
   if (launch_features_prepare(cam, nf, d_last_px + 2 * (size_t)f0, t->d_pt_world + 3 * (size_t)f0, t->d_ftr_image + f0, d_T_last, nullptr,
-                              t->d_xyz + 3 * (size_t)f0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: features_prepare failed");
-  init_pose_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, d_T_last + 7 * (size_t)c0, t->d_T_init + 7 * (size_t)c0); ++ctx->launches;
+                              t->d_xyz + 3 * (size_t)f0, s2, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: features_prepare failed");
+  init_pose_kernel<<<(cnt + 127) / 128, 128, 0, s2>>>(cnt, d_T_last + 7 * (size_t)c0, t->d_T_init + 7 * (size_t)c0); ++ctx->launches;
+  if (fork) { CU(cudaEventRecord(t->fork_ev[1], s2)); CU(cudaStreamWaitEvent(s, t->fork_ev[1], 0)); }
   MARK(2);
   // 3. SparseImgAlign::run(last, cur)
   if (launch_sparse_align(vlast, vcur, cam, cnt, t->N, t->max_per, t->d_ftr_off + c0, d_last_px, t->d_xyz, t->d_has_point,
@@ -394,6 +410,9 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   MARK(3);
   // 4. cur.T_f_w = T_cur_from_ref * last.T_f_w ; reprojection of the map points
   if (launch_compose_poses(cnt, t->d_align + c0, d_T_last + 7 * (size_t)c0, t->d_T_cur + 7 * (size_t)c0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: compose failed");
+  // chain mode: the depth filter waits for the pose optimiser's T_cur, so its branch cannot start here
+  cudaStream_t s_seeds = (fork && t->chain_cell <= 0) ? s2 : s;
+  if (s_seeds != s) { CU(cudaEventRecord(t->fork_ev[2], s)); CU(cudaStreamWaitEvent(s_seeds, t->fork_ev[2], 0)); }
   if (launch_reproject_prepare(cam, nf, t->d_ftrs + f0, t->d_pt_world + 3 * (size_t)f0, t->d_T_kf_ftr + 7 * (size_t)f0, t->d_T_cur,
                                t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
   MARK(4);
@@ -429,9 +448,10 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   }
   // 6. DepthFilter::updateSeeds(cur)
   if (launch_seeds_update(ctx->d_table, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
-                          t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s, &ctx->launches,
+                          t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s_seeds, &ctx->launches,
                           (marks && t->profiling) ? &t->ev[8] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
+  if (s_seeds != s) { CU(cudaEventRecord(t->fork_ev[3], s_seeds)); CU(cudaStreamWaitEvent(s, t->fork_ev[3], 0)); }
   MARK(11);
   // 7. per-sequence statistics (+ steady-state re-seeding)
   step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
@@ -465,8 +485,15 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     const std::vector<uintptr_t> key = {1, (uintptr_t)cur_imgs, (uintptr_t)stride, (uintptr_t)T_last_w, (uintptr_t)last_px, (uintptr_t)stats,
                                         (uintptr_t)px_refined, (uintptr_t)match_ok, (uintptr_t)t->fid_cur, (uintptr_t)t->fid_last,
                                         (uintptr_t)last->f.lvl[0], (uintptr_t)last->f.pitch[0]};
+    if (use_graph && t->graph_fork && !t->fork_stream) {
+      CU(cudaStreamCreateWithFlags(&t->fork_stream, cudaStreamNonBlocking));
+      for (auto& e : t->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     const int rc = graph_or_direct(t, use_graph, key, [&]() -> int {
-      if (int e = run_range(t, 0, B, T_last_w, last_px, true)) return e;
+      t->forking = use_graph && t->graph_fork;     // only a capture runs this body when use_graph is set
+      const int e0 = run_range(t, 0, B, T_last_w, last_px, true);
+      t->forking = false;
+      if (e0) return e0;
       if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
       if (px_refined) CU(cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s));
       if (match_ok) CU(cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s));
@@ -507,12 +534,30 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
                            r->f.w[0], (size_t)h * (c1 - c0), cudaMemcpyHostToDevice, t->copy_stream));
       CU(cudaEventRecord(t->chunk_ev[c], t->copy_stream));
     }
-    // (graph replay of the compute part was measured in host mode too: 0.202 -> 0.199 ms for C2 — the host path is bound by
-    //  the copies and the synchronisation, so it keeps plain launches)
+    // small batches: the kernels of the step (not the copies: the caller's host pointers change from call to call) are
+    // replayed as the same forked graph as in device mode; the kernels only see the tracker's own buffers here, so two
+    // graphs (the frame pair swaps every step) serve every call.  (A graph WITHOUT the parallel branches gained nothing in
+    // host mode: 0.202 -> 0.199 ms for C2.)
+    const bool use_graph = !t->profiling && n_chunks == 1 && B <= t->graph_max_batch && t->graph_max_batch > 0 && t->graph_fork;
+    if (use_graph && !t->fork_stream) {
+      CU(cudaStreamCreateWithFlags(&t->fork_stream, cudaStreamNonBlocking));
+      for (auto& e : t->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     for (int c = 0; c < n_chunks; ++c) {
       const int c0 = c * chunk, c1 = std::min(B, c0 + chunk);
       CU(cudaStreamWaitEvent(s, t->chunk_ev[c], 0));
-      if (int e = run_range(t, c0, c1, d_T_last, d_last_px, n_chunks == 1)) return e;
+      if (use_graph) {
+        FrameRec* last = find_frame(ctx, t->fid_last);
+        const std::vector<uintptr_t> key = {2, (uintptr_t)t->fid_cur, (uintptr_t)t->fid_last, (uintptr_t)r->f.lvl[0], (uintptr_t)r->f.pitch[0],
+                                            (uintptr_t)last->f.lvl[0], (uintptr_t)last->f.pitch[0], (uintptr_t)d_T_last};
+        const int rc = graph_or_direct(t, true, key, [&]() -> int {
+          t->forking = true;
+          const int e0 = run_range(t, 0, B, d_T_last, d_last_px, true);
+          t->forking = false;
+          return e0;
+        });
+        if (rc) return rc;
+      } else if (int e = run_range(t, c0, c1, d_T_last, d_last_px, n_chunks == 1)) return e;
     }
     uint8_t* ho = t->h_pinned + ((in_bytes + 255) & ~(size_t)255);
     uint8_t* h_stats = ho; uint8_t* h_px = h_stats + sizeof(svob200_step_stats) * B; uint8_t* h_ok = h_px + sizeof(double) * 2 * (size_t)N;
