@@ -30,7 +30,8 @@ size_t sparse_align_scratch_bytes(int total_features);
 int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
                         const int* d_offsets, const double* d_px, const double* d_xyz, const uint8_t* d_has_point,
                         const double* d_T_init, svob200_align_opts opts, svob200_align_result* d_results,
-                        void* d_scratch, cudaStream_t s, long long* launches);
+                        void* d_scratch, cudaStream_t s, long long* launches,
+                        const double* d_T_ref_w = nullptr, double* d_T_cur_w = nullptr);   // optional: T_cur_w = T_cur_ref * T_ref_w per problem
 
 int launch_chi2_chain_test(int block, const float* d_res, const uint8_t* d_visible, const uint8_t* d_contrib, int n, float* d_sums, int* d_cnts,
                            cudaStream_t s, long long* launches);

@@ -38,6 +38,8 @@ struct AlignArgs {
   const double* xyz;
   const uint8_t* has_point;
   const double* T_init;
+  const double* T_ref_w;   // optional (tracker): pose of the reference frames, 7 per problem ...
+  double* T_cur_w;         // ... and where T_cur_ref * T_ref_w goes (frame_handler_mono.cpp:186-188: cur.T_f_w_ = T_cur_from_ref * last.T_f_w_)
   svob200_align_opts opts;
   svob200_align_result* results;
   // scratch, indexed by global feature / feature-pixel
@@ -633,6 +635,14 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
     R->chi2 = chi2_;
     R->stop = stop_ ? 1 : 0;
     R->n_exact_chi2 = n_exact;
+    if (A.T_cur_w) {
+      double Tm[7], out[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) Tm[k] = s_model[k];
+      se3_mul(Tm, A.T_ref_w + 7 * (size_t)b, out);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) A.T_cur_w[7 * (size_t)b + k] = out[k];
+    }
 #ifdef ALIGN_TIMING
     R->H[0] = (double)tP; R->H[1] = (double)tA; R->H[2] = (double)tB; R->H[3] = (double)tC; R->H[4] = (double)tD; R->H[5] = (double)(clock64() - cstart);
 #endif
@@ -684,9 +694,10 @@ size_t sparse_align_scratch_bytes(int total_features)
 int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
                         const int* d_offsets, const double* d_px, const double* d_xyz, const uint8_t* d_has_point,
                         const double* d_T_init, svob200_align_opts opts, svob200_align_result* d_results,
-                        void* d_scratch, cudaStream_t s, long long* launches)
+                        void* d_scratch, cudaStream_t s, long long* launches, const double* d_T_ref_w, double* d_T_cur_w)
 {
   AlignArgs A{};
+  A.T_ref_w = d_T_ref_w; A.T_cur_w = d_T_cur_w;
   A.ref = ref; A.cur = cur; A.cam = cam; A.offsets = d_offsets; A.px = d_px; A.xyz = d_xyz; A.has_point = d_has_point;
   A.T_init = d_T_init; A.opts = opts; A.results = d_results;
   // carve the scratch in the order sparse_align_scratch_bytes() counts it (all sub-arrays stay 16-byte aligned)

@@ -144,14 +144,14 @@ struct svob200_tracker {
   double *d_m_f = nullptr, *d_m_pos = nullptr, *d_pose_work = nullptr;
   uint8_t* d_outlier = nullptr;
   void* d_reproj_scratch = nullptr;
-  // single-stream latency: in device mode with small batches the 14 launches of a step are replayed as ONE CUDA graph
+  // single-stream latency: in device mode with small batches the 13 launches of a step are replayed as ONE CUDA graph
   // (captured once per distinct set of buffer addresses: a camera ring buffer has only a few), which removes the
   // per-launch driver cost and most of the inter-kernel gaps
   struct StepGraph { std::vector<uintptr_t> key; cudaGraphExec_t exec; long long launches; };
   std::vector<StepGraph> graphs;
   int graph_max_batch = 64;
   // inside a captured step the independent stages fork onto a second stream (see run_range): the graph then has parallel
-  // branches and its critical path is 8 kernels instead of 14
+  // branches and its critical path is 7 kernels instead of 13
   cudaStream_t fork_stream = nullptr;
   cudaEvent_t fork_ev[4] = {};
   bool forking = false;
@@ -372,7 +372,10 @@ static DevFrame frame_view(const DevFrame& f, int c0, int cnt)
 }
 
 // all stages of one step for the sequences [c0, c1) on the compute stream (level 0 of cur is in place)
-static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last, const double* d_last_px, bool marks)
+// out_px / out_ok: optional device destinations of the refined pixels / match flags (device-mode callers): copied as soon as
+// the matching stage is done, beside the depth filter in a forked step
+static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last, const double* d_last_px, bool marks,
+                     double* out_px = nullptr, int* out_ok = nullptr)
 {
   svob200_ctx* ctx = t->ctx;
   cudaStream_t s = ctx->stream;
@@ -405,11 +408,11 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   MARK(2);
   // 3. SparseImgAlign::run(last, cur)
   if (launch_sparse_align(vlast, vcur, cam, cnt, t->N, t->max_per, t->d_ftr_off + c0, d_last_px, t->d_xyz, t->d_has_point,
-                          t->d_T_init + 7 * (size_t)c0, t->aopts, t->d_align + c0, t->d_align_scratch, s, &ctx->launches))
+                          t->d_T_init + 7 * (size_t)c0, t->aopts, t->d_align + c0, t->d_align_scratch, s, &ctx->launches,
+                          d_T_last + 7 * (size_t)c0, t->d_T_cur + 7 * (size_t)c0))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: sparse_align failed");
   MARK(3);
-  // 4. cur.T_f_w = T_cur_from_ref * last.T_f_w ; reprojection of the map points
-  if (launch_compose_poses(cnt, t->d_align + c0, d_T_last + 7 * (size_t)c0, t->d_T_cur + 7 * (size_t)c0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: compose failed");
+  // 4. cur.T_f_w = T_cur_from_ref * last.T_f_w (written by the alignment kernel's epilogue) ; reprojection of the map points
   // chain mode: the depth filter waits for the pose optimiser's T_cur, so its branch cannot start here
   cudaStream_t s_seeds = (fork && t->chain_cell <= 0) ? s2 : s;
   if (s_seeds != s) { CU(cudaEventRecord(t->fork_ev[2], s)); CU(cudaStreamWaitEvent(s_seeds, t->fork_ev[2], 0)); }
@@ -446,6 +449,8 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
   MARK(7);
   }
+  if (out_px) CU(cudaMemcpyAsync(out_px + 2 * (size_t)f0, t->d_px_out + 2 * (size_t)f0, sizeof(double) * 2 * (size_t)nf, cudaMemcpyDeviceToDevice, s));
+  if (out_ok) CU(cudaMemcpyAsync(out_ok + f0, t->d_match_ok + f0, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToDevice, s));
   // 6. DepthFilter::updateSeeds(cur)
   if (launch_seeds_update(ctx->d_table, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
                           t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s_seeds, &ctx->launches,
@@ -491,12 +496,10 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     }
     const int rc = graph_or_direct(t, use_graph, key, [&]() -> int {
       t->forking = use_graph && t->graph_fork;     // only a capture runs this body when use_graph is set
-      const int e0 = run_range(t, 0, B, T_last_w, last_px, true);
+      const int e0 = run_range(t, 0, B, T_last_w, last_px, true, px_refined, match_ok);
       t->forking = false;
       if (e0) return e0;
       if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
-      if (px_refined) CU(cudaMemcpyAsync(px_refined, t->d_px_out, sizeof(double) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, s));
-      if (match_ok) CU(cudaMemcpyAsync(match_ok, t->d_match_ok, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, s));
       return 0;
     });
     if (rc) return rc;
@@ -582,7 +585,7 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
   return SVOB200_OK;
 }
 
-int svob200_tracker_launches_per_step(void) { return 14; }
+int svob200_tracker_launches_per_step(void) { return 13; }
 
 // raw svob200_align_result records of the most recent step (diagnostics: tools/align_timing.py)
 int svob200_tracker_debug_align(svob200_tracker* t, svob200_align_result* out)
