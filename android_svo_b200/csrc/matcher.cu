@@ -542,48 +542,56 @@ __device__ __forceinline__ void emit_lk_job(LkJob* dst, const uint8_t* s_pwb, fl
 }
 
 // affine warp of the 10x10 reference patch (matcher.cpp:83-116) into shared memory by a group of 8 lanes
+// R taps per lane in flight together (tap i = sub + 8 r); (x, y) is the lane's running position in the row-major 10x10 patch
+template <int R>
+__device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, int rp, float xmax, float ymax, float a00, float a01, float a10, float a11,
+                                                float pr0, float pr1, float sc, uint8_t* s_pwb, int i0, int& x, int& y)
+{
+  bool inb[R];
+  float w00[R], w01[R], w10[R], w11[R];
+  uint8_t p00[R], p01[R], p10[R], p11[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + GL * r;
+    float p0 = (float)(x - 5), p1 = (float)(y - 5);
+    x += GL; if (x >= 10) { x -= 10; ++y; }
+    p0 *= sc; p1 *= sc;
+    const float qx = (a00 * p0 + a01 * p1) + pr0;
+    const float qy = (a10 * p0 + a11 * p1) + pr1;
+    inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    // vk::interpolateMat_8u (vision.h:19-36); floorf == truncation for the non-negative coordinates of an in-bounds tap
+    // (out-of-bounds taps produce 0 whatever ix, iy are)
+    const int ix = (int)qx, iy = (int)qy;
+    const float sx = qx - ix, sy = qy - iy;
+    w00[r] = (1.0f - sx) * (1.0f - sy);
+    w01[r] = (1.0f - sx) * sy;
+    w10[r] = sx * (1.0f - sy);
+    w11[r] = 1.0f - w00[r] - w01[r] - w10[r];
+    p00[r] = p01[r] = p10[r] = p11[r] = 0;
+    if (inb[r]) {
+      const uint8_t* p = rimg + (size_t)iy * rp + ix;
+      p00[r] = p[0]; p01[r] = p[rp]; p10[r] = p[1]; p11[r] = p[rp + 1];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + GL * r;
+    if (i < 100) s_pwb[i] = inb[r] ? (uint8_t)(w00[r] * p00[r] + w01[r] * p01[r] + w10[r] * p10[r] + w11[r] * p11[r]) : (uint8_t)0;
+  }
+}
+
 __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, int rc, int rr, float a00, float a01, float a10, float a11,
                                                  float pr0, float pr1, int L, uint8_t* s_pwb, int sub)
 {
-  // lane handles taps sub, sub+8, ... (< 100), four at a time so that the 16 pixel loads of a lane are in flight together
+  // 100 taps over 8 lanes = 12 full rounds + 4 taps: three passes of four rounds (the 16 pixel loads of a lane in flight
+  // together) and ONE tail round, not a fourth pass whose last three rounds would be all-idle instructions
   const float sc = (float)(1 << L);
   const float xmax = (float)(rc - 1), ymax = (float)(rr - 1);
-  // tap i = sub + 8 r walks the 10x10 patch row-major: (x, y) advance by 8 columns per round with a carry into the row
   int x = sub, y = 0;
 #pragma unroll 1
-  for (int r0 = 0; r0 < 13; r0 += 4) {
-    bool inb[4];
-    float w00[4], w01[4], w10[4], w11[4];
-    uint8_t p00[4], p01[4], p10[4], p11[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = sub + GL * (r0 + r);
-      float p0 = (float)(x - 5), p1 = (float)(y - 5);
-      x += GL; if (x >= 10) { x -= 10; ++y; }
-      p0 *= sc; p1 *= sc;
-      const float qx = (a00 * p0 + a01 * p1) + pr0;
-      const float qy = (a10 * p0 + a11 * p1) + pr1;
-      inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
-      // vk::interpolateMat_8u (vision.h:19-36); floorf == truncation for the non-negative coordinates of an in-bounds tap
-      // (out-of-bounds taps produce 0 whatever ix, iy are)
-      const int ix = (int)qx, iy = (int)qy;
-      const float sx = qx - ix, sy = qy - iy;
-      w00[r] = (1.0f - sx) * (1.0f - sy);
-      w01[r] = (1.0f - sx) * sy;
-      w10[r] = sx * (1.0f - sy);
-      w11[r] = 1.0f - w00[r] - w01[r] - w10[r];
-      p00[r] = p01[r] = p10[r] = p11[r] = 0;
-      if (inb[r]) {
-        const uint8_t* p = rimg + (size_t)iy * rp + ix;
-        p00[r] = p[0]; p01[r] = p[rp]; p10[r] = p[1]; p11[r] = p[rp + 1];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = sub + GL * (r0 + r);
-      if (i < 100) s_pwb[i] = inb[r] ? (uint8_t)(w00[r] * p00[r] + w01[r] * p01[r] + w10[r] * p10[r] + w11[r] * p11[r]) : (uint8_t)0;
-    }
-  }
+  for (int r0 = 0; r0 < 12; r0 += 4)
+    warp_patch_taps<4>(rimg, rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * r0, x, y);
+  warp_patch_taps<1>(rimg, rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * 12, x, y);
 }
 
 constexpr int JOB_BATCH = 8;             // LK job slots a group reserves per atomicAdd
