@@ -21,6 +21,7 @@
 // 64-long dependent FADD chain is ~256 cycles — cheaper than it sounds, and exact).  The epipolar
 // sample positions come from the reference's running sum `uv += step`, replayed by two threads
 // (x and y are independent chains).  Only libm calls (acos/sin/atan/exp) are tolerance-matched.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -111,6 +112,12 @@ __device__ __forceinline__ void inv3f(const float* m, float* r)
 // byte k of a register-resident byte array (k is a compile-time constant after unrolling)
 template <int NW> __device__ __forceinline__ int reg_byte(const uint32_t (&w)[NW], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu); }
 
+// byte k of a word as a float WITHOUT the conversion unit: PRMT builds the bit pattern of 2^23 + byte, one FADD removes the
+// 2^23 (both exact).  I2F.U8 / I2F.S16 run on the quarter-rate XU pipe, which was the most loaded pipe of the LK kernel
+// (~270 conversions per thread and iteration against ~1,000 FP32 operations).
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)) - 8388608.0f; }
+template <int NW> __device__ __forceinline__ float reg_byte_f(const uint32_t (&w)[NW], int k) { return byte_to_float(w[k >> 2], k & 3); }
+
 // nine consecutive pixels starting at p (any alignment) as floats; reads the three aligned words that hold them
 __device__ __forceinline__ void load_row9(const uint8_t* p, float (&o)[9])
 {
@@ -119,9 +126,9 @@ __device__ __forceinline__ void load_row9(const uint8_t* p, float (&o)[9])
   const unsigned sh = (unsigned)(a & 3) * 8;
   const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
   const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh), b8 = w2 >> sh;
-  o[0] = (float)(lo & 0xffu); o[1] = (float)((lo >> 8) & 0xffu); o[2] = (float)((lo >> 16) & 0xffu); o[3] = (float)(lo >> 24);
-  o[4] = (float)(hi & 0xffu); o[5] = (float)((hi >> 8) & 0xffu); o[6] = (float)((hi >> 16) & 0xffu); o[7] = (float)(hi >> 24);
-  o[8] = (float)(b8 & 0xffu);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { o[k] = byte_to_float(lo, k); o[4 + k] = byte_to_float(hi, k); }
+  o[8] = byte_to_float(b8, 0);
 }
 
 // align2D (feature_alignment.cpp:154-282).  w: template with border, rp: 8x8 reference patch, sd: this thread's
@@ -138,7 +145,9 @@ __device__ bool lk_align2d(const uint8_t* img, int pitch, int cols, int rows, co
       const int dxi = reg_byte(w, k + 1) - reg_byte(w, k - 1), dyi = reg_byte(w, k + 10) - reg_byte(w, k - 10);
       const float j0 = 0.5f * (float)dxi, j1 = 0.5f * (float)dyi;      // exact: 0.5 * int (the reference goes through double)
       h00 += j0 * j0; h01 += j0 * j1; h02 += j0; h11 += j1 * j1; h12 += j1;
-      sd[(y * 8 + x) * LK_T] = ((uint32_t)dxi & 0xffffu) | ((uint32_t)dyi << 16);
+      // staged as two halves: 0.5 * [-255, 255] is exact in binary16, and half -> float is a full-rate instruction
+      const __half2 jh = __floats2half2_rn(j0, j1);
+      sd[(y * 8 + x) * LK_T] = *reinterpret_cast<const uint32_t*>(&jh);
     }
   }
   const float H[9] = {h00, h01, h02, h01, h11, h12, h02, h12, 64.0f};
@@ -167,10 +176,10 @@ __device__ bool lk_align2d(const uint8_t* img, int pitch, int cols, int rows, co
 #pragma unroll
       for (int x = 0; x < 8; ++x) {
         const float search_pixel = wTL * top[x] + wTR * top[x + 1] + wBL * bot[x] + wBR * bot[x + 1];
-        const float res = search_pixel - (float)reg_byte(rp, y * 8 + x) + mean_diff;
+        const float res = search_pixel - reg_byte_f(rp, y * 8 + x) + mean_diff;
         const uint32_t d = sd[(y * 8 + x) * LK_T];
-        const float j0 = 0.5f * (float)(short)(d & 0xffffu), j1 = 0.5f * (float)((int)d >> 16);
-        J0 -= res * j0; J1 -= res * j1; J2 -= res;
+        const float2 j = __half22float2(*reinterpret_cast<const __half2*>(&d));
+        J0 -= res * j.x; J1 -= res * j.y; J2 -= res;
       }
 #pragma unroll
       for (int x = 0; x < 9; ++x) top[x] = bot[x];
@@ -232,7 +241,7 @@ __device__ bool lk_align1d(const uint8_t* img, int pitch, int cols, int rows, fl
 #pragma unroll
       for (int x = 0; x < 8; ++x) {
         const float search_pixel = wTL * top[x] + wTR * top[x + 1] + wBL * bot[x] + wBR * bot[x + 1];
-        const float res = search_pixel - (float)reg_byte(rp, y * 8 + x) + mean_diff;
+        const float res = search_pixel - reg_byte_f(rp, y * 8 + x) + mean_diff;
         const float j0 = __uint_as_float(sd[(y * 8 + x) * LK_T]);
         J0 -= res * j0; J1 -= res; new_chi2 += res * res;
       }
@@ -542,23 +551,35 @@ __device__ __forceinline__ void emit_lk_job(LkJob* dst, const uint8_t* s_pwb, fl
 }
 
 // affine warp of the 10x10 reference patch (matcher.cpp:83-116) into shared memory by a group of 8 lanes
-// R taps per lane in flight together (tap i = sub + 8 r); (x, y) is the lane's running position in the row-major 10x10 patch
-template <int R>
-__device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, int rp, float xmax, float ymax, float a00, float a01, float a10, float a11,
-                                                float pr0, float pr1, float sc, uint8_t* s_pwb, int i0, int& x, int& y)
+// R taps per lane in flight together (tap i = sub + 8 r).  (p0, p1) = ((x - 5) * 2^L, (y - 5) * 2^L) is the lane's running
+// position in the row-major 10x10 patch, kept in float (small integers times a power of two: every update is exact).
+// The four pixel loads of a tap are UNCONDITIONAL (an out-of-bounds tap reads the image's first 2x2 pixels and is discarded)
+// and stay raw 32-bit values until the second loop, so that all 4R loads are issued before the first conversion waits for
+// one (with a branch around the loads the compiler converted inside it and every tap waited for its own loads).
+// one byte through the read-only path as an opaque 32-bit value: the compiler cannot fold the int -> float conversion into
+// the load (it did, and then placed every tap's conversions — which wait for the data — before the next tap's loads)
+__device__ __forceinline__ unsigned ldg_u8_raw(const uint8_t* p)
+{
+  unsigned v;
+  asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <int R, bool TAIL>
+__device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, unsigned rp, float xmax, float ymax, float a00, float a01, float a10, float a11,
+                                                float pr0, float pr1, float sc, uint8_t* s_pwb, int i0, float& p0, float& p1)
 {
   bool inb[R];
   float w00[R], w01[R], w10[R], w11[R];
-  uint8_t p00[R], p01[R], p10[R], p11[R];
+  unsigned v00[R], v01[R], v10[R], v11[R];
+  const float step = 8.0f * sc, lim = 5.0f * sc, wrap = 10.0f * sc;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int i = i0 + GL * r;
-    float p0 = (float)(x - 5), p1 = (float)(y - 5);
-    x += GL; if (x >= 10) { x -= 10; ++y; }
-    p0 *= sc; p1 *= sc;
     const float qx = (a00 * p0 + a01 * p1) + pr0;
     const float qy = (a10 * p0 + a11 * p1) + pr1;
-    inb[r] = (i < 100) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    p0 += step; if (p0 >= lim) { p0 -= wrap; p1 += sc; }
+    inb[r] = !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    if (TAIL) inb[r] = inb[r] && (i0 + GL * r < 100);
     // vk::interpolateMat_8u (vision.h:19-36); floorf == truncation for the non-negative coordinates of an in-bounds tap
     // (out-of-bounds taps produce 0 whatever ix, iy are)
     const int ix = (int)qx, iy = (int)qy;
@@ -567,19 +588,19 @@ __device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, int rp, flo
     w01[r] = (1.0f - sx) * sy;
     w10[r] = sx * (1.0f - sy);
     w11[r] = 1.0f - w00[r] - w01[r] - w10[r];
-    p00[r] = p01[r] = p10[r] = p11[r] = 0;
-    if (inb[r]) {
-      const uint8_t* p = rimg + (size_t)iy * rp + ix;
-      p00[r] = p[0]; p01[r] = p[rp]; p10[r] = p[1]; p11[r] = p[rp + 1];
-    }
+    const unsigned off = inb[r] ? (unsigned)iy * rp + (unsigned)ix : 0u;
+    const uint8_t* p = rimg + off;
+    v00[r] = ldg_u8_raw(p); v10[r] = ldg_u8_raw(p + 1); v01[r] = ldg_u8_raw(p + rp); v11[r] = ldg_u8_raw(p + rp + 1);
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int i = i0 + GL * r;
-    if (i < 100) s_pwb[i] = inb[r] ? (uint8_t)(w00[r] * p00[r] + w01[r] * p01[r] + w10[r] * p10[r] + w11[r] * p11[r]) : (uint8_t)0;
+    const float f = w00[r] * (float)(int)v00[r] + w01[r] * (float)(int)v01[r] + w10[r] * (float)(int)v10[r] + w11[r] * (float)(int)v11[r];
+    if (!TAIL || i < 100) s_pwb[i] = inb[r] ? (uint8_t)f : (uint8_t)0;
   }
 }
 
+template <bool PREFETCH>
 __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, int rc, int rr, float a00, float a01, float a10, float a11,
                                                  float pr0, float pr1, int L, uint8_t* s_pwb, int sub)
 {
@@ -587,11 +608,29 @@ __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, in
   // together) and ONE tail round, not a fourth pass whose last three rounds would be all-idle instructions
   const float sc = (float)(1 << L);
   const float xmax = (float)(rc - 1), ymax = (float)(rr - 1);
-  int x = sub, y = 0;
+  // ptxas interleaves tap r's conversions (which wait for its pixels) with tap r+1's address arithmetic, so the ~11 image
+  // rows of the window are 11 exposed cache misses in a row; PREFETCH touches both ends of every patch row up front (two
+  // image rows each; lane `sub` takes patch row `sub`, lanes 0..3 also the ends of rows 8 and 9).  Measured per 4,096
+  // sequences: match_prepare (nothing else to overlap the misses with) 0.182 -> 0.162 ms; the persistent search kernel, whose
+  // other resident warps already cover them, 1.69 -> 1.77 ms — so only the former prefetches.
+#pragma unroll
+  for (int t = 0; PREFETCH && t < 3; ++t) {
+    const int tx = t == 0 ? 0 : (t == 1 ? 9 : ((sub & 1) ? 9 : 0));
+    const int ty = t < 2 ? sub : 8 + (sub >> 1);
+    const float q0 = (float)(tx - 5) * sc, q1 = (float)(ty - 5) * sc;
+    const float qx = (a00 * q0 + a01 * q1) + pr0, qy = (a10 * q0 + a11 * q1) + pr1;
+    const bool ok = (t < 2 || sub < 4) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    if (ok) {
+      const uint8_t* p = rimg + ((unsigned)(int)qy * (unsigned)rp + (unsigned)(int)qx);
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(p + rp));
+    }
+  }
+  float p0 = (float)(sub - 5) * sc, p1 = -5.0f * sc;
 #pragma unroll 1
   for (int r0 = 0; r0 < 12; r0 += 4)
-    warp_patch_taps<4>(rimg, rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * r0, x, y);
-  warp_patch_taps<1>(rimg, rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * 12, x, y);
+    warp_patch_taps<4, false>(rimg, (unsigned)rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * r0, p0, p1);
+  warp_patch_taps<1, true>(rimg, (unsigned)rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * 12, p0, p1);
 }
 
 constexpr int JOB_BATCH = 8;             // LK job slots a group reserves per atomicAdd
@@ -615,7 +654,7 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
     const DevFrame& ref = frames[(int)task_word(tq, ST_REF_SLOT, gbase, gmask)];
     const int ref_image = (int)task_word(tq, ST_REF_IMAGE, gbase, gmask);
     const uint8_t* rimg = ref.lvl[ref_level] + (size_t)ref_image * ref.img_stride[ref_level];
-    warp_patch_10x10(rimg, ref.pitch[ref_level], ref.w[ref_level], ref.h[ref_level],
+    warp_patch_10x10<false>(rimg, ref.pitch[ref_level], ref.w[ref_level], ref.h[ref_level],
                      __uint_as_float(task_word(tq, ST_A00, gbase, gmask)), __uint_as_float(task_word(tq, ST_A01, gbase, gmask)),
                      __uint_as_float(task_word(tq, ST_A10, gbase, gmask)), __uint_as_float(task_word(tq, ST_A11, gbase, gmask)),
                      __uint_as_float(task_word(tq, ST_PR0, gbase, gmask)), __uint_as_float(task_word(tq, ST_PR1, gbase, gmask)), L, S->pwb, sub);
@@ -1056,7 +1095,7 @@ __global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* fram
   if (flags & 2) {
     const DevFrame& ref = frames[(int)fp->ref_frame_id];
     const uint8_t* rimg = ref.lvl[level] + (size_t)ref_image * ref.img_stride[level];
-    warp_patch_10x10(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, sub);
+    warp_patch_10x10<true>(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, sub);
   }
   __syncwarp(gmask);
   if (results) {
