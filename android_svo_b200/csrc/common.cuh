@@ -158,6 +158,11 @@ __device__ __forceinline__ float warp_sum_f(float v)
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// byte k of a word as a float WITHOUT the conversion unit: PRMT builds the bit pattern of 2^23 + byte, one FADD removes the
+// 2^23 (both exact).  I2F.U8 / I2F.S16 run on the quarter-rate XU pipe, which was the most loaded pipe of the LK kernel
+// (~270 conversions per thread and iteration against ~1,000 FP32 operations).
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)) - 8388608.0f; }
+
 __device__ __forceinline__ int warp_sum_i(int v)
 {
 #pragma unroll

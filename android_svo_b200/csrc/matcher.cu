@@ -112,10 +112,6 @@ __device__ __forceinline__ void inv3f(const float* m, float* r)
 // byte k of a register-resident byte array (k is a compile-time constant after unrolling)
 template <int NW> __device__ __forceinline__ int reg_byte(const uint32_t (&w)[NW], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu); }
 
-// byte k of a word as a float WITHOUT the conversion unit: PRMT builds the bit pattern of 2^23 + byte, one FADD removes the
-// 2^23 (both exact).  I2F.U8 / I2F.S16 run on the quarter-rate XU pipe, which was the most loaded pipe of the LK kernel
-// (~270 conversions per thread and iteration against ~1,000 FP32 operations).
-__device__ __forceinline__ float byte_to_float(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)) - 8388608.0f; }
 template <int NW> __device__ __forceinline__ float reg_byte_f(const uint32_t (&w)[NW], int k) { return byte_to_float(w[k >> 2], k & 3); }
 
 // nine consecutive pixels starting at p (any alignment) as floats; reads the three aligned words that hold them

@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
           }
         }
         // pixel (row r, column c) of the window, r and c compile-time after unrolling; window (3,3) is (v_i, u_i)
-#define WPX(r, c) ((float)((((c) < 4 ? wlo[r] : whi[r]) >> (8 * ((c) & 3))) & 0xffu))
+#define WPX(r, c) byte_to_float((c) < 4 ? wlo[r] : whi[r], (c) & 3)
         float4* rp4 = reinterpret_cast<float4*>(ref_patch + 16 * (size_t)i);
 #pragma unroll
         for (int yy = 0; yy < 4; ++yy) {
@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
               const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (size_t)r * cstride);      // cstride % 4 == 0
               const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
               const uint32_t lo4 = __funnelshift_r(w0, w1, sh), b4 = (w1 >> sh) & 0xffu;
-              W[r][0] = (float)(lo4 & 0xffu); W[r][1] = (float)((lo4 >> 8) & 0xffu); W[r][2] = (float)((lo4 >> 16) & 0xffu);
-              W[r][3] = (float)(lo4 >> 24); W[r][4] = (float)b4;
+              W[r][0] = byte_to_float(lo4, 0); W[r][1] = byte_to_float(lo4, 1); W[r][2] = byte_to_float(lo4, 2);
+              W[r][3] = byte_to_float(lo4, 3); W[r][4] = byte_to_float(b4, 0);
             }
           }
           const float4* p4 = reinterpret_cast<const float4*>(ref_patch + 16 * (size_t)i);
