@@ -75,12 +75,14 @@ __device__ __forceinline__ float interpolate_8u(const uint8_t* img, int stride, 
 // associative, so the sums cannot be tree-reduced without changing results.  With millions of
 // independent problems per step the natural mapping is therefore the reference's own loop, one thread
 // per problem: the 10x10 template lives in 25 registers, the per-pixel template gradient (an integer in
-// [-255,255] per axis) is staged once as packed int16 pairs in shared memory ([64][LK_T] words, conflict
+// [-255,255] per axis) is staged once as packed binary16 pairs in shared memory ([64][LK_T] words, conflict
 // free), the 9x9 search window is streamed row by row with three aligned word loads per row, and every
 // float operation happens in the reference's order.  Results are bit-identical to the CPU code.
 constexpr int LK_T = 128;
+// resident CTAs per SM: 4 (128 registers, no spills since the byte conversions left the XU pipe: 0.702 -> 0.664 ms per 2.4 M jobs
+// against 3 CTAs at 167 registers; 5 CTAs = 96 registers spill)
 #ifndef LK_CTAS
-#define LK_CTAS 3
+#define LK_CTAS 4
 #endif
 
 // One refinement problem, written by the warp-cooperative producers with ONE coalesced 128-byte store.
@@ -447,9 +449,12 @@ constexpr int GL = 8;                    // lanes per group
 constexpr int GPW = 32 / GL;             // groups (items) per warp
 constexpr int EPI_GCHUNK = 32;           // epipolar samples a group stages per round (steady-state walks are <= 47 steps)
 #ifndef SEARCH_CTAS_PER_SM
-#define SEARCH_CTAS_PER_SM 6
+#define SEARCH_CTAS_PER_SM 5
 #endif
-constexpr int SEARCH_CTAS = SEARCH_CTAS_PER_SM;   // resident CTAs per SM of the persistent search kernel (6: 85 registers per thread, no spills)
+// resident CTAs per SM of the persistent search kernel.  Measured per 3.1 M seeds with the current patch-warp code (value of the
+// whole step in k frames/s): 4 CTAs (121 registers) 1.73 ms / 890 k, 5 (96 registers) 1.62 ms / 925 k, 6 (80) 1.67 ms / 907 k,
+// 7 (72, spills) 1.63 ms / 911 k, 8 (64, spills) 1.79 ms / 878 k: with 96 registers ptxas keeps a pass's 16 pixel loads in flight
+constexpr int SEARCH_CTAS = SEARCH_CTAS_PER_SM;
 
 struct EpiGroupSmem {
   __align__(16) uint8_t pwb[112];       // 100 used
@@ -853,6 +858,8 @@ struct SeedPre {
 };
 
 // phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry
+// (occupancy: 118 registers = 4 CTAs per SM; capping at 80 / 64 registers for 6 / 8 CTAs spills and measured 0.448 / 0.516 ms
+// against 0.440 ms — the kernel is bound by its per-thread 128-byte record loads and stores, not by resident warps)
 __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* T_ref_w_all,
                                                          const double* T_cur_w_all, svob200_matcher_opts o, const svob200_seed* seeds,
                                                          SeedPre* pre, EpiCold* cold, SearchTask* tasks, int* job_count)
