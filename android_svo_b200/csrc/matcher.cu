@@ -864,42 +864,73 @@ __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, cons
                                                          const double* T_cur_w_all, svob200_matcher_opts o, const svob200_seed* seeds,
                                                          SeedPre* pre, EpiCold* cold, SearchTask* tasks, int* job_count)
 {
+#ifndef SEEDS_GEOM_DIRECT_STORES
+  // the two 128-byte records of a seed go through shared memory (one padded slot per thread) so that a warp writes them as
+  // 512-byte contiguous requests instead of 32 scattered 16-byte pieces per store instruction
+  struct Slot { uint4 q[9]; };                                       // 8 used; 144-byte stride: conflict-free 16-byte accesses
+  __shared__ Slot s_cold[4][32], s_task[4][32];
+#endif
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (i == 0) *job_count = 0;                                        // consumed by the search kernel that follows on the stream
-  if (i >= n) return;
-  const svob200_feature_ref f = ftrs[i];
-  const svob200_seed s = seeds[i];
-  const double* T_ref_w = T_ref_w_all + 7 * (size_t)i;
-  const double* T_cur_w = T_cur_w_all + 7 * (size_t)f.cur_image;
-  double Tcw_inv[7], T_ref_cur[7], T_cur_ref[7];
-  se3_inverse(T_cur_w, Tcw_inv);
-  se3_mul(T_ref_w, Tcw_inv, T_ref_cur);                              // depth_filter.cpp:263
-  se3_inverse(T_ref_cur, T_cur_ref);
-  SeedPre p;
-  p.status = 0; p.z_inv_min = 0.f;
-  p.t_ref_cur[0] = T_ref_cur[0]; p.t_ref_cur[1] = T_ref_cur[1]; p.t_ref_cur[2] = T_ref_cur[2];
-  const double inv_mu = 1.0 / s.mu;
-  const v3d xyz_f = se3_transform(T_cur_ref, {inv_mu * f.f[0], inv_mu * f.f[1], inv_mu * f.f[2]});
-  if (xyz_f.z < 0.0) p.status = SVOB200_SEED_BEHIND;
-  else {
-    double pxf, pyf;
-    world2cam(cam, xyz_f, pxf, pyf);
-    if (!in_frame(cam, (int)pxf, (int)pyf, 0)) p.status = SVOB200_SEED_NOT_IN_FRAME;
+  const bool valid = i < n;
+  bool has_geom = false;
+  if (valid) {
+    const svob200_feature_ref f = ftrs[i];
+    const svob200_seed s = seeds[i];
+    const double* T_ref_w = T_ref_w_all + 7 * (size_t)i;
+    const double* T_cur_w = T_cur_w_all + 7 * (size_t)f.cur_image;
+    double Tcw_inv[7], T_ref_cur[7], T_cur_ref[7];
+    se3_inverse(T_cur_w, Tcw_inv);
+    se3_mul(T_ref_w, Tcw_inv, T_ref_cur);                              // depth_filter.cpp:263
+    se3_inverse(T_ref_cur, T_cur_ref);
+    SeedPre p;
+    p.status = 0; p.z_inv_min = 0.f;
+    p.t_ref_cur[0] = T_ref_cur[0]; p.t_ref_cur[1] = T_ref_cur[1]; p.t_ref_cur[2] = T_ref_cur[2];
+    const double inv_mu = 1.0 / s.mu;
+    const v3d xyz_f = se3_transform(T_cur_ref, {inv_mu * f.f[0], inv_mu * f.f[1], inv_mu * f.f[2]});
+    if (xyz_f.z < 0.0) p.status = SVOB200_SEED_BEHIND;
+    else {
+      double pxf, pyf;
+      world2cam(cam, xyz_f, pxf, pyf);
+      if (!in_frame(cam, (int)pxf, (int)pyf, 0)) p.status = SVOB200_SEED_NOT_IN_FRAME;
+    }
+    if (p.status == 0) {
+      const float z_inv_min = s.mu + sqrtf(s.sigma2);
+      const float z_inv_max = fmaxf(s.mu - sqrtf(s.sigma2), 0.00000001f);
+      p.z_inv_min = z_inv_min;
+      double Trw_inv[7], T_cur_ref_m[7];
+      se3_inverse(T_ref_w, Trw_inv);
+      se3_mul(T_cur_w, Trw_inv, T_cur_ref_m);                          // matcher.cpp:216
+      EpiGeom g;
+      epi_geometry(cam, f, T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &g);
+#ifdef SEEDS_GEOM_DIRECT_STORES
+      store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, &cold[i], &tasks[i]);
+#else
+      store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, reinterpret_cast<EpiCold*>(&s_cold[warp][lane]),
+                     reinterpret_cast<SearchTask*>(&s_task[warp][lane]));
+#endif
+      has_geom = true;
+    }
+#ifdef SEEDS_GEOM_DIRECT_STORES
+    else reinterpret_cast<uint4*>(&tasks[i])[0] = make_uint4(0, 0, 0, 0);      // flags = 0: nothing to search
+#endif
+    pre[i] = p;
   }
-  if (p.status == 0) {
-    const float z_inv_min = s.mu + sqrtf(s.sigma2);
-    const float z_inv_max = fmaxf(s.mu - sqrtf(s.sigma2), 0.00000001f);
-    p.z_inv_min = z_inv_min;
-    double Trw_inv[7], T_cur_ref_m[7];
-    se3_inverse(T_ref_w, Trw_inv);
-    se3_mul(T_cur_w, Trw_inv, T_cur_ref_m);                          // matcher.cpp:216
-    EpiGeom g;
-    epi_geometry(cam, f, T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &g);
-    store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, &cold[i], &tasks[i]);
-  } else {
-    reinterpret_cast<uint4*>(&tasks[i])[0] = make_uint4(0, 0, 0, 0);        // flags = 0: nothing to search
+#ifndef SEEDS_GEOM_DIRECT_STORES
+  const unsigned wrote = __ballot_sync(0xffffffffu, has_geom);
+  const unsigned skip = __ballot_sync(0xffffffffu, valid && !has_geom);       // flags = 0: nothing to search
+  __syncwarp();                                                                // the slots written above are read by other lanes
+  const size_t i0 = (size_t)(i - lane);                                        // first seed of this warp
+  uint4* gcold = reinterpret_cast<uint4*>(cold + i0);
+  uint4* gtask = reinterpret_cast<uint4*>(tasks + i0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = k * 32 + lane, r = e >> 3, j = e & 7;
+    if ((wrote >> r) & 1u) { gcold[e] = s_cold[warp][r].q[j]; gtask[e] = s_task[warp][r].q[j]; }
+    else if (((skip >> r) & 1u) && j == 0) gtask[e] = make_uint4(0, 0, 0, 0);
   }
-  pre[i] = p;
+#endif
 }
 
 // geometry of stand-alone epipolar queries (svob200_epipolar_match): T_cur_ref and the depth range come from the caller
