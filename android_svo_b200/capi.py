@@ -525,6 +525,45 @@ class Tracker:
                                                  _ptr(px), _ptr(ok), MEM_HOST))
         return (stats, px, ok) if want_px else stats
 
+    def step_device(self, cur_imgs, T_last_w, last_px, want_px=False):
+        """The same step with EVERY argument resident in device memory (SVOB200_MEM_DEVICE): level 0 of the current
+        frame aliases the caller's device buffer (svob200_frame_bind_only), nothing is staged, the whole batch runs as one
+        range (a CUDA graph with forked branches for small batches).  This is the path bench.py's `value` times.  The
+        images go through a ring of three device buffers (the aliased frame must outlive the next step)."""
+        cur_imgs = np.ascontiguousarray(cur_imgs, dtype=np.uint8)
+        T = np.ascontiguousarray(T_last_w, dtype=np.float64)
+        lp = np.ascontiguousarray(last_px, dtype=np.float64)
+        ctx = self.ctx
+        if getattr(self, "_dev", None) is None:
+            self._dev = dict(ring=[ctx.dev_alloc(cur_imgs.nbytes) for _ in range(3)], k=0, T=ctx.dev_alloc(T.nbytes), lp=ctx.dev_alloc(max(lp.nbytes, 8)),
+                             stats=ctx.dev_alloc(self.batch * step_stats_dt.itemsize), px=ctx.dev_alloc(max(self.N, 1) * 16),
+                             ok=ctx.dev_alloc(max(self.N, 1) * 4))
+        d = self._dev
+        img = d["ring"][d["k"] % 3]
+        d["k"] += 1
+        ctx.dev_upload(img, cur_imgs); ctx.dev_upload(d["T"], T); ctx.dev_upload(d["lp"], lp)
+        V = C.c_void_p
+        ctx._ck(self.L.svob200_tracker_step(self.h, V(img), cur_imgs.shape[-1], V(d["T"]), V(d["lp"]), V(d["stats"]),
+                                            V(d["px"]) if want_px else None, V(d["ok"]) if want_px else None, MEM_DEVICE))
+        ctx.sync()
+        stats = np.zeros(self.batch, step_stats_dt)
+        ctx.dev_download(stats, d["stats"])
+        if not want_px:
+            return stats
+        px = np.zeros((self.N, 2)); ok = np.zeros(self.N, np.int32)
+        if self.N:
+            ctx.dev_download(px, d["px"]); ctx.dev_download(ok, d["ok"])
+        return stats, px, ok
+
+    def set_last_device(self, imgs):
+        """last frame from a device buffer (svob200_tracker_set_last with SVOB200_MEM_DEVICE)"""
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        d = self.ctx.dev_alloc(imgs.nbytes)
+        self.ctx.dev_upload(d, imgs)
+        self.ctx._ck(self.L.svob200_tracker_set_last(self.h, C.c_void_p(d), imgs.shape[-1], MEM_DEVICE))
+        self.ctx.sync()
+        self.ctx.dev_free(d)
+
     def step_raw(self, cur_ptr, stride, T_ptr, px_ptr, stats_ptr, mem):
         """Pointer-level step (pinned host or device addresses), no allocation on the Python side."""
         rc = self.L.svob200_tracker_step(self.h, C.c_void_p(cur_ptr), int(stride), C.c_void_p(T_ptr), C.c_void_p(px_ptr),
@@ -554,5 +593,10 @@ class Tracker:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.svob200_tracker_destroy(self.h)
+            self.L.svob200_tracker_destroy(self.h)          # synchronises the stream first
             self.h = None
+            d = getattr(self, "_dev", None)
+            if d is not None:
+                for p in d["ring"] + [d[k] for k in ("T", "lp", "stats", "px", "ok")]:
+                    self.ctx.dev_free(p)
+                self._dev = None

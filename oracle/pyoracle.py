@@ -605,6 +605,20 @@ class OracleSeq(_SeqBase):
         self.lib.svo_oracle_seq_get_seeds(self.h, arr)
         return np.array([(s.a, s.b, s.mu, s.z_range, s.sigma2) for s in arr[:self.S]], np.float32).reshape(self.S, 5)
 
+    def seed_obs(self):
+        """per-seed observation of the last step, same fields as svob200_seed_obs"""
+        dt = np.dtype([("status", "i4"), ("search_level", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"), ("z", "f8"),
+                       ("px_cur", "f8", 2), ("epi_length", "f8")], align=True)
+        out = np.zeros(max(self.S, 1), dt)
+        self.lib.svo_oracle_seq_get_seed_obs.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.svo_oracle_seq_get_seed_obs(self.h, out.ctypes.data)
+        return out[:self.S]
+
+    def set_pose_override(self, T_cur_w):
+        """the matcher / depth-filter stages of the NEXT step use this pose instead of the aligned one"""
+        self.lib.svo_oracle_seq_set_pose_override.argtypes = [C.c_void_p, c_dp]
+        self.lib.svo_oracle_seq_set_pose_override(self.h, _p(f64(T_cur_w), c_dp))
+
     def close(self):
         if self.h:
             self.lib.svo_oracle_seq_destroy(self.h)

@@ -25,6 +25,9 @@ typedef struct {
   int n_reproj_trials, n_pose_obs;     /* chain mode: Reprojector::n_trials_, features left after the pose optimiser */
 } svo_step_stats;
 
+/* what DepthFilter::updateSeeds saw for one seed in the last step (mirror of svob200_seed_obs) */
+typedef struct svo_seq_seed_obs { int status, search_level, zmssd_best, n_evals; double z, px_cur[2], epi_length; } svo_seq_seed_obs;
+
 typedef struct svo_seq {
   svo_cam cam;
   int n_levels, w, h;
@@ -45,6 +48,11 @@ typedef struct svo_seq {
   /* chain mode (svo_oracle_seq_set_chain): Reprojector::reprojectMap + pose_optimizer::optimizeGaussNewton replace the
    * refine-every-map-point loop, as in FrameHandlerMono::processFrame (frame_handler_mono.cpp:191-222) */
   int chain_cell, chain_max_fts, chain_pose_opt;
+  /* test hooks: the pose the matcher / depth-filter stages of the NEXT step use instead of the aligned one (parity tests
+   * inject the device's pose to separate the tolerance-matched alignment sums from the depth filter's own arithmetic), and
+   * the per-seed observation of the last step */
+  double T_override[7]; int have_override;
+  struct svo_seq_seed_obs* obs;
 } svo_seq;
 
 static void build_frame(svo_seq* s, const uint8_t* img, uint8_t* l0, uint8_t* up, svo_pyr* p)
@@ -75,7 +83,7 @@ void svo_oracle_seq_destroy(svo_seq* s)
   if (!s) return;
   free(s->kf0); free(s->kfu); free(s->last0); free(s->lastu); free(s->cur0); free(s->curu);
   free(s->kf_px); free(s->kf_f); free(s->pt_world); free(s->kf_level);
-  free(s->seed_px); free(s->seed_f); free(s->seed_level); free(s->seeds); free(s->xyz); free(s->has_point);
+  free(s->seed_px); free(s->seed_f); free(s->seed_level); free(s->seeds); free(s->xyz); free(s->has_point); free(s->obs);
   free(s);
 }
 
@@ -90,6 +98,7 @@ void svo_oracle_seq_set_keyframe(svo_seq* s, const uint8_t* img, const double* T
   s->seed_px = (double*)malloc(sizeof(double) * 2 * (S + 1)); s->seed_f = (double*)malloc(sizeof(double) * 3 * (S + 1));
   s->seed_level = (int*)malloc(sizeof(int) * (S + 1)); s->seeds = (svo_seed*)malloc(sizeof(svo_seed) * (S + 1));
   s->xyz = (double*)malloc(sizeof(double) * 3 * (N + 1)); s->has_point = (uint8_t*)malloc(N + 1);
+  s->obs = (svo_seq_seed_obs*)calloc((size_t)S + 1, sizeof(svo_seq_seed_obs));
   memcpy(s->kf_px, kf_px, sizeof(double) * 2 * N); memcpy(s->pt_world, pt_world, sizeof(double) * 3 * N);
   memcpy(s->kf_level, kf_level, sizeof(int) * N);
   memcpy(s->seed_px, seed_px, sizeof(double) * 2 * S); memcpy(s->seed_level, seed_level, sizeof(int) * S);
@@ -127,6 +136,12 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
   st->chi2 = ar.chi2;
   for (int l = 0; l < SVO_MAX_LEVELS; ++l) st->align_iters += ar.iters[l];
   svo_oracle_se3_mul(ar.T_cur_ref, T_last_w, st->T_cur_w);
+  /* st->T_cur_w keeps this sequence's own pose; Tc is what the following stages see.  Default mode: the override replaces
+   * the aligned pose for the matcher and the depth filter.  Chain mode: the reprojector and the pose optimiser run on the own
+   * pose and the override (the device's pose AFTER its optimiser) replaces it for the depth filter only. */
+  double T_use[7];
+  const double* Tc = st->T_cur_w;
+  if (s->have_override) { memcpy(T_use, s->T_override, sizeof(T_use)); if (s->chain_cell <= 0) Tc = T_use; }
   if (s->chain_cell > 0) {
     /* Reprojector::reprojectMap over the keyframe's map points (one observation each, insertion order = fts_ order), every
      * point TYPE_UNKNOWN: the benchmark resets the per-point counters every frame to keep the workload stationary */
@@ -176,7 +191,7 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
   /* reprojection refinement */
   double Tkw_inv[7], T_cur_kf[7];
   svo_oracle_se3_inverse(s->T_kf_w, Tkw_inv);
-  svo_oracle_se3_mul(st->T_cur_w, Tkw_inv, T_cur_kf);
+  svo_oracle_se3_mul(Tc, Tkw_inv, T_cur_kf);
   for (int i = 0; i < s->N; ++i) {
     svo_ref_feature f;
     f.px_ref[0] = s->kf_px[2 * i]; f.px_ref[1] = s->kf_px[2 * i + 1];
@@ -184,7 +199,7 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
     f.level_ref = s->kf_level[i]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
     const double depth_ref = norm3d(Tkw_inv[0] - s->pt_world[3 * i], Tkw_inv[1] - s->pt_world[3 * i + 1], Tkw_inv[2] - s->pt_world[3 * i + 2]);
     double pc[3], px_in[2];
-    svo_oracle_se3_transform(st->T_cur_w, s->pt_world + 3 * i, pc);
+    svo_oracle_se3_transform(Tc, s->pt_world + 3 * i, pc);
     svo_oracle_world2cam(&s->cam, pc, px_in);
     svo_match_result mr;
     const int ok = svo_oracle_find_match_direct(&s->kf, &s->cur, &s->cam, &f, depth_ref, T_cur_kf, &s->mopts, px_in, &mr);
@@ -194,13 +209,26 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
   }
   }
   /* depth filter */
+  if (s->have_override) Tc = T_use;
+  s->have_override = 0;
   for (int i = 0; i < s->S; ++i) {
     svo_ref_feature f;
     f.px_ref[0] = s->seed_px[2 * i]; f.px_ref[1] = s->seed_px[2 * i + 1];
     memcpy(f.f_ref, s->seed_f + 3 * i, sizeof(f.f_ref));
     f.level_ref = s->seed_level[i]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
-    const int status = svo_oracle_update_seed_with_frame(&s->kf, &s->cur, &s->cam, &f, s->T_kf_w, st->T_cur_w, &s->mopts,
-                                                         s->conv_thresh, &s->seeds[i], NULL);
+    svo_epi_result epi;
+    const int status = svo_oracle_update_seed_with_frame(&s->kf, &s->cur, &s->cam, &f, s->T_kf_w, Tc, &s->mopts,
+                                                         s->conv_thresh, &s->seeds[i], &epi);
+    {
+      svo_seq_seed_obs* ob = &s->obs[i];
+      memset(ob, 0, sizeof(*ob));
+      ob->status = status; ob->zmssd_best = 2000 * 64;
+      if (status != SVO_SEED_BEHIND && status != SVO_SEED_NOT_IN_FRAME) {
+        ob->search_level = epi.search_level; ob->zmssd_best = epi.zmssd_best; ob->n_evals = epi.n_evals; ob->epi_length = epi.epi_length;
+        ob->px_cur[0] = epi.px_cur[0]; ob->px_cur[1] = epi.px_cur[1];
+        if (status != SVO_SEED_NO_MATCH) ob->z = epi.depth;
+      }
+    }
     if (status == SVO_SEED_UPDATED) st->n_seeds_updated++;
     else if (status == SVO_SEED_CONVERGED) st->n_seeds_converged++;
     else if (status == SVO_SEED_NO_MATCH) st->n_seeds_failed++;
@@ -213,6 +241,9 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
 }
 
 void svo_oracle_seq_get_seeds(const svo_seq* s, svo_seed* out) { memcpy(out, s->seeds, sizeof(svo_seed) * s->S); }
+void svo_oracle_seq_get_seed_obs(const svo_seq* s, svo_seq_seed_obs* out) { memcpy(out, s->obs, sizeof(svo_seq_seed_obs) * s->S); }
+/* the matcher / depth-filter stages of the next step use T_cur_w instead of the pose sparse alignment produced */
+void svo_oracle_seq_set_pose_override(svo_seq* s, const double* T_cur_w) { memcpy(s->T_override, T_cur_w, sizeof(s->T_override)); s->have_override = 1; }
 
 /* ---- batch of independent sequences over a pthread pool (one work item = one sequence step) ---- */
 typedef struct {

@@ -117,23 +117,37 @@ def test_seed_scalars_vs_reference(ctx):
     assert np.allclose(tau, G["tau_out"], rtol=1e-9, atol=0)
 
 
-def test_tracker_vs_reference_pipeline(ctx):
+def test_tracker_vs_reference_pipeline(ctx, oracle):
+    """svob200_tracker_step against the reference's own per-frame outputs (golden).  Seed states: the free-running oracle is
+    first pinned to the golden seeds BIT FOR BIT (so it stands for the reference), then test_pipeline.SeedParity applies: seeds
+    outside 1e-5 are counted and each must be reproduced exactly by the oracle run on the device's pose."""
+    from oracle.pyoracle import Cam, OracleSeq
+    from test_pipeline import SeedParity
     imgs, poses = G["scene_imgs"], G["scene_poses"]
     N, S = len(G["pipe_kf_level"]), len(G["pipe_seed_level"])
-    trk = capi.Tracker(ctx, cam_g(), 1, 4, 3, 1, 4)
+    cam = cam_g()
+    cam_o = Cam.make(cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy)
+    trk = capi.Tracker(ctx, cam, 1, 4, 3, 1, 4)
+    free, pinned = OracleSeq(oracle, cam_o, 4, 3, 1, 4), OracleSeq(oracle, cam_o, 4, 3, 1, 4)
+    par = SeedParity()
     try:
         trk.set_keyframe(imgs[:1], poses[:1], [0, N], G["pipe_kf_px"], G["pipe_kf_level"], G["pipe_pt_world"], [0, S],
                          G["pipe_seed_px"], G["pipe_seed_level"])
         trk.set_last(imgs[:1])
+        for s in (free, pinned):
+            s.set_keyframe(imgs[0], poses[0], G["pipe_kf_px"], G["pipe_kf_level"], G["pipe_pt_world"], G["pipe_seed_px"], G["pipe_seed_level"])
+            s.set_last(imgs[0])
         for k in range(1, 6):
             st, px, ok = trk.step(imgs[k:k + 1], poses[k - 1:k], G["pipe_last_px"][k - 1], want_px=True)
             rot, trans = synth.pose_error(st[0]["T_cur_w"], G["pipe_T"][k - 1])
             assert rot <= 1e-4 and trans <= 2e-4 and rot < 1e-9 and trans < 1e-9
             assert [st[0]["n_tracked"], st[0]["n_matched"], st[0]["n_seeds_converged"], st[0]["align_iters"]] == list(G["pipe_counts"][k - 1])
             assert np.array_equal(ok, G["pipe_ok"][k - 1]) and np.abs(px - G["pipe_px"][k - 1]).max() <= 1e-3
-            sg = trk.seeds()
-            sg = np.stack([sg[c] for c in ("a", "b", "mu", "z_range", "sigma2")], 1)
-            se = G["pipe_seeds"][k - 1]
-            assert np.isclose(sg, se, rtol=1e-5, atol=0).all(axis=1).mean() > 0.98 and np.allclose(sg, se, rtol=1e-3, atol=0)
+            free.step(imgs[k], poses[k - 1], G["pipe_last_px"][k - 1])
+            assert np.array_equal(free.seeds().view(np.uint32), np.ascontiguousarray(G["pipe_seeds"][k - 1], dtype=np.float32).view(np.uint32))
+            pinned.set_pose_override(st[0]["T_cur_w"])
+            pinned.step(imgs[k], poses[k - 1], G["pipe_last_px"][k - 1])
+            par.check(trk.seeds(), trk.seed_obs(), free, pinned)
+        par.finish(max_outside_frac=0.02)
     finally:
-        trk.close()
+        trk.close(); free.close(); pinned.close()
