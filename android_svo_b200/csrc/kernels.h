@@ -57,6 +57,32 @@ int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& ca
                         const double* d_T_ref_w, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
                         svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first,
                         cudaStream_t s, long long* launches, cudaEvent_t* marks = nullptr /* 3 events between the four kernels */);
+// The tracker's compact seed record (64 B, two sectors): the reference feature of a seed is (px, f, level) in keyframe `kf` of
+// image `image`; the keyframe's frame slot comes from a table indexed by kf, and everything that depends only on the pair
+// (keyframe, image) — the relative poses of depth_filter.cpp:263 / matcher.cpp:216 and the pixel error angle — from a table the
+// step refreshes with one tiny kernel instead of ~600 FP64 instructions per seed.  (f = cam2world(px) stays in the record:
+// recomputing it costs two divisions, a square root and three more divisions per seed and kernel, more than 24 bytes of HBM.)
+// state: 0 alive, 1 free slot.  batch_id: Seed::batch_id (depth_filter.h:38) for the ageing rule.
+struct __align__(16) SeedRef {
+  double px[2];
+  double f[3];
+  int image;
+  uint8_t level, kf; uint16_t batch_id;
+  uint8_t state, pad0; uint16_t pad1;
+  int pad2[3];
+};
+static_assert(sizeof(SeedRef) == 64, "SeedRef must be two 32-byte sectors");
+constexpr int SEED_RANGES = 32;
+// per (keyframe, image): T_ref_cur = ref.T_f_w * cur.T_f_w^-1 (depth_filter.cpp:263), its inverse (:264), the matcher's
+// T_cur_ref = cur.T_f_w * ref.T_f_w^-1 (matcher.cpp:216) and px_error_angle (depth_filter.cpp:245-247)
+struct __align__(16) SeedPoseRec { double T_ref_cur[7], T_cur_ref[7], T_cur_ref_m[7]; double px_error_angle; };
+static_assert(sizeof(SeedPoseRec) == 176, "SeedPoseRec layout");
+// image0 / n_images: the images [image0, image0 + n_images) this call covers (rows of the pose table it refreshes)
+int launch_seeds_update_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const SeedRef* d_refs, const double* d_T_kf_w,
+                                const int* d_kf_slot, int batch, int n_kfs, SeedPoseRec* d_pose_table, int image0, int n_images, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
+                                svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first,
+                                int range /* < SEED_RANGES: sub-ranges in flight together use distinct job regions / counters */,
+                                cudaStream_t s, long long* launches, cudaEvent_t* marks = nullptr);
 int launch_update_seed(int n, const float* d_x, const float* d_tau2, svob200_seed* d_seeds, cudaStream_t s, long long* launches);
 int launch_compute_tau(int n, const double* d_T, const double* d_f, const double* d_z, double angle, double* d_out,
                        cudaStream_t s, long long* launches);

@@ -393,25 +393,46 @@ struct __align__(16) EpiCold {
 static_assert(sizeof(EpiCold) == 128, "EpiCold layout");
 
 // what the search kernel needs, packed into ONE 128-byte line: a warp fetches it with a single coalesced load (lane k
-// holds word k) one item ahead of the item it is working on, and pulls fields out by shuffle
+// holds word k) one item ahead of the item it is working on, and pulls fields out by shuffle.  The first 16 bytes (flags, levels,
+// epi_length) are all the depth filter's finish kernel reads of it: one 32-byte sector per seed instead of a 128-byte cold record.
 struct __align__(16) SearchTask { uint32_t w[32]; };
-enum { ST_FLAGS = 0, ST_LEVELS = 1, ST_N = 2, ST_REF_SLOT = 3, ST_REF_IMAGE = 4, ST_CUR_IMAGE = 5, ST_A00 = 6, ST_A01 = 7, ST_A10 = 8, ST_A11 = 9,
-       ST_PR0 = 10, ST_PR1 = 11, ST_DIRX = 12, ST_DIRY = 13, ST_BX0 = 14, ST_BY0 = 16, ST_STEPX = 18, ST_STEPY = 20, ST_MIDX = 22, ST_MIDY = 24 };
-enum { ST_ACTIVE = 1, ST_WARP_OK = 2, ST_MODE_SHIFT = 2 };
+enum { ST_FLAGS = 0, ST_LEVELS = 1, ST_EPILEN = 2, ST_REF_SLOT = 4, ST_REF_IMAGE = 5, ST_CUR_IMAGE = 6, ST_A00 = 8, ST_A01 = 9, ST_A10 = 10, ST_A11 = 11,
+       ST_PR0 = 12, ST_PR1 = 13, ST_DIRX = 14, ST_DIRY = 15, ST_BX0 = 16, ST_BY0 = 18, ST_STEPX = 20, ST_STEPY = 22, ST_MIDX = 24, ST_MIDY = 26 };
+// flags: bit 0 search this item, bit 1 the warp matrix is finite, bits 2-3 EPI_MODE_*, bits 4-6 the depth filter's early status
+// (SVOB200_SEED_BEHIND / _NOT_IN_FRAME; 0 = the matcher runs), bit 7 z_inv_min is NaN (depth_filter.cpp:334)
+// levels: search level | reference level << 8 | samples of the walk << 16
+enum { ST_ACTIVE = 1, ST_WARP_OK = 2, ST_MODE_SHIFT = 2, ST_STATUS_SHIFT = 4, ST_ZMIN_NAN = 128 };
 
-__device__ inline void store_geometry(const EpiGeom& g, const svob200_feature_ref& f, bool active, EpiCold* cold, SearchTask* task)
+// the reference feature of an item, wherever its record lives (caller's svob200_feature_ref or the tracker's compact SeedRef)
+struct RefFtr {
+  double px[2]; v3d f; int level, type; double grad[2];
+  int ref_slot, ref_image, cur_image, kf;
+};
+__device__ __forceinline__ RefFtr ref_ftr_of(const svob200_feature_ref& r)
 {
-  EpiCold c;
-  for (int k = 0; k < 7; ++k) c.T_cur_ref[k] = g.T_cur_ref[k];
-  for (int k = 0; k < 4; ++k) c.A[k] = g.A[k];
-  c.ex = g.ex; c.ey = g.ey; c.epi_length = g.epi_length; c.L = g.L; c.mode = g.mode; c.reject = g.reject; c.n_steps_report = g.n_steps_report;
-  *cold = c;
+  RefFtr f;
+  f.px[0] = r.px[0]; f.px[1] = r.px[1]; f.f = {r.f[0], r.f[1], r.f[2]}; f.level = r.level; f.type = r.type; f.grad[0] = r.grad[0]; f.grad[1] = r.grad[1];
+  f.ref_slot = (int)r.ref_frame_id; f.ref_image = r.ref_image; f.cur_image = r.cur_image; f.kf = 0;
+  return f;
+}
+
+// cold: stand-alone queries only (nullptr for the depth filter, whose finish kernel recomputes the poses and reads the task's head)
+__device__ inline void store_geometry(const EpiGeom& g, const RefFtr& f, bool active, uint32_t extra_flags, EpiCold* cold, SearchTask* task)
+{
+  if (cold) {
+    EpiCold c;
+    for (int k = 0; k < 7; ++k) c.T_cur_ref[k] = g.T_cur_ref[k];
+    for (int k = 0; k < 4; ++k) c.A[k] = g.A[k];
+    c.ex = g.ex; c.ey = g.ey; c.epi_length = g.epi_length; c.L = g.L; c.mode = g.mode; c.reject = g.reject; c.n_steps_report = g.n_steps_report;
+    *cold = c;
+  }
   SearchTask t;
 #pragma unroll
   for (int k = 0; k < 32; ++k) t.w[k] = 0;
-  t.w[ST_FLAGS] = (active ? ST_ACTIVE : 0) | (g.warp_ok ? ST_WARP_OK : 0) | ((uint32_t)g.mode << ST_MODE_SHIFT);
-  t.w[ST_LEVELS] = (uint32_t)g.L | ((uint32_t)f.level << 8);
-  t.w[ST_N] = (uint32_t)g.n; t.w[ST_REF_SLOT] = (uint32_t)f.ref_frame_id; t.w[ST_REF_IMAGE] = (uint32_t)f.ref_image; t.w[ST_CUR_IMAGE] = (uint32_t)f.cur_image;
+  t.w[ST_FLAGS] = (active ? ST_ACTIVE : 0) | (g.warp_ok ? ST_WARP_OK : 0) | ((uint32_t)g.mode << ST_MODE_SHIFT) | extra_flags;
+  t.w[ST_LEVELS] = (uint32_t)g.L | ((uint32_t)f.level << 8) | ((uint32_t)g.n << 16);
+  t.w[ST_EPILEN] = (uint32_t)__double2loint(g.epi_length); t.w[ST_EPILEN + 1] = (uint32_t)__double2hiint(g.epi_length);
+  t.w[ST_REF_SLOT] = (uint32_t)f.ref_slot; t.w[ST_REF_IMAGE] = (uint32_t)f.ref_image; t.w[ST_CUR_IMAGE] = (uint32_t)f.cur_image;
   t.w[ST_A00] = __float_as_uint(g.a00); t.w[ST_A01] = __float_as_uint(g.a01); t.w[ST_A10] = __float_as_uint(g.a10); t.w[ST_A11] = __float_as_uint(g.a11);
   t.w[ST_PR0] = __float_as_uint(g.pr0); t.w[ST_PR1] = __float_as_uint(g.pr1); t.w[ST_DIRX] = __float_as_uint(g.dirx); t.w[ST_DIRY] = __float_as_uint(g.diry);
   const double d[6] = {g.Bx0, g.By0, g.stepx, g.stepy, g.px_mid[0], g.px_mid[1]};
@@ -430,6 +451,14 @@ struct __align__(16) EpiSearch {
   double pad_;
 };
 static_assert(sizeof(EpiSearch) == 64, "EpiSearch layout");
+
+// the depth filter's 32-byte variant of EpiSearch: xy = the matched pixel (REFINED, or the pre-refinement pixel while
+// found == NONE) or uv_best on the unit plane (UV_ONLY: the pixel is world2cam_uv(xy), recomputed by the consumer)
+struct __align__(16) SeedMatch {
+  int found, zmssd_best, n_evals, xy_valid;
+  double xy[2];
+};
+static_assert(sizeof(SeedMatch) == 32, "SeedMatch layout");
 
 __device__ __forceinline__ EpiSearch epi_search_none()
 {
@@ -478,14 +507,14 @@ __device__ __forceinline__ double task_double(const uint4& tq, int k, int gbase,
 }
 
 // matcher.cpp:207-288 up to the start of the walk: pure per-thread math
-__device__ inline void epi_geometry(const DevCam& cam, const svob200_feature_ref& f, const double* T_cur_ref, double d_estimate,
+__device__ inline void epi_geometry(const DevCam& cam, const RefFtr& f, const double* T_cur_ref, double d_estimate,
                                     double d_min, double d_max, const svob200_matcher_opts& o, EpiGeom* g)
 {
   for (int k = 0; k < 7; ++k) g->T_cur_ref[k] = T_cur_ref[k];
   g->reject = 0; g->mode = EPI_MODE_NONE; g->n = 0; g->n_steps_report = 0; g->L = 0; g->epi_length = 0; g->warp_ok = 0;
   g->Bx0 = g->By0 = g->stepx = g->stepy = 0; g->px_mid[0] = g->px_mid[1] = 0; g->ex = g->ey = 0;
   g->a00 = g->a01 = g->a10 = g->a11 = g->pr0 = g->pr1 = g->dirx = g->diry = 0;
-  const v3d f_ref = {f.f[0], f.f[1], f.f[2]};
+  const v3d f_ref = f.f;
   const v3d tA = se3_transform(T_cur_ref, {f_ref.x * d_min, f_ref.y * d_min, f_ref.z * d_min});
   const double Ax = tA.x / tA.z, Ay = tA.y / tA.z;
   const v3d tB = se3_transform(T_cur_ref, {f_ref.x * d_max, f_ref.y * d_max, f_ref.z * d_max});
@@ -642,7 +671,7 @@ constexpr int JOB_BATCH = 8;             // LK job slots a group reserves per at
 __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_slot, const DevCam& cam, const svob200_matcher_opts& o,
                                                 const uint4& tq, int item, EpiGroupSmem* S, int sub, int gbase, unsigned gmask,
                                                 LkJob* jobs, int* job_count, int& slot_base, int& slots_left, EpiSearch* search,
-                                                svob200_epi_result* api_results)
+                                                SeedMatch* seed_match, svob200_epi_result* api_results)
 {
   const int flags = (int)task_word(tq, ST_FLAGS, gbase, gmask);
   const int mode = (flags >> ST_MODE_SHIFT) & 3;
@@ -677,7 +706,7 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
     const DevFrame& cur = frames[cur_slot];
     const uint8_t* cimg = cur.lvl[L] + (size_t)cur_image * cur.img_stride[L];
     const int cpitch = cur.pitch[L];
-    const int n = (int)task_word(tq, ST_N, gbase, gmask);
+    const int n = levels >> 16;
     RefPatchRegs rpatch;
     load_ref_patch(S->patch, rpatch);
     unsigned long long best = ((unsigned long long)(2000 * 64) << 32);   // PatchScore::threshold(), strict <
@@ -741,7 +770,15 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
     }
   }
   if (want_job) { out.px_cur[0] = px0; out.px_cur[1] = px1; out.px_cur_valid = 1; }
-  if (sub == 0) search[item] = out;
+  if (sub == 0) {
+    if (seed_match) {
+      SeedMatch m;
+      m.found = out.found; m.zmssd_best = out.zmssd_best; m.n_evals = out.n_evals; m.xy_valid = out.px_cur_valid;
+      const bool uv = out.found == EPI_FOUND_UV_ONLY;
+      m.xy[0] = uv ? out.uv_best[0] : out.px_cur[0]; m.xy[1] = uv ? out.uv_best[1] : out.px_cur[1];
+      seed_match[item] = m;
+    } else search[item] = out;
+  }
   if (!want_job) return;
   // hand over to the LK kernel: px_scaled = px_cur / (1 << L) (double), cast to float at the start of align1D/2D
   if (slots_left == 0) {
@@ -756,21 +793,22 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
 }
 
 // matcher.cpp:269-276 / :341-351: triangulate from the matched pixel (per thread)
-__device__ inline bool epi_finish(const DevCam& cam, const svob200_feature_ref& f, const double* T_cur_ref, const EpiSearch& s, double* depth)
+__device__ inline bool epi_finish(const DevCam& cam, v3d f_ref, const double* T_cur_ref, int found, double x0, double x1, double* depth)
 {
   v3d fc;
-  if (s.found == EPI_FOUND_REFINED) fc = cam2world(cam, s.px_cur[0], s.px_cur[1]);
-  else if (s.found == EPI_FOUND_UV_ONLY) fc = normalized3({s.uv_best[0], s.uv_best[1], 1.0});
+  if (found == EPI_FOUND_REFINED) fc = cam2world(cam, x0, x1);               // x = the refined pixel
+  else if (found == EPI_FOUND_UV_ONLY) fc = normalized3({x0, x1, 1.0});       // x = uv_best on the unit plane
   else return false;
-  return depth_from_triangulation(T_cur_ref, {f.f[0], f.f[1], f.f[2]}, fc, depth);
+  return depth_from_triangulation(T_cur_ref, f_ref, fc, depth);
 }
 
 // ---------------------------------------------------------------- the LK kernel: thread per job
 // Where the result of a job goes (the consumers read plain arrays; no extra "finish" pass for the LK itself).
-enum { LK_SINK_EPI = 0, LK_SINK_MATCH_COMPACT = 1, LK_SINK_MATCH_RESULT = 2, LK_SINK_ARRAYS = 3 };
+enum { LK_SINK_EPI = 0, LK_SINK_MATCH_COMPACT = 1, LK_SINK_MATCH_RESULT = 2, LK_SINK_ARRAYS = 3, LK_SINK_SEED = 4 };
 struct LkSink {
   int kind;
-  EpiSearch* search;              // LK_SINK_EPI: found / px_cur / h_inv of seed `item`
+  EpiSearch* search;              // LK_SINK_EPI: found / px_cur / h_inv of query `item`
+  SeedMatch* seed_match;          // LK_SINK_SEED: found / xy of seed `item`
   double* px_out; int* ok_out;    // LK_SINK_MATCH_COMPACT (level-0 pixels) and LK_SINK_ARRAYS (pixels at the image's scale)
   svob200_match_result* mres;     // LK_SINK_MATCH_RESULT
   double* h_inv_out;              // LK_SINK_ARRAYS (may be null)
@@ -823,7 +861,9 @@ __global__ void __launch_bounds__(LK_T, LK_CTAS) lk_refine_kernel(const DevFrame
   if (mode1d) ok = lk_align1d(img, pitch, cols, rows, dirx, diry, w, rp, n_iter, u, v, h_inv, sd);
   else ok = lk_align2d(img, pitch, cols, rows, w, rp, n_iter, u, v, sd);
   const double s = (double)(1 << L);
-  if (sink.kind == LK_SINK_EPI) {
+  if (sink.kind == LK_SINK_SEED) {
+    if (ok) { SeedMatch* e = &sink.seed_match[item]; e->xy[0] = (double)u * s; e->xy[1] = (double)v * s; e->found = EPI_FOUND_REFINED; }
+  } else if (sink.kind == LK_SINK_EPI) {
     EpiSearch* e = &sink.search[item];
     e->h_inv = h_inv;
     if (ok) { e->px_cur[0] = (double)u * s; e->px_cur[1] = (double)v * s; e->found = EPI_FOUND_REFINED; }
@@ -850,87 +890,137 @@ int launch_lk_refine(const DevFrame* d_frames, int cur_slot, const LkJob* d_jobs
 }
 
 // ---------------------------------------------------------------- depth filter: DepthFilter::updateSeeds loop body
-// (depth_filter.cpp:250-340) as four kernels over all seeds: geometry (thread), search (warp), LK (thread), update (thread)
-struct SeedPre {
-  int status;                  // 0 = run the matcher; else the final status (BEHIND / NOT_IN_FRAME)
-  float z_inv_min;
-  double t_ref_cur[3];         // translation of T_ref_cur (computeTau)
+// (depth_filter.cpp:250-340) as four kernels over all seeds: geometry (thread), search (8-lane group), LK (thread), update (thread).
+//
+// HBM traffic per seed is what bounds the two thread-per-seed kernels (ncu r1f: 1.46 + 1.27 GB per 3.1 M seeds, 73-89 % of the
+// HBM peak), so the records are kept small:
+//   * where a seed's reference feature lives is a template parameter: the caller's svob200_feature_ref records + one keyframe
+//     pose per seed (svob200_seeds_update), or the tracker's 64-byte SeedRef + a table of relative poses indexed by
+//     (keyframe, image), refreshed by one tiny kernel per step (the poses are shared by all the seeds of an image);
+//   * the geometry kernel writes ONE record per seed, the search task; the finish kernel reads its 16-byte head (flags, levels,
+//     epi_length) instead of a 128-byte cold record and a 32-byte pre record;
+//   * the search / LK kernels hand over a 32-byte SeedMatch instead of the 64-byte EpiSearch.
+// Per seed: geometry reads 64 + 20 B and writes 128 B; finish reads 64 + 20 + 32 + 32 B and writes 20 + 48 B.
+
+// what a seed needs of the two frame poses
+struct SeedPoses { double T_ref_cur[7], T_cur_ref[7], T_cur_ref_m[7]; double px_error_angle; };
+
+// T_ref_cur = ref.T_f_w * cur.T_f_w^-1 (depth_filter.cpp:263), its inverse, the matcher's T_cur_ref = cur.T_f_w * ref.T_f_w^-1
+// (matcher.cpp:216) and the pixel error angle of depth_filter.cpp:245-247
+__device__ __forceinline__ void seed_relative_poses(const DevCam& cam, const double* T_ref_w, const double* T_cur_w, SeedPoses& P)
+{
+  double inv[7];
+  se3_inverse(T_cur_w, inv);
+  se3_mul(T_ref_w, inv, P.T_ref_cur);
+  se3_inverse(P.T_ref_cur, P.T_cur_ref);
+  se3_inverse(T_ref_w, inv);
+  se3_mul(T_cur_w, inv, P.T_cur_ref_m);
+  const double focal_length = fabs(cam.fx);
+  P.px_error_angle = atan(1.0 / (2.0 * focal_length)) * 2.0;
+}
+
+// the caller's records (svob200_seeds_update): Feature as given, T_ref_w per seed; poses derived per seed
+struct SeedSrcApi {
+  const svob200_feature_ref* ftrs; const double* T_ref_w; const double* T_cur_w;
+  __device__ __forceinline__ RefFtr get(int i) const { return ref_ftr_of(ftrs[i]); }
+  __device__ __forceinline__ void poses(const DevCam& cam, int i, const RefFtr& f, SeedPoses& P) const
+  {
+    seed_relative_poses(cam, T_ref_w + 7 * (size_t)i, T_cur_w + 7 * (size_t)f.cur_image, P);
+  }
+};
+// the tracker's compact records: keyframe k of image b lives in frame slot kf_slot[k]; its poses relative to the current
+// frame are row (k * batch + b) of the table seed_pose_table_kernel refreshed
+struct SeedSrcCompact {
+  const SeedRef* refs; const SeedPoseRec* table; const int* kf_slot; int batch;
+  __device__ __forceinline__ RefFtr get(int i) const
+  {
+    const uint4* q = reinterpret_cast<const uint4*>(&refs[i]);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    RefFtr f;
+    f.px[0] = __hiloint2double((int)a.y, (int)a.x); f.px[1] = __hiloint2double((int)a.w, (int)a.z);
+    f.f = {__hiloint2double((int)b.y, (int)b.x), __hiloint2double((int)b.w, (int)b.z), __hiloint2double((int)c.y, (int)c.x)};
+    f.ref_image = f.cur_image = (int)c.z;
+    f.level = (int)(c.w & 0xffu); f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
+    f.kf = (int)((c.w >> 8) & 0xffu);
+    f.ref_slot = __ldg(&kf_slot[f.kf]);
+    return f;
+  }
+  __device__ __forceinline__ void poses(const DevCam&, int, const RefFtr& f, SeedPoses& P) const
+  {
+    // 176 bytes shared by all the seeds of an image: consecutive threads read the same row (L1 broadcast)
+    const double2* q = reinterpret_cast<const double2*>(&table[(size_t)f.kf * batch + f.ref_image]);
+    double v[22];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) { const double2 d = __ldg(q + k); v[2 * k] = d.x; v[2 * k + 1] = d.y; }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { P.T_ref_cur[k] = v[k]; P.T_cur_ref[k] = v[7 + k]; P.T_cur_ref_m[k] = v[14 + k]; }
+    P.px_error_angle = v[21];
+  }
 };
 
-// phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry
-// (occupancy: 118 registers = 4 CTAs per SM; capping at 80 / 64 registers for 6 / 8 CTAs spills and measured 0.448 / 0.516 ms
-// against 0.440 ms — the kernel is bound by its per-thread 128-byte record loads and stores, not by resident warps)
-__global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, const double* T_ref_w_all,
-                                                         const double* T_cur_w_all, svob200_matcher_opts o, const svob200_seed* seeds,
-                                                         SeedPre* pre, EpiCold* cold, SearchTask* tasks, int* job_count)
+// one thread per (keyframe, image) of the range: the pose table of SeedSrcCompact
+__global__ void seed_pose_table_kernel(DevCam cam, int batch, int n_kfs, int image0, int n_images, const double* T_kf_w, const double* T_cur_w,
+                                       SeedPoseRec* table)
 {
-#ifndef SEEDS_GEOM_DIRECT_STORES
-  // the two 128-byte records of a seed go through shared memory (one padded slot per thread) so that a warp writes them as
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_kfs * n_images) return;
+  const int k = i / n_images, b = image0 + (i - k * n_images);
+  SeedPoses P;
+  seed_relative_poses(cam, T_kf_w + 7 * ((size_t)k * batch + b), T_cur_w + 7 * (size_t)b, P);
+  SeedPoseRec* r = &table[(size_t)k * batch + b];
+  for (int j = 0; j < 7; ++j) { r->T_ref_cur[j] = P.T_ref_cur[j]; r->T_cur_ref[j] = P.T_cur_ref[j]; r->T_cur_ref_m[j] = P.T_cur_ref_m[j]; }
+  r->px_error_angle = P.px_error_angle;
+}
+
+// phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry -> the search task
+// (occupancy: capping the registers for 6 / 8 CTAs spills and measured slower; the kernel is bound by its record traffic)
+template <class SRC>
+__global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, SRC src, svob200_matcher_opts o,
+                                                         const svob200_seed* seeds, SearchTask* tasks, int* job_count)
+{
+  // the 128-byte task of a seed goes through shared memory (one padded slot per thread) so that a warp writes it as
   // 512-byte contiguous requests instead of 32 scattered 16-byte pieces per store instruction
   struct Slot { uint4 q[9]; };                                       // 8 used; 144-byte stride: conflict-free 16-byte accesses
-  __shared__ Slot s_cold[4][32], s_task[4][32];
-#endif
+  __shared__ Slot s_task[4][32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (i == 0) *job_count = 0;                                        // consumed by the search kernel that follows on the stream
   const bool valid = i < n;
   bool has_geom = false;
   if (valid) {
-    const svob200_feature_ref f = ftrs[i];
+    const RefFtr f = src.get(i);
     const svob200_seed s = seeds[i];
-    const double* T_ref_w = T_ref_w_all + 7 * (size_t)i;
-    const double* T_cur_w = T_cur_w_all + 7 * (size_t)f.cur_image;
-    double Tcw_inv[7], T_ref_cur[7], T_cur_ref[7];
-    se3_inverse(T_cur_w, Tcw_inv);
-    se3_mul(T_ref_w, Tcw_inv, T_ref_cur);                              // depth_filter.cpp:263
-    se3_inverse(T_ref_cur, T_cur_ref);
-    SeedPre p;
-    p.status = 0; p.z_inv_min = 0.f;
-    p.t_ref_cur[0] = T_ref_cur[0]; p.t_ref_cur[1] = T_ref_cur[1]; p.t_ref_cur[2] = T_ref_cur[2];
+    SeedPoses P;
+    src.poses(cam, i, f, P);
+    int status = 0;
     const double inv_mu = 1.0 / s.mu;
-    const v3d xyz_f = se3_transform(T_cur_ref, {inv_mu * f.f[0], inv_mu * f.f[1], inv_mu * f.f[2]});
-    if (xyz_f.z < 0.0) p.status = SVOB200_SEED_BEHIND;
+    const v3d xyz_f = se3_transform(P.T_cur_ref, {inv_mu * f.f.x, inv_mu * f.f.y, inv_mu * f.f.z});
+    if (xyz_f.z < 0.0) status = SVOB200_SEED_BEHIND;
     else {
       double pxf, pyf;
       world2cam(cam, xyz_f, pxf, pyf);
-      if (!in_frame(cam, (int)pxf, (int)pyf, 0)) p.status = SVOB200_SEED_NOT_IN_FRAME;
+      if (!in_frame(cam, (int)pxf, (int)pyf, 0)) status = SVOB200_SEED_NOT_IN_FRAME;
     }
-    if (p.status == 0) {
+    if (status == 0) {
       const float z_inv_min = s.mu + sqrtf(s.sigma2);
       const float z_inv_max = fmaxf(s.mu - sqrtf(s.sigma2), 0.00000001f);
-      p.z_inv_min = z_inv_min;
-      double Trw_inv[7], T_cur_ref_m[7];
-      se3_inverse(T_ref_w, Trw_inv);
-      se3_mul(T_cur_w, Trw_inv, T_cur_ref_m);                          // matcher.cpp:216
       EpiGeom g;
-      epi_geometry(cam, f, T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &g);
-#ifdef SEEDS_GEOM_DIRECT_STORES
-      store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, &cold[i], &tasks[i]);
-#else
-      store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, reinterpret_cast<EpiCold*>(&s_cold[warp][lane]),
+      epi_geometry(cam, f, P.T_cur_ref_m, 1.0 / s.mu, 1.0 / z_inv_min, 1.0 / z_inv_max, o, &g);
+      store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, isnan(z_inv_min) ? ST_ZMIN_NAN : 0u, nullptr,
                      reinterpret_cast<SearchTask*>(&s_task[warp][lane]));
-#endif
       has_geom = true;
-    }
-#ifdef SEEDS_GEOM_DIRECT_STORES
-    else reinterpret_cast<uint4*>(&tasks[i])[0] = make_uint4(0, 0, 0, 0);      // flags = 0: nothing to search
-#endif
-    pre[i] = p;
+    } else s_task[warp][lane].q[0] = make_uint4((uint32_t)status << ST_STATUS_SHIFT, 0, 0, 0);   // nothing to search
   }
-#ifndef SEEDS_GEOM_DIRECT_STORES
   const unsigned wrote = __ballot_sync(0xffffffffu, has_geom);
-  const unsigned skip = __ballot_sync(0xffffffffu, valid && !has_geom);       // flags = 0: nothing to search
+  const unsigned skip = __ballot_sync(0xffffffffu, valid && !has_geom);
   __syncwarp();                                                                // the slots written above are read by other lanes
   const size_t i0 = (size_t)(i - lane);                                        // first seed of this warp
-  uint4* gcold = reinterpret_cast<uint4*>(cold + i0);
   uint4* gtask = reinterpret_cast<uint4*>(tasks + i0);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int e = k * 32 + lane, r = e >> 3, j = e & 7;
-    if ((wrote >> r) & 1u) { gcold[e] = s_cold[warp][r].q[j]; gtask[e] = s_task[warp][r].q[j]; }
-    else if (((skip >> r) & 1u) && j == 0) gtask[e] = make_uint4(0, 0, 0, 0);
+    if (((wrote >> r) & 1u) || (((skip >> r) & 1u) && j == 0)) gtask[e] = s_task[warp][r].q[j];
   }
-#endif
 }
 
 // geometry of stand-alone epipolar queries (svob200_epipolar_match): T_cur_ref and the depth range come from the caller
@@ -940,19 +1030,19 @@ __global__ void __launch_bounds__(128) epi_geom_kernel(DevCam cam, int n, const 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *job_count = 0;
   if (i >= n) return;
-  const svob200_feature_ref f = ftrs[i];
+  const RefFtr f = ref_ftr_of(ftrs[i]);
   EpiGeom g;
-  epi_geometry(cam, f, f.T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &g);
-  store_geometry(g, f, !g.reject, &cold[i], &tasks[i]);               // stand-alone queries always warp the patch (unless rejected)
+  epi_geometry(cam, f, ftrs[i].T_cur_ref, d[3 * i], d[3 * i + 1], d[3 * i + 2], o, &g);
+  store_geometry(g, f, !g.reject, 0u, &cold[i], &tasks[i]);           // stand-alone queries always warp the patch (unless rejected)
 }
 
-// phase 2: warp per item, PERSISTENT — the grid is sized to the machine (8 CTAs per SM) and every warp strides over the
+// phase 2: 8-lane group per item, PERSISTENT — the grid is sized to the machine and every group strides over the
 // items; the packed task of the next item is fetched (one coalesced 128-byte load) while the current one is processed,
 // and LK job slots are reserved JOB_BATCH at a time, so neither a DRAM round trip nor an atomic sits on the critical
 // path of an item.  api_results != nullptr: stand-alone queries, which also return the warped patch.
 __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevFrame* frames, int cur_slot, DevCam cam, int n, svob200_matcher_opts o,
-                                                            const SearchTask* tasks, EpiSearch* search, LkJob* jobs, int* job_count,
-                                                            svob200_epi_result* api_results)
+                                                            const SearchTask* tasks, EpiSearch* search, SeedMatch* seed_match, LkJob* jobs,
+                                                            int* job_count, svob200_epi_result* api_results)
 {
   __shared__ EpiGroupSmem SM[4 * GPW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -969,7 +1059,7 @@ __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevF
     const uint4 tq = next;
     if (i + stride < n) next = __ldg(reinterpret_cast<const uint4*>(&tasks[i + stride]) + sub);
     if (!(task_word(tq, ST_FLAGS, gbase, gmask) & ST_ACTIVE)) continue;
-    epi_search_item(frames, cur_slot, cam, o, tq, i, S, sub, gbase, gmask, jobs, job_count, slot_base, slots_left, search, api_results);
+    epi_search_item(frames, cur_slot, cam, o, tq, i, S, sub, gbase, gmask, jobs, job_count, slot_base, slots_left, search, seed_match, api_results);
     __syncwarp(gmask);
   }
   // reserved but unused job slots become empty jobs
@@ -977,39 +1067,48 @@ __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevF
 }
 
 // phase 4: thread per seed — triangulation, tau, Gaussian x Beta update, status
-__global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, const svob200_feature_ref* ftrs, double conv_thresh,
-                                                           const SeedPre* pre, const EpiCold* cold, const EpiSearch* search,
-                                                           svob200_seed* seeds, svob200_seed_obs* obs)
+template <class SRC>
+__global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, SRC src, double conv_thresh,
+                                                           const SearchTask* tasks, const SeedMatch* match, svob200_seed* seeds,
+                                                           svob200_seed_obs* obs)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const SeedPre p = pre[i];
+  const uint4 head = __ldg(reinterpret_cast<const uint4*>(&tasks[i]));          // flags, levels, epi_length
+  const uint32_t flags = head.x;
+  const int status0 = (int)((flags >> ST_STATUS_SHIFT) & 7u);
   svob200_seed_obs ob;
-  ob.status = p.status; ob.search_level = 0; ob.zmssd_best = 2000 * 64; ob.n_evals = 0; ob.z = 0; ob.px_cur[0] = ob.px_cur[1] = 0; ob.epi_length = 0;
-  if (p.status == 0) {
-    const svob200_feature_ref f = ftrs[i];
-    const EpiCold* g = &cold[i];
-    const EpiSearch sr = (!g->reject && g->mode != EPI_MODE_NONE) ? search[i] : epi_search_none();
+  ob.status = status0; ob.search_level = 0; ob.zmssd_best = 2000 * 64; ob.n_evals = 0; ob.z = 0; ob.px_cur[0] = ob.px_cur[1] = 0; ob.epi_length = 0;
+  if (status0 == 0) {
+    const RefFtr f = src.get(i);
+    SeedMatch sr;
+    if (flags & ST_ACTIVE) {
+      const uint4* q = reinterpret_cast<const uint4*>(&match[i]);
+      const uint4 a = q[0], b = q[1];
+      sr.found = (int)a.x; sr.zmssd_best = (int)a.y; sr.n_evals = (int)a.z; sr.xy_valid = (int)a.w;
+      sr.xy[0] = __hiloint2double((int)b.y, (int)b.x); sr.xy[1] = __hiloint2double((int)b.w, (int)b.z);
+    } else { sr.found = EPI_FOUND_NONE; sr.zmssd_best = 2000 * 64; sr.n_evals = 0; sr.xy_valid = 0; sr.xy[0] = sr.xy[1] = 0; }
     svob200_seed s = seeds[i];
-    ob.search_level = g->L; ob.zmssd_best = sr.zmssd_best; ob.n_evals = sr.n_evals; ob.epi_length = g->epi_length;
-    ob.px_cur[0] = sr.px_cur[0]; ob.px_cur[1] = sr.px_cur[1];
-    double T_cur_ref[7];
-    for (int k = 0; k < 7; ++k) T_cur_ref[k] = g->T_cur_ref[k];
+    ob.search_level = (int)(head.y & 0xffu); ob.zmssd_best = sr.zmssd_best; ob.n_evals = sr.n_evals;
+    ob.epi_length = __hiloint2double((int)head.w, (int)head.z);
+    if (sr.xy_valid) {
+      if (sr.found == EPI_FOUND_UV_ONLY) world2cam_uv(cam, sr.xy[0], sr.xy[1], ob.px_cur[0], ob.px_cur[1]);
+      else { ob.px_cur[0] = sr.xy[0]; ob.px_cur[1] = sr.xy[1]; }
+    }
+    SeedPoses P;
+    src.poses(cam, i, f, P);
     double z = 0;
-    if (!epi_finish(cam, f, T_cur_ref, sr, &z)) {
+    if (!epi_finish(cam, f.f, P.T_cur_ref_m, sr.found, sr.xy[0], sr.xy[1], &z)) {
       s.b++;                                                         // depth_filter.cpp:286
       ob.status = SVOB200_SEED_NO_MATCH;
     } else {
       ob.z = z;
-      const double focal_length = fabs(cam.fx);
-      const double px_error_angle = atan(1.0 / (2.0 * focal_length)) * 2.0;
-      const double T_ref_cur[7] = {p.t_ref_cur[0], p.t_ref_cur[1], p.t_ref_cur[2], 0, 0, 0, 1};
-      const double tau = compute_tau(T_ref_cur, {f.f[0], f.f[1], f.f[2]}, z, px_error_angle);
+      const double tau = compute_tau(P.T_ref_cur, f.f, z, P.px_error_angle);
       const double zmt = z - tau;
       const double tau_inverse = 0.5 * (1.0 / (0.0000001 > zmt ? 0.0000001 : zmt) - 1.0 / (z + tau));
       update_seed((float)(1. / z), (float)(tau_inverse * tau_inverse), &s);
       if ((double)sqrtf(s.sigma2) < (double)s.z_range / conv_thresh) ob.status = SVOB200_SEED_CONVERGED;
-      else if (isnan(p.z_inv_min)) ob.status = SVOB200_SEED_NAN_ERASED;
+      else if (flags & ST_ZMIN_NAN) ob.status = SVOB200_SEED_NAN_ERASED;
       else ob.status = SVOB200_SEED_UPDATED;
     }
     seeds[i] = s;
@@ -1034,7 +1133,8 @@ __global__ void __launch_bounds__(128) epi_result_kernel(DevCam cam, int n, cons
   double T_cur_ref[7];
   for (int k = 0; k < 7; ++k) T_cur_ref[k] = g->T_cur_ref[k];
   double depth = 0;
-  const bool ok = epi_finish(cam, f, T_cur_ref, sr, &depth);
+  const bool uv = sr.found == EPI_FOUND_UV_ONLY;
+  const bool ok = epi_finish(cam, {f.f[0], f.f[1], f.f[2]}, T_cur_ref, sr.found, uv ? sr.uv_best[0] : sr.px_cur[0], uv ? sr.uv_best[1] : sr.px_cur[1], &depth);
   svob200_epi_result* R = &results[i];
   R->success = ok ? 1 : 0; R->search_level = g->L; R->reject = g->reject; R->zmssd_best = sr.zmssd_best;
   R->n_evals = sr.n_evals; R->n_steps = g->n_steps_report; R->depth = ok ? depth : 0.0;
@@ -1306,7 +1406,7 @@ int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, i
   LkJob* jobs = reinterpret_cast<LkJob*>(p); p += up256(job_capacity(m) * sizeof(LkJob));
   int* count = reinterpret_cast<int*>(p);
   epi_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_d, opts, cold, tasks, count);
-  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, search, jobs, count, d_results);
+  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, search, nullptr, jobs, count, d_results);
   *launches += 2;
   LkSink sink{};
   sink.kind = LK_SINK_EPI; sink.search = search;
@@ -1316,43 +1416,66 @@ int launch_epipolar(const DevFrame* d_frames, int cur_slot, const DevCam& cam, i
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// The seed list may be processed as up to SEED_RANGES sub-ranges IN FLIGHT TOGETHER (the tracker pipelines sub-batches over two
+// streams): range r compacts its LK jobs into its own region [first_r + r * slack, ...) behind its own counter.
+static size_t job_slack() { return job_capacity(0); }
 size_t seeds_scratch_bytes(int n)
 {
   const size_t m = (size_t)(n > 0 ? n : 1);
-  return up256(m * sizeof(EpiCold)) + up256(m * sizeof(SearchTask)) + up256(m * sizeof(EpiSearch)) + up256(m * sizeof(SeedPre))
-         + up256(job_capacity(m) * sizeof(LkJob)) + 512;
+  return up256(m * sizeof(SearchTask)) + up256(m * sizeof(SeedMatch)) + up256((m + SEED_RANGES * job_slack()) * sizeof(LkJob)) + 512;
 }
 
-// DepthFilter::updateSeeds for n seeds: geometry (thread) -> search (warp, persistent) -> LK (thread per job) -> update (thread).
-// marks: optional 3 events recorded between the four kernels.
+// DepthFilter::updateSeeds for n seeds: geometry (thread) -> search (group, persistent) -> LK (thread per job) -> update (thread).
+// The scratch was sized for scratch_total seeds and is indexed by absolute seed number; `src`, d_seeds and d_obs already point at
+// seed `first`.  marks: optional 3 events recorded between the four kernels.
+template <class SRC>
+static int seeds_update_impl(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const SRC& src,
+                             svob200_matcher_opts opts, double conv_thresh, svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch,
+                             int scratch_total, int first, int range, cudaStream_t s, long long* launches, cudaEvent_t* marks)
+{
+  if (n <= 0) return 0;
+  if (range < 0 || range >= SEED_RANGES) return -1;
+  const size_t m = (size_t)(scratch_total > 0 ? scratch_total : 1);
+  char* p = static_cast<char*>(d_scratch);
+  SearchTask* tasks = reinterpret_cast<SearchTask*>(p) + first; p += up256(m * sizeof(SearchTask));
+  SeedMatch* match = reinterpret_cast<SeedMatch*>(p) + first; p += up256(m * sizeof(SeedMatch));
+  LkJob* jobs = reinterpret_cast<LkJob*>(p) + first + (size_t)range * job_slack(); p += up256((m + SEED_RANGES * job_slack()) * sizeof(LkJob));
+  int* count = reinterpret_cast<int*>(p) + range;
+  seeds_geom_kernel<SRC><<<(n + 127) / 128, 128, 0, s>>>(cam, n, src, opts, d_seeds, tasks, count);
+  if (marks) cudaEventRecord(marks[0], s);
+  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, nullptr, match, jobs, count, nullptr);
+  if (marks) cudaEventRecord(marks[1], s);
+  *launches += 2;
+  LkSink sink{};
+  sink.kind = LK_SINK_SEED; sink.seed_match = match;
+  if (launch_lk_refine(d_frames, cur_slot, jobs, count, (int)job_capacity((size_t)n), opts.align_max_iter, sink, s, launches)) return -1;
+  if (marks) cudaEventRecord(marks[2], s);
+  seeds_finish_kernel<SRC><<<(n + 127) / 128, 128, 0, s>>>(cam, n, src, conv_thresh, tasks, match, d_seeds, d_obs);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const svob200_feature_ref* d_ftrs,
                         const double* d_T_ref_w, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
                         svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first,
                         cudaStream_t s, long long* launches, cudaEvent_t* marks)
 {
-  // d_ftrs / d_T_ref_w / d_seeds / d_obs already point at seed `first`; the scratch was sized for
-  // scratch_total seeds and is indexed by absolute seed number
+  SeedSrcApi src{d_ftrs, d_T_ref_w, d_T_cur_w};
+  return seeds_update_impl(d_frames, cur_slot, cam, n, src, opts, conv_thresh, d_seeds, d_obs, d_scratch, scratch_total, first, 0, s, launches, marks);
+}
+
+int launch_seeds_update_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const SeedRef* d_refs, const double* d_T_kf_w,
+                                const int* d_kf_slot, int batch, int n_kfs, SeedPoseRec* d_pose_table, int image0, int n_images,
+                                const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
+                                svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first, int range,
+                                cudaStream_t s, long long* launches, cudaEvent_t* marks)
+{
   if (n <= 0) return 0;
-  const size_t m = (size_t)(scratch_total > 0 ? scratch_total : 1);
-  char* p = static_cast<char*>(d_scratch);
-  EpiCold* cold = reinterpret_cast<EpiCold*>(p) + first; p += up256(m * sizeof(EpiCold));
-  SearchTask* tasks = reinterpret_cast<SearchTask*>(p) + first; p += up256(m * sizeof(SearchTask));
-  EpiSearch* search = reinterpret_cast<EpiSearch*>(p) + first; p += up256(m * sizeof(EpiSearch));
-  SeedPre* pre = reinterpret_cast<SeedPre*>(p) + first; p += up256(m * sizeof(SeedPre));
-  LkJob* jobs = reinterpret_cast<LkJob*>(p) + first; p += up256(job_capacity(m) * sizeof(LkJob));
-  int* count = reinterpret_cast<int*>(p);
-  seeds_geom_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, d_T_ref_w, d_T_cur_w, opts, d_seeds, pre, cold, tasks, count);
-  if (marks) cudaEventRecord(marks[0], s);
-  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, search, jobs, count, nullptr);
-  if (marks) cudaEventRecord(marks[1], s);
-  *launches += 2;
-  LkSink sink{};
-  sink.kind = LK_SINK_EPI; sink.search = search;
-  if (launch_lk_refine(d_frames, cur_slot, jobs, count, (int)job_capacity((size_t)n), opts.align_max_iter, sink, s, launches)) return -1;
-  if (marks) cudaEventRecord(marks[2], s);
-  seeds_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(cam, n, d_ftrs, conv_thresh, pre, cold, search, d_seeds, d_obs);
+  const int rows = n_kfs * n_images;
+  seed_pose_table_kernel<<<(rows + 127) / 128, 128, 0, s>>>(cam, batch, n_kfs, image0, n_images, d_T_kf_w, d_T_cur_w, d_pose_table);
   ++*launches;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  SeedSrcCompact src{d_refs, d_pose_table, d_kf_slot, batch};
+  return seeds_update_impl(d_frames, cur_slot, cam, n, src, opts, conv_thresh, d_seeds, d_obs, d_scratch, scratch_total, first, range, s, launches, marks);
 }
 
 int launch_update_seed(int n, const float* d_x, const float* d_tau2, svob200_seed* d_seeds, cudaStream_t s, long long* launches)

@@ -9,6 +9,7 @@
 // with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
 // H2D of the small per-step inputs and one D2H of the per-sequence results.
 #include <cstdlib>
+#include <atomic>
 #include "ctx_internal.h"
 
 namespace {
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(128) step_stats_kernel(const int* ftr_off, con
     else if (st == SVOB200_SEED_CONVERGED) ++conv;
     else if (st == SVOB200_SEED_NO_MATCH) ++fail;
     else ++skipped;
-    if (reseed && (st == SVOB200_SEED_CONVERGED || st == SVOB200_SEED_NAN_ERASED)) seeds[i] = init;
+    // reseed 1: finished seeds start afresh (stationary workload); 2: EVERY seed starts afresh every frame (young-seed regime)
+    if (reseed == 2 || (reseed && (st == SVOB200_SEED_CONVERGED || st == SVOB200_SEED_NAN_ERASED))) seeds[i] = init;
   }
   __shared__ int s[5];
   if (tid < 5) s[tid] = 0;
@@ -116,8 +118,15 @@ struct svob200_tracker {
   int N = 0, S = 0, max_per = 0;
   int *d_ftr_off = nullptr, *d_seed_off = nullptr, *d_ftr_image = nullptr, *d_match_ok = nullptr;
   uint8_t* d_has_point = nullptr;
-  svob200_feature_ref *d_ftrs = nullptr, *d_seed_ftrs = nullptr;
-  double *d_pt_world = nullptr, *d_T_kf_ftr = nullptr, *d_T_kf_seed = nullptr;
+  svob200_feature_ref* d_ftrs = nullptr;
+  double *d_pt_world = nullptr, *d_T_kf_ftr = nullptr;
+  // depth-filter seeds: 32-byte compact records + keyframe tables (pose per (keyframe, image), frame slot per keyframe)
+  SeedRef* d_seed_refs = nullptr;
+  double* d_T_kf = nullptr;            // [max_kfs][batch][7]
+  int* d_kf_slot = nullptr;            // [max_kfs]
+  SeedPoseRec* d_seed_poses = nullptr; // [max_kfs][batch], refreshed every step
+  int n_kfs = 1;
+  int max_kfs = 1;
   svob200_seed* d_seeds = nullptr;
   double *d_step_in = nullptr;      // [T_last_w 7B | last_px 2N]
   double *d_xyz = nullptr, *d_T_init = nullptr, *d_T_cur = nullptr, *d_depth_ref = nullptr, *d_px_in = nullptr, *d_px_out = nullptr;
@@ -131,6 +140,13 @@ struct svob200_tracker {
   std::vector<void*> owned;
   std::vector<int> h_ftr_off, h_seed_off;
   int chunk = 256;                     // sequences per H2D/compute pipeline chunk (host mode)
+  // Big batches run as sub-ranges of sequences alternating between the context's stream and `range_stream`: the kernels of
+  // one sub-range fill the SMs while the other sits in a latency-bound stage (the sparse-alignment wave, whose length is its
+  // slowest problem's Gauss-Newton chain) or in a kernel's tail; results are bit-identical (same kernels, same per-sequence work).
+  int ranges = 2;                      // sub-ranges per step in device mode (direct launches); 1 = one range on one stream
+  int min_range = 128;                 // ... but never fewer sequences than this per sub-range
+  cudaStream_t range_stream = nullptr;
+  cudaEvent_t range_ev[2] = {};
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   // chain mode (svob200_tracker_set_chain): reprojector grid rules + pose optimiser instead of refining every map point
@@ -200,7 +216,16 @@ int svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batc
                            svob200_tracker** out)
 {
   if (!ctx || !cam || !aopts || !mopts || !out || batch <= 0) return fail(ctx, SVOB200_ERR_ARG, "tracker_create: bad arguments");
-  static int64_t uid = 0;
+  // a level outside the pyramid would make the kernels dereference DevFrame.lvl[l] == nullptr (a sticky device fault):
+  // the same range checks as svob200_sparse_align / svob200_match_direct, before anything is launched
+  if (n_levels < 1 || n_levels > 7) return fail(ctx, SVOB200_ERR_ARG, "tracker_create: n_levels %d outside [1, 7]", n_levels);
+  if (aopts->min_level < 0 || aopts->min_level > aopts->max_level || aopts->max_level >= n_levels)
+    return fail(ctx, SVOB200_ERR_ARG, "tracker_create: alignment level range [%d,%d] outside the %d-level pyramid", aopts->min_level, aopts->max_level, n_levels);
+  if (mopts->max_search_level < 0 || mopts->max_search_level >= n_levels)
+    return fail(ctx, SVOB200_ERR_ARG, "tracker_create: max_search_level %d outside the %d-level pyramid", mopts->max_search_level, n_levels);
+  if (cam->width <= 0 || cam->height <= 0) return fail(ctx, SVOB200_ERR_ARG, "tracker_create: bad camera size");
+  static std::atomic<int64_t> uid_counter{0};
+  const int64_t uid = ++uid_counter;
   svob200_tracker* t = new svob200_tracker();
   t->ctx = ctx; t->cam = *cam; t->batch = batch; t->n_levels = n_levels; t->aopts = *aopts; t->mopts = *mopts;
   t->conv_thresh = conv_thresh; t->reseed = reseed;
@@ -208,12 +233,15 @@ int svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batc
   t->seed_init.a = 10; t->seed_init.b = 10; t->seed_init.mu = (float)(1.0 / depth_mean); t->seed_init.z_range = (float)(1.0 / depth_min);
   t->seed_init.sigma2 = t->seed_init.z_range * t->seed_init.z_range / 36;
   if (const char* e = getenv("SVOB200_TRACKER_CHUNK")) { if (atoi(e) > 0) t->chunk = atoi(e); }   // sequences per H2D/compute pipeline chunk (A/B runs)
+  if (const char* e = getenv("SVOB200_TRACKER_RANGES")) { if (atoi(e) > 0) t->ranges = std::min(atoi(e), (int)SEED_RANGES); }   // A/B runs
   if (const char* e = getenv("SVOB200_TRACKER_FORK")) t->graph_fork = atoi(e) != 0;   // 0: captured steps stay one chain of kernels (A/B runs)
   if (const char* e = getenv("SVOB200_TRACKER_GRAPH")) t->graph_max_batch = atoi(e) > 0 ? atoi(e) : 0;   // 0 disables graph replay; N = largest batch replayed as a graph
-  ++uid;
   t->fid_kf = -(uid * 4 + 1); t->fid_last = -(uid * 4 + 2); t->fid_cur = -(uid * 4 + 3);
   for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur})
-    if (int e = svob200_frame_create(ctx, id, batch, cam->width, cam->height, n_levels)) { delete t; return e; }
+    if (int e = svob200_frame_create(ctx, id, batch, cam->width, cam->height, n_levels)) {
+      for (int64_t id2 : {t->fid_kf, t->fid_last, t->fid_cur}) if (id2 != id && find_frame(ctx, id2)) svob200_frame_release(ctx, id2);
+      delete t; return e;
+    }
   *out = t;
   return SVOB200_OK;
 }
@@ -229,6 +257,8 @@ void svob200_tracker_destroy(svob200_tracker* t)
   for (auto e : t->chunk_ev) cudaEventDestroy(e);
   for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  if (t->range_stream) cudaStreamDestroy(t->range_stream);
+  for (auto e : t->range_ev) if (e) cudaEventDestroy(e);
   if (t->fork_stream) cudaStreamDestroy(t->fork_stream);
   for (auto e : t->fork_ev) if (e) cudaEventDestroy(e);
   for (int k = 0; k <= kNumStages; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
@@ -243,19 +273,28 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
 {
   if (!t || !imgs || !T_kf_w || !ftr_offsets || !seed_offsets) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
-  if (t->N || t->S) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_keyframe: keyframe already set (create a new tracker)");
+  if (t->d_stats) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_keyframe: keyframe already set (svob200_tracker_add_keyframe inserts further ones)");
   const int B = t->batch;
-  if (int e = svob200_frame_upload(ctx, t->fid_kf, imgs, stride, nullptr, SVOB200_MEM_HOST)) return e;
   const int N = ftr_offsets[B], S = seed_offsets[B];
+  // validate everything BEFORE the first launch / allocation
+  if (N < 0 || S < 0 || ftr_offsets[0] != 0 || seed_offsets[0] != 0) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: bad offsets");
+  for (int b = 0; b < B; ++b)
+    if (ftr_offsets[b + 1] < ftr_offsets[b] || seed_offsets[b + 1] < seed_offsets[b]) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: offsets must be non-decreasing");
+  if (N > 0 && (!kf_px || !kf_level || !pt_world)) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: null feature arrays with %d features", N);
+  if (S > 0 && (!seed_px || !seed_level)) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: null seed arrays with %d seeds", S);
+  for (int i = 0; i < N; ++i) if (kf_level[i] < 0 || kf_level[i] >= t->n_levels) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: kf_level[%d] = %d outside the pyramid", i, kf_level[i]);
+  for (int i = 0; i < S; ++i) if (seed_level[i] < 0 || seed_level[i] >= t->n_levels) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: seed_level[%d] = %d outside the pyramid", i, seed_level[i]);
+  if (int e = svob200_frame_upload(ctx, t->fid_kf, imgs, stride, nullptr, SVOB200_MEM_HOST)) return e;
   t->N = N; t->S = S;
   t->h_ftr_off.assign(ftr_offsets, ftr_offsets + B + 1);
   t->h_pt_world.assign(pt_world, pt_world + 3 * (size_t)N);
   t->h_seed_off.assign(seed_offsets, seed_offsets + B + 1);
   for (int b = 0; b < B; ++b) t->max_per = std::max(t->max_per, ftr_offsets[b + 1] - ftr_offsets[b]);
   const int slot = svob200_frame_slot(ctx, t->fid_kf);
-  std::vector<svob200_feature_ref> ftrs(N), sftrs(S);
+  std::vector<svob200_feature_ref> ftrs(N);
+  std::vector<SeedRef> srefs(S);
   std::vector<int> image(N);
-  std::vector<double> Tf((size_t)7 * N), Ts((size_t)7 * S);
+  std::vector<double> Tf((size_t)7 * N);
   std::vector<svob200_seed> seeds(S, t->seed_init);
   for (int b = 0; b < B; ++b) {
     for (int i = ftr_offsets[b]; i < ftr_offsets[b + 1]; ++i) {
@@ -267,16 +306,15 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
       memcpy(&Tf[(size_t)7 * i], T_kf_w + 7 * b, 7 * sizeof(double));
     }
     for (int i = seed_offsets[b]; i < seed_offsets[b + 1]; ++i) {
-      svob200_feature_ref& f = sftrs[i];
-      memset(&f, 0, sizeof(f));
-      f.ref_frame_id = slot; f.ref_image = b; f.cur_image = b; f.level = seed_level[i]; f.type = 0;
-      f.px[0] = seed_px[2 * i]; f.px[1] = seed_px[2 * i + 1]; f.grad[0] = 1.0; f.grad[1] = 0.0;
-      memcpy(&Ts[(size_t)7 * i], T_kf_w + 7 * b, 7 * sizeof(double));
+      SeedRef& r = srefs[i];
+      memset(&r, 0, sizeof(r));
+      r.px[0] = seed_px[2 * i]; r.px[1] = seed_px[2 * i + 1]; r.image = b; r.level = (uint8_t)seed_level[i]; r.kf = 0; r.batch_id = 0; r.state = 0;
     }
   }
 #define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
   DA(t->d_ftr_off, B + 1); DA(t->d_seed_off, B + 1); DA(t->d_ftr_image, N); DA(t->d_match_ok, N); DA(t->d_has_point, N);
-  DA(t->d_ftrs, N); DA(t->d_seed_ftrs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N); DA(t->d_T_kf_seed, 7 * (size_t)S);
+  DA(t->d_ftrs, N); DA(t->d_seed_refs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N);
+  DA(t->d_T_kf, 7 * (size_t)B * t->max_kfs); DA(t->d_kf_slot, t->max_kfs); DA(t->d_seed_poses, (size_t)B * t->max_kfs);
   DA(t->d_seeds, S); DA(t->d_step_in, 7 * (size_t)B + 2 * (size_t)N); DA(t->d_xyz, 3 * (size_t)N); DA(t->d_T_init, 7 * (size_t)B);
   DA(t->d_T_cur, 7 * (size_t)B); DA(t->d_depth_ref, N); DA(t->d_px_in, 2 * (size_t)N); DA(t->d_px_out, 2 * (size_t)N);
   DA(t->d_align, B); DA(t->d_obs, S); DA(t->d_stats, B);
@@ -298,25 +336,31 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   CU(cudaMemcpyAsync(t->d_ftr_image, image.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(t->d_has_point, 1, N ? N : 1, s));
   CU(cudaMemcpyAsync(t->d_ftrs, ftrs.data(), sizeof(svob200_feature_ref) * N, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(t->d_seed_ftrs, sftrs.data(), sizeof(svob200_feature_ref) * S, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_seed_refs, srefs.data(), sizeof(SeedRef) * S, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_T_kf, T_kf_w, sizeof(double) * 7 * B, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_kf_slot, &slot, sizeof(int), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(t->d_pt_world, pt_world, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(t->d_T_kf_ftr, Tf.data(), sizeof(double) * 7 * N, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(t->d_T_kf_seed, Ts.data(), sizeof(double) * 7 * S, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(t->d_seeds, seeds.data(), sizeof(svob200_seed) * S, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
-  // Feature ctor: f = cam2world(px), for map features and seed features (device, bit-identical to the host formula)
+  // Feature ctor: f = cam2world(px) for map features and seed features, on the device (bit-identical to the host formula)
   {
-    std::vector<double> px(2 * (size_t)std::max(N, S)), f(3 * (size_t)std::max(N, S)), dummy_pt(3 * (size_t)std::max(N, S), 0.0), xyz(3 * (size_t)std::max(N, S));
-    std::vector<int> img0(std::max(N, S), 0);
+    const int M = std::max(N, S);
+    std::vector<double> px(2 * (size_t)M), f(3 * (size_t)M), dummy_pt(3 * (size_t)M, 0.0), xyz(3 * (size_t)M);
+    std::vector<int> img0(M, 0);
     const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
     for (int pass = 0; pass < 2; ++pass) {
       const int n = pass == 0 ? N : S;
-      std::vector<svob200_feature_ref>& v = pass == 0 ? ftrs : sftrs;
       if (!n) continue;
-      for (int i = 0; i < n; ++i) { px[2 * i] = v[i].px[0]; px[2 * i + 1] = v[i].px[1]; }
+      for (int i = 0; i < n; ++i) { px[2 * i] = pass == 0 ? ftrs[i].px[0] : srefs[i].px[0]; px[2 * i + 1] = pass == 0 ? ftrs[i].px[1] : srefs[i].px[1]; }
       if (int e = svob200_features_prepare(ctx, &t->cam, n, px.data(), dummy_pt.data(), img0.data(), 1, ident, f.data(), xyz.data(), SVOB200_MEM_HOST)) return e;
-      for (int i = 0; i < n; ++i) { v[i].f[0] = f[3 * i]; v[i].f[1] = f[3 * i + 1]; v[i].f[2] = f[3 * i + 2]; }
-      CU(cudaMemcpyAsync(pass == 0 ? t->d_ftrs : t->d_seed_ftrs, v.data(), sizeof(svob200_feature_ref) * n, cudaMemcpyHostToDevice, s));
+      if (pass == 0) {
+        for (int i = 0; i < n; ++i) { ftrs[i].f[0] = f[3 * i]; ftrs[i].f[1] = f[3 * i + 1]; ftrs[i].f[2] = f[3 * i + 2]; }
+        CU(cudaMemcpyAsync(t->d_ftrs, ftrs.data(), sizeof(svob200_feature_ref) * n, cudaMemcpyHostToDevice, s));
+      } else {
+        for (int i = 0; i < n; ++i) { srefs[i].f[0] = f[3 * i]; srefs[i].f[1] = f[3 * i + 1]; srefs[i].f[2] = f[3 * i + 2]; }
+        CU(cudaMemcpyAsync(t->d_seed_refs, srefs.data(), sizeof(SeedRef) * n, cudaMemcpyHostToDevice, s));
+      }
       CU(cudaStreamSynchronize(s));
     }
   }
@@ -375,11 +419,12 @@ static DevFrame frame_view(const DevFrame& f, int c0, int cnt)
 // all stages of one step for the sequences [c0, c1) on the compute stream (level 0 of cur is in place)
 // out_px / out_ok: optional device destinations of the refined pixels / match flags (device-mode callers): copied as soon as
 // the matching stage is done, beside the depth filter in a forked step
+// s: the stream this range runs on; range: its index among the ranges of the step that may be in flight together
 static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last, const double* d_last_px, bool marks,
-                     double* out_px = nullptr, int* out_ok = nullptr)
+                     double* out_px = nullptr, int* out_ok = nullptr, cudaStream_t s = nullptr, int range = 0)
 {
   svob200_ctx* ctx = t->ctx;
-  cudaStream_t s = ctx->stream;
+  if (!s) s = ctx->stream;
   const DevCam cam = to_cam(&t->cam);
   FrameRec* last = find_frame(ctx, t->fid_last);
   FrameRec* cur = find_frame(ctx, t->fid_cur);
@@ -453,9 +498,9 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   if (out_px) CU(cudaMemcpyAsync(out_px + 2 * (size_t)f0, t->d_px_out + 2 * (size_t)f0, sizeof(double) * 2 * (size_t)nf, cudaMemcpyDeviceToDevice, s));
   if (out_ok) CU(cudaMemcpyAsync(out_ok + f0, t->d_match_ok + f0, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToDevice, s));
   // 6. DepthFilter::updateSeeds(cur)
-  if (launch_seeds_update(ctx->d_table, cur->slot, cam, ns, t->d_seed_ftrs + s0, t->d_T_kf_seed + 7 * (size_t)s0, t->d_T_cur, t->mopts,
-                          t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, s_seeds, &ctx->launches,
-                          (marks && t->profiling) ? &t->ev[8] : nullptr))
+  if (launch_seeds_update_compact(ctx->d_table, cur->slot, cam, ns, t->d_seed_refs + s0, t->d_T_kf, t->d_kf_slot, t->batch, t->n_kfs, t->d_seed_poses, c0, cnt, t->d_T_cur, t->mopts,
+                                  t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, range, s_seeds, &ctx->launches,
+                                  (marks && t->profiling) ? &t->ev[8] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
   if (s_seeds != s) { CU(cudaEventRecord(t->fork_ev[3], s_seeds)); CU(cudaStreamWaitEvent(s, t->fork_ev[3], 0)); }
   MARK(11);
@@ -495,11 +540,30 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
       CU(cudaStreamCreateWithFlags(&t->fork_stream, cudaStreamNonBlocking));
       for (auto& e : t->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    // direct launches of a big batch: sub-ranges alternate between two streams (chain mode keeps one range: its reprojector
+    // scratch is shared)
+    int n_ranges = 1;
+    if (!use_graph && !t->profiling && t->chain_cell <= 0) n_ranges = std::max(1, std::min(t->ranges, B / std::max(1, t->min_range)));
+    if (n_ranges > 1 && !t->range_stream) {
+      CU(cudaStreamCreateWithFlags(&t->range_stream, cudaStreamNonBlocking));
+      for (auto& e : t->range_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     const int rc = graph_or_direct(t, use_graph, key, [&]() -> int {
-      t->forking = use_graph && t->graph_fork;     // only a capture runs this body when use_graph is set
-      const int e0 = run_range(t, 0, B, T_last_w, last_px, true, px_refined, match_ok);
-      t->forking = false;
-      if (e0) return e0;
+      if (n_ranges > 1) {
+        CU(cudaEventRecord(t->range_ev[0], s));
+        CU(cudaStreamWaitEvent(t->range_stream, t->range_ev[0], 0));
+        for (int r = 0; r < n_ranges; ++r) {
+          const int c0 = (int)((long long)B * r / n_ranges), c1 = (int)((long long)B * (r + 1) / n_ranges);
+          if (int e0 = run_range(t, c0, c1, T_last_w, last_px, false, px_refined, match_ok, (r & 1) ? t->range_stream : s, r)) return e0;
+        }
+        CU(cudaEventRecord(t->range_ev[1], t->range_stream));
+        CU(cudaStreamWaitEvent(s, t->range_ev[1], 0));
+      } else {
+        t->forking = use_graph && t->graph_fork;     // only a capture runs this body when use_graph is set
+        const int e0 = run_range(t, 0, B, T_last_w, last_px, true, px_refined, match_ok);
+        t->forking = false;
+        if (e0) return e0;
+      }
       if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
       return 0;
     });
@@ -569,9 +633,17 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
       CU(cudaStreamCreateWithFlags(&t->fork_stream, cudaStreamNonBlocking));
       for (auto& e : t->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    // chunks alternate between the two compute streams (see `ranges`), each waiting for its own frame copy
+    const bool two_streams = n_chunks > 1 && t->ranges > 1 && t->chain_cell <= 0 && n_chunks <= (int)SEED_RANGES;
+    if (two_streams && !t->range_stream) {
+      CU(cudaStreamCreateWithFlags(&t->range_stream, cudaStreamNonBlocking));
+      for (auto& e : t->range_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (two_streams) { CU(cudaEventRecord(t->range_ev[0], s)); CU(cudaStreamWaitEvent(t->range_stream, t->range_ev[0], 0)); }
     for (int c = 0; c < n_chunks; ++c) {
       const int c0 = c * chunk, c1 = std::min(B, c0 + chunk);
-      CU(cudaStreamWaitEvent(s, t->chunk_ev[c], 0));
+      cudaStream_t sc = (two_streams && (c & 1)) ? t->range_stream : s;
+      CU(cudaStreamWaitEvent(sc, t->chunk_ev[c], 0));
       if (use_graph) {
         FrameRec* last = find_frame(ctx, t->fid_last);
         const std::vector<uintptr_t> key = {2, (uintptr_t)t->fid_cur, (uintptr_t)t->fid_last, (uintptr_t)r->f.lvl[0], (uintptr_t)r->f.pitch[0],
@@ -583,8 +655,9 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
           return e0;
         });
         if (rc) return rc;
-      } else if (int e = run_range(t, c0, c1, d_T_last, d_last_px, n_chunks == 1)) return e;
+      } else if (int e = run_range(t, c0, c1, d_T_last, d_last_px, n_chunks == 1, nullptr, nullptr, sc, two_streams ? c : 0)) return e;
     }
+    if (two_streams) { CU(cudaEventRecord(t->range_ev[1], t->range_stream)); CU(cudaStreamWaitEvent(s, t->range_ev[1], 0)); }
     uint8_t* ho = t->h_pinned + ((in_bytes + 255) & ~(size_t)255);
     uint8_t* h_stats = ho; uint8_t* h_px = h_stats + sizeof(svob200_step_stats) * B; uint8_t* h_ok = h_px + sizeof(double) * 2 * (size_t)N;
     if (stats) CU(cudaMemcpyAsync(h_stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToHost, s));
@@ -608,7 +681,7 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
   return SVOB200_OK;
 }
 
-int svob200_tracker_launches_per_step(void) { return 13; }
+int svob200_tracker_launches_per_step(void) { return 14; }
 
 // raw svob200_align_result records of the most recent step (diagnostics: tools/align_timing.py)
 int svob200_tracker_debug_align(svob200_tracker* t, svob200_align_result* out)

@@ -7,9 +7,12 @@ import numpy as np
 from . import synth
 
 
-def select_features(cells, thr, n):
-    """First n cells (cell-index order, like FastDetector::detect's output order) whose score > thr."""
+def select_features(cells, thr, n, recycle=False):
+    """First n cells (cell-index order, like FastDetector::detect's output order) whose score > thr.
+    recycle: a view with fewer corners repeats the ones it has, so that every sequence carries the same load (bench only)."""
     good = cells[cells["score"].astype(np.float64) > thr]
+    if len(good) < n and recycle and len(good) > 0:
+        good = np.resize(good, n)
     if len(good) < n:
         raise ValueError("only %d corners above %.1f, need %d" % (len(good), thr, n))
     good = good[:n]
@@ -35,10 +38,10 @@ def project_many(cfg, T_f_w, pts):
     return np.stack([cfg["fx"] * pc[:, 0] / pc[:, 2] + cfg["cx"], cfg["fy"] * pc[:, 1] / pc[:, 2] + cfg["cy"]], 1)
 
 
-def keyframe_setup(cfg, T_kf_w, ftr_cells, seed_cells, ftr_thr, seed_thr, plane_z=2.0):
+def keyframe_setup(cfg, T_kf_w, ftr_cells, seed_cells, ftr_thr, seed_thr, plane_z=2.0, recycle=False):
     """Map features + seeds of one keyframe from two detector passes (coarse grid / fine grid)."""
-    kf_px, kf_level = select_features(ftr_cells, ftr_thr, cfg["n_features"])
-    seed_px, seed_level = select_features(seed_cells, seed_thr, cfg["n_seeds"])
+    kf_px, kf_level = select_features(ftr_cells, ftr_thr, cfg["n_features"], recycle)
+    seed_px, seed_level = select_features(seed_cells, seed_thr, cfg["n_seeds"], recycle)
     pt_world = np.array([synth.backproject_to_plane(cfg, T_kf_w, p, plane_z) for p in kf_px])
     return dict(kf_px=kf_px, kf_level=kf_level, pt_world=pt_world, seed_px=seed_px, seed_level=seed_level)
 

@@ -44,9 +44,14 @@ CHAIN_CELL, CHAIN_MAX_FTS = 30, 120   # Config::gridSize / maxFts defaults (conf
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "dropin"],
+                    help="b200: the CUDA path; reference: the reference's own CPU code; dropin: the reference's C++ harness linked over the "
+                         "B200 drop-in (libsvo_dropin.so) next to the same harness over the reference's TUs, per-frame latency")
+    ap.add_argument("--seed-regime", default="steady", choices=["steady", "young"],
+                    help="steady: finished seeds are re-initialised (stationary workload, most seeds near convergence); young: EVERY seed is "
+                         "re-initialised after every frame, so each update walks a long epipolar segment (north_star kernel 4)")
     ap.add_argument("--seqs", type=int, default=4096, help="total number of independent sequences (all GPUs)")
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences in the CPU sample (0 = 4 per host thread)")
     ap.add_argument("--no-latency", action="store_true")
@@ -118,21 +123,25 @@ def select_batch(cells, thr, n):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
+    """nvidia-smi polled every 20 ms in a child process; stop(t0, t1) keeps the samples whose timestamp falls inside the
+    load window [t0, t1] (host wall clock: warm-up + timed steps)."""
+
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -140,20 +149,25 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, n_all = [], [], set(), 0
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                clk, cmax = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+            n_all += 1
+            if t0 is not None and not (t0 <= ts <= t1):
+                continue
+            sm.append(clk); mx.append(cmax)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "samples_total": n_all}
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -165,28 +179,36 @@ class ClockSampler:
 CPU_FRAMES_PER_STEP = 16   # a CPU "step" = this many consecutive frames of every sampled sequence (bounded sample, ~10-30 core-s per run)
 
 
-def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False):
+def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False, regime="steady", o3=False, dropin=False):
     """Times the front-end step of `n_seqs` independent sequences on the host cores.  Uses the real
-    reference (oracle/_ref/libsvo_ref.so) when it was built, else the C restatement.  One timed step =
-    `inner` consecutive frames of every sequence, one worker task per sequence."""
+    reference (oracle/_ref/libsvo_ref.so; o3: the -O3 / AVX2 / FMA build of the same sources; dropin: the same harness over
+    the B200 drop-in) when it was built, else the C restatement.  One timed step = `inner` consecutive frames of every
+    sequence, one worker task per sequence.  Every frame is timed on its own (perf_counter around the step call), and the
+    reference harness splits it per operator with std::chrono::steady_clock (BASELINE.md section 3)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle.pyoracle import Oracle, Ref, Cam, OracleSeq, RefSeq
-    oracle, ref = Oracle(), Ref()
+    cfg = synth.CONFIGS[cfg_name]
+    oracle, ref = Oracle(), Ref(o3=o3, dropin=dropin)
     kind = "reference" if ref.available() else "port"
+    if dropin:
+        if not ref.available():
+            raise RuntimeError("oracle/_ref/libsvo_dropin.so is missing")
+        kind = "dropin"
     cam = Cam.make(cfg["w"], cfg["h"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"])
     tex = synth.make_texture(TEX_SIZE)
     idx = (KF_INDEX,) + POOL_INDICES
-    poses = poses_for(range(n_seqs), idx)
-    fc, ft, sc, st = frontend.DETECT[CFG_NAME]
+    poses = poses_for(range(4096, 4096 + n_seqs) if n_seqs == 1 else range(n_seqs), idx)
+    fc, ft, sc, st = frontend.DETECT[cfg_name]
+    reseed = 2 if regime == "young" else 1
 
     def setup(i):
         imgs = [oracle.synth_render(tex, PPM, PLANE_Z, cam, poses[i, k]) for k in range(len(idx))]
         pyr = oracle.pyramid(imgs[0], cfg["n_levels"])
         _, fcells = oracle.fast_detect(pyr, cfg["n_pyr"], fc, ft)
         _, scells = oracle.fast_detect(pyr, cfg["n_pyr"], sc, st)
-        kf = frontend.keyframe_setup(cfg, poses[i, 0], fcells, scells, ft, st, PLANE_Z)
-        args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, DEPTH_MEAN, DEPTH_MIN, 1)
-        s = RefSeq(ref, *args) if kind == "reference" else OracleSeq(oracle, *args)
+        kf = frontend.keyframe_setup(cfg, poses[i, 0], fcells, scells, ft, st, PLANE_Z, recycle=True)
+        args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, DEPTH_MEAN, DEPTH_MIN, reseed)
+        s = RefSeq(ref, *args) if kind != "port" else OracleSeq(oracle, *args)
         s.set_keyframe(imgs[0], poses[i, 0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
         if chain:
             s.set_chain(CHAIN_CELL, CHAIN_MAX_FTS, 1)
@@ -194,6 +216,7 @@ def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chai
         last_px = [frontend.project_many(cfg, poses[i, 1 + k], kf["pt_world"]) for k in range(len(POOL_INDICES))]
         return s, imgs[1:], last_px
 
+    frame_s = [[] for _ in range(n_seqs)]
     with ThreadPoolExecutor(threads) as ex:
         seqs = list(ex.map(setup, range(n_seqs)))
         order = ping_pong(len(POOL_INDICES), (warmup + steps) * inner)
@@ -202,7 +225,9 @@ def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chai
             st = None
             for j in range(k * inner, (k + 1) * inner):
                 a, b = order[j], order[j + 1]
+                t0 = time.perf_counter()
                 st = seqs[i][0].step(seqs[i][1][b], poses[i, 1 + a], seqs[i][2][a])
+                frame_s[i].append(time.perf_counter() - t0)
             return st
 
         def step_all(k):
@@ -210,14 +235,41 @@ def cpu_arm(cfg, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chai
 
         for k in range(warmup):
             step_all(k)
+        for f in frame_s:
+            del f[:]
+        if kind != "port":
+            for s, _, _ in seqs:
+                s.timing()
         t0 = time.perf_counter()
         for k in range(warmup, warmup + steps):
             stats = step_all(k)
         dt = time.perf_counter() - t0
     tracked = float(np.mean([s.n_tracked for s in stats]))
+    ops = None
+    if kind != "port":
+        acc = {}
+        for s, _, _ in seqs:
+            for k, v in s.timing().items():
+                acc[k] = acc.get(k, 0.0) + v
+        n = max(acc.pop("steps"), 1)
+        ops = {k + "_ms": round(v / n * 1e3, 4) for k, v in acc.items()}
     for s, _, _ in seqs:
         s.close()
-    return dict(kind=kind, fps=n_seqs * steps * inner / dt, seconds=dt, n_seqs=n_seqs, tracked=tracked, inner=inner)
+    ms = np.concatenate([np.array(f) for f in frame_s]) * 1e3
+    return dict(kind=kind, fps=n_seqs * steps * inner / dt, seconds=dt, n_seqs=n_seqs, tracked=tracked, inner=inner,
+                p50_ms=float(np.median(ms)), p95_ms=float(np.percentile(ms, 95)), mean_ms=float(ms.mean()), frames=int(len(ms)), per_operator=ops)
+
+
+def cpu_latency(cfg_name, chain=False, regime="steady", o3=False, frames=48):
+    """The reference's native single-stream mode: ONE sequence on ONE host thread, every frame timed; p50 / p95 over `frames`
+    frames after 16 warm-up frames, with the harness's steady_clock split per operator."""
+    r = cpu_arm(cfg_name, 1, frames // 16, 1, 1, chain=chain, regime=regime, o3=o3)
+    out = {"p50_ms": round(r["p50_ms"], 4), "p95_ms": round(r["p95_ms"], 4), "mean_ms": round(r["mean_ms"], 4), "kind": r["kind"], "cores": 1,
+           "build": "-O3 -march=x86-64-v3 (AVX2 + FMA), contraction allowed" if o3 else "-O2, the reference's CMake flags (baseline x86-64, no FMA)",
+           "sample": "1 sequence x %d frames timed one by one (+16 warm-up frames), 1 thread, depth filter synchronous" % r["frames"]}
+    if r["per_operator"]:
+        out["per_operator_mean"] = r["per_operator"]
+    return out
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -233,7 +285,7 @@ def pinned_array(ctx, shape, dtype):
 class GpuWorkload:
     """Everything the timed loops need, resident: tracker, frame pool on device + pinned host, per-step inputs."""
 
-    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME, chain=False):
+    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME, chain=False, regime="steady"):
         self.ctx, self.capi, self.cfg = ctx, capi, cfg
         B = len(seq_ids)
         self.B = B
@@ -277,7 +329,7 @@ class GpuWorkload:
         pt_world = backproject_many(cfg, poses[:, 0], kf_px)
         self.kf = dict(kf_px=kf_px, kf_level=kf_level, pt_world=pt_world, seed_px=seed_px, seed_level=seed_level)
         self.trk = capi.Tracker(ctx, cam, B, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0,
-                                DEPTH_MEAN, DEPTH_MIN, 1)
+                                DEPTH_MEAN, DEPTH_MIN, 2 if regime == "young" else 1)
         self.trk.set_keyframe(self.kf_host, poses[:, 0], np.arange(B + 1) * N, kf_px.reshape(-1, 2), kf_level.reshape(-1),
                               pt_world.reshape(-1, 3), np.arange(B + 1) * S, seed_px.reshape(-1, 2), seed_level.reshape(-1))
         if chain:
@@ -330,6 +382,21 @@ class GpuWorkload:
             self.trk.step_raw(self.pool_host[b][1], w, self.in_host[a][0], self.in_host[a][1], self.stats_ptr, mem)
 
 
+def seed_workload_of(obs, capi, regime):
+    """What the depth filter did in the last step (svob200_seed_obs of every seed): the epipolar-search load."""
+    ev = obs["n_evals"]
+    searched = obs["status"] >= capi.SEED_NO_MATCH
+    direct = searched & (obs["epi_length"] < 2.0)
+    walk = searched & (obs["epi_length"] >= 2.0)
+    n = max(len(obs), 1)
+    return {"regime": regime, "n_evals_mean": round(float(ev.mean()), 2), "n_evals_p50": float(np.percentile(ev, 50)), "n_evals_p95": float(np.percentile(ev, 95)),
+            "n_evals_mean_walk": round(float(ev[walk].mean()), 2) if walk.any() else 0.0,
+            "frac_direct": round(float(direct.sum()) / n, 4), "frac_walk": round(float(walk.sum()) / n, 4),
+            "frac_not_searched": round(float((~searched).sum()) / n, 4),
+            "frac_updated": round(float((obs["status"] >= capi.SEED_UPDATED).sum()) / n, 4),
+            "note": "direct = epipolar segment shorter than 2 px (align2D at the midpoint, matcher.cpp:257-278); walk = ZMSSD over the segment"}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -344,7 +411,7 @@ def run_b200(args, rank, world, local_rank):
     total, per, rng = sharding.shard(args.seqs, rank, world)     # contiguous block partition
     seq_ids = list(rng)
     t_setup = time.time()
-    wl = GpuWorkload(ctx, capi, cfg, seq_ids, chain=args.chain)
+    wl = GpuWorkload(ctx, capi, cfg, seq_ids, chain=args.chain, regime=args.seed_regime)
     t_setup = time.time() - t_setup
     K, W = args.steps, args.warmup
     order = ping_pong(len(POOL_INDICES), 2 * (W + K) + 8)
@@ -358,18 +425,25 @@ def run_b200(args, rank, world, local_rank):
         return sharding.max_over_ranks(x, world, "cuda")
 
     # ---------------- value: inputs resident in HBM, CUDA events on the launching stream
+    import datetime
     wl.reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        time.sleep(0.25)                    # nvidia-smi needs ~0.2 s before its first sample
+    t_load0 = datetime.datetime.now()
     for k in range(W):
         wl.step(order, k, capi.MEM_DEVICE)
     barrier()
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.timer_start()
     for k in range(W, W + K):
         wl.step(order, k, capi.MEM_DEVICE)
     ms = ctx.timer_stop_ms()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    t_load1 = datetime.datetime.now()
+    clocks = sampler.stop(t_load0, t_load1) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed steps, %.0f ms" % ((t_load1 - t_load0).total_seconds() * 1e3)
     launches = ctx.launch_count() - launches0
     ms = max_over_ranks(ms)
     value = total * K / (ms * 1e-3)
@@ -386,6 +460,7 @@ def run_b200(args, rank, world, local_rank):
     obs = wl.trk.seed_obs()
     wl.trk.enable_profiling(False)
     mean_evals = float(obs["n_evals"].mean())
+    seed_workload = seed_workload_of(obs, capi, args.seed_regime)
     N, S = cfg["n_features"], cfg["n_seeds"]
     iters_mean = float(stats_dev_copy["align_iters"].mean())
     # algorithmic bytes per launch (SURVEY.md §8d per-unit figures x units per launch)
@@ -491,6 +566,7 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": "C5: %d independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each), "
                                    "block-sharded over %d GPU(s); step = 1 frame of every sequence" % (total, N, S, world),
                        "sequences_total": total, "sequences_per_gpu": per, "frame_pool": list(POOL_INDICES),
+                       "seed_regime": args.seed_regime,
                        "step": ("chain: reprojector grid rules (cell %d, maxFts %d) + pose optimiser between alignment and the depth filter"
                                 % (CHAIN_CELL, CHAIN_MAX_FTS)) if args.chain else "refine every map point of the keyframe (batched superset of the reprojector)",
                        "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (per * cfg["w"] * cfg["h"] / 1e6)},
@@ -499,7 +575,9 @@ def run_b200(args, rank, world, local_rank):
                     "h2d_GBps_per_gpu": round(wl.h2d_bytes / (e2e_s / K) / 1e9, 2), "pcie_h2d_GBps_measured": round(pcie, 2),
                     "note": "host-buffer path is PCIe-bound: the frame upload (307,200 B/frame) is chunked and overlapped with compute"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(K, 1)),
-            "clocks": clocks, "roofline": roofline, "roofline_pyramid": roofline_pyr, "stages": stages, "sequence_stats": seq_stats,
+            "clocks": clocks, "roofline": roofline, "roofline_pyramid": roofline_pyr, "stages": stages, "seed_workload": seed_workload,
+            "zmssd_evals_per_s": round(float(obs["n_evals"].sum()) / max(stage_acc.get("seeds_search", 0.0), 1e-9) * 1e3, 1),
+            "sequence_stats": seq_stats,
             "setup_s": round(t_setup, 1),
         }
     return out, ctx, wl
@@ -703,10 +781,10 @@ LATENCY_DESC = {"C2": "C2: one 640x480 sequence, 4-level pyramid, 120 features, 
                 "C4": "C4: one 1920x1080 sequence (phone-shaped), 5-level pyramid, 1,000 features, 10,000 seeds"}
 
 
-def latency_single(ctx, capi, name, n_frames=60, chain=False):
+def latency_single(ctx, capi, name, n_frames=60, chain=False, regime="steady"):
     """Single-stream: one sequence, per-frame latency through the C ABI with host buffers (p50) and resident."""
     cfg = synth.CONFIGS[name]
-    wl = GpuWorkload(ctx, capi, cfg, [4096], cfg_name=name, chain=chain)
+    wl = GpuWorkload(ctx, capi, cfg, [4096], cfg_name=name, chain=chain, regime=regime)
     order = ping_pong(len(POOL_INDICES), n_frames + 30)
     res = {}
     for mode, mem in (("host_buffers", capi.MEM_HOST), ("resident", capi.MEM_DEVICE)):
@@ -738,6 +816,27 @@ def latency_single(ctx, capi, name, n_frames=60, chain=False):
     return res
 
 
+def dropin_line(args, cfg, threads):
+    """--impl dropin: the reference's C++ harness (oracle/ref_harness.cpp: new Frame -> SparseImgAlign::run -> Matcher::findMatchDirect
+    per map point -> DepthFilter::addFrame) linked over android_svo_b200/host/svo_b200_dropin.cpp, i.e. every operator call of the
+    reference's own control flow lands in CUDA through the C ABI, timed per frame on ONE host thread next to the same harness over the
+    reference's TUs.  Each drop-in call pays its own H2D / D2H and a synchronisation: this is the number a
+    maintainer gets by swapping the five TUs and changing nothing else."""
+    frames = max(16, min(args.steps, 10) * 16)
+    d = cpu_arm(CFG_NAME, 1, frames // 16, 1, 1, chain=args.chain, regime=args.seed_regime, dropin=True)
+    r = cpu_arm(CFG_NAME, 1, frames // 16, 1, 1, chain=args.chain, regime=args.seed_regime)
+    return {"impl": "dropin", "metric": "per-frame latency of the reference's own front-end loop with the hot-path TUs swapped for the B200 drop-in",
+            "value": round(d["p50_ms"], 4), "unit": "ms", "n_gpus": 1, "steps": frames, "warmup": 16, "ms_per_step": round(d["mean_ms"], 4),
+            "higher_is_better": False, "scaling": "none", "vs_baseline": None, "dtype": "u8 pixels / f32 photometric / f64 geometry", "data": "synthetic",
+            "config": {"workload": "one C2 sequence (640x480, 4-level pyramid, %d map features, %d seeds), one host thread" % (cfg["n_features"], cfg["n_seeds"]),
+                       "seed_regime": args.seed_regime, "step": "chain" if args.chain else "refine every map point of the keyframe"},
+            "dropin": {"p50_ms": round(d["p50_ms"], 4), "p95_ms": round(d["p95_ms"], 4), "frames_per_s": round(d["fps"], 1), "per_operator_mean": d["per_operator"],
+                       "tracked": d["tracked"]},
+            "reference": {"p50_ms": round(r["p50_ms"], 4), "p95_ms": round(r["p95_ms"], 4), "frames_per_s": round(r["fps"], 1), "per_operator_mean": r["per_operator"],
+                          "kind": r["kind"], "cores": 1, "tracked": r["tracked"]},
+            "speedup_p50": round(r["p50_ms"] / d["p50_ms"], 3)}
+
+
 _REAL_STDOUT = None
 
 
@@ -767,12 +866,17 @@ def main():
     global METRIC
     if args.chain:
         METRIC = "front-end frames/s (pyramid + sparse align + reprojector + pose optimiser + seed update), batched C2 sequences"
-    if args.impl == "reference":
+    if args.impl in ("reference", "dropin"):
         # the reference's own CPU implementation of the path, all host threads, rank 0 only
+        # (dropin: the SAME harness linked over the B200 drop-in: one sequence, one host thread, every operator call lands in CUDA)
         if rank != 0:
             return
+        if args.impl == "dropin":
+            line = dropin_line(args, cfg, threads)
+            emit(json.dumps(line))
+            return
         n = args.cpu_seqs or max(8, 4 * threads)
-        r = cpu_arm(cfg, n, args.steps, args.warmup, threads, chain=args.chain)
+        r = cpu_arm(CFG_NAME, n, args.steps, args.warmup, threads, chain=args.chain, regime=args.seed_regime)
         line = {"impl": "reference", "metric": METRIC, "value": round(r["fps"], 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["seconds"] / args.steps * 1e3, 3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 pixels / f32 photometric / f64 geometry",
@@ -780,10 +884,13 @@ def main():
                 "config": {"workload": "C5: independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each); "
                                        "step = 1 frame of every sequence of the sample" % (cfg["n_features"], cfg["n_seeds"]),
                            "sequences_total": args.seqs, "sample_sequences": n, "frames_per_sequence_per_step": r["inner"],
+                           "seed_regime": args.seed_regime,
                            "step": "chain (reprojector + pose optimiser)" if args.chain else "refine every map point of the keyframe"},
                 "cpu_baseline": {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                  "sample": "%d sequences x %d steps x %d frames (+%d warm-up steps), %d host threads, %.1f s wall"
-                                           % (n, args.steps, r["inner"], args.warmup, threads, r["seconds"])},
+                                           % (n, args.steps, r["inner"], args.warmup, threads, r["seconds"]),
+                                 "per_frame_ms_on_a_loaded_core": {"p50": round(r["p50_ms"], 3), "p95": round(r["p95_ms"], 3)},
+                                 "per_operator_mean": r["per_operator"]},
                 "e2e": {"value": round(r["fps"], 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "tracked_mean": r["tracked"]}
         emit(json.dumps(line))
@@ -804,20 +911,26 @@ def main():
             out["latency"] = {}
             for name in ("C2", "C3", "C4"):
                 try:
-                    out["latency"][name] = latency_single(ctx, capi, name, chain=args.chain)
+                    out["latency"][name] = latency_single(ctx, capi, name, chain=args.chain, regime=args.seed_regime)
                 except Exception as e:   # pragma: no cover
                     out["latency"][name] = {"error": str(e)}
-        if world == 1 and not args.no_cpu_baseline and not args.no_latency:
-            # the reference's per-frame latency on ONE host core, same C2 sequence shape (the reference's native single-stream mode)
-            r1 = cpu_arm(cfg, 1, 3, 1, 1, chain=args.chain)
-            out["latency"]["C2"]["cpu_reference_1_thread"] = {"p50_ms": round(1e3 / r1["fps"], 4), "kind": r1["kind"],
-                                                              "sample": "1 sequence x 3 steps x %d frames, 1 thread" % r1["inner"]}
+                if world == 1 and not args.no_cpu_baseline and "error" not in out["latency"][name]:
+                    # the reference's per-frame latency on ONE host core, same sequence shape (its native single-stream mode): true
+                    # per-frame p50 / p95 with the per-operator steady_clock split, for the -O2 build and the -O3 / AVX2 one
+                    try:
+                        out["latency"][name]["cpu_reference_1_thread"] = cpu_latency(name, chain=args.chain, regime=args.seed_regime,
+                                                                                     frames=48 if name != "C4" else 32)
+                        if name == "C2":
+                            out["latency"][name]["cpu_reference_1_thread_o3"] = cpu_latency(name, chain=args.chain, regime=args.seed_regime, o3=True)
+                    except Exception as e:   # pragma: no cover
+                        out["latency"][name]["cpu_reference_1_thread"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_seqs or max(8, 4 * threads)
-            r = cpu_arm(cfg, n, 10, 1, threads, chain=args.chain)
+            r = cpu_arm(CFG_NAME, n, 10, 1, threads, chain=args.chain, regime=args.seed_regime)
             out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                    "sample": "%d sequences x 10 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
-                                             % (n, r["inner"], threads, r["seconds"])}
+                                             % (n, r["inner"], threads, r["seconds"]),
+                                   "per_operator_mean": r["per_operator"]}
         emit(json.dumps(out))
     if world > 1:
         import torch.distributed as dist

@@ -251,9 +251,10 @@ int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n
  * (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), restricted to the hot-path operators:
  *   pyramid(cur) -> SparseImgAlign::run(last, cur) -> Matcher::findMatchDirect for every map point of
  *   the keyframe -> DepthFilter::updateSeeds(cur) for the keyframe's seeds,
- * for a batch of independent sequences, 11 kernel launches on one stream, no host round trip.
- * Finished seeds (converged / NaN) are re-initialised when `reseed` is set, which keeps the
- * per-frame workload stationary for benchmarking (0 = leave them, the caller mutates its list). */
+ * for a batch of independent sequences, 13 kernel launches, no host round trip.
+ * Finished seeds (converged / NaN) are re-initialised when `reseed` is 1, which keeps the
+ * per-frame workload stationary for benchmarking (0 = leave them, the caller mutates its list); with reseed = 2 EVERY seed is
+ * re-initialised after every step: the "young seed" regime, where each update walks a long epipolar segment. */
 typedef struct svob200_tracker svob200_tracker;
 typedef struct {
   double T_cur_w[7];       /* pose after sparse alignment */

@@ -51,6 +51,7 @@ def build(force=False):
         stale = not os.path.exists(ref_so) or any(
             os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(ref_so)
             for f in ("ref_harness.cpp", "ref_harness_map.cpp", "shim/cv_fast.cpp", "shim/opencv2/opencv.hpp", "svo_oracle.c"))
+        stale = stale or not os.path.exists(os.path.join(OUT, "libsvo_ref_o3.so"))
         if force or stale:
             subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
         # the same harness over the C++ drop-in (needs the product library to link against)
@@ -343,10 +344,11 @@ class Ref:
     machines where it was never built (e.g. a checkout without /root/reference and without the
     prebuilt .so)."""
 
-    def __init__(self, nosse=False, dropin=False):
+    def __init__(self, nosse=False, dropin=False, o3=False):
         # dropin: the SAME C++ harness linked over android_svo_b200/host/svo_b200_dropin.cpp instead of the
         # reference's hot-path TUs (oracle/_ref/libsvo_dropin.so) — every operator call lands in CUDA
-        name = "libsvo_dropin.so" if dropin else ("libsvo_ref_nosse.so" if nosse else "libsvo_ref.so")
+        # o3: the timing-only -O3 / AVX2 / FMA build (never used for parity)
+        name = "libsvo_dropin.so" if dropin else ("libsvo_ref_nosse.so" if nosse else ("libsvo_ref_o3.so" if o3 else "libsvo_ref.so"))
         self.path = os.path.join(OUT, name)
         self.lib = None
         if os.path.exists(self.path):
@@ -653,6 +655,13 @@ class RefSeq(_SeqBase):
 
     def set_last(self, img):
         self.lib.svo_ref_seq_set_last(self.h, _p(u8(img), c_u8p))
+
+    def timing(self):
+        """steady_clock seconds per operator since the last call: dict(pyramid, align, refine, seeds, steps)"""
+        out = np.zeros(5)
+        self.lib.svo_ref_seq_get_timing.argtypes = [C.c_void_p, c_dp]
+        self.lib.svo_ref_seq_get_timing(self.h, _p(out, c_dp))
+        return dict(pyramid=out[0], align=out[1], refine=out[2], seeds=out[3], steps=int(out[4]))
 
     def set_chain(self, cell_size=30, max_fts=120, pose_opt=1):
         """the reference's own Reprojector + pose_optimizer between alignment and the depth filter"""

@@ -27,6 +27,7 @@
 #include <svo/reprojector.h>
 #include <svo/pose_optimizer.h>
 #include <map>
+#include <chrono>
 #include <cstring>
 #ifdef SVOB200_DROPIN
 // Same harness, linked over android_svo_b200/host/svo_b200_dropin.cpp INSTEAD OF the reference's
@@ -496,7 +497,12 @@ struct RefSeq {
   svo::Map* map = NULL;
   Reprojector* reproj = NULL;
   int chain_pose_opt = 0;
+  // std::chrono::steady_clock seconds per operator, accumulated over the steps since the last svo_ref_seq_get_timing
+  // (BASELINE.md section 3): [0] Frame ctor (pyramid), [1] SparseImgAlign::run, [2] reprojection / refinement (+ pose optimiser in
+  // chain mode), [3] DepthFilter::addFrame (updateSeeds); [4] = number of steps
+  double timing[5] = {0, 0, 0, 0, 0};
 };
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void* svo_ref_seq_create(const int* wh, const double* k, int max_level, int min_level, int n_iter, double conv_thresh,
                          float depth_mean, float depth_min, int reseed)
@@ -572,7 +578,9 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
 {
   RefSeq* s = (RefSeq*)h;
   memset(st, 0, sizeof(*st));
+  const double t0 = now_s();
   FramePtr cur(new Frame(s->cam, aligned_copy(cur_img, s->cam->width(), s->cam->height()), 1.0));
+  const double t1 = now_s();
   FramePtr last = s->last;
   last->T_f_w_ = to_se3(T_last_w);
   for (auto f : last->fts_) delete f;
@@ -584,8 +592,10 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
     last->fts_.push_back(f);
   }
   cur->T_f_w_ = last->T_f_w_;                                       // frame_handler_mono.cpp:175
+  const double t2 = now_s();
   AlignProbe al(s->max_level, s->min_level, s->n_iter);
   st->n_tracked = (int)al.run(last, cur);
+  const double t3 = now_s();
   al.fetch_evals();
   st->chi2 = al.chi2();
   for (size_t l = 0; l < al.evals.size(); ++l) st->align_iters += al.evals[l];
@@ -622,7 +632,10 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   }
   }
   s->conv_points.clear();
+  const double t4 = now_s();
   s->df->addFrame(cur);                                             // synchronous updateSeeds
+  const double t5 = now_s();
+  s->timing[0] += t1 - t0; s->timing[1] += t3 - t2; s->timing[2] += t4 - t3; s->timing[3] += t5 - t4; s->timing[4] += 1.0;
   st->n_seeds_converged = (int)s->conv_points.size();
   st->n_seeds_updated = st->n_seeds_failed = st->n_seeds_skipped = -1;   // not observable through the reference API
   std::vector<Feature*> finished;
@@ -633,8 +646,19 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
     for (auto f : finished) seen[f] = 1;
     for (auto f : s->seed_ftrs) if (!seen.count(f)) finished.push_back(f);
   }
-  if (s->reseed) for (auto f : finished) s->df->getSeeds().push_back(Seed(f, s->depth_mean, s->depth_min));
+  if (s->reseed == 2) {
+    // "young seed" regime: EVERY seed starts afresh every frame (long epipolar segments), in the original order
+    s->df->getSeeds().clear();
+    for (auto f : s->seed_ftrs) s->df->getSeeds().push_back(Seed(f, s->depth_mean, s->depth_min));
+  } else if (s->reseed) for (auto f : finished) s->df->getSeeds().push_back(Seed(f, s->depth_mean, s->depth_min));
   s->last = cur;
+}
+
+// seconds per operator since the last call (5 doubles, see RefSeq::timing); resets the accumulators
+void svo_ref_seq_get_timing(void* h, double* out)
+{
+  RefSeq* s = (RefSeq*)h;
+  for (int k = 0; k < 5; ++k) { out[k] = s->timing[k]; s->timing[k] = 0; }
 }
 
 // state of every seed by original index; seeds no longer in the list get a = -1

@@ -233,7 +233,8 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
     else if (status == SVO_SEED_CONVERGED) st->n_seeds_converged++;
     else if (status == SVO_SEED_NO_MATCH) st->n_seeds_failed++;
     else st->n_seeds_skipped++;
-    if (s->reseed && (status == SVO_SEED_CONVERGED || status == SVO_SEED_NAN_ERASED)) s->seeds[i] = s->seed_init;
+    /* reseed 1: finished seeds start afresh (stationary workload); 2: EVERY seed starts afresh every frame (young-seed regime) */
+    if (s->reseed == 2 || (s->reseed && (status == SVO_SEED_CONVERGED || status == SVO_SEED_NAN_ERASED))) s->seeds[i] = s->seed_init;
   }
   /* the current frame becomes the last frame */
   { uint8_t* t0 = s->last0; uint8_t* tu = s->lastu; s->last0 = s->cur0; s->lastu = s->curu; s->cur0 = t0; s->curu = tu; }
