@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SVOB200_LIB") or os.path.join(HERE, "lib", "libsvob20
 MAX_LEVELS = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 ROUND_TRUNC, ROUND_SSE2 = 0, 1
-SEED_BEHIND, SEED_NOT_IN_FRAME, SEED_NO_MATCH, SEED_UPDATED, SEED_CONVERGED, SEED_NAN_ERASED = 1, 2, 3, 4, 5, 6
+SEED_BEHIND, SEED_NOT_IN_FRAME, SEED_NO_MATCH, SEED_UPDATED, SEED_CONVERGED, SEED_NAN_ERASED, SEED_TOO_OLD = 1, 2, 3, 4, 5, 6, 7
 
 c_u8p = C.POINTER(C.c_uint8)
 c_dp = C.POINTER(C.c_double)
@@ -122,6 +122,11 @@ def load_library():
     L.svob200_tracker_destroy.argtypes = [V]
     L.svob200_tracker_set_keyframe.argtypes = [V, V, C.c_int, V, V, V, V, V, V, V, V]
     L.svob200_tracker_set_last.argtypes = [V, V, C.c_int, C.c_int]
+    L.svob200_tracker_set_seed_pool.argtypes = [V, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.svob200_tracker_set_detector.argtypes = [V, C.c_int, C.c_int, C.c_double]
+    L.svob200_tracker_add_keyframe.argtypes = [V, V, V, V, V]
+    L.svob200_tracker_get_seed_refs.argtypes = [V, V, V, V, V, V]
+    L.svob200_tracker_num_seed_slots.argtypes = [V]
     L.svob200_tracker_step.argtypes = [V, V, C.c_int, V, V, V, V, V, C.c_int]
     L.svob200_tracker_get_seeds.argtypes = [V, V]
     L.svob200_tracker_enable_profiling.argtypes = [V, C.c_int]
@@ -171,6 +176,8 @@ EXPORTED_SYMBOLS = [
     "svob200_depth_from_triangulation", "svob200_debug_chi2_chain",
     "svob200_frame_upload_yuv420", "svob200_reproject_map", "svob200_pose_opt_opts_default", "svob200_pose_optimize",
     "svob200_points_optimize", "svob200_seeds_initialize", "svob200_tracker_debug_align", "svob200_tracker_set_chain",
+    "svob200_tracker_set_seed_pool", "svob200_tracker_set_detector", "svob200_tracker_add_keyframe", "svob200_tracker_get_seed_refs",
+    "svob200_tracker_num_seed_slots",
 ]
 
 
@@ -502,6 +509,30 @@ class Tracker:
         args = [a(T_kf_w, np.float64), fo, a(kf_px, np.float64), a(kf_level, np.int32), a(pt_world, np.float64), so,
                 a(seed_px, np.float64), a(seed_level, np.int32)]
         self.ctx._ck(self.L.svob200_tracker_set_keyframe(self.h, _ptr(imgs), imgs.shape[-1], *[_ptr(x) for x in args]))
+        self.S = int(self.L.svob200_tracker_num_seed_slots(self.h))          # pool slots (>= the seeds given)
+
+    # ---- keyframe insertion inside the tracker
+    def set_seed_pool(self, capacity_per_sequence, max_keyframes=4, max_n_kfs=3, reseed=3):
+        self.ctx._ck(self.L.svob200_tracker_set_seed_pool(self.h, int(capacity_per_sequence), int(max_keyframes), int(max_n_kfs), int(reseed)))
+
+    def set_detector(self, cell, levels, thr):
+        self.ctx._ck(self.L.svob200_tracker_set_detector(self.h, int(cell), int(levels), float(thr)))
+
+    def add_keyframe(self, depth_mean, depth_min):
+        """the frame of the most recent step becomes a keyframe: returns (new seeds, dropped corners) per sequence"""
+        dm = np.ascontiguousarray(np.broadcast_to(np.asarray(depth_mean, np.float32), (self.batch,)))
+        dn = np.ascontiguousarray(np.broadcast_to(np.asarray(depth_min, np.float32), (self.batch,)))
+        n_new = np.zeros(self.batch, np.int32); n_drop = np.zeros(self.batch, np.int32)
+        self.ctx._ck(self.L.svob200_tracker_add_keyframe(self.h, _ptr(dm), _ptr(dn), _ptr(n_new), _ptr(n_drop)))
+        return n_new, n_drop
+
+    def seed_refs(self):
+        """(px[S,2], level, kf, batch_id, state) of every pool slot; state 0 = alive"""
+        S = self.S
+        px = np.zeros((max(S, 1), 2)); lv = np.zeros(max(S, 1), np.int32); kf = np.zeros(max(S, 1), np.int32)
+        bt = np.zeros(max(S, 1), np.int32); st = np.zeros(max(S, 1), np.int32)
+        self.ctx._ck(self.L.svob200_tracker_get_seed_refs(self.h, _ptr(px), _ptr(lv), _ptr(kf), _ptr(bt), _ptr(st)))
+        return px[:S], lv[:S], kf[:S], bt[:S], st[:S]
 
     def set_last(self, imgs, mem=MEM_HOST, stride=None):
         if mem == MEM_HOST:

@@ -99,7 +99,9 @@ void svob200_ctx_destroy(svob200_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  ctx_join_aux(ctx);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& a : ctx->aux) cudaEventDestroy(a.second);
   for (auto& kv : ctx->frames) if (kv.second.base) cudaFree(kv.second.base);
   if (ctx->d_table) cudaFree(ctx->d_table);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -111,7 +113,13 @@ void svob200_ctx_destroy(svob200_ctx* ctx)
 }
 
 const char* svob200_last_error(const svob200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device?)"; }
-int svob200_ctx_sync(svob200_ctx* ctx) { if (!ctx) return SVOB200_ERR_ARG; CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+int svob200_ctx_sync(svob200_ctx* ctx)
+{
+  if (!ctx) return SVOB200_ERR_ARG;
+  if (int e = ctx_join_aux(ctx)) return e;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 void* svob200_ctx_stream(svob200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 long long svob200_ctx_launch_count(const svob200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -125,6 +133,7 @@ int svob200_ctx_timer_start(svob200_ctx* ctx)
 int svob200_ctx_timer_stop_ms(svob200_ctx* ctx, float* ms)
 {
   if (!ctx || !ms || !ctx->ev0) return SVOB200_ERR_ARG;
+  if (int e = ctx_join_aux(ctx)) return e;            // the stop event covers work still in flight on a tracker's depth-filter stream
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   CU(cudaEventSynchronize(ctx->ev1));
   CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
@@ -918,6 +927,7 @@ int svob200_dev_free(svob200_ctx* ctx, void* dptr) { if (!ctx) return SVOB200_ER
 int svob200_dev_upload(svob200_ctx* ctx, void* dptr, const void* host, size_t bytes)
 {
   if (!ctx) return SVOB200_ERR_ARG;
+  if (int e = ctx_join_aux(ctx)) return e;
   CU(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -925,6 +935,7 @@ int svob200_dev_upload(svob200_ctx* ctx, void* dptr, const void* host, size_t by
 int svob200_dev_download(svob200_ctx* ctx, void* host, const void* dptr, size_t bytes)
 {
   if (!ctx) return SVOB200_ERR_ARG;
+  if (int e = ctx_join_aux(ctx)) return e;
   CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;

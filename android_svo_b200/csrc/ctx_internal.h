@@ -48,6 +48,9 @@ struct svob200_ctx {
   uint8_t* h_stage = nullptr; size_t h_cap = 0;
   GrowBuf d_stage, d_scratch, d_scratch2;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // streams on which work of this context may still be in flight after an asynchronous call returned (a tracker's
+  // depth-filter stream): every synchronising entry point joins them into `stream` first (ctx_join_aux)
+  std::vector<std::pair<cudaStream_t, cudaEvent_t>> aux;
   std::mutex mu;
 };
 
@@ -59,6 +62,28 @@ inline int fail(svob200_ctx* c, int code, const char* fmt, ...)
   return code;
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+// make ctx->stream wait for everything enqueued so far on the auxiliary streams
+inline int ctx_join_aux(svob200_ctx* ctx)
+{
+  for (auto& a : ctx->aux) {
+    CU(cudaEventRecord(a.second, a.first));
+    CU(cudaStreamWaitEvent(ctx->stream, a.second, 0));
+  }
+  return 0;
+}
+inline int ctx_add_aux(svob200_ctx* ctx, cudaStream_t s)
+{
+  cudaEvent_t e = nullptr;
+  CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  ctx->aux.push_back({s, e});
+  return 0;
+}
+inline void ctx_remove_aux(svob200_ctx* ctx, cudaStream_t s)
+{
+  for (size_t i = 0; i < ctx->aux.size(); ++i)
+    if (ctx->aux[i].first == s) { cudaEventDestroy(ctx->aux[i].second); ctx->aux.erase(ctx->aux.begin() + i); return; }
+}
 
 inline DevCam to_cam(const svob200_camera* c) { DevCam d; d.width = c->width; d.height = c->height; d.fx = c->fx; d.fy = c->fy; d.cx = c->cx; d.cy = c->cy; return d; }
 

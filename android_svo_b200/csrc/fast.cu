@@ -5,16 +5,18 @@
 // OpenCV 4.5.4 features2d (fast.cpp / fast_score.cpp — third party, restated from the published
 // algorithm and pinned against python cv2 in tests/golden); vk::shiTomasiScore vision.cpp:113-154.
 //
-// B200 design: one pass over each detected level, a CTA per 128x32 tile staged in shared memory with 16-byte loads.
-//   A. byte-SIMD candidate test, FOUR pixels per thread: the 7x12-byte neighbourhood of a 4-pixel group sits in 21 registers,
-//      every ring position is one PRMT, and two pixels at a time go through VIMNMX.U16x2.  The test is OpenCV's own necessary
-//      condition: an arc of 9 of 16 contains one pixel of EVERY opposite pair (k, k+8), so all 8 pairs need a darker (or all a
-//      brighter) member: max over the pairs of min(pair) < v - t, or min over the pairs of max(pair) > v + t.
-//      It passes 33 % of the pixels of the bench texture (24 % are corners) where two adjacent compass points passed 58 %.
-//   B. thread per candidate: score = max over the 16 arcs of the minimum of |v - ring| over the arc (sliding-window minimum
-//      with 3-input VIMNMX3: 40 instructions), which is both the exact FAST-9 test (score > t) and cv's cornerScore - only the
-//      candidate's polarity is evaluated (a darker and a brighter arc of 9 cannot coexist on 16 pixels).
-//   C. thread per corner: strict 3x3 non-max suppression on the score tile.
+// B200 design: one pass over each detected level, a CTA per 120x30 tile staged in shared memory.  Everything per-pixel is
+// byte-SIMD on 16-bit lanes, FOUR pixels per thread, one warp per tile row, no data-dependent branch:
+//   A. score of EVERY pixel.  The 7x12-byte neighbourhood of a 4-pixel group sits in 21 registers; ring position k of the four
+//      pixels is one PRMT; X_k = 256 + v - ring_k on two lanes per word.  cv's cornerScore is S - 1 with
+//         S = max( max over the 16 arcs of 9 of  min over the arc of (v - ring) ,  max over the arcs of  min of (ring - v) )
+//      and the pixel is a FAST-9 corner iff S > t, so one sliding-window minimum AND maximum of X over the circular ring (3+3+3
+//      taps with VIMNMX3.U16x2: min over an arc of (ring - v) = 256 - max over the arc of X) gives test and score at once.
+//      A warp whose 128 pixels all fail OpenCV's necessary condition on four opposite pairs skips the rest (natural images).
+//      The dense score tile holds S - 1 for every pixel; values below t mark non-corners and never win a comparison against
+//      a corner's score (>= t), so the non-maximum suppression needs no mask.
+//   C. strict 3x3 non-max suppression, again four pixels per thread on 16-bit lanes; survivors (>= t and > all 8 neighbours)
+//      go to a compact keypoint list.
 //   D. thread per keypoint: grid cell, occupancy, Shi-Tomasi by byte dot products (dp4a on funnel-shifted words: the
 //      integer sums are exact, as the reference's float sums are), one 64-bit atomicMax per keypoint.
 // The reference's sequential "first strictly-greater wins" rule over (level, y, x) order becomes
@@ -25,16 +27,17 @@
 
 namespace {
 
-constexpr int TW = 128, TH = 32;                         // output tile
+constexpr int TW = 120, TH = 30;                         // output tile: the score tile (1-px ring, rounded to groups) is 128 x 32
 constexpr int HALO = 5;                                  // rows above / below (Shi-Tomasi reads y-5 .. y+4)
-constexpr int XOFF = 16;                                 // the staged tile starts 16 columns left of the output tile (16-byte aligned chunks)
-constexpr int PH = TH + 2 * HALO;                        // 42 staged rows
-constexpr int PP = TW + 2 * XOFF;                        // 160 staged columns = 40 words
+constexpr int XOFF = 8;                                  // the staged tile starts 8 columns left of the output tile (8-byte aligned chunks)
+constexpr int PH = TH + 2 * HALO;                        // 40 staged rows
+constexpr int PP = TW + 2 * XOFF;                        // 136 staged columns = 34 words
 constexpr int PW = PP / 4;
-constexpr int SG = TW / 4 + 2;                           // 34 groups of 4 pixels per score row: columns ox-4 .. ox+131
-constexpr int SW = 4 * SG, SH = TH + 2;                  // score tile 136 x 34 (1-px ring for the NMS, rounded to groups)
+constexpr int SG = 32;                                   // groups of 4 pixels per score row: columns ox-4 .. ox+123, one warp per row
+constexpr int SW = 4 * SG, SH = TH + 2;                  // score tile 128 x 32
 constexpr int NT = 256;
-constexpr int COL0 = XOFF - 4, ROW0 = HALO - 1;              // staged-tile position of score-tile column 0 / row 0
+constexpr int COL0 = XOFF - 4, ROW0 = HALO - 1;          // staged-tile position of score-tile column 0 / row 0
+static_assert(SH * SG == 4 * NT, "four groups per thread");
 
 __device__ constexpr int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
 __device__ constexpr int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
@@ -64,45 +67,54 @@ __device__ __forceinline__ void ring_lanes(const uint32_t (&W)[7][3], uint32_t& 
   O = __byte_perm(v, 0u, 0x4341);                                 // (v >> 8) & 0x00ff00ff
 }
 
-// one opposite pair (K, K + 8): its minimum feeds the running maximum (darker test), its maximum the running minimum (brighter
-// test), two pixels per VIMNMX on 16-bit lanes.  A pixel can be a darker corner only if EVERY pair has a member < v - t, i.e.
-// max over the pairs of min(pair) < v - t; and a brighter one only if min over the pairs of max(pair) > v + t.
-template <int K>
-__device__ __forceinline__ void pair_step(const uint32_t (&W)[7][3], uint32_t& mxE, uint32_t& mxO, uint32_t& mnE, uint32_t& mnO)
-{
-  uint32_t e0, o0, e1, o1;
-  ring_lanes<K>(W, e0, o0);
-  ring_lanes<K + 8>(W, e1, o1);
-  mxE = __vmaxu2(mxE, __vminu2(e0, e1)); mxO = __vmaxu2(mxO, __vminu2(o0, o1));
-  mnE = __vminu2(mnE, __vmaxu2(e0, e1)); mnO = __vminu2(mnO, __vmaxu2(o0, o1));
-}
+template <int K> struct RingFill {
+  static __device__ __forceinline__ void run(const uint32_t (&W)[7][3], uint32_t bE, uint32_t bO, uint32_t (&XE)[16], uint32_t (&XO)[16])
+  {
+    uint32_t e, o;
+    ring_lanes<K>(W, e, o);
+    XE[K] = bE - e; XO[K] = bO - o;                               // lane = 256 + v - ring_K in [1, 511]: no borrow between lanes
+    RingFill<K + 1>::run(W, bE, bO, XE, XO);
+  }
+};
+template <> struct RingFill<16> {
+  static __device__ __forceinline__ void run(const uint32_t (&)[7][3], uint32_t, uint32_t, uint32_t (&)[16], uint32_t (&)[16]) {}
+};
 
-// bit 15 / 31 of the result: pixel (lane) still passes.  darker: mx + t + 1 <= v; brighter: mn >= v + t + 1 (no lane can borrow:
-// the minuend carries bit 15 and the subtrahend is at most 511)
-__device__ __forceinline__ uint32_t dark_flags(uint32_t mx, uint32_t v_hi, uint32_t t1) { return v_hi - (mx + t1); }
-__device__ __forceinline__ uint32_t bright_flags(uint32_t mn, uint32_t v_t1) { return (mn | 0x80008000u) - v_t1; }
-
-// FAST-9 score of polarity `bright` from the ring of the pixel at smem position p: max over the 16 arcs of 9 contiguous
-// ring pixels of the arc's minimum of e_k = +-(v - ring_k).  > threshold <=> the pixel is a corner of that polarity, and then
-// it is cv's cornerScore + 1 (fast_score.cpp: a0 / -b0 are exactly these max-min values, the other polarity cannot exceed t).
-__device__ __forceinline__ int fast_arc_score(const uint8_t* p, bool bright)
+// S (two lanes, biased by 256) from the 16 biased differences of two pixels: max( max_arcs min_arc X , 512 - min_arcs max_arc X )
+__device__ __forceinline__ uint32_t arc_score_lanes(const uint32_t (&X)[16])
 {
-  const int sgn = bright ? -1 : 1;
-  const int sv = sgn * (int)p[0];
-  int e[16];
+  uint32_t lo3[16], hi3[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) e[k] = sv - sgn * (int)p[c_ring_dy[k] * PP + c_ring_dx[k]];     // +-(v - ring_k): one IMAD
-  int w3[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) w3[k] = __vimin3_s32(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-  int best = -256;
+  for (int k = 0; k < 16; ++k) {
+    lo3[k] = __vimin3_u16x2(X[k], X[(k + 1) & 15], X[(k + 2) & 15]);
+    hi3[k] = __vimax3_u16x2(X[k], X[(k + 1) & 15], X[(k + 2) & 15]);
+  }
+  uint32_t a = 0u, b = 0xffffffffu;
 #pragma unroll
   for (int k = 0; k < 16; k += 2) {
-    const int m0 = __vimin3_s32(w3[k], w3[(k + 3) & 15], w3[(k + 6) & 15]);
-    const int m1 = __vimin3_s32(w3[k + 1], w3[(k + 4) & 15], w3[(k + 7) & 15]);
-    best = __vimax3_s32(best, m0, m1);
+    const uint32_t m0 = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    const uint32_t m1 = __vimin3_u16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+    a = __vimax3_u16x2(a, m0, m1);
+    const uint32_t n0 = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    const uint32_t n1 = __vimax3_u16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+    b = __vimin3_u16x2(b, n0, n1);
   }
-  return best;
+  return __vmaxu2(a, 0x02000200u - b);
+}
+
+// necessary condition on four opposite pairs (0,8) (2,10) (4,12) (6,14): every pair needs a member < v - t (or every pair one
+// > v + t).  In biased lanes: min over the pairs of max(X_k, X_k+8) > 256 + t, or max over the pairs of min(...) < 256 - t.
+__device__ __forceinline__ bool group_may_have_corner(const uint32_t (&XE)[16], const uint32_t (&XO)[16], uint32_t thr_hi, uint32_t thr_lo)
+{
+  uint32_t f = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t (&X)[16] = h ? XO : XE;
+    const uint32_t mx = __vimin3_u16x2(__vmaxu2(X[0], X[8]), __vmaxu2(X[2], X[10]), __vminu2(__vmaxu2(X[4], X[12]), __vmaxu2(X[6], X[14])));
+    const uint32_t mn = __vimax3_u16x2(__vminu2(X[0], X[8]), __vminu2(X[2], X[10]), __vmaxu2(__vminu2(X[4], X[12]), __vminu2(X[6], X[14])));
+    f |= ((mx | 0x80008000u) - thr_hi) | (thr_lo - mn);          // bit 15 / 31: mx >= 257 + t ; mn <= 255 - t
+  }
+  return (f & 0x80008000u) != 0;
 }
 
 // vk::shiTomasiScore vision.cpp:113-154 on the staged tile; p points at (u,v).  The reference's float sums of integer-valued
@@ -177,13 +189,13 @@ __device__ __forceinline__ int list_reserve(int mine, int* counter)
   return base + incl - mine;
 }
 
-__global__ void __launch_bounds__(NT, 5) fast_kernel(FastArgs A)
+__global__ void __launch_bounds__(NT, 3) fast_kernel(FastArgs A)
 {
   __shared__ __align__(16) uint8_t s_px[PH * PP];
-  __shared__ __align__(4) uint8_t s_sc[SH * SW];
-  __shared__ unsigned short s_cand[SH * SW];              // pass A -> B: score-tile index | dark << 13 | bright << 14 ; reused C -> D
-  __shared__ unsigned short s_corner[SH * SW];            // pass B -> C
-  __shared__ int s_n[3];
+  __shared__ __align__(16) uint32_t s_scw[SH * SG];       // score tile, one word per group
+  __shared__ unsigned short s_kp[TH * TW];                // keypoints: score-tile index
+  __shared__ int s_n;
+  const uint8_t* s_sc = reinterpret_cast<const uint8_t*>(s_scw);
   const bool raw = A.raw_scores != nullptr;
   int level = 0;
   if (raw) level = A.raw_level;
@@ -197,143 +209,109 @@ __global__ void __launch_bounds__(NT, 5) fast_kernel(FastArgs A)
   const uint8_t* img = A.f.lvl[level] + (size_t)b * A.f.img_stride[level];
   const int threshold = raw ? A.raw_threshold : 10;
 
-  // stage the tile: 16-byte chunks (ox is a multiple of 128, the pitch a multiple of 16 => chunks are aligned); a chunk that
+  // stage the tile: 8-byte chunks (ox is a multiple of 8, the pitch a multiple of 16 => chunks are aligned); a chunk that
   // starts left of the image, or a row outside it, is zero.  Bytes at gx >= w come from the row padding / the next row:
   // no corner, score or Shi-Tomasi window that is evaluated ever reads them (gx + 5 < w for every evaluated pixel).
-  if (threadIdx.x < 3) s_n[threadIdx.x] = 0;
-  for (int i = threadIdx.x; i < PH * (PP / 16); i += NT) {
-    const int r = i / (PP / 16), c16 = i - r * (PP / 16);
-    const int gx = ox - XOFF + 16 * c16, gy = oy - HALO + r;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (gx >= 0 && gy >= 0 && gx < pitch && gy < h) v = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx));
-    *reinterpret_cast<uint4*>(&s_px[r * PP + 16 * c16]) = v;
+  if (threadIdx.x == 0) s_n = 0;
+  for (int i = threadIdx.x; i < PH * (PP / 8); i += NT) {
+    const int r = i / (PP / 8), c8 = i - r * (PP / 8);
+    const int gx = ox - XOFF + 8 * c8, gy = oy - HALO + r;
+    uint2 v = make_uint2(0u, 0u);
+    if (gx >= 0 && gy >= 0 && gx < pitch && gy < h) v = __ldg(reinterpret_cast<const uint2*>(img + (size_t)gy * pitch + gx));
+    *reinterpret_cast<uint2*>(&s_px[r * PP + 8 * c8]) = v;
   }
-  for (int i = threadIdx.x; i < SH * SW / 4; i += NT) reinterpret_cast<uint32_t*>(s_sc)[i] = 0;
   __syncthreads();
 
-  // pass A: candidate test, four pixels per thread.  Task i = (score row sr, group sg): pixels gx = ox - 4 + 4 sg + {0..3},
-  // gy = oy - 1 + sr; in the staged tile that is word COL0 / 4 + sg of row ROW0 + sr.
+  // pass A: S - 1 of every pixel of the score tile, four pixels per thread.  Task (sr, sg): pixels gx = ox - 4 + 4 sg + {0..3},
+  // gy = oy - 1 + sr; in the staged tile that is word COL0 / 4 + sg of row ROW0 + sr.  A warp = one score row.
   const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_px);
-  const uint32_t t1 = (uint32_t)(threshold + 1) * 0x00010001u;
-  for (int i0 = 0; i0 < SH * SG; i0 += NT) {
-    const int i = i0 + threadIdx.x;
-    // flags of the group's pixels 0..3 sit at bits 15, 14, 31, 30 (E lanes: pixels 0 and 2; O lanes, shifted right by one: 1 and 3)
-    uint32_t D = 0, B = 0;
-    int sr = 0, sg = 0;
-    if (i < SH * SG) {
-      sr = i / SG; sg = i - sr * SG;
-      const int gy = oy - 1 + sr, gx0 = ox - 4 + 4 * sg;
-      if (gy >= 3 && gy < h - 3 && gx0 + 3 >= 3 && gx0 < w - 3) {
-        uint32_t W[7][3];
-        const uint32_t* q = s_w + (sr + ROW0 - 3) * PW + (COL0 / 4 - 1) + sg;      // row gy - 3, word left of the group
+  const uint32_t thr_hi = (uint32_t)(257 + threshold) * 0x00010001u, thr_lo = (uint32_t)(255 - threshold) * 0x00010001u | 0x80008000u;
+  const int sg = threadIdx.x & 31;
+  const int gx0 = ox - 4 + 4 * sg;
+  // pixels of the group inside [3, w - 3), as a byte mask of the score word
+  uint32_t colmask = 0;
 #pragma unroll
-        for (int r = 0; r < 7; ++r) { W[r][0] = q[r * PW]; W[r][1] = q[r * PW + 1]; W[r][2] = q[r * PW + 2]; }
-        const uint32_t c = W[3][1];
-        const uint32_t vE = c & 0x00ff00ffu, vO = __byte_perm(c, 0u, 0x4341);
-        const uint32_t vhE = vE | 0x80008000u, vhO = vO | 0x80008000u, vtE = vE + t1, vtO = vO + t1;
-        uint32_t mxE = 0u, mxO = 0u, mnE = 0x00ff00ffu, mnO = 0x00ff00ffu;
-        pair_step<0>(W, mxE, mxO, mnE, mnO);
-        pair_step<4>(W, mxE, mxO, mnE, mnO);
-        pair_step<2>(W, mxE, mxO, mnE, mnO);
-        pair_step<6>(W, mxE, mxO, mnE, mnO);
-        const uint32_t alive = (dark_flags(mxE, vhE, t1) | dark_flags(mxO, vhO, t1) | bright_flags(mnE, vtE) | bright_flags(mnO, vtO)) & 0x80008000u;
-        if (alive) {
-          pair_step<1>(W, mxE, mxO, mnE, mnO);
-          pair_step<3>(W, mxE, mxO, mnE, mnO);
-          pair_step<5>(W, mxE, mxO, mnE, mnO);
-          pair_step<7>(W, mxE, mxO, mnE, mnO);
-          D = (dark_flags(mxE, vhE, t1) & 0x80008000u) | ((dark_flags(mxO, vhO, t1) & 0x80008000u) >> 1);
-          B = (bright_flags(mnE, vtE) & 0x80008000u) | ((bright_flags(mnO, vtO) & 0x80008000u) >> 1);
-          if (gx0 < 3 || gx0 + 3 >= w - 3) {               // groups that straddle the 3-pixel border
-            uint32_t ok = 0;
-            if (gx0 + 0 >= 3 && gx0 + 0 < w - 3) ok |= 1u << 15;
-            if (gx0 + 1 >= 3 && gx0 + 1 < w - 3) ok |= 1u << 14;
-            if (gx0 + 2 >= 3 && gx0 + 2 < w - 3) ok |= 1u << 31;
-            if (gx0 + 3 >= 3 && gx0 + 3 < w - 3) ok |= 1u << 30;
-            D &= ok; B &= ok;
-          }
-        }
+  for (int k = 0; k < 4; ++k) if (gx0 + k >= 3 && gx0 + k < w - 3) colmask |= 0xffu << (8 * k);
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int sr = it * 8 + (threadIdx.x >> 5);
+    const int gy = oy - 1 + sr;
+    uint32_t word = 0;
+    if (gy >= 3 && gy < h - 3 && colmask) {                // (uniform over the warp except for colmask at the image's right edge)
+      uint32_t W[7][3];
+      const uint32_t* q = s_w + (sr + ROW0 - 3) * PW + (COL0 / 4 - 1) + sg;      // row gy - 3, word left of the group
+#pragma unroll
+      for (int r = 0; r < 7; ++r) { W[r][0] = q[r * PW]; W[r][1] = q[r * PW + 1]; W[r][2] = q[r * PW + 2]; }
+      const uint32_t c = W[3][1];
+      const uint32_t bE = (c & 0x00ff00ffu) + 0x01000100u, bO = __byte_perm(c, 0u, 0x4341) + 0x01000100u;
+      uint32_t XE[16], XO[16];
+      RingFill<0>::run(W, bE, bO, XE, XO);
+      if (__any_sync(__activemask(), group_may_have_corner(XE, XO, thr_hi, thr_lo))) {
+        uint32_t sE = arc_score_lanes(XE), sO = arc_score_lanes(XO);
+        sE = __vmaxu2(sE, 0x01010101u) - 0x01010101u;      // S - 1 (biased by 256 -> - 257), clamped at 0: <= 254 per lane
+        sO = __vmaxu2(sO, 0x01010101u) - 0x01010101u;
+        word = (sE | (sO << 8)) & colmask;
       }
     }
-    const uint32_t any = D | B;
+    s_scw[sr * SG + sg] = word;
+  }
+  __syncthreads();
+
+  // pass C: strict 3x3 non-max suppression on 16-bit lanes, four pixels per thread.  Task (r, g): pixels gx = ox + 4 g + {0..3},
+  // gy = oy + r = score-tile row r + 1, word g + 1.  keep <=> s >= t (a corner) and s > every neighbour.
+  const uint32_t t_l = (uint32_t)threshold * 0x00010001u;
+  for (int j = threadIdx.x; j < (TH * (TW / 4) + 31) / 32 * 32; j += NT) {         // (rounded up: whole warps reach the ballots below)
+    uint32_t keepE = 0, keepO = 0, cE = 0, cO = 0;
+    const int r = j / (TW / 4), g = j - r * (TW / 4);
+    const bool live = j < TH * (TW / 4);
+    if (live) {
+      uint32_t LE[3], CE[3], CO[3], RO[3];
+#pragma unroll
+      for (int dr = 0; dr < 3; ++dr) {
+        const uint32_t* q = s_scw + (r + dr) * SG + g;
+        const uint32_t l = q[0], c = q[1], rr = q[2];
+        CE[dr] = c & 0x00ff00ffu; CO[dr] = __byte_perm(c, 0u, 0x4341);
+        LE[dr] = __byte_perm(__byte_perm(l, 0u, 0x4341), CO[dr], 0x5432);   // left neighbours of pixels 0, 2: pixel 3 of the left group, pixel 1
+        RO[dr] = __byte_perm(CE[dr], rr & 0x00ff00ffu, 0x5432);             // right neighbours of pixels 1, 3: pixel 2, pixel 0 of the right group
+      }
+      cE = CE[1]; cO = CO[1];
+      const uint32_t mE = __vmaxu2(__vimax3_u16x2(__vimax3_u16x2(LE[0], CE[0], CO[0]), LE[2], CE[2]), __vimax3_u16x2(CO[2], LE[1], CO[1]));
+      const uint32_t mO = __vmaxu2(__vimax3_u16x2(__vimax3_u16x2(CE[0], CO[0], RO[0]), CE[2], CO[2]), __vimax3_u16x2(RO[2], CE[1], RO[1]));
+      const bool nms = !raw || A.raw_nonmax;
+      // bit 15 / 31: s >= t and (s >= m + 1 or no suppression)
+      keepE = ((cE | 0x80008000u) - t_l) & (nms ? ((cE | 0x80008000u) - (mE + 0x00010001u)) : 0xffffffffu) & 0x80008000u;
+      keepO = ((cO | 0x80008000u) - t_l) & (nms ? ((cO | 0x80008000u) - (mO + 0x00010001u)) : 0xffffffffu) & 0x80008000u;
+      if (raw) {
+        const int gy = oy + r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int gx = ox + 4 * g + k;
+          const uint32_t keep = (k & 1) ? keepO : keepE, sc = (k & 1) ? cO : cE;
+          const int sh = (k & 2) ? 16 : 0;
+          if (gx < w && gy < h) A.raw_scores[(size_t)gy * w + gx] = ((keep >> (sh + 15)) & 1u) ? (uint8_t)((sc >> sh) & 0xffu) : (uint8_t)0;
+        }
+        keepE = keepO = 0;
+      }
+    }
+    const uint32_t any = keepE | (keepO >> 1);              // bits 15, 14, 31, 30: pixels 0, 1, 2, 3
     const int mine = __popc(any);
     if (__any_sync(0xffffffffu, mine != 0)) {
-      int slot = list_reserve(mine, &s_n[0]);
-      const int base = sr * SW + 4 * sg;
-      if (any & (1u << 15)) s_cand[slot++] = (unsigned short)((base + 0) | (((D >> 15) & 1u) << 13) | (((B >> 15) & 1u) << 14));
-      if (any & (1u << 14)) s_cand[slot++] = (unsigned short)((base + 1) | (((D >> 14) & 1u) << 13) | (((B >> 14) & 1u) << 14));
-      if (any & (1u << 31)) s_cand[slot++] = (unsigned short)((base + 2) | (((D >> 31) & 1u) << 13) | (((B >> 31) & 1u) << 14));
-      if (any & (1u << 30)) s_cand[slot++] = (unsigned short)((base + 3) | (((D >> 30) & 1u) << 13) | (((B >> 30) & 1u) << 14));
-    }
-  }
-  __syncthreads();
-  // pass B: exact FAST-9 test + corner score for the candidates, thread per candidate
-  const int n_cand = s_n[0];
-  for (int j0 = 0; j0 < n_cand; j0 += NT) {
-    const int j = j0 + threadIdx.x;
-    bool corner = false;
-    int idx = 0;
-    if (j < n_cand) {
-      const int e = s_cand[j];
-      idx = e & 0x1fff;
-      const int sr = idx / SW, c = idx - sr * SW;
-      const uint8_t* p = &s_px[(sr + ROW0) * PP + (c + COL0)];
-      // one polarity per candidate (both flags together are possible in principle, a darker AND a brighter arc are not)
-      int best = fast_arc_score(p, !(e & (1 << 13)));
-      if ((e & (3 << 13)) == (3 << 13)) best = max(best, fast_arc_score(p, true));
-      if (best > threshold) { s_sc[idx] = (uint8_t)((best - 1) & 0xff); corner = true; }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, corner);
-    if (m) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_n[1], __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (corner) s_corner[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)idx;
-    }
-  }
-  if (raw) {
-    // score map of the tile: zero, then the corners below
-    for (int i = threadIdx.x; i < TH * TW; i += NT) {
-      const int r = i / TW, c = i - r * TW;
-      if (ox + c < w && oy + r < h) A.raw_scores[(size_t)(oy + r) * w + ox + c] = 0;
-    }
-  }
-  __syncthreads();
-  // pass C: strict 3x3 non-max suppression, thread per corner of the output tile; keypoints -> s_cand
-  const int n_corner = s_n[1];
-  for (int j0 = 0; j0 < n_corner; j0 += NT) {
-    const int j = j0 + threadIdx.x;
-    bool keep = false;
-    int idx = 0;
-    if (j < n_corner) {
-      idx = s_corner[j];
-      const int sr = idx / SW, c = idx - sr * SW;
-      const int gx = ox - 4 + c, gy = oy - 1 + sr;
-      if (sr >= 1 && sr <= TH && c >= 4 && c < 4 + TW && gx < w && gy < h) {
-        const uint8_t* q = &s_sc[idx];
-        const int sc = q[0];
-        const int m = max(__vimax3_s32(__vimax3_s32(q[-SW - 1], q[-SW], q[-SW + 1]), q[-1], q[1]), __vimax3_s32(q[SW - 1], q[SW], q[SW + 1]));
-        keep = sc > m || (raw && !A.raw_nonmax);
-        if (raw) { if (keep) A.raw_scores[(size_t)gy * w + gx] = (uint8_t)sc; keep = false; }
-      }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_n[2], __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (keep) s_cand[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)idx;
+      int slot = list_reserve(mine, &s_n);
+      const int base = (r + 1) * SW + 4 * (g + 1);
+      if (any & (1u << 15)) s_kp[slot++] = (unsigned short)(base + 0);
+      if (any & (1u << 14)) s_kp[slot++] = (unsigned short)(base + 1);
+      if (any & (1u << 31)) s_kp[slot++] = (unsigned short)(base + 2);
+      if (any & (1u << 30)) s_kp[slot++] = (unsigned short)(base + 3);
     }
   }
   __syncthreads();
   // pass D: grid cell, occupancy, Shi-Tomasi score and the cell's 64-bit atomicMax, one thread per keypoint
-  const int n_kp = s_n[2];
+  const int n_kp = s_n;
   for (int j = threadIdx.x; j < n_kp; j += NT) {
-    const int idx = s_cand[j];
+    const int idx = s_kp[j];
     const int sr = idx / SW, c = idx - sr * SW;
     const int gx = ox - 4 + c, gy = oy - 1 + sr;
+    if (gx >= w || gy >= h) continue;
     // cell index: xy is a cv::Point2f, scale an int, cell_size_ an int (feature_detection.cpp:99-100)
     const float scale = (float)(1 << level);
     const int k = (int)(((float)gy * scale) / (float)A.cell) * A.grid_cols + (int)(((float)gx * scale) / (float)A.cell);
@@ -345,6 +323,7 @@ __global__ void __launch_bounds__(NT, 5) fast_kernel(FastArgs A)
     const unsigned long long key = ((unsigned long long)ordered_bits(score) << 32) | (unsigned long long)(~order);
     atomicMax(&A.keys[(size_t)b * A.n_cells + k], key);
   }
+  (void)s_sc;
 }
 
 __global__ void fast_init_keys_kernel(unsigned long long* keys, int n, float thr_f)

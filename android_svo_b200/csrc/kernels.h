@@ -77,9 +77,13 @@ constexpr int SEED_RANGES = 32;
 // T_cur_ref = cur.T_f_w * ref.T_f_w^-1 (matcher.cpp:216) and px_error_angle (depth_filter.cpp:245-247)
 struct __align__(16) SeedPoseRec { double T_ref_cur[7], T_cur_ref[7], T_cur_ref_m[7]; double px_error_angle; };
 static_assert(sizeof(SeedPoseRec) == 176, "SeedPoseRec layout");
-// image0 / n_images: the images [image0, image0 + n_images) this call covers (rows of the pose table it refreshes)
-int launch_seeds_update_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const SeedRef* d_refs, const double* d_T_kf_w,
-                                const int* d_kf_slot, int batch, int n_kfs, SeedPoseRec* d_pose_table, int image0, int n_images, const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
+// rows (keyframe k, image b), b in [image0, image0 + n_images), of the pose table: run after the step's final T_cur_w is known
+int launch_seed_pose_table(const DevCam& cam, int batch, int n_kfs, int image0, int n_images, const double* d_T_kf_w, const double* d_T_cur_w,
+                           SeedPoseRec* d_pose_table, cudaStream_t s, long long* launches);
+// batch_counter / max_n_kfs: Seed::batch_counter and DepthFilter::Options::max_n_kfs (seeds older than that are erased, :258-261)
+int launch_seeds_update_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, SeedRef* d_refs,
+                                const int* d_kf_slot, int batch, const SeedPoseRec* d_pose_table, int batch_counter, int max_n_kfs,
+                                svob200_matcher_opts opts, double conv_thresh,
                                 svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first,
                                 int range /* < SEED_RANGES: sub-ranges in flight together use distinct job regions / counters */,
                                 cudaStream_t s, long long* launches, cudaEvent_t* marks = nullptr);

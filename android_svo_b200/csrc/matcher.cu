@@ -399,20 +399,21 @@ struct __align__(16) SearchTask { uint32_t w[32]; };
 enum { ST_FLAGS = 0, ST_LEVELS = 1, ST_EPILEN = 2, ST_REF_SLOT = 4, ST_REF_IMAGE = 5, ST_CUR_IMAGE = 6, ST_A00 = 8, ST_A01 = 9, ST_A10 = 10, ST_A11 = 11,
        ST_PR0 = 12, ST_PR1 = 13, ST_DIRX = 14, ST_DIRY = 15, ST_BX0 = 16, ST_BY0 = 18, ST_STEPX = 20, ST_STEPY = 22, ST_MIDX = 24, ST_MIDY = 26 };
 // flags: bit 0 search this item, bit 1 the warp matrix is finite, bits 2-3 EPI_MODE_*, bits 4-6 the depth filter's early status
-// (SVOB200_SEED_BEHIND / _NOT_IN_FRAME; 0 = the matcher runs), bit 7 z_inv_min is NaN (depth_filter.cpp:334)
+// (SVOB200_SEED_BEHIND / _NOT_IN_FRAME / _TOO_OLD; 0 = the matcher runs), bit 7 z_inv_min is NaN (depth_filter.cpp:334)
 // levels: search level | reference level << 8 | samples of the walk << 16
-enum { ST_ACTIVE = 1, ST_WARP_OK = 2, ST_MODE_SHIFT = 2, ST_STATUS_SHIFT = 4, ST_ZMIN_NAN = 128 };
+enum { ST_ACTIVE = 1, ST_WARP_OK = 2, ST_MODE_SHIFT = 2, ST_STATUS_SHIFT = 4, ST_ZMIN_NAN = 128, ST_FREE = 256 /* empty slot of a seed pool */ };
 
 // the reference feature of an item, wherever its record lives (caller's svob200_feature_ref or the tracker's compact SeedRef)
 struct RefFtr {
   double px[2]; v3d f; int level, type; double grad[2];
   int ref_slot, ref_image, cur_image, kf;
+  int state, batch_id;                 // seed pools only (SeedRef)
 };
 __device__ __forceinline__ RefFtr ref_ftr_of(const svob200_feature_ref& r)
 {
   RefFtr f;
   f.px[0] = r.px[0]; f.px[1] = r.px[1]; f.f = {r.f[0], r.f[1], r.f[2]}; f.level = r.level; f.type = r.type; f.grad[0] = r.grad[0]; f.grad[1] = r.grad[1];
-  f.ref_slot = (int)r.ref_frame_id; f.ref_image = r.ref_image; f.cur_image = r.cur_image; f.kf = 0;
+  f.ref_slot = (int)r.ref_frame_id; f.ref_image = r.ref_image; f.cur_image = r.cur_image; f.kf = 0; f.state = 0; f.batch_id = 0;
   return f;
 }
 
@@ -927,11 +928,14 @@ struct SeedSrcApi {
   {
     seed_relative_poses(cam, T_ref_w + 7 * (size_t)i, T_cur_w + 7 * (size_t)f.cur_image, P);
   }
+  __device__ __forceinline__ int early_status(const RefFtr&) const { return 0; }
+  __device__ __forceinline__ void erase(int) const {}
 };
 // the tracker's compact records: keyframe k of image b lives in frame slot kf_slot[k]; its poses relative to the current
 // frame are row (k * batch + b) of the table seed_pose_table_kernel refreshed
 struct SeedSrcCompact {
-  const SeedRef* refs; const SeedPoseRec* table; const int* kf_slot; int batch;
+  SeedRef* refs; const SeedPoseRec* table; const int* kf_slot; int batch;
+  int batch_counter, max_n_kfs;          // Seed::batch_counter and DepthFilter::Options::max_n_kfs for the ageing rule
   __device__ __forceinline__ RefFtr get(int i) const
   {
     const uint4* q = reinterpret_cast<const uint4*>(&refs[i]);
@@ -942,9 +946,18 @@ struct SeedSrcCompact {
     f.ref_image = f.cur_image = (int)c.z;
     f.level = (int)(c.w & 0xffu); f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
     f.kf = (int)((c.w >> 8) & 0xffu);
+    f.batch_id = (int)(c.w >> 16);
+    f.state = (int)(reinterpret_cast<const uint8_t*>(&refs[i])[48]);      // (plain load: the slot may have been filled since the last kernel)
     f.ref_slot = __ldg(&kf_slot[f.kf]);
     return f;
   }
+  // -1: empty slot; SVOB200_SEED_TOO_OLD: "check if seed is not already too old" (depth_filter.cpp:258-261); 0: update it
+  __device__ __forceinline__ int early_status(const RefFtr& f) const
+  {
+    if (f.state != 0) return -1;
+    return (batch_counter - f.batch_id) > max_n_kfs ? SVOB200_SEED_TOO_OLD : 0;
+  }
+  __device__ __forceinline__ void erase(int i) const { reinterpret_cast<uint8_t*>(&refs[i])[48] = 1; }
   __device__ __forceinline__ void poses(const DevCam&, int, const RefFtr& f, SeedPoses& P) const
   {
     // 176 bytes shared by all the seeds of an image: consecutive threads read the same row (L1 broadcast)
@@ -991,15 +1004,17 @@ __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, SRC 
     const RefFtr f = src.get(i);
     const svob200_seed s = seeds[i];
     SeedPoses P;
-    src.poses(cam, i, f, P);
-    int status = 0;
-    const double inv_mu = 1.0 / s.mu;
-    const v3d xyz_f = se3_transform(P.T_cur_ref, {inv_mu * f.f.x, inv_mu * f.f.y, inv_mu * f.f.z});
-    if (xyz_f.z < 0.0) status = SVOB200_SEED_BEHIND;
-    else {
-      double pxf, pyf;
-      world2cam(cam, xyz_f, pxf, pyf);
-      if (!in_frame(cam, (int)pxf, (int)pyf, 0)) status = SVOB200_SEED_NOT_IN_FRAME;
+    int status = src.early_status(f);
+    if (status == 0) {
+      src.poses(cam, i, f, P);
+      const double inv_mu = 1.0 / s.mu;
+      const v3d xyz_f = se3_transform(P.T_cur_ref, {inv_mu * f.f.x, inv_mu * f.f.y, inv_mu * f.f.z});
+      if (xyz_f.z < 0.0) status = SVOB200_SEED_BEHIND;
+      else {
+        double pxf, pyf;
+        world2cam(cam, xyz_f, pxf, pyf);
+        if (!in_frame(cam, (int)pxf, (int)pyf, 0)) status = SVOB200_SEED_NOT_IN_FRAME;
+      }
     }
     if (status == 0) {
       const float z_inv_min = s.mu + sqrtf(s.sigma2);
@@ -1009,7 +1024,7 @@ __global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, SRC 
       store_geometry(g, f, !g.reject && g.mode != EPI_MODE_NONE, isnan(z_inv_min) ? ST_ZMIN_NAN : 0u, nullptr,
                      reinterpret_cast<SearchTask*>(&s_task[warp][lane]));
       has_geom = true;
-    } else s_task[warp][lane].q[0] = make_uint4((uint32_t)status << ST_STATUS_SHIFT, 0, 0, 0);   // nothing to search
+    } else s_task[warp][lane].q[0] = make_uint4(status < 0 ? (uint32_t)ST_FREE : ((uint32_t)status << ST_STATUS_SHIFT), 0, 0, 0);   // nothing to search
   }
   const unsigned wrote = __ballot_sync(0xffffffffu, has_geom);
   const unsigned skip = __ballot_sync(0xffffffffu, valid && !has_geom);
@@ -1079,7 +1094,8 @@ __global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, SR
   const int status0 = (int)((flags >> ST_STATUS_SHIFT) & 7u);
   svob200_seed_obs ob;
   ob.status = status0; ob.search_level = 0; ob.zmssd_best = 2000 * 64; ob.n_evals = 0; ob.z = 0; ob.px_cur[0] = ob.px_cur[1] = 0; ob.epi_length = 0;
-  if (status0 == 0) {
+  if (status0 == SVOB200_SEED_TOO_OLD) src.erase(i);                          // it = seeds_.erase(it) (depth_filter.cpp:259)
+  if (status0 == 0 && !(flags & ST_FREE)) {
     const RefFtr f = src.get(i);
     SeedMatch sr;
     if (flags & ST_ACTIVE) {
@@ -1464,17 +1480,24 @@ int launch_seeds_update(const DevFrame* d_frames, int cur_slot, const DevCam& ca
   return seeds_update_impl(d_frames, cur_slot, cam, n, src, opts, conv_thresh, d_seeds, d_obs, d_scratch, scratch_total, first, 0, s, launches, marks);
 }
 
-int launch_seeds_update_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, const SeedRef* d_refs, const double* d_T_kf_w,
-                                const int* d_kf_slot, int batch, int n_kfs, SeedPoseRec* d_pose_table, int image0, int n_images,
-                                const double* d_T_cur_w, svob200_matcher_opts opts, double conv_thresh,
+// rows (keyframe k, image b), b in [image0, image0 + n_images), of the pose table the compact seed kernels read
+int launch_seed_pose_table(const DevCam& cam, int batch, int n_kfs, int image0, int n_images, const double* d_T_kf_w, const double* d_T_cur_w,
+                           SeedPoseRec* d_pose_table, cudaStream_t s, long long* launches)
+{
+  const int rows = n_kfs * n_images;
+  if (rows <= 0) return 0;
+  seed_pose_table_kernel<<<(rows + 127) / 128, 128, 0, s>>>(cam, batch, n_kfs, image0, n_images, d_T_kf_w, d_T_cur_w, d_pose_table);
+  ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_seeds_update_compact(const DevFrame* d_frames, int cur_slot, const DevCam& cam, int n, SeedRef* d_refs,
+                                const int* d_kf_slot, int batch, const SeedPoseRec* d_pose_table, int batch_counter, int max_n_kfs,
+                                svob200_matcher_opts opts, double conv_thresh,
                                 svob200_seed* d_seeds, svob200_seed_obs* d_obs, void* d_scratch, int scratch_total, int first, int range,
                                 cudaStream_t s, long long* launches, cudaEvent_t* marks)
 {
-  if (n <= 0) return 0;
-  const int rows = n_kfs * n_images;
-  seed_pose_table_kernel<<<(rows + 127) / 128, 128, 0, s>>>(cam, batch, n_kfs, image0, n_images, d_T_kf_w, d_T_cur_w, d_pose_table);
-  ++*launches;
-  SeedSrcCompact src{d_refs, d_pose_table, d_kf_slot, batch};
+  SeedSrcCompact src{d_refs, d_pose_table, d_kf_slot, batch, batch_counter, max_n_kfs};
   return seeds_update_impl(d_frames, cur_slot, cam, n, src, opts, conv_thresh, d_seeds, d_obs, d_scratch, scratch_total, first, range, s, launches, marks);
 }
 

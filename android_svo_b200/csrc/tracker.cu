@@ -26,21 +26,27 @@ __global__ void init_pose_kernel(int batch, const double* T_last, double* T_init
 }
 
 // one CTA per sequence: per-sequence statistics + steady-state re-seeding of finished seeds
+// parts: 1 = the tracking fields (pose, alignment, matches), 2 = the depth-filter fields (+ re-seeding); 3 = both.  The
+// asynchronous depth filter runs part 2 on its own stream, after the tracking chain of the same step ran part 1.
 __global__ void __launch_bounds__(128) step_stats_kernel(const int* ftr_off, const int* seed_off, const svob200_align_result* align,
                                                          const double* T_cur_w, const int* match_ok, const svob200_seed_obs* obs,
-                                                         svob200_seed* seeds, svob200_seed init, int reseed, svob200_step_stats* stats)
+                                                         svob200_seed* seeds, svob200_seed init, int reseed, svob200_step_stats* stats, int parts,
+                                                         SeedRef* refs)
 {
   const int b = blockIdx.x, tid = threadIdx.x;
   int matched = 0, upd = 0, conv = 0, fail = 0, skipped = 0;
-  for (int i = ftr_off[b] + tid; i < ftr_off[b + 1]; i += 128) matched += match_ok[i] ? 1 : 0;
-  for (int i = seed_off[b] + tid; i < seed_off[b + 1]; i += 128) {
+  if (parts & 1) for (int i = ftr_off[b] + tid; i < ftr_off[b + 1]; i += 128) matched += match_ok[i] ? 1 : 0;
+  if (parts & 2) for (int i = seed_off[b] + tid; i < seed_off[b + 1]; i += 128) {
     const int st = obs[i].status;
+    if (st == 0 || st == SVOB200_SEED_TOO_OLD) continue;            // empty slot / erased by the ageing rule
     if (st == SVOB200_SEED_UPDATED) ++upd;
     else if (st == SVOB200_SEED_CONVERGED) ++conv;
     else if (st == SVOB200_SEED_NO_MATCH) ++fail;
     else ++skipped;
     // reseed 1: finished seeds start afresh (stationary workload); 2: EVERY seed starts afresh every frame (young-seed regime)
-    if (reseed == 2 || (reseed && (st == SVOB200_SEED_CONVERGED || st == SVOB200_SEED_NAN_ERASED))) seeds[i] = init;
+    // 3: the reference's list semantics — a converged seed (callback, depth_filter.cpp:314-331) or a NaN one (:334-338) is erased
+    if (reseed == 3) { if (st == SVOB200_SEED_CONVERGED || st == SVOB200_SEED_NAN_ERASED) refs[i].state = 1; }
+    else if (reseed == 2 || (reseed && (st == SVOB200_SEED_CONVERGED || st == SVOB200_SEED_NAN_ERASED))) seeds[i] = init;
   }
   __shared__ int s[5];
   if (tid < 5) s[tid] = 0;
@@ -50,15 +56,18 @@ __global__ void __launch_bounds__(128) step_stats_kernel(const int* ftr_off, con
   __syncthreads();
   if (tid == 0) {
     svob200_step_stats* o = &stats[b];
-    for (int k = 0; k < 7; ++k) o->T_cur_w[k] = T_cur_w[7 * (size_t)b + k];
-    o->chi2 = align[b].chi2;
-    o->n_tracked = align[b].n_meas / 16;
-    o->n_matched = s[0]; o->n_seeds_updated = s[1]; o->n_seeds_converged = s[2]; o->n_seeds_failed = s[3]; o->n_seeds_skipped = s[4];
-    int it = 0;
-    for (int l = 0; l < SVOB200_MAX_LEVELS; ++l) it += align[b].iters[l];
-    o->align_iters = it;
-    o->n_exact_chi2 = align[b].n_exact_chi2;
-    o->n_reproj_trials = 0; o->n_pose_obs = 0;
+    if (parts & 1) {
+      for (int k = 0; k < 7; ++k) o->T_cur_w[k] = T_cur_w[7 * (size_t)b + k];
+      o->chi2 = align[b].chi2;
+      o->n_tracked = align[b].n_meas / 16;
+      o->n_matched = s[0];
+      int it = 0;
+      for (int l = 0; l < SVOB200_MAX_LEVELS; ++l) it += align[b].iters[l];
+      o->align_iters = it;
+      o->n_exact_chi2 = align[b].n_exact_chi2;
+      o->n_reproj_trials = 0; o->n_pose_obs = 0;
+    }
+    if (parts & 2) { o->n_seeds_updated = s[1]; o->n_seeds_converged = s[2]; o->n_seeds_failed = s[3]; o->n_seeds_skipped = s[4]; }
   }
 }
 
@@ -89,6 +98,81 @@ __global__ void chain_stats_kernel(int batch, const svob200_reproj_stats* rs, co
   stats[b].n_pose_obs = pose_opt ? pr[b].num_obs : rs[b].n_matches;
 }
 
+// ---- keyframe insertion (svob200_tracker_add_keyframe)
+// occupancy of the frame's existing features = the map points matched in it (AbstractDetector::setExistingFeatures,
+// feature_detection.cpp:40-58: cell of (px.y / cell, px.x / cell) with the x86 double -> int conversion)
+__global__ void kf_occupancy_kernel(int n, const int* ftr_image, const double* px, const int* match_ok, int cell, int grid_cols, int n_cells, uint8_t* occ)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !match_ok[i]) return;
+  const double cy = px[2 * (size_t)i + 1] / cell, cx = px[2 * (size_t)i] / cell;
+  const int iy = (cy == cy && cy > -2147483649.0 && cy < 2147483648.0) ? (int)cy : (int)0x80000000;
+  const int ix = (cx == cx && cx > -2147483649.0 && cx < 2147483648.0) ? (int)cx : (int)0x80000000;
+  const long long k = (long long)iy * grid_cols + ix;
+  if (k >= 0 && k < n_cells) occ[(size_t)ftr_image[i] * n_cells + k] = 1;
+}
+
+// seeds of a dropped keyframe leave the pool (DepthFilter::removeKeyframe, depth_filter.cpp:153-170)
+__global__ void kf_erase_seeds_kernel(int n, SeedRef* refs, int kf)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && refs[i].state == 0 && refs[i].kf == kf) refs[i].state = 1;
+}
+
+// DepthFilter::initializeSeeds (depth_filter.cpp:129-151): one Seed (ctor :36-45) per new corner, in cell order, into the empty
+// slots of the sequence's pool in slot order.  One CTA per sequence; corners that find no slot are counted as dropped.
+__global__ void __launch_bounds__(256) kf_append_seeds_kernel(DevCam cam, const svob200_corner* cells, int n_cells, double thr, const float* depth_mean,
+                                                              const float* depth_min, const int* seed_off, SeedRef* refs, svob200_seed* seeds, int kf,
+                                                              int batch_id, int* appended, int* dropped)
+{
+  __shared__ int s_scan[256];
+  __shared__ int s_free_total, s_new_total;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const svob200_corner* C = cells + (size_t)b * n_cells;
+  const int p0 = seed_off[b], np = seed_off[b + 1] - p0;
+  // rank of every new corner (cell order) and of every empty slot (slot order): two block scans over contiguous chunks
+  auto scan = [&](int local) {
+    s_scan[tid] = local;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) { const int v = tid >= off ? s_scan[tid - off] : 0; __syncthreads(); s_scan[tid] += v; __syncthreads(); }
+    const int excl = s_scan[tid] - local, total = s_scan[255];
+    __syncthreads();
+    return make_int2(excl, total);
+  };
+  const int cchunk = (n_cells + 255) / 256, c0 = min(tid * cchunk, n_cells), c1 = min(c0 + cchunk, n_cells);
+  int ncor = 0;
+  for (int c = c0; c < c1; ++c) ncor += (double)C[c].score > thr;
+  const int2 cs = scan(ncor);
+  const int pchunk = (np + 255) / 256, q0 = min(tid * pchunk, np), q1 = min(q0 + pchunk, np);
+  int nfree = 0;
+  for (int q = q0; q < q1; ++q) nfree += refs[p0 + q].state != 0;
+  const int2 fs = scan(nfree);
+  if (tid == 0) { s_free_total = fs.y; s_new_total = cs.y; }
+  // slot of rank r: every thread walks its own chunk of slots and fills in the corners whose rank falls into it.  The corner of
+  // rank r is found by a second walk over the cells (ranks are monotone in the cell index): thread-local lists are short.
+  __shared__ int s_corner_of_rank[8192];              // cell index of the new corner of rank r (grids up to 8,192 cells)
+  { int r = cs.x; for (int c = c0; c < c1; ++c) if ((double)C[c].score > thr) { if (r < 8192) s_corner_of_rank[r] = c; ++r; } }
+  __syncthreads();
+  svob200_seed sd;
+  sd.a = 10; sd.b = 10; sd.mu = (float)(1.0 / depth_mean[b]); sd.z_range = (float)(1.0 / depth_min[b]); sd.sigma2 = sd.z_range * sd.z_range / 36;
+  const int n_fill = min(min(s_new_total, s_free_total), 8192);
+  int r = fs.x;
+  for (int q = q0; q < q1 && r < n_fill; ++q) {
+    if (refs[p0 + q].state == 0) continue;
+    const svob200_corner c = C[s_corner_of_rank[r]];
+    SeedRef ref;
+    ref.px[0] = (double)c.x; ref.px[1] = (double)c.y;                 // Feature(frame, Vector2d(x * scale, y * scale), level)
+    const v3d f = cam2world(cam, ref.px[0], ref.px[1]);               // Feature ctor, feature.h:43-51
+    ref.f[0] = f.x; ref.f[1] = f.y; ref.f[2] = f.z;
+    ref.image = b; ref.level = (uint8_t)c.level; ref.kf = (uint8_t)kf; ref.batch_id = (uint16_t)batch_id;
+    ref.state = 0; ref.pad0 = 0; ref.pad1 = 0; ref.pad2[0] = ref.pad2[1] = ref.pad2[2] = 0;
+    refs[p0 + q] = ref;
+    seeds[p0 + q] = sd;
+    ++r;
+  }
+  if (tid == 0) { appended[b] = n_fill; dropped[b] = s_new_total - n_fill; }
+}
+
 template <class T> int dalloc(svob200_ctx* ctx, T** p, size_t n)
 {
   *p = nullptr;
@@ -114,7 +198,24 @@ struct svob200_tracker {
   double conv_thresh = 100.0;
   svob200_seed seed_init{};
   int reseed = 1;
-  int64_t fid_kf = 0, fid_last = 0, fid_cur = 0;
+  int64_t fid_last = 0, fid_cur = 0;
+  // keyframes: up to max_kfs frames of the pool are keyframes (index k = position in the tables d_kf_slot / d_T_kf); the frame
+  // of a keyframe may at the same time be the `last` frame of the tracking chain
+  static constexpr int MAX_KFS = 16;
+  int64_t fid_kfs[MAX_KFS] = {};
+  int kf_batch[MAX_KFS] = {};          // Seed::batch_id of the seeds initialised in keyframe k (0 = unused slot of the ring)
+  std::vector<int64_t> frame_pool;     // every frame this tracker created
+  int64_t next_fid = 0;
+  int batch_counter = 0;               // Seed::batch_counter (depth_filter.cpp:139)
+  int max_n_kfs = 3;                   // DepthFilter::Options::max_n_kfs (depth_filter.h:75)
+  int seed_capacity = 0;               // slots per sequence of the seed pool (0: exactly the seeds of set_keyframe)
+  int det_cell = 30, det_levels = 3;   // Config::gridSize / nPyrLevels, Config::triangMinCornerScore
+  double det_thr = 20.0;
+  uint8_t* d_occ = nullptr; unsigned long long* d_det_keys = nullptr; svob200_corner* d_det_cells = nullptr;
+  int *d_det_counts = nullptr, *d_kf_appended = nullptr, *d_kf_dropped = nullptr;
+  float *d_depth_mean = nullptr, *d_depth_min = nullptr;
+  int det_cells_alloc = 0;
+  long long steps_done = 0;
   int N = 0, S = 0, max_per = 0;
   int *d_ftr_off = nullptr, *d_seed_off = nullptr, *d_ftr_image = nullptr, *d_match_ok = nullptr;
   uint8_t* d_has_point = nullptr;
@@ -125,8 +226,8 @@ struct svob200_tracker {
   double* d_T_kf = nullptr;            // [max_kfs][batch][7]
   int* d_kf_slot = nullptr;            // [max_kfs]
   SeedPoseRec* d_seed_poses = nullptr; // [max_kfs][batch], refreshed every step
-  int n_kfs = 1;
-  int max_kfs = 1;
+  int n_kfs = 1;                       // rows of the tables in use (highest keyframe index + 1)
+  int max_kfs = 4;                     // keyframe ring (svob200_tracker_set_keyframe_ring)
   svob200_seed* d_seeds = nullptr;
   double *d_step_in = nullptr;      // [T_last_w 7B | last_px 2N]
   double *d_xyz = nullptr, *d_T_init = nullptr, *d_T_cur = nullptr, *d_depth_ref = nullptr, *d_px_in = nullptr, *d_px_out = nullptr;
@@ -143,10 +244,27 @@ struct svob200_tracker {
   // Big batches run as sub-ranges of sequences alternating between the context's stream and `range_stream`: the kernels of
   // one sub-range fill the SMs while the other sits in a latency-bound stage (the sparse-alignment wave, whose length is its
   // slowest problem's Gauss-Newton chain) or in a kernel's tail; results are bit-identical (same kernels, same per-sequence work).
-  int ranges = 2;                      // sub-ranges per step in device mode (direct launches); 1 = one range on one stream
+  int ranges = 1;                      // sub-ranges per step in device mode (direct launches); 1 = one range on one stream (measured with the asynchronous depth filter: 1 range 0.601 ms per 512 sequences, 2 ranges 0.619; equal at 4,096)
   int min_range = 128;                 // ... but never fewer sequences than this per sub-range
   cudaStream_t range_stream = nullptr;
   cudaEvent_t range_ev[2] = {};
+  // Asynchronous depth filter (device-memory steps of big batches): like the reference, whose DepthFilter runs in its own
+  // thread behind a frame queue (depth_filter.cpp:63-103, :191-229), the seed update of frame k runs on its own stream while
+  // the tracking chain (pyramid -> alignment -> matching) of frame k+1 is already in flight: the latency-bound alignment wave
+  // overlaps the issue-bound epipolar search.  Everything a chain reads that the next steps overwrite is double-buffered by
+  // step parity (pose table, step records) or guarded by an event (the frame slot it searches in is reused two steps later).
+  // Every synchronising entry point joins the stream (ctx_join_aux).
+  int async_df = 1;                    // SVOB200_TRACKER_ASYNC_DF=0 switches it off (A/B runs)
+  cudaStream_t df_stream = nullptr;
+  cudaEvent_t df_done[2] = {}, ev_pose[4] = {}, ev_track[4] = {};
+  bool df_pending[2] = {false, false};
+  long long step_no = 0;
+  SeedPoseRec* d_seed_poses2 = nullptr;      // second pose table (odd steps)
+  svob200_step_stats* d_stats2 = nullptr;    // second step-record array (odd steps)
+  // what the current run_range call does with the depth filter: 0 = runs it in place, 1 = leaves it to the df stream
+  int df_defer = 0;
+  SeedPoseRec* cur_pose_table = nullptr;
+  svob200_step_stats* cur_stats = nullptr;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   // chain mode (svob200_tracker_set_chain): reprojector grid rules + pose optimiser instead of refining every map point
@@ -234,14 +352,19 @@ int svob200_tracker_create(svob200_ctx* ctx, const svob200_camera* cam, int batc
   t->seed_init.sigma2 = t->seed_init.z_range * t->seed_init.z_range / 36;
   if (const char* e = getenv("SVOB200_TRACKER_CHUNK")) { if (atoi(e) > 0) t->chunk = atoi(e); }   // sequences per H2D/compute pipeline chunk (A/B runs)
   if (const char* e = getenv("SVOB200_TRACKER_RANGES")) { if (atoi(e) > 0) t->ranges = std::min(atoi(e), (int)SEED_RANGES); }   // A/B runs
+  if (const char* e = getenv("SVOB200_TRACKER_ASYNC_DF")) t->async_df = atoi(e) != 0;
   if (const char* e = getenv("SVOB200_TRACKER_FORK")) t->graph_fork = atoi(e) != 0;   // 0: captured steps stay one chain of kernels (A/B runs)
   if (const char* e = getenv("SVOB200_TRACKER_GRAPH")) t->graph_max_batch = atoi(e) > 0 ? atoi(e) : 0;   // 0 disables graph replay; N = largest batch replayed as a graph
-  t->fid_kf = -(uid * 4 + 1); t->fid_last = -(uid * 4 + 2); t->fid_cur = -(uid * 4 + 3);
-  for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur})
-    if (int e = svob200_frame_create(ctx, id, batch, cam->width, cam->height, n_levels)) {
-      for (int64_t id2 : {t->fid_kf, t->fid_last, t->fid_cur}) if (id2 != id && find_frame(ctx, id2)) svob200_frame_release(ctx, id2);
-      delete t; return e;
-    }
+  // frame ids of this tracker: -(uid << 8 | n); three to start with (keyframe 0, last, cur), more as keyframes are inserted
+  t->next_fid = 1;
+  auto new_frame = [&](int64_t* out_id) -> int {
+    const int64_t id = -((uid << 8) | t->next_fid++);
+    if (int e = svob200_frame_create(ctx, id, batch, cam->width, cam->height, n_levels)) return e;
+    t->frame_pool.push_back(id); *out_id = id;
+    return 0;
+  };
+  for (int64_t* pid : {&t->fid_kfs[0], &t->fid_last, &t->fid_cur})
+    if (int e = new_frame(pid)) { for (int64_t id : t->frame_pool) svob200_frame_release(ctx, id); delete t; return e; }
   *out = t;
   return SVOB200_OK;
 }
@@ -250,8 +373,9 @@ void svob200_tracker_destroy(svob200_tracker* t)
 {
   if (!t) return;
   svob200_ctx* ctx = t->ctx;
+  ctx_join_aux(ctx);
   cudaStreamSynchronize(ctx->stream);
-  for (int64_t id : {t->fid_kf, t->fid_last, t->fid_cur}) svob200_frame_release(ctx, id);
+  for (int64_t id : t->frame_pool) svob200_frame_release(ctx, id);
   for (void* p : t->owned) cudaFree(p);
   if (t->h_pinned) cudaFreeHost(t->h_pinned);
   for (auto e : t->chunk_ev) cudaEventDestroy(e);
@@ -259,6 +383,10 @@ void svob200_tracker_destroy(svob200_tracker* t)
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->range_stream) cudaStreamDestroy(t->range_stream);
   for (auto e : t->range_ev) if (e) cudaEventDestroy(e);
+  if (t->df_stream) { cudaStreamSynchronize(t->df_stream); ctx_remove_aux(ctx, t->df_stream); cudaStreamDestroy(t->df_stream); }
+  for (auto e : t->df_done) if (e) cudaEventDestroy(e);
+  for (auto e : t->ev_pose) if (e) cudaEventDestroy(e);
+  for (auto e : t->ev_track) if (e) cudaEventDestroy(e);
   if (t->fork_stream) cudaStreamDestroy(t->fork_stream);
   for (auto e : t->fork_ev) if (e) cudaEventDestroy(e);
   for (int k = 0; k <= kNumStages; ++k) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
@@ -275,7 +403,8 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   svob200_ctx* ctx = t->ctx;
   if (t->d_stats) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_keyframe: keyframe already set (svob200_tracker_add_keyframe inserts further ones)");
   const int B = t->batch;
-  const int N = ftr_offsets[B], S = seed_offsets[B];
+  const int N = ftr_offsets[B];
+  int S = seed_offsets[B];
   // validate everything BEFORE the first launch / allocation
   if (N < 0 || S < 0 || ftr_offsets[0] != 0 || seed_offsets[0] != 0) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: bad offsets");
   for (int b = 0; b < B; ++b)
@@ -284,18 +413,24 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   if (S > 0 && (!seed_px || !seed_level)) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: null seed arrays with %d seeds", S);
   for (int i = 0; i < N; ++i) if (kf_level[i] < 0 || kf_level[i] >= t->n_levels) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: kf_level[%d] = %d outside the pyramid", i, kf_level[i]);
   for (int i = 0; i < S; ++i) if (seed_level[i] < 0 || seed_level[i] >= t->n_levels) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_keyframe: seed_level[%d] = %d outside the pyramid", i, seed_level[i]);
-  if (int e = svob200_frame_upload(ctx, t->fid_kf, imgs, stride, nullptr, SVOB200_MEM_HOST)) return e;
-  t->N = N; t->S = S;
+  if (int e = svob200_frame_upload(ctx, t->fid_kfs[0], imgs, stride, nullptr, SVOB200_MEM_HOST)) return e;
+  // seed pool: sequence b owns slots [pool_off[b], pool_off[b+1]) = its seeds followed by empty slots up to the capacity
+  std::vector<int> pool_off(B + 1, 0);
+  for (int b = 0; b < B; ++b) pool_off[b + 1] = pool_off[b] + std::max(seed_offsets[b + 1] - seed_offsets[b], t->seed_capacity);
+  const int S_pool = pool_off[B];
+  t->N = N; t->S = S_pool;
+  S = S_pool;                                                            // from here on S counts pool slots
   t->h_ftr_off.assign(ftr_offsets, ftr_offsets + B + 1);
   t->h_pt_world.assign(pt_world, pt_world + 3 * (size_t)N);
-  t->h_seed_off.assign(seed_offsets, seed_offsets + B + 1);
+  t->h_seed_off = pool_off;
   for (int b = 0; b < B; ++b) t->max_per = std::max(t->max_per, ftr_offsets[b + 1] - ftr_offsets[b]);
-  const int slot = svob200_frame_slot(ctx, t->fid_kf);
+  const int slot = svob200_frame_slot(ctx, t->fid_kfs[0]);
+  t->kf_batch[0] = 0; t->n_kfs = 1;
   std::vector<svob200_feature_ref> ftrs(N);
-  std::vector<SeedRef> srefs(S);
+  std::vector<SeedRef> srefs(S_pool);
   std::vector<int> image(N);
   std::vector<double> Tf((size_t)7 * N);
-  std::vector<svob200_seed> seeds(S, t->seed_init);
+  std::vector<svob200_seed> seeds(S_pool, t->seed_init);
   for (int b = 0; b < B; ++b) {
     for (int i = ftr_offsets[b]; i < ftr_offsets[b + 1]; ++i) {
       svob200_feature_ref& f = ftrs[i];
@@ -305,19 +440,21 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
       image[i] = b;
       memcpy(&Tf[(size_t)7 * i], T_kf_w + 7 * b, 7 * sizeof(double));
     }
-    for (int i = seed_offsets[b]; i < seed_offsets[b + 1]; ++i) {
-      SeedRef& r = srefs[i];
+    for (int q = pool_off[b]; q < pool_off[b + 1]; ++q) {
+      SeedRef& r = srefs[q];
       memset(&r, 0, sizeof(r));
-      r.px[0] = seed_px[2 * i]; r.px[1] = seed_px[2 * i + 1]; r.image = b; r.level = (uint8_t)seed_level[i]; r.kf = 0; r.batch_id = 0; r.state = 0;
+      r.image = b; r.state = 1;                                            // empty slot
+      const int i = seed_offsets[b] + (q - pool_off[b]);
+      if (i < seed_offsets[b + 1]) { r.px[0] = seed_px[2 * i]; r.px[1] = seed_px[2 * i + 1]; r.level = (uint8_t)seed_level[i]; r.kf = 0; r.batch_id = 0; r.state = 0; }
     }
   }
 #define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
   DA(t->d_ftr_off, B + 1); DA(t->d_seed_off, B + 1); DA(t->d_ftr_image, N); DA(t->d_match_ok, N); DA(t->d_has_point, N);
   DA(t->d_ftrs, N); DA(t->d_seed_refs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N);
-  DA(t->d_T_kf, 7 * (size_t)B * t->max_kfs); DA(t->d_kf_slot, t->max_kfs); DA(t->d_seed_poses, (size_t)B * t->max_kfs);
+  DA(t->d_T_kf, 7 * (size_t)B * t->max_kfs); DA(t->d_kf_slot, t->max_kfs); DA(t->d_seed_poses, (size_t)B * t->max_kfs); DA(t->d_seed_poses2, (size_t)B * t->max_kfs);
   DA(t->d_seeds, S); DA(t->d_step_in, 7 * (size_t)B + 2 * (size_t)N); DA(t->d_xyz, 3 * (size_t)N); DA(t->d_T_init, 7 * (size_t)B);
   DA(t->d_T_cur, 7 * (size_t)B); DA(t->d_depth_ref, N); DA(t->d_px_in, 2 * (size_t)N); DA(t->d_px_out, 2 * (size_t)N);
-  DA(t->d_align, B); DA(t->d_obs, S); DA(t->d_stats, B);
+  DA(t->d_align, B); DA(t->d_obs, S); DA(t->d_stats, B); DA(t->d_stats2, B);
   {
     uint8_t* p = nullptr;
     if (int e = dalloc(ctx, &p, sparse_align_scratch_bytes(N))) return e;
@@ -332,7 +469,7 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
 #undef DA
   cudaStream_t s = ctx->stream;
   CU(cudaMemcpyAsync(t->d_ftr_off, ftr_offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(t->d_seed_off, seed_offsets, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_seed_off, pool_off.data(), sizeof(int) * (B + 1), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(t->d_ftr_image, image.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(t->d_has_point, 1, N ? N : 1, s));
   CU(cudaMemcpyAsync(t->d_ftrs, ftrs.data(), sizeof(svob200_feature_ref) * N, cudaMemcpyHostToDevice, s));
@@ -367,11 +504,131 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   return SVOB200_OK;
 }
 
+int svob200_tracker_set_seed_pool(svob200_tracker* t, int capacity_per_sequence, int max_keyframes, int max_n_kfs, int reseed)
+{
+  if (!t) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (t->d_stats) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_seed_pool: call before set_keyframe");
+  if (capacity_per_sequence < 0 || max_keyframes < 1 || max_keyframes > svob200_tracker::MAX_KFS || max_n_kfs < 0 || reseed < 0 || reseed > 3)
+    return fail(ctx, SVOB200_ERR_ARG, "tracker_set_seed_pool: bad arguments");
+  t->seed_capacity = capacity_per_sequence; t->max_kfs = max_keyframes; t->max_n_kfs = max_n_kfs; t->reseed = reseed;
+  // the whole frame pool now (keyframe ring + last + cur), so that no keyframe insertion allocates
+  while ((int)t->frame_pool.size() < t->max_kfs + 2) {
+    const int64_t id = -(((-t->frame_pool[0]) & ~(int64_t)0xff) | t->next_fid++);
+    if (int e = svob200_frame_create(ctx, id, t->batch, t->cam.width, t->cam.height, t->n_levels)) return e;
+    t->frame_pool.push_back(id);
+  }
+  return SVOB200_OK;
+}
+
+int svob200_tracker_set_detector(svob200_tracker* t, int cell_size, int n_detect_levels, double detection_threshold)
+{
+  if (!t) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (cell_size <= 0 || n_detect_levels < 1 || n_detect_levels > t->n_levels) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_detector: bad arguments");
+  const int n_cells = ((t->cam.width + cell_size - 1) / cell_size) * ((t->cam.height + cell_size - 1) / cell_size);
+  if (n_cells > 8192) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_detector: grid of %d cells exceeds the kernel's table (8192)", n_cells);
+  t->det_cell = cell_size; t->det_levels = n_detect_levels; t->det_thr = detection_threshold;
+  return SVOB200_OK;
+}
+
+// The frame of the most recent step becomes a keyframe of every sequence.
+int svob200_tracker_add_keyframe(svob200_tracker* t, const float* depth_mean, const float* depth_min, int* n_new_seeds, int* n_dropped)
+{
+  if (!t || !depth_mean || !depth_min) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (!t->d_stats || t->steps_done == 0) return fail(ctx, SVOB200_ERR_ARG, "tracker_add_keyframe: needs a keyframe and at least one step");
+  if (t->chain_cell > 0) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_add_keyframe: not available in chain mode");
+  const int B = t->batch, N = t->N, S = t->S;
+  cudaStream_t s = ctx->stream;
+  if (int e = ctx_join_aux(ctx)) return e;                 // the depth filter of the last step may still be running
+  t->df_pending[0] = t->df_pending[1] = false;
+  for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);  // captured steps hold the old keyframe tables' values / frame roles
+  t->graphs.clear();
+  // 1. the keyframe's index in the ring: a free one, else the oldest keyframe leaves (its seeds with it: removeKeyframe)
+  int k = -1;
+  for (int i = 0; i < t->max_kfs; ++i) if (t->fid_kfs[i] == 0) { k = i; break; }
+  if (k < 0) {
+    // (keyframe 0 holds the reference patches of the map features and stays; its seeds age out by the batch rule anyway)
+    const int first = (N > 0 && t->max_kfs > 1) ? 1 : 0;
+    k = first;
+    for (int i = first + 1; i < t->max_kfs; ++i) if (t->kf_batch[i] < t->kf_batch[k]) k = i;
+    if (S) { kf_erase_seeds_kernel<<<(S + 255) / 256, 256, 0, s>>>(S, t->d_seed_refs, k); ++ctx->launches; }
+    t->fid_kfs[k] = 0;
+  }
+  // 2. the frame: the last step's current frame (now `last`).  Its level 0 may alias the caller's buffer: the keyframe owns a copy.
+  FrameRec* r = find_frame(ctx, t->fid_last);
+  if (!r) return fail(ctx, SVOB200_ERR_NOFRAME, "tracker_add_keyframe: last frame missing");
+  if (r->f.lvl[0] != r->own_l0) {
+    CU(cudaMemcpy2DAsync(r->own_l0, r->own_pitch0, r->f.lvl[0], r->f.pitch[0], r->f.w[0], (size_t)r->f.h[0] * B, cudaMemcpyDeviceToDevice, s));
+    r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
+    CU(cudaMemcpyAsync(ctx->d_table + r->slot, &r->f, sizeof(DevFrame), cudaMemcpyHostToDevice, s));
+  }
+  t->fid_kfs[k] = t->fid_last;
+  t->kf_batch[k] = ++t->batch_counter;                      // ++Seed::batch_counter (depth_filter.cpp:139)
+  if (t->batch_counter >= 65535) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_add_keyframe: batch counter exhausted");
+  t->n_kfs = std::max(t->n_kfs, k + 1);
+  const int slot = r->slot;
+  CU(cudaMemcpyAsync(t->d_kf_slot + k, &slot, sizeof(int), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_T_kf + 7 * (size_t)B * k, t->d_T_cur, sizeof(double) * 7 * B, cudaMemcpyDeviceToDevice, s));   // the frame's pose
+  // 3. detector scratch
+  const int gc = (t->cam.width + t->det_cell - 1) / t->det_cell, gr = (t->cam.height + t->det_cell - 1) / t->det_cell;
+  const int n_cells = gc * gr;
+  if (n_cells > 8192) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_add_keyframe: grid of %d cells exceeds the kernel's table (8192)", n_cells);
+  if (t->det_cells_alloc < n_cells) {
+#define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
+    const size_t M = (size_t)B * n_cells;
+    DA(t->d_occ, M); DA(t->d_det_keys, M); DA(t->d_det_cells, M);
+    if (!t->d_det_counts) { DA(t->d_det_counts, B); DA(t->d_kf_appended, B); DA(t->d_kf_dropped, B); DA(t->d_depth_mean, B); DA(t->d_depth_min, B); }
+#undef DA
+    t->det_cells_alloc = n_cells;
+  }
+  CU(cudaMemcpyAsync(t->d_depth_mean, depth_mean, sizeof(float) * B, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(t->d_depth_min, depth_min, sizeof(float) * B, cudaMemcpyHostToDevice, s));
+  // 4. occupancy from the frame's features (the map points matched in it), FAST + Shi-Tomasi + grid, one seed per new corner
+  CU(cudaMemsetAsync(t->d_occ, 0, (size_t)B * n_cells, s));
+  if (N) { kf_occupancy_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, t->d_ftr_image, t->d_px_out, t->d_match_ok, t->det_cell, gc, n_cells, t->d_occ); ++ctx->launches; }
+  if (launch_fast_detect(r->f, t->det_levels, t->det_cell, gc, gr, t->det_thr, t->d_occ, t->d_det_keys, t->d_det_cells, t->d_det_counts, s, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_add_keyframe: detector launch failed");
+  if (S) {
+    kf_append_seeds_kernel<<<B, 256, 0, s>>>(to_cam(&t->cam), t->d_det_cells, n_cells, t->det_thr, t->d_depth_mean, t->d_depth_min, t->d_seed_off, t->d_seed_refs,
+                                             t->d_seeds, k, t->batch_counter, t->d_kf_appended, t->d_kf_dropped);
+    ++ctx->launches;
+  }
+  if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_add_keyframe: launch error");
+  if (n_new_seeds) CU(cudaMemcpyAsync(n_new_seeds, S ? t->d_kf_appended : t->d_det_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  if (n_dropped && S) CU(cudaMemcpyAsync(n_dropped, t->d_kf_dropped, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));                             // depth_mean / depth_min are the caller's; the counts go back
+  if (n_dropped && !S) for (int b = 0; b < B; ++b) n_dropped[b] = n_new_seeds ? n_new_seeds[b] : 0;
+  return SVOB200_OK;
+}
+
+// the seed pool as it stands: 2 doubles px, level, keyframe index, batch id, state (0 alive, 1 empty) per slot (host arrays of S slots)
+int svob200_tracker_get_seed_refs(svob200_tracker* t, double* px, int* level, int* kf, int* batch_id, int* state)
+{
+  if (!t) return SVOB200_ERR_ARG;
+  svob200_ctx* ctx = t->ctx;
+  if (int e = ctx_join_aux(ctx)) return e;
+  std::vector<SeedRef> refs((size_t)std::max(t->S, 1));
+  CU(cudaMemcpyAsync(refs.data(), t->d_seed_refs, sizeof(SeedRef) * (size_t)t->S, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < t->S; ++i) {
+    if (px) { px[2 * i] = refs[i].px[0]; px[2 * i + 1] = refs[i].px[1]; }
+    if (level) level[i] = refs[i].level;
+    if (kf) kf[i] = refs[i].kf;
+    if (batch_id) batch_id[i] = refs[i].batch_id;
+    if (state) state[i] = refs[i].state;
+  }
+  return SVOB200_OK;
+}
+int svob200_tracker_num_seed_slots(svob200_tracker* t) { return t ? t->S : 0; }
+
 int svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, int pose_opt)
 {
   if (!t) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
   if (!t->d_stats) return fail(ctx, SVOB200_ERR_ARG, "tracker_set_chain: set_keyframe first");
+  if (int e = ctx_join_aux(ctx)) return e;
   CU(cudaStreamSynchronize(ctx->stream));
   for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);          // captured steps belong to the other mode
   t->graphs.clear();
@@ -404,6 +661,8 @@ int svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, in
 int svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride, int mem)
 {
   if (!t || !imgs) return SVOB200_ERR_ARG;
+  if (int e = ctx_join_aux(t->ctx)) return e;          // a depth-filter chain may still be reading the frame slots
+  t->df_pending[0] = t->df_pending[1] = false;
   return svob200_frame_upload(t->ctx, t->fid_last, imgs, stride, nullptr, mem);
 }
 
@@ -497,8 +756,25 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   }
   if (out_px) CU(cudaMemcpyAsync(out_px + 2 * (size_t)f0, t->d_px_out + 2 * (size_t)f0, sizeof(double) * 2 * (size_t)nf, cudaMemcpyDeviceToDevice, s));
   if (out_ok) CU(cudaMemcpyAsync(out_ok + f0, t->d_match_ok + f0, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToDevice, s));
+  SeedPoseRec* table = t->cur_pose_table ? t->cur_pose_table : t->d_seed_poses;
+  svob200_step_stats* d_stats = t->cur_stats ? t->cur_stats : t->d_stats;
+  if (t->df_defer) {
+    // asynchronous depth filter: this range only prepares what the df stream needs of it — its rows of the pose table (from
+    // the step's final T_cur) — and writes the tracking half of the step records; the events tell the df stream when
+    if (launch_seed_pose_table(cam, t->batch, t->n_kfs, c0, cnt, t->d_T_kf, t->d_T_cur, table, s, &ctx->launches))
+      return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seed pose table failed");
+    CU(cudaEventRecord(t->ev_pose[range], s));
+    step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
+                                          t->d_seeds, t->seed_init, t->reseed, d_stats + c0, 1, t->d_seed_refs);
+    ++ctx->launches;
+    CU(cudaEventRecord(t->ev_track[range], s));
+    if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
+    return 0;
+  }
   // 6. DepthFilter::updateSeeds(cur)
-  if (launch_seeds_update_compact(ctx->d_table, cur->slot, cam, ns, t->d_seed_refs + s0, t->d_T_kf, t->d_kf_slot, t->batch, t->n_kfs, t->d_seed_poses, c0, cnt, t->d_T_cur, t->mopts,
+  if (launch_seed_pose_table(cam, t->batch, t->n_kfs, c0, cnt, t->d_T_kf, t->d_T_cur, table, s_seeds, &ctx->launches))
+    return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seed pose table failed");
+  if (launch_seeds_update_compact(ctx->d_table, cur->slot, cam, ns, t->d_seed_refs + s0, t->d_kf_slot, t->batch, table, t->batch_counter, t->max_n_kfs, t->mopts,
                                   t->conv_thresh, t->d_seeds + s0, t->d_obs + s0, t->d_seed_scratch, t->S, s0, range, s_seeds, &ctx->launches,
                                   (marks && t->profiling) ? &t->ev[8] : nullptr))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
@@ -506,10 +782,10 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   MARK(11);
   // 7. per-sequence statistics (+ steady-state re-seeding)
   step_stats_kernel<<<cnt, 128, 0, s>>>(t->d_ftr_off + c0, t->d_seed_off + c0, t->d_align + c0, t->d_T_cur + 7 * (size_t)c0, t->d_match_ok, t->d_obs,
-                                        t->d_seeds, t->seed_init, t->reseed, t->d_stats + c0);
+                                        t->d_seeds, t->seed_init, t->reseed, d_stats + c0, 3, t->d_seed_refs);
   ++ctx->launches;
   if (t->chain_cell > 0) {
-    chain_stats_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->d_rstats + c0, t->d_pose + c0, t->chain_pose_opt, t->d_stats + c0); ++ctx->launches;
+    chain_stats_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(cnt, t->d_rstats + c0, t->d_pose + c0, t->chain_pose_opt, d_stats + c0); ++ctx->launches;
   }
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: launch error");
   MARK(12);
@@ -526,8 +802,31 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
   const int B = t->batch, N = t->N;
   cudaStream_t s = ctx->stream;
   const size_t in_bytes = sizeof(double) * (7 * (size_t)B + 2 * (size_t)N);
+  // the frame that receives the new images must not be a keyframe's (the frame of the step before a keyframe insertion is one):
+  // take a free frame of the pool, or create one (the pool holds at most max_kfs + 2 frames)
+  {
+    auto is_kf = [&](int64_t id) { for (int i = 0; i < svob200_tracker::MAX_KFS; ++i) if (t->fid_kfs[i] == id) return true; return false; };
+    if (is_kf(t->fid_cur)) {
+      if (int e = ctx_join_aux(ctx)) return e;            // frame roles change: no depth-filter chain may be in flight
+      t->df_pending[0] = t->df_pending[1] = false;
+      int64_t pick = 0;
+      for (int64_t id : t->frame_pool) if (id != t->fid_last && !is_kf(id)) { pick = id; break; }
+      if (!pick) {
+        pick = -(((-t->frame_pool[0]) & ~(int64_t)0xff) | t->next_fid++);
+        if (int e = svob200_frame_create(ctx, pick, B, t->cam.width, t->cam.height, t->n_levels)) return e;
+        t->frame_pool.push_back(pick);
+      }
+      t->fid_cur = pick;
+    }
+  }
   if (t->profiling) cudaEventRecord(t->ev[0], s);
   if (mem == SVOB200_MEM_DEVICE) {
+    // the frame slot that becomes `cur` now, the pose table and the step records of this parity were last used by the depth
+    // filter chain of two steps ago: wait for it (the chain of the previous step keeps running beside this step's tracking)
+    {
+      const int par = (int)(t->step_no & 1);
+      if (t->df_pending[par]) { CU(cudaStreamWaitEvent(s, t->df_done[par], 0)); t->df_pending[par] = false; }
+    }
     // level 0 of the current frames aliases the caller's device buffer: no copy at all
     if (int e = svob200_frame_bind_only(ctx, t->fid_cur, cur_imgs, stride)) return e;
     const bool use_graph = !t->profiling && B <= t->graph_max_batch && t->graph_max_batch > 0;
@@ -541,36 +840,77 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
       for (auto& e : t->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     // direct launches of a big batch: sub-ranges alternate between two streams (chain mode keeps one range: its reprojector
-    // scratch is shared)
+    // scratch is shared), and the depth filter of the whole batch follows on its own stream
     int n_ranges = 1;
-    if (!use_graph && !t->profiling && t->chain_cell <= 0) n_ranges = std::max(1, std::min(t->ranges, B / std::max(1, t->min_range)));
+    if (!use_graph && !t->profiling && t->chain_cell <= 0) n_ranges = std::max(1, std::min(std::min(t->ranges, 4), B / std::max(1, t->min_range)));
     if (n_ranges > 1 && !t->range_stream) {
       CU(cudaStreamCreateWithFlags(&t->range_stream, cudaStreamNonBlocking));
       for (auto& e : t->range_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    const bool async_df = t->async_df && !use_graph && !t->profiling && t->chain_cell <= 0 && t->S > 0;
+    if (async_df && !t->df_stream) {
+      CU(cudaStreamCreateWithFlags(&t->df_stream, cudaStreamNonBlocking));
+      if (int e = ctx_add_aux(ctx, t->df_stream)) return e;
+      for (auto& e : t->df_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : t->ev_pose) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : t->ev_track) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int par = (int)(t->step_no & 1);
+    if (!async_df && (t->df_pending[0] || t->df_pending[1])) {     // a step that runs the depth filter in place after asynchronous ones
+      if (int e = ctx_join_aux(ctx)) return e;
+      t->df_pending[0] = t->df_pending[1] = false;
+    }
     const int rc = graph_or_direct(t, use_graph, key, [&]() -> int {
+      if (async_df) {
+        t->df_defer = 1;
+        t->cur_pose_table = par ? t->d_seed_poses2 : t->d_seed_poses;
+        t->cur_stats = par ? t->d_stats2 : t->d_stats;
+      }
+      int e0 = 0;
       if (n_ranges > 1) {
         CU(cudaEventRecord(t->range_ev[0], s));
         CU(cudaStreamWaitEvent(t->range_stream, t->range_ev[0], 0));
-        for (int r = 0; r < n_ranges; ++r) {
+        for (int r = 0; r < n_ranges && !e0; ++r) {
           const int c0 = (int)((long long)B * r / n_ranges), c1 = (int)((long long)B * (r + 1) / n_ranges);
-          if (int e0 = run_range(t, c0, c1, T_last_w, last_px, false, px_refined, match_ok, (r & 1) ? t->range_stream : s, r)) return e0;
+          e0 = run_range(t, c0, c1, T_last_w, last_px, false, px_refined, match_ok, (r & 1) ? t->range_stream : s, r);
         }
-        CU(cudaEventRecord(t->range_ev[1], t->range_stream));
-        CU(cudaStreamWaitEvent(s, t->range_ev[1], 0));
+        if (!e0) { CU(cudaEventRecord(t->range_ev[1], t->range_stream)); CU(cudaStreamWaitEvent(s, t->range_ev[1], 0)); }
       } else {
         t->forking = use_graph && t->graph_fork;     // only a capture runs this body when use_graph is set
-        const int e0 = run_range(t, 0, B, T_last_w, last_px, true, px_refined, match_ok);
+        e0 = run_range(t, 0, B, T_last_w, last_px, true, px_refined, match_ok);
         t->forking = false;
-        if (e0) return e0;
       }
-      if (stats) CU(cudaMemcpyAsync(stats, t->d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
+      svob200_step_stats* d_stats = t->cur_stats ? t->cur_stats : t->d_stats;
+      SeedPoseRec* table = t->cur_pose_table;
+      t->df_defer = 0; t->cur_pose_table = nullptr; t->cur_stats = nullptr;
+      if (e0) return e0;
+      if (async_df) {
+        // the depth filter of the whole batch on its own stream: it starts as soon as every range has its pose rows, and its
+        // half of the step records (and their copy to the caller) follows the tracking half
+        cudaStream_t df = t->df_stream;
+        for (int r = 0; r < n_ranges; ++r) CU(cudaStreamWaitEvent(df, t->ev_pose[r], 0));
+        FrameRec* cur = find_frame(ctx, t->fid_cur);
+        if (launch_seeds_update_compact(ctx->d_table, cur->slot, to_cam(&t->cam), t->S, t->d_seed_refs, t->d_kf_slot, t->batch, table, t->batch_counter, t->max_n_kfs, t->mopts,
+                                        t->conv_thresh, t->d_seeds, t->d_obs, t->d_seed_scratch, t->S, 0, 0, df, &ctx->launches, nullptr))
+          return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: seeds_update failed");
+        for (int r = 0; r < n_ranges; ++r) CU(cudaStreamWaitEvent(df, t->ev_track[r], 0));
+        step_stats_kernel<<<B, 128, 0, df>>>(t->d_ftr_off, t->d_seed_off, t->d_align, t->d_T_cur, t->d_match_ok, t->d_obs, t->d_seeds, t->seed_init,
+                                             t->reseed, d_stats, 2, t->d_seed_refs);
+        ++ctx->launches;
+        if (stats) CU(cudaMemcpyAsync(stats, d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, df));
+        CU(cudaEventRecord(t->df_done[par], df));
+        t->df_pending[par] = true;
+        return 0;
+      }
+      if (stats) CU(cudaMemcpyAsync(stats, d_stats, sizeof(svob200_step_stats) * B, cudaMemcpyDeviceToDevice, s));
       return 0;
     });
     if (rc) return rc;
   } else {
     // host buffers: the frame copy is split into chunks on a copy stream so that chunk c+1 crosses
     // PCIe while chunk c is being processed; one small H2D for the per-step inputs, one D2H for results
+    if (int e = ctx_join_aux(ctx)) return e;           // a depth-filter chain of earlier device-memory steps
+    t->df_pending[0] = t->df_pending[1] = false;
     FrameRec* r = find_frame(ctx, t->fid_cur);
     if (r->f.lvl[0] != r->own_l0) {   // drop an earlier device binding
       r->f.lvl[0] = r->own_l0; r->f.pitch[0] = r->own_pitch0; r->f.img_stride[0] = (unsigned long long)r->own_pitch0 * r->f.h[0];
@@ -669,6 +1009,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     if (match_ok) memcpy(match_ok, h_ok, sizeof(int) * (size_t)N);
   }
   std::swap(t->fid_last, t->fid_cur);       // the current frame becomes the last frame
+  ++t->step_no; ++t->steps_done;
   return SVOB200_OK;
 }
 
@@ -676,6 +1017,7 @@ int svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out)
 {
   if (!t || !out) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
+  if (int e = ctx_join_aux(ctx)) return e;
   CU(cudaMemcpyAsync(out, t->d_seeds, sizeof(svob200_seed) * (size_t)t->S, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return SVOB200_OK;
@@ -720,6 +1062,7 @@ int svob200_tracker_get_seed_obs(svob200_tracker* t, svob200_seed_obs* out)
 {
   if (!t || !out) return SVOB200_ERR_ARG;
   svob200_ctx* ctx = t->ctx;
+  if (int e = ctx_join_aux(ctx)) return e;
   CU(cudaMemcpyAsync(out, t->d_obs, sizeof(svob200_seed_obs) * (size_t)t->S, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return SVOB200_OK;

@@ -58,6 +58,7 @@ struct Runtime {
   std::unordered_map<int, CacheEntry> cache;          // Frame::id_ -> mirror
   std::unordered_map<long long, int64_t> scratch;     // (w,h,levels) -> temp frame id for bare cv::Mat arguments
   size_t capacity = 64;
+  int pin_depth = 0;         // > 0 while a call is marshalling: no mirror is evicted until it is over (the cache may overshoot)
   unsigned long long clock = 0;
   int64_t next_temp_id = (int64_t)1 << 40;
 };
@@ -120,6 +121,7 @@ void matcher_opts_of(const Matcher::Options& o, svob200_matcher_opts* m)
 
 void evict_locked(Runtime& r)
 {
+  if (r.pin_depth > 0) return;
   while (r.cache.size() > r.capacity) {
     auto victim = r.cache.begin();
     for (auto it = r.cache.begin(); it != r.cache.end(); ++it) if (it->second.stamp < victim->second.stamp) victim = it;
@@ -187,6 +189,16 @@ thread_local int g_last_iters[SVOB200_MAX_LEVELS] = {0, 0, 0, 0, 0, 0, 0, 0};
 thread_local int g_last_exact = 0;
 
 typedef std::lock_guard<std::recursive_mutex> Lock;
+
+// Every frame a call touches stays resident until the svob200_* call that uses it has returned: a call may reference more
+// distinct frames than the cache holds (Reprojector::reprojectMap walks the observation lists of every candidate point, and
+// the reference's Android Config keeps an unbounded map), and evicting while marshalling would release a mirror the same call
+// already referenced.  Construct under the runtime lock; the eviction runs when the outermost scope ends.
+struct PinFrames {
+  Runtime& r;
+  PinFrames() : r(rt()) { ++r.pin_depth; }
+  ~PinFrames() { if (--r.pin_depth == 0 && r.ctx) evict_locked(r); }
+};
 
 }  // namespace
 
@@ -390,6 +402,7 @@ bool Matcher::findMatchDirect(const Point& pt, const Frame& cur_frame, Vector2d&
   svob200_match_result res;
   {
     Lock lk(rt().mu);
+    b200::PinFrames pin;
     svob200_ctx* ctx = ctx_locked();
     const int64_t ref_id = b200::ensure_frame_locked(*ref_ftr_->frame);
     const int64_t cur_id = b200::ensure_frame_locked(cur_frame);
@@ -418,6 +431,7 @@ bool Matcher::findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_f
   svob200_epi_result res;
   {
     Lock lk(rt().mu);
+    b200::PinFrames pin;
     svob200_ctx* ctx = ctx_locked();
     const int64_t ref_id = b200::ensure_frame_locked(ref_frame);
     const int64_t cur_id = b200::ensure_frame_locked(cur_frame);
@@ -494,6 +508,7 @@ size_t SparseImgAlign::run(FramePtr ref_frame, FramePtr cur_frame)
   svob200_align_result res;
   {
     Lock lk(rt().mu);
+    b200::PinFrames pin;
     svob200_ctx* ctx = ctx_locked();
     const int64_t ref_id = b200::ensure_frame_locked(*ref_frame_);
     const int64_t cur_id = b200::ensure_frame_locked(*cur_frame_);
@@ -634,6 +649,7 @@ void B200DepthFilter::updateSeeds(FramePtr frame)
   b200::pose7(frame->T_f_w_, T_cur_w);
   {
     Lock lk(rt().mu);
+    b200::PinFrames pin;
     svob200_ctx* ctx = ctx_locked();
     const int64_t cur_id = b200::ensure_frame_locked(*frame);
     int i = 0;
@@ -742,6 +758,7 @@ void Reprojector::reprojectMap(FramePtr frame, std::vector<std::pair<FramePtr, s
     std::vector<svob200_feature_ref> obs;
     std::vector<double> T_obs;
     Lock lk(rt().mu);
+    b200::PinFrames pin;
     svob200_ctx* ctx = ctx_locked();
     const int64_t cur_id = b200::ensure_frame_locked(*frame);
     const SE3 ident;

@@ -35,9 +35,11 @@ CFG_NAME = "C2"
 TEX_SIZE = 2048
 PPM = 400.0
 PLANE_Z = 2.0
+KF_RING, KF_MAX_N_KFS = 4, 3             # keyframes resident / DepthFilter::Options::max_n_kfs (--keyframe-every)
 KF_INDEX = 0
 POOL_INDICES = (36, 39, 42, 45)     # trajectory frames cycled (ping-pong) as the live stream
 DEPTH_MEAN, DEPTH_MIN = 2.4, 1.2
+DEPTH_MIN_YOUNG = 0.3                  # --seed-regime young: a wide depth prior (z_range = 1 / 0.3), so a fresh seed's epipolar segment is tens of pixels long
 CHAIN_CELL, CHAIN_MAX_FTS = 30, 120   # Config::gridSize / maxFts defaults (config.cpp)
 
 
@@ -60,6 +62,10 @@ def parse_args():
     ap.add_argument("--chain", action="store_true", help="run the step in chain mode in BOTH arms: reprojector grid rules (cell 30, maxFts 120) + "
                     "pose optimiser between alignment and the depth filter (FrameHandlerMono::processFrame Steps 2-3)")
     ap.add_argument("--no-widen", action="store_true", help="skip the timing of the SURVEY 8f operators (reprojector, optimizers, YUV, seed init)")
+    ap.add_argument("--keyframe-every", type=int, default=0, metavar="K",
+                    help="insert a keyframe every K frames INSIDE the timed region, in both arms (svob200_tracker_add_keyframe / "
+                         "DepthFilter::addKeyframe: occupancy, FAST + Shi-Tomasi + grid, seed initialisation; seeds of up to 4 keyframes, "
+                         "ageing by max_n_kfs = 3, finished seeds leave the pool): FAST shows up in a step time")
     return ap.parse_args()
 
 
@@ -106,6 +112,23 @@ def backproject_many(cfg, T_f_w, px):
 def project_many(cfg, T_f_w, pts):
     pc = q_rot_many(T_f_w[:, None, 3:], pts) + T_f_w[:, None, :3]
     return np.stack([cfg["fx"] * pc[..., 0] / pc[..., 2] + cfg["cx"], cfg["fy"] * pc[..., 1] / pc[..., 2] + cfg["cy"]], -1)
+
+
+def natural_texture(size):
+    """A texture with natural-image statistics for the detector: smooth shading (white noise, box-blurred to a ~24-px correlation
+    length) plus a few dozen flat rectangles of random grey level (sharp edges and corners)."""
+    rng = np.random.RandomState(12345)
+    a = rng.randint(0, 256, (size, size)).astype(np.float64)
+    for _ in range(3):
+        for ax in (0, 1):
+            c = np.cumsum(np.concatenate([a.take(range(-12, 0), axis=ax), a, a.take(range(0, 13), axis=ax)], axis=ax), axis=ax)
+            a = (np.take(c, range(25, 25 + size), axis=ax) - np.take(c, range(0, size), axis=ax)) / 25.0
+    a = (a - a.min()) / (a.max() - a.min()) * 160.0 + 40.0
+    for _ in range(60):
+        x0, y0 = rng.randint(0, size - 200, 2)
+        ww, hh = rng.randint(40, 200, 2)
+        a[y0:y0 + hh, x0:x0 + ww] = rng.randint(20, 236)
+    return np.clip(a, 0, 255).astype(np.uint8)
 
 
 def select_batch(cells, thr, n):
@@ -179,7 +202,7 @@ class ClockSampler:
 CPU_FRAMES_PER_STEP = 16   # a CPU "step" = this many consecutive frames of every sampled sequence (bounded sample, ~10-30 core-s per run)
 
 
-def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False, regime="steady", o3=False, dropin=False):
+def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False, regime="steady", o3=False, dropin=False, kf_every=0):
     """Times the front-end step of `n_seqs` independent sequences on the host cores.  Uses the real
     reference (oracle/_ref/libsvo_ref.so; o3: the -O3 / AVX2 / FMA build of the same sources; dropin: the same harness over
     the B200 drop-in) when it was built, else the C restatement.  One timed step = `inner` consecutive frames of every
@@ -207,8 +230,16 @@ def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP,
         _, fcells = oracle.fast_detect(pyr, cfg["n_pyr"], fc, ft)
         _, scells = oracle.fast_detect(pyr, cfg["n_pyr"], sc, st)
         kf = frontend.keyframe_setup(cfg, poses[i, 0], fcells, scells, ft, st, PLANE_Z, recycle=True)
-        args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, DEPTH_MEAN, DEPTH_MIN, reseed)
+        args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, DEPTH_MEAN,
+                DEPTH_MIN_YOUNG if regime == "young" else DEPTH_MIN, reseed)
+        if kf_every:
+            args = args[:-1] + (3,)          # the reference's list semantics: finished seeds leave the list
         s = RefSeq(ref, *args) if kind != "port" else OracleSeq(oracle, *args)
+        if kf_every:
+            if kind != "port":
+                s.set_pool(KF_RING, KF_MAX_N_KFS, 3, sc, cfg["n_pyr"], st)
+            else:
+                s.set_pool(KF_RING, KF_MAX_N_KFS, 3); s.set_detector(sc, cfg["n_pyr"], st)
         s.set_keyframe(imgs[0], poses[i, 0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
         if chain:
             s.set_chain(CHAIN_CELL, CHAIN_MAX_FTS, 1)
@@ -227,6 +258,8 @@ def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP,
                 a, b = order[j], order[j + 1]
                 t0 = time.perf_counter()
                 st = seqs[i][0].step(seqs[i][1][b], poses[i, 1 + a], seqs[i][2][a])
+                if kf_every and (j + 1) % kf_every == 0:
+                    seqs[i][0].add_keyframe(DEPTH_MEAN, DEPTH_MIN)
                 frame_s[i].append(time.perf_counter() - t0)
             return st
 
@@ -285,7 +318,7 @@ def pinned_array(ctx, shape, dtype):
 class GpuWorkload:
     """Everything the timed loops need, resident: tracker, frame pool on device + pinned host, per-step inputs."""
 
-    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME, chain=False, regime="steady"):
+    def __init__(self, ctx, capi, cfg, seq_ids, tex_dev=None, cfg_name=CFG_NAME, chain=False, regime="steady", kf_every=0):
         self.ctx, self.capi, self.cfg = ctx, capi, cfg
         B = len(seq_ids)
         self.B = B
@@ -329,7 +362,13 @@ class GpuWorkload:
         pt_world = backproject_many(cfg, poses[:, 0], kf_px)
         self.kf = dict(kf_px=kf_px, kf_level=kf_level, pt_world=pt_world, seed_px=seed_px, seed_level=seed_level)
         self.trk = capi.Tracker(ctx, cam, B, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0,
-                                DEPTH_MEAN, DEPTH_MIN, 2 if regime == "young" else 1)
+                                DEPTH_MEAN, DEPTH_MIN_YOUNG if regime == "young" else DEPTH_MIN, 2 if regime == "young" else 1)
+        self.kf_every = kf_every
+        self.kf_ms = []
+        if kf_every:
+            n_cells = -(-w // sc) * -(-h // sc)
+            self.trk.set_seed_pool(S + (KF_RING - 1) * n_cells, KF_RING, KF_MAX_N_KFS, 3)
+            self.trk.set_detector(sc, cfg["n_pyr"], st)
         self.trk.set_keyframe(self.kf_host, poses[:, 0], np.arange(B + 1) * N, kf_px.reshape(-1, 2), kf_level.reshape(-1),
                               pt_world.reshape(-1, 3), np.arange(B + 1) * S, seed_px.reshape(-1, 2), seed_level.reshape(-1))
         if chain:
@@ -380,6 +419,10 @@ class GpuWorkload:
             self.trk.step_raw(self.pool_dev[b], w, self.in_dev[a][0], self.in_dev[a][1], self.stats_dev, mem)
         else:
             self.trk.step_raw(self.pool_host[b][1], w, self.in_host[a][0], self.in_host[a][1], self.stats_ptr, mem)
+        if self.kf_every and (k + 1) % self.kf_every == 0:
+            t0 = time.perf_counter()
+            self.kf_new, self.kf_dropped = self.trk.add_keyframe(DEPTH_MEAN, DEPTH_MIN)     # synchronises (the counts go back to the host)
+            self.kf_ms.append((time.perf_counter() - t0) * 1e3)
 
 
 def seed_workload_of(obs, capi, regime):
@@ -411,7 +454,7 @@ def run_b200(args, rank, world, local_rank):
     total, per, rng = sharding.shard(args.seqs, rank, world)     # contiguous block partition
     seq_ids = list(rng)
     t_setup = time.time()
-    wl = GpuWorkload(ctx, capi, cfg, seq_ids, chain=args.chain, regime=args.seed_regime)
+    wl = GpuWorkload(ctx, capi, cfg, seq_ids, chain=args.chain, regime=args.seed_regime, kf_every=args.keyframe_every)
     t_setup = time.time() - t_setup
     K, W = args.steps, args.warmup
     order = ping_pong(len(POOL_INDICES), 2 * (W + K) + 8)
@@ -429,7 +472,7 @@ def run_b200(args, rank, world, local_rank):
     wl.reset()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        time.sleep(0.25)                    # nvidia-smi needs ~0.2 s before its first sample
+        time.sleep(1.0)                     # nvidia-smi needs most of a second before its first sample
     t_load0 = datetime.datetime.now()
     for k in range(W):
         wl.step(order, k, capi.MEM_DEVICE)
@@ -567,6 +610,7 @@ def run_b200(args, rank, world, local_rank):
                                    "block-sharded over %d GPU(s); step = 1 frame of every sequence" % (total, N, S, world),
                        "sequences_total": total, "sequences_per_gpu": per, "frame_pool": list(POOL_INDICES),
                        "seed_regime": args.seed_regime,
+                       "keyframe_every": args.keyframe_every or None,
                        "step": ("chain: reprojector grid rules (cell %d, maxFts %d) + pose optimiser between alignment and the depth filter"
                                 % (CHAIN_CELL, CHAIN_MAX_FTS)) if args.chain else "refine every map point of the keyframe (batched superset of the reprojector)",
                        "l2": "inputs larger than L2 (%.0f MB of frames per step per GPU)" % (per * cfg["w"] * cfg["h"] / 1e6)},
@@ -578,6 +622,12 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks, "roofline": roofline, "roofline_pyramid": roofline_pyr, "stages": stages, "seed_workload": seed_workload,
             "zmssd_evals_per_s": round(float(obs["n_evals"].sum()) / max(stage_acc.get("seeds_search", 0.0), 1e-9) * 1e3, 1),
             "sequence_stats": seq_stats,
+            "keyframes": None if not args.keyframe_every else {
+                "every": args.keyframe_every, "ring": KF_RING, "max_n_kfs": KF_MAX_N_KFS,
+                "add_keyframe_ms_host_wall_median": round(float(np.median(wl.kf_ms)), 3) if wl.kf_ms else None,
+                "note": "wall time of svob200_tracker_add_keyframe incl. the join of the in-flight depth filter of the preceding step, the level-0 copy, "
+                        "occupancy, FAST + Shi-Tomasi + grid over %d frames, seed initialisation and the read-back of the counts" % per,
+                "new_seeds_mean": float(np.mean(wl.kf_new)) if wl.kf_ms else None, "dropped_mean": float(np.mean(wl.kf_dropped)) if wl.kf_ms else None},
             "setup_s": round(t_setup, 1),
         }
     return out, ctx, wl
@@ -702,8 +752,22 @@ def widen_rows(ctx, capi, wl, cfg, peak, steps=5, warm=2):
         alg = B * (408000.0 + fnc * 20)
         out["fast_detect"] = {"ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1), "Mpx_per_s": round(B * 408000 / ms / 1e3, 1),
                               "algorithmic_bytes": int(alg), "alg_GBps": round(alg / ms / 1e6, 1), "hbm_frac": round(alg / ms / 1e6 / peak, 4),
-                              "bound": "integer issue (ncu: 75% issue-slot utilisation, 6.6 M warp instructions per VGA frame on this texture, "
-                                       "where more than half of the pixels pass the 4-point quick test)"}
+                              "bound": "integer ALU pipe (ncu r2b: ALU pipe 79 % busy, 2.4 M warp instructions per VGA frame; every pixel is scored with "
+                                       "16-bit-lane VIMNMX3, 24 % of this texture's pixels are FAST corners)"}
+        # ---- the same detector on a texture with natural-image statistics (smooth shading + a few objects with sharp edges: FAST's
+        # share of corners is ~1 % there, against 24 % on the bench texture, whose blurred noise makes every fourth pixel a corner)
+        nat = natural_texture(TEX_SIZE)
+        d_nat = ctx.dev_alloc(nat.nbytes); frees.append(d_nat)
+        ctx.dev_upload(d_nat, nat)
+        d_nimg = ctx.dev_alloc(B * w * h); frees.append(d_nimg)
+        ctx.synth_render(d_nat, TEX_SIZE, PPM, PLANE_Z, wl.cam, wl.poses[:, 0], d_nimg)
+        ctx.frame_create(904, B, w, h, cfg["n_levels"])
+        ctx._ck(L.svob200_frame_upload(ctx.h, 904, V(d_nimg), w, None, capi.MEM_DEVICE))
+        ms_nat = timed(lambda: ctx._ck(L.svob200_fast_detect(ctx.h, 904, cfg["n_pyr"], fcell, fthr, None, V(d_fc), V(d_fn), capi.MEM_DEVICE)))
+        fn = np.zeros(B, np.int32); ctx.dev_download(fn, d_fn)
+        ctx.frame_release(904)
+        out["fast_detect"]["natural_texture"] = {"ms": round(ms_nat, 4), "frames_per_s": round(B / ms_nat * 1e3, 1), "alg_GBps": round(alg / ms_nat / 1e6, 1),
+                                                 "hbm_frac": round(alg / ms_nat / 1e6 / peak, 4), "features_mean": float(fn.mean())}
         # ---- seed initialisation on the keyframe batch
         d_eoff, d_epx = dev(np.arange(B + 1, dtype=np.int32) * N), dev(wl.kf["kf_px"].reshape(-1, 2))
         d_dm, d_dn = dev(np.full(B, DEPTH_MEAN, np.float32)), dev(np.full(B, DEPTH_MIN, np.float32))
@@ -876,7 +940,7 @@ def main():
             emit(json.dumps(line))
             return
         n = args.cpu_seqs or max(8, 4 * threads)
-        r = cpu_arm(CFG_NAME, n, args.steps, args.warmup, threads, chain=args.chain, regime=args.seed_regime)
+        r = cpu_arm(CFG_NAME, n, args.steps, args.warmup, threads, chain=args.chain, regime=args.seed_regime, kf_every=args.keyframe_every)
         line = {"impl": "reference", "metric": METRIC, "value": round(r["fps"], 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["seconds"] / args.steps * 1e3, 3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 pixels / f32 photometric / f64 geometry",
@@ -884,7 +948,7 @@ def main():
                 "config": {"workload": "C5: independent C2 sequences (640x480, 4-level pyramid, %d map features, %d seeds each); "
                                        "step = 1 frame of every sequence of the sample" % (cfg["n_features"], cfg["n_seeds"]),
                            "sequences_total": args.seqs, "sample_sequences": n, "frames_per_sequence_per_step": r["inner"],
-                           "seed_regime": args.seed_regime,
+                           "seed_regime": args.seed_regime, "keyframe_every": args.keyframe_every or None,
                            "step": "chain (reprojector + pose optimiser)" if args.chain else "refine every map point of the keyframe"},
                 "cpu_baseline": {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                  "sample": "%d sequences x %d steps x %d frames (+%d warm-up steps), %d host threads, %.1f s wall"
@@ -926,7 +990,7 @@ def main():
                         out["latency"][name]["cpu_reference_1_thread"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_seqs or max(8, 4 * threads)
-            r = cpu_arm(CFG_NAME, n, 10, 1, threads, chain=args.chain, regime=args.seed_regime)
+            r = cpu_arm(CFG_NAME, n, 10, 1, threads, chain=args.chain, regime=args.seed_regime, kf_every=args.keyframe_every)
             out["cpu_baseline"] = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": threads, "kind": r["kind"],
                                    "sample": "%d sequences x 10 steps x %d frames (+1 warm-up step), %d host threads, %.1f s wall"
                                              % (n, r["inner"], threads, r["seconds"]),

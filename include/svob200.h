@@ -202,8 +202,9 @@ int svob200_epipolar_match(svob200_ctx* ctx, int64_t cur_frame_id, const svob200
  * replaces: DepthFilter::updateSeeds loop body (depth_filter.cpp:250-340), DepthFilter::updateSeed
  *           (:368-391), DepthFilter::computeTau (:396-416), Seed ctor (:36-45) */
 typedef struct { float a, b, mu, z_range, sigma2; } svob200_seed;
+/* status 0: empty slot of a tracker's seed pool; TOO_OLD: erased by the ageing rule (depth_filter.cpp:258-261) */
 enum { SVOB200_SEED_BEHIND = 1, SVOB200_SEED_NOT_IN_FRAME = 2, SVOB200_SEED_NO_MATCH = 3,
-       SVOB200_SEED_UPDATED = 4, SVOB200_SEED_CONVERGED = 5, SVOB200_SEED_NAN_ERASED = 6 };
+       SVOB200_SEED_UPDATED = 4, SVOB200_SEED_CONVERGED = 5, SVOB200_SEED_NAN_ERASED = 6, SVOB200_SEED_TOO_OLD = 7 };
 typedef struct {
   int status; int search_level; int zmssd_best; int n_evals;
   double z; double px_cur[2]; double epi_length;
@@ -277,6 +278,27 @@ int  svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int s
                                   const double* pt_world, const int* seed_offsets, const double* seed_px,
                                   const int* seed_level);
 int  svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int stride, int mem);
+/* ---- keyframe insertion inside the tracker: DepthFilter::addKeyframe -> initializeSeeds (depth_filter.cpp:109-151), the ageing
+ * rule of updateSeeds (:258-261), DepthFilter::removeKeyframe (:153-170) and the erase-on-convergence list semantics (:314-338),
+ * device-resident: detect -> seed init -> update never leaves the GPU.
+ * svob200_tracker_set_seed_pool (before set_keyframe): every sequence owns `capacity_per_sequence` seed slots (at least the
+ *   seeds set_keyframe gives it); up to `max_keyframes` keyframes stay resident (the oldest leaves, its seeds with it); seeds
+ *   older than `max_n_kfs` keyframe insertions are erased (DepthFilter::Options::max_n_kfs, default 3); reseed as in
+ *   svob200_tracker_create, plus 3 = finished seeds (converged / NaN) leave the pool like they leave the reference's list.
+ * svob200_tracker_set_detector: FastDetector(cell size = Config::gridSize, levels = Config::nPyrLevels) and the threshold
+ *   DepthFilter::initializeSeeds passes (Config::triangMinCornerScore).
+ * svob200_tracker_add_keyframe: the frame of the most recent step becomes a keyframe of every sequence, with the pose the step
+ *   gave it: occupancy grid from the frame's features (= the map points matched in it, AbstractDetector::setExistingFeatures),
+ *   FAST + Shi-Tomasi + grid selection on its pyramid, one Seed(ftr, depth_mean, depth_min) per new corner in cell order
+ *   (batch_id = ++Seed::batch_counter) into the empty slots of the sequence's pool.  depth_mean / depth_min: one per sequence,
+ *   host memory (FrameHandlerMono passes frame_utils::getSceneDepth's mean and 0.5 * min).  n_new_seeds / n_dropped (host,
+ *   one int per sequence, may be NULL): seeds created / corners that found no empty slot.
+ * svob200_tracker_get_seed_refs: the pool slot by slot (host arrays of svob200_tracker_num_seed_slots entries, any may be NULL). */
+int  svob200_tracker_set_seed_pool(svob200_tracker* t, int capacity_per_sequence, int max_keyframes, int max_n_kfs, int reseed);
+int  svob200_tracker_set_detector(svob200_tracker* t, int cell_size, int n_detect_levels, double detection_threshold);
+int  svob200_tracker_add_keyframe(svob200_tracker* t, const float* depth_mean, const float* depth_min, int* n_new_seeds, int* n_dropped);
+int  svob200_tracker_get_seed_refs(svob200_tracker* t, double* px, int* level, int* kf, int* batch_id, int* state);
+int  svob200_tracker_num_seed_slots(svob200_tracker* t);
 /* Chain mode (call after set_keyframe): between sparse alignment and the depth filter the step runs
  * Reprojector::reprojectMap over the keyframe's map points (grid of cell_size, first success per cell, max_fts) and, with
  * pose_opt != 0, pose_optimizer::optimizeGaussNewton on the matched features — FrameHandlerMono::processFrame's Step 2 and
@@ -287,7 +309,12 @@ int  svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, i
 /* cur_imgs: batch images; T_last_w: 7 doubles per sequence (pose of the last frame); last_px: 2 doubles
  * per map feature (its pixel in the last frame).  stats (batch), px_refined (2 per feature), match_ok
  * (1 per feature) may be NULL.  mem tells where ALL pointer arguments live; in device mode level 0 of
- * the current frame aliases cur_imgs (which must stay valid through the next step) and nothing syncs. */
+ * the current frame aliases cur_imgs and nothing syncs.  For batches above 64 sequences the device-mode step runs the depth
+ * filter ASYNCHRONOUSLY on its own stream, like the reference's depth-filter thread (depth_filter.cpp:63-103): the seed update
+ * of frame k overlaps the tracking chain of frame k+1, so cur_imgs must stay valid through the next TWO steps, and the seed
+ * half of `stats` (n_seeds_*), svob200_tracker_get_seeds and _get_seed_obs are complete only after a joining call
+ * (svob200_ctx_sync, svob200_ctx_timer_stop_ms, svob200_dev_download, the getters themselves, any host-memory step);
+ * px_refined, match_ok and the tracking half of `stats` are ordered on the context's stream as before. */
 int  svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride, const double* T_last_w,
                           const double* last_px, svob200_step_stats* stats, double* px_refined, int* match_ok, int mem);
 int  svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out /*host*/);

@@ -602,15 +602,45 @@ class OracleSeq(_SeqBase):
         self.lib.svo_oracle_seq_set_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         self.lib.svo_oracle_seq_set_chain(self.h, int(cell_size), int(max_fts), int(pose_opt))
 
+    def num_slots(self):
+        self.lib.svo_oracle_seq_num_slots.argtypes = [C.c_void_p]
+        return int(self.lib.svo_oracle_seq_num_slots(self.h))
+
     def seeds(self):
+        self.S = self.num_slots()
         arr = (Seed * max(self.S, 1))()
         self.lib.svo_oracle_seq_get_seeds(self.h, arr)
         return np.array([(s.a, s.b, s.mu, s.z_range, s.sigma2) for s in arr[:self.S]], np.float32).reshape(self.S, 5)
+
+    # ---- keyframe insertion (DepthFilter::addKeyframe -> initializeSeeds, ageing, removeKeyframe)
+    def set_pool(self, max_kfs=4, max_n_kfs=3, reseed=3):
+        self.lib.svo_oracle_seq_set_pool.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.lib.svo_oracle_seq_set_pool(self.h, int(max_kfs), int(max_n_kfs), int(reseed))
+
+    def set_detector(self, cell, levels, thr):
+        self.lib.svo_oracle_seq_set_detector.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        self.lib.svo_oracle_seq_set_detector(self.h, int(cell), int(levels), float(thr))
+
+    def add_keyframe(self, depth_mean, depth_min):
+        self.lib.svo_oracle_seq_add_keyframe.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        n = int(self.lib.svo_oracle_seq_add_keyframe(self.h, float(depth_mean), float(depth_min)))
+        self.S = self.num_slots()
+        return n
+
+    def seed_refs(self):
+        """(px[S,2], level, kf, batch_id, state) of every slot; state 0 = alive"""
+        S = self.num_slots()
+        px = np.zeros((max(S, 1), 2)); lv = np.zeros(max(S, 1), np.int32); kf = np.zeros(max(S, 1), np.int32)
+        bt = np.zeros(max(S, 1), np.int32); st = np.zeros(max(S, 1), np.int32)
+        self.lib.svo_oracle_seq_get_seed_refs.argtypes = [C.c_void_p, c_dp, c_ip, c_ip, c_ip, c_ip]
+        self.lib.svo_oracle_seq_get_seed_refs(self.h, _p(px, c_dp), _p(lv, c_ip), _p(kf, c_ip), _p(bt, c_ip), _p(st, c_ip))
+        return px[:S], lv[:S], kf[:S], bt[:S], st[:S]
 
     def seed_obs(self):
         """per-seed observation of the last step, same fields as svob200_seed_obs"""
         dt = np.dtype([("status", "i4"), ("search_level", "i4"), ("zmssd_best", "i4"), ("n_evals", "i4"), ("z", "f8"),
                        ("px_cur", "f8", 2), ("epi_length", "f8")], align=True)
+        self.S = self.num_slots()
         out = np.zeros(max(self.S, 1), dt)
         self.lib.svo_oracle_seq_get_seed_obs.argtypes = [C.c_void_p, C.c_void_p]
         self.lib.svo_oracle_seq_get_seed_obs(self.h, out.ctypes.data)
@@ -655,6 +685,24 @@ class RefSeq(_SeqBase):
 
     def set_last(self, img):
         self.lib.svo_ref_seq_set_last(self.h, _p(u8(img), c_u8p))
+
+    # ---- keyframe insertion through the reference's own DepthFilter::addKeyframe / removeKeyframe and FastDetector
+    def set_pool(self, max_kfs=4, max_n_kfs=3, reseed=3, det_cell=30, det_levels=3, det_thr=20.0):
+        """call before set_keyframe"""
+        self.lib.svo_ref_seq_set_pool.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        self.lib.svo_ref_seq_set_pool(self.h, int(max_kfs), int(max_n_kfs), int(reseed), int(det_cell), int(det_levels), float(det_thr))
+
+    def add_keyframe(self, depth_mean, depth_min):
+        self.lib.svo_ref_seq_add_keyframe.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        return int(self.lib.svo_ref_seq_add_keyframe(self.h, float(depth_mean), float(depth_min)))
+
+    def seed_list(self, cap=100000):
+        """the reference's std::list<Seed> as arrays: px[n,2], level, kf index, batch id, state[n,5]"""
+        px = np.zeros((cap, 2)); lv = np.zeros(cap, np.int32); kf = np.zeros(cap, np.int32); bt = np.zeros(cap, np.int32)
+        st = np.zeros((cap, 5), np.float32)
+        self.lib.svo_ref_seq_get_seed_list.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_ip, c_ip, c_fp]
+        n = int(self.lib.svo_ref_seq_get_seed_list(self.h, cap, _p(px, c_dp), _p(lv, c_ip), _p(kf, c_ip), _p(bt, c_ip), _p(st, c_fp)))
+        return px[:n], lv[:n], kf[:n], bt[:n], st[:n]
 
     def timing(self):
         """steady_clock seconds per operator since the last call: dict(pyramid, align, refine, seeds, steps)"""

@@ -501,6 +501,13 @@ struct RefSeq {
   // (BASELINE.md section 3): [0] Frame ctor (pyramid), [1] SparseImgAlign::run, [2] reprojection / refinement (+ pose optimiser in
   // chain mode), [3] DepthFilter::addFrame (updateSeeds); [4] = number of steps
   double timing[5] = {0, 0, 0, 0, 0};
+  // keyframe insertion (svo_ref_seq_add_keyframe): the reference's own DepthFilter::addKeyframe / removeKeyframe with its FastDetector
+  feature_detection::DetectorPtr det;
+  std::vector<FramePtr> kfs;            // ring: index = keyframe index (0 = the keyframe of set_keyframe)
+  std::vector<int> kf_batch;
+  int max_kfs = 4;
+  double conv_thresh = 100.0;
+  std::vector<double> step_px; std::vector<int> step_ok;
 };
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -513,7 +520,72 @@ void* svo_ref_seq_create(const int* wh, const double* k, int max_level, int min_
   s->depth_mean = depth_mean; s->depth_min = depth_min;
   s->df = new DepthFilterT(feature_detection::DetectorPtr(), [s](Point* p, double) { s->conv_points.push_back(p); });
   s->df->options_.seed_convergence_sigma2_thresh = conv_thresh;
+  s->conv_thresh = conv_thresh;
   return s;
+}
+
+// Before svo_ref_seq_set_keyframe: keyframe ring, DepthFilter::Options::max_n_kfs, reseed mode (3 = the reference's own list
+// semantics: finished seeds simply leave the list) and the detector DepthFilter::initializeSeeds runs
+// (FastDetector(width, height, Config::gridSize, Config::nPyrLevels), threshold Config::triangMinCornerScore).
+void svo_ref_seq_set_pool(void* h, int max_kfs, int max_n_kfs, int reseed, int det_cell, int det_levels, double det_thr)
+{
+  RefSeq* s = (RefSeq*)h;
+  s->max_kfs = max_kfs; s->reseed = reseed;
+  delete s->df;
+  s->det.reset(new feature_detection::FastDetector(s->cam->width(), s->cam->height(), det_cell, det_levels));
+  s->df = new DepthFilterT(s->det, [s](Point* p, double) { s->conv_points.push_back(p); });
+  s->df->options_.seed_convergence_sigma2_thresh = s->conv_thresh;
+  s->df->options_.max_n_kfs = max_n_kfs;
+  Config::triangMinCornerScore() = det_thr;
+}
+
+// The frame of the most recent step becomes a keyframe: FrameHandlerMono::processFrame :260-312 restricted to the depth filter's
+// part — setKeyframe, DepthFilter::addKeyframe (synchronous: initializeSeeds), removeKeyframe of the oldest one when the ring is full.
+int svo_ref_seq_add_keyframe(void* h, float depth_mean, float depth_min)
+{
+  RefSeq* s = (RefSeq*)h;
+  FramePtr fr = s->last;
+  // the frame's features: the map points matched in it, at their refined pixels (what Reprojector::reprojectCell adds, :219-231)
+  for (auto f : fr->fts_) delete f;
+  fr->fts_.clear();
+  for (size_t i = 0; i < s->pts.size(); ++i) {
+    if (!s->step_ok[i]) continue;
+    Feature* f = new Feature(fr.get(), Vector2d(s->step_px[2 * i], s->step_px[2 * i + 1]), 0);
+    f->point = s->pts[i];
+    fr->fts_.push_back(f);
+  }
+  fr->setKeyframe();
+  if (s->kfs.empty()) { s->kfs.assign(s->max_kfs, FramePtr()); s->kf_batch.assign(s->max_kfs, 0); s->kfs[0] = s->kf; }
+  int k = -1;
+  for (int i = 0; i < s->max_kfs; ++i) if (!s->kfs[i]) { k = i; break; }
+  if (k < 0) {
+    const int first = (!s->pts.empty() && s->max_kfs > 1) ? 1 : 0;
+    k = first;
+    for (int i = first + 1; i < s->max_kfs; ++i) if (s->kf_batch[i] < s->kf_batch[k]) k = i;
+    s->df->removeKeyframe(s->kfs[k]);
+  }
+  s->kfs[k] = fr;
+  const size_t before = s->df->getSeeds().size();
+  s->df->addKeyframe(fr, depth_mean, depth_min);
+  s->kf_batch[k] = Seed::batch_counter;
+  return (int)(s->df->getSeeds().size() - before);
+}
+
+// the seed list as it stands: px (2), level, keyframe index, batch id and the 5 state floats per seed; returns the count
+int svo_ref_seq_get_seed_list(void* h, int cap, double* px, int* level, int* kf, int* batch, float* state)
+{
+  RefSeq* s = (RefSeq*)h;
+  int n = 0;
+  for (auto& sd : s->df->getSeeds()) {
+    if (n >= cap) break;
+    px[2 * n] = sd.ftr->px[0]; px[2 * n + 1] = sd.ftr->px[1]; level[n] = sd.ftr->level; batch[n] = sd.batch_id;
+    int ki = 0;
+    for (size_t i = 0; i < s->kfs.size(); ++i) if (s->kfs[i].get() == sd.ftr->frame) ki = (int)i;
+    kf[n] = ki;
+    state[5 * n] = sd.a; state[5 * n + 1] = sd.b; state[5 * n + 2] = sd.mu; state[5 * n + 3] = sd.z_range; state[5 * n + 4] = sd.sigma2;
+    ++n;
+  }
+  return n;
 }
 
 // FrameHandlerMono::processFrame's Step 2 + Step 3 (frame_handler_mono.cpp:191-222) instead of refining every map point;
@@ -582,6 +654,11 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   FramePtr cur(new Frame(s->cam, aligned_copy(cur_img, s->cam->width(), s->cam->height()), 1.0));
   const double t1 = now_s();
   FramePtr last = s->last;
+  if (last->isKeyframe()) {
+    // a keyframe keeps the pose it was inserted with (and its features); tracking continues from a twin of the frame (same
+    // image, same pyramid) that takes the caller's pose of the last frame like every other `last`
+    last.reset(new Frame(s->cam, last->img_pyr_[0], 0.0));
+  }
   last->T_f_w_ = to_se3(T_last_w);
   for (auto f : last->fts_) delete f;
   last->fts_.clear();
@@ -629,6 +706,8 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
     st->n_matched += ok ? 1 : 0;
     if (px_refined) { px_refined[2 * i] = px[0]; px_refined[2 * i + 1] = px[1]; }
     if (match_ok) match_ok[i] = ok ? 1 : 0;
+    if ((int)s->step_ok.size() != N) { s->step_ok.assign(N, 0); s->step_px.assign(2 * (size_t)N, 0.0); }
+    s->step_px[2 * i] = px[0]; s->step_px[2 * i + 1] = px[1]; s->step_ok[i] = ok ? 1 : 0;
   }
   }
   s->conv_points.clear();
@@ -640,6 +719,7 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   st->n_seeds_updated = st->n_seeds_failed = st->n_seeds_skipped = -1;   // not observable through the reference API
   std::vector<Feature*> finished;
   for (auto p : s->conv_points) { Feature* f = p->obs_.front(); f->point = NULL; p->obs_.clear(); delete p; finished.push_back(f); }
+  if (s->reseed == 3) { s->last = cur; return; }                    // the reference's own list semantics: nothing to restore
   if ((int)s->df->getSeeds().size() + (int)finished.size() != (int)s->seed_ftrs.size()) {
     std::map<Feature*, char> seen;                                   // seeds erased because z_inv_min was NaN
     for (auto& sd : s->df->getSeeds()) seen[sd.ftr] = 1;

@@ -25,6 +25,8 @@ typedef struct {
   int n_reproj_trials, n_pose_obs;     /* chain mode: Reprojector::n_trials_, features left after the pose optimiser */
 } svo_step_stats;
 
+#define SVO_SEQ_MAX_KFS 16
+#define SVO_SEED_TOO_OLD 7
 /* what DepthFilter::updateSeeds saw for one seed in the last step (mirror of svob200_seed_obs) */
 typedef struct svo_seq_seed_obs { int status, search_level, zmssd_best, n_evals; double z, px_cur[2], epi_length; } svo_seq_seed_obs;
 
@@ -40,9 +42,20 @@ typedef struct svo_seq {
   uint8_t *kf0, *kfu, *last0, *lastu, *cur0, *curu;
   svo_pyr kf, last, cur;
   double T_kf_w[7];
-  int N, S;
+  int N, S;                            /* S = seed SLOTS (alive or not) */
   double *kf_px, *kf_f, *pt_world; int* kf_level;
   double *seed_px, *seed_f; int* seed_level; svo_seed* seeds;
+  /* keyframe insertion (svo_oracle_seq_add_keyframe): DepthFilter::addKeyframe -> initializeSeeds (depth_filter.cpp:109-151),
+   * the ageing rule (:258-261), removeKeyframe (:153-170).  Keyframe 0 is the one of set_keyframe (kf above). */
+  uint8_t *kfs0[SVO_SEQ_MAX_KFS], *kfsu[SVO_SEQ_MAX_KFS];
+  svo_pyr kfp[SVO_SEQ_MAX_KFS];
+  double T_kfs[SVO_SEQ_MAX_KFS][7];
+  int kf_used[SVO_SEQ_MAX_KFS], kf_batch[SVO_SEQ_MAX_KFS];
+  int max_kfs, max_n_kfs, batch_counter;
+  int det_cell, det_levels; double det_thr;
+  int S_cap;
+  int *seed_kf, *seed_batch, *seed_alive;
+  double *step_px; int* step_ok; double T_step[7]; int have_step;
   /* per-step scratch */
   double *xyz; uint8_t* has_point;
   /* chain mode (svo_oracle_seq_set_chain): Reprojector::reprojectMap + pose_optimizer::optimizeGaussNewton replace the
@@ -72,6 +85,7 @@ svo_seq* svo_oracle_seq_create(const svo_cam* cam, int n_levels, int align_max_l
   s->conv_thresh = conv_thresh; s->reseed = reseed;
   svo_oracle_seed_init(&s->seed_init, depth_mean, depth_min);
   const size_t l0 = (size_t)s->w * s->h, up = svo_oracle_pyramid_bytes(s->w, s->h, n_levels) + 16;
+  s->max_kfs = 4; s->max_n_kfs = 3; s->det_cell = 30; s->det_levels = 3; s->det_thr = 20.0;
   s->kf0 = (uint8_t*)malloc(l0); s->kfu = (uint8_t*)malloc(up);
   s->last0 = (uint8_t*)malloc(l0); s->lastu = (uint8_t*)malloc(up);
   s->cur0 = (uint8_t*)malloc(l0); s->curu = (uint8_t*)malloc(up);
@@ -84,6 +98,8 @@ void svo_oracle_seq_destroy(svo_seq* s)
   free(s->kf0); free(s->kfu); free(s->last0); free(s->lastu); free(s->cur0); free(s->curu);
   free(s->kf_px); free(s->kf_f); free(s->pt_world); free(s->kf_level);
   free(s->seed_px); free(s->seed_f); free(s->seed_level); free(s->seeds); free(s->xyz); free(s->has_point); free(s->obs);
+  free(s->seed_kf); free(s->seed_batch); free(s->seed_alive); free(s->step_px); free(s->step_ok);
+  for (int k = 1; k < SVO_SEQ_MAX_KFS; ++k) { free(s->kfs0[k]); free(s->kfsu[k]); }
   free(s);
 }
 
@@ -95,10 +111,15 @@ void svo_oracle_seq_set_keyframe(svo_seq* s, const uint8_t* img, const double* T
   s->N = N; s->S = S;
   s->kf_px = (double*)malloc(sizeof(double) * 2 * (N + 1)); s->kf_f = (double*)malloc(sizeof(double) * 3 * (N + 1));
   s->pt_world = (double*)malloc(sizeof(double) * 3 * (N + 1)); s->kf_level = (int*)malloc(sizeof(int) * (N + 1));
+  s->S_cap = S + 1;
   s->seed_px = (double*)malloc(sizeof(double) * 2 * (S + 1)); s->seed_f = (double*)malloc(sizeof(double) * 3 * (S + 1));
   s->seed_level = (int*)malloc(sizeof(int) * (S + 1)); s->seeds = (svo_seed*)malloc(sizeof(svo_seed) * (S + 1));
   s->xyz = (double*)malloc(sizeof(double) * 3 * (N + 1)); s->has_point = (uint8_t*)malloc(N + 1);
   s->obs = (svo_seq_seed_obs*)calloc((size_t)S + 1, sizeof(svo_seq_seed_obs));
+  s->seed_kf = (int*)calloc((size_t)S + 1, sizeof(int)); s->seed_batch = (int*)calloc((size_t)S + 1, sizeof(int)); s->seed_alive = (int*)malloc(sizeof(int) * (S + 1));
+  for (int i = 0; i < S; ++i) s->seed_alive[i] = 1;
+  s->step_px = (double*)malloc(sizeof(double) * 2 * (N + 1)); s->step_ok = (int*)calloc((size_t)N + 1, sizeof(int));
+  s->kf_used[0] = 1; s->kf_batch[0] = 0; s->kfp[0] = s->kf; memcpy(s->T_kfs[0], T_kf_w, sizeof(s->T_kfs[0]));
   memcpy(s->kf_px, kf_px, sizeof(double) * 2 * N); memcpy(s->pt_world, pt_world, sizeof(double) * 3 * N);
   memcpy(s->kf_level, kf_level, sizeof(int) * N);
   memcpy(s->seed_px, seed_px, sizeof(double) * 2 * S); memcpy(s->seed_level, seed_level, sizeof(int) * S);
@@ -206,18 +227,28 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
     st->n_matched += ok;
     if (px_refined) { px_refined[2 * i] = mr.px_cur[0]; px_refined[2 * i + 1] = mr.px_cur[1]; }
     if (match_ok) match_ok[i] = ok;
+    s->step_px[2 * i] = mr.px_cur[0]; s->step_px[2 * i + 1] = mr.px_cur[1]; s->step_ok[i] = ok;
   }
   }
+  memcpy(s->T_step, Tc, sizeof(s->T_step)); s->have_step = 1;
   /* depth filter */
   if (s->have_override) Tc = T_use;
   s->have_override = 0;
   for (int i = 0; i < s->S; ++i) {
+    if (!s->seed_alive[i]) { memset(&s->obs[i], 0, sizeof(s->obs[i])); s->obs[i].zmssd_best = 2000 * 64; continue; }   /* empty slot */
+    /* "check if seed is not already too old" (depth_filter.cpp:258-261) */
+    if (s->batch_counter - s->seed_batch[i] > s->max_n_kfs) {
+      s->seed_alive[i] = 0;
+      memset(&s->obs[i], 0, sizeof(s->obs[i])); s->obs[i].status = SVO_SEED_TOO_OLD; s->obs[i].zmssd_best = 2000 * 64;
+      continue;
+    }
     svo_ref_feature f;
     f.px_ref[0] = s->seed_px[2 * i]; f.px_ref[1] = s->seed_px[2 * i + 1];
     memcpy(f.f_ref, s->seed_f + 3 * i, sizeof(f.f_ref));
     f.level_ref = s->seed_level[i]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
     svo_epi_result epi;
-    const int status = svo_oracle_update_seed_with_frame(&s->kf, &s->cur, &s->cam, &f, s->T_kf_w, Tc, &s->mopts,
+    const int kfi = s->seed_kf[i];
+    const int status = svo_oracle_update_seed_with_frame(&s->kfp[kfi], &s->cur, &s->cam, &f, s->T_kfs[kfi], Tc, &s->mopts,
                                                          s->conv_thresh, &s->seeds[i], &epi);
     {
       svo_seq_seed_obs* ob = &s->obs[i];
@@ -234,7 +265,9 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
     else if (status == SVO_SEED_NO_MATCH) st->n_seeds_failed++;
     else st->n_seeds_skipped++;
     /* reseed 1: finished seeds start afresh (stationary workload); 2: EVERY seed starts afresh every frame (young-seed regime) */
-    if (s->reseed == 2 || (s->reseed && (status == SVO_SEED_CONVERGED || status == SVO_SEED_NAN_ERASED))) s->seeds[i] = s->seed_init;
+    /* 3: the reference's list semantics: a converged (callback + erase, :314-331) or NaN (:334-338) seed leaves the list */
+    if (s->reseed == 3) { if (status == SVO_SEED_CONVERGED || status == SVO_SEED_NAN_ERASED) s->seed_alive[i] = 0; }
+    else if (s->reseed == 2 || (s->reseed && (status == SVO_SEED_CONVERGED || status == SVO_SEED_NAN_ERASED))) s->seeds[i] = s->seed_init;
   }
   /* the current frame becomes the last frame */
   { uint8_t* t0 = s->last0; uint8_t* tu = s->lastu; s->last0 = s->cur0; s->lastu = s->curu; s->cur0 = t0; s->curu = tu; }
@@ -242,6 +275,86 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
 }
 
 void svo_oracle_seq_get_seeds(const svo_seq* s, svo_seed* out) { memcpy(out, s->seeds, sizeof(svo_seed) * s->S); }
+
+/* ---- keyframe insertion ---- */
+void svo_oracle_seq_set_pool(svo_seq* s, int max_kfs, int max_n_kfs, int reseed)
+{
+  s->max_kfs = max_kfs > SVO_SEQ_MAX_KFS ? SVO_SEQ_MAX_KFS : max_kfs; s->max_n_kfs = max_n_kfs; s->reseed = reseed;
+}
+void svo_oracle_seq_set_detector(svo_seq* s, int cell, int levels, double thr) { s->det_cell = cell; s->det_levels = levels; s->det_thr = thr; }
+int svo_oracle_seq_num_slots(const svo_seq* s) { return s->S; }
+void svo_oracle_seq_get_seed_refs(const svo_seq* s, double* px, int* level, int* kf, int* batch, int* state)
+{
+  for (int i = 0; i < s->S; ++i) {
+    px[2 * i] = s->seed_px[2 * i]; px[2 * i + 1] = s->seed_px[2 * i + 1]; level[i] = s->seed_level[i];
+    kf[i] = s->seed_kf[i]; batch[i] = s->seed_batch[i]; state[i] = s->seed_alive[i] ? 0 : 1;
+  }
+}
+
+static void seq_grow(svo_seq* s, int need)
+{
+  if (need <= s->S_cap) return;
+  const int cap = need + need / 2 + 64;
+  s->seed_px = (double*)realloc(s->seed_px, sizeof(double) * 2 * cap); s->seed_f = (double*)realloc(s->seed_f, sizeof(double) * 3 * cap);
+  s->seed_level = (int*)realloc(s->seed_level, sizeof(int) * cap); s->seeds = (svo_seed*)realloc(s->seeds, sizeof(svo_seed) * cap);
+  s->obs = (svo_seq_seed_obs*)realloc(s->obs, sizeof(svo_seq_seed_obs) * cap);
+  s->seed_kf = (int*)realloc(s->seed_kf, sizeof(int) * cap); s->seed_batch = (int*)realloc(s->seed_batch, sizeof(int) * cap);
+  s->seed_alive = (int*)realloc(s->seed_alive, sizeof(int) * cap);
+  s->S_cap = cap;
+}
+
+/* The frame of the most recent step becomes a keyframe (FrameHandlerMono::processFrame :260-312 -> DepthFilter::addKeyframe ->
+ * initializeSeeds, synchronous mode): occupancy from the frame's features (the map points matched in it), detector, one seed per new
+ * corner in cell order; the oldest keyframe leaves when the ring is full (removeKeyframe: its seeds are erased).  Returns the
+ * number of new seeds. */
+int svo_oracle_seq_add_keyframe(svo_seq* s, float depth_mean, float depth_min)
+{
+  if (!s->have_step) return -1;
+  int k = -1;
+  for (int i = 0; i < s->max_kfs; ++i) if (!s->kf_used[i]) { k = i; break; }
+  if (k < 0) {
+    const int first = (s->N > 0 && s->max_kfs > 1) ? 1 : 0;      /* keyframe 0 holds the map features' reference patches */
+    k = first;
+    for (int i = first + 1; i < s->max_kfs; ++i) if (s->kf_batch[i] < s->kf_batch[k]) k = i;
+    for (int i = 0; i < s->S; ++i) if (s->seed_alive[i] && s->seed_kf[i] == k) s->seed_alive[i] = 0;   /* removeKeyframe */
+  }
+  const size_t l0 = (size_t)s->w * s->h, up = svo_oracle_pyramid_bytes(s->w, s->h, s->n_levels) + 16;
+  if (k == 0) {                                                    /* only without map features: reuse keyframe 0's buffers */
+    memcpy(s->kf0, s->last0, l0); memcpy(s->kfu, s->lastu, up - 16);
+    svo_oracle_make_pyr(&s->kf, s->kf0, s->kfu, s->w, s->h, s->n_levels); s->kfp[0] = s->kf;
+  } else {
+    if (!s->kfs0[k]) { s->kfs0[k] = (uint8_t*)malloc(l0); s->kfsu[k] = (uint8_t*)malloc(up); }
+    memcpy(s->kfs0[k], s->last0, l0); memcpy(s->kfsu[k], s->lastu, up - 16);
+    svo_oracle_make_pyr(&s->kfp[k], s->kfs0[k], s->kfsu[k], s->w, s->h, s->n_levels);
+  }
+  memcpy(s->T_kfs[k], s->T_step, sizeof(s->T_kfs[k]));
+  if (k == 0) memcpy(s->T_kf_w, s->T_step, sizeof(s->T_kf_w));
+  s->kf_used[k] = 1; s->kf_batch[k] = ++s->batch_counter;          /* ++Seed::batch_counter (:139) */
+  /* AbstractDetector::setExistingFeatures (feature_detection.cpp:40-58) over the frame's features */
+  const int cols = (int)ceil((double)s->w / s->det_cell), rows = (int)ceil((double)s->h / s->det_cell);
+  uint8_t* occ = (uint8_t*)calloc((size_t)cols * rows, 1);
+  for (int i = 0; i < s->N; ++i) {
+    if (!s->step_ok[i]) continue;
+    const long long c = (long long)(int)(s->step_px[2 * i + 1] / s->det_cell) * cols + (int)(s->step_px[2 * i] / s->det_cell);
+    if (c >= 0 && c < (long long)cols * rows) occ[c] = 1;
+  }
+  svo_corner* cells = (svo_corner*)malloc(sizeof(svo_corner) * (size_t)cols * rows);
+  svo_oracle_fast_detect(&s->kfp[k], s->det_levels, s->det_cell, s->det_thr, occ, cells);
+  int n_new = 0;
+  int slot = 0;
+  for (int c = 0; c < cols * rows; ++c) {
+    if (!((double)cells[c].score > s->det_thr)) continue;
+    while (slot < s->S && s->seed_alive[slot]) ++slot;             /* next empty slot, else a new one at the end */
+    if (slot >= s->S) { seq_grow(s, s->S + 1); slot = s->S; s->S++; memset(&s->obs[slot], 0, sizeof(s->obs[slot])); s->obs[slot].zmssd_best = 2000 * 64; }
+    s->seed_px[2 * slot] = (double)cells[c].x; s->seed_px[2 * slot + 1] = (double)cells[c].y; s->seed_level[slot] = cells[c].level;
+    svo_oracle_cam2world(&s->cam, s->seed_px[2 * slot], s->seed_px[2 * slot + 1], s->seed_f + 3 * slot);
+    svo_oracle_seed_init(&s->seeds[slot], depth_mean, depth_min);
+    s->seed_kf[slot] = k; s->seed_batch[slot] = s->batch_counter; s->seed_alive[slot] = 1;     /* (obs keeps describing the last step) */
+    ++n_new; ++slot;
+  }
+  free(occ); free(cells);
+  return n_new;
+}
 void svo_oracle_seq_get_seed_obs(const svo_seq* s, svo_seq_seed_obs* out) { memcpy(out, s->obs, sizeof(svo_seq_seed_obs) * s->S); }
 /* the matcher / depth-filter stages of the next step use T_cur_w instead of the pose sparse alignment produced */
 void svo_oracle_seq_set_pose_override(svo_seq* s, const double* T_cur_w) { memcpy(s->T_override, T_cur_w, sizeof(s->T_override)); s->have_override = 1; }

@@ -392,3 +392,119 @@ def test_tracker_chain_matches_oracle(ctx, oracle, pose_opt, mode):
         trk.close()
         for s in free + pinned:
             s.close()
+
+
+# ---------------------------------------------------------------- keyframe insertion (DepthFilter::addKeyframe -> initializeSeeds)
+KF_DET = dict(cell=20, levels=3, thr=10.0)
+
+
+def seed_key_table(px, level, kf, state):
+    """alive seeds as sortable rows (kf, level, x, y) + their order"""
+    alive = state == 0
+    rows = np.stack([kf[alive], level[alive], px[alive, 0].astype(np.int64), px[alive, 1].astype(np.int64)], 1)
+    order = np.lexsort(rows.T[::-1])
+    return rows[order], np.nonzero(alive)[0][order]
+
+
+def test_oracle_keyframe_insertion_matches_reference(oracle, ref):
+    """Keyframes inserted every third frame: the restatement's add_keyframe (occupancy from the frame's matched features, FAST +
+    Shi-Tomasi + grid, one seed per new corner, batch ids, the ageing rule, the ring dropping its oldest keyframe) against the
+    reference's own DepthFilter::addKeyframe / removeKeyframe with its FastDetector.  Seed lists: same members, same bits."""
+    n_frames = 16
+    cfg, poses, imgs, kf, last_px = make_sequence(oracle, "C2", 0x00C0FFEE + 7, n_frames + 1)
+    cam = scenes.cam_of(cfg, Cam)
+    args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"], 100.0, 2.4, 1.2, 3)
+    so, sr = OracleSeq(oracle, *args), RefSeq(ref, *args)
+    try:
+        so.set_pool(3, 2, 3); so.set_detector(KF_DET["cell"], KF_DET["levels"], KF_DET["thr"])
+        sr.set_pool(3, 2, 3, KF_DET["cell"], KF_DET["levels"], KF_DET["thr"])
+        S0 = 200
+        for s in (so, sr):
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"][:S0], kf["seed_level"][:S0])
+            s.set_last(imgs[0])
+        n_kf = 0
+        for k in range(1, n_frames + 1):
+            a = so.step(imgs[k], poses[k - 1], last_px[k - 1])
+            b = sr.step(imgs[k], poses[k - 1], last_px[k - 1])
+            assert np.array_equal(np.array(a.T_cur_w[:]), np.array(b.T_cur_w[:])) and a.n_matched == b.n_matched
+            assert a.n_seeds_converged == b.n_seeds_converged
+            if k % 3 == 0:
+                na, nb = so.add_keyframe(2.0 + 0.01 * k, 1.0), sr.add_keyframe(2.0 + 0.01 * k, 1.0)
+                assert na == nb and na > 50, (na, nb)
+                n_kf += 1
+            px, lv, kfi, bt, st = so.seed_refs()
+            rows_o, idx_o = seed_key_table(px, lv, kfi, st)
+            rpx, rlv, rkf, rbt, rst = sr.seed_list()
+            rows_r, idx_r = seed_key_table(rpx, rlv, rkf, np.zeros(len(rlv), np.int32))
+            assert np.array_equal(rows_o, rows_r), "seed list membership differs at frame %d" % k
+            assert np.array_equal(so.seeds()[idx_o].view(np.uint32), rst[idx_r].view(np.uint32)), "seed states differ at frame %d" % k
+        assert n_kf == 5 and len(rows_o) > 100
+        assert len(np.unique(rows_o[:, 0])) >= 2                      # seeds of several keyframes are alive at the end
+    finally:
+        so.close(); sr.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["host", "device"])
+@pytest.mark.parametrize("batch", [2, 70])
+def test_tracker_keyframe_insertion_matches_oracle(ctx, oracle, batch, mode):
+    """svob200_tracker_add_keyframe (detect -> seed init -> update, device-resident) against the oracle over a sequence with a
+    keyframe every third frame: new-seed counts, pool membership slot by slot, seed bits under the device's pose (pinned oracle)."""
+    from android_svo_b200 import capi
+    n_frames, n_distinct = 13, min(batch, 2)
+    seqs = [make_sequence(oracle, "C2", 0x00C0FFEE + 60 + i, n_frames + 1) for i in range(n_distinct)]
+    which = np.arange(batch) % n_distinct
+    cfg = seqs[0][0]
+    cam_o, cam_g = scenes.cam_of(cfg, Cam), scenes.cam_of(cfg, capi.Camera)
+    args = (cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
+    N, S0, CAP = cfg["n_features"], 200, 1700
+    pinned = [OracleSeq(oracle, cam_o, *args, 100.0, 2.4, 1.2, 3) for _ in range(n_distinct)]
+    trk = capi.Tracker(ctx, cam_g, batch, *args)
+    try:
+        trk.set_seed_pool(CAP, 3, 2, 3); trk.set_detector(KF_DET["cell"], KF_DET["levels"], KF_DET["thr"])
+        for s, (_, poses, imgs, kf, _) in zip(pinned, seqs):
+            s.set_pool(3, 2, 3); s.set_detector(KF_DET["cell"], KF_DET["levels"], KF_DET["thr"])
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"][:S0], kf["seed_level"][:S0])
+            s.set_last(imgs[0])
+        take = lambda key, n=None: np.concatenate([seqs[w][3][key][:n] for w in which])
+        trk.set_keyframe(np.stack([seqs[w][2][0] for w in which]), np.stack([seqs[w][1][0] for w in which]), np.arange(batch + 1) * N,
+                         take("kf_px"), take("kf_level"), take("pt_world"), np.arange(batch + 1) * S0, take("seed_px", S0), take("seed_level", S0))
+        assert trk.S == batch * CAP
+        (trk.set_last if mode == "host" else trk.set_last_device)(np.stack([seqs[w][2][0] for w in which]))
+        n_bit_diff = n_seedframes = 0
+        for k in range(1, n_frames + 1):
+            stats = gpu_step(trk, mode, np.stack([seqs[w][2][k] for w in which]), np.stack([seqs[w][1][k - 1] for w in which]),
+                             np.concatenate([seqs[w][4][k - 1] for w in which]))
+            for d in range(n_distinct):
+                pinned[d].set_pose_override(stats[d]["T_cur_w"])
+                pinned[d].step(seqs[d][2][k], seqs[d][1][k - 1], seqs[d][4][k - 1])
+            if k % 3 == 0:
+                n_new, n_drop = trk.add_keyframe(2.0 + 0.01 * k, 1.0)
+                assert (n_drop == 0).all()
+                for d in range(n_distinct):
+                    n_o = pinned[d].add_keyframe(2.0 + 0.01 * k, 1.0)
+                    assert (n_new[which == d] == n_o).all(), "new-seed count differs at frame %d: %s vs %d" % (k, n_new[which == d][:4], n_o)
+                    assert n_o > 50
+            px, lv, kfi, bt, st = trk.seed_refs()
+            seeds_g, obs_g = seed_matrix(trk.seeds()), trk.seed_obs()
+            for b in range(batch):
+                d = which[b]
+                opx, olv, okf, obt, ost = pinned[d].seed_refs()
+                So = len(olv)
+                assert So <= CAP
+                sl = slice(b * CAP, b * CAP + So)
+                assert np.array_equal(st[sl], ost) and (st[b * CAP + So:(b + 1) * CAP] == 1).all(), "pool occupancy differs (seq %d, frame %d)" % (b, k)
+                alive = ost == 0
+                assert np.array_equal(px[sl][alive], opx[alive]) and np.array_equal(lv[sl][alive], olv[alive])
+                assert np.array_equal(kfi[sl][alive], okf[alive]) and np.array_equal(bt[sl][alive], obt[alive])
+                n_bit_diff += int((seeds_g[sl][alive].view(np.uint32) != pinned[d].seeds()[alive].view(np.uint32)).any(axis=1).sum())
+                n_seedframes += int(alive.sum())
+                oo = pinned[d].seed_obs()
+                assert np.array_equal(obs_g["status"][sl], oo["status"]), "seed statuses differ (seq %d, frame %d)" % (b, k)
+        print("keyframe insertion: %d seed-frames, %d bit differences under the device's pose" % (n_seedframes, n_bit_diff))
+        assert n_bit_diff == 0
+        assert len(np.unique(okf[ost == 0])) >= 2
+    finally:
+        trk.close()
+        for s in pinned:
+            s.close()
