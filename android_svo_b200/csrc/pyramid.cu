@@ -3,7 +3,7 @@
 //
 // B200 design: the job is pure HBM streaming (read level 0 once, write every
 // coarser level once: 408,000 B per VGA 4-level pyramid), so ONE fused kernel
-// builds all levels: each CTA owns a 64x64 level-0 tile, pulls it with two
+// builds all levels: each CTA owns a 128x64 level-0 tile, pulls it with two
 // coalesced uint8x16 loads per thread, reduces it with byte-SIMD integer ops in
 // registers, and walks the remaining levels through shared memory.  No level is
 // ever re-read from HBM.  Both reference roundings are implemented bit-exactly:
@@ -119,22 +119,58 @@ __device__ __forceinline__ void yuv_rows16(const YuvPlanes& s, int b, int x0, in
   g1 = make_uint4(o1[0], o1[1], o1[2], o1[3]);
 }
 
-// One CTA = one 64x64 level-0 tile of one image; 128 threads.
-// Thread t: 16-pixel segment (t&3) of row pair (t>>2).
+// levels >= 2 of a tile, all sizes compile-time: src is a SW x SH tile in shared memory, dst its SW/2 x SH/2 half-sample.
+// Four outputs per thread with the same byte-SIMD reduction as level 1 (two aligned 8-byte shared loads, one word to shared
+// memory and one word to HBM; the pitch padding absorbs the tail of a row); tiles narrower than 4 fall back to one output per thread.
+template <int SW_, int SH_, int NT_>
+__device__ __forceinline__ void tile_level(const uint8_t* src, uint8_t* dst, int mode, uint8_t* gout, int pitch, int wl, int hl, int ox, int oy, int t)
+{
+  constexpr int DW = SW_ / 2, DH = SH_ / 2;
+  if (DW >= 4) {
+    constexpr int WPR = DW / 4;                          // words per output row of the tile
+    for (int i = t; i < DH * WPR; i += NT_) {
+      const int ly = i / WPR, lw = i - ly * WPR;
+      const uint2 top = *reinterpret_cast<const uint2*>(src + (2 * ly) * SW_ + 8 * lw);
+      const uint2 bot = *reinterpret_cast<const uint2*>(src + (2 * ly + 1) * SW_ + 8 * lw);
+      const uint32_t v = mode ? half4_sse2(top.x, top.y, bot.x, bot.y) : half4_trunc(top.x, top.y, bot.x, bot.y);
+      *reinterpret_cast<uint32_t*>(dst + ly * DW + 4 * lw) = v;
+      const int gx = ox + 4 * lw, gy = oy + ly;
+      if (gx < wl && gy < hl) {
+        uint8_t* o = gout + (size_t)gy * pitch + gx;
+        if (gx + 4 <= pitch) *reinterpret_cast<uint32_t*>(o) = v;
+        else for (int k = 0; k < 4 && gx + k < wl; ++k) o[k] = (uint8_t)((v >> (8 * k)) & 0xff);
+      }
+    }
+  } else {
+    for (int i = t; i < DH * DW; i += NT_) {
+      const int ly = i / DW, lx = i - ly * DW;
+      const uint8_t* p = src + (2 * ly) * SW_ + 2 * lx;
+      const uint32_t v = half1(p[0], p[1], p[SW_], p[SW_ + 1], mode);
+      dst[ly * DW + lx] = (uint8_t)v;
+      const int gx = ox + lx, gy = oy + ly;
+      if (gx < wl && gy < hl) gout[(size_t)gy * pitch + gx] = (uint8_t)v;
+    }
+  }
+}
+
+// One CTA = one 128x64 level-0 tile of one image; 256 threads; the pyramid depth NL is a template parameter, so every tile
+// size, loop bound and index split below is a compile-time constant.
+// Thread t: 16-pixel segment (t&7) of row pair (t>>3).
 // YUV = true: level 0 is PRODUCED here from the camera's YUV planes (and written once) instead of being read,
 // so the input stage costs no extra pass over the frame.
-template <bool YUV>
-__global__ void __launch_bounds__(128) pyramid_fused_kernel(DevFrame f, int modes_mask, YuvPlanes yuv)
+constexpr int PTW = 128, PTH = 64, PNT = 256;
+template <bool YUV, int NL>
+__global__ void __launch_bounds__(PNT) pyramid_fused_kernel(DevFrame f, int modes_mask, YuvPlanes yuv)
 {
-  __shared__ __align__(16) uint8_t s_a[32 * 32];
-  __shared__ __align__(16) uint8_t s_b[16 * 16];
+  __shared__ __align__(16) uint8_t s_a[(PTH / 2) * (PTW / 2)];      // level-1 tile 64 x 32
+  __shared__ __align__(16) uint8_t s_b[(PTH / 4) * (PTW / 4)];      // level-2 tile 32 x 16
   const int t = threadIdx.x;
   const int b = blockIdx.z;
-  const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 64;
+  const int tx0 = blockIdx.x * PTW, ty0 = blockIdx.y * PTH;
 
   // ---- level 0 -> 1 (registers)
   {
-    const int seg = t & 3, rp = t >> 2;
+    const int seg = t & 7, rp = t >> 3;
     const int x0 = tx0 + seg * 16, y0 = ty0 + rp * 2;
     const int w1 = f.w[1], h1 = f.h[1];
     const int x1 = x0 >> 1, y1 = y0 >> 1;
@@ -174,52 +210,23 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(DevFrame f, int mode
         for (int k = 0; k < 8 && x1 + k < w1; ++k) out[k] = (uint8_t)(((k < 4 ? o0 : o1) >> (8 * (k & 3))) & 0xff);
       }
     }
-    *reinterpret_cast<uint2*>(&s_a[rp * 32 + seg * 8]) = make_uint2(o0, o1);
+    if (NL > 2) *reinterpret_cast<uint2*>(&s_a[rp * (PTW / 2) + seg * 8]) = make_uint2(o0, o1);
   }
-  if (f.n_levels <= 2) return;
+  if (NL <= 2) return;
   __syncthreads();
-
-  // ---- levels 2.. (shared memory ping-pong); tile edge halves each level
-  uint8_t* src = s_a;
-  uint8_t* dst = s_b;
-  int src_edge = 32;
-  for (int l = 2; l < f.n_levels; ++l) {
-    const int edge = src_edge >> 1;                  // 16, 8, 4, 2, 1
-    const int mode = (modes_mask >> (l - 1)) & 1;
-    const int wl = f.w[l], hl = f.h[l];
-    const int ox = tx0 >> l, oy = ty0 >> l;
-    uint8_t* gout = f.lvl[l] + (size_t)b * f.img_stride[l];
-    if (edge >= 4) {
-      // four outputs per thread with the same byte-SIMD reduction as level 1: two aligned 8-byte shared loads, one word
-      // to shared memory and one word to HBM (the pitch padding absorbs the tail of a row)
-      const int wpr = edge >> 2;                       // words per output row of the tile: 4, 2, 1
-      for (int i = t; i < edge * wpr; i += 128) {
-        const int ly = i / wpr, lw = i - ly * wpr;
-        const uint2 top = *reinterpret_cast<const uint2*>(src + (2 * ly) * src_edge + 8 * lw);
-        const uint2 bot = *reinterpret_cast<const uint2*>(src + (2 * ly + 1) * src_edge + 8 * lw);
-        const uint32_t v = mode ? half4_sse2(top.x, top.y, bot.x, bot.y) : half4_trunc(top.x, top.y, bot.x, bot.y);
-        *reinterpret_cast<uint32_t*>(dst + ly * edge + 4 * lw) = v;
-        const int gx = ox + 4 * lw, gy = oy + ly;
-        if (gx < wl && gy < hl) {
-          uint8_t* o = gout + (size_t)gy * f.pitch[l] + gx;
-          if (gx + 4 <= f.pitch[l]) *reinterpret_cast<uint32_t*>(o) = v;
-          else for (int k = 0; k < 4 && gx + k < wl; ++k) o[k] = (uint8_t)((v >> (8 * k)) & 0xff);
-        }
-      }
-    } else {
-      for (int i = t; i < edge * edge; i += 128) {
-        const int ly = i / edge, lx = i - ly * edge;
-        const uint8_t* p = src + (2 * ly) * src_edge + 2 * lx;
-        const uint32_t v = half1(p[0], p[1], p[src_edge], p[src_edge + 1], mode);
-        dst[ly * edge + lx] = (uint8_t)v;
-        const int gx = ox + lx, gy = oy + ly;
-        if (gx < wl && gy < hl) gout[(size_t)gy * f.pitch[l] + gx] = (uint8_t)v;
-      }
-    }
-    __syncthreads();
-    uint8_t* tmp = src; src = dst; dst = tmp;
-    src_edge = edge;
+  // ---- levels 2.. (shared memory ping-pong): tile 64x32 -> 32x16 -> 16x8 -> 8x4 -> 4x2 -> 2x1
+#define PYR_LEVEL(L, SW_, SH_, SRC, DST)                                                                                         \
+  if (NL > (L)) {                                                                                                                \
+    tile_level<SW_, SH_, PNT>(SRC, DST, (modes_mask >> ((L) - 1)) & 1, f.lvl[L] + (size_t)b * f.img_stride[L], f.pitch[L], f.w[L], \
+                              f.h[L], tx0 >> (L), ty0 >> (L), t);                                                                \
+    if (NL > (L) + 1) __syncthreads();                                                                                           \
   }
+  PYR_LEVEL(2, 64, 32, s_a, s_b)
+  PYR_LEVEL(3, 32, 16, s_b, s_a)
+  PYR_LEVEL(4, 16, 8, s_a, s_b)
+  PYR_LEVEL(5, 8, 4, s_b, s_a)
+  PYR_LEVEL(6, 4, 2, s_a, s_b)
+#undef PYR_LEVEL
 }
 
 // Generic single-level kernel: any size, both roundings, and the reference's scalar pointer
@@ -269,6 +276,20 @@ __global__ void __launch_bounds__(128) yuv_gray_kernel(DevFrame f, YuvPlanes yuv
 
 }  // namespace
 
+template <bool YUV>
+static void launch_fused(const DevFrame& f, int mask, const YuvPlanes& yuv, cudaStream_t s)
+{
+  dim3 grid((f.w[0] + PTW - 1) / PTW, (f.h[0] + PTH - 1) / PTH, f.batch);
+  switch (f.n_levels) {
+    case 2: pyramid_fused_kernel<YUV, 2><<<grid, PNT, 0, s>>>(f, mask, yuv); break;
+    case 3: pyramid_fused_kernel<YUV, 3><<<grid, PNT, 0, s>>>(f, mask, yuv); break;
+    case 4: pyramid_fused_kernel<YUV, 4><<<grid, PNT, 0, s>>>(f, mask, yuv); break;
+    case 5: pyramid_fused_kernel<YUV, 5><<<grid, PNT, 0, s>>>(f, mask, yuv); break;
+    case 6: pyramid_fused_kernel<YUV, 6><<<grid, PNT, 0, s>>>(f, mask, yuv); break;
+    default: pyramid_fused_kernel<YUV, 7><<<grid, PNT, 0, s>>>(f, mask, yuv); break;
+  }
+}
+
 static bool fused_ok(const DevFrame& f)
 {
   bool odd = false;
@@ -282,8 +303,7 @@ int launch_pyramid_yuv(const DevFrame& f, const YuvPlanes& yuv, const int* modes
   if (fused_ok(f)) {
     int mask = 0;
     for (int l = 0; l + 1 < f.n_levels; ++l) if (modes[l] == SVOB200_ROUND_SSE2) mask |= 1 << l;
-    dim3 grid((f.w[0] + 63) / 64, (f.h[0] + 63) / 64, f.batch);
-    pyramid_fused_kernel<true><<<grid, 128, 0, s>>>(f, mask, yuv);
+    launch_fused<true>(f, mask, yuv, s);
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
@@ -300,8 +320,7 @@ int launch_pyramid(const DevFrame& f, const int* modes, cudaStream_t s, long lon
   if (fused_ok(f)) {
     int mask = 0;
     for (int l = 0; l + 1 < f.n_levels; ++l) if (modes[l] == SVOB200_ROUND_SSE2) mask |= 1 << l;
-    dim3 grid((f.w[0] + 63) / 64, (f.h[0] + 63) / 64, f.batch);
-    pyramid_fused_kernel<false><<<grid, 128, 0, s>>>(f, mask, YuvPlanes{});
+    launch_fused<false>(f, mask, YuvPlanes{}, s);
     ++*launches;
   } else {
     for (int l = 0; l + 1 < f.n_levels; ++l) {

@@ -214,6 +214,10 @@ void releaseFrame(const Frame& frame)
   r.cache.erase(it);
 }
 
+static int g_seed_chunk = 2048;
+int seedChunk() { return g_seed_chunk; }
+void setSeedChunk(int seeds_per_call) { g_seed_chunk = seeds_per_call < 64 ? 64 : seeds_per_call; }
+
 void setFrameCacheCapacity(size_t capacity)
 {
   Runtime& r = rt();
@@ -647,25 +651,36 @@ void B200DepthFilter::updateSeeds(FramePtr frame)
   std::vector<svob200_seed_obs> obs(n);
   double T_cur_w[7];
   b200::pose7(frame->T_f_w_, T_cur_w);
+  // The list goes to the device in chunks of b200::seedChunk() seeds (default 2,048).  Between two chunks seeds_updating_halt_ is
+  // polled again — addKeyframe / removeKeyframe / reset set it and then wait for seeds_mut_ (depth_filter.cpp:112-117, :153-170):
+  // the reference returns at the next seed (:253-254), this returns at the next chunk — and the runtime lock is released, so
+  // the tracking thread's calls (SparseImgAlign::run, reprojectMap) interleave with a long update instead of queueing behind it.
+  int n_done = 0;
   {
-    Lock lk(rt().mu);
-    b200::PinFrames pin;
-    svob200_ctx* ctx = ctx_locked();
-    const int64_t cur_id = b200::ensure_frame_locked(*frame);
-    int i = 0;
-    for (auto it = seeds_.begin(); it != seeds_.end(); ++it, ++i) {
-      const int64_t ref_id = b200::ensure_frame_locked(*it->ftr->frame);
-      fill_feature_ref(*it->ftr, ref_id, SE3(), &ftrs[i]);              // poses travel separately (T_ref_w / T_cur_w)
-      b200::pose7(it->ftr->frame->T_f_w_, &T_ref_w[7 * (size_t)i]);
-      state[i].a = it->a; state[i].b = it->b; state[i].mu = it->mu; state[i].z_range = it->z_range; state[i].sigma2 = it->sigma2;
+    auto it = seeds_.begin();
+    const int chunk = b200::seedChunk();
+    while (n_done < n) {
+      if (n_done > 0 && seeds_updating_halt_) break;
+      const int m = std::min(chunk, n - n_done);
+      Lock lk(rt().mu);
+      b200::PinFrames pin;
+      svob200_ctx* ctx = ctx_locked();
+      const int64_t cur_id = b200::ensure_frame_locked(*frame);
+      for (int i = n_done; i < n_done + m; ++i, ++it) {
+        const int64_t ref_id = b200::ensure_frame_locked(*it->ftr->frame);
+        fill_feature_ref(*it->ftr, ref_id, SE3(), &ftrs[i]);              // poses travel separately (T_ref_w / T_cur_w)
+        b200::pose7(it->ftr->frame->T_f_w_, &T_ref_w[7 * (size_t)i]);
+        state[i].a = it->a; state[i].b = it->b; state[i].mu = it->mu; state[i].z_range = it->z_range; state[i].sigma2 = it->sigma2;
+      }
+      check(svob200_seeds_update(ctx, cur_id, &cam, m, ftrs.data() + n_done, T_ref_w.data() + 7 * (size_t)n_done, T_cur_w, &mo,
+                                 options_.seed_convergence_sigma2_thresh, state.data() + n_done, obs.data() + n_done, SVOB200_MEM_HOST),
+            "svob200_seeds_update");
+      n_done += m;
     }
-    b200::ensure_frame_locked(*frame);                                  // keep the current frame the most recently used entry
-    check(svob200_seeds_update(ctx, cur_id, &cam, n, ftrs.data(), T_ref_w.data(), T_cur_w, &mo, options_.seed_convergence_sigma2_thresh,
-                               state.data(), obs.data(), SVOB200_MEM_HOST), "svob200_seeds_update");
   }
 
   int i = 0;
-  for (auto it = seeds_.begin(); it != seeds_.end(); ++i) {
+  for (auto it = seeds_.begin(); it != seeds_.end() && i < n_done; ++i) {     // (a halted update leaves the rest of the list untouched, like :253-254)
     const svob200_seed_obs& o = obs[i];
     if (o.status == SVOB200_SEED_BEHIND || o.status == SVOB200_SEED_NOT_IN_FRAME) { ++it; continue; }     // :266-273
     it->a = state[i].a; it->b = state[i].b; it->mu = state[i].mu; it->sigma2 = state[i].sigma2;

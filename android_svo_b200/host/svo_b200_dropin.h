@@ -59,6 +59,10 @@ svob200_ctx* context();
 /// otherwise the cache evicts least-recently-used entries beyond `capacity` (default 64).
 void releaseFrame(const Frame& frame);
 void setFrameCacheCapacity(size_t capacity);
+/// B200DepthFilter::updateSeeds sends the seed list to the device in chunks of this many seeds (default 2,048) and polls
+/// seeds_updating_halt_ between chunks; the runtime lock is released between chunks so that the tracking thread's calls interleave.
+int seedChunk();
+void setSeedChunk(int seeds_per_call);
 void shutdown();
 
 /// FrameHandlerBase::optimizeStructure (frame_handler_base.cpp:190-210) with every Point::optimize (point.cpp:130-192)

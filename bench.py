@@ -202,7 +202,8 @@ class ClockSampler:
 CPU_FRAMES_PER_STEP = 16   # a CPU "step" = this many consecutive frames of every sampled sequence (bounded sample, ~10-30 core-s per run)
 
 
-def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False, regime="steady", o3=False, dropin=False, kf_every=0):
+def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP, chain=False, regime="steady", o3=False, dropin=False, kf_every=0,
+            two_threads=False):
     """Times the front-end step of `n_seqs` independent sequences on the host cores.  Uses the real
     reference (oracle/_ref/libsvo_ref.so; o3: the -O3 / AVX2 / FMA build of the same sources; dropin: the same harness over
     the B200 drop-in) when it was built, else the C restatement.  One timed step = `inner` consecutive frames of every
@@ -235,6 +236,8 @@ def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP,
         if kf_every:
             args = args[:-1] + (3,)          # the reference's list semantics: finished seeds leave the list
         s = RefSeq(ref, *args) if kind != "port" else OracleSeq(oracle, *args)
+        if two_threads:
+            s.set_threaded()             # the reference's native layout: the depth filter in its own thread (reference builds only)
         if kf_every:
             if kind != "port":
                 s.set_pool(KF_RING, KF_MAX_N_KFS, 3, sc, cfg["n_pyr"], st)
@@ -276,6 +279,9 @@ def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP,
         t0 = time.perf_counter()
         for k in range(warmup, warmup + steps):
             stats = step_all(k)
+        if two_threads:
+            for s, _, _ in seqs:
+                s.drain()                # the timed region ends when the depth-filter thread has consumed every frame
         dt = time.perf_counter() - t0
     tracked = float(np.mean([s.n_tracked for s in stats]))
     ops = None
@@ -291,6 +297,16 @@ def cpu_arm(cfg_name, n_seqs, steps, warmup, threads, inner=CPU_FRAMES_PER_STEP,
     ms = np.concatenate([np.array(f) for f in frame_s]) * 1e3
     return dict(kind=kind, fps=n_seqs * steps * inner / dt, seconds=dt, n_seqs=n_seqs, tracked=tracked, inner=inner,
                 p50_ms=float(np.median(ms)), p95_ms=float(np.percentile(ms, 95)), mean_ms=float(ms.mean()), frames=int(len(ms)), per_operator=ops)
+
+
+def cpu_two_threads(cfg_name, regime="steady", frames=96):
+    """The reference's native layout on TWO host threads: tracking (pyramid, alignment, refinement) in one, DepthFilter::updateSeedsLoop in
+    the other (depth_filter.cpp:63-67); the tracking thread is paced so that the filter's queue never drops a frame."""
+    r = cpu_arm(cfg_name, 1, frames // 16, 1, 1, regime=regime, two_threads=True)
+    return {"frames_per_s": round(r["fps"], 1), "ms_per_frame": round(1e3 / r["fps"], 4), "tracking_thread_p50_ms": round(r["p50_ms"], 4),
+            "tracking_thread_p95_ms": round(r["p95_ms"], 4), "kind": r["kind"], "cores": 2,
+            "sample": "1 sequence x %d frames (+16 warm-up), tracking thread + depth-filter thread, no dropped frames; throughput over the whole run "
+                      "incl. draining the filter's queue; the tracking-thread latency includes waiting for a queue slot" % r["frames"]}
 
 
 def cpu_latency(cfg_name, chain=False, regime="steady", o3=False, frames=48):
@@ -986,6 +1002,8 @@ def main():
                                                                                      frames=48 if name != "C4" else 32)
                         if name == "C2":
                             out["latency"][name]["cpu_reference_1_thread_o3"] = cpu_latency(name, chain=args.chain, regime=args.seed_regime, o3=True)
+                        if not args.chain:
+                            out["latency"][name]["cpu_reference_2_threads"] = cpu_two_threads(name, regime=args.seed_regime, frames=96 if name != "C4" else 48)
                     except Exception as e:   # pragma: no cover
                         out["latency"][name]["cpu_reference_1_thread"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:

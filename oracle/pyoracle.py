@@ -704,6 +704,15 @@ class RefSeq(_SeqBase):
         n = int(self.lib.svo_ref_seq_get_seed_list(self.h, cap, _p(px, c_dp), _p(lv, c_ip), _p(kf, c_ip), _p(bt, c_ip), _p(st, c_fp)))
         return px[:n], lv[:n], kf[:n], bt[:n], st[:n]
 
+    def set_threaded(self):
+        """timing only: the depth filter in its own thread, like the app (call before set_keyframe)"""
+        self.lib.svo_ref_seq_set_threaded.argtypes = [C.c_void_p]
+        self.lib.svo_ref_seq_set_threaded(self.h)
+
+    def drain(self):
+        self.lib.svo_ref_seq_drain.argtypes = [C.c_void_p]
+        self.lib.svo_ref_seq_drain(self.h)
+
     def timing(self):
         """steady_clock seconds per operator since the last call: dict(pyramid, align, refine, seeds, steps)"""
         out = np.zeros(5)

@@ -28,6 +28,8 @@
 #include <svo/pose_optimizer.h>
 #include <map>
 #include <chrono>
+#include <thread>
+#include <mutex>
 #include <cstring>
 #ifdef SVOB200_DROPIN
 // Same harness, linked over android_svo_b200/host/svo_b200_dropin.cpp INSTEAD OF the reference's
@@ -482,6 +484,29 @@ struct svo_ref_step_stats {
   int n_reproj_trials, n_pose_obs;
 };
 
+// The reference's native two-thread layout: tracking in the caller's thread, DepthFilter::updateSeedsLoop in its own
+// (DepthFilter::startThread, depth_filter.cpp:63-67).  pending() / wait_idle() let the harness pace the tracking thread so
+// that the frame queue never drops a frame (:95-97) and drain it at the end of a timed run.
+struct ThreadedDF : public DepthFilterT {
+  ThreadedDF(feature_detection::DetectorPtr d, callback_t cb) : DepthFilterT(d, cb) {}
+  size_t pending() { std::unique_lock<std::mutex> l(frame_queue_mut_); return frame_queue_.size(); }
+  void wait_idle()
+  {
+    while (pending() > 0) std::this_thread::yield();
+    for (int k = 0; k < 3; ++k) { { std::unique_lock<std::mutex> l(seeds_mut_); } std::this_thread::yield(); }   // the update in flight holds seeds_mut_
+  }
+  // DepthFilter::stopThread joins a thread that sleeps in frame_queue_cond_.wait with an empty queue and is never notified:
+  // wake it with one more frame (updateSeeds returns at once: seeds_updating_halt_ is set), then join
+  void shutdown(FramePtr any)
+  {
+    if (!thread_) return;
+    seeds_updating_halt_ = true; thread_stop_ = true;
+    { std::unique_lock<std::mutex> l(frame_queue_mut_); frame_queue_.push(any); }
+    frame_queue_cond_.notify_one();
+    if (thread_->joinable()) thread_->join();
+    thread_ = NULL;
+  }
+};
 struct RefSeq {
   vk::PinholeCamera* cam;
   FramePtr kf, last;
@@ -508,6 +533,8 @@ struct RefSeq {
   int max_kfs = 4;
   double conv_thresh = 100.0;
   std::vector<double> step_px; std::vector<int> step_ok;
+  ThreadedDF* tdf = NULL;               // two-thread layout (svo_ref_seq_set_threaded)
+  long n_conv_async = 0;
 };
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -538,6 +565,25 @@ void svo_ref_seq_set_pool(void* h, int max_kfs, int max_n_kfs, int reseed, int d
   s->df->options_.max_n_kfs = max_n_kfs;
   Config::triangMinCornerScore() = det_thr;
 }
+
+// Timing only: the depth filter runs in its own thread like in the app (call before svo_ref_seq_set_keyframe).  Finished seeds
+// are re-initialised inside the convergence callback (the list is being walked under seeds_mut_ there), so the workload stays
+// stationary without the tracking thread touching the list.
+void svo_ref_seq_set_threaded(void* h)
+{
+  RefSeq* s = (RefSeq*)h;
+  delete s->df;
+  s->tdf = new ThreadedDF(s->det, [s](Point* p, double) {
+    Feature* f = p->obs_.front(); f->point = NULL; p->obs_.clear(); delete p;
+    ++s->n_conv_async;
+    if (s->reseed) s->df->getSeeds().push_back(Seed(f, s->depth_mean, s->depth_min));
+  });
+  s->df = s->tdf;
+  s->df->options_.seed_convergence_sigma2_thresh = s->conv_thresh;
+  s->df->startThread();
+}
+// waits until the depth-filter thread has consumed every queued frame
+void svo_ref_seq_drain(void* h) { RefSeq* s = (RefSeq*)h; if (s->tdf) s->tdf->wait_idle(); }
 
 // The frame of the most recent step becomes a keyframe: FrameHandlerMono::processFrame :260-312 restricted to the depth filter's
 // part — setKeyframe, DepthFilter::addKeyframe (synchronous: initializeSeeds), removeKeyframe of the oldest one when the ring is full.
@@ -605,6 +651,7 @@ void svo_ref_seq_set_chain(void* h, int cell_size, int max_fts, int pose_opt)
 void svo_ref_seq_destroy(void* h)
 {
   RefSeq* s = (RefSeq*)h;
+  if (s->tdf) { s->tdf->wait_idle(); s->tdf->shutdown(s->last ? s->last : s->kf); }
   if (s->reproj) delete s->reproj;
   if (s->map) { s->map->keyframes_.clear(); delete s->map; }
   s->df->getSeeds().clear();
@@ -654,7 +701,7 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   FramePtr cur(new Frame(s->cam, aligned_copy(cur_img, s->cam->width(), s->cam->height()), 1.0));
   const double t1 = now_s();
   FramePtr last = s->last;
-  if (last->isKeyframe()) {
+  if (last->isKeyframe() || s->tdf) {        // (two-thread layout: the depth-filter thread may still be reading the frame)
     // a keyframe keeps the pose it was inserted with (and its features); tracking continues from a twin of the frame (same
     // image, same pyramid) that takes the caller's pose of the last frame like every other `last`
     last.reset(new Frame(s->cam, last->img_pyr_[0], 0.0));
@@ -712,14 +759,15 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   }
   s->conv_points.clear();
   const double t4 = now_s();
-  s->df->addFrame(cur);                                             // synchronous updateSeeds
+  if (s->tdf) while (s->tdf->pending() >= 2) std::this_thread::yield();   // never let the queue drop a frame (depth_filter.cpp:95-97)
+  s->df->addFrame(cur);                                             // synchronous updateSeeds, or the queue of the filter thread
   const double t5 = now_s();
   s->timing[0] += t1 - t0; s->timing[1] += t3 - t2; s->timing[2] += t4 - t3; s->timing[3] += t5 - t4; s->timing[4] += 1.0;
   st->n_seeds_converged = (int)s->conv_points.size();
   st->n_seeds_updated = st->n_seeds_failed = st->n_seeds_skipped = -1;   // not observable through the reference API
   std::vector<Feature*> finished;
   for (auto p : s->conv_points) { Feature* f = p->obs_.front(); f->point = NULL; p->obs_.clear(); delete p; finished.push_back(f); }
-  if (s->reseed == 3) { s->last = cur; return; }                    // the reference's own list semantics: nothing to restore
+  if (s->reseed == 3 || s->tdf) { s->last = cur; return; }         // list semantics of the reference / the filter thread owns the list
   if ((int)s->df->getSeeds().size() + (int)finished.size() != (int)s->seed_ftrs.size()) {
     std::map<Feature*, char> seen;                                   // seeds erased because z_inv_min was NaN
     for (auto& sd : s->df->getSeeds()) seen[sd.ftr] = 1;

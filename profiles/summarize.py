@@ -16,7 +16,7 @@ seqs = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "..", "gpurun_out")
 STEP_KERNELS = ["pyramid_fused_kernel", "features_prepare_kernel", "init_pose_kernel", "sparse_align_kernel", "compose_poses_kernel",
-                "reproject_prepare_kernel", "match_geom_kernel", "match_prepare_kernel", "match_direct_kernel", "seeds_geom_kernel",
+                "reproject_prepare_kernel", "match_geom_kernel", "match_prepare_kernel", "match_direct_kernel", "seed_pose_table_kernel", "seeds_geom_kernel",
                 "seeds_search_kernel", "epi_search_kernel", "lk_refine_kernel", "seeds_finish_kernel", "step_stats_kernel"]
 
 
@@ -71,6 +71,9 @@ if os.path.exists(raw):
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            "sm__inst_issued.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
             "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
             "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct",
             "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
@@ -105,7 +108,10 @@ if os.path.exists(raw):
                               "source": "profiles/%s_full_summary.txt" % tag}
                 def num(name):
                     return float(r[ix[name]].replace(",", "")) if name in ix else None
-                traffic[k]["ncu"] = {"issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                traffic[k]["ncu"] = {"issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active") or num("sm__inst_issued.avg.pct_of_peak_sustained_active"),
+                                     "alu_pipe_pct": num("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                                     "fma_pipe_pct": num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                                     "fp64_pipe_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                                      "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
                                      "warp_instructions_per_sequence": (num("smsp__inst_executed.sum") or 0) / seqs,
                                      "registers_per_thread": num("launch__registers_per_thread"),
