@@ -88,7 +88,11 @@ int svob200_ctx_create(int device, svob200_ctx** out)
   if (cudaSetDevice(device) != cudaSuccess) return SVOB200_ERR_CUDA;
   svob200_ctx* ctx = new svob200_ctx();
   ctx->device = device;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SVOB200_ERR_CUDA; }
+  // the context's stream carries the tracking chain; it gets the highest priority so that, beside a tracker's asynchronous
+  // depth-filter stream (default priority), its CTAs are scheduled first when slots free up
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { delete ctx; return SVOB200_ERR_CUDA; }
   if (cudaMalloc((void**)&ctx->d_table, sizeof(DevFrame) * kMaxFrames) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return SVOB200_ERR_CUDA; }
   for (int i = kMaxFrames - 1; i >= 0; --i) ctx->free_slots.push_back(i);
   *out = ctx;

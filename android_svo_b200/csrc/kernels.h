@@ -72,7 +72,7 @@ struct __align__(16) SeedRef {
   int pad2[3];
 };
 static_assert(sizeof(SeedRef) == 64, "SeedRef must be two 32-byte sectors");
-constexpr int SEED_RANGES = 32;
+constexpr int SEED_RANGES = 8;
 // per (keyframe, image): T_ref_cur = ref.T_f_w * cur.T_f_w^-1 (depth_filter.cpp:263), its inverse (:264), the matcher's
 // T_cur_ref = cur.T_f_w * ref.T_f_w^-1 (matcher.cpp:216) and px_error_angle (depth_filter.cpp:245-247)
 struct __align__(16) SeedPoseRec { double T_ref_cur[7], T_cur_ref[7], T_cur_ref_m[7]; double px_error_angle; };

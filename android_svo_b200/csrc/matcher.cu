@@ -21,6 +21,7 @@
 // 64-long dependent FADD chain is ~256 cycles — cheaper than it sounds, and exact).  The epipolar
 // sample positions come from the reference's running sum `uv += step`, replayed by two threads
 // (x and y are independent chains).  Only libm calls (acos/sin/atan/exp) are tolerance-matched.
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -985,10 +986,17 @@ __global__ void seed_pose_table_kernel(DevCam cam, int batch, int n_kfs, int ima
   r->px_error_angle = P.px_error_angle;
 }
 
+#ifndef SEEDS_GEOM_CTAS
+#define SEEDS_GEOM_CTAS 6
+#endif
+// resident CTAs per SM (measured per 3.1 M seeds): geometry 6 CTAs (78 registers) 0.203 ms, 8 (64, spills) 0.204; finish 6 (76) 0.185 ms, 8 (64, 56 B of spills) 0.168
+#ifndef SEEDS_FINISH_CTAS
+#define SEEDS_FINISH_CTAS 8
+#endif
 // phase 1: thread per seed — visibility, inverse-depth range, epipolar geometry -> the search task
 // (occupancy: capping the registers for 6 / 8 CTAs spills and measured slower; the kernel is bound by its record traffic)
 template <class SRC>
-__global__ void __launch_bounds__(128) seeds_geom_kernel(DevCam cam, int n, SRC src, svob200_matcher_opts o,
+__global__ void __launch_bounds__(128, SEEDS_GEOM_CTAS) seeds_geom_kernel(DevCam cam, int n, SRC src, svob200_matcher_opts o,
                                                          const svob200_seed* seeds, SearchTask* tasks, int* job_count)
 {
   // the 128-byte task of a seed goes through shared memory (one padded slot per thread) so that a warp writes it as
@@ -1083,7 +1091,7 @@ __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevF
 
 // phase 4: thread per seed — triangulation, tau, Gaussian x Beta update, status
 template <class SRC>
-__global__ void __launch_bounds__(128) seeds_finish_kernel(DevCam cam, int n, SRC src, double conv_thresh,
+__global__ void __launch_bounds__(128, SEEDS_FINISH_CTAS) seeds_finish_kernel(DevCam cam, int n, SRC src, double conv_thresh,
                                                            const SearchTask* tasks, const SeedMatch* match, svob200_seed* seeds,
                                                            svob200_seed_obs* obs)
 {
@@ -1396,13 +1404,24 @@ static int search_sms()
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   return sms;
 }
-static int search_grid(int n)
+// Grid of the search kernel = SEARCH_CTAS resident CTAs per SM times `waves`: 1 = persistent (every CTA lives for the whole kernel);
+// more = CTAs that retire during the kernel, so that CTAs of a higher-priority stream (the tracking chain running beside an
+// asynchronous depth filter) find free slots.  SVOB200_SEARCH_WAVES overrides (A/B runs).
+constexpr int SEARCH_MAX_WAVES = 4;
+static int search_waves_override()
 {
-  const int want = (n + 4 * GPW - 1) / (4 * GPW), cap = search_sms() * SEARCH_CTAS;
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVOB200_SEARCH_WAVES"); v = e ? atoi(e) : 0; if (v < 0 || v > SEARCH_MAX_WAVES) v = 0; }
+  return v;
+}
+static int search_grid(int n, int waves = 1)
+{
+  if (search_waves_override()) waves = search_waves_override();
+  const int want = (n + 4 * GPW - 1) / (4 * GPW), cap = search_sms() * SEARCH_CTAS * waves;
   return want < cap ? want : cap;
 }
 // LK jobs are compacted; a group reserves JOB_BATCH slots at a time, so the list can exceed n by the unused tail of every group
-static size_t job_capacity(size_t m) { return m + (size_t)JOB_BATCH * 4 * GPW * ((size_t)search_sms() * 8 + 8); }
+static size_t job_capacity(size_t m) { return m + (size_t)JOB_BATCH * 4 * GPW * ((size_t)search_sms() * 8 * SEARCH_MAX_WAVES + 8); }
 
 size_t epipolar_scratch_bytes(int n)
 {
@@ -1459,7 +1478,11 @@ static int seeds_update_impl(const DevFrame* d_frames, int cur_slot, const DevCa
   int* count = reinterpret_cast<int*>(p) + range;
   seeds_geom_kernel<SRC><<<(n + 127) / 128, 128, 0, s>>>(cam, n, src, opts, d_seeds, tasks, count);
   if (marks) cudaEventRecord(marks[0], s);
-  epi_search_kernel<<<search_grid(n), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, nullptr, match, jobs, count, nullptr);
+  // small seed lists (the shard of an 8-GPU run): two waves of CTAs instead of a persistent grid, so that the tracking chain of the next
+  // frame (higher-priority stream) gets SM slots while the search is running: 0.595 -> 0.564 ms per step at 512 sequences; bigger lists
+  // fill the machine either way and lose 3-8 % to the extra CTA turnover, so they stay persistent
+  const int waves = n <= 450000 ? 2 : 1;
+  epi_search_kernel<<<search_grid(n, waves), 128, 0, s>>>(d_frames, cur_slot, cam, n, opts, tasks, nullptr, match, jobs, count, nullptr);
   if (marks) cudaEventRecord(marks[1], s);
   *launches += 2;
   LkSink sink{};

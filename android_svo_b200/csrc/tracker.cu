@@ -842,7 +842,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
     // direct launches of a big batch: sub-ranges alternate between two streams (chain mode keeps one range: its reprojector
     // scratch is shared), and the depth filter of the whole batch follows on its own stream
     int n_ranges = 1;
-    if (!use_graph && !t->profiling && t->chain_cell <= 0) n_ranges = std::max(1, std::min(std::min(t->ranges, 4), B / std::max(1, t->min_range)));
+    if (!use_graph && !t->profiling && t->chain_cell <= 0) n_ranges = std::max(1, std::min(std::min(t->ranges, 4), B / std::max(1, t->min_range)));   // (<= 4 <= SEED_RANGES)
     if (n_ranges > 1 && !t->range_stream) {
       CU(cudaStreamCreateWithFlags(&t->range_stream, cudaStreamNonBlocking));
       for (auto& e : t->range_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -974,7 +974,7 @@ int svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride
       for (auto& e : t->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     // chunks alternate between the two compute streams (see `ranges`), each waiting for its own frame copy
-    const bool two_streams = n_chunks > 1 && t->ranges > 1 && t->chain_cell <= 0 && n_chunks <= (int)SEED_RANGES;
+    const bool two_streams = n_chunks > 1 && t->ranges > 1 && t->chain_cell <= 0 && n_chunks <= (int)SEED_RANGES;   // one job region per chunk in flight
     if (two_streams && !t->range_stream) {
       CU(cudaStreamCreateWithFlags(&t->range_stream, cudaStreamNonBlocking));
       for (auto& e : t->range_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
