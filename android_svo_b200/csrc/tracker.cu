@@ -112,6 +112,109 @@ __global__ void kf_occupancy_kernel(int n, const int* ftr_image, const double* p
   if (k >= 0 && k < n_cells) occ[(size_t)ftr_image[i] * n_cells + k] = 1;
 }
 
+// ---- map points with one observation per keyframe they were matched in (Point::obs_, point.h; Point::addFrameRef pushes to the front)
+// point i owns the K slots [i*K, (i+1)*K) of obs / T_obs; its list, newest first, is [obs_begin, obs_end) = the top end of that block.
+__device__ __forceinline__ v3d kf_frame_pos(const double* T)
+{
+  double inv[7];
+  se3_inverse(T, inv);
+  return {inv[0], inv[1], inv[2]};
+}
+
+__global__ void points_init_kernel(int n, int K, const svob200_feature_ref* ftrs, const double* T_kf, const double* pt_world, svob200_map_point* pts,
+                                   svob200_feature_ref* obs, double* T_obs)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = i * K + K - 1;
+  obs[slot] = ftrs[i];
+  for (int k = 0; k < 7; ++k) T_obs[7 * (size_t)slot + k] = T_kf[7 * (size_t)i + k];
+  svob200_map_point p;
+  for (int k = 0; k < 3; ++k) p.pos[k] = pt_world[3 * (size_t)i + k];
+  p.type = SVOB200_POINT_UNKNOWN; p.obs_begin = slot; p.obs_end = (i + 1) * K; p.reserved = 0;
+  pts[i] = p;
+}
+
+// The head of Matcher::findMatchDirect for every map point (matcher.cpp:156-173): Point::getCloseViewObs (point.cpp:101-125: arg-max of
+// the cosine over obs_ in list order, strict >, starting from 0; fails below 0.5), then px = cur.w2c(pos) (reprojector.cpp:131-145),
+// depth_ref = |ref.pos() - pos| and T_cur_ref = cur.T_f_w * ref.T_f_w^-1.  The chosen observation becomes this step's ftrs[i].
+__global__ void __launch_bounds__(128) points_select_kernel(DevCam cam, int n, const svob200_map_point* pts, const svob200_feature_ref* obs,
+                                                            const double* T_obs, const int* image, const double* T_cur_w, svob200_feature_ref* ftrs,
+                                                            double* depth_ref, double* px_in, uint8_t* active)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const svob200_map_point p = pts[i];
+  const int b = image[i];
+  const double* T = T_cur_w + 7 * (size_t)b;
+  const v3d pos = {p.pos[0], p.pos[1], p.pos[2]};
+  double u, v;
+  world2cam(cam, se3_transform(T, pos), u, v);
+  px_in[2 * (size_t)i] = u; px_in[2 * (size_t)i + 1] = v;
+  uint8_t act = 0;
+  double dref = 0.0;
+  if (p.obs_end > p.obs_begin) {
+    const v3d cur_pos = kf_frame_pos(T);
+    const v3d od = normalized3({cur_pos.x - pos.x, cur_pos.y - pos.y, cur_pos.z - pos.z});
+    int best = p.obs_begin;
+    double min_cos = 0.0;
+    v3d best_pos = kf_frame_pos(T_obs + 7 * (size_t)p.obs_begin);
+    for (int k = p.obs_begin; k < p.obs_end; ++k) {
+      const v3d op = kf_frame_pos(T_obs + 7 * (size_t)k);
+      const v3d d = normalized3({op.x - pos.x, op.y - pos.y, op.z - pos.z});
+      const double c = dot3(od, d);
+      if (c > min_cos) { min_cos = c; best = k; best_pos = op; }
+    }
+    if (!(min_cos < 0.5)) {
+      act = 1;
+      svob200_feature_ref f = obs[best];
+      f.cur_image = b;
+      double inv[7];
+      se3_inverse(T_obs + 7 * (size_t)best, inv);
+      se3_mul(T, inv, f.T_cur_ref);
+      ftrs[i] = f;
+      dref = norm3({best_pos.x - pos.x, best_pos.y - pos.y, best_pos.z - pos.z});
+    }
+  }
+  active[i] = act;
+  depth_ref[i] = dref;
+}
+
+// frame_handler_mono.cpp:277-279: every feature of the new keyframe with a point adds a frame reference to it (push_front).
+// The keyframe's features are the map points matched in it: Feature(frame, px_refined, search_level) (reprojector.cpp:219-231).
+__global__ void kf_add_obs_kernel(DevCam cam, int n, int K, svob200_map_point* pts, svob200_feature_ref* obs, double* T_obs, const int* image,
+                                  const int* match_ok, const double* px, const int* level, int kf_slot, const double* T_cur_w)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !match_ok[i]) return;
+  svob200_map_point p = pts[i];
+  if (p.obs_end - p.obs_begin >= K) return;                      // (cannot happen: at most one observation per resident keyframe)
+  const int slot = p.obs_begin - 1;
+  svob200_feature_ref f;
+  f.ref_frame_id = kf_slot; f.ref_image = image[i]; f.cur_image = image[i]; f.level = level[i]; f.type = 0;
+  f.px[0] = px[2 * (size_t)i]; f.px[1] = px[2 * (size_t)i + 1];
+  const v3d fv = cam2world(cam, f.px[0], f.px[1]);
+  f.f[0] = fv.x; f.f[1] = fv.y; f.f[2] = fv.z; f.grad[0] = 1.0; f.grad[1] = 0.0;
+  for (int k = 0; k < 7; ++k) { f.T_cur_ref[k] = 0.0; T_obs[7 * (size_t)slot + k] = T_cur_w[7 * (size_t)image[i] + k]; }
+  obs[slot] = f;
+  pts[i].obs_begin = slot;
+}
+
+// Map::safeDeleteFrame -> Point::deleteFrameRef for every point seen in the keyframe that leaves the ring
+__global__ void kf_drop_obs_kernel(int n, int K, svob200_map_point* pts, svob200_feature_ref* obs, double* T_obs, int kf_slot)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const svob200_map_point p = pts[i];
+  int w = p.obs_end;                                             // compact towards the top end, keeping the list order
+  for (int k = p.obs_end - 1; k >= p.obs_begin; --k) {
+    if ((int)obs[k].ref_frame_id == kf_slot) continue;
+    --w;
+    if (w != k) { obs[w] = obs[k]; for (int j = 0; j < 7; ++j) T_obs[7 * (size_t)w + j] = T_obs[7 * (size_t)k + j]; }
+  }
+  pts[i].obs_begin = w;
+}
+
 // seeds of a dropped keyframe leave the pool (DepthFilter::removeKeyframe, depth_filter.cpp:153-170)
 __global__ void kf_erase_seeds_kernel(int n, SeedRef* refs, int kf)
 {
@@ -219,8 +322,11 @@ struct svob200_tracker {
   int N = 0, S = 0, max_per = 0;
   int *d_ftr_off = nullptr, *d_seed_off = nullptr, *d_ftr_image = nullptr, *d_match_ok = nullptr;
   uint8_t* d_has_point = nullptr;
-  svob200_feature_ref* d_ftrs = nullptr;
+  svob200_feature_ref* d_ftrs = nullptr;            // the observation chosen for each map point in the current step
   double *d_pt_world = nullptr, *d_T_kf_ftr = nullptr;
+  // map points: K = max_kfs observation slots each (points / observations as svob200_reproject_map takes them)
+  svob200_feature_ref* d_pobs = nullptr; double* d_T_pobs = nullptr; uint8_t* d_active = nullptr;
+  int* d_match_level = nullptr; double* d_match_A = nullptr;
   // depth-filter seeds: 32-byte compact records + keyframe tables (pose per (keyframe, image), frame slot per keyframe)
   SeedRef* d_seed_refs = nullptr;
   double* d_T_kf = nullptr;            // [max_kfs][batch][7]
@@ -451,6 +557,8 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
 #define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
   DA(t->d_ftr_off, B + 1); DA(t->d_seed_off, B + 1); DA(t->d_ftr_image, N); DA(t->d_match_ok, N); DA(t->d_has_point, N);
   DA(t->d_ftrs, N); DA(t->d_seed_refs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N);
+  DA(t->d_pobs, (size_t)N * t->max_kfs); DA(t->d_T_pobs, 7 * (size_t)N * t->max_kfs); DA(t->d_active, N); DA(t->d_match_level, N); DA(t->d_match_A, 4 * (size_t)N);
+  DA(t->d_points, N);
   DA(t->d_T_kf, 7 * (size_t)B * t->max_kfs); DA(t->d_kf_slot, t->max_kfs); DA(t->d_seed_poses, (size_t)B * t->max_kfs); DA(t->d_seed_poses2, (size_t)B * t->max_kfs);
   DA(t->d_seeds, S); DA(t->d_step_in, 7 * (size_t)B + 2 * (size_t)N); DA(t->d_xyz, 3 * (size_t)N); DA(t->d_T_init, 7 * (size_t)B);
   DA(t->d_T_cur, 7 * (size_t)B); DA(t->d_depth_ref, N); DA(t->d_px_in, 2 * (size_t)N); DA(t->d_px_out, 2 * (size_t)N);
@@ -494,6 +602,9 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
       if (pass == 0) {
         for (int i = 0; i < n; ++i) { ftrs[i].f[0] = f[3 * i]; ftrs[i].f[1] = f[3 * i + 1]; ftrs[i].f[2] = f[3 * i + 2]; }
         CU(cudaMemcpyAsync(t->d_ftrs, ftrs.data(), sizeof(svob200_feature_ref) * n, cudaMemcpyHostToDevice, s));
+        // every map point starts with ONE observation, in keyframe 0: the last slot of its block of K
+        points_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, t->max_kfs, t->d_ftrs, t->d_T_kf_ftr, t->d_pt_world, t->d_points, t->d_pobs, t->d_T_pobs);
+        ++ctx->launches;
       } else {
         for (int i = 0; i < n; ++i) { srefs[i].f[0] = f[3 * i]; srefs[i].f[1] = f[3 * i + 1]; srefs[i].f[2] = f[3 * i + 2]; }
         CU(cudaMemcpyAsync(t->d_seed_refs, srefs.data(), sizeof(SeedRef) * n, cudaMemcpyHostToDevice, s));
@@ -549,11 +660,13 @@ int svob200_tracker_add_keyframe(svob200_tracker* t, const float* depth_mean, co
   int k = -1;
   for (int i = 0; i < t->max_kfs; ++i) if (t->fid_kfs[i] == 0) { k = i; break; }
   if (k < 0) {
-    // (keyframe 0 holds the reference patches of the map features and stays; its seeds age out by the batch rule anyway)
-    const int first = (N > 0 && t->max_kfs > 1) ? 1 : 0;
-    k = first;
-    for (int i = first + 1; i < t->max_kfs; ++i) if (t->kf_batch[i] < t->kf_batch[k]) k = i;
+    k = 0;
+    for (int i = 1; i < t->max_kfs; ++i) if (t->kf_batch[i] < t->kf_batch[k]) k = i;
     if (S) { kf_erase_seeds_kernel<<<(S + 255) / 256, 256, 0, s>>>(S, t->d_seed_refs, k); ++ctx->launches; }
+    if (N) {                                                 // Map::safeDeleteFrame: the points forget the keyframe
+      FrameRec* old = find_frame(ctx, t->fid_kfs[k]);
+      kf_drop_obs_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, t->max_kfs, t->d_points, t->d_pobs, t->d_T_pobs, old->slot); ++ctx->launches;
+    }
     t->fid_kfs[k] = 0;
   }
   // 2. the frame: the last step's current frame (now `last`).  Its level 0 may alias the caller's buffer: the keyframe owns a copy.
@@ -593,6 +706,12 @@ int svob200_tracker_add_keyframe(svob200_tracker* t, const float* depth_mean, co
   if (S) {
     kf_append_seeds_kernel<<<B, 256, 0, s>>>(to_cam(&t->cam), t->d_det_cells, n_cells, t->det_thr, t->d_depth_mean, t->d_depth_min, t->d_seed_off, t->d_seed_refs,
                                              t->d_seeds, k, t->batch_counter, t->d_kf_appended, t->d_kf_dropped);
+    ++ctx->launches;
+  }
+  // 5. the matched map points gain an observation in the new keyframe (frame_handler_mono.cpp:277-279)
+  if (N) {
+    kf_add_obs_kernel<<<(N + 255) / 256, 256, 0, s>>>(to_cam(&t->cam), N, t->max_kfs, t->d_points, t->d_pobs, t->d_T_pobs, t->d_ftr_image, t->d_match_ok, t->d_px_out,
+                                                      t->d_match_level, slot, t->d_T_cur);
     ++ctx->launches;
   }
   if (cudaGetLastError() != cudaSuccess) return fail(ctx, SVOB200_ERR_CUDA, "tracker_add_keyframe: launch error");
@@ -636,22 +755,16 @@ int svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, in
   const int B = t->batch, N = t->N;
   const int n_cells = ((t->cam.width + cell_size - 1) / cell_size) * ((t->cam.height + cell_size - 1) / cell_size);
   if (n_cells > 8192) return fail(ctx, SVOB200_ERR_UNSUPPORTED, "tracker_set_chain: grid of %d cells exceeds the kernel's table (8192)", n_cells);
-  if (!t->d_points || n_cells != t->chain_cells) {
+  if (!t->d_reproj || n_cells != t->chain_cells) {
 #define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
     const size_t M = (size_t)B * n_cells;
-    if (!t->d_points) { DA(t->d_points, N); DA(t->d_reproj, N); DA(t->d_rstats, B); DA(t->d_pose, B); DA(t->d_m_count, B); DA(t->d_seg_begin, B); DA(t->d_seg_end, B);
+    if (!t->d_reproj) { DA(t->d_reproj, N); DA(t->d_rstats, B); DA(t->d_pose, B); DA(t->d_m_count, B); DA(t->d_seg_begin, B); DA(t->d_seg_end, B);
       uint8_t* q = nullptr; if (int e = dalloc(ctx, &q, reproject_scratch_bytes(N))) return e; t->owned.push_back(q); t->d_reproj_scratch = q; }
     DA(t->d_winner, M); DA(t->d_m_level, M); DA(t->d_m_point, M); DA(t->d_m_f, 3 * M); DA(t->d_m_pos, 3 * M); DA(t->d_pose_work, M); DA(t->d_outlier, M);
 #undef DA
   }
-  // the keyframe's map points as reprojector candidates: insertion order = the keyframe's fts_ order, one observation each
-  // (the keyframe feature), every point TYPE_UNKNOWN
-  std::vector<svob200_map_point> pts((size_t)N);
-  for (int i = 0; i < N; ++i) {
-    for (int k = 0; k < 3; ++k) pts[i].pos[k] = t->h_pt_world[3 * (size_t)i + k];
-    pts[i].type = SVOB200_POINT_UNKNOWN; pts[i].obs_begin = i; pts[i].obs_end = i + 1; pts[i].reserved = 0;
-  }
-  CU(cudaMemcpyAsync(t->d_points, pts.data(), sizeof(svob200_map_point) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  // the map points as reprojector candidates: insertion order = the keyframe's fts_ order, every point TYPE_UNKNOWN (d_points /
+  // d_obs / d_T_obs already hold them with their observation lists)
   CU(cudaMemsetAsync(t->d_pose, 0, sizeof(svob200_pose_opt_result) * (size_t)B, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   t->chain_cell = cell_size; t->chain_max_fts = max_fts; t->chain_pose_opt = pose_opt ? 1 : 0; t->chain_cells = n_cells;
@@ -721,8 +834,12 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   // chain mode: the depth filter waits for the pose optimiser's T_cur, so its branch cannot start here
   cudaStream_t s_seeds = (fork && t->chain_cell <= 0) ? s2 : s;
   if (s_seeds != s) { CU(cudaEventRecord(t->fork_ev[2], s)); CU(cudaStreamWaitEvent(s_seeds, t->fork_ev[2], 0)); }
-  if (launch_reproject_prepare(cam, nf, t->d_ftrs + f0, t->d_pt_world + 3 * (size_t)f0, t->d_T_kf_ftr + 7 * (size_t)f0, t->d_T_cur,
-                               t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, s, &ctx->launches)) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_prepare failed");
+  if (t->chain_cell <= 0 && nf > 0) {
+    // Point::getCloseViewObs per map point + px = cur.w2c(pos), depth_ref, T_cur_ref (the head of findMatchDirect)
+    points_select_kernel<<<(nf + 127) / 128, 128, 0, s>>>(cam, nf, t->d_points + f0, t->d_pobs, t->d_T_pobs, t->d_ftr_image + f0, t->d_T_cur, t->d_ftrs + f0,
+                                                          t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->d_active + f0);
+    ++ctx->launches;
+  }
   MARK(4);
   if (t->chain_cell > 0) {
     // 4b-5. chain mode: Reprojector::reprojectMap (grid, every in-frame candidate matched in parallel, per-cell first success,
@@ -730,8 +847,8 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
     // on T_cur, so the depth filter sees the optimised pose).
     MARK(4);
     const size_t cb = (size_t)c0 * t->chain_cells;
-    const int rc = launch_reproject_map(ctx->d_table, cur->slot, cam, cnt, t->d_T_cur + 7 * (size_t)c0, t->d_ftr_off + c0, t->N, t->d_points, t->d_ftrs,
-                                        t->d_T_kf_ftr, t->chain_cell, t->chain_max_fts, t->mopts, t->d_reproj, t->d_winner + cb, t->d_rstats + c0,
+    const int rc = launch_reproject_map(ctx->d_table, cur->slot, cam, cnt, t->d_T_cur + 7 * (size_t)c0, t->d_ftr_off + c0, t->N, t->d_points, t->d_pobs,
+                                        t->d_T_pobs, t->chain_cell, t->chain_max_fts, t->mopts, t->d_reproj, t->d_winner + cb, t->d_rstats + c0,
                                         t->d_reproj_scratch, t->d_match_scratch, t->d_m_f + 3 * cb, t->d_m_level + cb, t->d_m_pos + 3 * cb,
                                         t->d_m_point + cb, t->d_m_count + c0, s, &ctx->launches, c0, f0, nf);
     if (rc) return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: reproject_map failed (%d)", rc);
@@ -750,7 +867,7 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   // (item indices inside the call are relative to f0, so the output arrays are passed at f0 as well)
   if (launch_match_direct(ctx->d_table, cur->slot, cam, nf, t->d_ftrs + f0, t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->mopts, nullptr,
                           t->d_px_out + 2 * (size_t)f0, t->d_match_ok + f0, t->d_match_scratch, t->N, f0, s, &ctx->launches,
-                          (marks && t->profiling) ? &t->ev[5] : nullptr))
+                          (marks && t->profiling) ? &t->ev[5] : nullptr, t->d_active + f0, t->d_match_level + f0, t->d_match_A + 4 * (size_t)f0))
     return fail(ctx, SVOB200_ERR_CUDA, "tracker_step: match_direct failed");
   MARK(7);
   }

@@ -290,7 +290,11 @@ int  svob200_tracker_set_last(svob200_tracker* t, const uint8_t* imgs, int strid
  * svob200_tracker_add_keyframe: the frame of the most recent step becomes a keyframe of every sequence, with the pose the step
  *   gave it: occupancy grid from the frame's features (= the map points matched in it, AbstractDetector::setExistingFeatures),
  *   FAST + Shi-Tomasi + grid selection on its pyramid, one Seed(ftr, depth_mean, depth_min) per new corner in cell order
- *   (batch_id = ++Seed::batch_counter) into the empty slots of the sequence's pool.  depth_mean / depth_min: one per sequence,
+ *   (batch_id = ++Seed::batch_counter) into the empty slots of the sequence's pool; every map point matched in the frame gains
+ *   an observation in it (Feature(frame, px_refined, search_level) + Point::addFrameRef, reprojector.cpp:219-231,
+ *   frame_handler_mono.cpp:277-279), and from then on each step matches a point against its closest-view observation
+ *   (Point::getCloseViewObs, point.cpp:101-125); when the oldest keyframe leaves the ring its seeds are erased
+ *   (DepthFilter::removeKeyframe) and the points forget it (Map::safeDeleteFrame).  depth_mean / depth_min: one per sequence,
  *   host memory (FrameHandlerMono passes frame_utils::getSceneDepth's mean and 0.5 * min).  n_new_seeds / n_dropped (host,
  *   one int per sequence, may be NULL): seeds created / corners that found no empty slot.
  * svob200_tracker_get_seed_refs: the pool slot by slot (host arrays of svob200_tracker_num_seed_slots entries, any may be NULL). */

@@ -532,8 +532,9 @@ struct RefSeq {
   std::vector<int> kf_batch;
   int max_kfs = 4;
   double conv_thresh = 100.0;
-  std::vector<double> step_px; std::vector<int> step_ok;
+  std::vector<double> step_px; std::vector<int> step_ok, step_level;
   ThreadedDF* tdf = NULL;               // two-thread layout (svo_ref_seq_set_threaded)
+  bool kf_dropped = false;
   long n_conv_async = 0;
 };
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -596,19 +597,21 @@ int svo_ref_seq_add_keyframe(void* h, float depth_mean, float depth_min)
   fr->fts_.clear();
   for (size_t i = 0; i < s->pts.size(); ++i) {
     if (!s->step_ok[i]) continue;
-    Feature* f = new Feature(fr.get(), Vector2d(s->step_px[2 * i], s->step_px[2 * i + 1]), 0);
+    Feature* f = new Feature(fr.get(), Vector2d(s->step_px[2 * i], s->step_px[2 * i + 1]), s->step_level[i]);
     f->point = s->pts[i];
     fr->fts_.push_back(f);
   }
   fr->setKeyframe();
+  for (auto f : fr->fts_) f->point->addFrameRef(f);                  // frame_handler_mono.cpp:277-279
   if (s->kfs.empty()) { s->kfs.assign(s->max_kfs, FramePtr()); s->kf_batch.assign(s->max_kfs, 0); s->kfs[0] = s->kf; }
   int k = -1;
   for (int i = 0; i < s->max_kfs; ++i) if (!s->kfs[i]) { k = i; break; }
   if (k < 0) {
-    const int first = (!s->pts.empty() && s->max_kfs > 1) ? 1 : 0;
-    k = first;
-    for (int i = first + 1; i < s->max_kfs; ++i) if (s->kf_batch[i] < s->kf_batch[k]) k = i;
+    k = 0;
+    for (int i = 1; i < s->max_kfs; ++i) if (s->kf_batch[i] < s->kf_batch[k]) k = i;
     s->df->removeKeyframe(s->kfs[k]);
+    for (auto p : s->pts) p->deleteFrameRef(s->kfs[k].get());           // Map::safeDeleteFrame (map.cpp): the points forget the keyframe
+    if (s->kfs[k] == s->kf) s->kf_dropped = true;
   }
   s->kfs[k] = fr;
   const size_t before = s->df->getSeeds().size();
@@ -749,12 +752,12 @@ void svo_ref_seq_step(void* h, const uint8_t* cur_img, const double* T_last_w, c
   } else {
   for (int i = 0; i < N; ++i) {
     Vector2d px(cur->w2c(s->pts[i]->pos_));                         // reprojector.cpp:131-145
-    const bool ok = s->matcher.findMatchDirect(*s->pts[i], *cur, px);
+    const bool ok = !s->pts[i]->obs_.empty() && s->matcher.findMatchDirect(*s->pts[i], *cur, px);   // (getCloseViewObs dereferences obs_.begin())
     st->n_matched += ok ? 1 : 0;
     if (px_refined) { px_refined[2 * i] = px[0]; px_refined[2 * i + 1] = px[1]; }
     if (match_ok) match_ok[i] = ok ? 1 : 0;
-    if ((int)s->step_ok.size() != N) { s->step_ok.assign(N, 0); s->step_px.assign(2 * (size_t)N, 0.0); }
-    s->step_px[2 * i] = px[0]; s->step_px[2 * i + 1] = px[1]; s->step_ok[i] = ok ? 1 : 0;
+    if ((int)s->step_ok.size() != N) { s->step_ok.assign(N, 0); s->step_level.assign(N, 0); s->step_px.assign(2 * (size_t)N, 0.0); }
+    s->step_px[2 * i] = px[0]; s->step_px[2 * i + 1] = px[1]; s->step_ok[i] = ok ? 1 : 0; s->step_level[i] = s->matcher.search_level_;
   }
   }
   s->conv_points.clear();

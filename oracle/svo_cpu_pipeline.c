@@ -55,7 +55,9 @@ typedef struct svo_seq {
   int det_cell, det_levels; double det_thr;
   int S_cap;
   int *seed_kf, *seed_batch, *seed_alive;
-  double *step_px; int* step_ok; double T_step[7]; int have_step;
+  double *step_px; int* step_ok; int* step_level; double T_step[7]; int have_step;
+  /* map points: one observation per keyframe the point was matched in (Point::obs_, newest first: addFrameRef pushes to the front) */
+  int* pobs_n; int* pobs_kf; double* pobs_px; double* pobs_f; int* pobs_level;      /* [N][SVO_SEQ_MAX_KFS] */
   /* per-step scratch */
   double *xyz; uint8_t* has_point;
   /* chain mode (svo_oracle_seq_set_chain): Reprojector::reprojectMap + pose_optimizer::optimizeGaussNewton replace the
@@ -98,7 +100,8 @@ void svo_oracle_seq_destroy(svo_seq* s)
   free(s->kf0); free(s->kfu); free(s->last0); free(s->lastu); free(s->cur0); free(s->curu);
   free(s->kf_px); free(s->kf_f); free(s->pt_world); free(s->kf_level);
   free(s->seed_px); free(s->seed_f); free(s->seed_level); free(s->seeds); free(s->xyz); free(s->has_point); free(s->obs);
-  free(s->seed_kf); free(s->seed_batch); free(s->seed_alive); free(s->step_px); free(s->step_ok);
+  free(s->seed_kf); free(s->seed_batch); free(s->seed_alive); free(s->step_px); free(s->step_ok); free(s->step_level);
+  free(s->pobs_n); free(s->pobs_kf); free(s->pobs_px); free(s->pobs_f); free(s->pobs_level);
   for (int k = 1; k < SVO_SEQ_MAX_KFS; ++k) { free(s->kfs0[k]); free(s->kfsu[k]); }
   free(s);
 }
@@ -119,11 +122,23 @@ void svo_oracle_seq_set_keyframe(svo_seq* s, const uint8_t* img, const double* T
   s->seed_kf = (int*)calloc((size_t)S + 1, sizeof(int)); s->seed_batch = (int*)calloc((size_t)S + 1, sizeof(int)); s->seed_alive = (int*)malloc(sizeof(int) * (S + 1));
   for (int i = 0; i < S; ++i) s->seed_alive[i] = 1;
   s->step_px = (double*)malloc(sizeof(double) * 2 * (N + 1)); s->step_ok = (int*)calloc((size_t)N + 1, sizeof(int));
+  s->step_level = (int*)calloc((size_t)N + 1, sizeof(int));
+  {
+    const size_t M = (size_t)(N + 1) * SVO_SEQ_MAX_KFS;
+    s->pobs_n = (int*)calloc((size_t)N + 1, sizeof(int)); s->pobs_kf = (int*)calloc(M, sizeof(int)); s->pobs_level = (int*)calloc(M, sizeof(int));
+    s->pobs_px = (double*)calloc(2 * M, sizeof(double)); s->pobs_f = (double*)calloc(3 * M, sizeof(double));
+  }
   s->kf_used[0] = 1; s->kf_batch[0] = 0; s->kfp[0] = s->kf; memcpy(s->T_kfs[0], T_kf_w, sizeof(s->T_kfs[0]));
   memcpy(s->kf_px, kf_px, sizeof(double) * 2 * N); memcpy(s->pt_world, pt_world, sizeof(double) * 3 * N);
   memcpy(s->kf_level, kf_level, sizeof(int) * N);
   memcpy(s->seed_px, seed_px, sizeof(double) * 2 * S); memcpy(s->seed_level, seed_level, sizeof(int) * S);
   for (int i = 0; i < N; ++i) { svo_oracle_cam2world(&s->cam, kf_px[2 * i], kf_px[2 * i + 1], s->kf_f + 3 * i); s->has_point[i] = 1; }
+  for (int i = 0; i < N; ++i) {                                /* every map point starts with one observation, in keyframe 0 */
+    const size_t o = (size_t)i * SVO_SEQ_MAX_KFS;
+    s->pobs_n[i] = 1; s->pobs_kf[o] = 0; s->pobs_level[o] = kf_level[i];
+    s->pobs_px[2 * o] = kf_px[2 * i]; s->pobs_px[2 * o + 1] = kf_px[2 * i + 1];
+    memcpy(s->pobs_f + 3 * o, s->kf_f + 3 * i, sizeof(double) * 3);
+  }
   for (int i = 0; i < S; ++i) { svo_oracle_cam2world(&s->cam, seed_px[2 * i], seed_px[2 * i + 1], s->seed_f + 3 * i); s->seeds[i] = s->seed_init; }
 }
 
@@ -209,25 +224,40 @@ void svo_oracle_seq_step(svo_seq* s, const uint8_t* cur_img, const double* T_las
     }
     free(pts); free(obs); free(res); free(winner);
   } else {
-  /* reprojection refinement */
-  double Tkw_inv[7], T_cur_kf[7];
-  svo_oracle_se3_inverse(s->T_kf_w, Tkw_inv);
-  svo_oracle_se3_mul(Tc, Tkw_inv, T_cur_kf);
+  /* reprojection refinement: Matcher::findMatchDirect per map point (matcher.cpp:156-202) incl. Point::getCloseViewObs over the
+   * point's observations (point.cpp:101-125) */
+  double cur_pos[3];
+  svo_oracle_frame_pos(Tc, cur_pos);
   for (int i = 0; i < s->N; ++i) {
-    svo_ref_feature f;
-    f.px_ref[0] = s->kf_px[2 * i]; f.px_ref[1] = s->kf_px[2 * i + 1];
-    memcpy(f.f_ref, s->kf_f + 3 * i, sizeof(f.f_ref));
-    f.level_ref = s->kf_level[i]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
-    const double depth_ref = norm3d(Tkw_inv[0] - s->pt_world[3 * i], Tkw_inv[1] - s->pt_world[3 * i + 1], Tkw_inv[2] - s->pt_world[3 * i + 2]);
+    const size_t o = (size_t)i * SVO_SEQ_MAX_KFS;
     double pc[3], px_in[2];
     svo_oracle_se3_transform(Tc, s->pt_world + 3 * i, pc);
     svo_oracle_world2cam(&s->cam, pc, px_in);
     svo_match_result mr;
-    const int ok = svo_oracle_find_match_direct(&s->kf, &s->cur, &s->cam, &f, depth_ref, T_cur_kf, &s->mopts, px_in, &mr);
+    memset(&mr, 0, sizeof(mr));
+    mr.px_cur[0] = px_in[0]; mr.px_cur[1] = px_in[1];
+    int ok = 0;
+    if (s->pobs_n[i] > 0) {
+      double obs_pos[3 * SVO_SEQ_MAX_KFS];
+      for (int k = 0; k < s->pobs_n[i]; ++k) svo_oracle_frame_pos(s->T_kfs[s->pobs_kf[o + k]], obs_pos + 3 * k);
+      int best = 0;
+      if (svo_oracle_close_view_obs(cur_pos, s->pt_world + 3 * i, s->pobs_n[i], obs_pos, &best)) {
+        const int kfi = s->pobs_kf[o + best];
+        svo_ref_feature f;
+        f.px_ref[0] = s->pobs_px[2 * (o + best)]; f.px_ref[1] = s->pobs_px[2 * (o + best) + 1];
+        memcpy(f.f_ref, s->pobs_f + 3 * (o + best), sizeof(f.f_ref));
+        f.level_ref = s->pobs_level[o + best]; f.type = 0; f.grad[0] = 1.0; f.grad[1] = 0.0;
+        double Tkw_inv[7], T_cur_kf[7];
+        svo_oracle_se3_inverse(s->T_kfs[kfi], Tkw_inv);
+        svo_oracle_se3_mul(Tc, Tkw_inv, T_cur_kf);
+        const double depth_ref = norm3d(obs_pos[3 * best] - s->pt_world[3 * i], obs_pos[3 * best + 1] - s->pt_world[3 * i + 1], obs_pos[3 * best + 2] - s->pt_world[3 * i + 2]);
+        ok = svo_oracle_find_match_direct(&s->kfp[kfi], &s->cur, &s->cam, &f, depth_ref, T_cur_kf, &s->mopts, px_in, &mr);
+      }
+    }
     st->n_matched += ok;
     if (px_refined) { px_refined[2 * i] = mr.px_cur[0]; px_refined[2 * i + 1] = mr.px_cur[1]; }
     if (match_ok) match_ok[i] = ok;
-    s->step_px[2 * i] = mr.px_cur[0]; s->step_px[2 * i + 1] = mr.px_cur[1]; s->step_ok[i] = ok;
+    s->step_px[2 * i] = mr.px_cur[0]; s->step_px[2 * i + 1] = mr.px_cur[1]; s->step_ok[i] = ok; s->step_level[i] = mr.search_level;
   }
   }
   memcpy(s->T_step, Tc, sizeof(s->T_step)); s->have_step = 1;
@@ -313,10 +343,20 @@ int svo_oracle_seq_add_keyframe(svo_seq* s, float depth_mean, float depth_min)
   int k = -1;
   for (int i = 0; i < s->max_kfs; ++i) if (!s->kf_used[i]) { k = i; break; }
   if (k < 0) {
-    const int first = (s->N > 0 && s->max_kfs > 1) ? 1 : 0;      /* keyframe 0 holds the map features' reference patches */
-    k = first;
-    for (int i = first + 1; i < s->max_kfs; ++i) if (s->kf_batch[i] < s->kf_batch[k]) k = i;
+    k = 0;
+    for (int i = 1; i < s->max_kfs; ++i) if (s->kf_batch[i] < s->kf_batch[k]) k = i;
     for (int i = 0; i < s->S; ++i) if (s->seed_alive[i] && s->seed_kf[i] == k) s->seed_alive[i] = 0;   /* removeKeyframe */
+    for (int i = 0; i < s->N; ++i) {                               /* Map::safeDeleteFrame: the points forget the keyframe */
+      const size_t o = (size_t)i * SVO_SEQ_MAX_KFS;
+      int w = 0;
+      for (int j = 0; j < s->pobs_n[i]; ++j) {
+        if (s->pobs_kf[o + j] == k) continue;
+        if (w != j) { s->pobs_kf[o + w] = s->pobs_kf[o + j]; s->pobs_level[o + w] = s->pobs_level[o + j];
+                      memcpy(s->pobs_px + 2 * (o + w), s->pobs_px + 2 * (o + j), sizeof(double) * 2); memcpy(s->pobs_f + 3 * (o + w), s->pobs_f + 3 * (o + j), sizeof(double) * 3); }
+        ++w;
+      }
+      s->pobs_n[i] = w;
+    }
   }
   const size_t l0 = (size_t)s->w * s->h, up = svo_oracle_pyramid_bytes(s->w, s->h, s->n_levels) + 16;
   if (k == 0) {                                                    /* only without map features: reuse keyframe 0's buffers */
@@ -353,6 +393,20 @@ int svo_oracle_seq_add_keyframe(svo_seq* s, float depth_mean, float depth_min)
     ++n_new; ++slot;
   }
   free(occ); free(cells);
+  /* frame_handler_mono.cpp:277-279: the keyframe's features with a point add a frame reference to it (push_front); the features are the
+   * map points matched in the frame: Feature(frame, px_refined, search_level) (reprojector.cpp:219-231) */
+  for (int i = 0; i < s->N; ++i) {
+    if (!s->step_ok[i] || s->pobs_n[i] >= SVO_SEQ_MAX_KFS) continue;
+    const size_t o = (size_t)i * SVO_SEQ_MAX_KFS;
+    for (int j = s->pobs_n[i]; j > 0; --j) {
+      s->pobs_kf[o + j] = s->pobs_kf[o + j - 1]; s->pobs_level[o + j] = s->pobs_level[o + j - 1];
+      memcpy(s->pobs_px + 2 * (o + j), s->pobs_px + 2 * (o + j - 1), sizeof(double) * 2); memcpy(s->pobs_f + 3 * (o + j), s->pobs_f + 3 * (o + j - 1), sizeof(double) * 3);
+    }
+    s->pobs_kf[o] = k; s->pobs_level[o] = s->step_level[i];
+    s->pobs_px[2 * o] = s->step_px[2 * i]; s->pobs_px[2 * o + 1] = s->step_px[2 * i + 1];
+    svo_oracle_cam2world(&s->cam, s->step_px[2 * i], s->step_px[2 * i + 1], s->pobs_f + 3 * o);
+    s->pobs_n[i]++;
+  }
   return n_new;
 }
 void svo_oracle_seq_get_seed_obs(const svo_seq* s, svo_seq_seed_obs* out) { memcpy(out, s->obs, sizeof(svo_seq_seed_obs) * s->S); }

@@ -424,10 +424,12 @@ def test_oracle_keyframe_insertion_matches_reference(oracle, ref):
             s.set_last(imgs[0])
         n_kf = 0
         for k in range(1, n_frames + 1):
-            a = so.step(imgs[k], poses[k - 1], last_px[k - 1])
-            b = sr.step(imgs[k], poses[k - 1], last_px[k - 1])
+            a, pxa, oka = so.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            b, pxb, okb = sr.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
             assert np.array_equal(np.array(a.T_cur_w[:]), np.array(b.T_cur_w[:])) and a.n_matched == b.n_matched
-            assert a.n_seeds_converged == b.n_seeds_converged
+            # map points are matched against the closest-view observation among the keyframes they were seen in
+            assert np.array_equal(oka, okb) and np.array_equal(pxa, pxb), "refined pixels differ at frame %d" % k
+            assert a.n_seeds_converged == b.n_seeds_converged and a.n_matched > 80
             if k % 3 == 0:
                 na, nb = so.add_keyframe(2.0 + 0.01 * k, 1.0), sr.add_keyframe(2.0 + 0.01 * k, 1.0)
                 assert na == nb and na > 50, (na, nb)
@@ -457,7 +459,7 @@ def test_tracker_keyframe_insertion_matches_oracle(ctx, oracle, batch, mode):
     cfg = seqs[0][0]
     cam_o, cam_g = scenes.cam_of(cfg, Cam), scenes.cam_of(cfg, capi.Camera)
     args = (cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
-    N, S0, CAP = cfg["n_features"], 200, 1700
+    N, S0, CAP = cfg["n_features"], 200, 2400
     pinned = [OracleSeq(oracle, cam_o, *args, 100.0, 2.4, 1.2, 3) for _ in range(n_distinct)]
     trk = capi.Tracker(ctx, cam_g, batch, *args)
     try:
@@ -473,11 +475,16 @@ def test_tracker_keyframe_insertion_matches_oracle(ctx, oracle, batch, mode):
         (trk.set_last if mode == "host" else trk.set_last_device)(np.stack([seqs[w][2][0] for w in which]))
         n_bit_diff = n_seedframes = 0
         for k in range(1, n_frames + 1):
-            stats = gpu_step(trk, mode, np.stack([seqs[w][2][k] for w in which]), np.stack([seqs[w][1][k - 1] for w in which]),
-                             np.concatenate([seqs[w][4][k - 1] for w in which]))
+            stats, px_g, ok_g = gpu_step(trk, mode, np.stack([seqs[w][2][k] for w in which]), np.stack([seqs[w][1][k - 1] for w in which]),
+                                         np.concatenate([seqs[w][4][k - 1] for w in which]), want_px=True)
             for d in range(n_distinct):
                 pinned[d].set_pose_override(stats[d]["T_cur_w"])
-                pinned[d].step(seqs[d][2][k], seqs[d][1][k - 1], seqs[d][4][k - 1])
+                _, px_o, ok_o = pinned[d].step(seqs[d][2][k], seqs[d][1][k - 1], seqs[d][4][k - 1], want_px=True)
+                # the closest-view observation of every map point (several keyframes after the first insertion): same choice, same pixels
+                for b in np.nonzero(which == d)[0][:3]:
+                    assert np.array_equal(ok_g[b * N:(b + 1) * N], ok_o) and np.array_equal(px_g[b * N:(b + 1) * N], px_o), \
+                        "map-point matches differ (seq %d, frame %d)" % (b, k)
+                assert ok_o.sum() > 80
             if k % 3 == 0:
                 n_new, n_drop = trk.add_keyframe(2.0 + 0.01 * k, 1.0)
                 assert (n_drop == 0).all()
