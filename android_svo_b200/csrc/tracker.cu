@@ -140,7 +140,7 @@ __global__ void points_init_kernel(int n, int K, const svob200_feature_ref* ftrs
 // depth_ref = |ref.pos() - pos| and T_cur_ref = cur.T_f_w * ref.T_f_w^-1.  The chosen observation becomes this step's ftrs[i].
 __global__ void __launch_bounds__(128) points_select_kernel(DevCam cam, int n, const svob200_map_point* pts, const svob200_feature_ref* obs,
                                                             const double* T_obs, const int* image, const double* T_cur_w, svob200_feature_ref* ftrs,
-                                                            double* depth_ref, double* px_in, uint8_t* active)
+                                                            double* depth_ref, double* px_in, uint8_t* active, int* sel)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -167,12 +167,13 @@ __global__ void __launch_bounds__(128) points_select_kernel(DevCam cam, int n, c
     }
     if (!(min_cos < 0.5)) {
       act = 1;
-      svob200_feature_ref f = obs[best];
-      f.cur_image = b;
-      double inv[7];
+      // the 144-byte record is copied only when the choice changes (after a keyframe insertion); every step writes the 56 bytes
+      // that depend on the current pose
+      if (sel[i] != best) { svob200_feature_ref f = obs[best]; f.cur_image = b; ftrs[i] = f; sel[i] = best; }
+      double inv[7], Tcr[7];
       se3_inverse(T_obs + 7 * (size_t)best, inv);
-      se3_mul(T, inv, f.T_cur_ref);
-      ftrs[i] = f;
+      se3_mul(T, inv, Tcr);
+      for (int k = 0; k < 7; ++k) ftrs[i].T_cur_ref[k] = Tcr[k];
       dref = norm3({best_pos.x - pos.x, best_pos.y - pos.y, best_pos.z - pos.z});
     }
   }
@@ -201,10 +202,11 @@ __global__ void kf_add_obs_kernel(DevCam cam, int n, int K, svob200_map_point* p
 }
 
 // Map::safeDeleteFrame -> Point::deleteFrameRef for every point seen in the keyframe that leaves the ring
-__global__ void kf_drop_obs_kernel(int n, int K, svob200_map_point* pts, svob200_feature_ref* obs, double* T_obs, int kf_slot)
+__global__ void kf_drop_obs_kernel(int n, int K, svob200_map_point* pts, svob200_feature_ref* obs, double* T_obs, int kf_slot, int* sel)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  sel[i] = -1;                                                   // slots move: the next step copies its choice afresh
   const svob200_map_point p = pts[i];
   int w = p.obs_end;                                             // compact towards the top end, keeping the list order
   for (int k = p.obs_end - 1; k >= p.obs_begin; --k) {
@@ -327,6 +329,7 @@ struct svob200_tracker {
   // map points: K = max_kfs observation slots each (points / observations as svob200_reproject_map takes them)
   svob200_feature_ref* d_pobs = nullptr; double* d_T_pobs = nullptr; uint8_t* d_active = nullptr;
   int* d_match_level = nullptr; double* d_match_A = nullptr;
+  int* d_sel = nullptr;                    // observation slot currently copied into d_ftrs[i] (-1: none)
   // depth-filter seeds: 32-byte compact records + keyframe tables (pose per (keyframe, image), frame slot per keyframe)
   SeedRef* d_seed_refs = nullptr;
   double* d_T_kf = nullptr;            // [max_kfs][batch][7]
@@ -557,7 +560,7 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
 #define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
   DA(t->d_ftr_off, B + 1); DA(t->d_seed_off, B + 1); DA(t->d_ftr_image, N); DA(t->d_match_ok, N); DA(t->d_has_point, N);
   DA(t->d_ftrs, N); DA(t->d_seed_refs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N);
-  DA(t->d_pobs, (size_t)N * t->max_kfs); DA(t->d_T_pobs, 7 * (size_t)N * t->max_kfs); DA(t->d_active, N); DA(t->d_match_level, N); DA(t->d_match_A, 4 * (size_t)N);
+  DA(t->d_pobs, (size_t)N * t->max_kfs); DA(t->d_T_pobs, 7 * (size_t)N * t->max_kfs); DA(t->d_active, N); DA(t->d_match_level, N); DA(t->d_match_A, 4 * (size_t)N); DA(t->d_sel, N);
   DA(t->d_points, N);
   DA(t->d_T_kf, 7 * (size_t)B * t->max_kfs); DA(t->d_kf_slot, t->max_kfs); DA(t->d_seed_poses, (size_t)B * t->max_kfs); DA(t->d_seed_poses2, (size_t)B * t->max_kfs);
   DA(t->d_seeds, S); DA(t->d_step_in, 7 * (size_t)B + 2 * (size_t)N); DA(t->d_xyz, 3 * (size_t)N); DA(t->d_T_init, 7 * (size_t)B);
@@ -603,6 +606,7 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
         for (int i = 0; i < n; ++i) { ftrs[i].f[0] = f[3 * i]; ftrs[i].f[1] = f[3 * i + 1]; ftrs[i].f[2] = f[3 * i + 2]; }
         CU(cudaMemcpyAsync(t->d_ftrs, ftrs.data(), sizeof(svob200_feature_ref) * n, cudaMemcpyHostToDevice, s));
         // every map point starts with ONE observation, in keyframe 0: the last slot of its block of K
+        CU(cudaMemsetAsync(t->d_sel, 0xff, sizeof(int) * (size_t)n, s));
         points_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, t->max_kfs, t->d_ftrs, t->d_T_kf_ftr, t->d_pt_world, t->d_points, t->d_pobs, t->d_T_pobs);
         ++ctx->launches;
       } else {
@@ -665,7 +669,7 @@ int svob200_tracker_add_keyframe(svob200_tracker* t, const float* depth_mean, co
     if (S) { kf_erase_seeds_kernel<<<(S + 255) / 256, 256, 0, s>>>(S, t->d_seed_refs, k); ++ctx->launches; }
     if (N) {                                                 // Map::safeDeleteFrame: the points forget the keyframe
       FrameRec* old = find_frame(ctx, t->fid_kfs[k]);
-      kf_drop_obs_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, t->max_kfs, t->d_points, t->d_pobs, t->d_T_pobs, old->slot); ++ctx->launches;
+      kf_drop_obs_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, t->max_kfs, t->d_points, t->d_pobs, t->d_T_pobs, old->slot, t->d_sel); ++ctx->launches;
     }
     t->fid_kfs[k] = 0;
   }
@@ -837,7 +841,7 @@ static int run_range(svob200_tracker* t, int c0, int c1, const double* d_T_last,
   if (t->chain_cell <= 0 && nf > 0) {
     // Point::getCloseViewObs per map point + px = cur.w2c(pos), depth_ref, T_cur_ref (the head of findMatchDirect)
     points_select_kernel<<<(nf + 127) / 128, 128, 0, s>>>(cam, nf, t->d_points + f0, t->d_pobs, t->d_T_pobs, t->d_ftr_image + f0, t->d_T_cur, t->d_ftrs + f0,
-                                                          t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->d_active + f0);
+                                                          t->d_depth_ref + f0, t->d_px_in + 2 * (size_t)f0, t->d_active + f0, t->d_sel + f0);
     ++ctx->launches;
   }
   MARK(4);
