@@ -184,12 +184,17 @@ int svob200_frame_create(svob200_ctx* ctx, int64_t frame_id, int batch, int w, i
   }
   total += 256;   // slack so word-granular reads at the very end stay inside the allocation
   if (cudaMalloc((void**)&r.base, total) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SVOB200_ERR_NOMEM, "frame_create: cudaMalloc(%zu) failed", total); }
-  CU(cudaMemsetAsync(r.base, 0, total, ctx->stream));
   for (int l = 0; l < n_levels; ++l) r.f.lvl[l] = r.base + off[l];
   r.own_l0 = r.f.lvl[0]; r.own_pitch0 = r.f.pitch[0];
   r.slot = ctx->free_slots.back(); ctx->free_slots.pop_back();
-  CU(cudaMemcpyAsync(ctx->d_table + r.slot, &r.f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));      // r.f is a stack object
+  cudaError_t e = cudaMemsetAsync(r.base, 0, total, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_table + r.slot, &r.f, sizeof(DevFrame), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // r.f is a stack object
+  if (e != cudaSuccess) {                                             // nothing is left behind: the allocation and the table slot go back
+    cudaFree(r.base);
+    ctx->free_slots.push_back(r.slot);
+    return fail(ctx, SVOB200_ERR_CUDA, "frame_create: %s", cudaGetErrorString(e));
+  }
   ctx->frames[frame_id] = r;
   return SVOB200_OK;
 }

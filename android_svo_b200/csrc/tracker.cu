@@ -557,7 +557,13 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
       if (i < seed_offsets[b + 1]) { r.px[0] = seed_px[2 * i]; r.px[1] = seed_px[2 * i + 1]; r.level = (uint8_t)seed_level[i]; r.kf = 0; r.batch_id = 0; r.state = 0; }
     }
   }
-#define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) return e_; t->owned.push_back(ptr); } while (0)
+  // an allocation that fails midway leaves the tracker as it was before the call (it can be retried or destroyed)
+  auto rollback = [&]() {
+    for (void* q : t->owned) cudaFree(q);
+    t->owned.clear();
+    t->N = t->S = 0; t->max_per = 0; t->d_stats = nullptr; t->d_reproj = nullptr; t->det_cells_alloc = 0; t->d_det_counts = nullptr;
+  };
+#define DA(ptr, n) do { if (int e_ = dalloc(ctx, &ptr, (size_t)(n))) { rollback(); return e_; } t->owned.push_back(ptr); } while (0)
   DA(t->d_ftr_off, B + 1); DA(t->d_seed_off, B + 1); DA(t->d_ftr_image, N); DA(t->d_match_ok, N); DA(t->d_has_point, N);
   DA(t->d_ftrs, N); DA(t->d_seed_refs, S); DA(t->d_pt_world, 3 * (size_t)N); DA(t->d_T_kf_ftr, 7 * (size_t)N);
   DA(t->d_pobs, (size_t)N * t->max_kfs); DA(t->d_T_pobs, 7 * (size_t)N * t->max_kfs); DA(t->d_active, N); DA(t->d_match_level, N); DA(t->d_match_A, 4 * (size_t)N); DA(t->d_sel, N);
@@ -568,13 +574,13 @@ int svob200_tracker_set_keyframe(svob200_tracker* t, const uint8_t* imgs, int st
   DA(t->d_align, B); DA(t->d_obs, S); DA(t->d_stats, B); DA(t->d_stats2, B);
   {
     uint8_t* p = nullptr;
-    if (int e = dalloc(ctx, &p, sparse_align_scratch_bytes(N))) return e;
+    if (int e = dalloc(ctx, &p, sparse_align_scratch_bytes(N))) { rollback(); return e; }
     t->owned.push_back(p); t->d_align_scratch = p;
     uint8_t* q = nullptr;
-    if (int e = dalloc(ctx, &q, seeds_scratch_bytes(S))) return e;
+    if (int e = dalloc(ctx, &q, seeds_scratch_bytes(S))) { rollback(); return e; }
     t->owned.push_back(q); t->d_seed_scratch = q;
     uint8_t* m = nullptr;
-    if (int e = dalloc(ctx, &m, match_scratch_bytes(N))) return e;
+    if (int e = dalloc(ctx, &m, match_scratch_bytes(N))) { rollback(); return e; }
     t->owned.push_back(m); t->d_match_scratch = m;
   }
 #undef DA

@@ -18,6 +18,10 @@
  *
  * There is no CPU fallback: every compute entry point launches CUDA kernels and fails with
  * SVOB200_ERR_CUDA if no device is usable.
+ *
+ * Threading: a context (and every tracker created on it) is used by ONE host thread at a time — it owns one stream, one staging
+ * arena, one error string.  Callers that share it across threads serialise their calls (the C++ drop-in does, behind its runtime
+ * lock); independent threads create independent contexts.
  */
 #ifndef SVOB200_H_
 #define SVOB200_H_
