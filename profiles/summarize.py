@@ -46,15 +46,17 @@ for r in rows[1:]:
     per.setdefault(short(r[ik]), []).append(v)
 # steady state: drop the first launch of each step kernel when there are several (cold start)
 mean = {k: (sum(v[1:]) / len(v[1:]) if len(v) > 2 else sum(v) / len(v)) for k, v in per.items()}
-step_total = sum(mean[k] for k in STEP_KERNELS if k in mean)
+# lk_refine_kernel runs twice per step (map features, then seeds): its mean counts twice in the step total and its share is of both
+PER_STEP = {"lk_refine_kernel": 2}
+step_total = sum(mean[k] * PER_STEP.get(k, 1) for k in STEP_KERNELS if k in mean)
 with open(os.path.join(HERE, tag + "_launches_summary.txt"), "w") as f:
     f.write("# %s ncu launch list (gpu__time_duration.sum, --clock-control none), command:\n" % tag)
     f.write("#   python bench.py --seqs %d --steps 2 --warmup 1 --no-latency --no-cpu-baseline --no-e2e --no-widen\n" % seqs)
-    f.write("# cold-cache, serialised launches: compare SHARES, not absolutes.  One tracker step = one launch of each kernel below.\n")
+    f.write("# cold-cache, serialised launches: compare SHARES, not absolutes.  One tracker step = one launch of each kernel below (lk_refine_kernel: two, share of both).\n")
     f.write("%-30s %6s %12s %s\n" % ("kernel", "n", "mean_us", "share_of_step"))
     for k in STEP_KERNELS:
         if k in mean:
-            f.write("%-30s %6d %12.1f %8.3f\n" % (k, len(per[k]), mean[k], mean[k] / step_total))
+            f.write("%-30s %6d %12.1f %8.3f\n" % (k, len(per[k]), mean[k], mean[k] * PER_STEP.get(k, 1) / step_total))
     f.write("# setup-only kernels (outside the timed region)\n")
     for k in per:
         if k not in STEP_KERNELS:
