@@ -151,6 +151,11 @@ __device__ __forceinline__ bool in_frame_level(const DevCam& c, int x, int y, in
   return x >= boundary && x < c.width / (1 << level) - boundary && y >= boundary && y < c.height / (1 << level) - boundary;
 }
 
+// 2^-L as a double, built from its bit pattern: x / (1 << L) == x * pow2_inv(L) bit for bit (a power-of-two scale is exact in
+// both forms), without the ~40-instruction FP64 division the compiler emits for a run-time divisor
+__device__ __forceinline__ double pow2_inv(int L) { return __longlong_as_double((long long)(1023 - L) << 52); }
+__device__ __forceinline__ float pow2_inv_f(int L) { return __int_as_float((127 - L) << 23); }
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float warp_sum_f(float v)
 {

@@ -139,3 +139,114 @@ __device__ inline void ldlt_solve_fixed(const double* Ain, const double* b, doub
 #pragma unroll
   for (int i = 0; i < N; ++i) x[i] = y[i];
 }
+
+// ---------------------------------------------------------------- the same solve, split into factor and substitution
+// ldlt_solve_fixed<N, true>(A, b, x) == ldlt_factor_rcp<N>(A, F); ldlt_subst_rcp<N>(F, b, x), bit for bit — for a caller
+// whose matrix stays the same over several right-hand sides (the inverse-compositional Hessian of the sparse alignment).
+//
+// Eigen's unblocked LDLT searches its pivot among the diagonal entries k .. N-1 BEFORE it updates any of them (only entry k
+// is updated, at step k, after the search): the pivot order is a selection sort of the ORIGINAL |diagonal| and does not
+// depend on the factorisation.  So the transpositions are worked out first, on an index word, and the factorisation runs on
+// the permuted matrix with compile-time indices — none of the predicated row / column swaps of the interleaved form.
+template <int N>
+struct LdltFactor {
+  double L[N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1];   // strictly lower triangle of the permuted matrix, row i at i(i-1)/2
+  double D[N];                                           // the pivots
+  double rcp[N];                                         // 1 / pivot (0 below the cut-off)
+  unsigned idx;                                          // nibble r = original index at permuted position r
+};
+
+// A: row-major N x N, SYMMETRIC (both triangles valid; any address space: only dynamic indexing is by the pivot order)
+template <int N>
+__device__ inline void ldlt_factor_rcp(const double* A, LdltFactor<N>* F)
+{
+  static_assert(N <= 8, "index word holds eight nibbles");
+  unsigned idx = 0x76543210u;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double big = fabs(A[((idx >> (4 * k)) & 15u) * (N + 1)]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) { const double v = fabs(A[((idx >> (4 * i)) & 15u) * (N + 1)]); if (v > big) { big = v; piv = i; } }
+    // swap nibbles k and piv
+    const unsigned a = (idx >> (4 * k)) & 15u, b = (idx >> (4 * piv)) & 15u, x = a ^ b;
+    idx ^= (x << (4 * k)) | (x << (4 * piv));           // piv == k: x = 0
+  }
+  double M[N][N];                                        // lower triangle of P A P^T
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    const unsigned ir = (idx >> (4 * r)) & 15u;
+#pragma unroll
+    for (int c = 0; c <= r; ++c) M[r][c] = A[ir * N + ((idx >> (4 * c)) & 15u)];
+  }
+  double rcp[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (k > 0) {
+      double temp[N];
+      double sdiag = 0;
+#pragma unroll
+      for (int j = 0; j < k; ++j) { temp[j] = M[j][j] * M[k][j]; sdiag += M[k][j] * temp[j]; }
+      M[k][k] -= sdiag;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < k; ++j) t += M[i][j] * temp[j];
+        M[i][k] -= t;
+      }
+    }
+    const double d = M[k][k];
+    if (fabs(d) > 2.2250738585072014e-308) {
+      const double r = 1.0 / d;
+      rcp[k] = r;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) { const double q0 = M[i][k] * r; M[i][k] = fma(fma(-d, q0, M[i][k]), r, q0); }
+    } else rcp[k] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) F->L[i * (i - 1) / 2 + j] = M[i][j];
+    F->D[i] = M[i][i];
+    F->rcp[i] = rcp[i];
+  }
+  F->idx = idx;
+}
+
+template <int N>
+__device__ inline void ldlt_subst_rcp(const LdltFactor<N>* F, const double* b, double* x)
+{
+  using namespace ldlt_detail;
+  const unsigned idx = F->idx;
+  double L[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) L[i][j] = F->L[i * (i - 1) / 2 + j];
+  double y[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = b[(idx >> (4 * i)) & 15u];
+#pragma unroll
+  for (int i = 1; i < N; ++i) {
+    double t[N];
+#pragma unroll
+    for (int j = 0; j < i; ++j) t[j] = L[i][j] * y[j];
+    y[i] -= halving_sum(t, i);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double d = F->D[i], r = F->rcp[i];
+    const double q0 = y[i] * r;
+    y[i] = (fabs(d) > 2.2250738585072014e-308) ? fma(fma(-d, q0, y[i]), r, q0) : 0.0;
+  }
+#pragma unroll
+  for (int i = N - 2; i >= 0; --i) {
+    double t[N];
+#pragma unroll
+    for (int j = 0; j < N - 1 - i; ++j) t[j] = L[i + 1 + j][i] * y[i + 1 + j];
+    y[i] -= packet2_sum(t, N - 1 - i);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[(idx >> (4 * i)) & 15u] = y[i];
+}

@@ -538,7 +538,7 @@ __device__ inline void epi_geometry(const DevCam& cam, const RefFtr& f, const do
   double pAx, pAy, pBx, pBy;
   world2cam_uv(cam, Ax, Ay, pAx, pAy);
   world2cam_uv(cam, Bx, By, pBx, pBy);
-  { const double dx = pAx - pBx, dy = pAy - pBy; g->epi_length = sqrt(dx * dx + dy * dy) / (1 << L); }
+  { const double dx = pAx - pBx, dy = pAy - pBy; g->epi_length = sqrt(dx * dx + dy * dy) * pow2_inv(L); }   // / (1 << L), exactly
   // warpAffine prologue (matcher.cpp:92-102)
   {
     const double det = A[0] * A[3] - A[2] * A[1];
@@ -546,7 +546,7 @@ __device__ inline void epi_geometry(const DevCam& cam, const RefFtr& f, const do
     g->a00 = (float)(A[3] * invdet); g->a01 = (float)(-A[1] * invdet);
     g->a10 = (float)(-A[2] * invdet); g->a11 = (float)(A[0] * invdet);
     g->warp_ok = isnan(g->a00) ? 0 : 1;
-    g->pr0 = (float)f.px[0] / (float)(1 << f.level); g->pr1 = (float)f.px[1] / (float)(1 << f.level);
+    g->pr0 = (float)f.px[0] * pow2_inv_f(f.level); g->pr1 = (float)f.px[1] * pow2_inv_f(f.level);   // / (float)(1 << level), exactly
   }
   {
     float dx = (float)(pAx - pBx), dy = (float)(pAy - pBy);
@@ -720,7 +720,7 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
     const double stx = task_double(tq, ST_STEPX, gbase, gmask), sty = task_double(tq, ST_STEPY, gbase, gmask);
     double uv = (sub & 1) ? by0 : bx0;
     const double st = (sub & 1) ? sty : stx;
-    const double inv_scale = 1.0 / (double)(1 << L);                     // exact: dividing by 2^L == multiplying by 2^-L
+    const double inv_scale = pow2_inv(L);                                 // exact: dividing by 2^L == multiplying by 2^-L
     short2 last = make_short2(0, 0);                                     // last_checked_pxi(0,0)
     for (int base = 0; base < n; base += EPI_GCHUNK) {
       const int m = min(EPI_GCHUNK, n - base);
@@ -790,7 +790,7 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
   }
   const int slot = slot_base + (JOB_BATCH - slots_left);
   --slots_left;
-  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), __uint_as_float(task_word(tq, ST_DIRX, gbase, gmask)),
+  emit_lk_job(&jobs[slot], S->pwb, (float)(px0 * pow2_inv(L)), (float)(px1 * pow2_inv(L)), __uint_as_float(task_word(tq, ST_DIRX, gbase, gmask)),
               __uint_as_float(task_word(tq, ST_DIRY, gbase, gmask)), item, cur_image, L | ((o.align_1d ? 1 : 0) << 8), sub);
 }
 
@@ -1218,7 +1218,7 @@ __global__ void __launch_bounds__(128) match_geom_kernel(DevCam cam, int n, cons
   const double invdet = 1.0 / det;
   g.a00 = (float)(g.A[3] * invdet); g.a01 = (float)(-g.A[1] * invdet); g.a10 = (float)(-g.A[2] * invdet); g.a11 = (float)(g.A[0] * invdet);
   if (!isnan(g.a00)) g.flags |= 2;
-  g.pr0 = (float)f.px[0] / (float)(1 << f.level); g.pr1 = (float)f.px[1] / (float)(1 << f.level);
+  g.pr0 = (float)f.px[0] * pow2_inv_f(f.level); g.pr1 = (float)f.px[1] * pow2_inv_f(f.level);   // / (float)(1 << level), exactly
   if (f.type == 1) {
     double dx = g.A[0] * f.grad[0] + g.A[1] * f.grad[1], dy = g.A[2] * f.grad[0] + g.A[3] * f.grad[1];
     { const double z = dx * dx + dy * dy; if (z > 0) { const double nn = sqrt(z); dx /= nn; dy /= nn; } }
@@ -1262,7 +1262,7 @@ __global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* fram
     for (int k = sub; k < 64; k += GL) R->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
   }
   const double px0 = px_in[2 * i], px1 = px_in[2 * i + 1];
-  emit_lk_job(&jobs[i], S->pwb, (float)(px0 / (1 << L)), (float)(px1 / (1 << L)), gp->dir0, gp->dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), sub);
+  emit_lk_job(&jobs[i], S->pwb, (float)(px0 * pow2_inv(L)), (float)(px1 * pow2_inv(L)), gp->dir0, gp->dir1, i, cur_image, L | ((type == 1 ? 1 : 0) << 8), sub);
 }
 
 // stand-alone align2D / align1D on caller-provided patches: thread per problem builds the job

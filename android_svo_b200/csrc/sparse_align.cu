@@ -30,6 +30,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+constexpr int JAB = 15;
+
 struct AlignArgs {
   DevFrame ref, cur;
   DevCam cam;
@@ -47,13 +49,14 @@ struct AlignArgs {
   float* gdx;         // 16 per feature: image gradient of the reference patch (zero when the feature is
   float* gdy;         //                 outside the level's border => zero Jacobian, :76)
   float* res[2];      // residuals of the last two evaluations (ping-pong), for the exact chi2 chain
-  double* jab;        // 12 per feature: a = J0*fl, b = J1*fl  (pixel Jacobian row = dx*a + dy*b)
+  double* jab;        // JAB per feature: a = J0*fl, b = J1*fl (pixel Jacobian row = dx*a + dy*b), then sum dx^2, sum dx*dy, sum dy^2 of the patch
   uint8_t* visible;   // sticky across levels (:67)
   uint8_t* contrib[2];
 };
 
-// The 6x6 solve is ldlt_solve_fixed<6> (ldlt.cuh): Eigen's pivoted LDL^T with the exact associations of its fixed-size
-// triangular solves, fully unrolled so the matrix lives in thread 0's registers.  (A warp-cooperative version with the
+// The 6x6 solve is ldlt_factor_rcp<6> + ldlt_subst_rcp<6> (ldlt.cuh): Eigen's pivoted LDL^T with the exact associations of its
+// fixed-size triangular solves, fully unrolled so the matrix lives in thread 0's registers; the factor stays in shared memory
+// and is re-used while the Hessian does not change (see the kernel).  (A warp-cooperative version with the
 // matrix in shared memory — five swap lanes, parallel column updates, the four libm calls of SE3::exp on four lanes — was
 // measured with tools/align_timing.py: 9.3 k cycles per solve against 6.2 k for this one; the shared-memory round trips and
 // warp barriers of a 6x6 problem cost more than the serial FP64 chain they replace.)
@@ -244,6 +247,9 @@ __device__ void exact_chi2_chain_parallel(const float* res, const uint8_t* visib
   __syncthreads();
 }
 
+#ifndef ALIGN_TIMING_PROBE
+#define ALIGN_TIMING_PROBE 7      // the worker thread whose sub-phase clocks the timing build reports (a feature visible at every level)
+#endif
 constexpr int NACC = 32;   // 21 (H upper) + 6 (J*res) + chi2 + n_meas + 3 pad
 // resident CTAs per SM of the 128-thread batch kernel: 4 (128 registers); 5 / 6 (96 / 80 registers, 1.5 / 2.5 KB of spills per
 // thread) measured 0.91 / 0.98 ms against 0.82 ms per 4,096 problems
@@ -265,6 +271,39 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NACC], int l
     }
   }
   return v[0];
+}
+
+// Entries 0..7 of an 8-entry accumulator: lane L of the warp ends with the warp-wide sum of v[L & 7], added in the SAME tree
+// as warp_transpose_reduce adds any one of its entries (partners 16, 8, 4, 2, 1 lanes away, in that order; IEEE addition is
+// commutative, so which partner "keeps" does not matter) — bit-identical to entries 21..28 of the 32-entry reduction.
+__device__ __forceinline__ double warp_transpose_reduce8(double (&v)[8], int lane)
+{
+#pragma unroll
+  for (int half = 16; half >= 8; half >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], half);
+  }
+#pragma unroll
+  for (int half = 4; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const double send = up ? v[j] : v[j + half];
+      const double keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+// entry h of the packed upper triangle (row-major, 21 entries) into both halves of the full 6x6 matrix
+__device__ __forceinline__ void store_h_entry(double* H, int h, double t)
+{
+  int r = 0, base = 0;
+  for (int len = 6; h >= base + len; base += len, --len) ++r;
+  const int c = r + (h - base);
+  H[r * 6 + c] = t;
+  H[c * 6 + r] = t;
 }
 
 // One CTA per alignment problem.  Every Gauss-Newton iteration is ONE data-parallel pass with a thread per feature:
@@ -289,6 +328,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   __shared__ double s_clu[CLUSTER > 1 ? CLUSTER : 1][NACC];   // rank 0 only: the partial sums of every CTA of the cluster
   __shared__ int s_ctrl;          // 0 continue iterating, 1 leave this level
   __shared__ double s_H[36], s_Jx[12];   // H_, Jres_, x_ of the last linearisation (copied to the result record once, at the end)
+  __shared__ LdltFactor<6> s_fac;        // the LDL^T factor of s_H (re-used while H_ stays the same)
   __shared__ int s_iters[SVOB200_MAX_LEVELS], s_nmeas;
   __shared__ int s_need;          // exact chi2 replay wanted: bit 0 this evaluation, bit 1 the previous one as well
   __shared__ float s_chain[2];
@@ -326,7 +366,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   float* ref_patch = A.ref_patch + 16 * (size_t)f0;
   float* gdx = A.gdx + 16 * (size_t)f0;
   float* gdy = A.gdy + 16 * (size_t)f0;
-  double* jab = A.jab + 12 * (size_t)f0;
+  double* jab = A.jab + JAB * (size_t)f0;
   const double focal_length = fabs(A.cam.fx);          // errorMultiplier2()
 
   // thread-0 solver state (NLLSSolver::reset nlls_solver_impl.hpp:299-309)
@@ -337,9 +377,14 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   int pp = 0;                                          // ping-pong index of the *current* evaluation
 #ifdef ALIGN_TIMING
   long long tA = 0, tB = 0, tC = 0, tD = 0, tP = 0, c0 = clock64(), cstart = c0;
+  long long tS[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s0 = 0;          // sub-phases of the pass as ONE worker thread sees them
 #define TICK(acc) do { const long long c1_ = clock64(); acc += c1_ - c0; c0 = c1_; } while (0)
+#define SUBTICK0() do { s0 = clock64(); } while (0)
+#define SUBTICK(k, dep) do { if ((dep) == 123456.789) s0 += 1; const long long c1_ = clock64(); tS[k] += c1_ - s0; s0 = c1_; } while (0)
 #else
 #define TICK(acc) do { } while (0)
+#define SUBTICK0() do { } while (0)
+#define SUBTICK(k, dep) do { } while (0)
 #endif
 
   for (int level = A.opts.max_level; level >= A.opts.min_level; --level) {
@@ -361,6 +406,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         if (!ok) {                                                    // jacobian_cache_.setZero() (:76)
 #pragma unroll
           for (int q = 0; q < 4; ++q) { gx4[q] = make_float4(0.f, 0.f, 0.f, 0.f); gy4[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          jab[JAB * (size_t)i + 12] = 0.0; jab[JAB * (size_t)i + 13] = 0.0; jab[JAB * (size_t)i + 14] = 0.0;   // the sums of a zero gradient
           continue;
         }
         visible[i] = 1;
@@ -369,7 +415,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
           const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
           const double z_inv = 1. / z, z_inv_2 = z_inv * z_inv;
           const double j02 = x * z_inv_2, j03 = y * j02, j12 = y * z_inv_2;
-          double* ja = jab + 12 * (size_t)i;
+          double* ja = jab + JAB * (size_t)i;
           ja[0] = -z_inv * fl; ja[1] = 0.0; ja[2] = j02 * fl; ja[3] = j03 * fl; ja[4] = -(1.0 + x * j02) * fl; ja[5] = y * z_inv * fl;
           ja[6] = 0.0; ja[7] = -z_inv * fl; ja[8] = j12 * fl; ja[9] = (1.0 + y * j12) * fl; ja[10] = -j03 * fl; ja[11] = -x * z_inv * fl;
         }
@@ -395,6 +441,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         // pixel (row r, column c) of the window, r and c compile-time after unrolling; window (3,3) is (v_i, u_i)
 #define WPX(r, c) byte_to_float((c) < 4 ? wlo[r] : whi[r], (c) & 3)
         float4* rp4 = reinterpret_cast<float4*>(ref_patch + 16 * (size_t)i);
+        double Sxx = 0, Sxy = 0, Syy = 0;      // the patch's share of J J^T in the (a, b) basis: constant over the level's iterations
 #pragma unroll
         for (int yy = 0; yy < 4; ++yy) {
           float pv[4], xv[4], yv[4];
@@ -407,11 +454,14 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
                              - (w_tl * WPX(r, c - 1) + w_tr * WPX(r, c) + w_bl * WPX(r + 1, c - 1) + w_br * WPX(r + 1, c)));
             yv[xx] = 0.5f * ((w_tl * WPX(r + 1, c) + w_tr * WPX(r + 1, c + 1) + w_bl * WPX(r + 2, c) + w_br * WPX(r + 2, c + 1))
                              - (w_tl * WPX(r - 1, c) + w_tr * WPX(r - 1, c + 1) + w_bl * WPX(r, c) + w_br * WPX(r, c + 1)));
+            const double X = (double)xv[xx], Y = (double)yv[xx];
+            Sxx += X * X; Sxy += X * Y; Syy += Y * Y;
           }
           rp4[yy] = make_float4(pv[0], pv[1], pv[2], pv[3]);
           gx4[yy] = make_float4(xv[0], xv[1], xv[2], xv[3]);
           gy4[yy] = make_float4(yv[0], yv[1], yv[2], yv[3]);
         }
+        jab[JAB * (size_t)i + 12] = Sxx; jab[JAB * (size_t)i + 13] = Sxy; jab[JAB * (size_t)i + 14] = Syy;
 #undef WPX
       }
     }
@@ -428,23 +478,33 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       // ---------------- one pass, thread per feature (sparse_img_align.cpp:219-266 + the normal equations):
       //   project with the current model (double) -> bounds test -> the 5x5 window of the current image that the 4x4
       //   patch's bilinear taps touch (two aligned words per row) -> 16 residuals (float, the reference's expression and
-      //   order per pixel) -> five patch sums -> 27 normal-equation entries.  Nothing but `res` / `contrib` (needed by the
-      //   exact chi2 replay) goes back to memory, and there is no barrier between projection, residuals and sums.
-      double acc[NACC];
+      //   order per pixel) -> J^T r.  Nothing but `res` / `contrib` (needed by the exact chi2 replay) goes back to memory.
+      // The alignment is inverse compositional: the Jacobian is taken at the reference patch, so a feature's 21 entries of
+      // J J^T — Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T with the patch sums of precomputeReferencePatches — are the SAME in
+      // every iteration of a level, and H_ changes only when the set of features inside the current image does (the reference
+      // re-adds the same numbers every iteration, sparse_img_align.cpp:253-262).  So an iteration whose set equals the previous
+      // one's (one block-wide vote) reduces 8 sums instead of 29, keeps H_, and the solve re-uses the LDL^T factor: only J^T r,
+      // chi2 and the substitution are new.  Bit-identical to recomputing: the sums run over the same features in the same tree.
+      double a8[8];                                    // J^T r (6), sum of res^2, pixel count
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      for (int k = 0; k < 8; ++k) a8[k] = 0.0;
+      bool flag = false;                               // an own feature entered or left the image since the last evaluation
       {
         double m[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) m[k] = s_model[k];
+        const uint8_t* was = A.contrib[pp ^ 1] + f0;
         for (int i = lo + tid; i < hi; i += BLOCK) {
+          SUBTICK0();
           if (!visible[i]) continue;
           const v3d pc = se3_transform(m, {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
           double pxd, pyd;
           world2cam(A.cam, pc, pxd, pyd);
+          SUBTICK(0, pxd + pyd);
           const float u_cur = (float)pxd * scale, v_cur = (float)pyd * scale;
           const int u_i = (int)floorf(u_cur), v_i = (int)floorf(v_cur);
           const bool in = !(u_i < 0 || v_i < 0 || u_i - 3 < 0 || v_i - 3 < 0 || u_i + 3 >= ccols || v_i + 3 >= crows);
+          if (iter > 0 && (was[i] != 0) != in) flag = true;
           contrib[i] = in ? 1 : 0;
           if (!in) continue;
           const float su = u_cur - u_i, sv = v_cur - v_i;
@@ -467,11 +527,12 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
               W[r][3] = byte_to_float(lo4, 3); W[r][4] = byte_to_float(b4, 0);
             }
           }
+          SUBTICK(1, (double)(W[0][0] + W[1][1] + W[2][2] + W[3][3] + W[4][4]));
           const float4* p4 = reinterpret_cast<const float4*>(ref_patch + 16 * (size_t)i);
           const float4* x4 = reinterpret_cast<const float4*>(gdx + 16 * (size_t)i);
           const float4* y4 = reinterpret_cast<const float4*>(gdy + 16 * (size_t)i);
           float4* r4 = reinterpret_cast<float4*>(res + 16 * (size_t)i);
-          double Sxx = 0, Sxy = 0, Syy = 0, Sxr = 0, Syr = 0, Srr = 0;
+          double Sxr = 0, Syr = 0, Srr = 0;
 #pragma unroll
           for (int yy = 0; yy < 4; ++yy) {
             const float4 rp = p4[yy], dx = x4[yy], dy = y4[yy];
@@ -482,48 +543,76 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
               const float intensity = w_tl * W[yy][xx] + w_tr * W[yy][xx + 1] + w_bl * W[yy + 1][xx] + w_br * W[yy + 1][xx + 1];
               rv[xx] = intensity - pv[xx];
               const double X = (double)xv[xx], Y = (double)yv[xx], Rr = (double)rv[xx];
-              Sxx += X * X; Sxy += X * Y; Syy += Y * Y; Sxr += X * Rr; Syr += Y * Rr;
+              Sxr += X * Rr; Syr += Y * Rr;
               Srr += (double)(rv[xx] * rv[xx] * 1.0f);          // the reference's float term res*res*weight
             }
             r4[yy] = make_float4(rv[0], rv[1], rv[2], rv[3]);
           }
-          const double* ja = jab + 12 * (size_t)i;
+          SUBTICK(2, Sxr + Syr + Srr);
+          const double* ja = jab + JAB * (size_t)i;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) a8[r] += Sxr * ja[r] + Syr * ja[6 + r];
+          a8[6] += Srr;
+          a8[7] += 16.0;
+          SUBTICK(3, a8[0] + a8[5]);
+        }
+      }
+      SUBTICK0();
+      // does this CTA's share of H_ have to be summed again?  (uniform over the CTA; iter is uniform over the cluster)
+      const bool full = iter == 0 || __syncthreads_or(flag ? 1 : 0) != 0;
+      SUBTICK(4, 0.0);
+      // ---------------- block reduction: lane L of a warp ends with the warp's sum of entry L
+      if (full) {
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+        for (int i = lo + tid; i < hi; i += BLOCK) {
+          if (!visible[i] || !contrib[i]) continue;     // contrib[i]: this thread's own store of a moment ago
+          const double* ja = jab + JAB * (size_t)i;
           double a[6], bb[6];
 #pragma unroll
           for (int k = 0; k < 6; ++k) { a[k] = ja[k]; bb[k] = ja[6 + k]; }
+          const double Sxx = ja[12], Sxy = ja[13], Syy = ja[14];
           int h = 0;
 #pragma unroll
           for (int r = 0; r < 6; ++r) {
 #pragma unroll
             for (int c = r; c < 6; ++c) acc[h++] += Sxx * (a[r] * a[c]) + Sxy * (a[r] * bb[c] + bb[r] * a[c]) + Syy * (bb[r] * bb[c]);
-            acc[21 + r] += Sxr * a[r] + Syr * bb[r];
           }
-          acc[27] += Srr;
-          acc[28] += 16.0;
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[21 + k] = a8[k];
+        const double mine = warp_transpose_reduce(acc, lane);
+        s_red[warp][lane] = mine;
+      } else {
+        const double mine = warp_transpose_reduce8(a8, lane);     // the same addition tree as entries 21..28 of the full one
+        if (lane < 8) s_red[warp][21 + lane] = mine;
       }
-      // ---------------- block reduction
-      const double mine = warp_transpose_reduce(acc, lane);
-      s_red[warp][lane] = mine;
+      SUBTICK(5, 0.0);
       __syncthreads();
-      if (warp == 0) {
+      SUBTICK(6, 0.0);
+      if (warp == 0 && (full || lane >= 21)) {
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) t += s_red[w][lane];
-        s_tot[lane] = t;
+        if (lane == 29) t = full ? 1.0 : 0.0;          // entry 29 (a pad of the sums): "H_ was summed again"
         if (CLUSTER > 1) cg::this_cluster().map_shared_rank(&s_clu[0][0], 0)[rank * NACC + lane] = t;
+        else { s_tot[lane] = t; if (lane < 21) store_h_entry(s_H, lane, t); }
       }
       if (CLUSTER > 1) {
         __threadfence();                               // residuals / flags of this slice: visible to rank 0's exact chi2 replay
         cg::this_cluster().sync();
         if (rank == 0 && warp == 0) {
+          // every rank's H_ share is still in its row of s_clu when that rank did not sum it again
           double t = s_clu[0][lane];
 #pragma unroll
           for (int r = 1; r < CLUSTER; ++r) t += s_clu[r][lane];
           s_tot[lane] = t;
+          if (lane < 21) store_h_entry(s_H, lane, t);
         }
       }
       __syncthreads();
+      SUBTICK(7, 0.0);
 
       TICK(tA);
       // ---------------- solve (thread 0 of rank 0), nlls_solver_impl.hpp:36-99
@@ -532,20 +621,14 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
       double new_chi2 = 0.0;
       bool new_exact = false;
       if (lead) {
-        double H[36], Jres[6];
-        int h = 0;
+        double Jres[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-#pragma unroll
-          for (int c = r; c < 6; ++c) { H[r * 6 + c] = s_tot[h]; H[c * 6 + r] = s_tot[h]; ++h; }
-          Jres[r] = -s_tot[21 + r];
-        }
+        for (int r = 0; r < 6; ++r) Jres[r] = -s_tot[21 + r];
         n_meas = (int)s_tot[28];
         new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
-        ldlt_solve_fixed<6, true>(H, Jres, xs);
+        if (s_tot[29] != 0.0) ldlt_factor_rcp<6>(s_H, &s_fac);     // H_ (warp 0 wrote it out) changed: factor it again
+        ldlt_subst_rcp<6>(&s_fac, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
-#pragma unroll
-        for (int k = 0; k < 36; ++k) s_H[k] = H[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { s_Jx[k] = Jres[k]; s_Jx[6 + k] = xs[k]; }
         s_nmeas = n_meas;
@@ -649,6 +732,10 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
     R->H[0] = (double)tP; R->H[1] = (double)tA; R->H[2] = (double)tB; R->H[3] = (double)tC; R->H[4] = (double)tD; R->H[5] = (double)(clock64() - cstart);
 #endif
   }
+#ifdef ALIGN_TIMING
+  __syncthreads();
+  if (rank == 0 && tid == ALIGN_TIMING_PROBE) for (int k = 0; k < 8; ++k) R->H[6 + k] = (double)tS[k];
+#endif
 }
 
 // diagnostics (svob200_debug_chi2_chain): the replays of the float chi2 chain over caller-supplied residuals, one CTA:
@@ -686,11 +773,11 @@ static int sparse_align_cluster_override()
   return v;
 }
 
-// per feature: 16 floats x (ref_patch, gdx, gdy, res0, res1) + 12 doubles (a, b) + 3 flag bytes
+// per feature: 16 floats x (ref_patch, gdx, gdy, res0, res1) + 15 doubles (a, b, patch gradient sums) + 3 flag bytes
 size_t sparse_align_scratch_bytes(int total_features)
 {
   const size_t n = (size_t)(total_features > 0 ? total_features : 1);
-  return n * (16 * sizeof(float) * 5 + 12 * sizeof(double) + 3) + 4096;
+  return n * (16 * sizeof(float) * 5 + JAB * sizeof(double) + 3) + 4096;
 }
 
 int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& cam, int batch, int total_features, int max_per_problem,
@@ -707,7 +794,7 @@ int launch_sparse_align(const DevFrame& ref, const DevFrame& cur, const DevCam& 
   char* p = static_cast<char*>(d_scratch);
   auto take = [&p](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
   const size_t fsz = T * 16 * sizeof(float);
-  A.jab = reinterpret_cast<double*>(take(T * 12 * sizeof(double)));
+  A.jab = reinterpret_cast<double*>(take(T * JAB * sizeof(double)));
   A.ref_patch = reinterpret_cast<float*>(take(fsz));
   A.gdx = reinterpret_cast<float*>(take(fsz));
   A.gdy = reinterpret_cast<float*>(take(fsz));

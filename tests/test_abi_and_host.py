@@ -79,3 +79,16 @@ def test_select_features_is_cell_ordered():
     assert list(px[:, 0]) == [10.0, 20.0, 40.0]       # strict >, first come first served in cell order
     with pytest.raises(ValueError):
         frontend.select_features(cells, 10.0, 5)
+
+
+def test_ldlt_split_bit_identical(tmp_path):
+    """ldlt.cuh built for the host: factor + substitution (what the sparse alignment re-uses across the iterations of a level,
+    sparse_img_align.cpp:253-262 / nlls_solver_impl.hpp:65) == the one-piece solve, bit for bit, on 50,000 systems."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "ldlt_split_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-I", os.path.join(here, "..", "android_svo_b200", "csrc"),
+                           "-o", exe, os.path.join(here, "ldlt_split_check.cpp"), "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "50000 systems, 0 mismatches" in out.stdout
