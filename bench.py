@@ -684,6 +684,21 @@ def widen_rows(ctx, capi, wl, cfg, peak, steps=5, warm=2):
         ctx.frame_create(902, B, w, h, cfg["n_levels"])
         ctx._ck(L.svob200_frame_upload(ctx.h, 902, V(wl.pool_dev[1]), w, None, capi.MEM_DEVICE))
         T_cur = np.ascontiguousarray(wl.poses[:, 2]); T_kf = np.ascontiguousarray(wl.poses[:, 0])
+        # ---- the pyramid kernel ALONE (device-memory bind of level 0 + one fused launch; in the step it shares the GPU with the
+        #      previous frame's depth-filter stream, so its stage time there is not its own)
+        lv = sum((w >> l) * (h >> l) for l in range(1, cfg["n_levels"]))
+        alg_p = B * (w * h + lv)
+        src = [wl.pool_dev[1], wl.pool_dev[2]]
+        cnt = [0]
+
+        def pyr_once():
+            cnt[0] += 1
+            ctx._ck(L.svob200_frame_bind(ctx.h, 902, V(src[cnt[0] & 1]), w, None))
+        ms = timed(pyr_once)
+        out["pyramid_alone"] = {"ms": round(ms, 4), "algorithmic_bytes": int(alg_p), "alg_GBps": round(alg_p / ms / 1e6, 1),
+                                "hbm_frac": round(alg_p / ms / 1e6 / peak, 4), "bound": "hbm",
+                                "note": "svob200_frame_bind (level 0 aliases the caller's device buffer, as in the tracker step), %d launches back to back, inputs alternate between two %d MB batches" % (steps, B * w * h >> 20)}
+        ctx._ck(L.svob200_frame_upload(ctx.h, 902, V(wl.pool_dev[1]), w, None, capi.MEM_DEVICE))
         # ---- YUV input stage: Y = the live frame, neutral chroma (NV21 layout: one interleaved VU plane)
         d_y = wl.pool_dev[2]
         d_vu = ctx.dev_alloc(B * (h // 2) * w + 16); frees.append(d_vu)
@@ -982,6 +997,8 @@ def main():
         if world == 1 and not args.no_widen:
             try:
                 out["next_rows"] = widen_rows(ctx, capi, wl, cfg, out["roofline"]["peak"])
+                if "pyramid_alone" in out["next_rows"]:
+                    out["roofline_pyramid"]["alone"] = out["next_rows"].pop("pyramid_alone")
                 if not args.no_cpu_baseline:
                     out["next_rows"]["cpu"] = widen_cpu(cfg)
             except Exception as e:   # pragma: no cover

@@ -60,6 +60,17 @@ def test_pyramid_bit_exact(ctx, oracle, shape, n_levels, mode):
         ctx.frame_release(fid)
 
 
+def test_pyramid_tma_kernel_bit_exact():
+    """The opt-in TMA-load pyramid kernel (SVOB200_PYRAMID_TMA=R, batches of 64+ frames; pyramid.cu) against the oracle, in a
+    process of its own because the library reads the knob once: frame sizes with partial tiles, 2 to 7 levels, both roundings."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SVOB200_PYRAMID_TMA="6")
+    out = subprocess.run([sys.executable, os.path.join(here, "tma_pyramid_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "TMA pyramid OK" in out.stdout
+
+
 def test_pyramid_odd_width_scalar_walk(ctx, oracle):
     """in.cols odd: the reference's scalar path drifts one pixel per row (vision.cpp:92-109); reproduced."""
     img = scenes.noise_image(30, 47, 5)
