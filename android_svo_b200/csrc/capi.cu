@@ -12,7 +12,11 @@ struct Stage {
   struct Item { const void* src; void* dst; size_t bytes, off; int kind; };   // kind 0 in, 1 inout, 2 out
   std::vector<Item> items;
   size_t total = 0, in_end = 0, io_begin = 0;
+  bool pushed = false, drained = false;
   Stage(svob200_ctx* c, int m) : ctx(c), mem(m) {}
+  // a call that fails between push() and download() must not leave its host->device copy in flight: the next call's upload()
+  // writes the same pinned staging buffer
+  ~Stage() { if (pushed && !drained) cudaStreamSynchronize(ctx->stream); }
   // returns an index; resolve() gives the device pointer
   int add(const void* src, void* dst, size_t bytes, int kind) { items.push_back({src, dst, bytes, 0, kind}); return (int)items.size() - 1; }
   int layout()
@@ -45,6 +49,7 @@ struct Stage {
   int push()
   {
     if (mem == SVOB200_MEM_DEVICE || in_end == 0) return 0;
+    pushed = true;
     CU(cudaMemcpyAsync(ctx->d_stage.p, ctx->h_stage, in_end, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
   }
@@ -54,6 +59,7 @@ struct Stage {
     if (total > io_begin)
       CU(cudaMemcpyAsync(ctx->h_stage + io_begin, static_cast<uint8_t*>(ctx->d_stage.p) + io_begin, total - io_begin, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    drained = true;
     for (auto& it : items) if (it.kind >= 1 && it.dst && it.bytes) memcpy(it.dst, ctx->h_stage + it.off, it.bytes);
     return 0;
   }

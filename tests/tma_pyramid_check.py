@@ -15,7 +15,7 @@ ctx = capi.Context(0)
 oracle = pyoracle.Oracle()
 checked = 0
 for (h, w, n_levels, b, modes) in ((480, 640, 4, 96, None), (480, 752, 5, 80, None), (1080, 1920, 5, 64, None), (480, 640, 4, 70, [0, 0, 0]),
-                                   (480, 640, 3, 65, [1, 0]), (66, 130, 4, 64, None), (64, 64, 7, 64, None), (480, 640, 2, 64, None)):
+                                   (480, 640, 3, 65, [1, 0]), (66, 144, 4, 64, None), (64, 64, 7, 64, None), (480, 640, 2, 64, None)):
     base = [scenes.noise_image(h, w, s, blur=(s % 2 == 0)) for s in range(4)]
     imgs = np.stack([base[i % 4] if i % 5 else np.roll(base[i % 4], i, axis=1) for i in range(b)])
     d = ctx.dev_alloc(imgs.nbytes)
