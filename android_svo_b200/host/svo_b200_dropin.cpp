@@ -740,22 +740,26 @@ void Reprojector::reprojectMap(FramePtr frame, std::vector<std::pair<FramePtr, s
 {
   resetGrid();
   // ---- which points (host, reprojector.cpp:78-119 and :125-131)
-  std::list<std::pair<FramePtr, double> > close_kfs;
-  map_.getCloseKeyframes(frame, close_kfs);
-  close_kfs.sort([](const std::pair<FramePtr, double>& l, const std::pair<FramePtr, double>& r) { return l.second < r.second; });
+  // nearest keyframes first, at most options_.max_n_kfs of them; a point seen from several of them is taken once (the stamp
+  // last_projected_kf_id_ carries this frame's id from the first time on)
+  typedef std::pair<FramePtr, double> KfDist;
+  std::list<KfDist> nearby;
+  map_.getCloseKeyframes(frame, nearby);
+  std::vector<KfDist> ranked(nearby.begin(), nearby.end());
+  std::stable_sort(ranked.begin(), ranked.end(), [](const KfDist& a, const KfDist& b) { return a.second < b.second; });
+  if (ranked.size() > options_.max_n_kfs) ranked.resize(options_.max_n_kfs);
   std::vector<Point*> pts;
   std::vector<int> owner;                       // index into overlap_kfs, -1 for point candidates
-  size_t n = 0;
   overlap_kfs.reserve(options_.max_n_kfs);
-  for (auto it_frame = close_kfs.begin(), ite_frame = close_kfs.end(); it_frame != ite_frame && n < options_.max_n_kfs; ++it_frame, ++n) {
-    FramePtr ref_frame = it_frame->first;
-    overlap_kfs.push_back(std::pair<FramePtr, size_t>(ref_frame, 0));
-    for (auto it_ftr = ref_frame->fts_.begin(), ite_ftr = ref_frame->fts_.end(); it_ftr != ite_ftr; ++it_ftr) {
-      if ((*it_ftr)->point == NULL) continue;
-      if ((*it_ftr)->point->last_projected_kf_id_ == frame->id_) continue;
-      (*it_ftr)->point->last_projected_kf_id_ = frame->id_;
-      pts.push_back((*it_ftr)->point);
-      owner.push_back((int)overlap_kfs.size() - 1);
+  for (const KfDist& kd : ranked) {
+    const int k = (int)overlap_kfs.size();
+    overlap_kfs.push_back(std::make_pair(kd.first, (std::size_t)0));
+    for (Feature* ftr : kd.first->fts_) {
+      Point* pt = ftr->point;
+      if (!pt || pt->last_projected_kf_id_ == frame->id_) continue;
+      pt->last_projected_kf_id_ = frame->id_;
+      pts.push_back(pt);
+      owner.push_back(k);
     }
   }
   std::unique_lock<std::mutex> cand_lock(map_.point_candidates_.mut_);
