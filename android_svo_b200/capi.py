@@ -42,7 +42,7 @@ class MatcherOpts(C.Structure):
 # numpy dtypes with C layout (align=True reproduces the struct padding)
 corner_dt = np.dtype([("x", "i4"), ("y", "i4"), ("level", "i4"), ("score", "f4")], align=True)
 align_result_dt = np.dtype([("T_cur_ref", "f8", 7), ("H", "f8", 36), ("Jres", "f8", 6), ("x", "f8", 6), ("chi2", "f8"),
-                            ("n_meas", "i4"), ("iters", "i4", MAX_LEVELS), ("stop", "i4"), ("n_exact_chi2", "i4")], align=True)
+                            ("n_meas", "i4"), ("iters", "i4", MAX_LEVELS), ("stop", "i4"), ("n_exact_chi2", "i4"), ("n_factorisations", "i4")], align=True)
 feature_ref_dt = np.dtype([("ref_frame_id", "i8"), ("ref_image", "i4"), ("cur_image", "i4"), ("level", "i4"), ("type", "i4"),
                            ("px", "f8", 2), ("f", "f8", 3), ("grad", "f8", 2), ("T_cur_ref", "f8", 7)], align=True)
 match_result_dt = np.dtype([("success", "i4"), ("search_level", "i4"), ("px_cur", "f8", 2), ("A_cur_ref", "f8", 4),

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
     for (int k = 0; k < 7; ++k) R->T_cur_ref[k] = A.T_init[7 * b + k];
     for (int k = 0; k < 36; ++k) { R->H[k] = 0; s_H[k] = 0; }
     for (int k = 0; k < 6; ++k) { R->Jres[k] = 0; R->x[k] = 0; s_Jx[k] = 0; s_Jx[6 + k] = 0; }
-    R->chi2 = 1e10; R->n_meas = 0; R->stop = 0; R->n_exact_chi2 = 0; s_nmeas = 0;
+    R->chi2 = 1e10; R->n_meas = 0; R->stop = 0; R->n_exact_chi2 = 0; R->n_factorisations = 0; s_nmeas = 0;
     for (int k = 0; k < SVOB200_MAX_LEVELS; ++k) { R->iters[k] = 0; s_iters[k] = 0; }
   }
   if (N <= 0) return;                                   // sparse_img_align.cpp:55-59 (uniform over the cluster)
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
   double chi2_ = 1e10;
   bool chi2_exact = true;
   bool stop_ = false;
-  int n_exact = 0;
+  int n_exact = 0, n_fac = 0;
   int pp = 0;                                          // ping-pong index of the *current* evaluation
 #ifdef ALIGN_TIMING
   long long tA = 0, tB = 0, tC = 0, tD = 0, tP = 0, c0 = clock64(), cstart = c0;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
         for (int r = 0; r < 6; ++r) Jres[r] = -s_tot[21 + r];
         n_meas = (int)s_tot[28];
         new_chi2 = (double)((float)s_tot[27] / (float)n_meas);
-        if (s_tot[29] != 0.0) ldlt_factor_rcp<6>(s_H, &s_fac);     // H_ (warp 0 wrote it out) changed: factor it again
+        if (s_tot[29] != 0.0) { ldlt_factor_rcp<6>(s_H, &s_fac); ++n_fac; }     // H_ (warp 0 wrote it out) changed: factor it again
         ldlt_subst_rcp<6>(&s_fac, Jres, xs);
         if (isnan(xs[0])) stop_ = true;
 #pragma unroll
@@ -720,6 +720,7 @@ __global__ void __launch_bounds__(BLOCK, CLUSTER > 1 ? 1 : (BLOCK == 128 ? ALIGN
     R->chi2 = chi2_;
     R->stop = stop_ ? 1 : 0;
     R->n_exact_chi2 = n_exact;
+    R->n_factorisations = n_fac;
     if (A.T_cur_w) {
       double Tm[7], out[7];
 #pragma unroll

@@ -125,6 +125,8 @@ typedef struct {
   int    iters[SVOB200_MAX_LEVELS];
   int    stop;
   int    n_exact_chi2;   /* iterations whose rollback decision needed the sequential float chi2 */
+  int    n_factorisations; /* iterations that summed H_ again and factorised it (the others re-used both: the set of features inside
+                              the current image was unchanged, and a feature's share of J J^T is constant over a level) */
 } svob200_align_result;
 /* One alignment problem per image of the batch.  ftr_offsets: batch+1 prefix offsets into the
  * per-feature arrays; px: 2 doubles (level-0 pixels); xyz_ref: 3 doubles (= f*depth,
@@ -256,7 +258,7 @@ int svob200_reproject_prepare(svob200_ctx* ctx, const svob200_camera* cam, int n
  * (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), restricted to the hot-path operators:
  *   pyramid(cur) -> SparseImgAlign::run(last, cur) -> Matcher::findMatchDirect for every map point of
  *   the keyframe -> DepthFilter::updateSeeds(cur) for the keyframe's seeds,
- * for a batch of independent sequences, 13 kernel launches, no host round trip.
+ * for a batch of independent sequences, 14 kernel launches (15 with the asynchronous depth filter), no host round trip.
  * Finished seeds (converged / NaN) are re-initialised when `reseed` is 1, which keeps the
  * per-frame workload stationary for benchmarking (0 = leave them, the caller mutates its list); with reseed = 2 EVERY seed is
  * re-initialised after every step: the "young seed" regime, where each update walks a long epipolar segment. */

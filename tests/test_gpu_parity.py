@@ -178,6 +178,60 @@ def test_sparse_align_cluster_paths(ctx, oracle, batch):
         ctx.frame_release(rid); ctx.frame_release(cid)
 
 
+@pytest.mark.parametrize("batch,N", [(4, 240), (80, 240), (300, 120)])
+def test_sparse_align_hessian_reuse_follows_the_feature_set(ctx, oracle, batch, N):
+    """An iteration re-uses H_ and its LDLT factor when the set of features inside the current image equals the previous
+    iteration's (sparse_align.cu; the reference re-adds the same J J^T every iteration, sparse_img_align.cpp:253-262) and sums /
+    factorises again when it does not.  Features are placed in the bands where the 3-px border test of the coarse levels flips as
+    the pose moves, so BOTH cases occur; iteration counts, n_meas, H_ and the pose must match the oracle on the cluster kernel
+    (batch 4), the 256-thread kernel (batch 80) and the 128-thread batch kernel (batch 300)."""
+    cfg, poses, imgs = scenes.scene("C2", n_frames=8, stride=2, amp=1.0)
+    nl = 5
+    w, h = cfg["w"], cfg["h"]
+    cam_o, cam_g = scenes.cam_of(cfg, Cam), scenes.cam_of(cfg, capi.Camera)
+    rng = np.random.RandomState(3)
+    probs = []
+    for (a, b) in ((0, 3), (1, 4), (2, 6), (0, 1)):
+        px = np.c_[rng.uniform(60, w - 60, N), rng.uniform(60, h - 60, N)]
+        k = N // 3
+        px[:2 * k, 0] = np.r_[rng.uniform(40, 58, k), rng.uniform(w - 58, w - 40, k)]
+        px[2 * k:2 * k + k // 2, 1] = rng.uniform(40, 58, k // 2)
+        has = np.ones(N, np.uint8)
+        ref_pos = oracle.se3_inverse(poses[a])[:3]
+        xyz = np.zeros((N, 3))
+        for i in range(N):
+            _, p = scenes.gt_depth(cfg, poses[a], px[i])
+            xyz[i] = oracle.cam2world(cam_o, px[i][0], px[i][1]) * np.sqrt(((p - ref_pos) ** 2).sum())
+        T_init = oracle.se3_mul(poses[a], oracle.se3_inverse(poses[a]))
+        n, res = oracle.sparse_align(oracle.pyramid(imgs[a], nl), oracle.pyramid(imgs[b], nl), cam_o, px.reshape(-1), xyz.reshape(-1), has, T_init, 4, 2)
+        probs.append(dict(a=a, b=b, px=px, has=has, xyz=xyz, T=T_init, n=n, res=res))
+    which = [i % 4 for i in range(batch)]
+    rid = upload(ctx, [imgs[probs[k]["a"]] for k in which], nl)
+    cid = upload(ctx, [imgs[probs[k]["b"]] for k in which], nl)
+    try:
+        offs = np.arange(batch + 1) * N
+        got = ctx.sparse_align(rid, cid, cam_g, offs, np.concatenate([probs[k]["px"] for k in which]), np.concatenate([probs[k]["xyz"] for k in which]),
+                               np.concatenate([probs[k]["has"] for k in which]), np.array([probs[k]["T"] for k in which]), 4, 2)
+        more, fewer = 0, 0
+        for i, k in enumerate(which):
+            g, res = got[i], probs[k]["res"]
+            assert g["n_meas"] == res.n_meas and list(g["iters"]) == list(res.iters) and g["stop"] == res.stop, (i, g["iters"], list(res.iters))
+            rot, trans = synth.pose_error(g["T_cur_ref"], np.array(res.T_cur_ref[:]))
+            assert rot < 1e-9 and trans < 1e-9, (rot, trans)
+            H = np.array(res.H[:])
+            assert np.abs(g["H"] - H).max() <= 1e-9 * np.abs(H).max()
+            levels_run, total = int((g["iters"] > 0).sum()), int(g["iters"].sum())
+            assert levels_run <= g["n_factorisations"] <= total, (g["n_factorisations"], g["iters"])
+            more += g["n_factorisations"] > levels_run
+            fewer += g["n_factorisations"] < total
+            if i >= 4:
+                assert g.tobytes() == got[i - 4].tobytes(), "replicas of one problem must agree bit for bit"
+        assert more > 0, "no iteration saw the feature set change: the test does not exercise the re-summation"
+        assert fewer > 0, "no iteration re-used H_: the test does not exercise the re-use"
+    finally:
+        ctx.frame_release(rid); ctx.frame_release(cid)
+
+
 @pytest.mark.parametrize("name,max_level,min_level", [("C2", 3, 2), ("C2", 4, 2), ("C3", 4, 2), ("C2", 2, 0)])
 def test_sparse_align_matches_oracle(ctx, oracle, name, max_level, min_level):
     cfg, poses, imgs = scenes.scene(name, n_frames=8, stride=2, amp=1.0)
