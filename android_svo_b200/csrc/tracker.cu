@@ -5,8 +5,8 @@
 // It chains the operators exactly the way FrameHandlerMono::processFrame + DepthFilter do
 // (frame_handler_mono.cpp:171-262, depth_filter.cpp:237-341), minus the host-only stages that are
 // out of scope (pose_optimizer, map management): everything between the operators that the
-// reference does in host code is done by the glue kernels, so a step is 11 launches on one stream
-// with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
+// reference does in host code is done by the glue kernels, so a step is 14 launches (15 when the depth
+// filter runs on its own stream and the step records are written in two halves) with no host round trip; in SVOB200_MEM_HOST mode it is bracketed by one H2D of the frame(s), one
 // H2D of the small per-step inputs and one D2H of the per-sequence results.
 #include <cstdlib>
 #include <atomic>
@@ -387,7 +387,7 @@ struct svob200_tracker {
   double *d_m_f = nullptr, *d_m_pos = nullptr, *d_pose_work = nullptr;
   uint8_t* d_outlier = nullptr;
   void* d_reproj_scratch = nullptr;
-  // single-stream latency: in device mode with small batches the 13 launches of a step are replayed as ONE CUDA graph
+  // single-stream latency: in device mode with small batches the 14 launches of a step are replayed as ONE CUDA graph
   // (captured once per distinct set of buffer addresses: a camera ring buffer has only a few), which removes the
   // per-launch driver cost and most of the inter-kernel gaps
   struct StepGraph { std::vector<uintptr_t> key; cudaGraphExec_t exec; long long launches; };

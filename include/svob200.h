@@ -328,7 +328,8 @@ int  svob200_tracker_set_chain(svob200_tracker* t, int cell_size, int max_fts, i
 int  svob200_tracker_step(svob200_tracker* t, const uint8_t* cur_imgs, int stride, const double* T_last_w,
                           const double* last_px, svob200_step_stats* stats, double* px_refined, int* match_ok, int mem);
 int  svob200_tracker_get_seeds(svob200_tracker* t, svob200_seed* out /*host*/);
-int  svob200_tracker_launches_per_step(void);
+int  svob200_tracker_launches_per_step(void);   /* kernels of a default-mode step on one stream: 14 (one more when the depth filter runs
+                                                   on its own stream and the step records are written in two halves) */
 /* diagnostics: the raw svob200_align_result records (one per sequence) of the most recent step, to host memory */
 int  svob200_tracker_debug_align(svob200_tracker* t, svob200_align_result* out);
 /* optional CUDA-event timing of the most recent step, one duration per stage (events recorded on the
