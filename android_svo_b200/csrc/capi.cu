@@ -113,6 +113,7 @@ void svob200_ctx_destroy(svob200_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   for (auto& a : ctx->aux) cudaEventDestroy(a.second);
   for (auto& kv : ctx->frames) if (kv.second.base) cudaFree(kv.second.base);
+  for (auto& sp : ctx->spare_frames) cudaFree(sp.second);
   if (ctx->d_table) cudaFree(ctx->d_table);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   ctx->d_stage.release(); ctx->d_scratch.release(); ctx->d_scratch2.release();
@@ -189,7 +190,10 @@ int svob200_frame_create(svob200_ctx* ctx, int64_t frame_id, int batch, int w, i
     lw /= 2; lh /= 2;
   }
   total += 256;   // slack so word-granular reads at the very end stay inside the allocation
-  if (cudaMalloc((void**)&r.base, total) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SVOB200_ERR_NOMEM, "frame_create: cudaMalloc(%zu) failed", total); }
+  for (size_t k = 0; k < ctx->spare_frames.size(); ++k)
+    if (ctx->spare_frames[k].first == total) { r.base = ctx->spare_frames[k].second; ctx->spare_frames.erase(ctx->spare_frames.begin() + k); break; }
+  if (!r.base && cudaMalloc((void**)&r.base, total) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SVOB200_ERR_NOMEM, "frame_create: cudaMalloc(%zu) failed", total); }
+  r.bytes = total;
   for (int l = 0; l < n_levels; ++l) r.f.lvl[l] = r.base + off[l];
   r.own_l0 = r.f.lvl[0]; r.own_pitch0 = r.f.pitch[0];
   r.slot = ctx->free_slots.back(); ctx->free_slots.pop_back();
@@ -274,8 +278,12 @@ int svob200_frame_release(svob200_ctx* ctx, int64_t frame_id)
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->frames.find(frame_id);
   if (it == ctx->frames.end()) return fail(ctx, SVOB200_ERR_NOFRAME, "frame %lld not found", (long long)frame_id);
+  if (int e = ctx_join_aux(ctx)) return e;
   CU(cudaStreamSynchronize(ctx->stream));
-  cudaFree(it->second.base);
+  // frames of up to 8 MB (single camera images with their pyramid) go to the spare list, at most kSpareFrames of them
+  constexpr size_t kSpareFrames = 8, kSpareBytes = 8u << 20;
+  if (it->second.bytes <= kSpareBytes && ctx->spare_frames.size() < kSpareFrames) ctx->spare_frames.push_back({it->second.bytes, it->second.base});
+  else cudaFree(it->second.base);
   ctx->free_slots.push_back(it->second.slot);
   ctx->frames.erase(it);
   return SVOB200_OK;

@@ -16,6 +16,7 @@ constexpr int kMaxFrames = 4096;
 struct FrameRec {
   DevFrame f;
   uint8_t* base = nullptr;       // owned allocation (all levels)
+  size_t bytes = 0;              // its size
   uint8_t* own_l0 = nullptr;     // owned level-0 storage (f.lvl[0] may alias caller memory after bind)
   int own_pitch0 = 0;
   int slot = -1;
@@ -43,6 +44,9 @@ struct svob200_ctx {
   long long launches = 0;
   std::unordered_map<int64_t, FrameRec> frames;
   std::vector<int> free_slots;
+  // allocations of released SMALL frames, kept for the next frame_create of the same size: a caller that mirrors one camera
+  // frame per step (the C++ drop-in) would otherwise pay a cudaMalloc and a cudaFree per frame (~0.1 ms, more than the kernels)
+  std::vector<std::pair<size_t, uint8_t*>> spare_frames;
   DevFrame* d_table = nullptr;
   // staging arenas (HOST mem mode)
   uint8_t* h_stage = nullptr; size_t h_cap = 0;

@@ -1400,8 +1400,8 @@ int launch_match_direct(const DevFrame* d_frames, int cur_slot, const DevCam& ca
 // persistent grid of the search kernel: SEARCH_CTAS CTAs of 4 warps (16 groups) per SM
 static int search_sms()
 {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  // (initialised once, thread-safely: two contexts may be driven from two threads)
+  static const int sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
   return sms;
 }
 // Grid of the search kernel = SEARCH_CTAS resident CTAs per SM times `waves`: 1 = persistent (every CTA lives for the whole kernel);
@@ -1410,8 +1410,7 @@ static int search_sms()
 constexpr int SEARCH_MAX_WAVES = 4;
 static int search_waves_override()
 {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SVOB200_SEARCH_WAVES"); v = e ? atoi(e) : 0; if (v < 0 || v > SEARCH_MAX_WAVES) v = 0; }
+  static const int v = [] { const char* e = getenv("SVOB200_SEARCH_WAVES"); const int w = e ? atoi(e) : 0; return (w < 0 || w > SEARCH_MAX_WAVES) ? 0 : w; }();
   return v;
 }
 static int search_grid(int n, int waves = 1)

@@ -410,8 +410,7 @@ static void launch_fused(const DevFrame& f, int mask, const YuvPlanes& yuv, cuda
 // of the previous frame and loses at every batch size but one.  So it stays opt-in.
 static int pyramid_tma_ctas()
 {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SVOB200_PYRAMID_TMA"); v = e ? atoi(e) : 0; if (v < 0 || v > 8) v = 0; }
+  static const int v = [] { const char* e = getenv("SVOB200_PYRAMID_TMA"); const int r = e ? atoi(e) : 0; return (r < 0 || r > 8) ? 0 : r; }();
   return v;
 }
 
@@ -419,14 +418,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled_fn()
 {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) return (EncodeTiledFn)p;
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
@@ -445,8 +442,7 @@ static bool launch_fused_tma(const DevFrame& f, int mask, cudaStream_t s)
   const cuuint32_t box[3] = {(cuuint32_t)TW, (cuuint32_t)TH, 1}, es[3] = {1, 1, 1};
   if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, f.lvl[0], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  static const int sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
   const int tiles_x = (f.w[0] + TW - 1) / TW, tiles_y = (f.h[0] + TH - 1) / TH;
   const long long total = (long long)tiles_x * tiles_y * f.batch;
   if (total >= (1ll << 30)) return false;

@@ -769,8 +769,7 @@ int launch_chi2_chain_test(int block, const float* d_res, const uint8_t* d_visib
 // SVOB200_ALIGN_CLUSTER=1|2|4|8 forces the cluster size (tests / A-B runs); unset or 0 = automatic
 static int sparse_align_cluster_override()
 {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SVOB200_ALIGN_CLUSTER"); v = e ? atoi(e) : 0; if (v != 1 && v != 2 && v != 4 && v != 8) v = 0; }
+  static const int v = [] { const char* e = getenv("SVOB200_ALIGN_CLUSTER"); const int c = e ? atoi(e) : 0; return (c == 1 || c == 2 || c == 4 || c == 8) ? c : 0; }();
   return v;
 }
 

@@ -63,11 +63,36 @@ struct Runtime {
   int64_t next_temp_id = (int64_t)1 << 40;
 };
 
-Runtime& rt()
+// Two runtimes, each with its own svob200 context (= its own CUDA stream, staging arenas, scratch and frame mirrors): [0] serves
+// the tracking thread's operators and, by default, the depth filter's updateSeeds too; with SVOB200_DROPIN_DF_CTX=1 updateSeeds —
+// which the reference runs on a thread of its own (DepthFilter::startThread, depth_filter.cpp:63-103) — gets runtime [1], and the
+// seed update of frame k and the alignment / reprojection of frame k+1 are in flight together on two streams instead of queueing
+// behind one lock (a context is single-threaded, svob200.h; two contexts are independent).  Measured on one 640x480 sequence
+// (bench.py --impl dropin --chain, ms per frame): two threads 0.80 with two contexts against 0.82 with one, ONE thread 0.70 against
+// 0.61 — a frame both sides use is created and mirrored twice, and 0.12 ms of seed work per frame is too little to hide that.  So
+// one context is the default; the second stream pays for batches, where the tracker's asynchronous depth filter provides it.
+constexpr int N_RUNTIMES = 2;
+thread_local int g_role = 0;
+
+Runtime& runtime(int k)
 {
-  static Runtime r;
-  return r;
+  static Runtime r[N_RUNTIMES];
+  return r[k];
 }
+Runtime& rt() { return runtime(g_role); }
+
+int depth_filter_role()
+{
+  static const int v = [] { const char* e = getenv("SVOB200_DROPIN_DF_CTX"); return (e && atoi(e) == 1) ? 1 : 0; }();
+  return v;
+}
+
+// everything the calling thread does through rt() until the scope ends goes to runtime `role`
+struct RoleScope {
+  int prev;
+  explicit RoleScope(int role) : prev(g_role) { g_role = role; }
+  ~RoleScope() { g_role = prev; }
+};
 
 [[noreturn]] void die(const char* what)
 {
@@ -130,6 +155,15 @@ void evict_locked(Runtime& r)
   }
 }
 
+// SVOB200_DROPIN_REBUILD_PYRAMID=0: mirror a Frame's pyramid level by level, exactly as the host holds it (five uploads, each with
+// its synchronisation: ~0.17 ms per VGA frame), for callers whose Frames carry pyramids that did not come from createImgPyramid.
+// Default: upload level 0 and rebuild the levels on the device (one upload + one kernel).
+bool rebuild_pyramids()
+{
+  static const bool v = [] { const char* e = getenv("SVOB200_DROPIN_REBUILD_PYRAMID"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+
 // Mirror a host pyramid on the device under `id`, level by level, exactly as the host holds it.
 void upload_pyramid_locked(svob200_ctx* ctx, int64_t id, const ImgPyr& pyr, int n_levels)
 {
@@ -161,7 +195,12 @@ int64_t ensure_frame_locked(const Frame& f)
     r.cache.erase(it);
   }
   check(svob200_frame_create(ctx, f.id_, 1, l0.cols, l0.rows, n_levels), "svob200_frame_create");
-  upload_pyramid_locked(ctx, f.id_, f.img_pyr_, n_levels);
+  if (rebuild_pyramids())
+    // ONE upload (level 0) and the fused pyramid kernel: the levels the host holds came out of createImgPyramid -> vk::halfSample,
+    // which in a process linked with this file is the same kernel with the same rounding rule — the mirror is bit-identical
+    check(svob200_frame_upload(ctx, f.id_, l0.data, step_of(l0), nullptr, SVOB200_MEM_HOST), "svob200_frame_upload");
+  else
+    upload_pyramid_locked(ctx, f.id_, f.img_pyr_, n_levels);
   r.cache[f.id_] = CacheEntry{l0.data, l0.cols, l0.rows, n_levels, ++r.clock};
   evict_locked(r);
   return f.id_;
@@ -206,12 +245,14 @@ svob200_ctx* context() { Lock lk(rt().mu); return ctx_locked(); }
 
 void releaseFrame(const Frame& frame)
 {
-  Runtime& r = rt();
-  Lock lk(r.mu);
-  auto it = r.cache.find(frame.id_);
-  if (it == r.cache.end() || !r.ctx) return;
-  svob200_frame_release(r.ctx, frame.id_);
-  r.cache.erase(it);
+  for (int k = 0; k < N_RUNTIMES; ++k) {
+    Runtime& r = runtime(k);
+    Lock lk(r.mu);
+    auto it = r.cache.find(frame.id_);
+    if (it == r.cache.end() || !r.ctx) continue;
+    svob200_frame_release(r.ctx, frame.id_);
+    r.cache.erase(it);
+  }
 }
 
 static int g_seed_chunk = 2048;
@@ -220,22 +261,31 @@ void setSeedChunk(int seeds_per_call) { g_seed_chunk = seeds_per_call < 64 ? 64 
 
 void setFrameCacheCapacity(size_t capacity)
 {
-  Runtime& r = rt();
-  Lock lk(r.mu);
-  r.capacity = capacity < 4 ? 4 : capacity;
-  if (r.ctx) evict_locked(r);
+  for (int k = 0; k < N_RUNTIMES; ++k) {
+    Runtime& r = runtime(k);
+    Lock lk(r.mu);
+    r.capacity = capacity < 4 ? 4 : capacity;
+    if (r.ctx) evict_locked(r);
+  }
 }
 
 void shutdown()
 {
-  Runtime& r = rt();
-  Lock lk(r.mu);
-  if (!r.ctx) return;
-  svob200_ctx_destroy(r.ctx);     // frees every resident frame
-  r.ctx = nullptr; r.cache.clear(); r.scratch.clear();
+  for (int k = 0; k < N_RUNTIMES; ++k) {
+    Runtime& r = runtime(k);
+    Lock lk(r.mu);
+    if (!r.ctx) continue;
+    svob200_ctx_destroy(r.ctx);     // frees every resident frame
+    r.ctx = nullptr; r.cache.clear(); r.scratch.clear();
+  }
 }
 
-long long launchCount() { Runtime& r = rt(); Lock lk(r.mu); return r.ctx ? svob200_ctx_launch_count(r.ctx) : 0; }
+long long launchCount()
+{
+  long long n = 0;
+  for (int k = 0; k < N_RUNTIMES; ++k) { Runtime& r = runtime(k); Lock lk(r.mu); if (r.ctx) n += svob200_ctx_launch_count(r.ctx); }
+  return n;
+}
 const int* lastAlignIterations() { return g_last_iters; }
 int lastAlignExactChi2() { return g_last_exact; }
 
@@ -630,6 +680,7 @@ void FastDetector::detect(Frame* frame, const ImgPyr& img_pyr, const double dete
 // two poses, so the sequential list walk is a batch: flatten -> three launches -> apply in list order.
 void B200DepthFilter::updateSeeds(FramePtr frame)
 {
+  svo::b200::RoleScope role(svo::b200::depth_filter_role());          // the depth filter's own context and stream
   lock_t lock(seeds_mut_);
   last_n_seeds_ = seeds_.size(); last_n_updates_ = 0; last_n_failed_matches_ = 0;
   if (seeds_updating_halt_) return;                                   // the reference polls the flag per seed (:253-254); a batch polls it once

@@ -50,8 +50,11 @@ protected:
 
 namespace b200 {
 
-/// The process-wide CUDA context behind the drop-in (created on first use; throws
-/// std::runtime_error when no usable CUDA device exists — there is no CPU fallback).
+/// The CUDA context behind the calling thread's role (created on first use; throws std::runtime_error when no usable CUDA
+/// device exists — there is no CPU fallback).  By default ONE svob200 context serves every operator; with SVOB200_DROPIN_DF_CTX=1
+/// B200DepthFilter::updateSeeds (the reference runs it on a thread of its own, depth_filter.cpp:63-103) gets a second context with
+/// its own stream, staging arenas and frame mirrors, so the two threads' GPU work overlaps instead of queueing behind one lock.
+/// Frame mirrors are made with one upload of level 0 and the pyramid kernel (SVOB200_DROPIN_REBUILD_PYRAMID=0: level by level).
 svob200_ctx* context();
 
 /// Device pyramids of host Frames are cached by Frame::id_ (the images are immutable after the Frame
@@ -60,7 +63,7 @@ svob200_ctx* context();
 void releaseFrame(const Frame& frame);
 void setFrameCacheCapacity(size_t capacity);
 /// B200DepthFilter::updateSeeds sends the seed list to the device in chunks of this many seeds (default 2,048) and polls
-/// seeds_updating_halt_ between chunks; the runtime lock is released between chunks so that the tracking thread's calls interleave.
+/// seeds_updating_halt_ between chunks (addKeyframe / removeKeyframe / reset return at the next chunk, like the reference at the next seed).
 int seedChunk();
 void setSeedChunk(int seeds_per_call);
 void shutdown();

@@ -246,6 +246,45 @@ def test_frontend_sequence(both, oracle):
         sr.close(); sd.close()
 
 
+@pytest.mark.gpu
+def test_frontend_sequence_two_threads(both, oracle):
+    """The reference's own two-thread layout over the drop-in (DepthFilter::startThread, depth_filter.cpp:63-103): the tracking
+    thread's operators and the depth-filter thread's updateSeeds drive TWO svob200 contexts (two streams) concurrently, nothing
+    is paced except the frame queue.  Tracking results are compared frame by frame, the seeds after the queue has drained,
+    against the reference TUs run sequentially (an update depends on its frame and the seed list only, so the order of the
+    two threads does not change it).  No re-seeding: converged seeds leave the list, as in the app."""
+    ref, d = both
+    cfg, poses, imgs, kf, last_px = make_sequence(oracle, "C2", 0x00C0FFEE + 9, 11)
+    cam = scenes.cam_of(cfg, Cam)
+    args = (cam, cfg["n_levels"], cfg["max_level"], cfg["min_level"], cfg["n_pyr"])
+    for r in (ref, d):
+        r.config(cfg["n_pyr"], cfg["max_level"], cfg["min_level"])
+    sr, sd = RefSeq(ref, *args, reseed=0), RefSeq(d, *args, reseed=0)
+    try:
+        sd.set_threaded()
+        for s in (sr, sd):
+            s.set_keyframe(imgs[0], poses[0], kf["kf_px"], kf["kf_level"], kf["pt_world"], kf["seed_px"], kf["seed_level"])
+            s.set_last(imgs[0])
+        for k in range(1, 11):
+            a, pxa, oka = sr.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            b, pxb, okb = sd.step(imgs[k], poses[k - 1], last_px[k - 1], want_px=True)
+            assert a.n_tracked == b.n_tracked and a.align_iters == b.align_iters
+            rot, trans = synth.pose_error(np.array(a.T_cur_w[:]), np.array(b.T_cur_w[:]))
+            assert rot < 1e-9 and trans < 1e-9
+            assert a.n_matched == b.n_matched and np.array_equal(oka, okb)
+            assert np.abs(pxa - pxb).max() <= 1e-3
+        sd.drain()
+        xa, xb = sr.seeds(), sd.seeds()
+        assert np.array_equal(xa[:, 0] < 0, xb[:, 0] < 0), "different seeds finished"
+        assert (xa[:, 0] < 0).sum() > 50, "the sequence should converge a good part of its seeds"
+        outside = ~np.isclose(xa, xb, rtol=1e-5, atol=0).all(axis=1)
+        assert np.allclose(xa, xb, rtol=2e-2, atol=0)
+        print("two-thread drop-in sequence: %d of %d seeds outside 1e-5 after 10 frames" % (int(outside.sum()), len(xa)))
+        assert outside.sum() <= 0.01 * len(xa)
+    finally:
+        sr.close(); sd.close()
+
+
 # ---------------------------------------------------------------- callers either side of the hot path (SURVEY §8f)
 @pytest.fixture(scope="module")
 def both_map(both):
