@@ -597,24 +597,33 @@ __device__ __forceinline__ unsigned ldg_u8_raw(const uint8_t* p)
   return v;
 }
 
+// (x - 5, y - 5) of tap i of the row-major 10x10 patch, as floats, in shared memory: one LDS.64 per tap instead of a running
+// position with its wrap test.  104 entries: the idle lanes of the tail round read 100..103.
+constexpr int TAP_TABLE = 104;
+__device__ __forceinline__ void fill_tap_table(float2* s_tap)
+{
+  for (int i = threadIdx.x; i < TAP_TABLE; i += blockDim.x) s_tap[i] = make_float2((float)(i % 10 - 5), (float)(i / 10 - 5));
+}
+
+// a00 .. a11 arrive multiplied by 2^L (exact), so (a00 * 2^L) * (x - 5) is the same float as the reference's a00 * ((x - 5) * 2^L).
 template <int R, bool TAIL>
-__device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, unsigned rp, float xmax, float ymax, float a00, float a01, float a10, float a11,
-                                                float pr0, float pr1, float sc, uint8_t* s_pwb, int i0, float& p0, float& p1)
+__device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, unsigned rp, unsigned xmax, unsigned ymax, float a00, float a01, float a10, float a11,
+                                                float pr0, float pr1, uint8_t* s_pwb, int i0, const float2* tap)
 {
   bool inb[R];
   float w00[R], w01[R], w10[R], w11[R];
   unsigned v00[R], v01[R], v10[R], v11[R];
-  const float step = 8.0f * sc, lim = 5.0f * sc, wrap = 10.0f * sc;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const float qx = (a00 * p0 + a01 * p1) + pr0;
-    const float qy = (a10 * p0 + a11 * p1) + pr1;
-    p0 += step; if (p0 >= lim) { p0 -= wrap; p1 += sc; }
-    inb[r] = !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    const float2 t = tap[GL * r];
+    const float qx = (a00 * t.x + a01 * t.y) + pr0;
+    const float qy = (a10 * t.x + a11 * t.y) + pr1;
+    // the reference's test !(qx < 0 || qy < 0 || qx >= cols - 1 || qy >= rows - 1) on the floored coordinates: for q >= 0
+    // floor(q) < n <=> q < n (n an integer), a negative q floors below zero = a huge unsigned, NaN converts to 0 and passes,
+    // as it passes the float comparisons.  vk::interpolateMat_8u (vision.h:19-36) floors too.
+    const int ix = __float2int_rd(qx), iy = __float2int_rd(qy);
+    inb[r] = (unsigned)ix < xmax && (unsigned)iy < ymax;
     if (TAIL) inb[r] = inb[r] && (i0 + GL * r < 100);
-    // vk::interpolateMat_8u (vision.h:19-36); floorf == truncation for the non-negative coordinates of an in-bounds tap
-    // (out-of-bounds taps produce 0 whatever ix, iy are)
-    const int ix = (int)qx, iy = (int)qy;
     const float sx = qx - ix, sy = qy - iy;
     w00[r] = (1.0f - sx) * (1.0f - sy);
     w01[r] = (1.0f - sx) * sy;
@@ -634,12 +643,11 @@ __device__ __forceinline__ void warp_patch_taps(const uint8_t* rimg, unsigned rp
 
 template <bool PREFETCH>
 __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, int rc, int rr, float a00, float a01, float a10, float a11,
-                                                 float pr0, float pr1, int L, uint8_t* s_pwb, int sub)
+                                                 float pr0, float pr1, int L, uint8_t* s_pwb, int sub, const float2* s_tap)
 {
   // 100 taps over 8 lanes = 12 full rounds + 4 taps: three passes of four rounds (the 16 pixel loads of a lane in flight
   // together) and ONE tail round, not a fourth pass whose last three rounds would be all-idle instructions
   const float sc = (float)(1 << L);
-  const float xmax = (float)(rc - 1), ymax = (float)(rr - 1);
   // ptxas interleaves tap r's conversions (which wait for its pixels) with tap r+1's address arithmetic, so the ~11 image
   // rows of the window are 11 exposed cache misses in a row; PREFETCH touches both ends of every patch row up front (two
   // image rows each; lane `sub` takes patch row `sub`, lanes 0..3 also the ends of rows 8 and 9).  Measured per 4,096
@@ -647,22 +655,25 @@ __device__ __forceinline__ void warp_patch_10x10(const uint8_t* rimg, int rp, in
   // other resident warps already cover them, 1.69 -> 1.77 ms — so only the former prefetches.
 #pragma unroll
   for (int t = 0; PREFETCH && t < 3; ++t) {
+    const float xmaxf = (float)(rc - 1), ymaxf = (float)(rr - 1);
     const int tx = t == 0 ? 0 : (t == 1 ? 9 : ((sub & 1) ? 9 : 0));
     const int ty = t < 2 ? sub : 8 + (sub >> 1);
     const float q0 = (float)(tx - 5) * sc, q1 = (float)(ty - 5) * sc;
     const float qx = (a00 * q0 + a01 * q1) + pr0, qy = (a10 * q0 + a11 * q1) + pr1;
-    const bool ok = (t < 2 || sub < 4) && !(qx < 0 || qy < 0 || qx >= xmax || qy >= ymax);
+    const bool ok = (t < 2 || sub < 4) && !(qx < 0 || qy < 0 || qx >= xmaxf || qy >= ymaxf);
     if (ok) {
       const uint8_t* p = rimg + ((unsigned)(int)qy * (unsigned)rp + (unsigned)(int)qx);
       asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
       asm volatile("prefetch.global.L1 [%0];" :: "l"(p + rp));
     }
   }
-  float p0 = (float)(sub - 5) * sc, p1 = -5.0f * sc;
+  const unsigned xmax = rc > 1 ? (unsigned)(rc - 1) : 0u, ymax = rr > 1 ? (unsigned)(rr - 1) : 0u;
+  const float b00 = a00 * sc, b01 = a01 * sc, b10 = a10 * sc, b11 = a11 * sc;      // exact: sc is a power of two
+  const float2* tap = s_tap + sub;
 #pragma unroll 1
   for (int r0 = 0; r0 < 12; r0 += 4)
-    warp_patch_taps<4, false>(rimg, (unsigned)rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * r0, p0, p1);
-  warp_patch_taps<1, true>(rimg, (unsigned)rp, xmax, ymax, a00, a01, a10, a11, pr0, pr1, sc, s_pwb, sub + GL * 12, p0, p1);
+    warp_patch_taps<4, false>(rimg, (unsigned)rp, xmax, ymax, b00, b01, b10, b11, pr0, pr1, s_pwb, sub + GL * r0, tap + GL * r0);
+  warp_patch_taps<1, true>(rimg, (unsigned)rp, xmax, ymax, b00, b01, b10, b11, pr0, pr1, s_pwb, sub + GL * 12, tap + GL * 12);
 }
 
 constexpr int JOB_BATCH = 8;             // LK job slots a group reserves per atomicAdd
@@ -673,7 +684,7 @@ constexpr int JOB_BATCH = 8;             // LK job slots a group reserves per at
 __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_slot, const DevCam& cam, const svob200_matcher_opts& o,
                                                 const uint4& tq, int item, EpiGroupSmem* S, int sub, int gbase, unsigned gmask,
                                                 LkJob* jobs, int* job_count, int& slot_base, int& slots_left, EpiSearch* search,
-                                                SeedMatch* seed_match, svob200_epi_result* api_results)
+                                                SeedMatch* seed_match, svob200_epi_result* api_results, const float2* s_tap)
 {
   const int flags = (int)task_word(tq, ST_FLAGS, gbase, gmask);
   const int mode = (flags >> ST_MODE_SHIFT) & 3;
@@ -689,7 +700,7 @@ __device__ __forceinline__ void epi_search_item(const DevFrame* frames, int cur_
     warp_patch_10x10<false>(rimg, ref.pitch[ref_level], ref.w[ref_level], ref.h[ref_level],
                      __uint_as_float(task_word(tq, ST_A00, gbase, gmask)), __uint_as_float(task_word(tq, ST_A01, gbase, gmask)),
                      __uint_as_float(task_word(tq, ST_A10, gbase, gmask)), __uint_as_float(task_word(tq, ST_A11, gbase, gmask)),
-                     __uint_as_float(task_word(tq, ST_PR0, gbase, gmask)), __uint_as_float(task_word(tq, ST_PR1, gbase, gmask)), L, S->pwb, sub);
+                     __uint_as_float(task_word(tq, ST_PR0, gbase, gmask)), __uint_as_float(task_word(tq, ST_PR1, gbase, gmask)), L, S->pwb, sub, s_tap);
   }
   __syncwarp(gmask);
   for (int k = sub; k < 64; k += GL) S->patch[k] = S->pwb[((k >> 3) + 1) * 10 + 1 + (k & 7)];
@@ -1068,6 +1079,9 @@ __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevF
                                                             int* job_count, svob200_epi_result* api_results)
 {
   __shared__ EpiGroupSmem SM[4 * GPW];
+  __shared__ float2 s_tap[TAP_TABLE];
+  fill_tap_table(s_tap);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (GL - 1), grp = lane / GL, gbase = grp * GL;
   const unsigned gmask = ((1u << GL) - 1u) << gbase;
@@ -1082,7 +1096,7 @@ __global__ void __launch_bounds__(128, SEARCH_CTAS) epi_search_kernel(const DevF
     const uint4 tq = next;
     if (i + stride < n) next = __ldg(reinterpret_cast<const uint4*>(&tasks[i + stride]) + sub);
     if (!(task_word(tq, ST_FLAGS, gbase, gmask) & ST_ACTIVE)) continue;
-    epi_search_item(frames, cur_slot, cam, o, tq, i, S, sub, gbase, gmask, jobs, job_count, slot_base, slots_left, search, seed_match, api_results);
+    epi_search_item(frames, cur_slot, cam, o, tq, i, S, sub, gbase, gmask, jobs, job_count, slot_base, slots_left, search, seed_match, api_results, s_tap);
     __syncwarp(gmask);
   }
   // reserved but unused job slots become empty jobs
@@ -1237,6 +1251,9 @@ __global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* fram
                                                             svob200_match_result* results)
 {
   __shared__ MatchSmem SM[4 * GPW];
+  __shared__ float2 s_tap[TAP_TABLE];
+  fill_tap_table(s_tap);
+  __syncthreads();                                       // (before any thread leaves)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (GL - 1), grp = lane / GL;
   const unsigned gmask = ((1u << GL) - 1u) << (grp * GL);
@@ -1253,7 +1270,7 @@ __global__ void __launch_bounds__(128) match_prepare_kernel(const DevFrame* fram
   if (flags & 2) {
     const DevFrame& ref = frames[(int)fp->ref_frame_id];
     const uint8_t* rimg = ref.lvl[level] + (size_t)ref_image * ref.img_stride[level];
-    warp_patch_10x10<true>(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, sub);
+    warp_patch_10x10<true>(rimg, ref.pitch[level], ref.w[level], ref.h[level], gp->a00, gp->a01, gp->a10, gp->a11, gp->pr0, gp->pr1, L, S->pwb, sub, s_tap);
   }
   __syncwarp(gmask);
   if (results) {
