@@ -8,19 +8,18 @@
 // depthFromTriangulation (matcher.cpp:123-136), DepthFilter::updateSeeds loop body, updateSeed,
 // computeTau (depth_filter.cpp:250-416).
 //
-// B200 design: one thread-block per seed (epipolar search / seed update) and one warp per
-// reprojection candidate (findMatchDirect).  The 10x10 affine-warped reference patch is produced
-// once into shared memory (100 lanes, one bilinear tap set each); the epipolar walk is evaluated
-// thread-per-candidate with the 8x8 reference patch held in 16 registers and ZMSSD computed with
-// byte dot products (dp4a) on funnel-shifted aligned words; the strict-minimum "first wins" rule
-// is a 64-bit min over (score << 32 | step index).
+// B200 design (deviates from north_star's "block per seed, warp per patch batch"): GROUPS OF 8 LANES — four
+// seeds or four reprojection candidates per warp in lockstep — warp the 10x10 patch into shared memory (13 rounds of 8 taps) and
+// walk the epipolar segment (one sample per lane, the 8x8 reference patch in 16 registers, ZMSSD by dp4a on funnel-shifted
+// aligned words, the strict-minimum "first wins" rule as a 64-bit min over (score << 32 | step index)); the Lucas-Kanade
+// refinement runs THREAD PER PROBLEM on 128-byte job records the groups emit; geometry before and the seed update after are
+// thread per seed in double precision.  The search kernel is persistent (SEARCH_CTAS resident CTAs per SM).
 //
-// Parity: the warp, ZMSSD and the LK iterations are bit-identical to the reference.  The LK sums
-// (H, Jres) are float accumulations whose order matters, so they are NOT tree-reduced: lanes
-// compute the 64 per-pixel terms in parallel and 3-5 lanes each replay one sequential chain (a
-// 64-long dependent FADD chain is ~256 cycles — cheaper than it sounds, and exact).  The epipolar
-// sample positions come from the reference's running sum `uv += step`, replayed by two threads
-// (x and y are independent chains).  Only libm calls (acos/sin/atan/exp) are tolerance-matched.
+// Parity: the warp, ZMSSD and the LK iterations are bit-identical to the reference.  The LK sums (H, Jres) are float
+// accumulations whose order matters, so they are NOT tree-reduced: each thread replays the reference's sequential loop over its
+// own problem.  The epipolar sample positions come from the reference's running sum `uv += step`, replayed by two lanes of the
+// group (x and y are independent chains).  Only libm calls (acos/sin/atan/exp) are tolerance-matched — and fed the same pose they
+// reproduce the oracle's seeds bit for bit.
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
