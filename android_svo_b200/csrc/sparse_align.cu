@@ -6,20 +6,20 @@
 //
 // B200 design: the whole run() — every pyramid level, every Gauss-Newton iteration, the 6x6
 // solve, the SE3 update and the solver's convergence / rollback logic — is ONE kernel launch with
-// one CTA per alignment problem (= per sequence of a batch).  A GN iteration is a dependency
-// chain, not a bandwidth problem, so the design minimises round trips: the model lives in shared
-// memory; each iteration is three data-parallel phases (thread per feature: projection; thread per
-// pixel: bilinear residual; thread per feature: normal equations from five patch sums, exploiting
-// that the 16 Jacobian rows of a patch are dx*a + dy*b with the same a, b), the 21 + 6 + 2 sums are
-// reduced with a 31-shuffle transposing butterfly per warp and one shared-memory pass, and thread 0
-// runs the register-resident pivoted LDL^T and the decision logic.
+// one CTA (or, for a handful of sequences, one thread-block cluster) per alignment problem.  A GN iteration is a
+// dependency chain, not a bandwidth problem, so the design minimises round trips: the model lives in shared memory; each
+// iteration is ONE thread-per-feature pass (projection, the 5x5 window under the patch from ten aligned word loads, 16
+// bilinear residuals, J^T r from two patch sums — the 16 Jacobian rows of a patch are dx*a + dy*b with the same a, b), a
+// transposing shuffle reduction per warp and one shared-memory pass, and thread 0 solves and decides.  The Hessian is a
+// constant of the level as long as the same features contribute (inverse compositional): it is summed and factorised again
+// only when a block-wide vote says the set changed; the other iterations reduce 8 sums and do a substitution.
 //
 // Parity: per-residual arithmetic (bilinear weights with their double promotions, unfused float
 // sums, Jacobian rows) is bit-identical to the reference.  H/Jres are summed in double in a
 // different order (tolerance-matched).  The rollback test `new_chi2 > chi2_` hangs on a float sum
 // accumulated sequentially in the reference; it is decided here on the double sum unless the two
-// values are closer than the worst-case rounding error of the float chain, in which case thread 0
-// replays the exact sequential float chain (counted in n_exact_chi2).
+// values are closer than the worst-case rounding error of the float chain, in which case the CTA
+// replays the exact sequential float chain in parallel (counted in n_exact_chi2).
 #include <cooperative_groups.h>
 #include <cstdlib>
 #include "common.cuh"
