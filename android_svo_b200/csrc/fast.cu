@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(NT, 3) fast_kernel(FastArgs A)
   __shared__ __align__(16) uint32_t s_scw[SH * SG];       // score tile, one word per group
   __shared__ unsigned short s_kp[TH * TW];                // keypoints: score-tile index
   __shared__ int s_n;
-  const uint8_t* s_sc = reinterpret_cast<const uint8_t*>(s_scw);
   const bool raw = A.raw_scores != nullptr;
   int level = 0;
   if (raw) level = A.raw_level;
@@ -323,7 +322,6 @@ __global__ void __launch_bounds__(NT, 3) fast_kernel(FastArgs A)
     const unsigned long long key = ((unsigned long long)ordered_bits(score) << 32) | (unsigned long long)(~order);
     atomicMax(&A.keys[(size_t)b * A.n_cells + k], key);
   }
-  (void)s_sc;
 }
 
 __global__ void fast_init_keys_kernel(unsigned long long* keys, int n, float thr_f)

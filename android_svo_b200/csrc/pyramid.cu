@@ -130,7 +130,7 @@ __device__ __forceinline__ void tile_level(const uint8_t* src, uint8_t* dst, int
 {
   constexpr int DW = SW_ / 2, DH = SH_ / 2;
   if (DW >= 4) {
-    constexpr int WPR = DW / 4;                          // words per output row of the tile
+    constexpr int WPR = DW >= 4 ? DW / 4 : 1;            // words per output row of the tile (the branch is dead for narrower tiles)
     for (int i = t; i < DH * WPR; i += NT_) {
       const int ly = i / WPR, lw = i - ly * WPR;
       const uint2 top = *reinterpret_cast<const uint2*>(src + (2 * ly) * SW_ + 8 * lw);
